@@ -1,0 +1,166 @@
+/*
+ * quan_sm100.h — C ABI of libquan_sm100.so: the B200 (sm_100a) implementation of QUAN's
+ * quaternion layer stack (QConv2D separable Hamilton convolution, IQBN, QUpsample, Poincare map).
+ *
+ * This is the drop-in boundary for the hot path named in BASELINE.json.north_star / SURVEY.md §8.
+ * Every entry point cites the reference interface it replaces (paths relative to the reference
+ * repository root, bryceag11/QUAN_ultralytics).
+ *
+ * Conventions
+ *   - Plain C: raw device pointers, sizes, enums.  No torch / ATen types.
+ *   - The CALLER allocates every output and the workspace (SURVEY §8(b) "Ownership"); kernels never
+ *     allocate device memory.  All launches go to the `stream` argument (a cudaStream_t passed as void*).
+ *   - Return value: 0 = ok, <0 = argument/shape error (QUAN_E_*), >0 = a cudaError_t raised by the launch.
+ *     `quan_last_error()` returns a thread-local human-readable message for the last non-zero return.
+ *   - Logical activation shape is always the reference's BCHWQ = [B, C, H, W, 4] with C counted in
+ *     QUATERNION channels (ultralytics/nn/modules/conv.py:118-126).  Two physical layouts are accepted:
+ *       QUAN_LAYOUT_BCHWQ (0): contiguous [B][C][H][W][4]       — the reference's layout (conv.py:441).
+ *       QUAN_LAYOUT_BHWQC (1): contiguous [B][H][W][4][C]       — torch.channels_last_3d of the same logical
+ *                              tensor; the tensor-core (TMA/tcgen05) kernels require this one.
+ *   - dtype: QUAN_F32 (fp32 storage, TF32 tensor-core math, fp32 accumulate) or QUAN_BF16 (bf16 storage,
+ *     fp32 accumulate).  Parameters/statistics (gamma, beta, mean, var, bias, master weights, weight grads)
+ *     are always fp32.
+ *   - mix[16]: the 4x4 mixing matrix M, row-major, out_p = sum_q mix[4*p+q] * S_q.  The reference has two:
+ *       M_A  ultralytics/nn/modules/conv.py:493-496  {+1,-1,-1,-1, -1,+1,+1,-1, -1,-1,+1,+1, -1,+1,-1,+1}
+ *       M_B  classification/quaternion/qconv.py:606-609 and ultralytics/nn/cuda/quaternion_ops.cu:152-155
+ *            {+1,+1,+1,+1, +1,-1,-1,+1, +1,+1,-1,-1, +1,-1,+1,-1}
+ */
+#ifndef QUAN_SM100_H
+#define QUAN_SM100_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QUAN_ABI_VERSION 1
+
+enum quan_dtype  { QUAN_F32 = 0, QUAN_BF16 = 1 };
+enum quan_layout { QUAN_LAYOUT_BCHWQ = 0, QUAN_LAYOUT_BHWQC = 1 };
+enum quan_act    { QUAN_ACT_NONE = 0, QUAN_ACT_SILU = 1 };
+
+enum quan_status {
+  QUAN_OK = 0,
+  QUAN_E_ARG = -1,          /* null pointer / bad enum / non-positive size */
+  QUAN_E_SHAPE = -2,        /* inconsistent dims (e.g. Ci % groups != 0) */
+  QUAN_E_UNSUPPORTED = -3,  /* valid request this build cannot serve (message says why) */
+  QUAN_E_WORKSPACE = -4,    /* workspace too small; see quan_*_workspace_bytes */
+  QUAN_E_DRIVER = -5        /* CUDA driver entry point (TMA descriptor encode) unavailable */
+};
+
+/* Convolution geometry.  Ci/Co are quaternion channels per component (conv.py:118-131);
+ * H/W are the INPUT spatial sizes; the output size follows torch's conv2d rule. */
+typedef struct quan_conv_dims {
+  int32_t B, Ci, Co, H, W;
+  int32_t kH, kW, sH, sW, pH, pW, dH, dW, groups;
+} quan_conv_dims;
+
+/* Which engine a conv call should use.  AUTO picks tcgen05 when the shape qualifies. */
+enum quan_conv_algo { QUAN_ALGO_AUTO = 0, QUAN_ALGO_DIRECT = 1, QUAN_ALGO_TCGEN05 = 2 };
+
+/* ---- library ------------------------------------------------------------------------------- */
+int         quan_version(void);                 /* QUAN_ABI_VERSION */
+const char* quan_last_error(void);              /* thread-local message of the last failure */
+const char* quan_build_info(void);              /* "sm_100a nvcc 12.9 ..." */
+
+/* ---- Poincare RGB -> quaternion ------------------------------------------------------------
+ * Replaces QConv2D._rgb_to_quaternion (poincare branch), ultralytics/nn/modules/conv.py:378-408
+ * (map at :388-397) == classification/quaternion/qconv.py:514-544.
+ * rgb: fp32 [B,3,H,W] contiguous.  out: [B,1,H,W,4] (both layouts coincide for C=1), dtype out_dtype.
+ * bwd: grad_rgb (fp32 [B,3,H,W]) from grad_out (out_dtype) and rgb. */
+int quan_poincare_fwd(const float* rgb, void* out, int32_t B, int32_t H, int32_t W,
+                      int out_dtype, void* stream);
+int quan_poincare_bwd(const float* rgb, const void* grad_out, float* grad_rgb,
+                      int32_t B, int32_t H, int32_t W, int out_dtype, void* stream);
+
+/* ---- IQBN -----------------------------------------------------------------------------------
+ * Training branch: IQBN.forward, ultralytics/nn/modules/conv.py:553-571 ==
+ * classification/quaternion/qconv.py:378-396.  Eval branch: conv.py:546-552 and the extension entry
+ * iqbn_forward, ultralytics/nn/cuda/quaternion_ops_py.cpp:113-128 -> quaternion_ops.cu:8-39,683-731.
+ *
+ * quan_iqbn_train_stats: one pass over x; per (c,q): mean, biased var (+1e-8 as the reference adds,
+ *   conv.py:557), rstd = 1/sqrt(var+eps); updates running_mean/var in place with `momentum`
+ *   (conv.py:561-562) when running_mean != NULL.  Writes stats[0..4C) = mean, [4C..8C) = var(+1e-8),
+ *   [8C..12C) = rstd, all indexed [c*4+q].  When `count_scale` > 1 the sums are treated as partial
+ *   (synced IQBN): see quan_iqbn_partial_sums / quan_iqbn_finalize_stats.
+ * quan_iqbn_apply_fwd: y = act(gamma*(x-mean)*rstd + beta)  (SiLU fused: conv.py:789,809).
+ * quan_iqbn_eval_fwd: y = act(gamma*(x-running_mean)/sqrt(running_var+eps)+beta) (no +1e-8).
+ * quan_iqbn_bwd_reduce: sums[0..4C) = sum dz, sums[4C..8C) = sum dz*xhat, dz = dy*act'(z).
+ * quan_iqbn_bwd_apply: dx = gamma*rstd*(dz - sums_dz/n - xhat*sums_dzxhat/n); if mix_t != NULL the result
+ *   is additionally multiplied per quaternion by mix_t (used to emit G = M^T dY for the preceding QConv2D).
+ * Workspace: quan_iqbn_workspace_bytes(C) bytes, zero-initialised ONCE by the caller (the kernels leave
+ *   it zeroed again on exit). */
+size_t quan_iqbn_workspace_bytes(int32_t C);
+int quan_iqbn_train_stats(const void* x, int32_t B, int32_t C, int32_t H, int32_t W, int dtype, int layout,
+                          float eps, float momentum, float* running_mean, float* running_var,
+                          float* stats /* [12*C] */, void* workspace, size_t ws_bytes, void* stream);
+/* synced-IQBN building blocks: raw per-(c,q) sums in fp64 {sum, sumsq}[c*4+q] (+ shift-free), then finalize
+ * after the caller all-reduced them across ranks (new work, no reference call site). */
+int quan_iqbn_partial_sums(const void* x, int32_t B, int32_t C, int32_t H, int32_t W, int dtype, int layout,
+                           double* sums /* [8*C]: sum[4C], sumsq[4C] */, void* workspace, size_t ws_bytes,
+                           void* stream);
+int quan_iqbn_finalize_stats(const double* sums, double count, int32_t C, float eps, float momentum,
+                             float* running_mean, float* running_var, float* stats, void* stream);
+int quan_iqbn_apply_fwd(const void* x, void* y, int32_t B, int32_t C, int32_t H, int32_t W, int dtype,
+                        int layout, const float* stats, const float* gamma, const float* beta, int act,
+                        void* stream);
+int quan_iqbn_eval_fwd(const void* x, void* y, int32_t B, int32_t C, int32_t H, int32_t W, int dtype,
+                       int layout, const float* gamma, const float* beta, const float* running_mean,
+                       const float* running_var, float eps, int act, void* stream);
+int quan_iqbn_bwd_reduce(const void* dy, const void* x, int32_t B, int32_t C, int32_t H, int32_t W,
+                         int dtype, int layout, const float* stats, const float* gamma, const float* beta,
+                         int act, double* sums /* [8*C] */, void* workspace, size_t ws_bytes, void* stream);
+int quan_iqbn_bwd_apply(const void* dy, const void* x, void* dx, int32_t B, int32_t C, int32_t H, int32_t W,
+                        int dtype, int layout, const float* stats, const float* gamma, const float* beta,
+                        int act, const double* sums, double count, float* dgamma, float* dbeta,
+                        const float* mix_t /* NULL or [16] */, void* stream);
+/* backward of the eval-mode affine (running stats are constants): dx = dz*gamma*rstd_run. */
+int quan_iqbn_eval_bwd(const void* dy, const void* x, void* dx, int32_t B, int32_t C, int32_t H, int32_t W,
+                       int dtype, int layout, const float* gamma, const float* beta,
+                       const float* running_mean, const float* running_var, float eps, int act,
+                       void* stream);
+
+/* ---- QUpsample (nearest) --------------------------------------------------------------------
+ * Replaces QUpsample.forward, ultralytics/nn/modules/conv.py:1229-1246 (F.interpolate nearest on each
+ * component).  x [B,C,H,W,4] -> y [B,C,H*s,W*s,4]; bwd sums the s*s taps. */
+int quan_qupsample_nearest_fwd(const void* x, void* y, int32_t B, int32_t C, int32_t H, int32_t W,
+                               int32_t scale, int dtype, int layout, void* stream);
+int quan_qupsample_nearest_bwd(const void* dy, void* dx, int32_t B, int32_t C, int32_t H, int32_t W,
+                               int32_t scale, int dtype, int layout, void* stream);
+
+/* ---- helpers ---------------------------------------------------------------------------------
+ * quan_mix: out_p = sum_q mix[4p+q] in_q per quaternion (qmix_forward/backward kernels,
+ *   ultralytics/nn/cuda/quaternion_ops_head.cu:8-95).  n_quat = B*C*H*W.
+ * quan_layout_convert: BCHWQ <-> BHWQC (what `.contiguous()` at conv.py:441 does for the reference). */
+int quan_mix(const void* in, void* out, int32_t B, int32_t C, int32_t H, int32_t W, int dtype, int layout,
+             const float* mix, void* stream);
+int quan_layout_convert(const void* src, int src_layout, void* dst, int dst_layout, int32_t B, int32_t C,
+                        int32_t H, int32_t W, int dtype, void* stream);
+
+/* ---- QConv2D ---------------------------------------------------------------------------------
+ * fwd replaces QConv2D.forward's compute (conv.py:472-499, classification/quaternion/qconv.py:592-612)
+ *   and the extension entry qconv_forward (quaternion_ops_py.cpp:48-86 -> quaternion_ops.cu:43-181,735-799):
+ *   S_q = conv2d(x_q, w_q) (+ bias_r on q=0), y_p = sum_q mix[4p+q] S_q.
+ * bwd replaces QConvFunction.backward (quaternion_autograd_cuda.py:42-67) and qconv_backward
+ *   (quaternion_ops_py.cpp:89-111 -> quaternion_ops.cu:532-679): G = M^T dY,
+ *   dX_q = conv_transpose(G_q, w_q), dW_q = corr(G_q, x_q), db_r = sum G_r (the autograd-correct bias grad;
+ *   the reference extension's `sum dY_r`, quaternion_ops.cu:500, is a documented defect — SURVEY §8(c)).
+ * w[4]: fp32 master weights, each [Co, Ci/groups, kH, kW] contiguous (conv.py:133-141); bias_r fp32 [Co] or NULL.
+ * dw[4]: fp32 grads, same shape, OVERWRITTEN.  Any of dx / dw / dbias may be NULL to skip that product.
+ * Workspace sized by quan_qconv2d_workspace_bytes (0 allowed for the direct engine's fwd). */
+size_t quan_qconv2d_workspace_bytes(const quan_conv_dims* d, int dtype, int layout, int algo);
+int quan_qconv2d_fwd(const void* x, const float* const w[4], const float* bias_r, void* y,
+                     const quan_conv_dims* d, int dtype, int layout, const float* mix, int algo,
+                     void* workspace, size_t ws_bytes, void* stream);
+int quan_qconv2d_bwd(const void* dy, const void* x, const float* const w[4], void* dx, float* const dw[4],
+                     float* dbias_r, const quan_conv_dims* d, int dtype, int layout, const float* mix,
+                     int algo, void* workspace, size_t ws_bytes, void* stream);
+/* reports which engine AUTO would pick for this shape: QUAN_ALGO_DIRECT or QUAN_ALGO_TCGEN05 */
+int quan_qconv2d_pick_algo(const quan_conv_dims* d, int dtype, int layout, int pass /*0 fwd,1 dgrad,2 wgrad*/);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QUAN_SM100_H */

@@ -1,0 +1,141 @@
+// common.cuh — shared helpers for libquan_sm100.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include "../../include/quan_sm100.h"
+
+#define QUAN_NUM_SMS 148  // B200: 2 dies x 74 SMs; grids are sized in multiples of this.
+#define QUAN_STR_(x) #x
+#define QUAN_STR(x) QUAN_STR_(x)
+
+namespace quan {
+
+// ---- error plumbing ---------------------------------------------------------------------------
+void set_error(const char* fmt, ...);   // defined in api.cu (thread-local buffer)
+
+#define QUAN_REQUIRE(cond, code, ...)                    \
+  do {                                                   \
+    if (!(cond)) {                                       \
+      ::quan::set_error(__VA_ARGS__);                    \
+      return (code);                                     \
+    }                                                    \
+  } while (0)
+
+// Always check the launch (the reference never does: quaternion_ops.cu:777-799).
+#define QUAN_CHECK_LAUNCH(name)                                                     \
+  do {                                                                              \
+    cudaError_t e__ = cudaGetLastError();                                           \
+    if (e__ != cudaSuccess) {                                                       \
+      ::quan::set_error("%s: launch failed: %s", name, cudaGetErrorString(e__));    \
+      return (int)e__;                                                              \
+    }                                                                               \
+  } while (0)
+
+#define QUAN_CUDA(call)                                                             \
+  do {                                                                              \
+    cudaError_t e__ = (call);                                                       \
+    if (e__ != cudaSuccess) {                                                       \
+      ::quan::set_error("%s failed: %s", #call, cudaGetErrorString(e__));           \
+      return (int)e__;                                                              \
+    }                                                                               \
+  } while (0)
+
+// ---- dtype traits -----------------------------------------------------------------------------
+template <typename T> struct VecTraits;
+template <> struct VecTraits<float> {
+  static constexpr int kMaxVec = 4;  // 16 B
+};
+template <> struct VecTraits<__nv_bfloat16> {
+  static constexpr int kMaxVec = 8;  // 16 B
+};
+
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) {
+  return __float2bfloat16_rn(v);
+}
+
+// A V-wide vector of T moved with one (<=16 B) load/store.
+template <typename T, int V> struct alignas(sizeof(T) * V) Vec {
+  T v[V];
+};
+
+template <typename T, int V>
+__device__ __forceinline__ void load_vec(const T* __restrict__ p, float (&out)[V]) {
+  Vec<T, V> t = *reinterpret_cast<const Vec<T, V>*>(p);
+#pragma unroll
+  for (int i = 0; i < V; ++i) out[i] = to_f32(t.v[i]);
+}
+template <typename T, int V>
+__device__ __forceinline__ void store_vec(T* __restrict__ p, const float (&in)[V]) {
+  Vec<T, V> t;
+#pragma unroll
+  for (int i = 0; i < V; ++i) t.v[i] = from_f32<T>(in[i]);
+  *reinterpret_cast<Vec<T, V>*>(p) = t;
+}
+
+// ---- activation -------------------------------------------------------------------------------
+__device__ __forceinline__ float sigmoid_f(float z) { return __fdividef(1.0f, 1.0f + __expf(-z)); }
+template <int ACT> __device__ __forceinline__ float act_fwd(float z) {
+  if constexpr (ACT == QUAN_ACT_SILU) return z * sigmoid_f(z);
+  return z;
+}
+// d act(z) / dz
+template <int ACT> __device__ __forceinline__ float act_grad(float z) {
+  if constexpr (ACT == QUAN_ACT_SILU) {
+    float s = sigmoid_f(z);
+    return s * (1.0f + z * (1.0f - s));
+  }
+  return 1.0f;
+}
+
+// ---- small host helpers -----------------------------------------------------------------------
+static inline int conv_out(int in, int k, int s, int p, int d) { return (in + 2 * p - d * (k - 1) - 1) / s + 1; }
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline int largest_pow2_divisor(int c, int cap) {
+  int v = 1;
+  while (v < cap && (c % (v * 2)) == 0) v *= 2;
+  return v;
+}
+static inline int grid_for(int64_t work_items, int threads, int blocks_per_sm) {
+  int64_t need = ceil_div64(work_items, threads);
+  int64_t cap = (int64_t)QUAN_NUM_SMS * blocks_per_sm;
+  if (need < 1) need = 1;
+  return (int)(need < cap ? need : cap);
+}
+
+struct Mix16 {
+  float m[16];
+};
+static inline Mix16 make_mix(const float* mix) {
+  Mix16 r;
+  for (int i = 0; i < 16; ++i) r.m[i] = mix[i];
+  return r;
+}
+static inline Mix16 make_mix_t(const float* mix) {  // transpose
+  Mix16 r;
+  for (int p = 0; p < 4; ++p)
+    for (int q = 0; q < 4; ++q) r.m[q * 4 + p] = mix[p * 4 + q];
+  return r;
+}
+__device__ __forceinline__ void apply_mix(const Mix16& M, const float (&in)[4], float (&out)[4]) {
+#pragma unroll
+  for (int p = 0; p < 4; ++p)
+    out[p] = M.m[p * 4 + 0] * in[0] + M.m[p * 4 + 1] * in[1] + M.m[p * 4 + 2] * in[2] + M.m[p * 4 + 3] * in[3];
+}
+
+// element offset of (b,c,h,w,q) in the two physical layouts
+template <int LAYOUT>
+__device__ __forceinline__ int64_t elem_off(int b, int c, int h, int w, int q, int C, int H, int W) {
+  if constexpr (LAYOUT == QUAN_LAYOUT_BCHWQ)
+    return ((((int64_t)b * C + c) * H + h) * W + w) * 4 + q;
+  else
+    return ((((int64_t)b * H + h) * W + w) * 4 + q) * C + c;
+}
+
+}  // namespace quan

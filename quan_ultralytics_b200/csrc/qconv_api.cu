@@ -1,0 +1,136 @@
+// qconv_api.cu — C-ABI entry points for QConv2D (argument validation, engine selection, workspace carving).
+// Replaces the reference extension's host wrappers qconv_forward_cuda / qconv_backward_cuda
+// (ultralytics/nn/cuda/quaternion_ops.cu:735-799, :532-679); unlike those, every launch goes to the caller's
+// stream, outputs/workspace are caller-allocated, and launch errors are reported.
+#include "qconv_internal.cuh"
+
+namespace quan {
+
+static int validate(const quan_conv_dims* d, int dtype, int layout, const float* mix) {
+  QUAN_REQUIRE(d != nullptr, QUAN_E_ARG, "qconv2d: null dims");
+  QUAN_REQUIRE(dtype == QUAN_F32 || dtype == QUAN_BF16, QUAN_E_ARG, "qconv2d: bad dtype %d", dtype);
+  QUAN_REQUIRE(layout == QUAN_LAYOUT_BCHWQ || layout == QUAN_LAYOUT_BHWQC, QUAN_E_ARG, "qconv2d: bad layout %d", layout);
+  QUAN_REQUIRE(mix != nullptr, QUAN_E_ARG, "qconv2d: null mixing matrix");
+  QUAN_REQUIRE(d->B > 0 && d->Ci > 0 && d->Co > 0 && d->H > 0 && d->W > 0, QUAN_E_ARG, "qconv2d: non-positive tensor dims");
+  QUAN_REQUIRE(d->kH > 0 && d->kW > 0 && d->sH > 0 && d->sW > 0 && d->dH > 0 && d->dW > 0 && d->pH >= 0 && d->pW >= 0,
+               QUAN_E_ARG, "qconv2d: bad kernel/stride/padding/dilation");
+  QUAN_REQUIRE(d->groups > 0 && d->Ci % d->groups == 0 && d->Co % d->groups == 0, QUAN_E_SHAPE,
+               "qconv2d: Ci=%d / Co=%d not divisible by groups=%d", d->Ci, d->Co, d->groups);
+  QUAN_REQUIRE(conv_out(d->H, d->kH, d->sH, d->pH, d->dH) > 0 && conv_out(d->W, d->kW, d->sW, d->pW, d->dW) > 0,
+               QUAN_E_SHAPE, "qconv2d: empty output (input %dx%d, kernel %dx%d)", d->H, d->W, d->kH, d->kW);
+  return QUAN_OK;
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static size_t g_bytes(const quan_conv_dims& d, int dtype) {
+  const int Ho = conv_out(d.H, d.kH, d.sH, d.pH, d.dH), Wo = conv_out(d.W, d.kW, d.sW, d.pW, d.dW);
+  return align_up((size_t)d.B * d.Co * Ho * Wo * 4 * (dtype == QUAN_F32 ? 4 : 2), 1024);
+}
+
+static int resolve_algo(const quan_conv_dims& d, int dtype, int layout, int pass, int algo) {
+  if (algo == QUAN_ALGO_DIRECT) return QUAN_ALGO_DIRECT;
+  const bool ok = qconv_tc_supported(d, dtype, layout, pass);
+  if (algo == QUAN_ALGO_TCGEN05) return ok ? QUAN_ALGO_TCGEN05 : -1;
+  return ok ? QUAN_ALGO_TCGEN05 : QUAN_ALGO_DIRECT;
+}
+
+}  // namespace quan
+
+using namespace quan;
+
+extern "C" {
+
+int quan_qconv2d_pick_algo(const quan_conv_dims* d, int dtype, int layout, int pass) {
+  if (d == nullptr || pass < 0 || pass > 2) return QUAN_E_ARG;
+  return resolve_algo(*d, dtype, layout, pass, QUAN_ALGO_AUTO);
+}
+
+size_t quan_qconv2d_workspace_bytes(const quan_conv_dims* d, int dtype, int layout, int algo) {
+  if (d == nullptr) return 0;
+  size_t tc = 0;
+  if (algo != QUAN_ALGO_DIRECT && layout == QUAN_LAYOUT_BHWQC) {
+    for (int pass = 0; pass < 3; ++pass)
+      if (qconv_tc_supported(*d, dtype, layout, pass)) {
+        size_t b = qconv_tc_workspace_bytes(*d, dtype, pass);
+        if (b > tc) tc = b;
+      }
+  }
+  return g_bytes(*d, dtype) + align_up(tc, 1024);
+}
+
+int quan_qconv2d_fwd(const void* x, const float* const w[4], const float* bias_r, void* y, const quan_conv_dims* d,
+                     int dtype, int layout, const float* mix, int algo, void* workspace, size_t ws_bytes,
+                     void* stream) {
+  int rc = validate(d, dtype, layout, mix);
+  if (rc) return rc;
+  QUAN_REQUIRE(x != nullptr && y != nullptr && w != nullptr && w[0] && w[1] && w[2] && w[3], QUAN_E_ARG,
+               "qconv2d_fwd: null tensor pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int a = resolve_algo(*d, dtype, layout, PASS_FWD, algo);
+  QUAN_REQUIRE(a > 0, QUAN_E_UNSUPPORTED, "qconv2d_fwd: tcgen05 engine requested but shape/layout does not qualify");
+  if (a == QUAN_ALGO_TCGEN05) {
+    const size_t need = qconv_tc_workspace_bytes(*d, dtype, PASS_FWD);
+    QUAN_REQUIRE(workspace != nullptr && ws_bytes >= need, QUAN_E_WORKSPACE,
+                 "qconv2d_fwd: tcgen05 engine needs %zu workspace bytes, got %zu", need, ws_bytes);
+    return qconv_tc_fwd(x, w, bias_r, y, *d, dtype, mix, workspace, ws_bytes, st);
+  }
+  return qconv_fwd_direct_launch(x, w, bias_r, y, *d, dtype, layout, mix, st);
+}
+
+int quan_qconv2d_bwd(const void* dy, const void* x, const float* const w[4], void* dx, float* const dw[4],
+                     float* dbias_r, const quan_conv_dims* d, int dtype, int layout, const float* mix, int algo,
+                     void* workspace, size_t ws_bytes, void* stream) {
+  int rc = validate(d, dtype, layout, mix);
+  if (rc) return rc;
+  QUAN_REQUIRE(dy != nullptr && w != nullptr && w[0] && w[1] && w[2] && w[3], QUAN_E_ARG, "qconv2d_bwd: null tensor pointer");
+  QUAN_REQUIRE(dw == nullptr || (dw[0] && dw[1] && dw[2] && dw[3]), QUAN_E_ARG, "qconv2d_bwd: dw must hold 4 pointers");
+  QUAN_REQUIRE(dw == nullptr || x != nullptr, QUAN_E_ARG, "qconv2d_bwd: weight gradient needs the input x");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t gb = g_bytes(*d, dtype);
+  QUAN_REQUIRE(workspace != nullptr && ws_bytes >= gb, QUAN_E_WORKSPACE,
+               "qconv2d_bwd: workspace needs >= %zu bytes (see quan_qconv2d_workspace_bytes), got %zu", gb, ws_bytes);
+  void* gq = workspace;
+  void* tc_ws = (char*)workspace + gb;
+  const size_t tc_ws_bytes = ws_bytes - gb;
+
+  // G = M^T dY, once, shared by dgrad / wgrad / bias grad
+  float mix_t[16];
+  for (int p = 0; p < 4; ++p)
+    for (int q = 0; q < 4; ++q) mix_t[q * 4 + p] = mix[p * 4 + q];
+  const int Ho = conv_out(d->H, d->kH, d->sH, d->pH, d->dH), Wo = conv_out(d->W, d->kW, d->sW, d->pW, d->dW);
+  rc = quan_mix(dy, gq, d->B, d->Co, Ho, Wo, dtype, layout, mix_t, stream);
+  if (rc) return rc;
+
+  if (dx != nullptr) {
+    const int a = resolve_algo(*d, dtype, layout, PASS_DGRAD, algo);
+    QUAN_REQUIRE(a > 0, QUAN_E_UNSUPPORTED, "qconv2d_bwd: tcgen05 dgrad requested but shape/layout does not qualify");
+    if (a == QUAN_ALGO_TCGEN05) {
+      const size_t need = qconv_tc_workspace_bytes(*d, dtype, PASS_DGRAD);
+      QUAN_REQUIRE(tc_ws_bytes >= need, QUAN_E_WORKSPACE, "qconv2d_bwd: dgrad needs %zu more workspace bytes", need);
+      rc = qconv_tc_dgrad(gq, w, dx, *d, dtype, tc_ws, tc_ws_bytes, st);
+    } else {
+      rc = qconv_dgrad_direct_launch(gq, w, dx, *d, dtype, layout, st);
+    }
+    if (rc) return rc;
+  }
+  if (dw != nullptr) {
+    const int a = resolve_algo(*d, dtype, layout, PASS_WGRAD, algo);
+    QUAN_REQUIRE(a > 0, QUAN_E_UNSUPPORTED, "qconv2d_bwd: tcgen05 wgrad requested but shape/layout does not qualify");
+    if (a == QUAN_ALGO_TCGEN05) {
+      const size_t need = qconv_tc_workspace_bytes(*d, dtype, PASS_WGRAD);
+      QUAN_REQUIRE(tc_ws_bytes >= need, QUAN_E_WORKSPACE, "qconv2d_bwd: wgrad needs %zu more workspace bytes", need);
+      rc = qconv_tc_wgrad(gq, x, dw, *d, dtype, tc_ws, tc_ws_bytes, st);
+    } else {
+      rc = qconv_wgrad_direct_launch(gq, x, dw, *d, dtype, layout, st);
+    }
+    if (rc) return rc;
+  }
+  if (dbias_r != nullptr) {
+    rc = qconv_bias_grad_launch(gq, dbias_r, *d, dtype, layout, st);
+    if (rc) return rc;
+  }
+  return QUAN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,170 @@
+"""torch.autograd bridge for the sm_100a quaternion ops.
+
+Plays the role of the reference's `QConvFunction` (ultralytics/nn/modules/quaternion_autograd_cuda.py:18-75) and
+extends it to the ops the reference left to PyTorch autograd (IQBN training fwd/bwd, QUpsample, the Poincare map).
+All arithmetic happens in libquan_sm100.so; this file only wires saved tensors and gradients.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+from ._lib import ACT_NONE, ACT_SILU, ALGO_AUTO
+
+_state = {"layout": ops.LAYOUT_BHWQC}
+
+
+def set_internal_layout(name: str) -> None:
+    """'bhwqc' (channels_last_3d, tensor-core path; default) or 'bchwq' (the reference's contiguous layout)."""
+    _state["layout"] = {"bhwqc": ops.LAYOUT_BHWQC, "bchwq": ops.LAYOUT_BCHWQ}[name.lower()]
+
+
+def internal_layout() -> int:
+    return _state["layout"]
+
+
+class _Poincare(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rgb: torch.Tensor, out_dtype: torch.dtype):
+        ctx.save_for_backward(rgb)
+        return ops.poincare_fwd(rgb, out_dtype)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (rgb,) = ctx.saved_tensors
+        grad = ops.poincare_bwd(rgb, grad_out) if ctx.needs_input_grad[0] else None
+        if grad is not None and grad.dtype != rgb.dtype:
+            grad = grad.to(rgb.dtype)
+        return grad, None
+
+
+def poincare_map(rgb: torch.Tensor, out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """RGB [B,3,H,W] -> unit quaternions [B,1,H,W,4] (conv.py:388-397)."""
+    if out_dtype is None:
+        out_dtype = torch.bfloat16 if (rgb.dtype == torch.bfloat16 or
+                                       (torch.is_autocast_enabled() and
+                                        torch.get_autocast_dtype("cuda") == torch.bfloat16)) else torch.float32
+    return _Poincare.apply(rgb, out_dtype)
+
+
+class _QConv2d(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w_r, w_i, w_j, w_k, bias_r, stride, padding, dilation, groups, mix, algo):
+        x, layout = ops.as_layout(x, _state["layout"])
+        ctx.save_for_backward(x, w_r, w_i, w_j, w_k)
+        ctx.conf = (tuple(stride), tuple(padding), tuple(dilation), int(groups), tuple(mix), algo, bias_r is not None)
+        return ops.qconv2d_fwd(x, (w_r, w_i, w_j, w_k), bias_r, stride, padding, dilation, groups, mix, algo, layout)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, w_r, w_i, w_j, w_k = ctx.saved_tensors
+        stride, padding, dilation, groups, mix, algo, has_bias = ctx.conf
+        need_dx = ctx.needs_input_grad[0]
+        need_dw = any(ctx.needs_input_grad[1:5])
+        need_db = has_bias and ctx.needs_input_grad[5]
+        dx, dws, db = ops.qconv2d_bwd(grad_out, x, (w_r, w_i, w_j, w_k), stride, padding, dilation, groups, mix,
+                                      need_dx, need_dw, need_db, algo)
+        if dws is None:
+            dws = [None] * 4
+        else:
+            dws = [g.to(w.dtype) if g.dtype != w.dtype else g for g, w in zip(dws, (w_r, w_i, w_j, w_k))]
+        return (dx, dws[0], dws[1], dws[2], dws[3], db, None, None, None, None, None, None)
+
+
+def qconv2d(x: torch.Tensor, w_r, w_i, w_j, w_k, bias_r=None, stride=(1, 1), padding=(0, 0), dilation=(1, 1),
+            groups: int = 1, mix: Sequence[float] = ops.M_A, algo: int = ALGO_AUTO) -> torch.Tensor:
+    """Separable Hamilton convolution on a BCHWQ tensor; same argument meaning as the reference's
+    `qconv2d_function` (quaternion_autograd_cuda.py:72-75) plus the mixing matrix."""
+    return _QConv2d.apply(x, w_r, w_i, w_j, w_k, bias_r, stride, padding, dilation, groups, mix, algo)
+
+
+class _IQBNTrain(torch.autograd.Function):
+    """Batch-statistics IQBN (+ optional fused SiLU).  Saves only x and the [12C] stats."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, eps, momentum, act, group):
+        x, layout = ops.as_layout(x)
+        B, C_, H, W, _ = x.shape
+        g32, b32 = ops._f32c(gamma), ops._f32c(beta)
+        world = dist.get_world_size(group) if (group is not None and dist.is_initialized()) else 1
+        if world > 1:  # synced IQBN: all-reduce {sum, sumsq} (new work)
+            sums = ops.iqbn_partial_sums(x, layout)
+            dist.all_reduce(sums, group=group)
+            count = float(B * H * W * world)
+            stats = ops.iqbn_finalize_stats(sums, count, C_, eps, momentum, running_mean, running_var)
+        else:
+            count = float(B * H * W)
+            stats = ops.iqbn_train_stats(x, layout, eps, momentum, running_mean, running_var)
+        y = ops.iqbn_apply_fwd(x, layout, stats, g32, b32, act)
+        ctx.save_for_backward(x, stats, g32, b32)
+        ctx.conf = (layout, act, count, group if world > 1 else None, gamma.dtype)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, stats, g32, b32 = ctx.saved_tensors
+        layout, act, count, group, pdtype = ctx.conf
+        dy, _ = ops.as_layout(dy, layout)
+        if dy.dtype != x.dtype:
+            dy = dy.to(x.dtype)
+        sums = ops.iqbn_bwd_reduce(dy, x, layout, stats, g32, b32, act)
+        C_ = x.size(1)
+        if group is not None:
+            # parameter grads stay LOCAL sums (DDP averages them); dx needs the global sums
+            dbeta = sums[:4 * C_].to(torch.float32).view(C_, 4)
+            dgamma = sums[4 * C_:].to(torch.float32).view(C_, 4)
+            dist.all_reduce(sums, group=group)
+            dx, _, _ = ops.iqbn_bwd_apply(dy, x, layout, stats, g32, b32, act, sums, count, want_param_grads=False)
+        else:
+            dx, dgamma, dbeta = ops.iqbn_bwd_apply(dy, x, layout, stats, g32, b32, act, sums, count)
+        if pdtype != torch.float32:
+            dgamma, dbeta = dgamma.to(pdtype), dbeta.to(pdtype)
+        return dx, dgamma, dbeta, None, None, None, None, None, None
+
+
+class _IQBNEval(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, eps, act):
+        x, layout = ops.as_layout(x)
+        g32, b32 = ops._f32c(gamma), ops._f32c(beta)
+        rm, rv = ops._f32c(running_mean), ops._f32c(running_var)
+        ctx.save_for_backward(x, g32, b32, rm, rv)
+        ctx.conf = (layout, act, eps)
+        return ops.iqbn_eval_fwd(x, layout, g32, b32, rm, rv, eps, act)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, g32, b32, rm, rv = ctx.saved_tensors
+        layout, act, eps = ctx.conf
+        dy, _ = ops.as_layout(dy, layout)
+        if dy.dtype != x.dtype:
+            dy = dy.to(x.dtype)
+        dx = ops.iqbn_eval_bwd(dy, x, layout, g32, b32, rm, rv, eps, act)
+        # gamma/beta grads in eval mode are not needed by any QUAN training path (IQBN trains in train mode)
+        return dx, None, None, None, None, None, None
+
+
+def iqbn(x: torch.Tensor, gamma, beta, running_mean, running_var, training: bool, eps: float = 1e-5,
+         momentum: float = 0.1, act: int = ACT_NONE, process_group=None) -> torch.Tensor:
+    """IQBN on a BCHWQ tensor (conv.py:520-571); `act=ACT_SILU` fuses the SiLU that follows it in `Conv`."""
+    if training:
+        return _IQBNTrain.apply(x, gamma, beta, running_mean, running_var, eps, momentum, act, process_group)
+    return _IQBNEval.apply(x, gamma, beta, running_mean, running_var, eps, act)
+
+
+class _QUpsample(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, scale):
+        ctx.scale = scale
+        return ops.qupsample_fwd(x, scale)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return ops.qupsample_bwd(dy, ctx.scale), None
+
+
+def qupsample_nearest(x: torch.Tensor, scale: int = 2) -> torch.Tensor:
+    return _QUpsample.apply(x, int(scale))

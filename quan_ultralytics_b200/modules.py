@@ -1,0 +1,233 @@
+"""nn.Module mirror of the reference's quaternion layer API, computing through libquan_sm100.so.
+
+Same class names, constructor signatures, parameter/buffer names and shapes as
+  ultralytics/nn/modules/conv.py      — QConv2D :70-499, IQBN :501-571, Conv :788-813, DWConv :918-923, QUpsample :1218-1246
+  classification/quaternion/qconv.py  — QConv2D :399-612 (mixing matrix M_B), IQBN :337-396
+so state dicts are interchangeable (weight_r/i/j/k, bias_r, gamma, beta, running_mean, running_var,
+num_batches_tracked — SURVEY §5 "Checkpoint / resume").  Differences, all deliberate and documented in DESIGN.md:
+  * IQBN uses batch statistics whenever `self.training` (the reference's `not CUDA_EXT` guard, conv.py:537, is a
+    defect — SURVEY §0.2) and updates the running buffers in place instead of re-assigning them.
+  * `mix` selects the reference's mixing matrix: "A" (ultralytics conv.py:493-496) or "B" (classification/ext).
+  * tensors stay in the internal BHWQC (channels_last_3d) layout between layers; logical shapes are unchanged.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Tuple, Union
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import functional as QF
+from . import ops
+from ._lib import ACT_NONE, ACT_SILU, ALGO_AUTO
+
+__all__ = ["QConv2D", "QConv2D_B", "IQBN", "QUpsample", "Conv", "DWConv", "autopad"]
+
+
+def autopad(k, p=None, d=1):
+    """Pad to 'same' shape outputs (conv.py:62-68)."""
+    if d > 1:
+        k = d * (k - 1) + 1 if isinstance(k, int) else [d * (x - 1) + 1 for x in k]
+    if p is None:
+        p = k // 2 if isinstance(k, int) else [x // 2 for x in k]
+    return p
+
+
+class QConv2D(nn.Module):
+    """Separable Hamilton-product convolution, y = M · (W_sep * x) (conv.py:70-499)."""
+
+    default_mix = "A"
+
+    def __init__(self, in_channels: int, out_channels: int, kernel_size: Union[int, Tuple[int, int]],
+                 stride: Union[int, Tuple[int, int]] = 1, padding: Union[str, int, Tuple[int, int]] = 0,
+                 dilation: Union[int, Tuple[int, int]] = 1, groups: int = 1, bias: bool = True,
+                 padding_mode: str = "zeros", dtype=None, mapping_type: str = "poincare",
+                 mix: Optional[str] = None):
+        super().__init__()
+        if isinstance(kernel_size, int):
+            kernel_size = (kernel_size, kernel_size)
+        if isinstance(stride, int):
+            stride = (stride, stride)
+        if isinstance(dilation, int):
+            dilation = (dilation, dilation)
+        if padding == "same":  # conv.py:91-98
+            if stride == (1, 1):
+                padding = ((kernel_size[0] - 1) // 2, (kernel_size[1] - 1) // 2)
+            else:
+                padding = tuple(autopad(k, None, d) for k, d in zip(kernel_size, dilation))
+        elif isinstance(padding, int):
+            padding = (padding, padding)
+        elif isinstance(padding, (list, tuple)) and len(padding) == 2:
+            padding = tuple(padding)
+        else:
+            raise ValueError(f"Invalid padding: {padding}")
+        if padding_mode != "zeros":
+            raise NotImplementedError("only padding_mode='zeros' is implemented (the reference ignores the argument)")
+
+        self.in_channels_total = in_channels
+        self.out_channels_total = out_channels
+        self.kernel_size = tuple(kernel_size)
+        self.stride = tuple(stride)
+        self.padding = padding
+        self.dilation = tuple(dilation)
+        self.groups = groups
+        self.mapping_type = mapping_type
+        self.mix = mix or self.default_mix
+        self.algo = ALGO_AUTO
+
+        self.is_first_layer = in_channels == 3
+        if self.is_first_layer:
+            self.in_channels_per_comp = 1
+        else:
+            assert in_channels % 4 == 0, "in_channels must be multiple of 4 for non-first layers"
+            self.in_channels_per_comp = in_channels // 4
+        assert out_channels % 4 == 0, "out_channels must be multiple of 4"
+        self.out_channels_per_comp = out_channels // 4
+        assert self.in_channels_per_comp % groups == 0, "Input channels per component must be divisible by groups"
+        self.in_channels_per_comp_grp = self.in_channels_per_comp // groups
+        self.bias_flag_overall = bias
+
+        shape = (self.out_channels_per_comp, self.in_channels_per_comp_grp, *self.kernel_size)
+        self.weight_r = nn.Parameter(torch.zeros(shape))
+        self.weight_i = nn.Parameter(torch.zeros(shape))
+        self.weight_j = nn.Parameter(torch.zeros(shape))
+        self.weight_k = nn.Parameter(torch.zeros(shape))
+        if bias:
+            self.bias_r = nn.Parameter(torch.zeros(self.out_channels_per_comp))
+        else:
+            self.register_parameter("bias_r", None)
+        self.register_parameter("bias_i", None)
+        self.register_parameter("bias_j", None)
+        self.register_parameter("bias_k", None)
+        self._initialize_weights()
+
+    def _initialize_weights(self):
+        """kaiming_uniform(a=sqrt(5)·scale) per component, bias U(±1/sqrt(fan_in)) (conv.py:232-256)."""
+        fan_in = self.in_channels_per_comp_grp * int(np.prod(self.kernel_size))
+        scales = {"mean_brightness": [1.0, 0.75, 0.75, 0.75]}.get(
+            self.mapping_type,
+            [1.0] * 4 if self.mapping_type in ("luminance", "raw_normalized", "hamilton", "poincare") else [0.5] * 4)
+        for i, w in enumerate((self.weight_r, self.weight_i, self.weight_j, self.weight_k)):
+            nn.init.kaiming_uniform_(w, a=math.sqrt(5.0) * scales[i])
+        if self.bias_flag_overall and self.bias_r is not None:
+            bound = (1 / math.sqrt(fan_in)) * scales[0] if fan_in > 0 else 0
+            nn.init.uniform_(self.bias_r, -bound, bound)
+
+    def _rgb_to_quaternion(self, rgb: torch.Tensor) -> torch.Tensor:
+        if self.mapping_type != "poincare":
+            raise NotImplementedError(
+                f"mapping_type={self.mapping_type!r}: only the Poincare map (conv.py:388-397) is part of the "
+                "B200 hot path (SURVEY §8 a3)")
+        return QF.poincare_map(rgb)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if self.is_first_layer:
+            assert x.dim() == 4 and x.size(1) == 3, f"Expected [B,3,H,W] RGB input, got {tuple(x.shape)}"
+            x = self._rgb_to_quaternion(x)
+        elif x.dim() == 4:  # [B, 4C, H, W] -> BCHWQ view (conv.py:427-433)
+            B, C, H, W = x.shape
+            assert C == self.in_channels_total, f"Expected {self.in_channels_total} channels, got {C}"
+            x = x.view(B, C // 4, 4, H, W).permute(0, 1, 3, 4, 2)
+        elif x.dim() == 5:
+            assert x.size(1) == self.in_channels_per_comp, \
+                f"Input C_per_q mismatch {x.size(1)} vs {self.in_channels_per_comp}"
+            assert x.size(4) == 4, "Input quaternion dim must be 4"
+        else:
+            raise ValueError(f"Unsupported input shape: {x.shape}")
+        return QF.qconv2d(x, self.weight_r, self.weight_i, self.weight_j, self.weight_k, self.bias_r, self.stride,
+                          self.padding, self.dilation, self.groups, ops.MIX[self.mix], self.algo)
+
+    def extra_repr(self) -> str:
+        return (f"{self.in_channels_total}, {self.out_channels_total}, kernel_size={self.kernel_size}, "
+                f"stride={self.stride}, padding={self.padding}, groups={self.groups}, "
+                f"bias={self.bias_r is not None}, mix={self.mix}")
+
+
+class QConv2D_B(QConv2D):
+    """classification/quaternion/qconv.py:399-612 flavour (mixing matrix M_B, also what the reference's CUDA
+    extension computes, quaternion_ops.cu:152-155)."""
+
+    default_mix = "B"
+
+
+class IQBN(nn.Module):
+    """Independent quaternion batch-norm over (B,H,W) per (channel, component) (conv.py:501-571)."""
+
+    def __init__(self, num_features, eps=1e-5, momentum=0.1):
+        super().__init__()
+        assert num_features % 4 == 0, "num_features must be a multiple of 4 for IQBN"
+        self.num_features = num_features // 4
+        self.eps = eps
+        self.momentum = momentum
+        self.gamma = nn.Parameter(torch.ones(self.num_features, 4))
+        self.beta = nn.Parameter(torch.zeros(self.num_features, 4))
+        self.register_buffer("running_mean", torch.zeros(self.num_features, 4))
+        self.register_buffer("running_var", torch.ones(self.num_features, 4))
+        self.register_buffer("num_batches_tracked", torch.tensor(0, dtype=torch.long))
+        self.process_group = None   # set by distributed.convert_sync_iqbn
+        self.sync = False
+
+    def forward(self, x: torch.Tensor, act: int = ACT_NONE) -> torch.Tensor:
+        assert x.dim() == 5 and x.size(4) == 4, "Input must be [B, C, H, W, 4]"
+        assert x.size(1) == self.num_features, f"expected {self.num_features} quaternion channels, got {x.size(1)}"
+        if self.training:
+            with torch.no_grad():
+                self.num_batches_tracked += 1
+            group = None
+            if self.sync and torch.distributed.is_available() and torch.distributed.is_initialized():
+                group = self.process_group or torch.distributed.group.WORLD
+            return QF.iqbn(x, self.gamma, self.beta, self.running_mean, self.running_var, True, self.eps,
+                           self.momentum, act, group)
+        return QF.iqbn(x, self.gamma, self.beta, self.running_mean, self.running_var, False, self.eps,
+                       self.momentum, act)
+
+    def extra_repr(self) -> str:
+        return f"{self.num_features * 4}, eps={self.eps}, momentum={self.momentum}, sync={self.sync}"
+
+
+class QUpsample(nn.Module):
+    """Nearest-neighbour upsampling of every quaternion component (conv.py:1218-1246)."""
+
+    def __init__(self, scale_factor=2, mode="nearest"):
+        super().__init__()
+        if mode != "nearest":
+            raise NotImplementedError("QUpsample: only mode='nearest' is used by the QUAN models (yolo11-obb-quan.yaml:35,39)")
+        if int(scale_factor) != scale_factor:
+            raise NotImplementedError("QUpsample: integer scale factors only")
+        self.scale_factor = int(scale_factor)
+        self.mode = mode
+
+    def forward(self, x):
+        assert x.dim() == 5 and x.size(4) == 4, "Expected quaternion format [B, C, H, W, 4]"
+        return QF.qupsample_nearest(x, self.scale_factor)
+
+
+class Conv(nn.Module):
+    """QConv2D -> IQBN -> SiLU (conv.py:788-813); IQBN-apply and SiLU run as one fused kernel."""
+
+    default_act = nn.SiLU()
+    conv_cls = QConv2D
+
+    def __init__(self, c1, c2, k=1, s=1, p=None, g=1, d=1, act=True):
+        super().__init__()
+        self.conv = self.conv_cls(c1, c2, k, s, autopad(k, p, d), groups=g, dilation=d, bias=False)
+        self.bn = IQBN(c2)
+        self.act = self.default_act if act is True else act if isinstance(act, nn.Module) else nn.Identity()
+
+    def forward(self, x):
+        y = self.conv(x)
+        if isinstance(self.act, nn.SiLU):
+            return self.bn(y, ACT_SILU)
+        return self.act(self.bn(y))
+
+    def forward_fuse(self, x):
+        return self.act(self.conv(x))
+
+
+class DWConv(Conv):
+    """Depth-wise quaternion convolution (conv.py:918-923)."""
+
+    def __init__(self, c1, c2, k=1, s=1, d=1, act=True):
+        super().__init__(c1, c2, k, s, g=math.gcd(c1 // 4, c2 // 4), d=d, act=act)

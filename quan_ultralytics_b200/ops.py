@@ -1,0 +1,352 @@
+"""Tensor-level wrappers over the C ABI (include/quan_sm100.h): torch owns memory and streams, the library computes.
+
+Every function here takes CUDA tensors, allocates outputs with torch (so the caching allocator and autograd own the
+memory), passes raw pointers + the current stream to libquan_sm100.so and raises RuntimeError on a
+non-zero return.  Nothing in this module computes with torch ops.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import (ACT_NONE, ACT_SILU, ALGO_AUTO, ALGO_DIRECT, ALGO_TCGEN05, BF16, F32, LAYOUT_BCHWQ, LAYOUT_BHWQC,
+                   ConvDims, PtrArray4, check)
+
+# Mixing matrices of the reference
+M_A = (1., -1., -1., -1., -1., 1., 1., -1., -1., -1., 1., 1., -1., 1., -1., 1.)   # ultralytics conv.py:493-496
+M_B = (1., 1., 1., 1., 1., -1., -1., 1., 1., 1., -1., -1., 1., -1., 1., -1.)       # classification qconv.py:606-609
+MIX = {"A": M_A, "B": M_B}
+
+_FloatArr16 = C.c_float * 16
+
+
+def _mix_arg(mix: Sequence[float]):
+    assert len(mix) == 16
+    return _FloatArr16(*[float(v) for v in mix])
+
+
+def _mix_t(mix: Sequence[float]) -> Tuple[float, ...]:
+    return tuple(mix[p * 4 + q] for q in range(4) for p in range(4))
+
+
+def _dtype_code(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise RuntimeError(f"quan ops support float32 and bfloat16 activations, got {t.dtype}")
+
+
+def _stream(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _require_cuda(*ts: Optional[torch.Tensor]) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("quan ops need CUDA tensors: there is no CPU fallback (oracle/ is test infrastructure only)")
+
+
+def layout_of(x: torch.Tensor) -> Optional[int]:
+    """Physical layout code of a logical [B,C,H,W,4] tensor, or None if it is neither supported layout."""
+    if x.dim() != 5 or x.size(4) != 4:
+        raise RuntimeError(f"expected a BCHWQ tensor [B,C,H,W,4], got {tuple(x.shape)}")
+    if x.is_contiguous(memory_format=torch.channels_last_3d) and x.size(1) > 1:
+        return LAYOUT_BHWQC
+    if x.is_contiguous():
+        return LAYOUT_BCHWQ
+    if x.is_contiguous(memory_format=torch.channels_last_3d):
+        return LAYOUT_BHWQC
+    return None
+
+
+def empty_q(shape, dtype, device, layout: int) -> torch.Tensor:
+    fmt = torch.channels_last_3d if layout == LAYOUT_BHWQC else torch.contiguous_format
+    return torch.empty(shape, dtype=dtype, device=device, memory_format=fmt)
+
+
+def _memory_format(layout: int):
+    return torch.channels_last_3d if layout == LAYOUT_BHWQC else torch.contiguous_format
+
+
+def as_layout(x: torch.Tensor, layout: Optional[int] = None) -> Tuple[torch.Tensor, int]:
+    """Return (tensor, layout code) with the tensor dense in one of the two layouts (converting only if needed)."""
+    cur = layout_of(x)
+    if cur is not None and (layout is None or cur == layout) and x.data_ptr() % 16 == 0:
+        return x, cur
+    target = layout if layout is not None else (cur if cur is not None else LAYOUT_BCHWQ)
+    if cur is not None and x.data_ptr() % 16 == 0:
+        return convert_layout(x, target), target
+    y = x.contiguous(memory_format=_memory_format(target))
+    if y.data_ptr() % 16 != 0:
+        y = y.clone(memory_format=_memory_format(target))
+    return y, target
+
+
+# ---- workspaces ------------------------------------------------------------------------------------------------
+_ws_cache = {}
+_iqbn_ws_cache = {}
+
+
+def _workspace(nbytes: int, device: torch.device) -> torch.Tensor:
+    key = (device.type, device.index)
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf
+
+
+def _iqbn_workspace(C_: int, device: torch.device) -> torch.Tensor:
+    key = (device.type, device.index, C_)
+    buf = _iqbn_ws_cache.get(key)
+    if buf is None:
+        n = _lib.load().quan_iqbn_workspace_bytes(C_)
+        buf = torch.zeros(n, dtype=torch.uint8, device=device)  # zeroed once; kernels leave it zeroed
+        _iqbn_ws_cache[key] = buf
+    return buf
+
+
+def _f32c(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    if t is None:
+        return None
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        t = t.detach().to(torch.float32).contiguous()
+    return t
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+# ---- Poincare ----------------------------------------------------------------------------------------------------
+def poincare_fwd(rgb: torch.Tensor, out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
+    _require_cuda(rgb)
+    if rgb.dim() != 4 or rgb.size(1) != 3:
+        raise RuntimeError(f"poincare_fwd expects [B,3,H,W], got {tuple(rgb.shape)}")
+    rgb = _f32c(rgb)
+    B, _, H, W = rgb.shape
+    out = torch.empty((B, 1, H, W, 4), dtype=out_dtype, device=rgb.device)
+    check(_lib.load().quan_poincare_fwd(rgb.data_ptr(), out.data_ptr(), B, H, W, _dtype_code(out), _stream(rgb)),
+          "quan_poincare_fwd")
+    return out
+
+
+def poincare_bwd(rgb: torch.Tensor, grad_out: torch.Tensor) -> torch.Tensor:
+    _require_cuda(rgb, grad_out)
+    rgb = _f32c(rgb)
+    B, _, H, W = rgb.shape
+    grad_out = grad_out.contiguous()
+    grad = torch.empty_like(rgb)
+    check(_lib.load().quan_poincare_bwd(rgb.data_ptr(), grad_out.data_ptr(), grad.data_ptr(), B, H, W,
+                                        _dtype_code(grad_out), _stream(rgb)), "quan_poincare_bwd")
+    return grad
+
+
+# ---- layout / mix -----------------------------------------------------------------------------------------------
+def convert_layout(x: torch.Tensor, dst_layout: int) -> torch.Tensor:
+    _require_cuda(x)
+    src = layout_of(x)
+    if src is None:
+        raise RuntimeError("convert_layout: tensor is not dense in either supported layout")
+    if src == dst_layout:
+        return x
+    B, C_, H, W, _ = x.shape
+    out = empty_q(x.shape, x.dtype, x.device, dst_layout)
+    check(_lib.load().quan_layout_convert(x.data_ptr(), src, out.data_ptr(), dst_layout, B, C_, H, W, _dtype_code(x),
+                                          _stream(x)), "quan_layout_convert")
+    return out
+
+
+def mix(x: torch.Tensor, matrix: Sequence[float]) -> torch.Tensor:
+    _require_cuda(x)
+    x, layout = as_layout(x)
+    B, C_, H, W, _ = x.shape
+    out = torch.empty_like(x, memory_format=torch.preserve_format)
+    check(_lib.load().quan_mix(x.data_ptr(), out.data_ptr(), B, C_, H, W, _dtype_code(x), layout,
+                               C.cast(_mix_arg(matrix), C.c_void_p), _stream(x)), "quan_mix")
+    return out
+
+
+# ---- QUpsample ---------------------------------------------------------------------------------------------------
+def qupsample_fwd(x: torch.Tensor, scale: int) -> torch.Tensor:
+    _require_cuda(x)
+    x, layout = as_layout(x)
+    B, C_, H, W, _ = x.shape
+    out = empty_q((B, C_, H * scale, W * scale, 4), x.dtype, x.device, layout)
+    check(_lib.load().quan_qupsample_nearest_fwd(x.data_ptr(), out.data_ptr(), B, C_, H, W, scale, _dtype_code(x),
+                                                 layout, _stream(x)), "quan_qupsample_nearest_fwd")
+    return out
+
+
+def qupsample_bwd(dy: torch.Tensor, scale: int) -> torch.Tensor:
+    _require_cuda(dy)
+    dy, layout = as_layout(dy)
+    B, C_, Ho, Wo, _ = dy.shape
+    H, W = Ho // scale, Wo // scale
+    out = empty_q((B, C_, H, W, 4), dy.dtype, dy.device, layout)
+    check(_lib.load().quan_qupsample_nearest_bwd(dy.data_ptr(), out.data_ptr(), B, C_, H, W, scale, _dtype_code(dy),
+                                                 layout, _stream(dy)), "quan_qupsample_nearest_bwd")
+    return out
+
+
+# ---- IQBN ----------------------------------------------------------------------------------------------------------
+def iqbn_train_stats(x: torch.Tensor, layout: int, eps: float, momentum: float,
+                     running_mean: Optional[torch.Tensor], running_var: Optional[torch.Tensor]) -> torch.Tensor:
+    """One launch: per-(c,q) mean / var(+1e-8) / rstd into stats[12C]; updates running stats in place."""
+    B, C_, H, W, _ = x.shape
+    stats = torch.empty(12 * C_, dtype=torch.float32, device=x.device)
+    ws = _iqbn_workspace(C_, x.device)
+    check(_lib.load().quan_iqbn_train_stats(x.data_ptr(), B, C_, H, W, _dtype_code(x), layout, eps, momentum,
+                                            _ptr(running_mean), _ptr(running_var), stats.data_ptr(), ws.data_ptr(),
+                                            ws.numel(), _stream(x)), "quan_iqbn_train_stats")
+    return stats
+
+
+def iqbn_partial_sums(x: torch.Tensor, layout: int) -> torch.Tensor:
+    B, C_, H, W, _ = x.shape
+    sums = torch.empty(8 * C_, dtype=torch.float64, device=x.device)
+    ws = _iqbn_workspace(C_, x.device)
+    check(_lib.load().quan_iqbn_partial_sums(x.data_ptr(), B, C_, H, W, _dtype_code(x), layout, sums.data_ptr(),
+                                             ws.data_ptr(), ws.numel(), _stream(x)), "quan_iqbn_partial_sums")
+    return sums
+
+
+def iqbn_finalize_stats(sums: torch.Tensor, count: float, C_: int, eps: float, momentum: float,
+                        running_mean: Optional[torch.Tensor], running_var: Optional[torch.Tensor]) -> torch.Tensor:
+    stats = torch.empty(12 * C_, dtype=torch.float32, device=sums.device)
+    check(_lib.load().quan_iqbn_finalize_stats(sums.data_ptr(), float(count), C_, eps, momentum, _ptr(running_mean),
+                                               _ptr(running_var), stats.data_ptr(), _stream(sums)),
+          "quan_iqbn_finalize_stats")
+    return stats
+
+
+def iqbn_apply_fwd(x: torch.Tensor, layout: int, stats: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor,
+                   act: int) -> torch.Tensor:
+    B, C_, H, W, _ = x.shape
+    y = torch.empty_like(x, memory_format=torch.preserve_format)
+    check(_lib.load().quan_iqbn_apply_fwd(x.data_ptr(), y.data_ptr(), B, C_, H, W, _dtype_code(x), layout,
+                                          stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), act, _stream(x)),
+          "quan_iqbn_apply_fwd")
+    return y
+
+
+def iqbn_eval_fwd(x: torch.Tensor, layout: int, gamma, beta, running_mean, running_var, eps: float,
+                  act: int) -> torch.Tensor:
+    B, C_, H, W, _ = x.shape
+    y = torch.empty_like(x, memory_format=torch.preserve_format)
+    check(_lib.load().quan_iqbn_eval_fwd(x.data_ptr(), y.data_ptr(), B, C_, H, W, _dtype_code(x), layout,
+                                         gamma.data_ptr(), beta.data_ptr(), running_mean.data_ptr(),
+                                         running_var.data_ptr(), eps, act, _stream(x)), "quan_iqbn_eval_fwd")
+    return y
+
+
+def iqbn_bwd_reduce(dy: torch.Tensor, x: torch.Tensor, layout: int, stats, gamma, beta, act: int) -> torch.Tensor:
+    B, C_, H, W, _ = x.shape
+    sums = torch.empty(8 * C_, dtype=torch.float64, device=x.device)
+    ws = _iqbn_workspace(C_, x.device)
+    check(_lib.load().quan_iqbn_bwd_reduce(dy.data_ptr(), x.data_ptr(), B, C_, H, W, _dtype_code(x), layout,
+                                           stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), act, sums.data_ptr(),
+                                           ws.data_ptr(), ws.numel(), _stream(x)), "quan_iqbn_bwd_reduce")
+    return sums
+
+
+def iqbn_bwd_apply(dy, x, layout: int, stats, gamma, beta, act: int, sums, count: float,
+                   want_param_grads: bool = True, mix_t: Optional[Sequence[float]] = None):
+    B, C_, H, W, _ = x.shape
+    dx = torch.empty_like(x, memory_format=torch.preserve_format)
+    dgamma = dbeta = None
+    if want_param_grads:
+        dgamma = torch.empty(C_, 4, dtype=torch.float32, device=x.device)
+        dbeta = torch.empty(C_, 4, dtype=torch.float32, device=x.device)
+    mix_arg = None if mix_t is None else C.cast(_mix_arg(mix_t), C.c_void_p)
+    check(_lib.load().quan_iqbn_bwd_apply(dy.data_ptr(), x.data_ptr(), dx.data_ptr(), B, C_, H, W, _dtype_code(x),
+                                          layout, stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), act,
+                                          sums.data_ptr(), float(count), _ptr(dgamma), _ptr(dbeta), mix_arg,
+                                          _stream(x)), "quan_iqbn_bwd_apply")
+    return dx, dgamma, dbeta
+
+
+def iqbn_eval_bwd(dy, x, layout: int, gamma, beta, running_mean, running_var, eps: float, act: int) -> torch.Tensor:
+    B, C_, H, W, _ = x.shape
+    dx = torch.empty_like(x, memory_format=torch.preserve_format)
+    check(_lib.load().quan_iqbn_eval_bwd(dy.data_ptr(), x.data_ptr(), dx.data_ptr(), B, C_, H, W, _dtype_code(x),
+                                         layout, gamma.data_ptr(), beta.data_ptr(), running_mean.data_ptr(),
+                                         running_var.data_ptr(), eps, act, _stream(x)), "quan_iqbn_eval_bwd")
+    return dx
+
+
+# ---- QConv2D ---------------------------------------------------------------------------------------------------------
+def conv_dims(x_shape, w_shape, stride, padding, dilation, groups) -> ConvDims:
+    B, Ci, H, W, _ = x_shape
+    Co, _, kH, kW = w_shape
+    return ConvDims(B, Ci, Co, H, W, kH, kW, stride[0], stride[1], padding[0], padding[1], dilation[0], dilation[1],
+                    groups)
+
+
+def conv_out_shape(d: ConvDims) -> Tuple[int, int]:
+    Ho = (d.H + 2 * d.pH - d.dH * (d.kH - 1) - 1) // d.sH + 1
+    Wo = (d.W + 2 * d.pW - d.dW * (d.kW - 1) - 1) // d.sW + 1
+    return Ho, Wo
+
+
+def _weights_arg(ws: Sequence[torch.Tensor]):
+    return PtrArray4(*[w.data_ptr() for w in ws])
+
+
+def qconv2d_fwd(x: torch.Tensor, weights: Sequence[torch.Tensor], bias_r: Optional[torch.Tensor], stride, padding,
+                dilation, groups: int, mix_matrix: Sequence[float], algo: int = ALGO_AUTO,
+                layout: Optional[int] = None) -> torch.Tensor:
+    _require_cuda(x, *weights, bias_r)
+    x, layout = as_layout(x, layout)
+    ws = [_f32c(w) for w in weights]
+    bias_r = _f32c(bias_r)
+    if ws[0].dim() != 4 or x.size(1) != ws[0].size(1) * groups:
+        raise RuntimeError(f"qconv2d_fwd: input has {x.size(1)} quaternion channels, weight expects "
+                           f"{ws[0].size(1) * groups} (weight {tuple(ws[0].shape)}, groups={groups})")
+    d = conv_dims(x.shape, ws[0].shape, stride, padding, dilation, groups)
+    Ho, Wo = conv_out_shape(d)
+    if Ho <= 0 or Wo <= 0:
+        raise RuntimeError(f"qconv2d_fwd: empty output for input {tuple(x.shape)} and kernel {tuple(ws[0].shape)}")
+    y = empty_q((d.B, d.Co, Ho, Wo, 4), x.dtype, x.device, layout)
+    lib = _lib.load()
+    nws = lib.quan_qconv2d_workspace_bytes(C.byref(d), _dtype_code(x), layout, algo)
+    wsb = _workspace(nws, x.device)
+    wa = _weights_arg(ws)
+    check(lib.quan_qconv2d_fwd(x.data_ptr(), C.cast(wa, C.c_void_p), _ptr(bias_r), y.data_ptr(), C.byref(d),
+                               _dtype_code(x), layout, C.cast(_mix_arg(mix_matrix), C.c_void_p), algo, wsb.data_ptr(),
+                               wsb.numel(), _stream(x)), "quan_qconv2d_fwd")
+    return y
+
+
+def qconv2d_bwd(dy: torch.Tensor, x: torch.Tensor, weights: Sequence[torch.Tensor], stride, padding, dilation,
+                groups: int, mix_matrix: Sequence[float], need_dx: bool = True, need_dw: bool = True,
+                need_db: bool = False, algo: int = ALGO_AUTO):
+    """Returns (dx or None, [dw_r, dw_i, dw_j, dw_k] or None, db_r or None)."""
+    _require_cuda(dy, x, *weights)
+    x, layout = as_layout(x)
+    dy, _ = as_layout(dy, layout)
+    ws = [_f32c(w) for w in weights]
+    d = conv_dims(x.shape, ws[0].shape, stride, padding, dilation, groups)
+    lib = _lib.load()
+    dx = torch.empty_like(x, memory_format=torch.preserve_format) if need_dx else None
+    dws = [torch.empty_like(w) for w in ws] if need_dw else None
+    db = torch.empty(d.Co, dtype=torch.float32, device=x.device) if need_db else None
+    nws = lib.quan_qconv2d_workspace_bytes(C.byref(d), _dtype_code(x), layout, algo)
+    wsb = _workspace(nws, x.device)
+    wa = _weights_arg(ws)
+    dwa = None if dws is None else _weights_arg(dws)
+    check(lib.quan_qconv2d_bwd(dy.data_ptr(), x.data_ptr(), C.cast(wa, C.c_void_p), _ptr(dx),
+                               None if dwa is None else C.cast(dwa, C.c_void_p), _ptr(db), C.byref(d), _dtype_code(x),
+                               layout, C.cast(_mix_arg(mix_matrix), C.c_void_p), algo, wsb.data_ptr(), wsb.numel(),
+                               _stream(x)), "quan_qconv2d_bwd")
+    return dx, dws, db
+
+
+def qconv2d_pick_algo(x_shape, w_shape, stride, padding, dilation, groups, dtype: torch.dtype, layout: int,
+                      pass_: int = 0) -> int:
+    d = conv_dims(x_shape, w_shape, stride, padding, dilation, groups)
+    return _lib.load().quan_qconv2d_pick_algo(C.byref(d), F32 if dtype == torch.float32 else BF16, layout, pass_)
