@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""bench.py — hot-path benchmark (contract in the task statement, read per SURVEY §8(d)).
+
+Workload (config[1] of BASELINE.json, "QConv2D/IQBN layer sweep" point): a stack of `depth` reference `Conv` blocks
+(QConv2D 3x3 s1 p1 C_q->C_q  ->  IQBN(batch stats)  ->  SiLU), training step = forward + backward (dX, dW, dgamma,
+dbeta) + SGD(momentum) update, on synthetic N x C_q x H x W x 4 activations.  metric = train images/s.
+
+  value      : images/s with the batch already resident in HBM (CUDA-event timed, max over ranks)
+  e2e        : same step through the public nn.Module API with HOST (pinned) inputs: H2D of the batch and D2H of the
+               step's result (first block's weight gradient) inside the timed region
+  roofline   : dominant kernel (by share of the step) against MEASURED_PEAKS.json
+  cpu_baseline / --impl reference : the reference's PyTorch CPU path (oracle/torch_port.py, all host threads) on a
+               bounded sample of the same workload
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+import torch  # noqa: E402
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cq", type=int, default=256, help="quaternion channels per component")
+    ap.add_argument("--hw", type=int, default=32)
+    ap.add_argument("--n", type=int, default=64, help="images per GPU per step")
+    ap.add_argument("--depth", type=int, default=4)
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
+    ap.add_argument("--mix", default="A", choices=["A", "B"])
+    ap.add_argument("--sync-iqbn", action="store_true")
+    ap.add_argument("--cpu-n", type=int, default=4, help="images per step of the bounded CPU sample")
+    ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-kernel-table", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return f"conv_block_stack(depth={a.depth},Cq={a.cq},k3s1,{a.hw}x{a.hw},N={a.n}/gpu,mix={a.mix})"
+
+
+def flops_per_image(a):
+    """Separable QConv2D FLOPs, train = 3 x fwd."""
+    return 3 * a.depth * 4 * 2 * a.hw * a.hw * a.cq * a.cq * 9
+
+
+def load_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "src": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "src": "fallback"}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the reference's PyTorch CPU path (port), all host threads
+# ---------------------------------------------------------------------------------------------------------------
+def run_cpu_port(a, n_images, steps, warmup):
+    from oracle import torch_port as TP
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(*[TP.Conv(a.cq, a.cq, 3, 1, mix=a.mix) for _ in range(a.depth)]).train()
+    opt = torch.optim.SGD(net.parameters(), lr=0.01, momentum=0.9)
+    x = torch.randn(n_images, a.cq, a.hw, a.hw, 4)
+    dy = torch.randn(n_images, a.cq, a.hw, a.hw, 4)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad(set_to_none=True)
+        y = net(x)
+        y.backward(dy)
+        opt.step()
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    return n_images / sec, sec, cores
+
+
+def reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = a.cpu_n
+    ips, sec, cores = run_cpu_port(a, n, a.steps, min(a.warmup, 1))
+    line = {
+        "impl": "reference", "metric": "train_images_per_sec", "value": ips, "unit": "images/s", "n_gpus": a.gpus,
+        "steps": a.steps, "warmup": min(a.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "note": "reference PyTorch CPU path (oracle/torch_port.py), fp32"},
+        "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
+                         "sample": f"{n} images/step of the same block stack, {a.steps} timed steps"},
+        "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [v.strip() for v in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def time_op(fn, iters, flush=None):
+    """Mean device time (ms) of fn() over `iters` launches, CUDA events on the current stream."""
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    tot = 0.0
+    for _ in range(iters):
+        if flush is not None:
+            flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        e1.synchronize()
+        tot += e0.elapsed_time(e1)
+    return tot / iters
+
+
+def kernel_table(a, dev, dtype, peaks):
+    """Per-op device times for one block of the stack, each timed alone with the L2 flushed between launches."""
+    import quan_ultralytics_b200 as Q
+    from quan_ultralytics_b200 import ops
+    L = ops.LAYOUT_BHWQC
+    esz = 2 if dtype == torch.bfloat16 else 4
+    N, C, H = a.n, a.cq, a.hw
+    x = torch.randn(N, C, H, H, 4, device=dev).to(dtype).contiguous(memory_format=torch.channels_last_3d)
+    dy = torch.randn_like(x)
+    w = [torch.randn(C, C, 3, 3, device=dev) * 0.02 for _ in range(4)]
+    gamma, beta = torch.ones(C, 4, device=dev), torch.zeros(C, 4, device=dev)
+    mix = ops.MIX[a.mix]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    S = x.numel() * esz
+    conv_flops = 4 * 2 * N * H * H * C * C * 9
+    stats = ops.iqbn_train_stats(x, L, 1e-5, 0.1, None, None)
+    sums = ops.iqbn_bwd_reduce(dy, x, L, stats, gamma, beta, Q.ACT_SILU)
+    cnt = float(N * H * H)
+    rows = {}
+
+    def add(name, fn, kind, work):
+        ms = time_op(fn, 10, flush)
+        if kind == "tensor":
+            peak = peaks["bf16_tflops"] * (1.0 if dtype == torch.bfloat16 else 0.5)
+            ach = work / ms / 1e9
+            rows[name] = {"ms": ms, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak}
+        else:
+            ach = work / ms / 1e6
+            rows[name] = {"ms": ms, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                          "frac": ach / peaks["hbm_gbs"]}
+
+    add("qconv2d_fwd", lambda: ops.qconv2d_fwd(x, w, None, (1, 1), (1, 1), (1, 1), 1, mix, ops.ALGO_AUTO, L), "tensor",
+        conv_flops)
+    add("qconv2d_bwd(dgrad+wgrad+mixT)", lambda: ops.qconv2d_bwd(dy, x, w, (1, 1), (1, 1), (1, 1), 1, mix, True, True, False),
+        "tensor", 2 * conv_flops)
+    add("iqbn_train_stats", lambda: ops.iqbn_train_stats(x, L, 1e-5, 0.1, None, None), "hbm", S)
+    add("iqbn_apply_fwd_silu", lambda: ops.iqbn_apply_fwd(x, L, stats, gamma, beta, Q.ACT_SILU), "hbm", 2 * S)
+    add("iqbn_bwd_reduce", lambda: ops.iqbn_bwd_reduce(dy, x, L, stats, gamma, beta, Q.ACT_SILU), "hbm", 2 * S)
+    add("iqbn_bwd_apply", lambda: ops.iqbn_bwd_apply(dy, x, L, stats, gamma, beta, Q.ACT_SILU, sums, cnt), "hbm", 3 * S)
+    return rows
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        reference_arm(a)
+        return
+
+    import quan_ultralytics_b200 as Q
+    lib = Q._lib.load()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product has no CPU path); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    dtype = torch.bfloat16 if a.dtype == "bf16" else torch.float32
+    peaks = load_peaks()
+
+    torch.manual_seed(1 + rank)
+    conv_cls = Q.Conv
+    blocks = []
+    for _ in range(a.depth):
+        b = conv_cls(a.cq * 4, a.cq * 4, 3, 1)
+        b.conv.mix = a.mix
+        blocks.append(b)
+    net = torch.nn.Sequential(*blocks).to(dev).train()
+    if a.sync_iqbn and world > 1:
+        from quan_ultralytics_b200.distributed import convert_sync_iqbn
+        convert_sync_iqbn(net)
+    model = net
+    if world > 1:
+        model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local_rank], gradient_as_bucket_view=True)
+    opt = torch.optim.SGD(net.parameters(), lr=0.01, momentum=0.9, foreach=True)
+
+    shape = (a.n, a.cq, a.hw, a.hw, 4)
+    fmt = torch.channels_last_3d
+    x_dev = torch.randn(shape, device=dev).to(dtype).contiguous(memory_format=fmt)
+    dy_dev = torch.randn(shape, device=dev).to(dtype).contiguous(memory_format=fmt)
+    # host copies for the e2e leg, already in the layout the device uses
+    x_host = torch.empty(x_dev.shape, dtype=dtype).contiguous(memory_format=fmt).pin_memory()
+    x_host.copy_(x_dev)
+    x_stage = torch.empty_like(x_dev, memory_format=torch.preserve_format)
+    g_host = torch.empty_like(net[0].conv.weight_r, device="cpu").pin_memory()
+
+    def step(xin):
+        opt.zero_grad(set_to_none=True)
+        y = model(xin)
+        y.backward(dy_dev)
+        opt.step()
+
+    def e2e_step():
+        x_stage.copy_(x_host, non_blocking=True)          # H2D of this step's inputs
+        step(x_stage)
+        g_host.copy_(net[0].conv.weight_r.grad, non_blocking=True)   # D2H of the step's result
+        torch.cuda.current_stream().synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(max(a.warmup, 3)):
+        step(x_dev)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    n0 = lib.quan_launch_count()
+    ms = timed(lambda: step(x_dev), a.steps)
+    launches = lib.quan_launch_count() - n0
+    for _ in range(2):
+        e2e_step()
+    ms_e2e = timed(e2e_step, a.steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    imgs = a.n * world * a.steps
+    value = imgs / (ms / 1e3)
+    e2e_value = imgs / (ms_e2e / 1e3)
+
+    if rank == 0:
+        line = {
+            "metric": "train_images_per_sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": a.steps,
+            "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": a.dtype, "data": "synthetic",
+            "config": {"workload": workload_name(a), "l2": "activations (%.0f MB/tensor) exceed the 126 MB L2" %
+                       (x_dev.numel() * x_dev.element_size() / 1e6), "parallelism": f"dp{world}",
+                       "sync_iqbn": bool(a.sync_iqbn and world > 1), "optimizer": "SGD(momentum=0.9)",
+                       "train_gflop_per_image": flops_per_image(a) / 1e9},
+            "e2e": {"value": e2e_value, "unit": "images/s",
+                    "h2d_bytes_per_step": x_host.numel() * x_host.element_size(),
+                    "d2h_bytes_per_step": g_host.numel() * g_host.element_size()},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "step_tflops": flops_per_image(a) * a.n * world / (ms / a.steps) / 1e9,
+        }
+        if not a.no_kernel_table:
+            table = kernel_table(a, dev, dtype, peaks)
+            # dominant kernel = largest share of one block's step
+            dom = max(table, key=lambda k: table[k]["ms"])
+            r = dict(table[dom])
+            r.update({"kernel": dom, "peak_src": peaks["src"], "traffic": None,
+                      "share_of_block": r["ms"] / sum(v["ms"] for v in table.values())})
+            line["roofline"] = r
+            line["kernels"] = table
+        if world == 1 and not a.no_cpu_baseline:
+            ips, sec, cores = run_cpu_port(a, a.cpu_n, a.cpu_steps, 1)
+            line["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
+                                    "sample": f"{a.cpu_n} images/step of the same block stack, {a.cpu_steps} timed steps, fp32"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -64,6 +64,7 @@ enum quan_conv_algo { QUAN_ALGO_AUTO = 0, QUAN_ALGO_DIRECT = 1, QUAN_ALGO_TCGEN0
 int         quan_version(void);                 /* QUAN_ABI_VERSION */
 const char* quan_last_error(void);              /* thread-local message of the last failure */
 const char* quan_build_info(void);              /* "sm_100a nvcc 12.9 ..." */
+uint64_t    quan_launch_count(void);            /* kernels launched by this library so far (process-wide) */
 
 /* ---- Poincare RGB -> quaternion ------------------------------------------------------------
  * Replaces QConv2D._rgb_to_quaternion (poincare branch), ultralytics/nn/modules/conv.py:378-408

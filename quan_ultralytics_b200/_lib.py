@@ -34,6 +34,7 @@ PROTOTYPES = {
     "quan_version": (_int, []),
     "quan_last_error": (C.c_char_p, []),
     "quan_build_info": (C.c_char_p, []),
+    "quan_launch_count": (C.c_uint64, []),
     "quan_poincare_fwd": (_int, [_vp, _vp, _i32, _i32, _i32, _int, _vp]),
     "quan_poincare_bwd": (_int, [_vp, _vp, _vp, _i32, _i32, _i32, _int, _vp]),
     "quan_iqbn_workspace_bytes": (_sz, [_i32]),

@@ -25,8 +25,11 @@ void set_error(const char* fmt, ...);   // defined in api.cu (thread-local buffe
   } while (0)
 
 // Always check the launch (the reference never does: quaternion_ops.cu:777-799).
+void count_launch();                    // defined in api.cu (process-wide atomic counter)
+
 #define QUAN_CHECK_LAUNCH(name)                                                     \
   do {                                                                              \
+    ::quan::count_launch();                                                         \
     cudaError_t e__ = cudaGetLastError();                                           \
     if (e__ != cudaSuccess) {                                                       \
       ::quan::set_error("%s: launch failed: %s", name, cudaGetErrorString(e__));    \

@@ -11,7 +11,7 @@ HEADER = ROOT / "include" / "quan_sm100.h"
 
 def declared_functions():
     text = re.sub(r"/\*.*?\*/", "", HEADER.read_text(), flags=re.S)
-    names = re.findall(r"^\s*(?:int|size_t|const char\*)\s+(quan_[a-z0-9_]+)\s*\(", text, flags=re.M)
+    names = re.findall(r"^\s*(?:int|size_t|uint64_t|const char\*)\s+(quan_[a-z0-9_]+)\s*\(", text, flags=re.M)
     assert len(names) >= 20
     return sorted(set(names))
 

@@ -1,0 +1,328 @@
+"""GPU parity: the CUDA path (through the C ABI) against the reference's own outputs (tests/golden) and the CPU
+oracle on seeded inputs.  Tolerances are BASELINE.json's: max relative error <= 1e-3 in fp32/tf32, <= 1e-2 in
+bf16, Poincare within 1e-6.  "Relative" = max|a-b| / max|b| over the tensor (per-tensor scale).
+"""
+import numpy as np
+import pytest
+import torch
+
+import quan_ultralytics_b200 as Q
+from quan_ultralytics_b200 import ops, quaternion_ops
+from oracle import quan_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+TOL_F32, TOL_BF16, TOL_POINCARE = 1e-3, 1e-2, 1e-6
+# the direct engine computes in true fp32 and must do much better than the tf32 budget
+TOL_F32_DIRECT = 2e-5
+LAYOUTS = [ops.LAYOUT_BCHWQ, ops.LAYOUT_BHWQC]
+CONV_CASES = ["k3s1", "k3s2", "k1", "dw", "g2d2", "k7s2"]
+
+
+def rel_err(a, b):
+    a = a.detach().double().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-30))
+
+
+def to_dev(a, dtype=torch.float32, layout=None):
+    t = torch.from_numpy(np.ascontiguousarray(a)).to(DEV, dtype)
+    if layout == ops.LAYOUT_BHWQC:
+        t = t.contiguous(memory_format=torch.channels_last_3d)
+    return t
+
+
+def bf16_round(a):
+    return torch.from_numpy(np.asarray(a)).to(torch.bfloat16).double().numpy()
+
+
+def conv_rec(golden, name):
+    g = lambda k: golden[f"{name}/{k}"]
+    cin, cout, k, s, p, d, grp, bias = [int(v) for v in g("conf")]
+    return g, [g("w_r"), g("w_i"), g("w_j"), g("w_k")], (g("bias_r") if bias else None), (s, p, d, grp)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def test_library_loaded_is_in_tree():
+    from quan_ultralytics_b200 import _lib
+    _lib.load()
+    maps = open("/proc/self/maps").read()
+    assert "libquan_sm100.so" in maps
+
+
+def test_poincare_golden(golden):
+    rgb = to_dev(golden["poincare/rgb"])
+    q = Q.poincare_map(rgb.requires_grad_(True), torch.float32)
+    assert q.shape == (2, 1, 8, 8, 4)
+    assert np.max(np.abs(q.detach().cpu().numpy() - golden["poincare/q"])) <= TOL_POINCARE
+    q.backward(to_dev(golden["poincare/gq"]))
+    assert np.max(np.abs(rgb.grad.cpu().numpy() - golden["poincare/grgb"])) <= 1e-5
+    qn = Q.poincare_map(to_dev(golden["poincare_n/rgb"]), torch.float32)
+    assert np.max(np.abs(qn.cpu().numpy() - golden["poincare_n/q"])) <= TOL_POINCARE
+    qb = Q.poincare_map(rgb.detach(), torch.bfloat16)
+    assert qb.dtype == torch.bfloat16 and rel_err(qb, golden["poincare/q"]) <= TOL_BF16
+
+
+@pytest.mark.parametrize("layout", LAYOUTS)
+@pytest.mark.parametrize("mix", ["A", "B"])
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_qconv_fp32_golden(golden, case, mix, layout):
+    g, w, b, (s, p, d, grp) = conv_rec(golden, f"conv{mix}_{case}")
+    x = to_dev(g("x"), layout=layout)
+    wt = [to_dev(v) for v in w]
+    bt = None if b is None else to_dev(b)
+    y = ops.qconv2d_fwd(x, wt, bt, (s, s), (p, p), (d, d), grp, ops.MIX[mix], ops.ALGO_DIRECT, layout)
+    assert ops.layout_of(y) in (layout, ops.LAYOUT_BCHWQ if y.size(1) == 1 else layout)
+    assert rel_err(y, g("y")) <= TOL_F32_DIRECT
+    dy = to_dev(g("dy"), layout=layout)
+    dx, dws, db = ops.qconv2d_bwd(dy, x, wt, (s, s), (p, p), (d, d), grp, ops.MIX[mix], True, True, b is not None,
+                                  ops.ALGO_DIRECT)
+    assert rel_err(dx, g("dx")) <= TOL_F32_DIRECT
+    for q, n in enumerate("rijk"):
+        assert rel_err(dws[q], g(f"dw_{n}")) <= TOL_F32_DIRECT
+    if b is not None:
+        assert rel_err(db, g("db_r")) <= TOL_F32_DIRECT
+
+
+@pytest.mark.parametrize("layout", LAYOUTS)
+@pytest.mark.parametrize("case", ["k3s1", "k3s2", "dw"])
+def test_qconv_bf16_vs_oracle(golden, case, layout):
+    g, w, b, (s, p, d, grp) = conv_rec(golden, f"convA_{case}")
+    xr, dyr = bf16_round(g("x")), bf16_round(g("dy"))
+    y_ref = O.qconv2d_fwd(xr, w, b, s, p, d, grp, O.M_A)
+    dx_ref, dw_ref, _ = O.qconv2d_bwd(dyr, xr, w, s, p, d, grp, O.M_A)
+    x = to_dev(g("x"), torch.bfloat16, layout)
+    wt = [to_dev(v) for v in w]
+    bt = None if b is None else to_dev(b)
+    y = ops.qconv2d_fwd(x, wt, bt, (s, s), (p, p), (d, d), grp, ops.M_A, ops.ALGO_DIRECT, layout)
+    assert y.dtype == torch.bfloat16 and rel_err(y, y_ref) <= TOL_BF16
+    dx, dws, _ = ops.qconv2d_bwd(to_dev(g("dy"), torch.bfloat16, layout), x, wt, (s, s), (p, p), (d, d), grp, ops.M_A,
+                                 True, True, False, ops.ALGO_DIRECT)
+    assert rel_err(dx, dx_ref) <= 2 * TOL_BF16       # G = M^T dY is itself rounded to bf16 once
+    for q in range(4):
+        assert rel_err(dws[q], dw_ref[q]) <= 2 * TOL_BF16
+
+
+@pytest.mark.parametrize("layout", LAYOUTS)
+@pytest.mark.parametrize("tag", ["iqbnA", "iqbnB"])
+def test_iqbn_golden(golden, tag, layout):
+    g = lambda k: golden[f"{tag}/{k}"]
+    bn = Q.IQBN(24).to(DEV)
+    with torch.no_grad():
+        bn.gamma.copy_(to_dev(g("gamma")))
+        bn.beta.copy_(to_dev(g("beta")))
+        bn.running_mean.copy_(to_dev(g("rm0")))
+        bn.running_var.copy_(to_dev(g("rv0")))
+    x = to_dev(g("x"), layout=layout).requires_grad_(True)
+    bn.train()
+    y = bn(x)
+    assert rel_err(y, g("y")) <= 1e-5
+    assert rel_err(bn.running_mean, g("rm1")) <= 1e-6 and rel_err(bn.running_var, g("rv1")) <= 1e-6
+    assert int(bn.num_batches_tracked) == int(g("nbt"))
+    y.backward(to_dev(g("dy"), layout=layout))
+    assert rel_err(x.grad, g("dx")) <= 1e-4
+    assert rel_err(bn.gamma.grad, g("dgamma")) <= 1e-5 and rel_err(bn.beta.grad, g("dbeta")) <= 1e-5
+    bn.eval()
+    assert rel_err(bn(x.detach()), g("y_eval")) <= 1e-5
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("layout", LAYOUTS)
+@pytest.mark.parametrize("shape", [(4, 16, 12, 10), (2, 3, 7, 5), (3, 1, 9, 9), (2, 48, 6, 6), (1, 130, 4, 4)])
+def test_iqbn_silu_vs_oracle(shape, layout, dtype):
+    B, C, H, W = shape
+    rng = np.random.default_rng(C * 100 + H)
+    x = rng.normal(size=(B, C, H, W, 4)) * 2.0 + rng.normal(size=(1, C, 1, 1, 4))
+    dy = rng.normal(size=x.shape)
+    gamma, beta = rng.normal(size=(C, 4)) * 0.5 + 1, rng.normal(size=(C, 4)) * 0.3
+    if dtype == torch.bfloat16:
+        x, dy = bf16_round(x), bf16_round(dy)
+    tol = TOL_BF16 if dtype == torch.bfloat16 else 1e-4
+    y_ref, rm, rv, _ = O.iqbn_train_fwd(x, gamma, beta, np.zeros((C, 4)), np.ones((C, 4)), act=True)
+    dx_ref, dg_ref, db_ref = O.iqbn_train_bwd(dy, x, gamma, beta, act=True)
+    xt = to_dev(x, dtype, layout).requires_grad_(True)
+    gt, bt = to_dev(gamma).requires_grad_(True), to_dev(beta).requires_grad_(True)
+    rmt, rvt = torch.zeros(C, 4, device=DEV), torch.ones(C, 4, device=DEV)
+    y = Q.iqbn(xt, gt, bt, rmt, rvt, True, 1e-5, 0.1, Q.ACT_SILU)
+    assert y.dtype == dtype and rel_err(y, y_ref) <= tol
+    assert rel_err(rmt, rm) <= 1e-5 and rel_err(rvt, rv) <= 1e-5
+    y.backward(to_dev(dy, dtype, layout))
+    assert rel_err(xt.grad, dx_ref) <= 2 * tol
+    assert rel_err(gt.grad, dg_ref) <= tol and rel_err(bt.grad, db_ref) <= tol
+    # eval mode fwd/bwd
+    xe = to_dev(x, dtype, layout).requires_grad_(True)
+    ye = Q.iqbn(xe, gt.detach(), bt.detach(), rmt, rvt, False, 1e-5, 0.1, Q.ACT_SILU)
+    assert rel_err(ye, O.iqbn_eval_fwd(x, gamma, beta, rmt.cpu().numpy(), rvt.cpu().numpy(), act=True)) <= tol
+    ye.backward(to_dev(dy, dtype, layout))
+    assert rel_err(xe.grad, O.iqbn_eval_bwd(dy, x, gamma, beta, rmt.cpu().numpy().astype(np.float64),
+                                            rvt.cpu().numpy().astype(np.float64), act=True)) <= 2 * tol
+
+
+def test_iqbn_workspace_is_left_zeroed_and_reusable():
+    x = torch.randn(2, 8, 5, 5, 4, device=DEV)
+    a = ops.iqbn_train_stats(x, ops.LAYOUT_BCHWQ, 1e-5, 0.1, None, None)
+    b = ops.iqbn_train_stats(x, ops.LAYOUT_BCHWQ, 1e-5, 0.1, None, None)
+    assert torch.equal(a, b)
+    assert int(ops._iqbn_workspace(8, x.device).count_nonzero()) == 0
+
+
+@pytest.mark.parametrize("layout", LAYOUTS)
+def test_conv_block_golden(golden, layout):
+    g = lambda k: golden[f"block/{k}"]
+    Q.set_internal_layout("bhwqc" if layout == ops.LAYOUT_BHWQC else "bchwq")
+    try:
+        blk = Q.Conv(16, 32, 3, 1).to(DEV)
+        with torch.no_grad():
+            for n in "rijk":
+                getattr(blk.conv, f"weight_{n}").copy_(to_dev(g(f"w_{n}")))
+        blk.train()
+        x = to_dev(g("x")).requires_grad_(True)
+        y = blk(x)
+        assert y.shape == (2, 8, 6, 6, 4)
+        assert rel_err(y, g("y")) <= 1e-4
+        y.backward(to_dev(g("dy")))
+        assert rel_err(x.grad, g("dx")) <= 1e-3
+        assert rel_err(blk.conv.weight_r.grad, g("dw_r")) <= 1e-3 and rel_err(blk.conv.weight_k.grad, g("dw_k")) <= 1e-3
+        assert rel_err(blk.bn.gamma.grad, g("dgamma")) <= 1e-3 and rel_err(blk.bn.beta.grad, g("dbeta")) <= 1e-3
+        assert rel_err(blk.bn.running_mean, g("rm1")) <= 1e-5 and rel_err(blk.bn.running_var, g("rv1")) <= 1e-5
+    finally:
+        Q.set_internal_layout("bhwqc")
+
+
+def test_first_layer_rgb_golden(golden):
+    m = Q.QConv2D(3, 16, 3, stride=2, padding=1, bias=False).to(DEV)
+    with torch.no_grad():
+        for n in "rijk":
+            getattr(m, f"weight_{n}").copy_(to_dev(golden[f"poincare/w_{n}"]))
+    y = m(to_dev(golden["poincare/rgb"]))
+    assert rel_err(y, golden["poincare/y"]) <= TOL_F32_DIRECT
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("layout", LAYOUTS)
+def test_upsample_golden(golden, layout, dtype):
+    g = lambda k: golden[f"upsample/{k}"]
+    x = to_dev(g("x"), dtype, layout).requires_grad_(True)
+    y = Q.QUpsample(2)(x)
+    ref_y = O.qupsample_fwd(x.detach().double().cpu().numpy(), 2)
+    assert y.shape == (2, 3, 8, 10, 4) and rel_err(y, ref_y) == 0.0          # pure data movement: bit exact
+    if dtype == torch.float32:
+        assert rel_err(y, g("y")) <= 1e-7
+    y.backward(to_dev(g("dy"), dtype, layout))
+    dy_r = to_dev(g("dy"), dtype).double().cpu().numpy()
+    assert rel_err(x.grad, O.qupsample_bwd(dy_r, 2)) <= (1e-6 if dtype == torch.float32 else TOL_BF16)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(2, 5, 3, 7), (1, 64, 8, 8), (3, 33, 5, 6), (2, 1, 4, 4)])
+def test_layout_convert_and_mix(shape, dtype):
+    B, C, H, W = shape
+    x = torch.randn(B, C, H, W, 4, device=DEV).to(dtype)
+    xb = ops.convert_layout(x, ops.LAYOUT_BHWQC)
+    assert xb.shape == x.shape and torch.equal(xb, x)                          # same logical tensor
+    if C > 1:
+        assert xb.is_contiguous(memory_format=torch.channels_last_3d)
+    xa = ops.convert_layout(xb, ops.LAYOUT_BCHWQ)
+    assert xa.is_contiguous() and torch.equal(xa, x)
+    for t in (x, xb):
+        m = ops.mix(t, ops.M_A)
+        ref = O.mix_apply(x.double().cpu().numpy(), O.M_A)
+        assert rel_err(m, ref) <= (1e-6 if dtype == torch.float32 else TOL_BF16)
+    # Hadamard property of M_B: M_B^T M_B = 4 I
+    back = ops.mix(ops.mix(x.float(), ops.M_B), ops._mix_t(ops.M_B))
+    assert rel_err(back, 4 * x.float().double().cpu().numpy()) <= 1e-6
+
+
+def test_quaternion_ops_shim_matches_reference_extension_contract(golden):
+    """Same entry points / argument order as quaternion_ops_py.cpp:132-165; M_B like the reference kernels."""
+    g, w, b, (s, p, d, grp) = conv_rec(golden, "convB_k3s2")
+    x, wt, bt = to_dev(g("x")), [to_dev(v) for v in w], to_dev(b)
+    assert quaternion_ops.get_mixing() == "B"
+    y = quaternion_ops.qconv_forward(x, *wt, bt, None, None, None, [s, s], [p, p], [d, d], grp)
+    assert y.is_contiguous() and rel_err(y, g("y")) <= TOL_F32_DIRECT
+    outs = quaternion_ops.qconv_backward(to_dev(g("dy")), x, *wt, True, [s, s], [p, p], [d, d], grp)
+    assert len(outs) == 6 and rel_err(outs[0], g("dx")) <= TOL_F32_DIRECT
+    for q, n in enumerate("rijk"):
+        assert rel_err(outs[1 + q], g(f"dw_{n}")) <= TOL_F32_DIRECT
+    assert rel_err(outs[5], g("db_r")) <= TOL_F32_DIRECT
+    assert quaternion_ops.qconv_backward(to_dev(g("dy")), x, *wt, False, [s, s], [p, p], [d, d], grp)[5] is None
+    gi = lambda k: golden[f"iqbnA/{k}"]
+    ye = quaternion_ops.iqbn_forward(to_dev(gi("x")), to_dev(gi("gamma")), to_dev(gi("beta")), to_dev(gi("rm1")),
+                                     to_dev(gi("rv1")), 1e-5)
+    assert rel_err(ye, gi("y_eval")) <= 1e-5
+    with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
+        quaternion_ops.qconv_forward(x.cpu(), *wt, bt, None, None, None, [s, s], [p, p], [d, d], grp)
+    with pytest.raises(RuntimeError):
+        quaternion_ops.qconv_forward(x, *wt, None, bt, None, None, [s, s], [p, p], [d, d], grp)
+    quaternion_ops.set_mixing("A")
+    try:
+        ga, wa, ba, (s, p, d, grp) = conv_rec(golden, "convA_k3s1")
+        ya = quaternion_ops.qconv_forward(to_dev(ga("x")), *[to_dev(v) for v in wa], None, None, None, None,
+                                          [s, s], [p, p], [d, d], grp)
+        assert rel_err(ya, ga("y")) <= TOL_F32_DIRECT
+    finally:
+        quaternion_ops.set_mixing("B")
+
+
+def test_error_convention_on_device_tensors():
+    x = torch.randn(1, 4, 8, 8, 4, device=DEV)
+    w = [torch.randn(6, 2, 3, 3, device=DEV) for _ in range(4)]       # Ci=4, groups=2, Co=6: fine; groups=4: error
+    with pytest.raises(RuntimeError):
+        ops.qconv2d_fwd(x, w, None, (1, 1), (1, 1), (1, 1), 4, ops.M_A)
+    with pytest.raises(RuntimeError, match="float32 and bfloat16"):
+        ops.qconv2d_fwd(x.half(), w, None, (1, 1), (1, 1), (1, 1), 2, ops.M_A)
+    with pytest.raises(RuntimeError, match="empty output"):
+        ops.qconv2d_fwd(torch.randn(1, 4, 2, 2, 4, device=DEV), w, None, (1, 1), (0, 0), (1, 1), 2, ops.M_A)
+
+
+# ---- medium sizes against the oracle (seconds on CPU) ---------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("cfg", [(2, 16, 16, 3, 1, 1, 24, 20), (2, 32, 16, 3, 2, 1, 17, 19), (1, 64, 64, 1, 1, 1, 16, 16),
+                                 (2, 16, 16, 3, 1, 16, 12, 12)])
+def test_qconv_medium_vs_oracle(cfg, dtype):
+    B, Ci, Co, k, s, grp, H, W = cfg
+    rng = np.random.default_rng(Ci + Co + k)
+    x = rng.normal(size=(B, Ci, H, W, 4))
+    w = [rng.normal(size=(Co, Ci // grp, k, k)) * 0.1 for _ in range(4)]
+    if dtype == torch.bfloat16:
+        x = bf16_round(x)
+    p = k // 2
+    y_ref = O.qconv2d_fwd(x, w, None, s, p, 1, grp, O.M_A)
+    dy = rng.normal(size=y_ref.shape)
+    if dtype == torch.bfloat16:
+        dy = bf16_round(dy)
+    dx_ref, dw_ref, _ = O.qconv2d_bwd(dy, x, w, s, p, 1, grp, O.M_A)
+    conv = Q.QConv2D(Ci * 4, Co * 4, k, s, p, groups=grp, bias=False).to(DEV)
+    with torch.no_grad():
+        for q, n in enumerate("rijk"):
+            getattr(conv, f"weight_{n}").copy_(to_dev(w[q]))
+    xt = to_dev(x, dtype).requires_grad_(True)
+    y = conv(xt)
+    tol = TOL_BF16 if dtype == torch.bfloat16 else TOL_F32
+    assert rel_err(y, y_ref) <= tol
+    y.backward(to_dev(dy, dtype))
+    assert rel_err(xt.grad, dx_ref) <= 2 * tol
+    for q, n in enumerate("rijk"):
+        assert rel_err(getattr(conv, f"weight_{n}").grad, dw_ref[q]) <= 2 * tol
+
+
+# ---- BASELINE-size properties (no oracle needed) -------------------------------------------------------------------
+def test_full_size_properties():
+    torch.manual_seed(0)
+    B, C, H, W = 16, 64, 64, 64                               # SURVEY §8(d) config 2, smallest sweep point
+    x = torch.randn(B, C, H, W, 4, device=DEV, dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last_3d)
+    bn = Q.IQBN(C * 4).to(DEV).train()
+    y = bn(x).float()
+    # idempotence property of batch-norm: output has zero mean / unit variance per (c,q)
+    assert y.mean(dim=(0, 2, 3)).abs().max() < 2e-2 and (y.var(dim=(0, 2, 3), unbiased=False) - 1).abs().max() < 3e-2
+    up = Q.QUpsample(2)(x)
+    assert torch.equal(up[:, :, ::2, ::2], x) and torch.equal(up[:, :, 1::2, 1::2], x)
+    assert torch.equal(ops.qupsample_bwd(up, 2).float(), (4 * x.float()).to(torch.bfloat16).float())
+    # linearity of the convolution in x
+    conv = Q.QConv2D(C * 4, C * 4, 3, 1, 1, bias=False).to(DEV)
+    x32 = torch.randn(2, C, 32, 32, 4, device=DEV)
+    x2 = torch.randn_like(x32)
+    lhs = conv(x32 + 2 * x2)
+    rhs = conv(x32) + 2 * conv(x2)
+    assert rel_err(lhs, rhs.detach().double().cpu().numpy()) <= TOL_F32
