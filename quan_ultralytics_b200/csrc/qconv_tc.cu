@@ -1,10 +1,448 @@
-// qconv_tc.cu — tcgen05/TMEM/TMA implicit-GEMM engine for QConv2D (placeholder: engine reports "unsupported"
-// until the kernels land; qconv_api.cu then routes everything to the direct engine).
+// qconv_tc.cu — tcgen05 / TMEM / TMA implicit-GEMM engine for QConv2D on sm_100a (layout BHWQC, groups = 1).
+//
+// Math (reference semantics): the separable stage of QConv2D is four independent real convolutions
+// S_q = conv2d(x_q, W_q) (ultralytics/nn/modules/conv.py:480-483) followed by the 4x4 mix y = M S (conv.py:485-499).
+// Here each S_q is an implicit GEMM  [128 output pixels] x [BN out channels] x [K = taps * C_in]:
+//   * A tile  = 128 pixels x BK input channels of component q at filter tap (kh,kw): ONE 5-D TMA box
+//               {BK, 1(q), Wt*sW, Ht*sH, Bt} with element strides {1,1,sW,sH,1} and start coordinate shifted by the tap;
+//               out-of-bounds coordinates are zero-filled by TMA = the convolution's zero padding.  Rows land
+//               K-major (channels contiguous) with the hardware swizzle the UMMA descriptor names.
+//   * B tile  = BN x BK slice of the pre-packed weights Wp[q][tap][n][k] (4-D TMA box).
+//   * D       = four fp32 accumulators (one per component q) of 128 lanes x BN columns, all resident in TMEM
+//               (4*BN <= 512 columns); tcgen05.mma is issued by one thread, operands straight from shared memory.
+//   * epilogue: 4 warps tcgen05.ld the four accumulators, apply the mixing matrix (+ bias on S_r, conv.py:480) in
+//               registers and store the mixed quaternion outputs — S never touches HBM.
+// dgrad (stride 1) is the same kernel on G = M^T dY with tap-flipped, transposed weights and identity mix;
+// wgrad is its own kernel below (MN-major operands, split-K over pixels).
 #include "qconv_internal.cuh"
+#include "tc_ptx.cuh"
+#include <mutex>
+
 namespace quan {
-bool qconv_tc_supported(const quan_conv_dims&, int, int, int) { return false; }
-size_t qconv_tc_workspace_bytes(const quan_conv_dims&, int, int) { return 0; }
-int qconv_tc_fwd(const void*, const float* const*, const float*, void*, const quan_conv_dims&, int, const float*, void*, size_t, cudaStream_t) { set_error("tcgen05 engine not built"); return QUAN_E_UNSUPPORTED; }
-int qconv_tc_dgrad(const void*, const float* const*, void*, const quan_conv_dims&, int, void*, size_t, cudaStream_t) { set_error("tcgen05 engine not built"); return QUAN_E_UNSUPPORTED; }
-int qconv_tc_wgrad(const void*, const void*, float* const*, const quan_conv_dims&, int, void*, size_t, cudaStream_t) { set_error("tcgen05 engine not built"); return QUAN_E_UNSUPPORTED; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// driver entry point for TMA descriptor encoding (libcuda is not linked: fetched through the runtime)
+// ---------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
 }
+
+static int encode_map(CUtensorMap* map, int dtype, int rank, const void* base, const uint64_t* dims, const uint64_t* strides_b,
+                      const uint32_t* box, const uint32_t* estr, uint32_t row_bytes) {
+  EncodeTiledFn fn = get_encode_fn();
+  QUAN_REQUIRE(fn != nullptr, QUAN_E_DRIVER, "cuTensorMapEncodeTiled is not available from this driver");
+  CUtensorMapSwizzle sw = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                            : CU_TENSOR_MAP_SWIZZLE_32B;
+  cuuint64_t gd[5], gs[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = estr[i]; }
+  for (int i = 0; i < rank - 1; ++i) gs[i] = strides_b[i];
+  CUresult r = fn(map, dtype == QUAN_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank,
+                  const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  QUAN_REQUIRE(r == CUDA_SUCCESS, QUAN_E_DRIVER, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d, box %u,%u,%u,%u,%u)",
+               (int)r, rank, bx[0], bx[1], bx[2], rank > 3 ? bx[3] : 0, rank > 4 ? bx[4] : 0);
+  return QUAN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// weight packing: fp32 master W_q[co][ci][tap] -> T Wp[q][tap][n][k]
+//   FWD  : n = co, k = ci, tap kept          DGRAD: n = ci, k = co, tap flipped (taps-1-tap)
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T, bool DGRAD>
+__global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restrict__ w0, const float* __restrict__ w1,
+                                                           const float* __restrict__ w2, const float* __restrict__ w3,
+                                                           T* __restrict__ out, int Co, int Ci, int taps) {
+  const int64_t per_q = (int64_t)Co * Ci * taps;
+  const int64_t total = 4 * per_q;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int q = (int)(i / per_q);
+    int64_t r = i - q * per_q;
+    const int N = DGRAD ? Ci : Co, K = DGRAD ? Co : Ci;
+    const int k = (int)(r % K);
+    r /= K;
+    const int n = (int)(r % N);
+    const int t = (int)(r / N);
+    const int co = DGRAD ? k : n, ci = DGRAD ? n : k, tap = DGRAD ? taps - 1 - t : t;
+    const float* w = q == 0 ? w0 : q == 1 ? w1 : q == 2 ? w2 : w3;
+    out[i] = from_f32<T>(__ldg(w + ((int64_t)co * Ci + ci) * taps + tap));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// forward / dgrad implicit-GEMM kernel
+// ---------------------------------------------------------------------------------------------------------------
+struct TcConvParams {
+  int B, Ho, Wo, Cout;                 // output tensor [B][Ho][Wo][4][Cout]
+  int Wt, Ht, Bt, tiles_w, tiles_h;    // 128-pixel tile = Bt x Ht x Wt (w fastest), tiles per image plane
+  int kH, kW, sH, sW, pH, pW, dH, dW;
+  int kblocks, bk_elems, ksteps;       // k-blocks per tap, elements per k-block row, UMMAs per stage
+  int BN, stages;
+  uint32_t a_stage_bytes, b_stage_bytes, sbo_bytes, layout_type, idesc, tmem_cols;
+  const float* bias;                   // [Cout] or null (joins S_r before the mix)
+  Mix16 mix;
+};
+
+constexpr int TC_THREADS = 192;   // warp 0: TMA producer, warp 1: TMEM alloc + MMA issuer, warps 2-5: epilogue
+
+template <typename T, bool MIX>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+qconv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, T* __restrict__ y,
+                   const TcConvParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024-byte alignment is required by the 128B swizzle atoms
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + (size_t)p.stages * p.a_stage_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + (size_t)p.stages * p.b_stage_bytes);
+  uint64_t* empty_bar = full_bar + p.stages;
+  uint64_t* tmem_full_bar = empty_bar + p.stages;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int KIND = sizeof(T) == 2 ? 0 : 1;
+
+  // tile coordinates
+  const int tile = blockIdx.x;
+  const int tw = tile % p.tiles_w;
+  const int th = (tile / p.tiles_w) % p.tiles_h;
+  const int tb = tile / (p.tiles_w * p.tiles_h);
+  const int w0 = tw * p.Wt, h0 = th * p.Ht, b0 = tb * p.Bt;
+  const int n0 = blockIdx.y * p.BN;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&map_a);
+    ptx::prefetch_tensormap(&map_b);
+    for (int s = 0; s < p.stages; ++s) {
+      ptx::mbar_init(full_bar + s, 1);
+      ptx::mbar_init(empty_bar + s, 1);
+    }
+    ptx::mbar_init(tmem_full_bar, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc(tmem_ptr, p.tmem_cols);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int taps = p.kH * p.kW;
+  const int iters_per_q = taps * p.kblocks;
+  const int total_iters = 4 * iters_per_q;
+
+  if (warp == 0) {
+    // ===== TMA producer (one lane) =====
+    if (lane == 0) {
+      const uint32_t tx = p.a_stage_bytes + p.b_stage_bytes;
+      for (int it = 0; it < total_iters; ++it) {
+        const int s = it % p.stages;
+        const uint32_t phase = (it / p.stages) & 1;
+        ptx::mbar_wait(empty_bar + s, phase ^ 1);
+        const int q = it / iters_per_q;
+        const int r = it - q * iters_per_q;
+        const int tap = r / p.kblocks, kb = r - tap * p.kblocks;
+        const int kh = tap / p.kW, kw = tap - kh * p.kW;
+        ptx::mbar_arrive_expect_tx(full_bar + s, tx);
+        ptx::tma_load_5d(smem_a + (size_t)s * p.a_stage_bytes, &map_a, full_bar + s, kb * p.bk_elems, q,
+                         w0 * p.sW - p.pW + kw * p.dW, h0 * p.sH - p.pH + kh * p.dH, b0);
+        ptx::tma_load_4d(smem_b + (size_t)s * p.b_stage_bytes, &map_b, full_bar + s, kb * p.bk_elems, n0, tap, q);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one lane) =====
+    if (lane == 0) {
+      for (int it = 0; it < total_iters; ++it) {
+        const int s = it % p.stages;
+        const uint32_t phase = (it / p.stages) & 1;
+        ptx::mbar_wait(full_bar + s, phase);
+        ptx::tc_fence_after();
+        const int q = it / iters_per_q;
+        const bool first = (it - q * iters_per_q) == 0;
+        const uint32_t a_addr = ptx::smem_u32(smem_a + (size_t)s * p.a_stage_bytes);
+        const uint32_t b_addr = ptx::smem_u32(smem_b + (size_t)s * p.b_stage_bytes);
+        const uint64_t da = ptx::make_smem_desc(a_addr, 16, p.sbo_bytes, p.layout_type);
+        const uint64_t db = ptx::make_smem_desc(b_addr, 16, p.sbo_bytes, p.layout_type);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(q * p.BN);
+        for (int k = 0; k < p.ksteps; ++k) {
+          // advance 32 bytes (one UMMA_K slice) inside the swizzle row: +2 in the 16-byte-unit start-address field
+          ptx::umma<KIND>(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (first && k == 0) ? 0u : 1u);
+        }
+        ptx::umma_commit(empty_bar + s);   // frees the smem slot once these MMAs have read it
+      }
+      ptx::umma_commit(tmem_full_bar);     // all four accumulators complete
+    }
+  } else {
+    // ===== epilogue: warps 2..5 own TMEM lane quarters (warp % 4) =====
+    const int quarter = warp & 3;
+    const int m = quarter * 32 + lane;                 // accumulator row = pixel within the tile
+    const int wt = m % p.Wt, ht = (m / p.Wt) % p.Ht, bt = m / (p.Wt * p.Ht);
+    const int wo = w0 + wt, ho = h0 + ht, b = b0 + bt;
+    const bool valid = (wo < p.Wo) && (ho < p.Ho) && (b < p.B);
+    T* yrow = y + ((((int64_t)b * p.Ho + ho) * p.Wo + wo) * 4) * p.Cout + n0;
+    ptx::mbar_wait(tmem_full_bar, 0);
+    ptx::tc_fence_after();
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    for (int c0 = 0; c0 < p.BN; c0 += 16) {
+      float acc[4][16];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) ptx::tmem_ld16(lane_base + (uint32_t)(q * p.BN + c0), acc[q]);
+      ptx::tmem_ld_wait();
+      if (p.bias != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[0][j] += __ldg(p.bias + n0 + c0 + j);
+      }
+      if (valid) {
+#pragma unroll
+        for (int pc = 0; pc < 4; ++pc) {
+          float o[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if constexpr (MIX)
+              o[j] = p.mix.m[pc * 4 + 0] * acc[0][j] + p.mix.m[pc * 4 + 1] * acc[1][j] + p.mix.m[pc * 4 + 2] * acc[2][j] +
+                     p.mix.m[pc * 4 + 3] * acc[3][j];
+            else
+              o[j] = acc[pc][j];
+          }
+          T* dst = yrow + (int64_t)pc * p.Cout + c0;
+          constexpr int VW = 16 / sizeof(T);   // elements per 16-byte store
+#pragma unroll
+          for (int v = 0; v < 16 / VW; ++v) {
+            float part[VW];
+#pragma unroll
+            for (int j = 0; j < VW; ++j) part[j] = o[v * VW + j];
+            store_vec<T, VW>(dst + v * VW, part);
+          }
+        }
+      }
+    }
+    ptx::tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+static int pow2_ceil(int v) {
+  int r = 1;
+  while (r < v) r <<= 1;
+  return r;
+}
+static int pick_bn(int n) {   // largest multiple of 16 that is <= 128 and divides n
+  for (int bn = 128; bn >= 16; bn -= 16)
+    if (n % bn == 0) return bn;
+  return 0;
+}
+static int pick_row_bytes(int k_elems, int esz) {   // widest swizzle row that tiles the K extent
+  const int kb = k_elems * esz;
+  if (kb % 128 == 0) return 128;
+  if (kb % 64 == 0) return 64;
+  if (kb % 32 == 0) return 32;
+  return 0;
+}
+
+struct TilePlan {
+  int Wt, Ht, Bt, tiles_w, tiles_h, tiles_b;
+};
+static bool plan_tiles(int B, int Ho, int Wo, int sH, int sW, TilePlan& t) {
+  t.Wt = pow2_ceil(Wo) < 128 ? pow2_ceil(Wo) : 128;
+  while (t.Wt * sW > 256) t.Wt >>= 1;                 // TMA box extent limit
+  int rem = 128 / t.Wt;
+  t.Ht = pow2_ceil(Ho) < rem ? pow2_ceil(Ho) : rem;
+  while (t.Ht * sH > 256) t.Ht >>= 1;
+  t.Bt = 128 / (t.Wt * t.Ht);
+  if (t.Bt > B || t.Bt > 256) return false;           // tiny problems stay on the direct engine
+  t.tiles_w = (Wo + t.Wt - 1) / t.Wt;
+  t.tiles_h = (Ho + t.Ht - 1) / t.Ht;
+  t.tiles_b = (B + t.Bt - 1) / t.Bt;
+  return true;
+}
+
+// geometry of a conv expressed as "output [B,Ho,Wo,N] from input [B,Hi,Wi,K]" (dgrad swaps the roles)
+struct IgemmShape {
+  int B, Hi, Wi, K, Ho, Wo, N, kH, kW, sH, sW, pH, pW, dH, dW;
+};
+
+static bool igemm_supported(const IgemmShape& s, int dtype) {
+  const int esz = dtype == QUAN_BF16 ? 2 : 4;
+  if (pick_row_bytes(s.K, esz) == 0) return false;
+  if (pick_bn(s.N) == 0) return false;
+  if ((s.N * esz) % 16 != 0 || (s.K * esz) % 16 != 0) return false;
+  if (s.sH > 8 || s.sW > 8) return false;             // TMA element-stride limit
+  TilePlan t;
+  if (!plan_tiles(s.B, s.Ho, s.Wo, s.sH, s.sW, t)) return false;
+  if ((int64_t)t.tiles_w * t.tiles_h * t.tiles_b > 0x7fffffff) return false;
+  return true;
+}
+
+static size_t packed_weight_bytes(const quan_conv_dims& d, int dtype) {
+  return ((size_t)4 * d.kH * d.kW * d.Co * d.Ci * (dtype == QUAN_BF16 ? 2 : 4) + 1023) / 1024 * 1024;
+}
+
+template <typename T, bool MIX>
+static int launch_igemm(const void* in, const void* wpacked, const float* bias, void* out, const IgemmShape& s, int dtype,
+                        const Mix16& mix, cudaStream_t st) {
+  const int esz = sizeof(T);
+  const int row_bytes = pick_row_bytes(s.K, esz);
+  TilePlan t;
+  QUAN_REQUIRE(row_bytes != 0 && plan_tiles(s.B, s.Ho, s.Wo, s.sH, s.sW, t), QUAN_E_UNSUPPORTED,
+               "tcgen05 conv: shape does not qualify");
+  TcConvParams p = {};
+  p.B = s.B; p.Ho = s.Ho; p.Wo = s.Wo; p.Cout = s.N;
+  p.Wt = t.Wt; p.Ht = t.Ht; p.Bt = t.Bt; p.tiles_w = t.tiles_w; p.tiles_h = t.tiles_h;
+  p.kH = s.kH; p.kW = s.kW; p.sH = s.sH; p.sW = s.sW; p.pH = s.pH; p.pW = s.pW; p.dH = s.dH; p.dW = s.dW;
+  p.bk_elems = row_bytes / esz;
+  p.kblocks = s.K / p.bk_elems;
+  p.ksteps = row_bytes / 32;
+  p.BN = pick_bn(s.N);
+  p.a_stage_bytes = 128u * row_bytes;
+  p.b_stage_bytes = (uint32_t)p.BN * row_bytes;
+  p.sbo_bytes = 8u * row_bytes;
+  p.layout_type = row_bytes == 128 ? 2u : row_bytes == 64 ? 4u : 6u;
+  p.idesc = ptx::make_idesc(sizeof(T) == 2 ? 1u : 2u, 0u, 0u, 128u, (uint32_t)p.BN);
+  p.tmem_cols = (uint32_t)pow2_ceil(4 * p.BN < 32 ? 32 : 4 * p.BN);
+  p.bias = bias;
+  p.mix = mix;
+  const size_t stage_bytes = (size_t)p.a_stage_bytes + p.b_stage_bytes;
+  const size_t budget = 200 * 1024;
+  int stages = (int)(budget / stage_bytes);
+  if (stages > 8) stages = 8;
+  QUAN_REQUIRE(stages >= 2, QUAN_E_UNSUPPORTED, "tcgen05 conv: stage too large");
+  p.stages = stages;
+  const size_t smem = 1024 + stages * stage_bytes + (2 * stages + 1) * sizeof(uint64_t) + 16;
+
+  // A: input activations [B][Hi][Wi][4][K] -> 5-D map {K, 4, Wi, Hi, B}
+  CUtensorMap map_a, map_b;
+  {
+    const uint64_t dims[5] = {(uint64_t)s.K, 4, (uint64_t)s.Wi, (uint64_t)s.Hi, (uint64_t)s.B};
+    const uint64_t str[4] = {(uint64_t)s.K * esz, (uint64_t)4 * s.K * esz, (uint64_t)s.Wi * 4 * s.K * esz,
+                             (uint64_t)s.Hi * s.Wi * 4 * s.K * esz};
+    const uint32_t box[5] = {(uint32_t)p.bk_elems, 1, (uint32_t)(t.Wt * s.sW), (uint32_t)(t.Ht * s.sH), (uint32_t)t.Bt};
+    const uint32_t est[5] = {1, 1, (uint32_t)s.sW, (uint32_t)s.sH, 1};
+    int rc = encode_map(&map_a, dtype, 5, in, dims, str, box, est, row_bytes);
+    if (rc) return rc;
+  }
+  // B: packed weights [4][taps][N][K] -> 4-D map {K, N, taps, 4}
+  {
+    const int taps = s.kH * s.kW;
+    const uint64_t dims[4] = {(uint64_t)s.K, (uint64_t)s.N, (uint64_t)taps, 4};
+    const uint64_t str[3] = {(uint64_t)s.K * esz, (uint64_t)s.N * s.K * esz, (uint64_t)taps * s.N * s.K * esz};
+    const uint32_t box[4] = {(uint32_t)p.bk_elems, (uint32_t)p.BN, 1, 1};
+    const uint32_t est[4] = {1, 1, 1, 1};
+    int rc = encode_map(&map_b, dtype, 4, wpacked, dims, str, box, est, row_bytes);
+    if (rc) return rc;
+  }
+  auto kern = qconv_igemm_kernel<T, MIX>;
+  static thread_local size_t smem_set = 0;   // raise the dynamic-smem cap once per (thread, instantiation)
+  if (smem > smem_set) {
+    QUAN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    smem_set = 227 * 1024;
+  }
+  dim3 grid((unsigned)(t.tiles_w * t.tiles_h * t.tiles_b), (unsigned)(s.N / p.BN));
+  kern<<<grid, TC_THREADS, smem, st>>>(map_a, map_b, reinterpret_cast<T*>(out), p);
+  QUAN_CHECK_LAUNCH("qconv_igemm_kernel");
+  return QUAN_OK;
+}
+
+template <typename T, bool DGRAD>
+static int pack_weights(const float* const w[4], void* out, const quan_conv_dims& d, cudaStream_t st) {
+  const int taps = d.kH * d.kW;
+  const int64_t total = (int64_t)4 * d.Co * d.Ci * taps;
+  int grid = grid_for(total, 256, 4);
+  pack_weights_kernel<T, DGRAD><<<grid, 256, 0, st>>>(w[0], w[1], w[2], w[3], reinterpret_cast<T*>(out), d.Co, d.Ci, taps);
+  QUAN_CHECK_LAUNCH("pack_weights_kernel");
+  return QUAN_OK;
+}
+
+static IgemmShape fwd_shape(const quan_conv_dims& d) {
+  IgemmShape s;
+  s.B = d.B; s.Hi = d.H; s.Wi = d.W; s.K = d.Ci; s.N = d.Co;
+  s.Ho = conv_out(d.H, d.kH, d.sH, d.pH, d.dH);
+  s.Wo = conv_out(d.W, d.kW, d.sW, d.pW, d.dW);
+  s.kH = d.kH; s.kW = d.kW; s.sH = d.sH; s.sW = d.sW; s.pH = d.pH; s.pW = d.pW; s.dH = d.dH; s.dW = d.dW;
+  return s;
+}
+// stride-1 dgrad as a forward conv of G (Co channels, Ho x Wo) with flipped kernels and padding d*(k-1)-p
+static IgemmShape dgrad_shape(const quan_conv_dims& d) {
+  IgemmShape s;
+  s.B = d.B; s.K = d.Co; s.N = d.Ci;
+  s.Hi = conv_out(d.H, d.kH, d.sH, d.pH, d.dH);
+  s.Wi = conv_out(d.W, d.kW, d.sW, d.pW, d.dW);
+  s.Ho = d.H; s.Wo = d.W;
+  s.kH = d.kH; s.kW = d.kW; s.sH = 1; s.sW = 1;
+  s.pH = d.dH * (d.kH - 1) - d.pH; s.pW = d.dW * (d.kW - 1) - d.pW;
+  s.dH = d.dH; s.dW = d.dW;
+  return s;
+}
+
+bool qconv_tc_supported(const quan_conv_dims& d, int dtype, int layout, int pass) {
+  if (layout != QUAN_LAYOUT_BHWQC || d.groups != 1) return false;
+  if (get_encode_fn() == nullptr) return false;
+  if (pass == PASS_FWD) return igemm_supported(fwd_shape(d), dtype);
+  if (pass == PASS_DGRAD) {
+    if (d.sH != 1 || d.sW != 1) return false;
+    return igemm_supported(dgrad_shape(d), dtype);
+  }
+  return false;   // wgrad: direct engine until the MN-major kernel lands
+}
+
+size_t qconv_tc_workspace_bytes(const quan_conv_dims& d, int dtype, int pass) {
+  if (pass == PASS_FWD || pass == PASS_DGRAD) return packed_weight_bytes(d, dtype);
+  return 0;
+}
+
+int qconv_tc_fwd(const void* x, const float* const w[4], const float* bias_r, void* y, const quan_conv_dims& d, int dtype,
+                 const float* mix, void* ws, size_t ws_bytes, cudaStream_t st) {
+  QUAN_REQUIRE(ws_bytes >= packed_weight_bytes(d, dtype), QUAN_E_WORKSPACE, "tcgen05 fwd: workspace too small");
+  const Mix16 M = make_mix(mix);
+  const IgemmShape s = fwd_shape(d);
+  int rc;
+  if (dtype == QUAN_BF16) {
+    rc = pack_weights<__nv_bfloat16, false>(w, ws, d, st);
+    if (rc) return rc;
+    return launch_igemm<__nv_bfloat16, true>(x, ws, bias_r, y, s, dtype, M, st);
+  }
+  rc = pack_weights<float, false>(w, ws, d, st);
+  if (rc) return rc;
+  return launch_igemm<float, true>(x, ws, bias_r, y, s, dtype, M, st);
+}
+
+int qconv_tc_dgrad(const void* gq, const float* const w[4], void* dx, const quan_conv_dims& d, int dtype, void* ws,
+                   size_t ws_bytes, cudaStream_t st) {
+  QUAN_REQUIRE(ws_bytes >= packed_weight_bytes(d, dtype), QUAN_E_WORKSPACE, "tcgen05 dgrad: workspace too small");
+  const IgemmShape s = dgrad_shape(d);
+  Mix16 ident = {};
+  int rc;
+  if (dtype == QUAN_BF16) {
+    rc = pack_weights<__nv_bfloat16, true>(w, ws, d, st);
+    if (rc) return rc;
+    return launch_igemm<__nv_bfloat16, false>(gq, ws, nullptr, dx, s, dtype, ident, st);
+  }
+  rc = pack_weights<float, true>(w, ws, d, st);
+  if (rc) return rc;
+  return launch_igemm<float, false>(gq, ws, nullptr, dx, s, dtype, ident, st);
+}
+
+int qconv_tc_wgrad(const void*, const void*, float* const*, const quan_conv_dims&, int, void*, size_t, cudaStream_t) {
+  set_error("tcgen05 wgrad kernel not built yet");
+  return QUAN_E_UNSUPPORTED;
+}
+
+}  // namespace quan
