@@ -39,11 +39,16 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+constexpr uint32_t SWZ_128B_ATOM32 = 1128;
+
 static int encode_map(CUtensorMap* map, int dtype, int rank, const void* base, const uint64_t* dims, const uint64_t* strides_b,
                       const uint32_t* box, const uint32_t* estr, uint32_t row_bytes) {
   EncodeTiledFn fn = get_encode_fn();
   QUAN_REQUIRE(fn != nullptr, QUAN_E_DRIVER, "cuTensorMapEncodeTiled is not available from this driver");
-  CUtensorMapSwizzle sw = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+  // row_bytes 128/64/32 select the plain swizzles; SWZ_128B_ATOM32 selects "128B swizzle with 32B atoms", the only
+  // layout the tensor core accepts for MN-major tf32 operands (UMMA layout type SWIZZLE_128B_BASE32B)
+  CUtensorMapSwizzle sw = row_bytes == SWZ_128B_ATOM32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+                          : row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                           : row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
                                             : CU_TENSOR_MAP_SWIZZLE_32B;
   cuuint64_t gd[5], gs[4];
@@ -78,7 +83,15 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restri
     const int t = (int)(r / N);
     const int co = DGRAD ? k : n, ci = DGRAD ? n : k, tap = DGRAD ? taps - 1 - t : t;
     const float* w = q == 0 ? w0 : q == 1 ? w1 : q == 2 ? w2 : w3;
-    out[i] = from_f32<T>(__ldg(w + ((int64_t)co * Ci + ci) * taps + tap));
+    float v = __ldg(w + ((int64_t)co * Ci + ci) * taps + tap);
+    if constexpr (sizeof(T) == 4) {
+      // the tensor core truncates fp32 operands to tf32; round the weights to nearest here so only the activation
+      // operand carries truncation bias (measured: halves the systematic error of the tf32 path)
+      uint32_t r32;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r32) : "f"(v));
+      v = __uint_as_float(r32);
+    }
+    out[i] = from_f32<T>(v);
   }
 }
 
@@ -237,6 +250,174 @@ qconv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// wgrad kernel:  dW_q[co][ci][tap] = sum_pixels G_q[pix][co] * x_q[pix (+) tap][ci]
+// GEMM per (q, tap): D[M = 128 co][N ci] += A^T B with K = pixels.  Both operands are "MN-major" for the tensor core
+// (channels contiguous, K = pixel rows of 128 bytes), which is exactly how the same TMA boxes as the forward pass land
+// in shared memory — no transposes.  One CTA owns (q, one kh row of taps, a 128-wide co block, one ci atom) and a
+// contiguous range of 64-pixel chunks (split-K); its TG accumulators (one per kw) live in TMEM.  Partials go to a
+// [split][q][tap][co][ci] fp32 workspace and a small deterministic reduce kernel writes dW in the master layout.
+// ---------------------------------------------------------------------------------------------------------------
+struct TcWgradParams {
+  int Wt, Ht, Bt, tiles_w, tiles_h, nchunks;   // 64-pixel chunk = Bt x Ht x Wt over the OUTPUT (G) grid
+  int kH, kW, sH, sW, pH, pW, dH, dW;
+  int Co, Ci, taps;
+  int TG;                      // taps per CTA (= kW)
+  int NA;                      // ci elements per CTA (one 128-byte atom)
+  int MA;                      // co atoms per CTA (M = 128 -> 128*es/128)
+  int co_blocks, ci_blocks, tap_groups;
+  int chunks_per_split;
+  int ksteps;                  // UMMAs per chunk per tap
+  uint32_t kadv;               // start-address advance per UMMA (in 16-byte units)
+  int stages;
+  uint32_t atom_bytes;         // 64 rows x 128 B
+  uint32_t sbo_bytes, layout_type;   // bf16: 8-row groups, SWIZZLE_128B; tf32: 4-row groups, SWIZZLE_128B_BASE32B
+  uint32_t a_stage_bytes, b_stage_bytes, idesc, tmem_cols;
+  float* partial;              // [splits][4][taps][Co][Ci]
+};
+
+constexpr int WG_PIX = 64;     // pixels (K) per pipeline stage
+
+template <typename T>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+qconv_wgrad_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant__ CUtensorMap map_x, const TcWgradParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + (size_t)p.stages * p.a_stage_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + (size_t)p.stages * p.b_stage_bytes);
+  uint64_t* empty_bar = full_bar + p.stages;
+  uint64_t* tmem_full_bar = empty_bar + p.stages;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int KIND = sizeof(T) == 2 ? 0 : 1;
+
+  // work decomposition
+  int combo = blockIdx.y;
+  const int nb = combo % p.ci_blocks; combo /= p.ci_blocks;
+  const int mb = combo % p.co_blocks; combo /= p.co_blocks;
+  const int tg = combo % p.tap_groups;
+  const int q = combo / p.tap_groups;
+  const int split = blockIdx.x;
+  const int chunk0 = split * p.chunks_per_split;
+  const int chunk1 = min(chunk0 + p.chunks_per_split, p.nchunks);
+  const int nch = chunk1 - chunk0;
+  const int co0 = mb * 128, ci0 = nb * p.NA;
+  const int kh = tg;   // tap group = one filter row
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&map_g);
+    ptx::prefetch_tensormap(&map_x);
+    for (int s = 0; s < p.stages; ++s) {
+      ptx::mbar_init(full_bar + s, 1);
+      ptx::mbar_init(empty_bar + s, 1);
+    }
+    ptx::mbar_init(tmem_full_bar, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc(tmem_ptr, p.tmem_cols);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t tx = p.a_stage_bytes + p.b_stage_bytes;
+      for (int it = 0; it < nch; ++it) {
+        const int s = it % p.stages;
+        const uint32_t phase = (it / p.stages) & 1;
+        ptx::mbar_wait(empty_bar + s, phase ^ 1);
+        const int chunk = chunk0 + it;
+        const int tw = chunk % p.tiles_w;
+        const int th = (chunk / p.tiles_w) % p.tiles_h;
+        const int tb = chunk / (p.tiles_w * p.tiles_h);
+        const int w0 = tw * p.Wt, h0 = th * p.Ht, b0 = tb * p.Bt;
+        ptx::mbar_arrive_expect_tx(full_bar + s, tx);
+        uint8_t* a_dst = smem_a + (size_t)s * p.a_stage_bytes;
+        for (int a = 0; a < p.MA; ++a)
+          ptx::tma_load_5d(a_dst + (size_t)a * p.atom_bytes, &map_g, full_bar + s, co0 + a * p.NA, q, w0, h0, b0);
+        uint8_t* b_dst = smem_b + (size_t)s * p.b_stage_bytes;
+        for (int t = 0; t < p.TG; ++t)
+          ptx::tma_load_5d(b_dst + (size_t)t * p.atom_bytes, &map_x, full_bar + s, ci0, q, w0 * p.sW - p.pW + t * p.dW,
+                           h0 * p.sH - p.pH + kh * p.dH, b0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      for (int it = 0; it < nch; ++it) {
+        const int s = it % p.stages;
+        const uint32_t phase = (it / p.stages) & 1;
+        ptx::mbar_wait(full_bar + s, phase);
+        ptx::tc_fence_after();
+        const uint32_t a_addr = ptx::smem_u32(smem_a + (size_t)s * p.a_stage_bytes);
+        const uint32_t b_addr = ptx::smem_u32(smem_b + (size_t)s * p.b_stage_bytes);
+        // MN-major, 128B swizzle: LBO = distance between 128-byte column atoms, SBO = one K-row group
+        const uint64_t da = ptx::make_smem_desc(a_addr, p.atom_bytes, p.sbo_bytes, p.layout_type);
+        for (int t = 0; t < p.TG; ++t) {
+          const uint64_t db = ptx::make_smem_desc(b_addr + (uint32_t)t * p.atom_bytes, p.atom_bytes, p.sbo_bytes, p.layout_type);
+          const uint32_t d_tmem = tmem_base + (uint32_t)(t * p.NA);
+          for (int k = 0; k < p.ksteps; ++k)
+            ptx::umma<KIND>(d_tmem, da + (uint64_t)(k * p.kadv), db + (uint64_t)(k * p.kadv), p.idesc,
+                            (it == 0 && k == 0) ? 0u : 1u);
+        }
+        ptx::umma_commit(empty_bar + s);
+      }
+      ptx::umma_commit(tmem_full_bar);
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int m = quarter * 32 + lane;            // co row inside the 128 block
+    const int co = co0 + m;
+    ptx::mbar_wait(tmem_full_bar, 0);
+    ptx::tc_fence_after();
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    for (int t = 0; t < p.TG; ++t) {
+      const int tap = kh * p.kW + t;
+      float* dst = p.partial + ((((int64_t)split * 4 + q) * p.taps + tap) * p.Co + co) * p.Ci + ci0;
+      for (int c0 = 0; c0 < p.NA; c0 += 16) {
+        float acc[16];
+        ptx::tmem_ld16(lane_base + (uint32_t)(t * p.NA + c0), acc);
+        ptx::tmem_ld_wait();
+        if (co < p.Co && nch > 0) {
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            float part[4] = {acc[v * 4], acc[v * 4 + 1], acc[v * 4 + 2], acc[v * 4 + 3]};
+            store_vec<float, 4>(dst + c0 + v * 4, part);
+          }
+        }
+      }
+    }
+    ptx::tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// dW_q[co][ci][tap] = sum_split partial[split][q][tap][co][ci]
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw0,
+                                                           float* __restrict__ dw1, float* __restrict__ dw2,
+                                                           float* __restrict__ dw3, int splits, int taps, int Co, int Ci) {
+  const int64_t per_q = (int64_t)taps * Co * Ci;
+  const int64_t total = 4 * per_q;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int sp = 0; sp < splits; ++sp) s += __ldg(partial + (int64_t)sp * total + i);
+    const int q = (int)(i / per_q);
+    int64_t r = i - q * per_q;
+    const int ci = (int)(r % Ci);
+    r /= Ci;
+    const int co = (int)(r % Co);
+    const int tap = (int)(r / Co);
+    float* dw = q == 0 ? dw0 : q == 1 ? dw1 : q == 2 ? dw2 : dw3;
+    dw[((int64_t)co * Ci + ci) * taps + tap] = s;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
@@ -392,6 +573,126 @@ static IgemmShape dgrad_shape(const quan_conv_dims& d) {
   return s;
 }
 
+
+struct WgradPlan {
+  TilePlan t;
+  int nchunks, TG, NA, MA, co_blocks, ci_blocks, tap_groups, splits, chunks_per_split, stages;
+  size_t smem, partial_bytes;
+};
+
+static bool plan_tiles_n(int B, int Ho, int Wo, int sH, int sW, int npix, TilePlan& t) {
+  t.Wt = pow2_ceil(Wo) < npix ? pow2_ceil(Wo) : npix;
+  while (t.Wt * sW > 256) t.Wt >>= 1;
+  int rem = npix / t.Wt;
+  t.Ht = pow2_ceil(Ho) < rem ? pow2_ceil(Ho) : rem;
+  while (t.Ht * sH > 256) t.Ht >>= 1;
+  t.Bt = npix / (t.Wt * t.Ht);
+  if (t.Bt > B || t.Bt > 256) return false;
+  t.tiles_w = (Wo + t.Wt - 1) / t.Wt;
+  t.tiles_h = (Ho + t.Ht - 1) / t.Ht;
+  t.tiles_b = (B + t.Bt - 1) / t.Bt;
+  return true;
+}
+
+static bool plan_wgrad(const quan_conv_dims& d, int dtype, WgradPlan& w) {
+  const int esz = dtype == QUAN_BF16 ? 2 : 4;
+  w.NA = 128 / esz;                                  // one 128-byte atom of channels
+  if (d.Ci % w.NA != 0 || d.Co % w.NA != 0) return false;
+  if (d.sH > 8 || d.sW > 8) return false;
+  const int Ho = conv_out(d.H, d.kH, d.sH, d.pH, d.dH), Wo = conv_out(d.W, d.kW, d.sW, d.pW, d.dW);
+  if (!plan_tiles_n(d.B, Ho, Wo, d.sH, d.sW, WG_PIX, w.t)) return false;
+  const int64_t nchunks = (int64_t)w.t.tiles_w * w.t.tiles_h * w.t.tiles_b;
+  if (nchunks > 0x3fffffff) return false;
+  w.nchunks = (int)nchunks;
+  w.TG = d.kW;
+  if (w.TG * w.NA > 512) return false;
+  w.tap_groups = d.kH;
+  w.MA = 128 / w.NA;                                 // atoms that make M = 128
+  w.co_blocks = (d.Co + 127) / 128;
+  w.ci_blocks = d.Ci / w.NA;
+  const int64_t combos = (int64_t)4 * w.tap_groups * w.co_blocks * w.ci_blocks;
+  if (combos > 65535) return false;
+  int64_t splits = (2 * QUAN_NUM_SMS + combos - 1) / combos;
+  if (splits > w.nchunks) splits = w.nchunks;
+  if (splits < 1) splits = 1;
+  w.chunks_per_split = (int)((w.nchunks + splits - 1) / splits);
+  w.splits = (w.nchunks + w.chunks_per_split - 1) / w.chunks_per_split;
+  const size_t atom = (size_t)WG_PIX * 128;
+  const size_t stage = (size_t)(w.MA + w.TG) * atom;
+  int stages = (int)((200 * 1024) / stage);
+  if (stages > 8) stages = 8;
+  if (stages < 2) return false;
+  w.stages = stages;
+  w.smem = 1024 + stages * stage + (2 * stages + 1) * sizeof(uint64_t) + 16;
+  w.partial_bytes = (size_t)w.splits * 4 * d.kH * d.kW * d.Co * d.Ci * sizeof(float);
+  return true;
+}
+
+template <typename T>
+static int launch_wgrad(const void* gq, const void* x, float* const dw[4], const quan_conv_dims& d, int dtype, void* ws,
+                        size_t ws_bytes, cudaStream_t st) {
+  WgradPlan w;
+  QUAN_REQUIRE(plan_wgrad(d, dtype, w), QUAN_E_UNSUPPORTED, "tcgen05 wgrad: shape does not qualify");
+  QUAN_REQUIRE(ws_bytes >= w.partial_bytes, QUAN_E_WORKSPACE, "tcgen05 wgrad: workspace needs %zu bytes, got %zu",
+               w.partial_bytes, ws_bytes);
+  const int esz = sizeof(T);
+  const int Ho = conv_out(d.H, d.kH, d.sH, d.pH, d.dH), Wo = conv_out(d.W, d.kW, d.sW, d.pW, d.dW);
+  TcWgradParams p = {};
+  p.Wt = w.t.Wt; p.Ht = w.t.Ht; p.Bt = w.t.Bt; p.tiles_w = w.t.tiles_w; p.tiles_h = w.t.tiles_h; p.nchunks = w.nchunks;
+  p.kH = d.kH; p.kW = d.kW; p.sH = d.sH; p.sW = d.sW; p.pH = d.pH; p.pW = d.pW; p.dH = d.dH; p.dW = d.dW;
+  p.Co = d.Co; p.Ci = d.Ci; p.taps = d.kH * d.kW;
+  p.TG = w.TG; p.NA = w.NA; p.MA = w.MA;
+  p.co_blocks = w.co_blocks; p.ci_blocks = w.ci_blocks; p.tap_groups = w.tap_groups;
+  p.chunks_per_split = w.chunks_per_split;
+  const int umma_k = 32 / esz;                       // pixels per UMMA
+  p.ksteps = WG_PIX / umma_k;
+  p.kadv = (uint32_t)(umma_k * 128) >> 4;            // umma_k rows of 128 B
+  p.stages = w.stages;
+  p.atom_bytes = WG_PIX * 128;
+  p.sbo_bytes = sizeof(T) == 2 ? 1024u : 512u;
+  p.layout_type = sizeof(T) == 2 ? 2u : 1u;
+  const uint32_t swz = sizeof(T) == 2 ? 128u : SWZ_128B_ATOM32;
+  p.a_stage_bytes = (uint32_t)w.MA * p.atom_bytes;
+  p.b_stage_bytes = (uint32_t)w.TG * p.atom_bytes;
+  p.idesc = ptx::make_idesc(sizeof(T) == 2 ? 1u : 2u, 1u, 1u, 128u, (uint32_t)w.NA);
+  p.tmem_cols = (uint32_t)pow2_ceil(w.TG * w.NA < 32 ? 32 : w.TG * w.NA);
+  p.partial = reinterpret_cast<float*>(ws);
+
+  CUtensorMap map_g, map_x;
+  {
+    const uint64_t dims[5] = {(uint64_t)d.Co, 4, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)d.B};
+    const uint64_t str[4] = {(uint64_t)d.Co * esz, (uint64_t)4 * d.Co * esz, (uint64_t)Wo * 4 * d.Co * esz,
+                             (uint64_t)Ho * Wo * 4 * d.Co * esz};
+    const uint32_t box[5] = {(uint32_t)w.NA, 1, (uint32_t)w.t.Wt, (uint32_t)w.t.Ht, (uint32_t)w.t.Bt};
+    const uint32_t est[5] = {1, 1, 1, 1, 1};
+    int rc = encode_map(&map_g, dtype, 5, gq, dims, str, box, est, swz);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[5] = {(uint64_t)d.Ci, 4, (uint64_t)d.W, (uint64_t)d.H, (uint64_t)d.B};
+    const uint64_t str[4] = {(uint64_t)d.Ci * esz, (uint64_t)4 * d.Ci * esz, (uint64_t)d.W * 4 * d.Ci * esz,
+                             (uint64_t)d.H * d.W * 4 * d.Ci * esz};
+    const uint32_t box[5] = {(uint32_t)w.NA, 1, (uint32_t)(w.t.Wt * d.sW), (uint32_t)(w.t.Ht * d.sH), (uint32_t)w.t.Bt};
+    const uint32_t est[5] = {1, 1, (uint32_t)d.sW, (uint32_t)d.sH, 1};
+    int rc = encode_map(&map_x, dtype, 5, x, dims, str, box, est, swz);
+    if (rc) return rc;
+  }
+  auto kern = qconv_wgrad_kernel<T>;
+  static thread_local bool attr_set = false;
+  if (!attr_set) {
+    QUAN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)w.splits, (unsigned)(4 * w.tap_groups * w.co_blocks * w.ci_blocks));
+  kern<<<grid, TC_THREADS, w.smem, st>>>(map_g, map_x, p);
+  QUAN_CHECK_LAUNCH("qconv_wgrad_kernel");
+  const int64_t total = (int64_t)4 * p.taps * d.Co * d.Ci;
+  wgrad_reduce_kernel<<<grid_for(total, 256, 4), 256, 0, st>>>(p.partial, dw[0], dw[1], dw[2], dw[3], w.splits, p.taps,
+                                                                d.Co, d.Ci);
+  QUAN_CHECK_LAUNCH("wgrad_reduce_kernel");
+  return QUAN_OK;
+}
+
 bool qconv_tc_supported(const quan_conv_dims& d, int dtype, int layout, int pass) {
   if (layout != QUAN_LAYOUT_BHWQC || d.groups != 1) return false;
   if (get_encode_fn() == nullptr) return false;
@@ -400,12 +701,14 @@ bool qconv_tc_supported(const quan_conv_dims& d, int dtype, int layout, int pass
     if (d.sH != 1 || d.sW != 1) return false;
     return igemm_supported(dgrad_shape(d), dtype);
   }
-  return false;   // wgrad: direct engine until the MN-major kernel lands
+  WgradPlan w;
+  return plan_wgrad(d, dtype, w);
 }
 
 size_t qconv_tc_workspace_bytes(const quan_conv_dims& d, int dtype, int pass) {
   if (pass == PASS_FWD || pass == PASS_DGRAD) return packed_weight_bytes(d, dtype);
-  return 0;
+  WgradPlan w;
+  return plan_wgrad(d, dtype, w) ? w.partial_bytes : 0;
 }
 
 int qconv_tc_fwd(const void* x, const float* const w[4], const float* bias_r, void* y, const quan_conv_dims& d, int dtype,
@@ -440,9 +743,10 @@ int qconv_tc_dgrad(const void* gq, const float* const w[4], void* dx, const quan
   return launch_igemm<float, false>(gq, ws, nullptr, dx, s, dtype, ident, st);
 }
 
-int qconv_tc_wgrad(const void*, const void*, float* const*, const quan_conv_dims&, int, void*, size_t, cudaStream_t) {
-  set_error("tcgen05 wgrad kernel not built yet");
-  return QUAN_E_UNSUPPORTED;
+int qconv_tc_wgrad(const void* gq, const void* x, float* const dw[4], const quan_conv_dims& d, int dtype, void* ws,
+                   size_t ws_bytes, cudaStream_t st) {
+  if (dtype == QUAN_BF16) return launch_wgrad<__nv_bfloat16>(gq, x, dw, d, dtype, ws, ws_bytes, st);
+  return launch_wgrad<float>(gq, x, dw, d, dtype, ws, ws_bytes, st);
 }
 
 }  // namespace quan

@@ -1,0 +1,99 @@
+"""GPU parity of the tcgen05/TMEM/TMA engine (qconv_tc.cu) through the C ABI: against the golden-validated direct
+engine on identical device tensors, and against the CPU oracle at sizes it finishes in seconds."""
+import numpy as np
+import pytest
+import torch
+
+from quan_ultralytics_b200 import ops
+from oracle import quan_oracle as O
+from tests.tc_probe import CASES
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+L = ops.LAYOUT_BHWQC
+
+
+def rel(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def make(case, seed=0):
+    name, dt, B, Ci, Co, H, W, k, s, p, d, bias, mix = case
+    dtype = torch.bfloat16 if dt == "bf16" else torch.float32
+    torch.manual_seed(seed)
+    x = torch.randn(B, Ci, H, W, 4, device=DEV).to(dtype).contiguous(memory_format=torch.channels_last_3d)
+    w = [torch.randn(Co, Ci, k, k, device=DEV) / (Ci * k * k) ** 0.5 for _ in range(4)]
+    b = torch.randn(Co, device=DEV) if bias else None
+    return dtype, x, w, b, ((s, s), (p, p), (d, d), 1, ops.MIX[mix])
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_tc_matches_direct_engine(case):
+    dtype, x, w, b, args = make(case)
+    tol = 1e-2 if dtype == torch.bfloat16 else 1e-3
+    picks = [ops.qconv2d_pick_algo(x.shape, w[0].shape, *args[:4], dtype, L, ps) for ps in range(3)]
+    assert picks[0] == ops.ALGO_TCGEN05, "every probe case is meant to qualify for the tensor-core forward"
+    y_ref = ops.qconv2d_fwd(x, w, b, *args, ops.ALGO_DIRECT, L)
+    y = ops.qconv2d_fwd(x, w, b, *args, ops.ALGO_TCGEN05, L)
+    assert rel(y, y_ref) <= tol
+    dy = torch.randn_like(y_ref)
+    dx_ref, dw_ref, db_ref = ops.qconv2d_bwd(dy, x, w, *args, True, True, b is not None, ops.ALGO_DIRECT)
+    dx, dw, db = ops.qconv2d_bwd(dy, x, w, *args, True, True, b is not None, ops.ALGO_AUTO)
+    assert rel(dx, dx_ref) <= 2 * tol
+    for a, r in zip(dw, dw_ref):
+        assert rel(a, r) <= 2 * tol
+    if b is not None:
+        assert rel(db, db_ref) <= 1e-4
+
+
+@pytest.mark.parametrize("dt", ["bf16", "f32"])
+def test_tc_vs_oracle_fp64(dt):
+    """Independent of the direct engine: fp64 numpy oracle on the same (bf16-rounded) inputs."""
+    case = ("oracle", dt, 2, 64, 64, 12, 10, 3, 1, 1, 1, True, "A")
+    dtype, x, w, b, args = make(case, seed=3)
+    tol = 1e-2 if dtype == torch.bfloat16 else 1e-3
+    xn = x.double().cpu().numpy()
+    wn = [t.double().cpu().numpy() for t in w]
+    if dtype == torch.bfloat16:          # the engine multiplies bf16 copies of the master weights
+        wn = [t.to(torch.bfloat16).double().cpu().numpy() for t in w]
+    y_ref = O.qconv2d_fwd(xn, wn, b.double().cpu().numpy(), 1, 1, 1, 1, O.M_A)
+    y = ops.qconv2d_fwd(x, w, b, *args, ops.ALGO_TCGEN05, L)
+    assert float(np.max(np.abs(y.double().cpu().numpy() - y_ref)) / np.max(np.abs(y_ref))) <= tol
+    dy = torch.randn_like(y)
+    dx_ref, dw_ref, db_ref = O.qconv2d_bwd(dy.double().cpu().numpy(), xn, wn, 1, 1, 1, 1, O.M_A, has_bias=True)
+    dx, dw, db = ops.qconv2d_bwd(dy, x, w, *args, True, True, True, ops.ALGO_TCGEN05)
+    nerr = lambda a, r: float(np.max(np.abs(a.double().cpu().numpy() - r)) / np.max(np.abs(r)))
+    assert nerr(dx, dx_ref) <= 2 * tol
+    for q in range(4):
+        assert nerr(dw[q], dw_ref[q]) <= 2 * tol
+    assert nerr(db, db_ref) <= 2 * tol
+
+
+def test_tc_is_what_auto_picks_for_the_sweep_shapes():
+    for C in (64, 128, 256, 512):
+        for dtype in (torch.bfloat16, torch.float32):
+            for s in (1, 2):
+                picks = [ops.qconv2d_pick_algo((16, C, 32, 32, 4), (C, C, 3, 3), (s, s), (1, 1), (1, 1), 1, dtype, L, ps)
+                         for ps in range(3)]
+                assert picks[0] == ops.ALGO_TCGEN05 and picks[2] == ops.ALGO_TCGEN05
+                assert picks[1] == (ops.ALGO_TCGEN05 if s == 1 else ops.ALGO_DIRECT)
+    # reference layout / grouped / tiny-channel convs stay on the direct engine
+    assert ops.qconv2d_pick_algo((16, 64, 32, 32, 4), (64, 64, 3, 3), (1, 1), (1, 1), (1, 1), 1, torch.bfloat16,
+                                 ops.LAYOUT_BCHWQ, 0) == ops.ALGO_DIRECT
+    assert ops.qconv2d_pick_algo((16, 64, 32, 32, 4), (64, 1, 3, 3), (1, 1), (1, 1), (1, 1), 64, torch.bfloat16, L, 0) \
+        == ops.ALGO_DIRECT
+    assert ops.qconv2d_pick_algo((16, 4, 32, 32, 4), (8, 4, 3, 3), (1, 1), (1, 1), (1, 1), 1, torch.bfloat16, L, 0) \
+        == ops.ALGO_DIRECT
+
+
+def test_tc_linearity_at_sweep_size():
+    """BASELINE-size property (no oracle): conv(a + 2b) == conv(a) + 2 conv(b) through the tensor-core path."""
+    torch.manual_seed(0)
+    C = 128
+    w = [torch.randn(C, C, 3, 3, device=DEV) * 0.03 for _ in range(4)]
+    a = torch.randn(16, C, 64, 64, 4, device=DEV).contiguous(memory_format=torch.channels_last_3d)
+    b = torch.randn_like(a)
+    args = ((1, 1), (1, 1), (1, 1), 1, ops.M_B)
+    f = lambda t: ops.qconv2d_fwd(t, w, None, *args, ops.ALGO_TCGEN05, L)
+    assert rel(f(a + 2 * b), f(a) + 2 * f(b)) <= 2e-3
