@@ -12,6 +12,7 @@
 //
 // Two physical layouts (include/quan_sm100.h): BCHWQ (reference) and BHWQC (channels_last_3d, tensor-core path).
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace quan {
 
@@ -90,16 +91,22 @@ __device__ bool last_block_arrive(unsigned int* counter) {
 }
 
 // =================================================================================================
-// Layout BHWQC: rows R = B*H*W, row length L = 4C, column vector cv covers V consecutive elements of a row.
-// Column-vector cv -> first column col = cv*V -> q = col / C, c = col % C (V | C so a vector never straddles q).
-// blockDim.x = rpb * cvpg (cvpg column vectors per column group, blockIdx.y = column group).
+// Layout BHWQC: rows R = B*H*W, row length L = 4C.  A column vector cv covers V consecutive elements of a row
+// (col = cv*V -> q = col / C, c = col % C; V | C so a vector never straddles q).
+// A block is rpb row lanes x cvpg column vectors with the column index fastest, so one block-iteration reads
+// rpb whole rows (or a <=4 KB contiguous piece of a wide row: blockIdx.y = column group) — long contiguous bursts
+// keep HBM pages open (a 128-byte-wide column-slice mapping measured 2x slower).  A thread owns its column vector for
+// the whole kernel: per-channel parameters and partial sums stay in registers, U row loads are in flight at once.
+// Reductions: fp64 through shared memory across the row lanes, then ONE fp64 atomic per column element per block and
+// at most 2 blocks per SM, so an accumulator address sees <= 296 atomics (the first version issued one per thread —
+// 2368 per address — and the same-address serialisation in L2 held the kernel at 15% of HBM bandwidth).
 // =================================================================================================
 struct GeomB {
   int64_t R;      // rows
   int L;          // 4C
   int C;
-  int cvpg;       // column vectors per group
-  int rpb;        // rows per block iteration
+  int cvpg;       // column vectors per group (per block row)
+  int rpb;        // row lanes per block
 };
 
 template <int V>
@@ -111,7 +118,7 @@ __device__ __forceinline__ void colvec_param_index(int cv, int C, int (&idx)[V])
 }
 
 // MODE 0: sums of x and x^2.  MODE 1: sums of dz and dz*x (dz = dy*act'(x*scale+shift)).
-template <typename T, int V, int MODE, int ACT>
+template <typename T, int V, int MODE, int ACT, int U>
 __global__ void __launch_bounds__(256) iqbn_reduce_b(const T* __restrict__ x, const T* __restrict__ dy, GeomB g,
                                                      const float* __restrict__ gamma,
                                                      const float* __restrict__ beta, IqbnWs ws, TailArgs tail) {
@@ -138,51 +145,71 @@ __global__ void __launch_bounds__(256) iqbn_reduce_b(const T* __restrict__ x, co
   for (int i = 0; i < V; ++i) s0[i] = s1[i] = k[i] = 0.f;
 
   const int64_t rstride = (int64_t)gridDim.x * g.rpb;
-  for (int64_t r = (int64_t)blockIdx.x * g.rpb + rl; r < g.R; r += rstride) {
-    const int64_t off = r * g.L + (int64_t)cv * V;
-    float xv[V];
-    load_vec<T, V>(x + off, xv);
-    if constexpr (MODE == 0) {
-      if (cnt == 0) {
+  const int64_t coloff = (int64_t)cv * V;
+  for (int64_t r = (int64_t)blockIdx.x * g.rpb + rl; r < g.R; r += rstride * U) {
+    float xv[U][V], gv[U][V];
 #pragma unroll
-        for (int i = 0; i < V; ++i) k[i] = xv[i];  // local shift: keeps fp32 partials well conditioned
-      }
-#pragma unroll
-      for (int i = 0; i < V; ++i) {
-        float d = xv[i] - k[i];
-        s0[i] += d;
-        s1[i] = fmaf(d, d, s1[i]);
-      }
-    } else {
-      float gv[V];
-      load_vec<T, V>(dy + off, gv);
-#pragma unroll
-      for (int i = 0; i < V; ++i) {
-        float dz = gv[i];
-        if constexpr (ACT != QUAN_ACT_NONE) dz *= act_grad<ACT>(fmaf(xv[i], scale[i], shift[i]));
-        s0[i] += dz;
-        s1[i] = fmaf(dz, xv[i], s1[i]);
+    for (int u = 0; u < U; ++u) {
+      const int64_t rr = r + u * rstride;
+      if (rr < g.R) {
+        load_vec<T, V>(x + rr * g.L + coloff, xv[u]);
+        if constexpr (MODE == 1) load_vec<T, V>(dy + rr * g.L + coloff, gv[u]);
       }
     }
-    ++cnt;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t rr = r + u * rstride;
+      if (rr < g.R) {
+        if constexpr (MODE == 0) {
+          if (cnt == 0) {
+#pragma unroll
+            for (int i = 0; i < V; ++i) k[i] = xv[u][i];  // local shift: keeps fp32 partials well conditioned
+          }
+#pragma unroll
+          for (int i = 0; i < V; ++i) {
+            float d = xv[u][i] - k[i];
+            s0[i] += d;
+            s1[i] = fmaf(d, d, s1[i]);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < V; ++i) {
+            float dz = gv[u][i];
+            if constexpr (ACT != QUAN_ACT_NONE) dz *= act_grad<ACT>(fmaf(xv[u][i], scale[i], shift[i]));
+            s0[i] += dz;
+            s1[i] = fmaf(dz, xv[u][i], s1[i]);
+          }
+        }
+        ++cnt;
+      }
+    }
   }
 
-  if (cnt > 0) {
-    const int n = 4 * g.C;
+  // thread partials -> fp64 raw sums -> shared memory; row lane 0 of every column vector folds the other lanes and
+  // issues the block's single atomic per accumulator
+  extern __shared__ double red[];   // [blockDim.x][2V]
+  double* mine = red + (size_t)threadIdx.x * (2 * V);
 #pragma unroll
-    for (int i = 0; i < V; ++i) {
-      double a0, a1;
-      if constexpr (MODE == 0) {  // un-shift in fp64: sum x = sum d + n k ; sum x^2 = sum d^2 + 2k sum d + n k^2
-        double kd = (double)k[i], nd = (double)cnt;
-        a0 = (double)s0[i] + nd * kd;
-        a1 = (double)s1[i] + 2.0 * kd * (double)s0[i] + nd * kd * kd;
-      } else {
-        a0 = (double)s0[i];
-        a1 = (double)s1[i];
-      }
-      atomicAdd(ws.acc + pidx[i], a0);
-      atomicAdd(ws.acc + n + pidx[i], a1);
+  for (int i = 0; i < V; ++i) {
+    if constexpr (MODE == 0) {  // un-shift in fp64: sum x = sum d + n k ; sum x^2 = sum d^2 + 2k sum d + n k^2
+      double kd = (double)k[i], nd = (double)cnt;
+      mine[2 * i] = (double)s0[i] + nd * kd;
+      mine[2 * i + 1] = (double)s1[i] + 2.0 * kd * (double)s0[i] + nd * kd * kd;
+    } else {
+      mine[2 * i] = (double)s0[i];
+      mine[2 * i + 1] = (double)s1[i];
     }
+  }
+  __syncthreads();
+  // 2V values per column vector, cvpg column vectors: spread the folding over all threads of the block
+  const int nval = g.cvpg * 2 * V;
+  for (int e = threadIdx.x; e < nval; e += blockDim.x) {
+    const int c_v = e / (2 * V), j = e - c_v * (2 * V);      // column vector, value index (2*i + which)
+    double acc = 0.0;
+    for (int l = 0; l < g.rpb; ++l) acc += red[(size_t)(l * g.cvpg + c_v) * (2 * V) + j];
+    const int col = (blockIdx.y * g.cvpg + c_v) * V + (j >> 1);
+    const int q = col / g.C, c = col - q * g.C;
+    atomicAdd(ws.acc + (j & 1) * 4 * g.C + c * 4 + q, acc);
   }
   if (last_block_arrive(ws.counter)) tail_finalize(tail, ws.acc);
 }
@@ -250,7 +277,7 @@ __device__ __forceinline__ void write_param_grads(const ApplyArgs& a) {
   }
 }
 
-template <typename T, int V, int ACT, bool BWD>
+template <typename T, int V, int ACT, bool BWD, int U>
 __global__ void __launch_bounds__(256) iqbn_apply_b(const T* __restrict__ x, const T* __restrict__ dy,
                                                     T* __restrict__ out, GeomB g, ApplyArgs a) {
   const int cvl = threadIdx.x % g.cvpg;
@@ -267,24 +294,36 @@ __global__ void __launch_bounds__(256) iqbn_apply_b(const T* __restrict__ x, con
   if constexpr (BWD) write_param_grads(a);
 
   const int64_t rstride = (int64_t)gridDim.x * g.rpb;
-  for (int64_t r = (int64_t)blockIdx.x * g.rpb + rl; r < g.R; r += rstride) {
-    const int64_t off = r * g.L + (int64_t)cv * V;
-    float xv[V], ov[V];
-    load_vec<T, V>(x + off, xv);
-    if constexpr (!BWD) {
+  const int64_t coloff = (int64_t)cv * V;
+  for (int64_t r = (int64_t)blockIdx.x * g.rpb + rl; r < g.R; r += rstride * U) {
+    float xv[U][V], gv[U][V];
 #pragma unroll
-      for (int i = 0; i < V; ++i) ov[i] = act_fwd<ACT>(fmaf(xv[i], scale[i], shift[i]));
-    } else {
-      float gv[V];
-      load_vec<T, V>(dy + off, gv);
-#pragma unroll
-      for (int i = 0; i < V; ++i) {
-        float dz = gv[i];
-        if constexpr (ACT != QUAN_ACT_NONE) dz *= act_grad<ACT>(fmaf(xv[i], scale[i], shift[i]));
-        ov[i] = fmaf(k1[i], dz, fmaf(k2[i], xv[i], k3[i]));
+    for (int u = 0; u < U; ++u) {
+      const int64_t rr = r + u * rstride;
+      if (rr < g.R) {
+        load_vec<T, V>(x + rr * g.L + coloff, xv[u]);
+        if constexpr (BWD) load_vec<T, V>(dy + rr * g.L + coloff, gv[u]);
       }
     }
-    store_vec<T, V>(out + off, ov);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t rr = r + u * rstride;
+      if (rr < g.R) {
+        float ov[V];
+        if constexpr (!BWD) {
+#pragma unroll
+          for (int i = 0; i < V; ++i) ov[i] = act_fwd<ACT>(fmaf(xv[u][i], scale[i], shift[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < V; ++i) {
+            float dz = gv[u][i];
+            if constexpr (ACT != QUAN_ACT_NONE) dz *= act_grad<ACT>(fmaf(xv[u][i], scale[i], shift[i]));
+            ov[i] = fmaf(k1[i], dz, fmaf(k2[i], xv[u][i], k3[i]));
+          }
+        }
+        store_vec<T, V>(out + rr * g.L + coloff, ov);
+      }
+    }
   }
 }
 
@@ -433,29 +472,33 @@ struct LaunchB {
   int V;
 };
 
+// Tuning overrides (bring-up only): QUAN_IQBN_BPS = blocks per SM for the BHWQC kernels, QUAN_IQBN_U = rows in flight.
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
 template <typename T>
-static bool plan_b(int B, int C, int H, int W, int vcap, LaunchB& p) {
-  int vmax = VecTraits<T>::kMaxVec < vcap ? VecTraits<T>::kMaxVec : vcap;
-  p.V = largest_pow2_divisor(C, vmax);
-  int colvecs = 4 * C / p.V;
-  int cg = (colvecs + 255) / 256;
+static bool plan_b(int B, int C, int H, int W, int unroll, int blocks_per_sm, LaunchB& p) {
+  blocks_per_sm = env_int("QUAN_IQBN_BPS", blocks_per_sm);
+  p.V = largest_pow2_divisor(C, VecTraits<T>::kMaxVec);
+  const int colvecs = 4 * C / p.V;
+  int cg = (colvecs + 255) / 256;                   // column groups (wide rows only)
   while (colvecs % cg) ++cg;
-  int cvpg = colvecs / cg;
-  if (cvpg > 256) return false;
-  int rpb = 256 / cvpg;
+  const int cvpg = colvecs / cg;
+  if (cvpg > 256 || cg > 65535) return false;
+  const int rpb = 256 / cvpg;
   p.g.R = (int64_t)B * H * W;
   p.g.L = 4 * C;
   p.g.C = C;
   p.g.cvpg = cvpg;
   p.g.rpb = rpb;
   p.block = dim3(rpb * cvpg);
-  int64_t row_blocks = ceil_div64(p.g.R, rpb);
-  int64_t cap = (int64_t)QUAN_NUM_SMS * 8 / cg;
-  if (cap < 1) cap = 1;
-  // >= 2 rows per thread keeps loads in flight; small problems just get fewer blocks
-  int64_t want = ceil_div64(row_blocks, 2);
+  int64_t want = ceil_div64(p.g.R, (int64_t)rpb * unroll);
+  int64_t cap = ceil_div64((int64_t)QUAN_NUM_SMS * blocks_per_sm, cg);
   if (want < 1) want = 1;
-  p.grid = dim3((unsigned)(want < cap ? want : cap), cg);
+  if (cap < 1) cap = 1;
+  p.grid = dim3((unsigned)(want < cap ? want : cap), (unsigned)cg);
   return true;
 }
 
@@ -497,16 +540,14 @@ static int launch_reduce(const void* x, const void* dy, int B, int C, int H, int
   const T* dyp = reinterpret_cast<const T*>(dy);
   if (layout == QUAN_LAYOUT_BHWQC && C > 1) {
     LaunchB p;
-    // bwd-reduce keeps scale/shift + two accumulators per lane element: cap V at 4 to stay under 128 registers
-    if (!plan_b<T>(B, C, H, W, MODE == 1 ? 4 : 8, p)) {
+    constexpr int U = MODE == 1 ? 4 : 8;   // rows in flight per thread (two tensors are streamed in MODE 1)
+    if (!plan_b<T>(B, C, H, W, U, 2, p)) {
       set_error("iqbn: C=%d too large for the BHWQC kernels", C);
       return QUAN_E_UNSUPPORTED;
     }
-    if constexpr (sizeof(T) == 4) {
-      if (p.V == 8) p.V = 4;
-    }
-    QUAN_DISPATCH_V(p.V, (iqbn_reduce_b<T, (sizeof(T) == 4 && kV == 8) ? 4 : kV, MODE, ACT>
-                          <<<p.grid, p.block, 0, st>>>(xp, dyp, p.g, gamma, beta, ws, tail)));
+    QUAN_DISPATCH_V(p.V, (iqbn_reduce_b<T, (sizeof(T) == 4 && kV == 8) ? 4 : kV, MODE, ACT, U>
+                          <<<p.grid, p.block, (size_t)p.block.x * 2 * kV * sizeof(double), st>>>(xp, dyp, p.g, gamma, beta,
+                                                                                                  ws, tail)));
   } else {
     LaunchA p;
     plan_a<T>(B, C, H, W, p);
@@ -529,12 +570,22 @@ static int launch_apply(const void* x, const void* dy, void* out, int B, int C, 
   T* op = reinterpret_cast<T*>(out);
   if (layout == QUAN_LAYOUT_BHWQC && C > 1) {
     LaunchB p;
-    if (!plan_b<T>(B, C, H, W, BWD ? 4 : 8, p)) {
+    // measured on B200 (profiles/r01_iqbn_tune.log): the per-thread coefficient prologue makes many light blocks lose to
+    // few blocks; U = 1 with 4 (fwd) / 2 (bwd) blocks per SM is the best point of the sweep
+    const int U = env_int("QUAN_IQBN_U", 1);
+    if (!plan_b<T>(B, C, H, W, U, BWD ? 2 : 4, p)) {
       set_error("iqbn: C=%d too large for the BHWQC kernels", C);
       return QUAN_E_UNSUPPORTED;
     }
-    QUAN_DISPATCH_V(p.V, (iqbn_apply_b<T, (sizeof(T) == 4 && kV == 8) ? 4 : kV, ACT, BWD>
-                          <<<p.grid, p.block, 0, st>>>(xp, dyp, op, p.g, a)));
+#define QUAN_APPLY_B(UU) QUAN_DISPATCH_V(p.V, (iqbn_apply_b<T, (sizeof(T) == 4 && kV == 8) ? 4 : kV, ACT, BWD, UU> \
+                          <<<p.grid, p.block, 0, st>>>(xp, dyp, op, p.g, a)))
+    switch (U) {
+      case 1: QUAN_APPLY_B(1); break;
+      case 2: QUAN_APPLY_B(2); break;
+      case 8: QUAN_APPLY_B(8); break;
+      default: QUAN_APPLY_B(4); break;
+    }
+#undef QUAN_APPLY_B
     QUAN_CHECK_LAUNCH("iqbn_apply_b");
     if (BWD && mix_t != nullptr) {  // G = M^T dY for the producing QConv2D: second in-place pass in this layout
       int rc = quan_mix(out, out, B, C, H, W, sizeof(T) == 4 ? QUAN_F32 : QUAN_BF16, layout, mix_t, st);

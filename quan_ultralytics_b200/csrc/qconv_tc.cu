@@ -154,46 +154,56 @@ qconv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 
   const int taps = p.kH * p.kW;
   const int iters_per_q = taps * p.kblocks;
-  const int total_iters = 4 * iters_per_q;
 
   if (warp == 0) {
-    // ===== TMA producer (one lane) =====
+    // ===== TMA producer (one lane).  Nested counters instead of div/mod: this single thread's instruction stream is
+    // on the critical path of every pipeline stage (first ncu capture: ~170 scalar instructions per stage, mostly
+    // integer division, made the kernel issue-bound at 27% tensor-pipe activity). =====
     if (lane == 0) {
       const uint32_t tx = p.a_stage_bytes + p.b_stage_bytes;
-      for (int it = 0; it < total_iters; ++it) {
-        const int s = it % p.stages;
-        const uint32_t phase = (it / p.stages) & 1;
-        ptx::mbar_wait(empty_bar + s, phase ^ 1);
-        const int q = it / iters_per_q;
-        const int r = it - q * iters_per_q;
-        const int tap = r / p.kblocks, kb = r - tap * p.kblocks;
-        const int kh = tap / p.kW, kw = tap - kh * p.kW;
-        ptx::mbar_arrive_expect_tx(full_bar + s, tx);
-        ptx::tma_load_5d(smem_a + (size_t)s * p.a_stage_bytes, &map_a, full_bar + s, kb * p.bk_elems, q,
-                         w0 * p.sW - p.pW + kw * p.dW, h0 * p.sH - p.pH + kh * p.dH, b0);
-        ptx::tma_load_4d(smem_b + (size_t)s * p.b_stage_bytes, &map_b, full_bar + s, kb * p.bk_elems, n0, tap, q);
+      const int wbase = w0 * p.sW - p.pW, hbase = h0 * p.sH - p.pH;
+      int s = 0;
+      uint32_t phase = 0;
+      for (int q = 0; q < 4; ++q) {
+        int tap = 0;
+        for (int kh = 0; kh < p.kH; ++kh) {
+          const int hc = hbase + kh * p.dH;
+          for (int kw = 0; kw < p.kW; ++kw, ++tap) {
+            const int wc = wbase + kw * p.dW;
+            for (int kb = 0; kb < p.kblocks; ++kb) {
+              ptx::mbar_wait(empty_bar + s, phase ^ 1);
+              ptx::mbar_arrive_expect_tx(full_bar + s, tx);
+              ptx::tma_load_5d(smem_a + (size_t)s * p.a_stage_bytes, &map_a, full_bar + s, kb * p.bk_elems, q, wc, hc, b0);
+              ptx::tma_load_4d(smem_b + (size_t)s * p.b_stage_bytes, &map_b, full_bar + s, kb * p.bk_elems, n0, tap, q);
+              if (++s == p.stages) { s = 0; phase ^= 1; }
+            }
+          }
+        }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer (one lane) =====
     if (lane == 0) {
-      for (int it = 0; it < total_iters; ++it) {
-        const int s = it % p.stages;
-        const uint32_t phase = (it / p.stages) & 1;
-        ptx::mbar_wait(full_bar + s, phase);
-        ptx::tc_fence_after();
-        const int q = it / iters_per_q;
-        const bool first = (it - q * iters_per_q) == 0;
-        const uint32_t a_addr = ptx::smem_u32(smem_a + (size_t)s * p.a_stage_bytes);
-        const uint32_t b_addr = ptx::smem_u32(smem_b + (size_t)s * p.b_stage_bytes);
-        const uint64_t da = ptx::make_smem_desc(a_addr, 16, p.sbo_bytes, p.layout_type);
-        const uint64_t db = ptx::make_smem_desc(b_addr, 16, p.sbo_bytes, p.layout_type);
+      const uint64_t da0 = ptx::make_smem_desc(ptx::smem_u32(smem_a), 16, p.sbo_bytes, p.layout_type);
+      const uint64_t db0 = ptx::make_smem_desc(ptx::smem_u32(smem_b), 16, p.sbo_bytes, p.layout_type);
+      const uint64_t a_step = (uint64_t)(p.a_stage_bytes >> 4), b_step = (uint64_t)(p.b_stage_bytes >> 4);
+      int s = 0;
+      uint32_t phase = 0;
+      uint64_t da = da0, db = db0;
+      for (int q = 0; q < 4; ++q) {
         const uint32_t d_tmem = tmem_base + (uint32_t)(q * p.BN);
-        for (int k = 0; k < p.ksteps; ++k) {
-          // advance 32 bytes (one UMMA_K slice) inside the swizzle row: +2 in the 16-byte-unit start-address field
-          ptx::umma<KIND>(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (first && k == 0) ? 0u : 1u);
+        for (int i = 0; i < iters_per_q; ++i) {
+          ptx::mbar_wait(full_bar + s, phase);
+          ptx::tc_fence_after();
+          for (int k = 0; k < p.ksteps; ++k) {
+            // advance 32 bytes (one UMMA_K slice) inside the swizzle row: +2 in the 16-byte-unit start-address field
+            ptx::umma<KIND>(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (i | k) ? 1u : 0u);
+          }
+          ptx::umma_commit(empty_bar + s);   // frees the smem slot once these MMAs have read it
+          da += a_step;
+          db += b_step;
+          if (++s == p.stages) { s = 0; phase ^= 1; da = da0; db = db0; }
         }
-        ptx::umma_commit(empty_bar + s);   // frees the smem slot once these MMAs have read it
       }
       ptx::umma_commit(tmem_full_bar);     // all four accumulators complete
     }
@@ -325,44 +335,50 @@ qconv_wgrad_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_const
   if (warp == 0) {
     if (lane == 0) {
       const uint32_t tx = p.a_stage_bytes + p.b_stage_bytes;
+      // chunk -> (tb, th, tw) once, then incrementally (no div/mod on the producer's critical path)
+      int tw = chunk0 % p.tiles_w;
+      int th = (chunk0 / p.tiles_w) % p.tiles_h;
+      int tb = chunk0 / (p.tiles_w * p.tiles_h);
+      int s = 0;
+      uint32_t phase = 0;
       for (int it = 0; it < nch; ++it) {
-        const int s = it % p.stages;
-        const uint32_t phase = (it / p.stages) & 1;
         ptx::mbar_wait(empty_bar + s, phase ^ 1);
-        const int chunk = chunk0 + it;
-        const int tw = chunk % p.tiles_w;
-        const int th = (chunk / p.tiles_w) % p.tiles_h;
-        const int tb = chunk / (p.tiles_w * p.tiles_h);
         const int w0 = tw * p.Wt, h0 = th * p.Ht, b0 = tb * p.Bt;
         ptx::mbar_arrive_expect_tx(full_bar + s, tx);
         uint8_t* a_dst = smem_a + (size_t)s * p.a_stage_bytes;
         for (int a = 0; a < p.MA; ++a)
           ptx::tma_load_5d(a_dst + (size_t)a * p.atom_bytes, &map_g, full_bar + s, co0 + a * p.NA, q, w0, h0, b0);
         uint8_t* b_dst = smem_b + (size_t)s * p.b_stage_bytes;
+        const int wc = w0 * p.sW - p.pW, hc = h0 * p.sH - p.pH + kh * p.dH;
         for (int t = 0; t < p.TG; ++t)
-          ptx::tma_load_5d(b_dst + (size_t)t * p.atom_bytes, &map_x, full_bar + s, ci0, q, w0 * p.sW - p.pW + t * p.dW,
-                           h0 * p.sH - p.pH + kh * p.dH, b0);
+          ptx::tma_load_5d(b_dst + (size_t)t * p.atom_bytes, &map_x, full_bar + s, ci0, q, wc + t * p.dW, hc, b0);
+        if (++s == p.stages) { s = 0; phase ^= 1; }
+        if (++tw == p.tiles_w) { tw = 0; if (++th == p.tiles_h) { th = 0; ++tb; } }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
+      // MN-major, 128B swizzle: LBO = distance between 128-byte column atoms, SBO = one K-row group
+      const uint64_t da0 = ptx::make_smem_desc(ptx::smem_u32(smem_a), p.atom_bytes, p.sbo_bytes, p.layout_type);
+      const uint64_t db0 = ptx::make_smem_desc(ptx::smem_u32(smem_b), p.atom_bytes, p.sbo_bytes, p.layout_type);
+      const uint64_t a_step = (uint64_t)(p.a_stage_bytes >> 4), b_step = (uint64_t)(p.b_stage_bytes >> 4);
+      const uint64_t atom_step = (uint64_t)(p.atom_bytes >> 4);
+      int s = 0;
+      uint32_t phase = 0;
+      uint64_t da = da0, db = db0;
       for (int it = 0; it < nch; ++it) {
-        const int s = it % p.stages;
-        const uint32_t phase = (it / p.stages) & 1;
         ptx::mbar_wait(full_bar + s, phase);
         ptx::tc_fence_after();
-        const uint32_t a_addr = ptx::smem_u32(smem_a + (size_t)s * p.a_stage_bytes);
-        const uint32_t b_addr = ptx::smem_u32(smem_b + (size_t)s * p.b_stage_bytes);
-        // MN-major, 128B swizzle: LBO = distance between 128-byte column atoms, SBO = one K-row group
-        const uint64_t da = ptx::make_smem_desc(a_addr, p.atom_bytes, p.sbo_bytes, p.layout_type);
-        for (int t = 0; t < p.TG; ++t) {
-          const uint64_t db = ptx::make_smem_desc(b_addr + (uint32_t)t * p.atom_bytes, p.atom_bytes, p.sbo_bytes, p.layout_type);
+        uint64_t dbt = db;
+        for (int t = 0; t < p.TG; ++t, dbt += atom_step) {
           const uint32_t d_tmem = tmem_base + (uint32_t)(t * p.NA);
           for (int k = 0; k < p.ksteps; ++k)
-            ptx::umma<KIND>(d_tmem, da + (uint64_t)(k * p.kadv), db + (uint64_t)(k * p.kadv), p.idesc,
-                            (it == 0 && k == 0) ? 0u : 1u);
+            ptx::umma<KIND>(d_tmem, da + (uint64_t)(k * p.kadv), dbt + (uint64_t)(k * p.kadv), p.idesc, (it | k) ? 1u : 0u);
         }
         ptx::umma_commit(empty_bar + s);
+        da += a_step;
+        db += b_step;
+        if (++s == p.stages) { s = 0; phase ^= 1; da = da0; db = db0; }
       }
       ptx::umma_commit(tmem_full_bar);
     }
