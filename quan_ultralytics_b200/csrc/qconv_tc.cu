@@ -17,6 +17,7 @@
 #include "qconv_internal.cuh"
 #include "tc_ptx.cuh"
 #include <mutex>
+#include <stdlib.h>
 
 namespace quan {
 
@@ -102,30 +103,46 @@ struct TcConvParams {
   int B, Ho, Wo, Cout;                 // output tensor [B][Ho][Wo][4][Cout]
   int Wt, Ht, Bt, tiles_w, tiles_h;    // 128-pixel tile = Bt x Ht x Wt (w fastest), tiles per image plane
   int kH, kW, sH, sW, pH, pW, dH, dW;
-  int kblocks, bk_elems, ksteps;       // k-blocks per tap, elements per k-block row, UMMAs per stage
+  int kblocks, bk_elems;               // k-blocks per tap, elements per k-block row
+  int sub;                             // (tap, k-block) sub-steps bundled into one pipeline stage (1 or 2)
   int BN, stages;
-  uint32_t a_stage_bytes, b_stage_bytes, sbo_bytes, layout_type, idesc, tmem_cols;
+  uint32_t a_sub_bytes, b_sub_bytes;   // one sub-step's A / B tile (per CTA)
+  uint32_t sbo_bytes, layout_type, idesc, tmem_cols;
   const float* bias;                   // [Cout] or null (joins S_r before the mix)
   Mix16 mix;
 };
 
 constexpr int TC_THREADS = 192;   // warp 0: TMA producer, warp 1: TMEM alloc + MMA issuer, warps 2-5: epilogue
 
-template <typename T, bool MIX>
+// CG = 1: one CTA per 128-pixel tile.  CG = 2: a CTA pair (cluster of 2) drives tcgen05.mma.cta_group::2 — M = 256
+// (each CTA's own 128-pixel A tile), the BN x BK weight tile is split in halves between the two CTAs' shared memory, so
+// per-CTA L2->SM and SM-local operand traffic drop from (A + B) to (A + B/2) per step.
+// KSTEPS = UMMAs per sub-step (row bytes / 32), compile time so the issue sequence is branch-free.
+//
+// What bounds this kernel (clock64 / debug-switch experiments on B200, profiles/r01_conv_issue_experiments.md): not the
+// loads (removing every TMA changes nothing) but the MMA-issuing thread — a UTCHMMA M128 N128 K16 holds the issuing
+// thread for about its 64-cycle execution time, so the tensor pipe is busy only while that thread issues, and every
+// other cycle of its loop iteration (barrier wait, commit, bookkeeping: ~250 cycles) is tensor idle time.  Hence
+// (1) role loops are warp-uniform with `elect.sync` around the single-thread instructions (a divergent `lane == 0`
+// loop makes the compiler re-uniformise each UTCHMMA operand: +70 cycles per MMA), and (2) a pipeline stage bundles
+// `sub` (tap, k-block) steps, i.e. 8 MMAs per barrier round trip instead of 4.
+template <typename T, bool MIX, int CG, int KSTEPS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 qconv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, T* __restrict__ y,
                    const TcConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment is required by the 128B swizzle atoms
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t a_stage_bytes = p.a_sub_bytes * p.sub, b_stage_bytes = p.b_sub_bytes * p.sub;
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + (size_t)p.stages * p.a_stage_bytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + (size_t)p.stages * p.b_stage_bytes);
+  uint8_t* smem_b = smem + (size_t)p.stages * a_stage_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + (size_t)p.stages * b_stage_bytes);
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* tmem_full_bar = empty_bar + p.stages;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform
+  const int lane = threadIdx.x & 31;
   constexpr int KIND = sizeof(T) == 2 ? 0 : 1;
 
   // tile coordinates
@@ -135,6 +152,7 @@ qconv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   const int tb = tile / (p.tiles_w * p.tiles_h);
   const int w0 = tw * p.Wt, h0 = th * p.Ht, b0 = tb * p.Bt;
   const int n0 = blockIdx.y * p.BN;
+  const uint32_t cta_rank = CG == 2 ? ptx::cluster_ctarank() : 0u;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&map_a);
@@ -146,66 +164,97 @@ qconv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     ptx::mbar_init(tmem_full_bar, 1);
     ptx::fence_barrier_init();
   }
-  if (warp == 1) ptx::tmem_alloc(tmem_ptr, p.tmem_cols);
+  if (warp == 1) {
+    if constexpr (CG == 2) ptx::tmem_alloc_2cta(tmem_ptr, p.tmem_cols);
+    else ptx::tmem_alloc(tmem_ptr, p.tmem_cols);
+  }
   ptx::tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) ptx::cluster_sync_all();   // peer's barriers must be initialised before anything signals them
+  else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
   const int taps = p.kH * p.kW;
-  const int iters_per_q = taps * p.kblocks;
+  const int iters_per_q = taps * p.kblocks;          // (tap, k-block) steps per component
 
   if (warp == 0) {
-    // ===== TMA producer (one lane).  Nested counters instead of div/mod: this single thread's instruction stream is
-    // on the critical path of every pipeline stage (first ncu capture: ~170 scalar instructions per stage, mostly
-    // integer division, made the kernel issue-bound at 27% tensor-pipe activity). =====
-    if (lane == 0) {
-      const uint32_t tx = p.a_stage_bytes + p.b_stage_bytes;
-      const int wbase = w0 * p.sW - p.pW, hbase = h0 * p.sH - p.pH;
-      int s = 0;
-      uint32_t phase = 0;
-      for (int q = 0; q < 4; ++q) {
-        int tap = 0;
-        for (int kh = 0; kh < p.kH; ++kh) {
-          const int hc = hbase + kh * p.dH;
-          for (int kw = 0; kw < p.kW; ++kw, ++tap) {
-            const int wc = wbase + kw * p.dW;
-            for (int kb = 0; kb < p.kblocks; ++kb) {
-              ptx::mbar_wait(empty_bar + s, phase ^ 1);
-              ptx::mbar_arrive_expect_tx(full_bar + s, tx);
-              ptx::tma_load_5d(smem_a + (size_t)s * p.a_stage_bytes, &map_a, full_bar + s, kb * p.bk_elems, q, wc, hc, b0);
-              ptx::tma_load_4d(smem_b + (size_t)s * p.b_stage_bytes, &map_b, full_bar + s, kb * p.bk_elems, n0, tap, q);
-              if (++s == p.stages) { s = 0; phase ^= 1; }
+    // ===== TMA producer: warp-uniform loop; one elected lane issues.  Counters instead of div/mod. =====
+    const uint32_t sub_tx = (p.a_sub_bytes + p.b_sub_bytes) * CG;   // CG = 2: the leader's barrier counts both CTAs' bytes
+    const int wbase = w0 * p.sW - p.pW, hbase = h0 * p.sH - p.pH;
+    const int nb0 = n0 + (int)cta_rank * (p.BN / CG);               // this CTA's slice of the weight tile
+    int s = 0;
+    uint32_t phase = 0;
+    for (int q = 0; q < 4; ++q) {
+      int tap = 0, kh = 0, kw = 0, kb = 0;
+      for (int i = 0; i < iters_per_q; i += p.sub) {
+        const int nsub = min(p.sub, iters_per_q - i);
+        ptx::mbar_wait(empty_bar + s, phase ^ 1);
+        const bool leader = ptx::elect_one();
+        if (leader && (CG == 1 || cta_rank == 0)) ptx::mbar_arrive_expect_tx(full_bar + s, sub_tx * nsub);
+        for (int u = 0; u < nsub; ++u) {
+          if (leader) {
+            uint8_t* a_dst = smem_a + (size_t)s * a_stage_bytes + (size_t)u * p.a_sub_bytes;
+            uint8_t* b_dst = smem_b + (size_t)s * b_stage_bytes + (size_t)u * p.b_sub_bytes;
+            const int wc = wbase + kw * p.dW, hc = hbase + kh * p.dH, kc = kb * p.bk_elems;
+            if constexpr (CG == 2) {
+              ptx::tma_load_5d_2cta(a_dst, &map_a, full_bar + s, kc, q, wc, hc, b0);
+              ptx::tma_load_4d_2cta(b_dst, &map_b, full_bar + s, kc, nb0, tap, q);
+            } else {
+              ptx::tma_load_5d(a_dst, &map_a, full_bar + s, kc, q, wc, hc, b0);
+              ptx::tma_load_4d(b_dst, &map_b, full_bar + s, kc, n0, tap, q);
             }
           }
+          if (++kb == p.kblocks) { kb = 0; ++tap; if (++kw == p.kW) { kw = 0; ++kh; } }
         }
+        __syncwarp();
+        if (++s == p.stages) { s = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (one lane) =====
-    if (lane == 0) {
+    // ===== MMA issuer: warp-uniform loop; one elected lane issues (with CG = 2 only in the pair's leader CTA) =====
+    if (cta_rank == 0) {
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint64_t da0 = ptx::make_smem_desc(ptx::smem_u32(smem_a), 16, p.sbo_bytes, p.layout_type);
       const uint64_t db0 = ptx::make_smem_desc(ptx::smem_u32(smem_b), 16, p.sbo_bytes, p.layout_type);
-      const uint64_t a_step = (uint64_t)(p.a_stage_bytes >> 4), b_step = (uint64_t)(p.b_stage_bytes >> 4);
+      const uint64_t a_step = (uint64_t)(a_stage_bytes >> 4), b_step = (uint64_t)(b_stage_bytes >> 4);
+      const uint64_t a_sub = (uint64_t)(p.a_sub_bytes >> 4), b_sub = (uint64_t)(p.b_sub_bytes >> 4);
       int s = 0;
       uint32_t phase = 0;
       uint64_t da = da0, db = db0;
       for (int q = 0; q < 4; ++q) {
-        const uint32_t d_tmem = tmem_base + (uint32_t)(q * p.BN);
-        for (int i = 0; i < iters_per_q; ++i) {
+        const uint32_t d_tmem = tmem_u + (uint32_t)(q * p.BN);
+        for (int i = 0; i < iters_per_q; i += p.sub) {
+          const int nsub = min(p.sub, iters_per_q - i);
           ptx::mbar_wait(full_bar + s, phase);
           ptx::tc_fence_after();
-          for (int k = 0; k < p.ksteps; ++k) {
-            // advance 32 bytes (one UMMA_K slice) inside the swizzle row: +2 in the 16-byte-unit start-address field
-            ptx::umma<KIND>(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), p.idesc, (i | k) ? 1u : 0u);
+          if (ptx::elect_one()) {
+            for (int u = 0; u < nsub; ++u) {
+              const uint64_t dau = da + (uint64_t)u * a_sub, dbu = db + (uint64_t)u * b_sub;
+#pragma unroll
+              for (int k = 0; k < KSTEPS; ++k) {
+                // advance 32 bytes (one UMMA_K slice) inside the swizzle row: +2 in the 16-byte-unit start-address field
+                if constexpr (CG == 2)
+                  ptx::umma_2cta<KIND>(d_tmem, dau + (uint64_t)(2 * k), dbu + (uint64_t)(2 * k), p.idesc, (i | u | k) ? 1u : 0u);
+                else
+                  ptx::umma<KIND>(d_tmem, dau + (uint64_t)(2 * k), dbu + (uint64_t)(2 * k), p.idesc, (i | u | k) ? 1u : 0u);
+              }
+            }
+            // frees the smem slot (in both CTAs when CG = 2) once these MMAs have read it
+            if constexpr (CG == 2) ptx::umma_commit_2cta(empty_bar + s, 3);
+            else ptx::umma_commit(empty_bar + s);
           }
-          ptx::umma_commit(empty_bar + s);   // frees the smem slot once these MMAs have read it
+          __syncwarp();
           da += a_step;
           db += b_step;
           if (++s == p.stages) { s = 0; phase ^= 1; da = da0; db = db0; }
         }
       }
-      ptx::umma_commit(tmem_full_bar);     // all four accumulators complete
+      // all four accumulators complete
+      if (ptx::elect_one()) {
+        if constexpr (CG == 2) ptx::umma_commit_2cta(tmem_full_bar, 3);
+        else ptx::umma_commit(tmem_full_bar);
+      }
+      __syncwarp();
     }
   } else {
     // ===== epilogue: warps 2..5 own TMEM lane quarters (warp % 4) =====
@@ -253,13 +302,14 @@ qconv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     }
     ptx::tc_fence_before();
   }
-  __syncthreads();
+  if constexpr (CG == 2) ptx::cluster_sync_all();   // neither CTA may release TMEM / exit while the pair is still using it
+  else __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, p.tmem_cols);
+    if constexpr (CG == 2) ptx::tmem_dealloc_2cta(tmem_base, p.tmem_cols);
+    else ptx::tmem_dealloc(tmem_base, p.tmem_cols);
   }
 }
-
 
 // ---------------------------------------------------------------------------------------------------------------
 // wgrad kernel:  dW_q[co][ci][tap] = sum_pixels G_q[pix][co] * x_q[pix (+) tap][ci]
@@ -274,7 +324,8 @@ struct TcWgradParams {
   int kH, kW, sH, sW, pH, pW, dH, dW;
   int Co, Ci, taps;
   int TG;                      // taps per CTA (= kW)
-  int NA;                      // ci elements per CTA (one 128-byte atom)
+  int NA;                      // channels per 128-byte atom
+  int NB;                      // ci atoms per CTA: N = NB * NA
   int MA;                      // co atoms per CTA (M = 128 -> 128*es/128)
   int co_blocks, ci_blocks, tap_groups;
   int chunks_per_split;
@@ -289,7 +340,7 @@ struct TcWgradParams {
 
 constexpr int WG_PIX = 64;     // pixels (K) per pipeline stage
 
-template <typename T>
+template <typename T, int KSTEPS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 qconv_wgrad_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant__ CUtensorMap map_x, const TcWgradParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -300,8 +351,10 @@ qconv_wgrad_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_const
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* tmem_full_bar = empty_bar + p.stages;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform
+  const int lane = threadIdx.x & 31;
   constexpr int KIND = sizeof(T) == 2 ? 0 : 1;
+  const int N = p.NB * p.NA;
 
   // work decomposition
   int combo = blockIdx.y;
@@ -313,7 +366,7 @@ qconv_wgrad_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_const
   const int chunk0 = split * p.chunks_per_split;
   const int chunk1 = min(chunk0 + p.chunks_per_split, p.nchunks);
   const int nch = chunk1 - chunk0;
-  const int co0 = mb * 128, ci0 = nb * p.NA;
+  const int co0 = mb * 128, ci0 = nb * N;
   const int kh = tg;   // tap group = one filter row
 
   if (warp == 0 && lane == 0) {
@@ -333,16 +386,17 @@ qconv_wgrad_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_const
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
-    if (lane == 0) {
-      const uint32_t tx = p.a_stage_bytes + p.b_stage_bytes;
-      // chunk -> (tb, th, tw) once, then incrementally (no div/mod on the producer's critical path)
-      int tw = chunk0 % p.tiles_w;
-      int th = (chunk0 / p.tiles_w) % p.tiles_h;
-      int tb = chunk0 / (p.tiles_w * p.tiles_h);
-      int s = 0;
-      uint32_t phase = 0;
-      for (int it = 0; it < nch; ++it) {
-        ptx::mbar_wait(empty_bar + s, phase ^ 1);
+    // ===== TMA producer: warp-uniform loop, one elected lane issues =====
+    const uint32_t tx = p.a_stage_bytes + p.b_stage_bytes;
+    // chunk -> (tb, th, tw) once, then incrementally (no div/mod on the producer's critical path)
+    int tw = chunk0 % p.tiles_w;
+    int th = (chunk0 / p.tiles_w) % p.tiles_h;
+    int tb = chunk0 / (p.tiles_w * p.tiles_h);
+    int s = 0;
+    uint32_t phase = 0;
+    for (int it = 0; it < nch; ++it) {
+      ptx::mbar_wait(empty_bar + s, phase ^ 1);
+      if (ptx::elect_one()) {
         const int w0 = tw * p.Wt, h0 = th * p.Ht, b0 = tb * p.Bt;
         ptx::mbar_arrive_expect_tx(full_bar + s, tx);
         uint8_t* a_dst = smem_a + (size_t)s * p.a_stage_bytes;
@@ -351,37 +405,45 @@ qconv_wgrad_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_const
         uint8_t* b_dst = smem_b + (size_t)s * p.b_stage_bytes;
         const int wc = w0 * p.sW - p.pW, hc = h0 * p.sH - p.pH + kh * p.dH;
         for (int t = 0; t < p.TG; ++t)
-          ptx::tma_load_5d(b_dst + (size_t)t * p.atom_bytes, &map_x, full_bar + s, ci0, q, wc + t * p.dW, hc, b0);
-        if (++s == p.stages) { s = 0; phase ^= 1; }
-        if (++tw == p.tiles_w) { tw = 0; if (++th == p.tiles_h) { th = 0; ++tb; } }
+          for (int a = 0; a < p.NB; ++a)
+            ptx::tma_load_5d(b_dst + (size_t)(t * p.NB + a) * p.atom_bytes, &map_x, full_bar + s, ci0 + a * p.NA, q,
+                             wc + t * p.dW, hc, b0);
       }
+      __syncwarp();
+      if (++s == p.stages) { s = 0; phase ^= 1; }
+      if (++tw == p.tiles_w) { tw = 0; if (++th == p.tiles_h) { th = 0; ++tb; } }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // MN-major, 128B swizzle: LBO = distance between 128-byte column atoms, SBO = one K-row group
-      const uint64_t da0 = ptx::make_smem_desc(ptx::smem_u32(smem_a), p.atom_bytes, p.sbo_bytes, p.layout_type);
-      const uint64_t db0 = ptx::make_smem_desc(ptx::smem_u32(smem_b), p.atom_bytes, p.sbo_bytes, p.layout_type);
-      const uint64_t a_step = (uint64_t)(p.a_stage_bytes >> 4), b_step = (uint64_t)(p.b_stage_bytes >> 4);
-      const uint64_t atom_step = (uint64_t)(p.atom_bytes >> 4);
-      int s = 0;
-      uint32_t phase = 0;
-      uint64_t da = da0, db = db0;
-      for (int it = 0; it < nch; ++it) {
-        ptx::mbar_wait(full_bar + s, phase);
-        ptx::tc_fence_after();
+    // ===== MMA issuer: warp-uniform loop, one elected lane issues =====
+    // MN-major, 128B swizzle: LBO = distance between 128-byte column atoms, SBO = one K-row group
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint64_t da0 = ptx::make_smem_desc(ptx::smem_u32(smem_a), p.atom_bytes, p.sbo_bytes, p.layout_type);
+    const uint64_t db0 = ptx::make_smem_desc(ptx::smem_u32(smem_b), p.atom_bytes, p.sbo_bytes, p.layout_type);
+    const uint64_t a_step = (uint64_t)(p.a_stage_bytes >> 4), b_step = (uint64_t)(p.b_stage_bytes >> 4);
+    const uint64_t tap_step = (uint64_t)((p.atom_bytes * p.NB) >> 4);
+    int s = 0;
+    uint32_t phase = 0;
+    uint64_t da = da0, db = db0;
+    for (int it = 0; it < nch; ++it) {
+      ptx::mbar_wait(full_bar + s, phase);
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {
         uint64_t dbt = db;
-        for (int t = 0; t < p.TG; ++t, dbt += atom_step) {
-          const uint32_t d_tmem = tmem_base + (uint32_t)(t * p.NA);
-          for (int k = 0; k < p.ksteps; ++k)
+        for (int t = 0; t < p.TG; ++t, dbt += tap_step) {
+          const uint32_t d_tmem = tmem_u + (uint32_t)(t * N);
+#pragma unroll
+          for (int k = 0; k < KSTEPS; ++k)
             ptx::umma<KIND>(d_tmem, da + (uint64_t)(k * p.kadv), dbt + (uint64_t)(k * p.kadv), p.idesc, (it | k) ? 1u : 0u);
         }
         ptx::umma_commit(empty_bar + s);
-        da += a_step;
-        db += b_step;
-        if (++s == p.stages) { s = 0; phase ^= 1; da = da0; db = db0; }
       }
-      ptx::umma_commit(tmem_full_bar);
+      __syncwarp();
+      da += a_step;
+      db += b_step;
+      if (++s == p.stages) { s = 0; phase ^= 1; da = da0; db = db0; }
     }
+    if (ptx::elect_one()) ptx::umma_commit(tmem_full_bar);
+    __syncwarp();
   } else {
     const int quarter = warp & 3;
     const int m = quarter * 32 + lane;            // co row inside the 128 block
@@ -392,9 +454,9 @@ qconv_wgrad_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_const
     for (int t = 0; t < p.TG; ++t) {
       const int tap = kh * p.kW + t;
       float* dst = p.partial + ((((int64_t)split * 4 + q) * p.taps + tap) * p.Co + co) * p.Ci + ci0;
-      for (int c0 = 0; c0 < p.NA; c0 += 16) {
+      for (int c0 = 0; c0 < N; c0 += 16) {
         float acc[16];
-        ptx::tmem_ld16(lane_base + (uint32_t)(t * p.NA + c0), acc);
+        ptx::tmem_ld16(lane_base + (uint32_t)(t * N + c0), acc);
         ptx::tmem_ld_wait();
         if (co < p.Co && nch > 0) {
 #pragma unroll
@@ -493,6 +555,36 @@ static size_t packed_weight_bytes(const quan_conv_dims& d, int dtype) {
   return ((size_t)4 * d.kH * d.kW * d.Co * d.Ci * (dtype == QUAN_BF16 ? 2 : 4) + 1023) / 1024 * 1024;
 }
 
+template <typename T, bool MIX, int CG, int KSTEPS>
+static int launch_igemm_inst(const CUtensorMap& map_a, const CUtensorMap& map_b, void* out, const TcConvParams& p,
+                             int64_t mtiles, int ntiles, size_t smem, cudaStream_t st) {
+  auto kern = qconv_igemm_kernel<T, MIX, CG, KSTEPS>;
+  static thread_local bool attr_set = false;
+  if (!attr_set) {
+    QUAN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  if (CG == 2) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)((mtiles + 1) / 2 * 2), (unsigned)ntiles);   // whole pairs; the spare tile is masked
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    QUAN_CUDA(cudaLaunchKernelEx(&cfg, kern, map_a, map_b, reinterpret_cast<T*>(out), p));
+  } else {
+    kern<<<dim3((unsigned)mtiles, (unsigned)ntiles), TC_THREADS, smem, st>>>(map_a, map_b, reinterpret_cast<T*>(out), p);
+  }
+  QUAN_CHECK_LAUNCH("qconv_igemm_kernel");
+  return QUAN_OK;
+}
+
 template <typename T, bool MIX>
 static int launch_igemm(const void* in, const void* wpacked, const float* bias, void* out, const IgemmShape& s, int dtype,
                         const Mix16& mix, cudaStream_t st) {
@@ -507,20 +599,30 @@ static int launch_igemm(const void* in, const void* wpacked, const float* bias, 
   p.kH = s.kH; p.kW = s.kW; p.sH = s.sH; p.sW = s.sW; p.pH = s.pH; p.pW = s.pW; p.dH = s.dH; p.dW = s.dW;
   p.bk_elems = row_bytes / esz;
   p.kblocks = s.K / p.bk_elems;
-  p.ksteps = row_bytes / 32;
+  const int ksteps = row_bytes / 32;
   p.BN = pick_bn(s.N);
-  p.a_stage_bytes = 128u * row_bytes;
-  p.b_stage_bytes = (uint32_t)p.BN * row_bytes;
+  const int64_t mtiles = (int64_t)t.tiles_w * t.tiles_h * t.tiles_b;
+  // CTA pairs (cta_group::2) when the weight tile splits into two halves that are themselves legal UMMA-N slices.
+  // Measured equal to single CTAs while the kernel is issue-bound; opt-in until the loop overhead is gone.
+  // Measured on B200 (C=256 3x3): 283 us with pairs vs 312 us without, once the issue loop was tight.
+  int cg = (p.BN % 32 == 0 && mtiles >= 2) ? 2 : 1;
+  if (const char* e = getenv("QUAN_TC_CG")) { if (atoi(e) == 1) cg = 1; }
+  p.a_sub_bytes = 128u * row_bytes;
+  p.b_sub_bytes = (uint32_t)(p.BN / cg) * row_bytes;
   p.sbo_bytes = 8u * row_bytes;
   p.layout_type = row_bytes == 128 ? 2u : row_bytes == 64 ? 4u : 6u;
-  p.idesc = ptx::make_idesc(sizeof(T) == 2 ? 1u : 2u, 0u, 0u, 128u, (uint32_t)p.BN);
+  p.idesc = ptx::make_idesc(sizeof(T) == 2 ? 1u : 2u, 0u, 0u, 128u * cg, (uint32_t)p.BN);
   p.tmem_cols = (uint32_t)pow2_ceil(4 * p.BN < 32 ? 32 : 4 * p.BN);
   p.bias = bias;
   p.mix = mix;
-  const size_t stage_bytes = (size_t)p.a_stage_bytes + p.b_stage_bytes;
+  const int iters_per_q = s.kH * s.kW * p.kblocks;
+  p.sub = iters_per_q >= 2 ? 2 : 1;                  // 8 MMAs per barrier round trip when there is enough K
+  if (const char* e = getenv("QUAN_TC_SUB")) { int v = atoi(e); if (v >= 1 && v <= 4 && v <= iters_per_q) p.sub = v; }
+  const size_t stage_bytes = (size_t)(p.a_sub_bytes + p.b_sub_bytes) * p.sub;
   const size_t budget = 200 * 1024;
   int stages = (int)(budget / stage_bytes);
   if (stages > 8) stages = 8;
+  if (const char* e = getenv("QUAN_TC_STAGES")) { int v = atoi(e); if (v >= 1 && v < stages) stages = v; }
   QUAN_REQUIRE(stages >= 2, QUAN_E_UNSUPPORTED, "tcgen05 conv: stage too large");
   p.stages = stages;
   const size_t smem = 1024 + stages * stage_bytes + (2 * stages + 1) * sizeof(uint64_t) + 16;
@@ -541,21 +643,22 @@ static int launch_igemm(const void* in, const void* wpacked, const float* bias, 
     const int taps = s.kH * s.kW;
     const uint64_t dims[4] = {(uint64_t)s.K, (uint64_t)s.N, (uint64_t)taps, 4};
     const uint64_t str[3] = {(uint64_t)s.K * esz, (uint64_t)s.N * s.K * esz, (uint64_t)taps * s.N * s.K * esz};
-    const uint32_t box[4] = {(uint32_t)p.bk_elems, (uint32_t)p.BN, 1, 1};
+    const uint32_t box[4] = {(uint32_t)p.bk_elems, (uint32_t)(p.BN / cg), 1, 1};
     const uint32_t est[4] = {1, 1, 1, 1};
     int rc = encode_map(&map_b, dtype, 4, wpacked, dims, str, box, est, row_bytes);
     if (rc) return rc;
   }
-  auto kern = qconv_igemm_kernel<T, MIX>;
-  static thread_local size_t smem_set = 0;   // raise the dynamic-smem cap once per (thread, instantiation)
-  if (smem > smem_set) {
-    QUAN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    smem_set = 227 * 1024;
+  const int ntiles = s.N / p.BN;
+#define QUAN_IGEMM_CASE(CGV, KS) return launch_igemm_inst<T, MIX, CGV, KS>(map_a, map_b, out, p, mtiles, ntiles, smem, st)
+  if (cg == 2) {
+    if (ksteps == 4) { QUAN_IGEMM_CASE(2, 4); }
+    if (ksteps == 2) { QUAN_IGEMM_CASE(2, 2); }
+    QUAN_IGEMM_CASE(2, 1);
   }
-  dim3 grid((unsigned)(t.tiles_w * t.tiles_h * t.tiles_b), (unsigned)(s.N / p.BN));
-  kern<<<grid, TC_THREADS, smem, st>>>(map_a, map_b, reinterpret_cast<T*>(out), p);
-  QUAN_CHECK_LAUNCH("qconv_igemm_kernel");
-  return QUAN_OK;
+  if (ksteps == 4) { QUAN_IGEMM_CASE(1, 4); }
+  if (ksteps == 2) { QUAN_IGEMM_CASE(1, 2); }
+  QUAN_IGEMM_CASE(1, 1);
+#undef QUAN_IGEMM_CASE
 }
 
 template <typename T, bool DGRAD>
@@ -592,7 +695,7 @@ static IgemmShape dgrad_shape(const quan_conv_dims& d) {
 
 struct WgradPlan {
   TilePlan t;
-  int nchunks, TG, NA, MA, co_blocks, ci_blocks, tap_groups, splits, chunks_per_split, stages;
+  int nchunks, TG, NA, NB, MA, co_blocks, ci_blocks, tap_groups, splits, chunks_per_split, stages;
   size_t smem, partial_bytes;
 };
 
@@ -624,8 +727,16 @@ static bool plan_wgrad(const quan_conv_dims& d, int dtype, WgradPlan& w) {
   if (w.TG * w.NA > 512) return false;
   w.tap_groups = d.kH;
   w.MA = 128 / w.NA;                                 // atoms that make M = 128
+  // N = NB atoms of ci per CTA: as wide as TMEM (TG accumulators of N columns), UMMA (N <= 256) and a >= 3-stage smem
+  // ring allow — wider N means fewer, longer MMAs per barrier round trip and fewer re-reads of the G tile
+  w.NB = 1;
+  for (int nb = 2; nb <= 4; nb *= 2) {
+    const size_t stage_nb = (size_t)(w.MA + w.TG * nb) * WG_PIX * 128;
+    if (d.Ci % (nb * w.NA) == 0 && w.TG * nb * w.NA <= 512 && nb * w.NA <= 256 && (200 * 1024) / stage_nb >= 3) w.NB = nb;
+  }
+  if (const char* e = getenv("QUAN_TC_WG_NB")) { int v = atoi(e); if (v >= 1 && v <= w.NB) w.NB = v; }
   w.co_blocks = (d.Co + 127) / 128;
-  w.ci_blocks = d.Ci / w.NA;
+  w.ci_blocks = d.Ci / (w.NA * w.NB);
   const int64_t combos = (int64_t)4 * w.tap_groups * w.co_blocks * w.ci_blocks;
   if (combos > 65535) return false;
   int64_t splits = (2 * QUAN_NUM_SMS + combos - 1) / combos;
@@ -634,7 +745,7 @@ static bool plan_wgrad(const quan_conv_dims& d, int dtype, WgradPlan& w) {
   w.chunks_per_split = (int)((w.nchunks + splits - 1) / splits);
   w.splits = (w.nchunks + w.chunks_per_split - 1) / w.chunks_per_split;
   const size_t atom = (size_t)WG_PIX * 128;
-  const size_t stage = (size_t)(w.MA + w.TG) * atom;
+  const size_t stage = (size_t)(w.MA + w.TG * w.NB) * atom;
   int stages = (int)((200 * 1024) / stage);
   if (stages > 8) stages = 8;
   if (stages < 2) return false;
@@ -657,7 +768,7 @@ static int launch_wgrad(const void* gq, const void* x, float* const dw[4], const
   p.Wt = w.t.Wt; p.Ht = w.t.Ht; p.Bt = w.t.Bt; p.tiles_w = w.t.tiles_w; p.tiles_h = w.t.tiles_h; p.nchunks = w.nchunks;
   p.kH = d.kH; p.kW = d.kW; p.sH = d.sH; p.sW = d.sW; p.pH = d.pH; p.pW = d.pW; p.dH = d.dH; p.dW = d.dW;
   p.Co = d.Co; p.Ci = d.Ci; p.taps = d.kH * d.kW;
-  p.TG = w.TG; p.NA = w.NA; p.MA = w.MA;
+  p.TG = w.TG; p.NA = w.NA; p.NB = w.NB; p.MA = w.MA;
   p.co_blocks = w.co_blocks; p.ci_blocks = w.ci_blocks; p.tap_groups = w.tap_groups;
   p.chunks_per_split = w.chunks_per_split;
   const int umma_k = 32 / esz;                       // pixels per UMMA
@@ -669,9 +780,9 @@ static int launch_wgrad(const void* gq, const void* x, float* const dw[4], const
   p.layout_type = sizeof(T) == 2 ? 2u : 1u;
   const uint32_t swz = sizeof(T) == 2 ? 128u : SWZ_128B_ATOM32;
   p.a_stage_bytes = (uint32_t)w.MA * p.atom_bytes;
-  p.b_stage_bytes = (uint32_t)w.TG * p.atom_bytes;
-  p.idesc = ptx::make_idesc(sizeof(T) == 2 ? 1u : 2u, 1u, 1u, 128u, (uint32_t)w.NA);
-  p.tmem_cols = (uint32_t)pow2_ceil(w.TG * w.NA < 32 ? 32 : w.TG * w.NA);
+  p.b_stage_bytes = (uint32_t)(w.TG * w.NB) * p.atom_bytes;
+  p.idesc = ptx::make_idesc(sizeof(T) == 2 ? 1u : 2u, 1u, 1u, 128u, (uint32_t)(w.NA * w.NB));
+  p.tmem_cols = (uint32_t)pow2_ceil(w.TG * w.NA * w.NB < 32 ? 32 : w.TG * w.NA * w.NB);
   p.partial = reinterpret_cast<float*>(ws);
 
   CUtensorMap map_g, map_x;
@@ -693,7 +804,7 @@ static int launch_wgrad(const void* gq, const void* x, float* const dw[4], const
     int rc = encode_map(&map_x, dtype, 5, x, dims, str, box, est, swz);
     if (rc) return rc;
   }
-  auto kern = qconv_wgrad_kernel<T>;
+  auto kern = qconv_wgrad_kernel<T, WG_PIX / (32 / (int)sizeof(T))>;
   static thread_local bool attr_set = false;
   if (!attr_set) {
     QUAN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
