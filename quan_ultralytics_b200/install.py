@@ -1,0 +1,59 @@
+"""Bind an importable checkout of bryceag11/QUAN_ultralytics to the B200 ops (INTEGRATION.md levels 1 and 2).
+
+    import quan_ultralytics_b200.install as qi
+    qi.install(ultralytics=True, classification=True)       # swap the layer classes
+    with torch.device("cuda"):                               # the reference runs a probe forward while building
+        model = OBBModel("yolo11n-obb-quan.yaml", ch=3, nc=15)
+
+Nothing here is needed on a box without the reference; it is plumbing, not compute.
+"""
+from __future__ import annotations
+
+import importlib
+import sys
+import types
+
+from . import modules as M
+from . import quaternion_ops as shim
+
+_SWAP = ("QConv2D", "IQBN", "Conv", "DWConv", "QUpsample")
+
+
+def install_extension_shim(mixing: str = "A") -> types.ModuleType:
+    """Level 1: make `import quaternion_ops` (conv.py:47-60) resolve to the ctypes-backed shim."""
+    shim.set_mixing(mixing)
+    sys.modules["quaternion_ops"] = shim
+    return shim
+
+
+def install(ultralytics: bool = True, classification: bool = True) -> dict:
+    """Level 2: replace the reference's layer classes with the B200 modules in every namespace that re-exports them.
+    Returns {module_name: [swapped names]} for logging."""
+    done = {}
+    if ultralytics:
+        for modname in ("ultralytics.nn.modules.conv", "ultralytics.nn.modules", "ultralytics.nn.modules.block",
+                        "ultralytics.nn.modules.head", "ultralytics.nn.tasks"):
+            try:
+                mod = importlib.import_module(modname)
+            except Exception:
+                continue
+            names = [n for n in _SWAP if hasattr(mod, n)]
+            for n in names:
+                setattr(mod, n, getattr(M, n))
+            done[modname] = names
+    if classification:
+        for modname in ("quaternion.qconv", "quaternion", "models.quaternion_blocks", "models.quaternion_models",
+                        "models.blocks.quaternion_blocks"):
+            try:
+                mod = importlib.import_module(modname)
+            except Exception:
+                continue
+            names = []
+            if hasattr(mod, "QConv2D"):
+                mod.QConv2D = M.QConv2D_B      # classification/quaternion/qconv.py:606-609 mixes with M_B
+                names.append("QConv2D")
+            if hasattr(mod, "IQBN"):
+                mod.IQBN = M.IQBN
+                names.append("IQBN")
+            done[modname] = names
+    return done
