@@ -193,9 +193,9 @@ def kernel_table(a, dev, dtype, peaks):
     flush = torch.zeros(64 << 20, dtype=torch.int32, device=dev)   # 256 MB
     S = x.numel() * esz
     conv_flops = 4 * 2 * N * H * H * C * C * 9
-    stats = ops.iqbn_train_stats(x, L, 1e-5, 0.1, None, None)
-    sums = ops.iqbn_bwd_reduce(dy, x, L, stats, gamma, beta, Q.ACT_SILU)
     cnt = float(N * H * H)
+    stats = ops.iqbn_train_stats(x, L, gamma, beta, 1e-5, 0.1, None, None)
+    sums = ops.iqbn_bwd_reduce(dy, x, L, stats, gamma, beta, Q.ACT_SILU, cnt)
     rows = {}
 
     def add(name, fn, kind, work):
@@ -213,9 +213,9 @@ def kernel_table(a, dev, dtype, peaks):
         conv_flops)
     add("qconv2d_bwd(dgrad+wgrad+mixT)", lambda: ops.qconv2d_bwd(dy, x, w, (1, 1), (1, 1), (1, 1), 1, mix, True, True, False),
         "tensor", 2 * conv_flops)
-    add("iqbn_train_stats", lambda: ops.iqbn_train_stats(x, L, 1e-5, 0.1, None, None), "hbm", S)
+    add("iqbn_train_stats", lambda: ops.iqbn_train_stats(x, L, gamma, beta, 1e-5, 0.1, None, None), "hbm", S)
     add("iqbn_apply_fwd_silu", lambda: ops.iqbn_apply_fwd(x, L, stats, gamma, beta, Q.ACT_SILU), "hbm", 2 * S)
-    add("iqbn_bwd_reduce", lambda: ops.iqbn_bwd_reduce(dy, x, L, stats, gamma, beta, Q.ACT_SILU), "hbm", 2 * S)
+    add("iqbn_bwd_reduce", lambda: ops.iqbn_bwd_reduce(dy, x, L, stats, gamma, beta, Q.ACT_SILU, cnt), "hbm", 2 * S)
     add("iqbn_bwd_apply", lambda: ops.iqbn_bwd_apply(dy, x, L, stats, gamma, beta, Q.ACT_SILU, sums, cnt), "hbm", 3 * S)
     return rows
 

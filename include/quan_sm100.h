@@ -83,39 +83,49 @@ int quan_poincare_bwd(const float* rgb, const void* grad_out, float* grad_rgb,
  *
  * quan_iqbn_train_stats: one pass over x; per (c,q): mean, biased var (+1e-8 as the reference adds,
  *   conv.py:557), rstd = 1/sqrt(var+eps); updates running_mean/var in place with `momentum`
- *   (conv.py:561-562) when running_mean != NULL.  Writes stats[0..4C) = mean, [4C..8C) = var(+1e-8),
- *   [8C..12C) = rstd, all indexed [c*4+q].  When `count_scale` > 1 the sums are treated as partial
- *   (synced IQBN): see quan_iqbn_partial_sums / quan_iqbn_finalize_stats.
+ *   (conv.py:561-562) when running_mean != NULL.  Writes the [20C] stats table described below.
  * quan_iqbn_apply_fwd: y = act(gamma*(x-mean)*rstd + beta)  (SiLU fused: conv.py:789,809).
  * quan_iqbn_eval_fwd: y = act(gamma*(x-running_mean)/sqrt(running_var+eps)+beta) (no +1e-8).
  * quan_iqbn_bwd_reduce: sums[0..4C) = sum dz, sums[4C..8C) = sum dz*xhat, dz = dy*act'(z).
  * quan_iqbn_bwd_apply: dx = gamma*rstd*(dz - sums_dz/n - xhat*sums_dzxhat/n); if mix_t != NULL the result
  *   is additionally multiplied per quaternion by mix_t (used to emit G = M^T dY for the preceding QConv2D).
- * Workspace: quan_iqbn_workspace_bytes(C) bytes, zero-initialised ONCE by the caller (the kernels leave
- *   it zeroed again on exit). */
+ * Workspace: quan_iqbn_workspace_bytes(C) bytes of scratch (per-row-split fp64 partial sums; no initialisation
+ *   needed, results are deterministic).  Every reduction is two launches: stream + fold. */
 size_t quan_iqbn_workspace_bytes(int32_t C);
+/* stats: [20*C] floats = mean | var(+1e-8) | rstd (index c*4+q) | scaleT | shiftT (index q*C+c, the BHWQC column order:
+ * scale = gamma*rstd, shift = beta - mean*scale) — the table lets the streaming kernels fetch coefficients with 16-byte loads. */
 int quan_iqbn_train_stats(const void* x, int32_t B, int32_t C, int32_t H, int32_t W, int dtype, int layout,
-                          float eps, float momentum, float* running_mean, float* running_var,
-                          float* stats /* [12*C] */, void* workspace, size_t ws_bytes, void* stream);
-/* synced-IQBN building blocks: raw per-(c,q) sums in fp64 {sum, sumsq}[c*4+q] (+ shift-free), then finalize
- * after the caller all-reduced them across ranks (new work, no reference call site). */
+                          const float* gamma, const float* beta, float eps, float momentum, float* running_mean,
+                          float* running_var, float* stats /* [20*C] */, void* workspace, size_t ws_bytes, void* stream);
+/* synced-IQBN building blocks: raw per-(c,q) sums in fp64 {sum, sumsq}[c*4+q], then finalize after the caller
+ * all-reduced them across ranks (new work, no reference call site). */
 int quan_iqbn_partial_sums(const void* x, int32_t B, int32_t C, int32_t H, int32_t W, int dtype, int layout,
                            double* sums /* [8*C]: sum[4C], sumsq[4C] */, void* workspace, size_t ws_bytes,
                            void* stream);
-int quan_iqbn_finalize_stats(const double* sums, double count, int32_t C, float eps, float momentum,
-                             float* running_mean, float* running_var, float* stats, void* stream);
+int quan_iqbn_finalize_stats(const double* sums, double count, int32_t C, const float* gamma, const float* beta, float eps,
+                             float momentum, float* running_mean, float* running_var, float* stats /* [20*C] */,
+                             void* stream);
+/* eval mode: the same [20*C] table from the running statistics (no +1e-8, conv.py:550); then quan_iqbn_apply_fwd. */
+int quan_iqbn_eval_stats(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                         float eps, int32_t C, float* stats /* [20*C] */, void* stream);
 int quan_iqbn_apply_fwd(const void* x, void* y, int32_t B, int32_t C, int32_t H, int32_t W, int dtype,
                         int layout, const float* stats, const float* gamma, const float* beta, int act,
                         void* stream);
 int quan_iqbn_eval_fwd(const void* x, void* y, int32_t B, int32_t C, int32_t H, int32_t W, int dtype,
                        int layout, const float* gamma, const float* beta, const float* running_mean,
                        const float* running_var, float eps, int act, void* stream);
+/* sums: [14*C] doubles = {sum dz, sum dz*xhat}[c*4+q] (8C) followed by the backward coefficient table k1T|k2T|k3T
+ * (12C floats, index q*C+c; dx = k1*dz + k2*x + k3).  count > 0: the table is written by the same launch;
+ * count <= 0: sums only — all-reduce sums[0..8C) across ranks, then quan_iqbn_bwd_coef with the global count. */
 int quan_iqbn_bwd_reduce(const void* dy, const void* x, int32_t B, int32_t C, int32_t H, int32_t W,
                          int dtype, int layout, const float* stats, const float* gamma, const float* beta,
-                         int act, double* sums /* [8*C] */, void* workspace, size_t ws_bytes, void* stream);
+                         int act, double count, double* sums /* [14*C] */, void* workspace, size_t ws_bytes,
+                         void* stream);
+int quan_iqbn_bwd_coef(double* sums /* [14*C] */, double count, int32_t C, const float* stats, const float* gamma,
+                       void* stream);
 int quan_iqbn_bwd_apply(const void* dy, const void* x, void* dx, int32_t B, int32_t C, int32_t H, int32_t W,
                         int dtype, int layout, const float* stats, const float* gamma, const float* beta,
-                        int act, const double* sums, double count, float* dgamma, float* dbeta,
+                        int act, const double* sums /* [14*C] */, double count, float* dgamma, float* dbeta,
                         const float* mix_t /* NULL or [16] */, void* stream);
 /* backward of the eval-mode affine (running stats are constants): dx = dz*gamma*rstd_run. */
 int quan_iqbn_eval_bwd(const void* dy, const void* x, void* dx, int32_t B, int32_t C, int32_t H, int32_t W,

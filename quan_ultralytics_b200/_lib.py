@@ -38,12 +38,14 @@ PROTOTYPES = {
     "quan_poincare_fwd": (_int, [_vp, _vp, _i32, _i32, _i32, _int, _vp]),
     "quan_poincare_bwd": (_int, [_vp, _vp, _vp, _i32, _i32, _i32, _int, _vp]),
     "quan_iqbn_workspace_bytes": (_sz, [_i32]),
-    "quan_iqbn_train_stats": (_int, [_vp, _i32, _i32, _i32, _i32, _int, _int, _f, _f, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "quan_iqbn_train_stats": (_int, [_vp, _i32, _i32, _i32, _i32, _int, _int, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _sz, _vp]),
     "quan_iqbn_partial_sums": (_int, [_vp, _i32, _i32, _i32, _i32, _int, _int, _vp, _vp, _sz, _vp]),
-    "quan_iqbn_finalize_stats": (_int, [_vp, _d, _i32, _f, _f, _vp, _vp, _vp, _vp]),
+    "quan_iqbn_finalize_stats": (_int, [_vp, _d, _i32, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp]),
+    "quan_iqbn_eval_stats": (_int, [_vp, _vp, _vp, _vp, _f, _i32, _vp, _vp]),
+    "quan_iqbn_bwd_coef": (_int, [_vp, _d, _i32, _vp, _vp, _vp]),
     "quan_iqbn_apply_fwd": (_int, [_vp, _vp, _i32, _i32, _i32, _i32, _int, _int, _vp, _vp, _vp, _int, _vp]),
     "quan_iqbn_eval_fwd": (_int, [_vp, _vp, _i32, _i32, _i32, _i32, _int, _int, _vp, _vp, _vp, _vp, _f, _int, _vp]),
-    "quan_iqbn_bwd_reduce": (_int, [_vp, _vp, _i32, _i32, _i32, _i32, _int, _int, _vp, _vp, _vp, _int, _vp, _vp, _sz, _vp]),
+    "quan_iqbn_bwd_reduce": (_int, [_vp, _vp, _i32, _i32, _i32, _i32, _int, _int, _vp, _vp, _vp, _int, _d, _vp, _vp, _sz, _vp]),
     "quan_iqbn_bwd_apply": (_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _int, _int, _vp, _vp, _vp, _int, _vp, _d,
                                    _vp, _vp, _vp, _vp]),
     "quan_iqbn_eval_bwd": (_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _int, _int, _vp, _vp, _vp, _vp, _f, _int, _vp]),

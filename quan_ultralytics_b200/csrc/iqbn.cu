@@ -4,11 +4,12 @@
 // + 1e-8, running-stat update with momentum), :546-552 (eval branch), SiLU from conv.py:789,809.
 // Backward is the analytic gradient of that expression (the reference relies on autograd).
 //
-// Design: every kernel is a grid-stride stream of 16-byte vector loads.  A thread owns a
-// fixed "column" (c,q) set for its whole life, so per-channel parameters live in registers and per-channel
-// partial sums are private fp32 registers (locally shifted, so cancellation stays local), flushed once per
-// thread as fp64 atomics into a [8C] accumulator; the last block to finish (threadfence + counter) turns the
-// sums into mean/var/rstd (+ running-stat update) and re-zeroes the workspace, so stats take ONE launch.
+// Design: every kernel is a grid-stride stream of 16-byte vector loads.  A thread owns a fixed
+// "column" (c,q) set for its whole life: per-channel coefficients come from a precomputed table in column order (a few
+// 16-byte loads) and per-channel partial sums are private fp32 registers (locally shifted, so cancellation stays
+// local), un-shifted in fp64, folded across the block through shared memory and written to the block's own slot of a
+// partials buffer; a second small kernel folds the slots and finishes (mean/var/rstd + running stats + coefficient
+// tables).  No atomics, deterministic.
 //
 // Two physical layouts (include/quan_sm100.h): BCHWQ (reference) and BHWQC (channels_last_3d, tensor-core path).
 #include "common.cuh"
@@ -16,78 +17,129 @@
 
 namespace quan {
 
-// workspace: [8C] doubles of accumulators + one unsigned counter (padded to 16 B)
+// workspace: per-row-split partial sums part[split][which][c*4+q] in fp64, written with plain stores by the reduction
+// kernels and folded by a second, parallel finalize kernel.  Deterministic, nothing to zero.  (The first versions used
+// fp64 atomics + a last-block tail: the L2 retires only ~18 G fp64 atomics/s chip-wide, so 1.2 M atomics — 592 blocks x
+// 2048 accumulators — cost 69 us on top of a 24 us stream; measured in profiles/r01_iqbn_tune2.log.)
+constexpr int IQBN_MAX_PARTS = 4 * QUAN_NUM_SMS;
 struct IqbnWs {
-  double* acc;
-  unsigned int* counter;
+  double* part;
 };
 static inline IqbnWs carve_ws(void* ws, int C) {
+  (void)C;
   IqbnWs w;
-  w.acc = reinterpret_cast<double*>(ws);
-  w.counter = reinterpret_cast<unsigned int*>(w.acc + 8 * (size_t)C);
+  w.part = reinterpret_cast<double*>(ws);
   return w;
 }
 
 // What the last block does with the accumulated sums.
 enum TailMode { TAIL_RAW_SUMS = 0, TAIL_FWD_STATS = 1, TAIL_BWD_SUMS = 2 };
 
+// stats buffer [20C] floats: mean | var(+1e-8) | rstd (index c*4+q)  |  scaleT | shiftT (index q*C+c: BHWQC column order,
+//                            so a thread's V coefficients are one or two 16-byte loads instead of 4V scalar ones)
+// bwd buffer: [8C] doubles {sum dz, sum dz*xhat} (index c*4+q) followed by [12C] floats k1T | k2T | k3T (index q*C+c)
 struct TailArgs {
   int mode;
   int C;
-  double count;
+  double count;        // bwd: <= 0 means "sums only" (synced IQBN: coefficients are made after the all-reduce)
   float eps, momentum;
   float* running_mean;
   float* running_var;
-  float* stats;        // [12C] (fwd: out; bwd: in)
-  double* sums_out;    // [8C] (raw sums or bwd sums)
+  float* stats;        // [20C] (fwd: out; bwd: in)
+  double* sums_out;    // [8C] raw sums / [8C + 6C] bwd sums + coefficient table
+  const float* gamma;  // fwd stats + bwd coefficients
+  const float* beta;
 };
 
-// Executed by every thread of the LAST block.  acc[0..4C) = first sum, acc[4C..8C) = second sum.
-__device__ void tail_finalize(const TailArgs& t, double* acc) {
+// dx = k1*dz + k2*x + k3 with xhat = (x - mean)*rstd:  k1 = g r, k2 = -g r^2 mdzx, k3 = -g r (mdz - mean r mdzx)
+__device__ __forceinline__ void bwd_coefficients(float gamma, float mean, float rstd, double sdz, double sdzx, double count,
+                                                 float& k1, float& k2, float& k3) {
+  const float gr = gamma * rstd;
+  const float mdz = (float)(sdz / count), mdzx = (float)(sdzx / count);
+  k1 = gr;
+  k2 = -gr * rstd * mdzx;
+  k3 = -gr * (mdz - mean * rstd * mdzx);
+}
+
+__device__ __forceinline__ void write_fwd_stats(const TailArgs& t, int i, double s0, double s1) {
   const int n = 4 * t.C;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    // atomics landed in L2; read through L2 (volatile) — L1 may hold nothing for these but be explicit
-    double s0 = __ldcg(acc + i), s1 = __ldcg(acc + n + i);
+  double mean = s0 / t.count;
+  double var = s1 / t.count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  var += 1e-8;  // conv.py:557
+  const float rstd = (float)(1.0 / sqrt(var + (double)t.eps));
+  t.stats[i] = (float)mean;
+  t.stats[n + i] = (float)var;
+  t.stats[2 * n + i] = rstd;
+  if (t.gamma != nullptr) {
+    const int c = i >> 2, q = i & 3;
+    const float scale = t.gamma[i] * rstd;
+    t.stats[3 * n + q * t.C + c] = scale;
+    t.stats[4 * n + q * t.C + c] = t.beta[i] - (float)mean * scale;
+  }
+  if (t.running_mean != nullptr) {  // conv.py:561-562
+    t.running_mean[i] = (1.0f - t.momentum) * t.running_mean[i] + t.momentum * (float)mean;
+    t.running_var[i] = (1.0f - t.momentum) * t.running_var[i] + t.momentum * (float)var;
+  }
+}
+
+__device__ __forceinline__ void write_bwd_sums(const TailArgs& t, int i, double s0, double s1) {
+  // s0 = sum dz, s1 = sum dz*x  ->  sum dz*xhat = rstd*(s1 - mean*s0)
+  const int n = 4 * t.C;
+  const double mean = (double)t.stats[i], rstd = (double)t.stats[2 * n + i];
+  const double sdzx = rstd * (s1 - mean * s0);
+  t.sums_out[i] = s0;
+  t.sums_out[n + i] = sdzx;
+  if (t.count > 0.0) {
+    float* coef = reinterpret_cast<float*>(t.sums_out + 2 * n);
+    const int c = i >> 2, q = i & 3, j = q * t.C + c;
+    float k1, k2, k3;
+    bwd_coefficients(t.gamma[i], (float)mean, (float)rstd, s0, sdzx, t.count, k1, k2, k3);
+    coef[j] = k1;
+    coef[n + j] = k2;
+    coef[2 * n + j] = k3;
+  }
+}
+
+// Second kernel of every reduction: fold the per-split partials of accumulator i = c*4+q and finish.
+// block = 8 accumulators x 32 split-groups (4 independent loads in flight per thread); grid = ceil(4C / 8).
+__global__ void __launch_bounds__(256) iqbn_fold_kernel(const double* __restrict__ part, int nparts, TailArgs t) {
+  __shared__ double red[2][32][9];
+  const int n = 4 * t.C;
+  const int il = threadIdx.x & 7, gl = threadIdx.x >> 3;
+  const int i = blockIdx.x * 8 + il;
+  double s0 = 0.0, s1 = 0.0;
+  if (i < n) {
+    int sp = gl;
+    for (; sp + 32 < nparts; sp += 64) {
+      const double a0 = part[((size_t)sp * 2 + 0) * n + i], a1 = part[((size_t)sp * 2 + 1) * n + i];
+      const double b0 = part[((size_t)(sp + 32) * 2 + 0) * n + i], b1 = part[((size_t)(sp + 32) * 2 + 1) * n + i];
+      s0 += a0 + b0;
+      s1 += a1 + b1;
+    }
+    for (; sp < nparts; sp += 32) {
+      s0 += part[((size_t)sp * 2 + 0) * n + i];
+      s1 += part[((size_t)sp * 2 + 1) * n + i];
+    }
+  }
+  red[0][gl][il] = s0;
+  red[1][gl][il] = s1;
+  __syncthreads();
+  if (gl == 0 && i < n) {
+#pragma unroll
+    for (int g = 1; g < 32; ++g) {
+      s0 += red[0][g][il];
+      s1 += red[1][g][il];
+    }
     if (t.mode == TAIL_RAW_SUMS) {
       t.sums_out[i] = s0;
       t.sums_out[n + i] = s1;
     } else if (t.mode == TAIL_FWD_STATS) {
-      double mean = s0 / t.count;
-      double var = s1 / t.count - mean * mean;
-      if (var < 0.0) var = 0.0;
-      var += 1e-8;  // conv.py:557
-      float rstd = (float)(1.0 / sqrt(var + (double)t.eps));
-      t.stats[i] = (float)mean;
-      t.stats[n + i] = (float)var;
-      t.stats[2 * n + i] = rstd;
-      if (t.running_mean != nullptr) {  // conv.py:561-562
-        t.running_mean[i] = (1.0f - t.momentum) * t.running_mean[i] + t.momentum * (float)mean;
-        t.running_var[i] = (1.0f - t.momentum) * t.running_var[i] + t.momentum * (float)var;
-      }
-    } else {  // TAIL_BWD_SUMS: s0 = sum dz, s1 = sum dz*x  ->  sum dz*xhat = rstd*(s1 - mean*s0)
-      double mean = (double)t.stats[i], rstd = (double)t.stats[2 * n + i];
-      t.sums_out[i] = s0;
-      t.sums_out[n + i] = rstd * (s1 - mean * s0);
+      write_fwd_stats(t, i, s0, s1);
+    } else {
+      write_bwd_sums(t, i, s0, s1);
     }
-    acc[i] = 0.0;  // leave the workspace zeroed for the next call
-    acc[n + i] = 0.0;
   }
-}
-
-// Block-level epilogue shared by the reduction kernels: returns true in the last block.
-__device__ bool last_block_arrive(unsigned int* counter) {
-  __shared__ bool is_last;
-  __threadfence();  // make this block's atomics visible before the counter bump
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    unsigned int total = gridDim.x * gridDim.y;
-    unsigned int prev = atomicAdd(counter, 1u);
-    is_last = (prev == total - 1);
-    if (is_last) *counter = 0u;
-  }
-  __syncthreads();
-  if (is_last) __threadfence();
-  return is_last;
 }
 
 // =================================================================================================
@@ -109,6 +161,20 @@ struct GeomB {
   int rpb;        // row lanes per block
 };
 
+// V consecutive fp32 coefficients (V <= 8) as 16-byte loads where alignment allows
+template <typename TT, int V>
+__device__ __forceinline__ void load_coef(const float* __restrict__ p, float (&out)[V]) {
+  if constexpr (V == 8) {
+    float a[4], b[4];
+    load_vec<float, 4>(p, a);
+    load_vec<float, 4>(p + 4, b);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { out[i] = a[i]; out[4 + i] = b[i]; }
+  } else {
+    load_vec<float, V>(p, out);
+  }
+}
+
 template <int V>
 __device__ __forceinline__ void colvec_param_index(int cv, int C, int (&idx)[V]) {
   int col = cv * V;
@@ -128,15 +194,11 @@ __global__ void __launch_bounds__(256) iqbn_reduce_b(const T* __restrict__ x, co
   int pidx[V];
   colvec_param_index<V>(cv, g.C, pidx);
 
+  const int64_t coloff = (int64_t)cv * V;
   float scale[V], shift[V];
-  if constexpr (MODE == 1 && ACT != QUAN_ACT_NONE) {
-    const int n = 4 * g.C;
-#pragma unroll
-    for (int i = 0; i < V; ++i) {
-      float mean = tail.stats[pidx[i]], rstd = tail.stats[2 * n + pidx[i]];
-      scale[i] = gamma[pidx[i]] * rstd;
-      shift[i] = beta[pidx[i]] - mean * scale[i];
-    }
+  if constexpr (MODE == 1 && ACT != QUAN_ACT_NONE) {   // coefficient table in column order: vector loads
+    load_coef<float, V>(tail.stats + 12 * g.C + coloff, scale);
+    load_coef<float, V>(tail.stats + 16 * g.C + coloff, shift);
   }
 
   float s0[V], s1[V], k[V];
@@ -145,7 +207,6 @@ __global__ void __launch_bounds__(256) iqbn_reduce_b(const T* __restrict__ x, co
   for (int i = 0; i < V; ++i) s0[i] = s1[i] = k[i] = 0.f;
 
   const int64_t rstride = (int64_t)gridDim.x * g.rpb;
-  const int64_t coloff = (int64_t)cv * V;
   for (int64_t r = (int64_t)blockIdx.x * g.rpb + rl; r < g.R; r += rstride * U) {
     float xv[U][V], gv[U][V];
 #pragma unroll
@@ -209,9 +270,8 @@ __global__ void __launch_bounds__(256) iqbn_reduce_b(const T* __restrict__ x, co
     for (int l = 0; l < g.rpb; ++l) acc += red[(size_t)(l * g.cvpg + c_v) * (2 * V) + j];
     const int col = (blockIdx.y * g.cvpg + c_v) * V + (j >> 1);
     const int q = col / g.C, c = col - q * g.C;
-    atomicAdd(ws.acc + (j & 1) * 4 * g.C + c * 4 + q, acc);
+    ws.part[((size_t)blockIdx.x * 2 + (j & 1)) * 4 * g.C + c * 4 + q] = acc;   // this block's slot: plain store
   }
-  if (last_block_arrive(ws.counter)) tail_finalize(tail, ws.acc);
 }
 
 // Elementwise coefficient form shared by fwd apply / eval / bwd apply:
@@ -229,6 +289,7 @@ struct ApplyArgs {
   float* dgamma;              // bwd train: optional outputs (written by block 0)
   float* dbeta;
   int C;
+  const float* coefT;         // bwd train, BHWQC: k1T | k2T | k3T (index q*C+c), made by the bwd-reduce tail / bwd_coef
 };
 
 __device__ __forceinline__ void coeff_fwd(const ApplyArgs& a, int idx, float& scale, float& shift) {
@@ -283,18 +344,29 @@ __global__ void __launch_bounds__(256) iqbn_apply_b(const T* __restrict__ x, con
   const int cvl = threadIdx.x % g.cvpg;
   const int rl = threadIdx.x / g.cvpg;
   const int cv = blockIdx.y * g.cvpg + cvl;
-  int pidx[V];
-  colvec_param_index<V>(cv, g.C, pidx);
+  const int64_t coloff = (int64_t)cv * V;
   float scale[V], shift[V], k1[V], k2[V], k3[V];
+  if (a.stats != nullptr && (!BWD || a.coefT != nullptr)) {
+    // training path: coefficient tables in column order (stats[12C..20C), coefT) — a few 16-byte loads per thread
+    load_coef<float, V>(a.stats + 12 * g.C + coloff, scale);
+    load_coef<float, V>(a.stats + 16 * g.C + coloff, shift);
+    if constexpr (BWD) {
+      load_coef<float, V>(a.coefT + coloff, k1);
+      load_coef<float, V>(a.coefT + 4 * g.C + coloff, k2);
+      load_coef<float, V>(a.coefT + 8 * g.C + coloff, k3);
+    }
+  } else {
+    int pidx[V];
+    colvec_param_index<V>(cv, g.C, pidx);
 #pragma unroll
-  for (int i = 0; i < V; ++i) {
-    coeff_fwd(a, pidx[i], scale[i], shift[i]);
-    if constexpr (BWD) coeff_bwd(a, pidx[i], k1[i], k2[i], k3[i]);
+    for (int i = 0; i < V; ++i) {
+      coeff_fwd(a, pidx[i], scale[i], shift[i]);
+      if constexpr (BWD) coeff_bwd(a, pidx[i], k1[i], k2[i], k3[i]);
+    }
   }
   if constexpr (BWD) write_param_grads(a);
 
   const int64_t rstride = (int64_t)gridDim.x * g.rpb;
-  const int64_t coloff = (int64_t)cv * V;
   for (int64_t r = (int64_t)blockIdx.x * g.rpb + rl; r < g.R; r += rstride * U) {
     float xv[U][V], gv[U][V];
 #pragma unroll
@@ -406,15 +478,21 @@ __global__ void __launch_bounds__(256) iqbn_reduce_a(const T* __restrict__ x, co
       a1[q] += __shfl_xor_sync(0xffffffffu, a1[q], o);
     }
   }
+  __shared__ double wred[8][8];
   if ((threadIdx.x & 31) == 0) {
-    const int n = 4 * g.C;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      atomicAdd(ws.acc + c * 4 + q, a0[q]);
-      atomicAdd(ws.acc + n + c * 4 + q, a1[q]);
+      wred[threadIdx.x >> 5][q] = a0[q];
+      wred[threadIdx.x >> 5][4 + q] = a1[q];
     }
   }
-  if (last_block_arrive(ws.counter)) tail_finalize(tail, ws.acc);
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    double acc = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) acc += wred[w][threadIdx.x];
+    const int n = 4 * g.C, which = threadIdx.x >> 2, q = threadIdx.x & 3;
+    ws.part[((size_t)blockIdx.x * 2 + which) * n + c * 4 + q] = acc;
+  }
 }
 
 template <typename T, int V, int ACT, bool BWD, bool MIX>
@@ -480,7 +558,7 @@ static int env_int(const char* name, int dflt) {
 
 template <typename T>
 static bool plan_b(int B, int C, int H, int W, int unroll, int blocks_per_sm, LaunchB& p) {
-  blocks_per_sm = env_int("QUAN_IQBN_BPS", blocks_per_sm);
+  if (blocks_per_sm >= 8) blocks_per_sm = env_int("QUAN_IQBN_BPS", blocks_per_sm);   // apply kernels only
   p.V = largest_pow2_divisor(C, VecTraits<T>::kMaxVec);
   const int colvecs = 4 * C / p.V;
   int cg = (colvecs + 255) / 256;                   // column groups (wide rows only)
@@ -538,19 +616,34 @@ static int launch_reduce(const void* x, const void* dy, int B, int C, int H, int
                          const float* gamma, const float* beta, IqbnWs ws, TailArgs tail, cudaStream_t st) {
   const T* xp = reinterpret_cast<const T*>(x);
   const T* dyp = reinterpret_cast<const T*>(dy);
+  int nparts = 1;
   if (layout == QUAN_LAYOUT_BHWQC && C > 1) {
     LaunchB p;
-    constexpr int U = MODE == 1 ? 4 : 8;   // rows in flight per thread (two tensors are streamed in MODE 1)
-    if (!plan_b<T>(B, C, H, W, U, 2, p)) {
+    // measured (profiles/r01_iqbn_tune5.log): many light warps beat unrolled ones — U = 1 at 4 blocks/SM is the best
+    // point for both reductions (stats 46 us, bwd-reduce 80 us on 134 MB tensors); U > 1 only costs registers
+    const int U = env_int("QUAN_IQBN_RU", 1);
+    int bps = env_int("QUAN_IQBN_RBPS", 4);
+    if (bps > 4) bps = 4;
+    if (!plan_b<T>(B, C, H, W, U, bps, p)) {
       set_error("iqbn: C=%d too large for the BHWQC kernels", C);
       return QUAN_E_UNSUPPORTED;
     }
-    QUAN_DISPATCH_V(p.V, (iqbn_reduce_b<T, (sizeof(T) == 4 && kV == 8) ? 4 : kV, MODE, ACT, U>
-                          <<<p.grid, p.block, (size_t)p.block.x * 2 * kV * sizeof(double), st>>>(xp, dyp, p.g, gamma, beta,
-                                                                                                  ws, tail)));
+    if (p.grid.x > (unsigned)IQBN_MAX_PARTS) p.grid.x = IQBN_MAX_PARTS;
+    nparts = (int)p.grid.x;
+#define QUAN_REDUCE_B(UU) QUAN_DISPATCH_V(p.V, (iqbn_reduce_b<T, (sizeof(T) == 4 && kV == 8) ? 4 : kV, MODE, ACT, UU> \
+                          <<<p.grid, p.block, (size_t)p.block.x * 2 * kV * sizeof(double), st>>>(xp, dyp, p.g, gamma, beta, ws, tail)))
+    switch (U) {
+      case 1: QUAN_REDUCE_B(1); break;
+      case 2: QUAN_REDUCE_B(2); break;
+      case 8: QUAN_REDUCE_B(8); break;
+      default: QUAN_REDUCE_B(4); break;
+    }
+#undef QUAN_REDUCE_B
   } else {
     LaunchA p;
     plan_a<T>(B, C, H, W, p);
+    if (p.grid.x > (unsigned)IQBN_MAX_PARTS) p.grid.x = IQBN_MAX_PARTS;
+    nparts = (int)p.grid.x;
     if (p.V == 8) {
       if constexpr (sizeof(T) == 2)
         iqbn_reduce_a<T, 8, MODE, ACT><<<p.grid, p.block, 0, st>>>(xp, dyp, p.g, gamma, beta, ws, tail);
@@ -559,6 +652,8 @@ static int launch_reduce(const void* x, const void* dy, int B, int C, int H, int
     }
   }
   QUAN_CHECK_LAUNCH("iqbn_reduce");
+  iqbn_fold_kernel<<<(4 * C + 7) / 8, 256, 0, st>>>(ws.part, nparts, tail);
+  QUAN_CHECK_LAUNCH("iqbn_fold");
   return QUAN_OK;
 }
 
@@ -572,8 +667,8 @@ static int launch_apply(const void* x, const void* dy, void* out, int B, int C, 
     LaunchB p;
     // measured on B200 (profiles/r01_iqbn_tune.log): the per-thread coefficient prologue makes many light blocks lose to
     // few blocks; U = 1 with 4 (fwd) / 2 (bwd) blocks per SM is the best point of the sweep
-    const int U = env_int("QUAN_IQBN_U", 1);
-    if (!plan_b<T>(B, C, H, W, U, BWD ? 2 : 4, p)) {
+    const int U = env_int("QUAN_IQBN_U", BWD ? 1 : 2);
+    if (!plan_b<T>(B, C, H, W, U, 8, p)) {
       set_error("iqbn: C=%d too large for the BHWQC kernels", C);
       return QUAN_E_UNSUPPORTED;
     }
@@ -625,7 +720,7 @@ using namespace quan;
 
 extern "C" {
 
-size_t quan_iqbn_workspace_bytes(int32_t C) { return (size_t)8 * C * sizeof(double) + 16; }
+size_t quan_iqbn_workspace_bytes(int32_t C) { return (size_t)IQBN_MAX_PARTS * 8 * C * sizeof(double); }
 
 static int reduce_entry(int mode, const void* x, const void* dy, int B, int C, int H, int W, int dtype, int layout,
                         const float* gamma, const float* beta, int act, TailArgs tail, void* workspace,
@@ -651,9 +746,9 @@ static int reduce_entry(int mode, const void* x, const void* dy, int B, int C, i
 }
 
 int quan_iqbn_train_stats(const void* x, int32_t B, int32_t C, int32_t H, int32_t W, int dtype, int layout,
-                          float eps, float momentum, float* running_mean, float* running_var, float* stats,
-                          void* workspace, size_t ws_bytes, void* stream) {
-  QUAN_REQUIRE(stats != nullptr, QUAN_E_ARG, "iqbn_train_stats: null stats");
+                          const float* gamma, const float* beta, float eps, float momentum, float* running_mean,
+                          float* running_var, float* stats, void* workspace, size_t ws_bytes, void* stream) {
+  QUAN_REQUIRE(stats != nullptr && gamma != nullptr && beta != nullptr, QUAN_E_ARG, "iqbn_train_stats: null pointer");
   QUAN_REQUIRE((running_mean == nullptr) == (running_var == nullptr), QUAN_E_ARG,
                "iqbn_train_stats: running_mean/var must both be given or both NULL");
   TailArgs t = {};
@@ -664,6 +759,8 @@ int quan_iqbn_train_stats(const void* x, int32_t B, int32_t C, int32_t H, int32_
   t.running_mean = running_mean;
   t.running_var = running_var;
   t.stats = stats;
+  t.gamma = gamma;
+  t.beta = beta;
   return reduce_entry(0, x, nullptr, B, C, H, W, dtype, layout, nullptr, nullptr, 0, t, workspace, ws_bytes, stream);
 }
 
@@ -677,39 +774,68 @@ int quan_iqbn_partial_sums(const void* x, int32_t B, int32_t C, int32_t H, int32
 }
 
 namespace quan {
-__global__ void iqbn_finalize_kernel(const double* __restrict__ sums, TailArgs t) {
+// mode 0: finalize forward stats from all-reduced raw sums; 1: eval-mode table from running stats;
+// 2: backward coefficient table from all-reduced backward sums
+__global__ void iqbn_small_kernel(int mode, const double* __restrict__ sums, const float* __restrict__ rm,
+                                  const float* __restrict__ rv, TailArgs t) {
   const int n = 4 * t.C;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    double mean = sums[i] / t.count;
-    double var = sums[n + i] / t.count - mean * mean;
-    if (var < 0.0) var = 0.0;
-    var += 1e-8;
-    t.stats[i] = (float)mean;
-    t.stats[n + i] = (float)var;
-    t.stats[2 * n + i] = (float)(1.0 / sqrt(var + (double)t.eps));
-    if (t.running_mean != nullptr) {
-      t.running_mean[i] = (1.0f - t.momentum) * t.running_mean[i] + t.momentum * (float)mean;
-      t.running_var[i] = (1.0f - t.momentum) * t.running_var[i] + t.momentum * (float)var;
+    if (mode == 0) {
+      write_fwd_stats(t, i, sums[i], sums[n + i]);
+    } else if (mode == 1) {
+      const float mean = rm[i], var = rv[i];
+      const float rstd = 1.0f / sqrtf(var + t.eps);            // conv.py:550 (no +1e-8 in eval)
+      const int c = i >> 2, q = i & 3;
+      const float scale = t.gamma[i] * rstd;
+      t.stats[i] = mean;
+      t.stats[n + i] = var;
+      t.stats[2 * n + i] = rstd;
+      t.stats[3 * n + q * t.C + c] = scale;
+      t.stats[4 * n + q * t.C + c] = t.beta[i] - mean * scale;
+    } else {
+      float* coef = reinterpret_cast<float*>(t.sums_out + 2 * n);
+      const int c = i >> 2, q = i & 3, j = q * t.C + c;
+      float k1, k2, k3;
+      bwd_coefficients(t.gamma[i], t.stats[i], t.stats[2 * n + i], sums[i], sums[n + i], t.count, k1, k2, k3);
+      coef[j] = k1;
+      coef[n + j] = k2;
+      coef[2 * n + j] = k3;
     }
   }
 }
+static int launch_small(int mode, const double* sums, const float* rm, const float* rv, const TailArgs& t, void* stream) {
+  int threads = 128, blocks = (4 * t.C + threads - 1) / threads;
+  iqbn_small_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(mode, sums, rm, rv, t);
+  QUAN_CHECK_LAUNCH("iqbn_small_kernel");
+  return QUAN_OK;
+}
 }  // namespace quan
 
-int quan_iqbn_finalize_stats(const double* sums, double count, int32_t C, float eps, float momentum,
-                             float* running_mean, float* running_var, float* stats, void* stream) {
-  QUAN_REQUIRE(sums != nullptr && stats != nullptr && C > 0 && count > 0, QUAN_E_ARG, "iqbn_finalize_stats: bad args");
+int quan_iqbn_finalize_stats(const double* sums, double count, int32_t C, const float* gamma, const float* beta, float eps,
+                             float momentum, float* running_mean, float* running_var, float* stats, void* stream) {
+  QUAN_REQUIRE(sums != nullptr && stats != nullptr && gamma != nullptr && beta != nullptr && C > 0 && count > 0, QUAN_E_ARG,
+               "iqbn_finalize_stats: bad args");
   TailArgs t = {};
-  t.C = C;
-  t.count = count;
-  t.eps = eps;
-  t.momentum = momentum;
-  t.running_mean = running_mean;
-  t.running_var = running_var;
-  t.stats = stats;
-  int threads = 128, blocks = (4 * C + threads - 1) / threads;
-  iqbn_finalize_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(sums, t);
-  QUAN_CHECK_LAUNCH("iqbn_finalize");
-  return QUAN_OK;
+  t.C = C; t.count = count; t.eps = eps; t.momentum = momentum;
+  t.running_mean = running_mean; t.running_var = running_var; t.stats = stats; t.gamma = gamma; t.beta = beta;
+  return launch_small(0, sums, nullptr, nullptr, t, stream);
+}
+
+int quan_iqbn_eval_stats(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                         float eps, int32_t C, float* stats, void* stream) {
+  QUAN_REQUIRE(gamma != nullptr && beta != nullptr && running_mean != nullptr && running_var != nullptr && stats != nullptr && C > 0,
+               QUAN_E_ARG, "iqbn_eval_stats: bad args");
+  TailArgs t = {};
+  t.C = C; t.eps = eps; t.stats = stats; t.gamma = gamma; t.beta = beta;
+  return launch_small(1, nullptr, running_mean, running_var, t, stream);
+}
+
+int quan_iqbn_bwd_coef(double* sums, double count, int32_t C, const float* stats, const float* gamma, void* stream) {
+  QUAN_REQUIRE(sums != nullptr && stats != nullptr && gamma != nullptr && C > 0 && count > 0, QUAN_E_ARG,
+               "iqbn_bwd_coef: bad args");
+  TailArgs t = {};
+  t.C = C; t.count = count; t.stats = const_cast<float*>(stats); t.gamma = gamma; t.sums_out = sums;
+  return launch_small(2, sums, nullptr, nullptr, t, stream);
 }
 
 static int apply_entry(bool bwd, const void* x, const void* dy, void* out, int B, int C, int H, int W, int dtype,
@@ -749,7 +875,7 @@ int quan_iqbn_eval_fwd(const void* x, void* y, int32_t B, int32_t C, int32_t H, 
 }
 
 int quan_iqbn_bwd_reduce(const void* dy, const void* x, int32_t B, int32_t C, int32_t H, int32_t W, int dtype,
-                         int layout, const float* stats, const float* gamma, const float* beta, int act,
+                         int layout, const float* stats, const float* gamma, const float* beta, int act, double count,
                          double* sums, void* workspace, size_t ws_bytes, void* stream) {
   QUAN_REQUIRE(dy != nullptr && stats != nullptr && sums != nullptr && gamma != nullptr && beta != nullptr,
                QUAN_E_ARG, "iqbn_bwd_reduce: null pointer");
@@ -757,6 +883,9 @@ int quan_iqbn_bwd_reduce(const void* dy, const void* x, int32_t B, int32_t C, in
   t.mode = TAIL_BWD_SUMS;
   t.stats = const_cast<float*>(stats);
   t.sums_out = sums;
+  t.count = count;
+  t.gamma = gamma;
+  t.beta = beta;
   return reduce_entry(1, x, dy, B, C, H, W, dtype, layout, gamma, beta, act, t, workspace, ws_bytes, stream);
 }
 
@@ -770,6 +899,7 @@ int quan_iqbn_bwd_apply(const void* dy, const void* x, void* dx, int32_t B, int3
   ApplyArgs a = {};
   a.gamma = gamma; a.beta = beta; a.stats = stats; a.sums = sums; a.count = count;
   a.dgamma = dgamma; a.dbeta = dbeta; a.C = C;
+  a.coefT = reinterpret_cast<const float*>(sums + 8 * (size_t)C);   // written by the bwd-reduce tail or quan_iqbn_bwd_coef
   return apply_entry(true, x, dy, dx, B, C, H, W, dtype, layout, a, act, mix_t, stream);
 }
 

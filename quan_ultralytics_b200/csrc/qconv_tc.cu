@@ -739,9 +739,20 @@ static bool plan_wgrad(const quan_conv_dims& d, int dtype, WgradPlan& w) {
   w.ci_blocks = d.Ci / (w.NA * w.NB);
   const int64_t combos = (int64_t)4 * w.tap_groups * w.co_blocks * w.ci_blocks;
   if (combos > 65535) return false;
-  int64_t splits = (2 * QUAN_NUM_SMS + combos - 1) / combos;
-  if (splits > w.nchunks) splits = w.nchunks;
-  if (splits < 1) splits = 1;
+  // split-K factor: 1 CTA/SM is resident, so pick the split count whose grid fills whole waves of 148 best
+  // (first ncu capture: 336 CTAs = 2.27 waves, i.e. a third wave at 27% occupancy)
+  int64_t splits = 1;
+  double best = 1e30;
+  const double flops = 8.0 * (double)d.B * Ho * Wo * d.Co * d.Ci * d.kH * d.kW;
+  const double part_bytes = 4.0 * d.kH * d.kW * (double)d.Co * d.Ci * 4.0;          // one split's fp32 partials
+  for (int64_t sp = 1; sp <= 24 && sp <= w.nchunks; ++sp) {
+    const int64_t ctas = combos * sp;
+    const int64_t waves = (ctas + QUAN_NUM_SMS - 1) / QUAN_NUM_SMS;
+    const double eff = (double)ctas / (double)(waves * QUAN_NUM_SMS);
+    // modelled time: tensor work at ~1 PFLOP/s scaled by wave fill + partial write/read at ~4 TB/s + per-CTA prologue
+    const double t = flops / (1.0e15 * eff) + sp * part_bytes * 2.0 / 4.0e12 + waves * 4.0e-6;
+    if (t < best) { best = t; splits = sp; }
+  }
   w.chunks_per_split = (int)((w.nchunks + splits - 1) / splits);
   w.splits = (w.nchunks + w.chunks_per_split - 1) / w.chunks_per_split;
   const size_t atom = (size_t)WG_PIX * 128;

@@ -94,10 +94,10 @@ class _IQBNTrain(torch.autograd.Function):
             sums = ops.iqbn_partial_sums(x, layout)
             dist.all_reduce(sums, group=group)
             count = float(B * H * W * world)
-            stats = ops.iqbn_finalize_stats(sums, count, C_, eps, momentum, running_mean, running_var)
+            stats = ops.iqbn_finalize_stats(sums, count, C_, g32, b32, eps, momentum, running_mean, running_var)
         else:
             count = float(B * H * W)
-            stats = ops.iqbn_train_stats(x, layout, eps, momentum, running_mean, running_var)
+            stats = ops.iqbn_train_stats(x, layout, g32, b32, eps, momentum, running_mean, running_var)
         y = ops.iqbn_apply_fwd(x, layout, stats, g32, b32, act)
         ctx.save_for_backward(x, stats, g32, b32)
         ctx.conf = (layout, act, count, group if world > 1 else None, gamma.dtype)
@@ -110,15 +110,17 @@ class _IQBNTrain(torch.autograd.Function):
         dy, _ = ops.as_layout(dy, layout)
         if dy.dtype != x.dtype:
             dy = dy.to(x.dtype)
-        sums = ops.iqbn_bwd_reduce(dy, x, layout, stats, g32, b32, act)
         C_ = x.size(1)
         if group is not None:
             # parameter grads stay LOCAL sums (DDP averages them); dx needs the global sums
+            sums = ops.iqbn_bwd_reduce(dy, x, layout, stats, g32, b32, act, 0.0)
             dbeta = sums[:4 * C_].to(torch.float32).view(C_, 4)
-            dgamma = sums[4 * C_:].to(torch.float32).view(C_, 4)
-            dist.all_reduce(sums, group=group)
+            dgamma = sums[4 * C_:8 * C_].to(torch.float32).view(C_, 4)
+            dist.all_reduce(sums[:8 * C_], group=group)
+            ops.iqbn_bwd_coef(sums, count, stats, g32)
             dx, _, _ = ops.iqbn_bwd_apply(dy, x, layout, stats, g32, b32, act, sums, count, want_param_grads=False)
         else:
+            sums = ops.iqbn_bwd_reduce(dy, x, layout, stats, g32, b32, act, count)
             dx, dgamma, dbeta = ops.iqbn_bwd_apply(dy, x, layout, stats, g32, b32, act, sums, count)
         if pdtype != torch.float32:
             dgamma, dbeta = dgamma.to(pdtype), dbeta.to(pdtype)
@@ -133,7 +135,8 @@ class _IQBNEval(torch.autograd.Function):
         rm, rv = ops._f32c(running_mean), ops._f32c(running_var)
         ctx.save_for_backward(x, g32, b32, rm, rv)
         ctx.conf = (layout, act, eps)
-        return ops.iqbn_eval_fwd(x, layout, g32, b32, rm, rv, eps, act)
+        stats = ops.iqbn_eval_stats(g32, b32, rm, rv, eps)          # [20C] table once, then the streaming apply kernel
+        return ops.iqbn_apply_fwd(x, layout, stats, g32, b32, act)
 
     @staticmethod
     def backward(ctx, dy):

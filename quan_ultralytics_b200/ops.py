@@ -194,15 +194,16 @@ def qupsample_bwd(dy: torch.Tensor, scale: int) -> torch.Tensor:
 
 
 # ---- IQBN ----------------------------------------------------------------------------------------------------------
-def iqbn_train_stats(x: torch.Tensor, layout: int, eps: float, momentum: float,
+def iqbn_train_stats(x: torch.Tensor, layout: int, gamma: torch.Tensor, beta: torch.Tensor, eps: float, momentum: float,
                      running_mean: Optional[torch.Tensor], running_var: Optional[torch.Tensor]) -> torch.Tensor:
-    """One launch: per-(c,q) mean / var(+1e-8) / rstd into stats[12C]; updates running stats in place."""
+    """One launch: per-(c,q) mean / var(+1e-8) / rstd + the scale/shift table into stats[20C]; updates running stats."""
     B, C_, H, W, _ = x.shape
-    stats = torch.empty(12 * C_, dtype=torch.float32, device=x.device)
+    stats = torch.empty(20 * C_, dtype=torch.float32, device=x.device)
     ws = _iqbn_workspace(C_, x.device)
-    check(_lib.load().quan_iqbn_train_stats(x.data_ptr(), B, C_, H, W, _dtype_code(x), layout, eps, momentum,
-                                            _ptr(running_mean), _ptr(running_var), stats.data_ptr(), ws.data_ptr(),
-                                            ws.numel(), _stream(x)), "quan_iqbn_train_stats")
+    check(_lib.load().quan_iqbn_train_stats(x.data_ptr(), B, C_, H, W, _dtype_code(x), layout, gamma.data_ptr(),
+                                            beta.data_ptr(), eps, momentum, _ptr(running_mean), _ptr(running_var),
+                                            stats.data_ptr(), ws.data_ptr(), ws.numel(), _stream(x)),
+          "quan_iqbn_train_stats")
     return stats
 
 
@@ -215,12 +216,22 @@ def iqbn_partial_sums(x: torch.Tensor, layout: int) -> torch.Tensor:
     return sums
 
 
-def iqbn_finalize_stats(sums: torch.Tensor, count: float, C_: int, eps: float, momentum: float,
+def iqbn_finalize_stats(sums: torch.Tensor, count: float, C_: int, gamma, beta, eps: float, momentum: float,
                         running_mean: Optional[torch.Tensor], running_var: Optional[torch.Tensor]) -> torch.Tensor:
-    stats = torch.empty(12 * C_, dtype=torch.float32, device=sums.device)
-    check(_lib.load().quan_iqbn_finalize_stats(sums.data_ptr(), float(count), C_, eps, momentum, _ptr(running_mean),
-                                               _ptr(running_var), stats.data_ptr(), _stream(sums)),
-          "quan_iqbn_finalize_stats")
+    stats = torch.empty(20 * C_, dtype=torch.float32, device=sums.device)
+    check(_lib.load().quan_iqbn_finalize_stats(sums.data_ptr(), float(count), C_, gamma.data_ptr(), beta.data_ptr(), eps,
+                                               momentum, _ptr(running_mean), _ptr(running_var), stats.data_ptr(),
+                                               _stream(sums)), "quan_iqbn_finalize_stats")
+    return stats
+
+
+def iqbn_eval_stats(gamma, beta, running_mean, running_var, eps: float) -> torch.Tensor:
+    """The [20C] coefficient table of eval-mode IQBN (running statistics); feed it to iqbn_apply_fwd."""
+    C_ = gamma.size(0)
+    stats = torch.empty(20 * C_, dtype=torch.float32, device=gamma.device)
+    check(_lib.load().quan_iqbn_eval_stats(gamma.data_ptr(), beta.data_ptr(), running_mean.data_ptr(),
+                                           running_var.data_ptr(), eps, C_, stats.data_ptr(), _stream(gamma)),
+          "quan_iqbn_eval_stats")
     return stats
 
 
@@ -244,14 +255,23 @@ def iqbn_eval_fwd(x: torch.Tensor, layout: int, gamma, beta, running_mean, runni
     return y
 
 
-def iqbn_bwd_reduce(dy: torch.Tensor, x: torch.Tensor, layout: int, stats, gamma, beta, act: int) -> torch.Tensor:
+def iqbn_bwd_reduce(dy: torch.Tensor, x: torch.Tensor, layout: int, stats, gamma, beta, act: int,
+                    count: float = 0.0) -> torch.Tensor:
+    """sums[14C] doubles: {sum dz, sum dz*xhat} + (when count > 0) the backward coefficient table."""
     B, C_, H, W, _ = x.shape
-    sums = torch.empty(8 * C_, dtype=torch.float64, device=x.device)
+    sums = torch.empty(14 * C_, dtype=torch.float64, device=x.device)
     ws = _iqbn_workspace(C_, x.device)
     check(_lib.load().quan_iqbn_bwd_reduce(dy.data_ptr(), x.data_ptr(), B, C_, H, W, _dtype_code(x), layout,
-                                           stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), act, sums.data_ptr(),
-                                           ws.data_ptr(), ws.numel(), _stream(x)), "quan_iqbn_bwd_reduce")
+                                           stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), act, float(count),
+                                           sums.data_ptr(), ws.data_ptr(), ws.numel(), _stream(x)), "quan_iqbn_bwd_reduce")
     return sums
+
+
+def iqbn_bwd_coef(sums: torch.Tensor, count: float, stats, gamma) -> None:
+    """Synced IQBN: build the backward coefficient table after sums[0:8C] were all-reduced."""
+    C_ = gamma.size(0)
+    check(_lib.load().quan_iqbn_bwd_coef(sums.data_ptr(), float(count), C_, stats.data_ptr(), gamma.data_ptr(),
+                                         _stream(sums)), "quan_iqbn_bwd_coef")
 
 
 def iqbn_bwd_apply(dy, x, layout: int, stats, gamma, beta, act: int, sums, count: float,

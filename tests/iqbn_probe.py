@@ -24,18 +24,18 @@ dys = [torch.randn_like(x) for x in xs]
 outs = [torch.empty_like(x) for x in xs]
 gamma, beta = torch.ones(C, 4, device=dev), torch.zeros(C, 4, device=dev)
 S = xs[0].numel() * xs[0].element_size()
-stats = ops.iqbn_train_stats(xs[0], L, 1e-5, 0.1, None, None)
-sums = ops.iqbn_bwd_reduce(dys[0], xs[0], L, stats, gamma, beta, Q.ACT_SILU)
 cnt = float(N * H * H)
+stats = ops.iqbn_train_stats(xs[0], L, gamma, beta, 1e-5, 0.1, None, None)
+sums = ops.iqbn_bwd_reduce(dys[0], xs[0], L, stats, gamma, beta, Q.ACT_SILU, cnt)
 i = [0]
 def rot():
     i[0] = (i[0] + 1) % 3
     return i[0]
 res = {}
-res["stats"] = (t(lambda: ops.iqbn_train_stats(xs[rot()], L, 1e-5, 0.1, None, None)), 1)
+res["stats"] = (t(lambda: ops.iqbn_train_stats(xs[rot()], L, gamma, beta, 1e-5, 0.1, None, None)), 1)
 res["apply"] = (t(lambda: ops.iqbn_apply_fwd(xs[rot()], L, stats, gamma, beta, Q.ACT_SILU)), 2)
 res["apply_noact"] = (t(lambda: ops.iqbn_apply_fwd(xs[rot()], L, stats, gamma, beta, Q.ACT_NONE)), 2)
-res["bwd_reduce"] = (t(lambda: ops.iqbn_bwd_reduce(dys[rot()], xs[i[0]], L, stats, gamma, beta, Q.ACT_SILU)), 2)
+res["bwd_reduce"] = (t(lambda: ops.iqbn_bwd_reduce(dys[rot()], xs[i[0]], L, stats, gamma, beta, Q.ACT_SILU, cnt)), 2)
 res["bwd_apply"] = (t(lambda: ops.iqbn_bwd_apply(dys[rot()], xs[i[0]], L, stats, gamma, beta, Q.ACT_SILU, sums, cnt)), 3)
 res["copy(torch)"] = (t(lambda: outs[rot()].copy_(xs[i[0]])), 2)
 tag = f"BPS={os.environ.get('QUAN_IQBN_BPS','-')} U={os.environ.get('QUAN_IQBN_U','-')}"

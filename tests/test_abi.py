@@ -46,9 +46,9 @@ def test_argument_errors_use_the_c_convention():
     mix = (ctypes.c_float * 16)(*([1.0] * 16))
     rc = lib.quan_qconv2d_fwd(1, 1, None, 1, ctypes.byref(d), 0, 0, ctypes.cast(mix, ctypes.c_void_p), 0, None, 0, None)
     assert rc == -2 and b"groups" in lib.quan_last_error()
-    assert lib.quan_iqbn_train_stats(None, 1, 1, 1, 1, 0, 0, 1e-5, 0.1, None, None, 1, None, 0, None) == -1
+    assert lib.quan_iqbn_train_stats(None, 1, 1, 1, 1, 0, 0, None, None, 1e-5, 0.1, None, None, 1, None, 0, None) == -1
     assert lib.quan_qupsample_nearest_fwd(1, 1, 1, 1, 1, 1, 0, 0, 0, None) == -1
     with pytest.raises(RuntimeError, match="argument/shape error"):
         _lib.check(-2, "quan_qconv2d_fwd")
-    assert lib.quan_iqbn_workspace_bytes(16) == 8 * 16 * 8 + 16
+    assert lib.quan_iqbn_workspace_bytes(16) == 592 * 8 * 16 * 8      # 4 x 148 row-split partials of [8C] fp64
     assert lib.quan_qconv2d_pick_algo(ctypes.byref(_lib.ConvDims(1, 4, 4, 8, 8, 3, 3, 1, 1, 1, 1, 1, 1, 1)), 1, 0, 0) == 1
