@@ -35,6 +35,9 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="block_stack", choices=["block_stack", "yolo11n_trace"],
+                    help="block_stack: BASELINE config[1] sweep point (default, the bench line); yolo11n_trace: replay of "
+                         "the 87 QConv2D / 84 IQBN+SiLU calls of QUAN-YOLO11n-OBB at 1024^2 (SURVEY 8(a) histogram)")
     ap.add_argument("--cq", type=int, default=256, help="quaternion channels per component")
     ap.add_argument("--hw", type=int, default=32)
     ap.add_argument("--n", type=int, default=64, help="images per GPU per step")
@@ -46,6 +49,7 @@ def parse_args():
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-table", action="store_true")
+    ap.add_argument("--graph", action="store_true", help="yolo11n_trace: capture the step in a CUDA graph (removes host launch overhead)")
     return ap.parse_args()
 
 
@@ -220,8 +224,150 @@ def kernel_table(a, dev, dtype, peaks):
     return rows
 
 
+# (C_i, C_o, k, s, groups, H_o, count): QConv2D calls of yolo11n-obb-quan @1024^2 per image (probed from the
+# reference with forward hooks); H_in = H_o * s.  The first row is the RGB first layer (Poincare map + C_i = 1 conv).
+YOLO11N_TRACE = [
+    (1, 4, 3, 2, 1, 512, 1), (4, 8, 3, 2, 1, 256, 1), (8, 8, 1, 1, 1, 256, 1), (4, 2, 3, 1, 1, 256, 1), (2, 4, 3, 1, 1, 256, 1),
+    (12, 16, 1, 1, 1, 256, 1), (16, 16, 3, 2, 1, 128, 1), (16, 16, 1, 1, 1, 128, 3), (8, 4, 3, 1, 1, 128, 2),
+    (4, 8, 3, 1, 1, 128, 2), (24, 32, 1, 1, 1, 128, 1), (24, 16, 1, 1, 1, 128, 1), (64, 16, 1, 1, 1, 128, 1),
+    (16, 16, 3, 1, 1, 128, 2), (16, 4, 3, 1, 1, 128, 1), (4, 4, 3, 1, 1, 128, 1), (16, 16, 3, 1, 16, 128, 2),
+    (32, 32, 3, 2, 1, 64, 1), (16, 16, 3, 2, 1, 64, 1), (32, 32, 1, 1, 1, 64, 1), (16, 8, 1, 1, 1, 64, 2), (8, 8, 3, 1, 1, 64, 4),
+    (16, 16, 1, 1, 1, 64, 2), (48, 32, 1, 1, 1, 64, 4), (96, 32, 1, 1, 1, 64, 1), (16, 8, 3, 1, 1, 64, 2), (8, 16, 3, 1, 1, 64, 2),
+    (32, 16, 3, 1, 1, 64, 1), (16, 16, 3, 1, 1, 64, 1), (32, 16, 1, 1, 1, 64, 1), (32, 4, 3, 1, 1, 64, 1), (4, 4, 3, 1, 1, 64, 1),
+    (32, 32, 3, 1, 32, 64, 1), (16, 16, 3, 1, 16, 64, 1), (32, 64, 3, 2, 1, 32, 1), (32, 32, 3, 2, 1, 32, 1),
+    (64, 64, 1, 1, 1, 32, 3), (32, 16, 1, 1, 1, 32, 4), (16, 16, 3, 1, 1, 32, 9), (32, 32, 1, 1, 1, 32, 3), (96, 64, 1, 1, 1, 32, 3),
+    (64, 32, 1, 1, 1, 32, 2), (128, 64, 1, 1, 1, 32, 1), (32, 64, 1, 1, 1, 32, 2), (32, 32, 3, 1, 32, 32, 1),
+    (64, 16, 3, 1, 1, 32, 1), (64, 16, 1, 1, 1, 32, 1), (64, 4, 3, 1, 1, 32, 1), (4, 4, 3, 1, 1, 32, 1), (64, 64, 3, 1, 64, 32, 1),
+    (16, 16, 1, 1, 1, 32, 1), (16, 16, 3, 1, 16, 32, 1),
+]
+
+
+def run_yolo11n_trace(a):
+    """Hot-path replay of one QUAN-YOLO11n-OBB training step at 1024^2: every QConv2D (+ IQBN + SiLU) call of the model
+    with its real shape, forward + backward, on synthetic activations.  Glue the reference does in Python (concat, split,
+    attention matmuls, heads, loss) is not part of the path and not replayed."""
+    import quan_ultralytics_b200 as Q
+    lib = Q._lib.load()
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    dtype = torch.bfloat16 if a.dtype == "bf16" else torch.float32
+    B = a.n
+    assert sum(r[6] for r in YOLO11N_TRACE) == 87
+    torch.manual_seed(0)
+    layers = []
+    fwd_flops = 0
+    bn_elems = 0
+    for ci, co, k, s, g, ho, cnt in YOLO11N_TRACE:
+        hin = ho * s
+        for rep in range(cnt):
+            bare = (ci, co, k, ho) == (64, 64, 1, 32)              # the three BN-less QConv2Ds of QAttention
+            if ci == 1:
+                mod = Q.Conv(3, co * 4, k, s).to(dev).train()
+                x = torch.rand(B, 3, hin, hin, device=dev)
+            else:
+                mod = (Q.QConv2D(ci * 4, co * 4, k, s, k // 2, groups=g, bias=False) if bare
+                       else Q.Conv(ci * 4, co * 4, k, s, g=g)).to(dev).train()
+                x = torch.randn(B, ci, hin, hin, 4, device=dev).to(dtype).contiguous(memory_format=torch.channels_last_3d)
+                x.requires_grad_(True)
+            dy = torch.randn(B, co, ho, ho, 4, device=dev).to(dtype).contiguous(memory_format=torch.channels_last_3d)
+            layers.append((mod, x, dy))
+            fwd_flops += 4 * 2 * ho * ho * co * (ci // g) * k * k
+            bn_elems += 0 if bare else co * ho * ho * 4
+    params = [p for m, _, _ in layers for p in m.parameters()]
+
+    def step():
+        for p in params:
+            p.grad = None
+        for mod, x, dy in layers:
+            if x.grad is not None:
+                x.grad = None
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=(dtype == torch.bfloat16)):
+                y = mod(x)
+            y.backward(dy)
+
+    for _ in range(max(a.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    if os.environ.get("QUAN_TRACE_DETAIL"):
+        rows = []
+        i = 0
+        for ci, co, k, s, g, ho, cnt in YOLO11N_TRACE:
+            mod, x, dy = layers[i]
+            i += cnt
+
+            def f():
+                with torch.autocast("cuda", dtype=torch.bfloat16, enabled=(dtype == torch.bfloat16)):
+                    return mod(x)
+            y = f()
+            tf = time_op(f, 5)
+            tfb = time_op(lambda: f().backward(dy), 5)
+            from quan_ultralytics_b200 import ops as _ops
+            algo = [_ops.qconv2d_pick_algo((B, max(ci, 1), ho * s, ho * s, 4), (co, ci // g, k, k), (s, s), (k // 2, k // 2), (1, 1),
+                                            g, dtype, _ops.LAYOUT_BHWQC, ps) for ps in range(3)]
+            rows.append((cnt * tfb, f"({ci},{co},k{k},s{s},g{g},{ho}^2)x{cnt}: fwd {tf:.3f} ms, fwd+bwd {tfb:.3f} ms, algo {algo}"))
+        tot = sum(r[0] for r in rows)
+        for t, txt in sorted(rows, reverse=True):
+            print(f"{100 * t / tot:5.1f}%  {txt}", flush=True)
+    run = step
+    launches_per_step = None
+    if a.graph:
+        # the library's workspaces are static and every launch goes to the current stream, so a whole step captures
+        n0 = lib.quan_launch_count()
+        step()
+        launches_per_step = lib.quan_launch_count() - n0
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            step()
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            step()
+        run = graph.replay
+        for _ in range(2):
+            run()
+        torch.cuda.synchronize()
+    sampler = ClockSampler(0)
+    sampler.start()
+    time.sleep(0.3)
+    n0 = lib.quan_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        run()
+    e1.record()
+    e1.synchronize()
+    ms = e0.elapsed_time(e1)
+    launches = lib.quan_launch_count() - n0
+    if launches_per_step is not None:
+        launches = launches_per_step * a.steps          # replayed by the graph, counted when it was recorded
+    clocks = sampler.stop()
+    peaks = load_peaks()
+    esz = 2 if dtype == torch.bfloat16 else 4
+    t_step = ms / a.steps / 1e3
+    # per-image roofline of the replayed path: sum over layers of max(FLOPs/peak, bytes/BW) is approximated by the two totals
+    flops_img = 3 * fwd_flops
+    bytes_img = 8 * bn_elems * esz                     # IQBN 3S fwd + 5S bwd (SURVEY §8(d)); conv traffic comes on top
+    line = {
+        "metric": "train_images_per_sec", "value": B * a.steps / (ms / 1e3), "unit": "images/s", "n_gpus": 1,
+        "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": a.dtype, "data": "synthetic",
+        "config": {"workload": f"yolo11n_obb_quan_hotpath_trace(1024x1024,B={B}): 87 QConv2D + 84 IQBN.SiLU fwd+bwd, per-layer replay",
+                   "qconv_gflop_per_image_train": flops_img / 1e9, "iqbn_melems_per_image": bn_elems / 1e6},
+        "gpu_launches": int(launches), "clocks": clocks, "cuda_graph": bool(a.graph),
+        "hotpath_tflops": flops_img * B / t_step / 1e12,
+        "roofline_floor_ms_per_step": 1e3 * B * max(flops_img / (peaks["bf16_tflops"] * 1e12), bytes_img / (peaks["hbm_gbs"] * 1e9)),
+    }
+    print(json.dumps(line))
+
+
 def main():
     a = parse_args()
+    if a.workload == "yolo11n_trace" and a.impl == "ours":
+        if a.n == 64:
+            a.n = 16
+        run_yolo11n_trace(a)
+        return
     if a.impl == "reference":
         reference_arm(a)
         return
