@@ -100,36 +100,46 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restri
 // forward / dgrad implicit-GEMM kernel
 // ---------------------------------------------------------------------------------------------------------------
 struct TcConvParams {
-  int B, Ho, Wo, Cout;                 // output tensor [B][Ho][Wo][4][Cout]
+  int B, Ho, Wo, Cout;                 // output tensor [B][Ho][Wo][NQ][Cout]
   int Wt, Ht, Bt, tiles_w, tiles_h;    // 128-pixel tile = Bt x Ht x Wt (w fastest), tiles per image plane
+  int ntiles_n, units;                 // N tiles; work units = (pixel tile [pair], N tile), N fastest
   int kH, kW, sH, sW, pH, pW, dH, dW;
   int kblocks, bk_elems;               // k-blocks per tap, elements per k-block row
   int sub;                             // (tap, k-block) sub-steps bundled into one pipeline stage (1 or 2)
   int BN, stages;
   uint32_t a_sub_bytes, b_sub_bytes;   // one sub-step's A / B tile (per CTA)
   uint32_t sbo_bytes, layout_type, idesc, tmem_cols;
-  const float* bias;                   // [Cout] or null (joins S_r before the mix)
+  const float* bias;                   // NQ = 4: [Cout], joins S_r before the mix; NQ = 1: [Cout] added to the output
   Mix16 mix;
 };
 
-constexpr int TC_THREADS = 192;   // warp 0: TMA producer, warp 1: TMEM alloc + MMA issuer, warps 2-5: epilogue
+constexpr int TC_THREADS = 192;    // wgrad kernel: warp 0 TMA producer, warp 1 TMEM alloc + MMA issuer, warps 2-5 epilogue
+constexpr int EPI_WARPS = 8;       // igemm kernel: two epilogue warps per TMEM lane quarter (they split the columns)
+constexpr int IG_THREADS = 64 + 32 * EPI_WARPS;
 
-// CG = 1: one CTA per 128-pixel tile.  CG = 2: a CTA pair (cluster of 2) drives tcgen05.mma.cta_group::2 — M = 256
-// (each CTA's own 128-pixel A tile), the BN x BK weight tile is split in halves between the two CTAs' shared memory, so
-// per-CTA L2->SM and SM-local operand traffic drop from (A + B) to (A + B/2) per step.
+// Persistent implicit-GEMM kernel.  One CTA (CG = 1) or CTA pair (CG = 2, tcgen05.mma.cta_group::2, M = 256, the
+// BN x BK weight tile split across the pair's shared memory) per SM loops over work units; the three roles run as
+// independent pipelines that only meet at mbarriers, so TMA loads of unit u+1 and, as far as TMEM allows, its MMAs
+// overlap the epilogue of unit u:
+//   NQ = 4 (separable form): TMEM holds the four component accumulators S_q (4*BN <= 512 columns — no room for a second
+//     set).  The epilogue first copies S_0 into registers and hands accumulator 0 back, so the next unit's q = 0
+//     mainloop (a quarter of its MMAs) runs while S_1..S_3 are drained, mixed with the stashed S_0 and stored.
+//   NQ = 1 (dense Hamilton form for narrow layers: channels = 4*C_q, mixing matrix folded into the packed weights):
+//     two accumulators of BN <= 256 columns alternate between units.
 // KSTEPS = UMMAs per sub-step (row bytes / 32), compile time so the issue sequence is branch-free.
 //
-// What bounds this kernel (clock64 / debug-switch experiments on B200, profiles/r01_conv_issue_experiments.md): not the
-// loads (removing every TMA changes nothing) but the MMA-issuing thread — a UTCHMMA M128 N128 K16 holds the issuing
-// thread for about its 64-cycle execution time, so the tensor pipe is busy only while that thread issues, and every
-// other cycle of its loop iteration (barrier wait, commit, bookkeeping: ~250 cycles) is tensor idle time.  Hence
-// (1) role loops are warp-uniform with `elect.sync` around the single-thread instructions (a divergent `lane == 0`
-// loop makes the compiler re-uniformise each UTCHMMA operand: +70 cycles per MMA), and (2) a pipeline stage bundles
-// `sub` (tap, k-block) steps, i.e. 8 MMAs per barrier round trip instead of 4.
-template <typename T, bool MIX, int CG, int KSTEPS>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+// What bounded the non-persistent version (clock64 / debug-switch experiments, profiles/r01_conv_issue_experiments.md):
+// not the loads but the MMA-issuing thread — a UTCHMMA M128 N128 K16 holds the issuing thread for about its 64-cycle
+// execution time, so the tensor pipe is busy only while that thread issues.  Hence (1) role loops are warp-uniform with
+// `elect.sync` around the single-thread instructions, (2) a pipeline stage bundles `sub` (tap, k-block) steps, and
+// (3) this persistent form removes the per-CTA prologue and all but the S_0 copy of the epilogue from the MMA
+// thread's critical path.
+template <typename T, bool MIX, int CG, int KSTEPS, int NQ>
+__global__ void __launch_bounds__(IG_THREADS, 1)
 qconv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, T* __restrict__ y,
                    const TcConvParams p) {
+  constexpr int NACC = NQ == 4 ? 4 : 2;   // TMEM accumulators of BN columns
+  constexpr int NTB = NACC / NQ;          // units that can be in flight in TMEM (tile_full barriers)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment is required by the 128B swizzle atoms
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -138,21 +148,16 @@ qconv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   uint8_t* smem_b = smem + (size_t)p.stages * a_stage_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + (size_t)p.stages * b_stage_bytes);
   uint64_t* empty_bar = full_bar + p.stages;
-  uint64_t* tmem_full_bar = empty_bar + p.stages;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tile_full = empty_bar + p.stages;     // [2]  MMA -> epilogue: all accumulators of a unit are complete
+  uint64_t* acc_empty = tile_full + 2;            // [4]  epilogue -> MMA: accumulator a has been read out
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 4);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform
   const int lane = threadIdx.x & 31;
   constexpr int KIND = sizeof(T) == 2 ? 0 : 1;
-
-  // tile coordinates
-  const int tile = blockIdx.x;
-  const int tw = tile % p.tiles_w;
-  const int th = (tile / p.tiles_w) % p.tiles_h;
-  const int tb = tile / (p.tiles_w * p.tiles_h);
-  const int w0 = tw * p.Wt, h0 = th * p.Ht, b0 = tb * p.Bt;
-  const int n0 = blockIdx.y * p.BN;
   const uint32_t cta_rank = CG == 2 ? ptx::cluster_ctarank() : 0u;
+  const int cluster = CG == 2 ? (int)ptx::cluster_id_x() : (int)blockIdx.x;
+  const int nclusters = CG == 2 ? (int)ptx::cluster_nctaid_x() : (int)gridDim.x;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&map_a);
@@ -161,7 +166,8 @@ qconv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       ptx::mbar_init(full_bar + s, 1);
       ptx::mbar_init(empty_bar + s, 1);
     }
-    ptx::mbar_init(tmem_full_bar, 1);
+    for (int i = 0; i < 2; ++i) ptx::mbar_init(tile_full + i, 1);
+    for (int i = 0; i < 4; ++i) ptx::mbar_init(acc_empty + i, EPI_WARPS * CG);
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
@@ -176,38 +182,45 @@ qconv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 
   const int taps = p.kH * p.kW;
   const int iters_per_q = taps * p.kblocks;          // (tap, k-block) steps per component
+  const int tiles_per_b = p.tiles_w * p.tiles_h;
 
   if (warp == 0) {
     // ===== TMA producer: warp-uniform loop; one elected lane issues.  Counters instead of div/mod. =====
     const uint32_t sub_tx = (p.a_sub_bytes + p.b_sub_bytes) * CG;   // CG = 2: the leader's barrier counts both CTAs' bytes
-    const int wbase = w0 * p.sW - p.pW, hbase = h0 * p.sH - p.pH;
-    const int nb0 = n0 + (int)cta_rank * (p.BN / CG);               // this CTA's slice of the weight tile
     int s = 0;
     uint32_t phase = 0;
-    for (int q = 0; q < 4; ++q) {
-      int tap = 0, kh = 0, kw = 0, kb = 0;
-      for (int i = 0; i < iters_per_q; i += p.sub) {
-        const int nsub = min(p.sub, iters_per_q - i);
-        ptx::mbar_wait(empty_bar + s, phase ^ 1);
-        const bool leader = ptx::elect_one();
-        if (leader && (CG == 1 || cta_rank == 0)) ptx::mbar_arrive_expect_tx(full_bar + s, sub_tx * nsub);
-        for (int u = 0; u < nsub; ++u) {
-          if (leader) {
-            uint8_t* a_dst = smem_a + (size_t)s * a_stage_bytes + (size_t)u * p.a_sub_bytes;
-            uint8_t* b_dst = smem_b + (size_t)s * b_stage_bytes + (size_t)u * p.b_sub_bytes;
-            const int wc = wbase + kw * p.dW, hc = hbase + kh * p.dH, kc = kb * p.bk_elems;
-            if constexpr (CG == 2) {
-              ptx::tma_load_5d_2cta(a_dst, &map_a, full_bar + s, kc, q, wc, hc, b0);
-              ptx::tma_load_4d_2cta(b_dst, &map_b, full_bar + s, kc, nb0, tap, q);
-            } else {
-              ptx::tma_load_5d(a_dst, &map_a, full_bar + s, kc, q, wc, hc, b0);
-              ptx::tma_load_4d(b_dst, &map_b, full_bar + s, kc, n0, tap, q);
+    for (int unit = cluster; unit < p.units; unit += nclusters) {
+      const int nt = unit % p.ntiles_n, tile = (unit / p.ntiles_n) * CG + (int)cta_rank;
+      const int tw = tile % p.tiles_w, th = (tile / p.tiles_w) % p.tiles_h, tb = tile / tiles_per_b;
+      const int b0 = tb * p.Bt;
+      const int wbase = tw * p.Wt * p.sW - p.pW, hbase = th * p.Ht * p.sH - p.pH;
+      const int n0 = nt * p.BN;
+      const int nb0 = n0 + (int)cta_rank * (p.BN / CG);             // this CTA's slice of the weight tile
+      for (int q = 0; q < NQ; ++q) {
+        int tap = 0, kh = 0, kw = 0, kb = 0;
+        for (int i = 0; i < iters_per_q; i += p.sub) {
+          const int nsub = min(p.sub, iters_per_q - i);
+          ptx::mbar_wait(empty_bar + s, phase ^ 1);
+          const bool leader = ptx::elect_one();
+          if (leader && (CG == 1 || cta_rank == 0)) ptx::mbar_arrive_expect_tx(full_bar + s, sub_tx * nsub);
+          for (int u = 0; u < nsub; ++u) {
+            if (leader) {
+              uint8_t* a_dst = smem_a + (size_t)s * a_stage_bytes + (size_t)u * p.a_sub_bytes;
+              uint8_t* b_dst = smem_b + (size_t)s * b_stage_bytes + (size_t)u * p.b_sub_bytes;
+              const int wc = wbase + kw * p.dW, hc = hbase + kh * p.dH, kc = kb * p.bk_elems;
+              if constexpr (CG == 2) {
+                ptx::tma_load_5d_2cta(a_dst, &map_a, full_bar + s, kc, q, wc, hc, b0);
+                ptx::tma_load_4d_2cta(b_dst, &map_b, full_bar + s, kc, nb0, tap, q);
+              } else {
+                ptx::tma_load_5d(a_dst, &map_a, full_bar + s, kc, q, wc, hc, b0);
+                ptx::tma_load_4d(b_dst, &map_b, full_bar + s, kc, n0, tap, q);
+              }
             }
+            if (++kb == p.kblocks) { kb = 0; ++tap; if (++kw == p.kW) { kw = 0; ++kh; } }
           }
-          if (++kb == p.kblocks) { kb = 0; ++tap; if (++kw == p.kW) { kw = 0; ++kh; } }
+          __syncwarp();
+          if (++s == p.stages) { s = 0; phase ^= 1; }
         }
-        __syncwarp();
-        if (++s == p.stages) { s = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -221,83 +234,156 @@ qconv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       int s = 0;
       uint32_t phase = 0;
       uint64_t da = da0, db = db0;
-      for (int q = 0; q < 4; ++q) {
-        const uint32_t d_tmem = tmem_u + (uint32_t)(q * p.BN);
-        for (int i = 0; i < iters_per_q; i += p.sub) {
-          const int nsub = min(p.sub, iters_per_q - i);
-          ptx::mbar_wait(full_bar + s, phase);
+      uint32_t t_local = 0;
+      for (int unit = cluster; unit < p.units; unit += nclusters, ++t_local) {
+        for (int q = 0; q < NQ; ++q) {
+          // accumulator a is reused every NACC/NQ units: wait until the epilogue warps (of both CTAs) have read it out
+          const uint32_t a = NQ == 4 ? (uint32_t)q : (t_local & 1u);
+          const uint32_t use = NQ == 4 ? t_local : (t_local >> 1);
+          ptx::mbar_wait(acc_empty + a, (use & 1u) ^ 1u);
           ptx::tc_fence_after();
-          if (ptx::elect_one()) {
-            for (int u = 0; u < nsub; ++u) {
-              const uint64_t dau = da + (uint64_t)u * a_sub, dbu = db + (uint64_t)u * b_sub;
+          const uint32_t d_tmem = tmem_u + a * (uint32_t)p.BN;
+          for (int i = 0; i < iters_per_q; i += p.sub) {
+            const int nsub = min(p.sub, iters_per_q - i);
+            ptx::mbar_wait(full_bar + s, phase);
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {
+              for (int u = 0; u < nsub; ++u) {
+                const uint64_t dau = da + (uint64_t)u * a_sub, dbu = db + (uint64_t)u * b_sub;
 #pragma unroll
-              for (int k = 0; k < KSTEPS; ++k) {
-                // advance 32 bytes (one UMMA_K slice) inside the swizzle row: +2 in the 16-byte-unit start-address field
-                if constexpr (CG == 2)
-                  ptx::umma_2cta<KIND>(d_tmem, dau + (uint64_t)(2 * k), dbu + (uint64_t)(2 * k), p.idesc, (i | u | k) ? 1u : 0u);
-                else
-                  ptx::umma<KIND>(d_tmem, dau + (uint64_t)(2 * k), dbu + (uint64_t)(2 * k), p.idesc, (i | u | k) ? 1u : 0u);
+                for (int k = 0; k < KSTEPS; ++k) {
+                  // advance 32 bytes (one UMMA_K slice) inside the swizzle row: +2 in the 16-byte-unit start-address field
+                  if constexpr (CG == 2)
+                    ptx::umma_2cta<KIND>(d_tmem, dau + (uint64_t)(2 * k), dbu + (uint64_t)(2 * k), p.idesc, (i | u | k) ? 1u : 0u);
+                  else
+                    ptx::umma<KIND>(d_tmem, dau + (uint64_t)(2 * k), dbu + (uint64_t)(2 * k), p.idesc, (i | u | k) ? 1u : 0u);
+                }
               }
+              // frees the smem slot (in both CTAs when CG = 2) once these MMAs have read it
+              if constexpr (CG == 2) ptx::umma_commit_2cta(empty_bar + s, 3);
+              else ptx::umma_commit(empty_bar + s);
             }
-            // frees the smem slot (in both CTAs when CG = 2) once these MMAs have read it
-            if constexpr (CG == 2) ptx::umma_commit_2cta(empty_bar + s, 3);
-            else ptx::umma_commit(empty_bar + s);
+            __syncwarp();
+            da += a_step;
+            db += b_step;
+            if (++s == p.stages) { s = 0; phase ^= 1; da = da0; db = db0; }
           }
-          __syncwarp();
-          da += a_step;
-          db += b_step;
-          if (++s == p.stages) { s = 0; phase ^= 1; da = da0; db = db0; }
         }
+        // every accumulator of this unit is complete once the MMAs issued so far have retired
+        if (ptx::elect_one()) {
+          uint64_t* tf = tile_full + (NTB == 2 ? (t_local & 1u) : 0u);
+          if constexpr (CG == 2) ptx::umma_commit_2cta(tf, 3);
+          else ptx::umma_commit(tf);
+        }
+        __syncwarp();
       }
-      // all four accumulators complete
-      if (ptx::elect_one()) {
-        if constexpr (CG == 2) ptx::umma_commit_2cta(tmem_full_bar, 3);
-        else ptx::umma_commit(tmem_full_bar);
-      }
-      __syncwarp();
     }
   } else {
-    // ===== epilogue: warps 2..5 own TMEM lane quarters (warp % 4) =====
+    // ===== epilogue: warps 2..9; TMEM lane quarter = warp % 4, the two warps of a quarter take alternate 16-column chunks =====
     const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int m = quarter * 32 + lane;                 // accumulator row = pixel within the tile
     const int wt = m % p.Wt, ht = (m / p.Wt) % p.Ht, bt = m / (p.Wt * p.Ht);
-    const int wo = w0 + wt, ho = h0 + ht, b = b0 + bt;
-    const bool valid = (wo < p.Wo) && (ho < p.Ho) && (b < p.B);
-    T* yrow = y + ((((int64_t)b * p.Ho + ho) * p.Wo + wo) * 4) * p.Cout + n0;
-    ptx::mbar_wait(tmem_full_bar, 0);
-    ptx::tc_fence_after();
     const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    for (int c0 = 0; c0 < p.BN; c0 += 16) {
-      float acc[4][16];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) ptx::tmem_ld16(lane_base + (uint32_t)(q * p.BN + c0), acc[q]);
-      ptx::tmem_ld_wait();
-      if (p.bias != nullptr) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) acc[0][j] += __ldg(p.bias + n0 + c0 + j);
+    const int nchunks = p.BN >> 4;
+    constexpr int VW = 16 / sizeof(T);                 // elements per 16-byte store
+    uint32_t t_local = 0;
+    auto release = [&](uint64_t* bar) {                // one arrival per epilogue warp (TMEM reads of this warp are done)
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (ptx::elect_one()) {
+        if constexpr (CG == 2) ptx::mbar_arrive_cluster(bar, 0);
+        else ptx::mbar_arrive(bar);
       }
-      if (valid) {
+      __syncwarp();
+    };
+    for (int unit = cluster; unit < p.units; unit += nclusters, ++t_local) {
+      const int nt = unit % p.ntiles_n, tile = (unit / p.ntiles_n) * CG + (int)cta_rank;
+      const int tw = tile % p.tiles_w, th = (tile / p.tiles_w) % p.tiles_h, tb = tile / tiles_per_b;
+      const int wo = tw * p.Wt + wt, ho = th * p.Ht + ht, b = tb * p.Bt + bt;
+      const int n0 = nt * p.BN;
+      const bool valid = (wo < p.Wo) && (ho < p.Ho) && (b < p.B);
+      T* yrow = y + ((((int64_t)b * p.Ho + ho) * p.Wo + wo) * NQ) * p.Cout + n0;
+      if constexpr (NQ == 4) {
+        ptx::mbar_wait(tile_full, t_local & 1u);
+        ptx::tc_fence_after();
+        // stash this warp's chunks of S_0, then hand accumulator 0 back to the MMA thread
+        float st[4][16];
 #pragma unroll
-        for (int pc = 0; pc < 4; ++pc) {
-          float o[16];
+        for (int ci = 0; ci < 4; ++ci)
+          if (ci * 2 + half < nchunks) ptx::tmem_ld16(lane_base + (uint32_t)((ci * 2 + half) * 16), st[ci]);
+        ptx::tmem_ld_wait();
+        release(acc_empty + 0);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            if constexpr (MIX)
-              o[j] = p.mix.m[pc * 4 + 0] * acc[0][j] + p.mix.m[pc * 4 + 1] * acc[1][j] + p.mix.m[pc * 4 + 2] * acc[2][j] +
-                     p.mix.m[pc * 4 + 3] * acc[3][j];
-            else
-              o[j] = acc[pc][j];
-          }
-          T* dst = yrow + (int64_t)pc * p.Cout + c0;
-          constexpr int VW = 16 / sizeof(T);   // elements per 16-byte store
+        for (int ci = 0; ci < 4; ++ci) {
+          const int c0 = (ci * 2 + half) * 16;
+          if (ci * 2 + half < nchunks) {
+            float acc[3][16];
 #pragma unroll
-          for (int v = 0; v < 16 / VW; ++v) {
-            float part[VW];
+            for (int q = 1; q < 4; ++q) ptx::tmem_ld16(lane_base + (uint32_t)(q * p.BN + c0), acc[q - 1]);
+            ptx::tmem_ld_wait();
+            if (p.bias != nullptr) {
 #pragma unroll
-            for (int j = 0; j < VW; ++j) part[j] = o[v * VW + j];
-            store_vec<T, VW>(dst + v * VW, part);
+              for (int j = 0; j < 16; ++j) st[ci][j] += __ldg(p.bias + n0 + c0 + j);
+            }
+            if (valid) {
+#pragma unroll
+              for (int pc = 0; pc < 4; ++pc) {
+                float o[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  if constexpr (MIX)
+                    o[j] = p.mix.m[pc * 4 + 0] * st[ci][j] + p.mix.m[pc * 4 + 1] * acc[0][j] + p.mix.m[pc * 4 + 2] * acc[1][j] +
+                           p.mix.m[pc * 4 + 3] * acc[2][j];
+                  else
+                    o[j] = pc == 0 ? st[ci][j] : acc[pc == 0 ? 0 : pc - 1][j];
+                }
+                T* dst = yrow + (int64_t)pc * p.Cout + c0;
+#pragma unroll
+                for (int v = 0; v < 16 / VW; ++v) {
+                  float part[VW];
+#pragma unroll
+                  for (int j = 0; j < VW; ++j) part[j] = o[v * VW + j];
+                  store_vec<T, VW>(dst + v * VW, part);
+                }
+              }
+            }
           }
         }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (ptx::elect_one()) {
+#pragma unroll
+          for (int a = 1; a < 4; ++a) {
+            if constexpr (CG == 2) ptx::mbar_arrive_cluster(acc_empty + a, 0);
+            else ptx::mbar_arrive(acc_empty + a);
+          }
+        }
+        __syncwarp();
+      } else {
+        const uint32_t a = t_local & 1u;
+        ptx::mbar_wait(tile_full + a, (t_local >> 1) & 1u);
+        ptx::tc_fence_after();
+        for (int c = half; c < nchunks; c += 2) {
+          const int c0 = c * 16;
+          float acc[16];
+          ptx::tmem_ld16(lane_base + a * (uint32_t)p.BN + (uint32_t)c0, acc);
+          ptx::tmem_ld_wait();
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[j] += __ldg(p.bias + n0 + c0 + j);
+          }
+          if (valid) {
+#pragma unroll
+            for (int v = 0; v < 16 / VW; ++v) {
+              float part[VW];
+#pragma unroll
+              for (int j = 0; j < VW; ++j) part[j] = acc[v * VW + j];
+              store_vec<T, VW>(yrow + c0 + v * VW, part);
+            }
+          }
+        }
+        release(acc_empty + a);
       }
     }
     ptx::tc_fence_before();
@@ -504,8 +590,8 @@ static int pow2_ceil(int v) {
   while (r < v) r <<= 1;
   return r;
 }
-static int pick_bn(int n) {   // largest multiple of 16 that is <= 128 and divides n
-  for (int bn = 128; bn >= 16; bn -= 16)
+static int pick_bn(int n, int cap) {   // largest multiple of 16 that is <= cap and divides n
+  for (int bn = cap; bn >= 16; bn -= 16)
     if (n % bn == 0) return bn;
   return 0;
 }
@@ -535,14 +621,16 @@ static bool plan_tiles(int B, int Ho, int Wo, int sH, int sW, TilePlan& t) {
 }
 
 // geometry of a conv expressed as "output [B,Ho,Wo,N] from input [B,Hi,Wi,K]" (dgrad swaps the roles)
+// nq = 4: separable form, tensors [B][H][W][4][K or N]; nq = 1: dense Hamilton form, K and N count all 4*C_q real channels
 struct IgemmShape {
-  int B, Hi, Wi, K, Ho, Wo, N, kH, kW, sH, sW, pH, pW, dH, dW;
+  int B, Hi, Wi, K, Ho, Wo, N, kH, kW, sH, sW, pH, pW, dH, dW, nq;
 };
+static int bn_cap(int nq) { return nq == 4 ? 128 : 256; }   // TMEM: 4 accumulators of BN, or 2 of BN
 
 static bool igemm_supported(const IgemmShape& s, int dtype) {
   const int esz = dtype == QUAN_BF16 ? 2 : 4;
   if (pick_row_bytes(s.K, esz) == 0) return false;
-  if (pick_bn(s.N) == 0) return false;
+  if (pick_bn(s.N, bn_cap(s.nq)) == 0) return false;
   if ((s.N * esz) % 16 != 0 || (s.K * esz) % 16 != 0) return false;
   if (s.sH > 8 || s.sW > 8) return false;             // TMA element-stride limit
   TilePlan t;
@@ -555,43 +643,52 @@ static size_t packed_weight_bytes(const quan_conv_dims& d, int dtype) {
   return ((size_t)4 * d.kH * d.kW * d.Co * d.Ci * (dtype == QUAN_BF16 ? 2 : 4) + 1023) / 1024 * 1024;
 }
 
-template <typename T, bool MIX, int CG, int KSTEPS>
-static int launch_igemm_inst(const CUtensorMap& map_a, const CUtensorMap& map_b, void* out, const TcConvParams& p,
-                             int64_t mtiles, int ntiles, size_t smem, cudaStream_t st) {
-  auto kern = qconv_igemm_kernel<T, MIX, CG, KSTEPS>;
-  static thread_local bool attr_set = false;
-  if (!attr_set) {
+template <typename T, bool MIX, int CG, int KSTEPS, int NQ>
+static int launch_igemm_inst(const CUtensorMap& map_a, const CUtensorMap& map_b, void* out, const TcConvParams& p, size_t smem,
+                             cudaStream_t st) {
+  auto kern = qconv_igemm_kernel<T, MIX, CG, KSTEPS, NQ>;
+  // persistent grid: one CTA (pair) per SM, as many as can be co-resident (queried once per instantiation)
+  static thread_local int max_groups = 0;
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(IG_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (max_groups == 0) {
     QUAN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
+    int n = 0;
+    if (CG == 2) {
+      cfg.gridDim = dim3(QUAN_NUM_SMS);
+      QUAN_CUDA(cudaOccupancyMaxActiveClusters(&n, kern, &cfg));
+    } else {
+      int dev = 0, sms = 0;
+      QUAN_CUDA(cudaGetDevice(&dev));
+      QUAN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+      n = sms;
+    }
+    QUAN_REQUIRE(n > 0, QUAN_E_DRIVER, "tcgen05 conv: no co-resident CTA %s fits on this device", CG == 2 ? "pair" : "");
+    max_groups = n;
   }
-  if (CG == 2) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)((mtiles + 1) / 2 * 2), (unsigned)ntiles);   // whole pairs; the spare tile is masked
-    cfg.blockDim = dim3(TC_THREADS);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    QUAN_CUDA(cudaLaunchKernelEx(&cfg, kern, map_a, map_b, reinterpret_cast<T*>(out), p));
-  } else {
-    kern<<<dim3((unsigned)mtiles, (unsigned)ntiles), TC_THREADS, smem, st>>>(map_a, map_b, reinterpret_cast<T*>(out), p);
-  }
+  const int groups = p.units < max_groups ? p.units : max_groups;
+  cfg.gridDim = dim3((unsigned)(groups * CG));
+  QUAN_CUDA(cudaLaunchKernelEx(&cfg, kern, map_a, map_b, reinterpret_cast<T*>(out), p));
   QUAN_CHECK_LAUNCH("qconv_igemm_kernel");
   return QUAN_OK;
 }
 
-template <typename T, bool MIX>
+template <typename T, bool MIX, int NQ>
 static int launch_igemm(const void* in, const void* wpacked, const float* bias, void* out, const IgemmShape& s, int dtype,
                         const Mix16& mix, cudaStream_t st) {
   const int esz = sizeof(T);
   const int row_bytes = pick_row_bytes(s.K, esz);
   TilePlan t;
-  QUAN_REQUIRE(row_bytes != 0 && plan_tiles(s.B, s.Ho, s.Wo, s.sH, s.sW, t), QUAN_E_UNSUPPORTED,
+  QUAN_REQUIRE(row_bytes != 0 && s.nq == NQ && plan_tiles(s.B, s.Ho, s.Wo, s.sH, s.sW, t), QUAN_E_UNSUPPORTED,
                "tcgen05 conv: shape does not qualify");
   TcConvParams p = {};
   p.B = s.B; p.Ho = s.Ho; p.Wo = s.Wo; p.Cout = s.N;
@@ -600,19 +697,21 @@ static int launch_igemm(const void* in, const void* wpacked, const float* bias, 
   p.bk_elems = row_bytes / esz;
   p.kblocks = s.K / p.bk_elems;
   const int ksteps = row_bytes / 32;
-  p.BN = pick_bn(s.N);
+  p.BN = pick_bn(s.N, bn_cap(NQ));
   const int64_t mtiles = (int64_t)t.tiles_w * t.tiles_h * t.tiles_b;
   // CTA pairs (cta_group::2) when the weight tile splits into two halves that are themselves legal UMMA-N slices.
-  // Measured equal to single CTAs while the kernel is issue-bound; opt-in until the loop overhead is gone.
-  // Measured on B200 (C=256 3x3): 283 us with pairs vs 312 us without, once the issue loop was tight.
+  // Measured on B200 (C=256 3x3, non-persistent kernel): 283 us with pairs vs 312 us without.
   int cg = (p.BN % 32 == 0 && mtiles >= 2) ? 2 : 1;
   if (const char* e = getenv("QUAN_TC_CG")) { if (atoi(e) == 1) cg = 1; }
+  p.ntiles_n = s.N / p.BN;
+  p.units = (int)((mtiles + cg - 1) / cg) * p.ntiles_n;   // whole pairs; a spare tile is masked (TMA zero fill + row mask)
   p.a_sub_bytes = 128u * row_bytes;
   p.b_sub_bytes = (uint32_t)(p.BN / cg) * row_bytes;
   p.sbo_bytes = 8u * row_bytes;
   p.layout_type = row_bytes == 128 ? 2u : row_bytes == 64 ? 4u : 6u;
   p.idesc = ptx::make_idesc(sizeof(T) == 2 ? 1u : 2u, 0u, 0u, 128u * cg, (uint32_t)p.BN);
-  p.tmem_cols = (uint32_t)pow2_ceil(4 * p.BN < 32 ? 32 : 4 * p.BN);
+  const int acc_cols = (NQ == 4 ? 4 : 2) * p.BN;
+  p.tmem_cols = (uint32_t)pow2_ceil(acc_cols < 32 ? 32 : acc_cols);
   p.bias = bias;
   p.mix = mix;
   const int iters_per_q = s.kH * s.kW * p.kblocks;
@@ -625,31 +724,30 @@ static int launch_igemm(const void* in, const void* wpacked, const float* bias, 
   if (const char* e = getenv("QUAN_TC_STAGES")) { int v = atoi(e); if (v >= 1 && v < stages) stages = v; }
   QUAN_REQUIRE(stages >= 2, QUAN_E_UNSUPPORTED, "tcgen05 conv: stage too large");
   p.stages = stages;
-  const size_t smem = 1024 + stages * stage_bytes + (2 * stages + 1) * sizeof(uint64_t) + 16;
+  const size_t smem = 1024 + stages * stage_bytes + (2 * stages + 6) * sizeof(uint64_t) + 16;
 
-  // A: input activations [B][Hi][Wi][4][K] -> 5-D map {K, 4, Wi, Hi, B}
+  // A: input activations [B][Hi][Wi][nq][K] -> 5-D map {K, nq, Wi, Hi, B}
   CUtensorMap map_a, map_b;
   {
-    const uint64_t dims[5] = {(uint64_t)s.K, 4, (uint64_t)s.Wi, (uint64_t)s.Hi, (uint64_t)s.B};
-    const uint64_t str[4] = {(uint64_t)s.K * esz, (uint64_t)4 * s.K * esz, (uint64_t)s.Wi * 4 * s.K * esz,
-                             (uint64_t)s.Hi * s.Wi * 4 * s.K * esz};
+    const uint64_t dims[5] = {(uint64_t)s.K, (uint64_t)NQ, (uint64_t)s.Wi, (uint64_t)s.Hi, (uint64_t)s.B};
+    const uint64_t str[4] = {(uint64_t)s.K * esz, (uint64_t)NQ * s.K * esz, (uint64_t)s.Wi * NQ * s.K * esz,
+                             (uint64_t)s.Hi * s.Wi * NQ * s.K * esz};
     const uint32_t box[5] = {(uint32_t)p.bk_elems, 1, (uint32_t)(t.Wt * s.sW), (uint32_t)(t.Ht * s.sH), (uint32_t)t.Bt};
     const uint32_t est[5] = {1, 1, (uint32_t)s.sW, (uint32_t)s.sH, 1};
     int rc = encode_map(&map_a, dtype, 5, in, dims, str, box, est, row_bytes);
     if (rc) return rc;
   }
-  // B: packed weights [4][taps][N][K] -> 4-D map {K, N, taps, 4}
+  // B: packed weights [nq][taps][N][K] -> 4-D map {K, N, taps, nq}
   {
     const int taps = s.kH * s.kW;
-    const uint64_t dims[4] = {(uint64_t)s.K, (uint64_t)s.N, (uint64_t)taps, 4};
+    const uint64_t dims[4] = {(uint64_t)s.K, (uint64_t)s.N, (uint64_t)taps, (uint64_t)NQ};
     const uint64_t str[3] = {(uint64_t)s.K * esz, (uint64_t)s.N * s.K * esz, (uint64_t)taps * s.N * s.K * esz};
     const uint32_t box[4] = {(uint32_t)p.bk_elems, (uint32_t)(p.BN / cg), 1, 1};
     const uint32_t est[4] = {1, 1, 1, 1};
     int rc = encode_map(&map_b, dtype, 4, wpacked, dims, str, box, est, row_bytes);
     if (rc) return rc;
   }
-  const int ntiles = s.N / p.BN;
-#define QUAN_IGEMM_CASE(CGV, KS) return launch_igemm_inst<T, MIX, CGV, KS>(map_a, map_b, out, p, mtiles, ntiles, smem, st)
+#define QUAN_IGEMM_CASE(CGV, KS) return launch_igemm_inst<T, MIX, CGV, KS, NQ>(map_a, map_b, out, p, smem, st)
   if (cg == 2) {
     if (ksteps == 4) { QUAN_IGEMM_CASE(2, 4); }
     if (ksteps == 2) { QUAN_IGEMM_CASE(2, 2); }
@@ -677,6 +775,7 @@ static IgemmShape fwd_shape(const quan_conv_dims& d) {
   s.Ho = conv_out(d.H, d.kH, d.sH, d.pH, d.dH);
   s.Wo = conv_out(d.W, d.kW, d.sW, d.pW, d.dW);
   s.kH = d.kH; s.kW = d.kW; s.sH = d.sH; s.sW = d.sW; s.pH = d.pH; s.pW = d.pW; s.dH = d.dH; s.dW = d.dW;
+  s.nq = 4;
   return s;
 }
 // stride-1 dgrad as a forward conv of G (Co channels, Ho x Wo) with flipped kernels and padding d*(k-1)-p
@@ -689,6 +788,7 @@ static IgemmShape dgrad_shape(const quan_conv_dims& d) {
   s.kH = d.kH; s.kW = d.kW; s.sH = 1; s.sW = 1;
   s.pH = d.dH * (d.kH - 1) - d.pH; s.pW = d.dW * (d.kW - 1) - d.pW;
   s.dH = d.dH; s.dW = d.dW;
+  s.nq = 4;
   return s;
 }
 
@@ -858,11 +958,11 @@ int qconv_tc_fwd(const void* x, const float* const w[4], const float* bias_r, vo
   if (dtype == QUAN_BF16) {
     rc = pack_weights<__nv_bfloat16, false>(w, ws, d, st);
     if (rc) return rc;
-    return launch_igemm<__nv_bfloat16, true>(x, ws, bias_r, y, s, dtype, M, st);
+    return launch_igemm<__nv_bfloat16, true, 4>(x, ws, bias_r, y, s, dtype, M, st);
   }
   rc = pack_weights<float, false>(w, ws, d, st);
   if (rc) return rc;
-  return launch_igemm<float, true>(x, ws, bias_r, y, s, dtype, M, st);
+  return launch_igemm<float, true, 4>(x, ws, bias_r, y, s, dtype, M, st);
 }
 
 int qconv_tc_dgrad(const void* gq, const float* const w[4], void* dx, const quan_conv_dims& d, int dtype, void* ws,
@@ -874,11 +974,11 @@ int qconv_tc_dgrad(const void* gq, const float* const w[4], void* dx, const quan
   if (dtype == QUAN_BF16) {
     rc = pack_weights<__nv_bfloat16, true>(w, ws, d, st);
     if (rc) return rc;
-    return launch_igemm<__nv_bfloat16, false>(gq, ws, nullptr, dx, s, dtype, ident, st);
+    return launch_igemm<__nv_bfloat16, false, 4>(gq, ws, nullptr, dx, s, dtype, ident, st);
   }
   rc = pack_weights<float, true>(w, ws, d, st);
   if (rc) return rc;
-  return launch_igemm<float, false>(gq, ws, nullptr, dx, s, dtype, ident, st);
+  return launch_igemm<float, false, 4>(gq, ws, nullptr, dx, s, dtype, ident, st);
 }
 
 int qconv_tc_wgrad(const void* gq, const void* x, float* const dw[4], const quan_conv_dims& d, int dtype, void* ws,

@@ -28,6 +28,11 @@ CASES = [
     ("tf32_c128_s2", "f32", 2, 128, 128, 32, 32, 3, 2, 1, 1, True, "A"),
     ("bf16_k7s2", "bf16", 2, 16, 32, 32, 32, 7, 2, 3, 1, False, "A"),
     ("bf16_c96_64", "bf16", 2, 96, 64, 20, 12, 1, 1, 0, 1, False, "A"),
+    # more work units than SMs: every CTA (pair) of the persistent kernel loops over several units (barrier phases,
+    # accumulator hand-back, odd tile count -> masked spare tile of the last pair)
+    ("bf16_c64_persist", "bf16", 75, 64, 64, 32, 32, 3, 1, 1, 1, True, "B"),
+    ("tf32_c32_persist", "f32", 40, 32, 64, 40, 24, 3, 1, 1, 1, False, "A"),
+    ("bf16_c128_k1_persist", "bf16", 33, 128, 256, 32, 32, 1, 1, 0, 1, False, "A"),
 ]
 
 
