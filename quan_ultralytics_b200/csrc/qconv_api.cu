@@ -52,7 +52,7 @@ size_t quan_qconv2d_workspace_bytes(const quan_conv_dims* d, int dtype, int layo
   if (algo != QUAN_ALGO_DIRECT && layout == QUAN_LAYOUT_BHWQC) {
     for (int pass = 0; pass < 3; ++pass)
       if (qconv_tc_supported(*d, dtype, layout, pass)) {
-        size_t b = qconv_tc_workspace_bytes(*d, dtype, pass);
+        size_t b = qconv_tc_workspace_bytes(*d, dtype, layout, pass);
         if (b > tc) tc = b;
       }
   }
@@ -70,10 +70,10 @@ int quan_qconv2d_fwd(const void* x, const float* const w[4], const float* bias_r
   const int a = resolve_algo(*d, dtype, layout, PASS_FWD, algo);
   QUAN_REQUIRE(a > 0, QUAN_E_UNSUPPORTED, "qconv2d_fwd: tcgen05 engine requested but shape/layout does not qualify");
   if (a == QUAN_ALGO_TCGEN05) {
-    const size_t need = qconv_tc_workspace_bytes(*d, dtype, PASS_FWD);
+    const size_t need = qconv_tc_workspace_bytes(*d, dtype, layout, PASS_FWD);
     QUAN_REQUIRE(workspace != nullptr && ws_bytes >= need, QUAN_E_WORKSPACE,
                  "qconv2d_fwd: tcgen05 engine needs %zu workspace bytes, got %zu", need, ws_bytes);
-    return qconv_tc_fwd(x, w, bias_r, y, *d, dtype, mix, workspace, ws_bytes, st);
+    return qconv_tc_fwd(x, w, bias_r, y, *d, dtype, qconv_tc_mode(*d, dtype, layout, PASS_FWD), mix, workspace, ws_bytes, st);
   }
   return qconv_fwd_direct_launch(x, w, bias_r, y, *d, dtype, layout, mix, st);
 }
@@ -94,33 +94,44 @@ int quan_qconv2d_bwd(const void* dy, const void* x, const float* const w[4], voi
   void* tc_ws = (char*)workspace + gb;
   const size_t tc_ws_bytes = ws_bytes - gb;
 
-  // G = M^T dY, once, shared by dgrad / wgrad / bias grad
-  float mix_t[16];
-  for (int p = 0; p < 4; ++p)
-    for (int q = 0; q < 4; ++q) mix_t[q * 4 + p] = mix[p * 4 + q];
-  const int Ho = conv_out(d->H, d->kH, d->sH, d->pH, d->dH), Wo = conv_out(d->W, d->kW, d->sW, d->pW, d->dW);
-  rc = quan_mix(dy, gq, d->B, d->Co, Ho, Wo, dtype, layout, mix_t, stream);
-  if (rc) return rc;
+  // engine per pass; the dense tensor-core form consumes dY directly (M is folded into its weights / reduce step)
+  int a_dx = 0, a_dw = 0, m_dx = TC_NONE, m_dw = TC_NONE;
+  if (dx != nullptr) {
+    a_dx = resolve_algo(*d, dtype, layout, PASS_DGRAD, algo);
+    QUAN_REQUIRE(a_dx > 0, QUAN_E_UNSUPPORTED, "qconv2d_bwd: tcgen05 dgrad requested but shape/layout does not qualify");
+    if (a_dx == QUAN_ALGO_TCGEN05) m_dx = qconv_tc_mode(*d, dtype, layout, PASS_DGRAD);
+  }
+  if (dw != nullptr) {
+    a_dw = resolve_algo(*d, dtype, layout, PASS_WGRAD, algo);
+    QUAN_REQUIRE(a_dw > 0, QUAN_E_UNSUPPORTED, "qconv2d_bwd: tcgen05 wgrad requested but shape/layout does not qualify");
+    if (a_dw == QUAN_ALGO_TCGEN05) m_dw = qconv_tc_mode(*d, dtype, layout, PASS_WGRAD);
+  }
+  // G = M^T dY, once, shared by every consumer that needs it (separable dgrad / wgrad, direct engine, bias grad)
+  const bool need_g = (dx != nullptr && m_dx != TC_DENSE) || (dw != nullptr && m_dw != TC_DENSE) || dbias_r != nullptr;
+  if (need_g) {
+    float mix_t[16];
+    for (int p = 0; p < 4; ++p)
+      for (int q = 0; q < 4; ++q) mix_t[q * 4 + p] = mix[p * 4 + q];
+    const int Ho = conv_out(d->H, d->kH, d->sH, d->pH, d->dH), Wo = conv_out(d->W, d->kW, d->sW, d->pW, d->dW);
+    rc = quan_mix(dy, gq, d->B, d->Co, Ho, Wo, dtype, layout, mix_t, stream);
+    if (rc) return rc;
+  }
 
   if (dx != nullptr) {
-    const int a = resolve_algo(*d, dtype, layout, PASS_DGRAD, algo);
-    QUAN_REQUIRE(a > 0, QUAN_E_UNSUPPORTED, "qconv2d_bwd: tcgen05 dgrad requested but shape/layout does not qualify");
-    if (a == QUAN_ALGO_TCGEN05) {
-      const size_t need = qconv_tc_workspace_bytes(*d, dtype, PASS_DGRAD);
+    if (a_dx == QUAN_ALGO_TCGEN05) {
+      const size_t need = qconv_tc_workspace_bytes(*d, dtype, layout, PASS_DGRAD);
       QUAN_REQUIRE(tc_ws_bytes >= need, QUAN_E_WORKSPACE, "qconv2d_bwd: dgrad needs %zu more workspace bytes", need);
-      rc = qconv_tc_dgrad(gq, w, dx, *d, dtype, tc_ws, tc_ws_bytes, st);
+      rc = qconv_tc_dgrad(m_dx == TC_DENSE ? dy : gq, w, dx, *d, dtype, m_dx, mix, tc_ws, tc_ws_bytes, st);
     } else {
       rc = qconv_dgrad_direct_launch(gq, w, dx, *d, dtype, layout, st);
     }
     if (rc) return rc;
   }
   if (dw != nullptr) {
-    const int a = resolve_algo(*d, dtype, layout, PASS_WGRAD, algo);
-    QUAN_REQUIRE(a > 0, QUAN_E_UNSUPPORTED, "qconv2d_bwd: tcgen05 wgrad requested but shape/layout does not qualify");
-    if (a == QUAN_ALGO_TCGEN05) {
-      const size_t need = qconv_tc_workspace_bytes(*d, dtype, PASS_WGRAD);
+    if (a_dw == QUAN_ALGO_TCGEN05) {
+      const size_t need = qconv_tc_workspace_bytes(*d, dtype, layout, PASS_WGRAD);
       QUAN_REQUIRE(tc_ws_bytes >= need, QUAN_E_WORKSPACE, "qconv2d_bwd: wgrad needs %zu more workspace bytes", need);
-      rc = qconv_tc_wgrad(gq, x, dw, *d, dtype, tc_ws, tc_ws_bytes, st);
+      rc = qconv_tc_wgrad(m_dw == TC_DENSE ? dy : gq, x, dw, *d, dtype, m_dw, mix, tc_ws, tc_ws_bytes, st);
     } else {
       rc = qconv_wgrad_direct_launch(gq, x, dw, *d, dtype, layout, st);
     }

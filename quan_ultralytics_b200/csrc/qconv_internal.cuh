@@ -15,15 +15,20 @@ int qconv_bias_grad_launch(const void* gq, float* db, const quan_conv_dims& d, i
 
 // ---- tcgen05 (tensor-core) engine, qconv_tc.cu ----------------------------------------------------
 enum { PASS_FWD = 0, PASS_DGRAD = 1, PASS_WGRAD = 2 };
-// true when the implicit-GEMM kernels can serve this shape (layout BHWQC, channel multiples, ...)
+// how the implicit-GEMM kernels serve a shape: not at all, one GEMM per quaternion component (mix in the epilogue),
+// or the dense Hamilton form (one GEMM over all 4*C_q channels, mix folded into the weights) used for narrow layers
+enum { TC_NONE = 0, TC_SEPARABLE = 1, TC_DENSE = 2 };
+int qconv_tc_mode(const quan_conv_dims& d, int dtype, int layout, int pass);
 bool qconv_tc_supported(const quan_conv_dims& d, int dtype, int layout, int pass);
 // bytes of workspace the tc engine needs for a pass (packed weights, split-K partials)
-size_t qconv_tc_workspace_bytes(const quan_conv_dims& d, int dtype, int pass);
+size_t qconv_tc_workspace_bytes(const quan_conv_dims& d, int dtype, int layout, int pass);
+// `mode` is qconv_tc_mode()'s answer for the pass.  dgrad / wgrad take G = M^T dY in the separable form and dY itself
+// in the dense form (`mix` is always the forward mixing matrix).
 int qconv_tc_fwd(const void* x, const float* const w[4], const float* bias_r, void* y, const quan_conv_dims& d,
-                 int dtype, const float* mix, void* ws, size_t ws_bytes, cudaStream_t st);
-int qconv_tc_dgrad(const void* gq, const float* const w[4], void* dx, const quan_conv_dims& d, int dtype, void* ws,
-                   size_t ws_bytes, cudaStream_t st);
-int qconv_tc_wgrad(const void* gq, const void* x, float* const dw[4], const quan_conv_dims& d, int dtype, void* ws,
-                   size_t ws_bytes, cudaStream_t st);
+                 int dtype, int mode, const float* mix, void* ws, size_t ws_bytes, cudaStream_t st);
+int qconv_tc_dgrad(const void* g, const float* const w[4], void* dx, const quan_conv_dims& d, int dtype, int mode,
+                   const float* mix, void* ws, size_t ws_bytes, cudaStream_t st);
+int qconv_tc_wgrad(const void* g, const void* x, float* const dw[4], const quan_conv_dims& d, int dtype, int mode,
+                   const float* mix, void* ws, size_t ws_bytes, cudaStream_t st);
 
 }  // namespace quan

@@ -408,9 +408,10 @@ qconv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 struct TcWgradParams {
   int Wt, Ht, Bt, tiles_w, tiles_h, nchunks;   // 64-pixel chunk = Bt x Ht x Wt over the OUTPUT (G) grid
   int kH, kW, sH, sW, pH, pW, dH, dW;
-  int Co, Ci, taps;
+  int Co, Ci, taps;            // channel counts of the GEMM (dense form: 4*C_o, 4*C_i)
+  int nq;                      // 4: separable form (one GEMM per component); 1: dense Hamilton form
   int TG;                      // taps per CTA (= kW)
-  int NA;                      // channels per 128-byte atom
+  int NA;                      // channels per swizzle atom row (128 / 64 / 32 bytes)
   int NB;                      // ci atoms per CTA: N = NB * NA
   int MA;                      // co atoms per CTA (M = 128 -> 128*es/128)
   int co_blocks, ci_blocks, tap_groups;
@@ -421,7 +422,7 @@ struct TcWgradParams {
   uint32_t atom_bytes;         // 64 rows x 128 B
   uint32_t sbo_bytes, layout_type;   // bf16: 8-row groups, SWIZZLE_128B; tf32: 4-row groups, SWIZZLE_128B_BASE32B
   uint32_t a_stage_bytes, b_stage_bytes, idesc, tmem_cols;
-  float* partial;              // [splits][4][taps][Co][Ci]
+  float* partial;              // [splits][nq][taps][Co][Ci]
 };
 
 constexpr int WG_PIX = 64;     // pixels (K) per pipeline stage
@@ -473,7 +474,9 @@ qconv_wgrad_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_const
 
   if (warp == 0) {
     // ===== TMA producer: warp-uniform loop, one elected lane issues =====
-    const uint32_t tx = p.a_stage_bytes + p.b_stage_bytes;
+    // co atoms past C_o are not loaded (their accumulator rows are never stored)
+    const int ma_load = min(p.MA, (p.Co - co0 + p.NA - 1) / p.NA);
+    const uint32_t tx = (uint32_t)ma_load * p.atom_bytes + p.b_stage_bytes;
     // chunk -> (tb, th, tw) once, then incrementally (no div/mod on the producer's critical path)
     int tw = chunk0 % p.tiles_w;
     int th = (chunk0 / p.tiles_w) % p.tiles_h;
@@ -486,7 +489,7 @@ qconv_wgrad_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_const
         const int w0 = tw * p.Wt, h0 = th * p.Ht, b0 = tb * p.Bt;
         ptx::mbar_arrive_expect_tx(full_bar + s, tx);
         uint8_t* a_dst = smem_a + (size_t)s * p.a_stage_bytes;
-        for (int a = 0; a < p.MA; ++a)
+        for (int a = 0; a < ma_load; ++a)
           ptx::tma_load_5d(a_dst + (size_t)a * p.atom_bytes, &map_g, full_bar + s, co0 + a * p.NA, q, w0, h0, b0);
         uint8_t* b_dst = smem_b + (size_t)s * p.b_stage_bytes;
         const int wc = w0 * p.sW - p.pW, hc = h0 * p.sH - p.pH + kh * p.dH;
@@ -539,7 +542,7 @@ qconv_wgrad_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_const
     const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
     for (int t = 0; t < p.TG; ++t) {
       const int tap = kh * p.kW + t;
-      float* dst = p.partial + ((((int64_t)split * 4 + q) * p.taps + tap) * p.Co + co) * p.Ci + ci0;
+      float* dst = p.partial + ((((int64_t)split * p.nq + q) * p.taps + tap) * p.Co + co) * p.Ci + ci0;
       for (int c0 = 0; c0 < N; c0 += 16) {
         float acc[16];
         ptx::tmem_ld16(lane_base + (uint32_t)(t * N + c0), acc);
@@ -579,6 +582,66 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
     const int tap = (int)(r / Co);
     float* dw = q == 0 ? dw0 : q == 1 ? dw1 : q == 2 ? dw2 : dw3;
     dw[((int64_t)co * Ci + ci) * taps + tap] = s;
+  }
+}
+
+// dense form: partial[split][tap][p*Co + co][q*Ci + ci] holds sum_pix dY_p[co] x_q[ci]; the mixing matrix is applied here:
+// dW_q[co][ci][tap] = sum_p M[p][q] sum_split partial[...]      (G = M^T dY never materialises)
+__global__ void __launch_bounds__(256) wgrad_reduce_dense_kernel(const float* __restrict__ partial, float* __restrict__ dw0,
+                                                                 float* __restrict__ dw1, float* __restrict__ dw2,
+                                                                 float* __restrict__ dw3, int splits, int taps, int Co, int Ci,
+                                                                 const Mix16 mix) {
+  const int64_t per_q = (int64_t)taps * Co * Ci;
+  const int64_t total = 4 * per_q;
+  const int64_t split_stride = (int64_t)taps * 16 * Co * Ci;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int q = (int)(i / per_q);
+    int64_t r = i - q * per_q;
+    const int ci = (int)(r % Ci);
+    r /= Ci;
+    const int co = (int)(r % Co);
+    const int tap = (int)(r / Co);
+    float s = 0.f;
+#pragma unroll
+    for (int pc = 0; pc < 4; ++pc) {
+      const float* src = partial + (((int64_t)tap * 4 * Co + pc * Co + co) * 4 * Ci + q * Ci + ci);
+      float t = 0.f;
+      for (int sp = 0; sp < splits; ++sp) t += __ldg(src + sp * split_stride);
+      s += mix.m[pc * 4 + q] * t;
+    }
+    float* dw = q == 0 ? dw0 : q == 1 ? dw1 : q == 2 ? dw2 : dw3;
+    dw[((int64_t)co * Ci + ci) * taps + tap] = s;
+  }
+}
+
+// dense Hamilton weights for narrow layers: one real conv over all 4*C_q channels with the mixing matrix folded in,
+//   FWD  : Wp[tap][n = p*Co + co][k = q*Ci + ci] = M[p][q] W_q[co][ci][tap];  bias'[p*Co + co] = M[p][0] b_r[co]
+//   DGRAD: Wp[tap][n = q*Ci + ci][k = p*Co + co] = M[p][q] W_q[co][ci][taps-1-tap]      (input is dY itself)
+template <typename T, bool DGRAD>
+__global__ void __launch_bounds__(256) pack_weights_dense_kernel(const float* __restrict__ w0, const float* __restrict__ w1,
+                                                                 const float* __restrict__ w2, const float* __restrict__ w3,
+                                                                 const float* __restrict__ bias_r, T* __restrict__ out,
+                                                                 float* __restrict__ bias_out, int Co, int Ci, int taps,
+                                                                 const Mix16 mix) {
+  const int N = DGRAD ? 4 * Ci : 4 * Co, K = DGRAD ? 4 * Co : 4 * Ci;
+  const int64_t total = (int64_t)taps * N * K;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i % K);
+    int64_t r = i / K;
+    const int n = (int)(r % N);
+    const int t = (int)(r / N);
+    int pc, q, co, ci, tap;
+    if constexpr (DGRAD) { q = n / Ci; ci = n % Ci; pc = k / Co; co = k % Co; tap = taps - 1 - t; }
+    else { pc = n / Co; co = n % Co; q = k / Ci; ci = k % Ci; tap = t; }
+    const float* w = q == 0 ? w0 : q == 1 ? w1 : q == 2 ? w2 : w3;
+    float v = mix.m[pc * 4 + q] * __ldg(w + ((int64_t)co * Ci + ci) * taps + tap);
+    if constexpr (sizeof(T) == 4) {
+      uint32_t r32;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r32) : "f"(v));
+      v = __uint_as_float(r32);
+    }
+    out[i] = from_f32<T>(v);
+    if (!DGRAD && bias_out != nullptr && i < 4 * Co) bias_out[i] = bias_r ? mix.m[(i / Co) * 4] * __ldg(bias_r + i % Co) : 0.f;
   }
 }
 
@@ -639,9 +702,6 @@ static bool igemm_supported(const IgemmShape& s, int dtype) {
   return true;
 }
 
-static size_t packed_weight_bytes(const quan_conv_dims& d, int dtype) {
-  return ((size_t)4 * d.kH * d.kW * d.Co * d.Ci * (dtype == QUAN_BF16 ? 2 : 4) + 1023) / 1024 * 1024;
-}
 
 template <typename T, bool MIX, int CG, int KSTEPS, int NQ>
 static int launch_igemm_inst(const CUtensorMap& map_a, const CUtensorMap& map_b, void* out, const TcConvParams& p, size_t smem,
@@ -768,33 +828,55 @@ static int pack_weights(const float* const w[4], void* out, const quan_conv_dims
   QUAN_CHECK_LAUNCH("pack_weights_kernel");
   return QUAN_OK;
 }
+template <typename T, bool DGRAD>
+static int pack_weights_dense(const float* const w[4], const float* bias_r, void* out, float* bias_out, const quan_conv_dims& d,
+                              const Mix16& mix, cudaStream_t st) {
+  const int taps = d.kH * d.kW;
+  const int64_t total = (int64_t)16 * d.Co * d.Ci * taps;
+  int grid = grid_for(total, 256, 4);
+  pack_weights_dense_kernel<T, DGRAD><<<grid, 256, 0, st>>>(w[0], w[1], w[2], w[3], bias_r, reinterpret_cast<T*>(out), bias_out,
+                                                            d.Co, d.Ci, taps, mix);
+  QUAN_CHECK_LAUNCH("pack_weights_dense_kernel");
+  return QUAN_OK;
+}
 
-static IgemmShape fwd_shape(const quan_conv_dims& d) {
+// ---- shapes -------------------------------------------------------------------------------------------------------
+// dense = 1: the conv over all 4*C_q real channels (nq = 1); dense = 0: one conv per component (nq = 4)
+static IgemmShape fwd_shape(const quan_conv_dims& d, int dense) {
   IgemmShape s;
-  s.B = d.B; s.Hi = d.H; s.Wi = d.W; s.K = d.Ci; s.N = d.Co;
+  const int f = dense ? 4 : 1;
+  s.B = d.B; s.Hi = d.H; s.Wi = d.W; s.K = d.Ci * f; s.N = d.Co * f;
   s.Ho = conv_out(d.H, d.kH, d.sH, d.pH, d.dH);
   s.Wo = conv_out(d.W, d.kW, d.sW, d.pW, d.dW);
   s.kH = d.kH; s.kW = d.kW; s.sH = d.sH; s.sW = d.sW; s.pH = d.pH; s.pW = d.pW; s.dH = d.dH; s.dW = d.dW;
-  s.nq = 4;
+  s.nq = dense ? 1 : 4;
   return s;
 }
 // stride-1 dgrad as a forward conv of G (Co channels, Ho x Wo) with flipped kernels and padding d*(k-1)-p
-static IgemmShape dgrad_shape(const quan_conv_dims& d) {
+static IgemmShape dgrad_shape(const quan_conv_dims& d, int dense) {
   IgemmShape s;
-  s.B = d.B; s.K = d.Co; s.N = d.Ci;
+  const int f = dense ? 4 : 1;
+  s.B = d.B; s.K = d.Co * f; s.N = d.Ci * f;
   s.Hi = conv_out(d.H, d.kH, d.sH, d.pH, d.dH);
   s.Wi = conv_out(d.W, d.kW, d.sW, d.pW, d.dW);
   s.Ho = d.H; s.Wo = d.W;
   s.kH = d.kH; s.kW = d.kW; s.sH = 1; s.sW = 1;
   s.pH = d.dH * (d.kH - 1) - d.pH; s.pW = d.dW * (d.kW - 1) - d.pW;
   s.dH = d.dH; s.dW = d.dW;
-  s.nq = 4;
+  s.nq = dense ? 1 : 4;
   return s;
 }
 
+static size_t packed_weight_bytes(const quan_conv_dims& d, int dtype, int dense) {
+  const size_t w = ((size_t)(dense ? 16 : 4) * d.kH * d.kW * d.Co * d.Ci * (dtype == QUAN_BF16 ? 2 : 4) + 1023) / 1024 * 1024;
+  return w + (dense ? (size_t)4 * d.Co * sizeof(float) + 1024 : 0);   // dense: + the mixed bias vector
+}
 
+// ---- wgrad plan ----------------------------------------------------------------------------------------------------
 struct WgradPlan {
   TilePlan t;
+  int Co, Ci;                  // channel counts of the GEMM (dense: 4x the quaternion counts)
+  int row_bytes;               // swizzle atom row: 128 / 64 / 32 bytes of channels
   int nchunks, TG, NA, NB, MA, co_blocks, ci_blocks, tap_groups, splits, chunks_per_split, stages;
   size_t smem, partial_bytes;
 };
@@ -813,10 +895,18 @@ static bool plan_tiles_n(int B, int Ho, int Wo, int sH, int sW, int npix, TilePl
   return true;
 }
 
-static bool plan_wgrad(const quan_conv_dims& d, int dtype, WgradPlan& w) {
+static bool plan_wgrad(const quan_conv_dims& d, int dtype, int dense, WgradPlan& w) {
   const int esz = dtype == QUAN_BF16 ? 2 : 4;
-  w.NA = 128 / esz;                                  // one 128-byte atom of channels
-  if (d.Ci % w.NA != 0 || d.Co % w.NA != 0) return false;
+  const int nq = dense ? 1 : 4;
+  w.Co = d.Co * (dense ? 4 : 1);
+  w.Ci = d.Ci * (dense ? 4 : 1);
+  // MN-major operands: rows of `row_bytes` channel bytes per pixel.  tf32 only has the 128-byte form
+  // (SWIZZLE_128B_BASE32B); bf16 also takes 64- and 32-byte rows, which is what narrow layers need.
+  w.row_bytes = 0;
+  for (int rb = 128; rb >= (esz == 2 ? 32 : 128); rb >>= 1)
+    if ((w.Ci * esz) % rb == 0 && (w.Co * esz) % rb == 0) { w.row_bytes = rb; break; }
+  if (w.row_bytes == 0) return false;
+  w.NA = w.row_bytes / esz;
   if (d.sH > 8 || d.sW > 8) return false;
   const int Ho = conv_out(d.H, d.kH, d.sH, d.pH, d.dH), Wo = conv_out(d.W, d.kW, d.sW, d.pW, d.dW);
   if (!plan_tiles_n(d.B, Ho, Wo, d.sH, d.sW, WG_PIX, w.t)) return false;
@@ -824,72 +914,83 @@ static bool plan_wgrad(const quan_conv_dims& d, int dtype, WgradPlan& w) {
   if (nchunks > 0x3fffffff) return false;
   w.nchunks = (int)nchunks;
   w.TG = d.kW;
-  if (w.TG * w.NA > 512) return false;
+  if (w.TG * 16 > 512) return false;
   w.tap_groups = d.kH;
-  w.MA = 128 / w.NA;                                 // atoms that make M = 128
-  // N = NB atoms of ci per CTA: as wide as TMEM (TG accumulators of N columns), UMMA (N <= 256) and a >= 3-stage smem
-  // ring allow — wider N means fewer, longer MMAs per barrier round trip and fewer re-reads of the G tile
-  w.NB = 1;
-  for (int nb = 2; nb <= 4; nb *= 2) {
-    const size_t stage_nb = (size_t)(w.MA + w.TG * nb) * WG_PIX * 128;
-    if (d.Ci % (nb * w.NA) == 0 && w.TG * nb * w.NA <= 512 && nb * w.NA <= 256 && (200 * 1024) / stage_nb >= 3) w.NB = nb;
+  w.MA = 128 / w.NA;                                 // atom slots that make M = 128
+  // N = NB atoms of ci per CTA: as wide as TMEM (TG accumulators of N columns), UMMA (N <= 256, multiple of 16) and a
+  // >= 3-stage smem ring allow — wider N means fewer, longer MMAs per barrier round trip and fewer re-reads of the G tile
+  const size_t atom = (size_t)WG_PIX * w.row_bytes;
+  w.NB = 0;
+  for (int nb = 1; nb * w.NA <= 256; ++nb) {
+    const int n = nb * w.NA;
+    const size_t stage_nb = (size_t)(w.MA + w.TG * nb) * atom;
+    if (w.Ci % n != 0 || n % 16 != 0 || w.TG * n > 512) continue;
+    if (w.NB != 0 && (200 * 1024) / stage_nb < 3) continue;
+    w.NB = nb;
   }
-  if (const char* e = getenv("QUAN_TC_WG_NB")) { int v = atoi(e); if (v >= 1 && v <= w.NB) w.NB = v; }
-  w.co_blocks = (d.Co + 127) / 128;
-  w.ci_blocks = d.Ci / (w.NA * w.NB);
-  const int64_t combos = (int64_t)4 * w.tap_groups * w.co_blocks * w.ci_blocks;
+  if (w.NB == 0) return false;
+  if (const char* e = getenv("QUAN_TC_WG_NB")) { int v = atoi(e); if (v >= 1 && v <= w.NB && w.Ci % (v * w.NA) == 0 && (v * w.NA) % 16 == 0) w.NB = v; }
+  w.co_blocks = (w.Co + 127) / 128;
+  w.ci_blocks = w.Ci / (w.NA * w.NB);
+  const int64_t combos = (int64_t)nq * w.tap_groups * w.co_blocks * w.ci_blocks;
   if (combos > 65535) return false;
   // split-K factor: 1 CTA/SM is resident, so pick the split count whose grid fills whole waves of 148 best
   // (first ncu capture: 336 CTAs = 2.27 waves, i.e. a third wave at 27% occupancy)
   int64_t splits = 1;
   double best = 1e30;
-  const double flops = 8.0 * (double)d.B * Ho * Wo * d.Co * d.Ci * d.kH * d.kW;
-  const double part_bytes = 4.0 * d.kH * d.kW * (double)d.Co * d.Ci * 4.0;          // one split's fp32 partials
-  for (int64_t sp = 1; sp <= 24 && sp <= w.nchunks; ++sp) {
+  const int taps = d.kH * d.kW;
+  const double flops = 2.0 * nq * (double)d.B * Ho * Wo * (w.co_blocks * 128.0) * w.Ci * taps;   // what the tensor pipe executes
+  const double in_bytes = (double)d.B * Ho * Wo * 4.0 * (d.Co + d.Ci * d.sH * d.sW) * esz;       // one pass over dY and x
+  const double part_bytes = (double)nq * taps * w.Co * w.Ci * 4.0;                               // one split's fp32 partials
+  for (int64_t sp = 1; sp <= 64 && sp <= w.nchunks; ++sp) {
     const int64_t ctas = combos * sp;
     const int64_t waves = (ctas + QUAN_NUM_SMS - 1) / QUAN_NUM_SMS;
     const double eff = (double)ctas / (double)(waves * QUAN_NUM_SMS);
-    // modelled time: tensor work at ~1 PFLOP/s scaled by wave fill + partial write/read at ~4 TB/s + per-CTA prologue
-    const double t = flops / (1.0e15 * eff) + sp * part_bytes * 2.0 / 4.0e12 + waves * 4.0e-6;
+    // modelled time: tensor work at ~1 PFLOP/s or the operand stream at ~4 TB/s, scaled by wave fill, + partial
+    // write/read at ~4 TB/s + per-CTA prologue
+    const double work = flops / 1.0e15 > in_bytes / 4.0e12 ? flops / 1.0e15 : in_bytes / 4.0e12;
+    const double t = work / eff + sp * part_bytes * 2.0 / 4.0e12 + waves * 4.0e-6;
     if (t < best) { best = t; splits = sp; }
   }
   w.chunks_per_split = (int)((w.nchunks + splits - 1) / splits);
   w.splits = (w.nchunks + w.chunks_per_split - 1) / w.chunks_per_split;
-  const size_t atom = (size_t)WG_PIX * 128;
   const size_t stage = (size_t)(w.MA + w.TG * w.NB) * atom;
   int stages = (int)((200 * 1024) / stage);
   if (stages > 8) stages = 8;
   if (stages < 2) return false;
   w.stages = stages;
   w.smem = 1024 + stages * stage + (2 * stages + 1) * sizeof(uint64_t) + 16;
-  w.partial_bytes = (size_t)w.splits * 4 * d.kH * d.kW * d.Co * d.Ci * sizeof(float);
+  w.partial_bytes = (size_t)w.splits * nq * taps * w.Co * w.Ci * sizeof(float);
   return true;
 }
 
+// gq: G = M^T dY (separable form) or dY itself (dense form, the mix is applied by the reduce kernel)
 template <typename T>
-static int launch_wgrad(const void* gq, const void* x, float* const dw[4], const quan_conv_dims& d, int dtype, void* ws,
-                        size_t ws_bytes, cudaStream_t st) {
+static int launch_wgrad(const void* gq, const void* x, float* const dw[4], const quan_conv_dims& d, int dtype, int dense,
+                        const Mix16& mix, void* ws, size_t ws_bytes, cudaStream_t st) {
   WgradPlan w;
-  QUAN_REQUIRE(plan_wgrad(d, dtype, w), QUAN_E_UNSUPPORTED, "tcgen05 wgrad: shape does not qualify");
+  QUAN_REQUIRE(plan_wgrad(d, dtype, dense, w), QUAN_E_UNSUPPORTED, "tcgen05 wgrad: shape does not qualify");
   QUAN_REQUIRE(ws_bytes >= w.partial_bytes, QUAN_E_WORKSPACE, "tcgen05 wgrad: workspace needs %zu bytes, got %zu",
                w.partial_bytes, ws_bytes);
   const int esz = sizeof(T);
+  const int nq = dense ? 1 : 4;
   const int Ho = conv_out(d.H, d.kH, d.sH, d.pH, d.dH), Wo = conv_out(d.W, d.kW, d.sW, d.pW, d.dW);
   TcWgradParams p = {};
   p.Wt = w.t.Wt; p.Ht = w.t.Ht; p.Bt = w.t.Bt; p.tiles_w = w.t.tiles_w; p.tiles_h = w.t.tiles_h; p.nchunks = w.nchunks;
   p.kH = d.kH; p.kW = d.kW; p.sH = d.sH; p.sW = d.sW; p.pH = d.pH; p.pW = d.pW; p.dH = d.dH; p.dW = d.dW;
-  p.Co = d.Co; p.Ci = d.Ci; p.taps = d.kH * d.kW;
+  p.Co = w.Co; p.Ci = w.Ci; p.taps = d.kH * d.kW; p.nq = nq;
   p.TG = w.TG; p.NA = w.NA; p.NB = w.NB; p.MA = w.MA;
   p.co_blocks = w.co_blocks; p.ci_blocks = w.ci_blocks; p.tap_groups = w.tap_groups;
   p.chunks_per_split = w.chunks_per_split;
   const int umma_k = 32 / esz;                       // pixels per UMMA
   p.ksteps = WG_PIX / umma_k;
-  p.kadv = (uint32_t)(umma_k * 128) >> 4;            // umma_k rows of 128 B
+  p.kadv = (uint32_t)(umma_k * w.row_bytes) >> 4;    // umma_k pixel rows
   p.stages = w.stages;
-  p.atom_bytes = WG_PIX * 128;
-  p.sbo_bytes = sizeof(T) == 2 ? 1024u : 512u;
-  p.layout_type = sizeof(T) == 2 ? 2u : 1u;
-  const uint32_t swz = sizeof(T) == 2 ? 128u : SWZ_128B_ATOM32;
+  p.atom_bytes = (uint32_t)(WG_PIX * w.row_bytes);
+  // bf16: 8-row groups, SWIZZLE_128B / 64B / 32B; tf32: 4-row groups, SWIZZLE_128B_BASE32B
+  p.sbo_bytes = sizeof(T) == 2 ? 8u * w.row_bytes : 512u;
+  p.layout_type = sizeof(T) == 2 ? (w.row_bytes == 128 ? 2u : w.row_bytes == 64 ? 4u : 6u) : 1u;
+  const uint32_t swz = sizeof(T) == 2 ? (uint32_t)w.row_bytes : SWZ_128B_ATOM32;
   p.a_stage_bytes = (uint32_t)w.MA * p.atom_bytes;
   p.b_stage_bytes = (uint32_t)(w.TG * w.NB) * p.atom_bytes;
   p.idesc = ptx::make_idesc(sizeof(T) == 2 ? 1u : 2u, 1u, 1u, 128u, (uint32_t)(w.NA * w.NB));
@@ -898,18 +999,18 @@ static int launch_wgrad(const void* gq, const void* x, float* const dw[4], const
 
   CUtensorMap map_g, map_x;
   {
-    const uint64_t dims[5] = {(uint64_t)d.Co, 4, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)d.B};
-    const uint64_t str[4] = {(uint64_t)d.Co * esz, (uint64_t)4 * d.Co * esz, (uint64_t)Wo * 4 * d.Co * esz,
-                             (uint64_t)Ho * Wo * 4 * d.Co * esz};
+    const uint64_t dims[5] = {(uint64_t)w.Co, (uint64_t)nq, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)d.B};
+    const uint64_t str[4] = {(uint64_t)w.Co * esz, (uint64_t)nq * w.Co * esz, (uint64_t)Wo * nq * w.Co * esz,
+                             (uint64_t)Ho * Wo * nq * w.Co * esz};
     const uint32_t box[5] = {(uint32_t)w.NA, 1, (uint32_t)w.t.Wt, (uint32_t)w.t.Ht, (uint32_t)w.t.Bt};
     const uint32_t est[5] = {1, 1, 1, 1, 1};
     int rc = encode_map(&map_g, dtype, 5, gq, dims, str, box, est, swz);
     if (rc) return rc;
   }
   {
-    const uint64_t dims[5] = {(uint64_t)d.Ci, 4, (uint64_t)d.W, (uint64_t)d.H, (uint64_t)d.B};
-    const uint64_t str[4] = {(uint64_t)d.Ci * esz, (uint64_t)4 * d.Ci * esz, (uint64_t)d.W * 4 * d.Ci * esz,
-                             (uint64_t)d.H * d.W * 4 * d.Ci * esz};
+    const uint64_t dims[5] = {(uint64_t)w.Ci, (uint64_t)nq, (uint64_t)d.W, (uint64_t)d.H, (uint64_t)d.B};
+    const uint64_t str[4] = {(uint64_t)w.Ci * esz, (uint64_t)nq * w.Ci * esz, (uint64_t)d.W * nq * w.Ci * esz,
+                             (uint64_t)d.H * d.W * nq * w.Ci * esz};
     const uint32_t box[5] = {(uint32_t)w.NA, 1, (uint32_t)(w.t.Wt * d.sW), (uint32_t)(w.t.Ht * d.sH), (uint32_t)w.t.Bt};
     const uint32_t est[5] = {1, 1, (uint32_t)d.sW, (uint32_t)d.sH, 1};
     int rc = encode_map(&map_x, dtype, 5, x, dims, str, box, est, swz);
@@ -921,70 +1022,125 @@ static int launch_wgrad(const void* gq, const void* x, float* const dw[4], const
     QUAN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  dim3 grid((unsigned)w.splits, (unsigned)(4 * w.tap_groups * w.co_blocks * w.ci_blocks));
+  dim3 grid((unsigned)w.splits, (unsigned)(nq * w.tap_groups * w.co_blocks * w.ci_blocks));
   kern<<<grid, TC_THREADS, w.smem, st>>>(map_g, map_x, p);
   QUAN_CHECK_LAUNCH("qconv_wgrad_kernel");
   const int64_t total = (int64_t)4 * p.taps * d.Co * d.Ci;
-  wgrad_reduce_kernel<<<grid_for(total, 256, 4), 256, 0, st>>>(p.partial, dw[0], dw[1], dw[2], dw[3], w.splits, p.taps,
-                                                                d.Co, d.Ci);
-  QUAN_CHECK_LAUNCH("wgrad_reduce_kernel");
+  if (dense) {
+    wgrad_reduce_dense_kernel<<<grid_for(total, 256, 4), 256, 0, st>>>(p.partial, dw[0], dw[1], dw[2], dw[3], w.splits, p.taps,
+                                                                        d.Co, d.Ci, mix);
+    QUAN_CHECK_LAUNCH("wgrad_reduce_dense_kernel");
+  } else {
+    wgrad_reduce_kernel<<<grid_for(total, 256, 4), 256, 0, st>>>(p.partial, dw[0], dw[1], dw[2], dw[3], w.splits, p.taps,
+                                                                  d.Co, d.Ci);
+    QUAN_CHECK_LAUNCH("wgrad_reduce_kernel");
+  }
   return QUAN_OK;
 }
 
-bool qconv_tc_supported(const quan_conv_dims& d, int dtype, int layout, int pass) {
-  if (layout != QUAN_LAYOUT_BHWQC || d.groups != 1) return false;
-  if (get_encode_fn() == nullptr) return false;
-  if (pass == PASS_FWD) return igemm_supported(fwd_shape(d), dtype);
-  if (pass == PASS_DGRAD) {
-    if (d.sH != 1 || d.sW != 1) return false;
-    return igemm_supported(dgrad_shape(d), dtype);
-  }
-  WgradPlan w;
-  return plan_wgrad(d, dtype, w);
+// ---- form selection --------------------------------------------------------------------------------------------------
+// Narrow layers (QUAN-YOLO11n: 4..32 quaternion channels) are HBM-bound and their per-component GEMMs are too thin for
+// the tensor core (K rows of C_i*2 bytes < one swizzle row, N = C_o).  For them the Hamilton-structured weight is
+// treated as the dense contraction it is: one GEMM over all 4*C_q channels, M folded into the packed weights — 4x the
+// separable FLOPs on a pipe with far more than 4x headroom, no mix epilogue and no G = M^T dY pre-pass.
+static int env_dense() {   // QUAN_TC_DENSE = 0: never, 1: whenever the shape allows (tests), unset: by channel count
+  static int v = -2;
+  if (v == -2) { const char* e = getenv("QUAN_TC_DENSE"); v = e ? atoi(e) : -1; }
+  return v;
+}
+static bool prefer_dense(int k_channels, int dtype) {   // k_channels: per-component contraction width
+  return k_channels * (dtype == QUAN_BF16 ? 2 : 4) <= 64;
 }
 
-size_t qconv_tc_workspace_bytes(const quan_conv_dims& d, int dtype, int pass) {
-  if (pass == PASS_FWD || pass == PASS_DGRAD) return packed_weight_bytes(d, dtype);
+int qconv_tc_mode(const quan_conv_dims& d, int dtype, int layout, int pass) {
+  if (layout != QUAN_LAYOUT_BHWQC || d.groups != 1) return TC_NONE;
+  if (get_encode_fn() == nullptr) return TC_NONE;
+  const int e = env_dense();
+  bool sep = false, dense = false;
+  int kch = d.Ci;
+  if (pass == PASS_FWD) {
+    sep = igemm_supported(fwd_shape(d, 0), dtype);
+    dense = igemm_supported(fwd_shape(d, 1), dtype);
+  } else if (pass == PASS_DGRAD) {
+    if (d.sH != 1 || d.sW != 1) return TC_NONE;
+    sep = igemm_supported(dgrad_shape(d, 0), dtype);
+    dense = igemm_supported(dgrad_shape(d, 1), dtype);
+    kch = d.Co;
+  } else {
+    WgradPlan w;
+    sep = plan_wgrad(d, dtype, 0, w);
+    dense = plan_wgrad(d, dtype, 1, w);
+    kch = d.Ci < d.Co ? d.Ci : d.Co;
+  }
+  if (e == 0) dense = false;
+  if (dense && (e == 1 || !sep || prefer_dense(kch, dtype))) return TC_DENSE;
+  return sep ? TC_SEPARABLE : TC_NONE;
+}
+
+bool qconv_tc_supported(const quan_conv_dims& d, int dtype, int layout, int pass) {
+  return qconv_tc_mode(d, dtype, layout, pass) != TC_NONE;
+}
+
+size_t qconv_tc_workspace_bytes(const quan_conv_dims& d, int dtype, int layout, int pass) {
+  const int mode = qconv_tc_mode(d, dtype, layout, pass);
+  if (mode == TC_NONE) return 0;
+  if (pass == PASS_FWD || pass == PASS_DGRAD) return packed_weight_bytes(d, dtype, mode == TC_DENSE);
   WgradPlan w;
-  return plan_wgrad(d, dtype, w) ? w.partial_bytes : 0;
+  return plan_wgrad(d, dtype, mode == TC_DENSE, w) ? w.partial_bytes : 0;
+}
+
+template <typename T>
+static int tc_fwd_t(const void* x, const float* const w[4], const float* bias_r, void* y, const quan_conv_dims& d, int dtype,
+                    int dense, const Mix16& M, void* ws, cudaStream_t st) {
+  if (dense) {
+    float* bias_out = reinterpret_cast<float*>((char*)ws + packed_weight_bytes(d, dtype, 1) - (size_t)4 * d.Co * sizeof(float) - 1024);
+    int rc = pack_weights_dense<T, false>(w, bias_r, ws, bias_out, d, M, st);
+    if (rc) return rc;
+    return launch_igemm<T, false, 1>(x, ws, bias_r ? bias_out : nullptr, y, fwd_shape(d, 1), dtype, M, st);
+  }
+  int rc = pack_weights<T, false>(w, ws, d, st);
+  if (rc) return rc;
+  return launch_igemm<T, true, 4>(x, ws, bias_r, y, fwd_shape(d, 0), dtype, M, st);
 }
 
 int qconv_tc_fwd(const void* x, const float* const w[4], const float* bias_r, void* y, const quan_conv_dims& d, int dtype,
-                 const float* mix, void* ws, size_t ws_bytes, cudaStream_t st) {
-  QUAN_REQUIRE(ws_bytes >= packed_weight_bytes(d, dtype), QUAN_E_WORKSPACE, "tcgen05 fwd: workspace too small");
+                 int mode, const float* mix, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const int dense = mode == TC_DENSE;
+  QUAN_REQUIRE(ws_bytes >= packed_weight_bytes(d, dtype, dense), QUAN_E_WORKSPACE, "tcgen05 fwd: workspace too small");
   const Mix16 M = make_mix(mix);
-  const IgemmShape s = fwd_shape(d);
-  int rc;
-  if (dtype == QUAN_BF16) {
-    rc = pack_weights<__nv_bfloat16, false>(w, ws, d, st);
-    if (rc) return rc;
-    return launch_igemm<__nv_bfloat16, true, 4>(x, ws, bias_r, y, s, dtype, M, st);
-  }
-  rc = pack_weights<float, false>(w, ws, d, st);
-  if (rc) return rc;
-  return launch_igemm<float, true, 4>(x, ws, bias_r, y, s, dtype, M, st);
+  if (dtype == QUAN_BF16) return tc_fwd_t<__nv_bfloat16>(x, w, bias_r, y, d, dtype, dense, M, ws, st);
+  return tc_fwd_t<float>(x, w, bias_r, y, d, dtype, dense, M, ws, st);
 }
 
-int qconv_tc_dgrad(const void* gq, const float* const w[4], void* dx, const quan_conv_dims& d, int dtype, void* ws,
-                   size_t ws_bytes, cudaStream_t st) {
-  QUAN_REQUIRE(ws_bytes >= packed_weight_bytes(d, dtype), QUAN_E_WORKSPACE, "tcgen05 dgrad: workspace too small");
-  const IgemmShape s = dgrad_shape(d);
-  Mix16 ident = {};
-  int rc;
-  if (dtype == QUAN_BF16) {
-    rc = pack_weights<__nv_bfloat16, true>(w, ws, d, st);
+template <typename T>
+static int tc_dgrad_t(const void* g, const float* const w[4], void* dx, const quan_conv_dims& d, int dtype, int dense,
+                      const Mix16& M, void* ws, cudaStream_t st) {
+  if (dense) {
+    int rc = pack_weights_dense<T, true>(w, nullptr, ws, nullptr, d, M, st);
     if (rc) return rc;
-    return launch_igemm<__nv_bfloat16, false, 4>(gq, ws, nullptr, dx, s, dtype, ident, st);
+    return launch_igemm<T, false, 1>(g, ws, nullptr, dx, dgrad_shape(d, 1), dtype, M, st);
   }
-  rc = pack_weights<float, true>(w, ws, d, st);
+  int rc = pack_weights<T, true>(w, ws, d, st);
   if (rc) return rc;
-  return launch_igemm<float, false, 4>(gq, ws, nullptr, dx, s, dtype, ident, st);
+  return launch_igemm<T, false, 4>(g, ws, nullptr, dx, dgrad_shape(d, 0), dtype, M, st);
 }
 
-int qconv_tc_wgrad(const void* gq, const void* x, float* const dw[4], const quan_conv_dims& d, int dtype, void* ws,
-                   size_t ws_bytes, cudaStream_t st) {
-  if (dtype == QUAN_BF16) return launch_wgrad<__nv_bfloat16>(gq, x, dw, d, dtype, ws, ws_bytes, st);
-  return launch_wgrad<float>(gq, x, dw, d, dtype, ws, ws_bytes, st);
+// g: G = M^T dY for the separable form, dY itself for the dense form (mix: the forward mixing matrix)
+int qconv_tc_dgrad(const void* g, const float* const w[4], void* dx, const quan_conv_dims& d, int dtype, int mode,
+                   const float* mix, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const int dense = mode == TC_DENSE;
+  QUAN_REQUIRE(ws_bytes >= packed_weight_bytes(d, dtype, dense), QUAN_E_WORKSPACE, "tcgen05 dgrad: workspace too small");
+  const Mix16 M = make_mix(mix);
+  if (dtype == QUAN_BF16) return tc_dgrad_t<__nv_bfloat16>(g, w, dx, d, dtype, dense, M, ws, st);
+  return tc_dgrad_t<float>(g, w, dx, d, dtype, dense, M, ws, st);
+}
+
+int qconv_tc_wgrad(const void* g, const void* x, float* const dw[4], const quan_conv_dims& d, int dtype, int mode,
+                   const float* mix, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const int dense = mode == TC_DENSE;
+  const Mix16 M = make_mix(mix);
+  if (dtype == QUAN_BF16) return launch_wgrad<__nv_bfloat16>(g, x, dw, d, dtype, dense, M, ws, ws_bytes, st);
+  return launch_wgrad<float>(g, x, dw, d, dtype, dense, M, ws, ws_bytes, st);
 }
 
 }  // namespace quan

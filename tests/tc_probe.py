@@ -33,6 +33,15 @@ CASES = [
     ("bf16_c64_persist", "bf16", 75, 64, 64, 32, 32, 3, 1, 1, 1, True, "B"),
     ("tf32_c32_persist", "f32", 40, 32, 64, 40, 24, 3, 1, 1, 1, False, "A"),
     ("bf16_c128_k1_persist", "bf16", 33, 128, 256, 32, 32, 1, 1, 0, 1, False, "A"),
+    # narrow layers (QUAN-YOLO11n channel counts): dense Hamilton form, 128/64/32-byte swizzle rows, partial M tiles
+    ("bf16_c4_c8_dense", "bf16", 4, 4, 8, 32, 32, 3, 1, 1, 1, True, "A"),
+    ("bf16_c8_k1_dense", "bf16", 4, 8, 8, 32, 32, 1, 1, 0, 1, False, "B"),
+    ("bf16_c12_c16_k1_dense", "bf16", 4, 12, 16, 32, 32, 1, 1, 0, 1, False, "A"),
+    ("bf16_c24_c32_dense", "bf16", 4, 24, 32, 32, 32, 3, 1, 1, 1, False, "A"),
+    ("bf16_c32_s2_dense", "bf16", 4, 32, 32, 32, 32, 3, 2, 1, 1, False, "A"),
+    ("bf16_c16_c4_dense", "bf16", 4, 16, 4, 32, 32, 3, 1, 1, 1, True, "B"),
+    ("tf32_c8_dense", "f32", 4, 8, 8, 32, 32, 3, 1, 1, 1, True, "B"),
+    ("bf16_c16_persist_dense", "bf16", 40, 16, 16, 64, 64, 3, 1, 1, 1, False, "A"),
 ]
 
 

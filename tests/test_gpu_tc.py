@@ -78,12 +78,15 @@ def test_tc_is_what_auto_picks_for_the_sweep_shapes():
                          for ps in range(3)]
                 assert picks[0] == ops.ALGO_TCGEN05 and picks[2] == ops.ALGO_TCGEN05
                 assert picks[1] == (ops.ALGO_TCGEN05 if s == 1 else ops.ALGO_DIRECT)
-    # reference layout / grouped / tiny-channel convs stay on the direct engine
+    # narrow layers take the dense Hamilton form of the tensor-core engine
+    assert ops.qconv2d_pick_algo((16, 4, 32, 32, 4), (8, 4, 3, 3), (1, 1), (1, 1), (1, 1), 1, torch.bfloat16, L, 0) \
+        == ops.ALGO_TCGEN05
+    # reference layout / grouped / 1-2 channel convs stay on the direct engine
     assert ops.qconv2d_pick_algo((16, 64, 32, 32, 4), (64, 64, 3, 3), (1, 1), (1, 1), (1, 1), 1, torch.bfloat16,
                                  ops.LAYOUT_BCHWQ, 0) == ops.ALGO_DIRECT
     assert ops.qconv2d_pick_algo((16, 64, 32, 32, 4), (64, 1, 3, 3), (1, 1), (1, 1), (1, 1), 64, torch.bfloat16, L, 0) \
         == ops.ALGO_DIRECT
-    assert ops.qconv2d_pick_algo((16, 4, 32, 32, 4), (8, 4, 3, 3), (1, 1), (1, 1), (1, 1), 1, torch.bfloat16, L, 0) \
+    assert ops.qconv2d_pick_algo((16, 2, 32, 32, 4), (4, 2, 3, 3), (1, 1), (1, 1), (1, 1), 1, torch.bfloat16, L, 0) \
         == ops.ALGO_DIRECT
 
 

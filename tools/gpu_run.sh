@@ -1,3 +1,1 @@
-set -x
-for i in 0 7 14 15 16; do timeout 120 python tests/tc_probe.py $i 2>&1 | tail -5; done
-timeout 300 python tests/conv_probe.py | tail -1
+for i in 3 8 17 18 19 20 21 22 23 24; do timeout 120 python tests/tc_probe.py $i 2>&1 | grep -v "^\[.*pick_algo\|sample\|mismatches" | tail -5; done
