@@ -99,11 +99,27 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restri
 // ---------------------------------------------------------------------------------------------------------------
 // forward / dgrad implicit-GEMM kernel
 // ---------------------------------------------------------------------------------------------------------------
+// The filter as a table of (input offset, packed-weight index) entries, grouped in output "classes":
+//   forward / stride-1 dgrad: one class, entry (kh,kw) -> offset (kh*dH - pH, kw*dW - pW);
+//   stride-s dgrad: s*s classes, one per output parity (ph,pw) — dX[i*s+ph][j*s+pw] only receives the taps with
+//   (ph + pH - kh*dH) % s == 0, each a plain (stride-1) shifted read of G at offset (ph + pH - kh*dH)/s — so a strided
+//   dgrad is s*s small stride-1 implicit GEMMs whose tiles are scattered with stride s by the epilogue.
+constexpr int TC_MAX_TAPS = 64;
+struct TapTable {
+  int ncls;
+  int start[5];                        // entries of class c: [start[c], start[c+1])
+  int8_t dw[TC_MAX_TAPS], dh[TC_MAX_TAPS];
+  uint8_t tap[TC_MAX_TAPS];
+  int8_t ow[4], oh[4];                 // output offset of the class
+};
+
 struct TcConvParams {
   int B, Ho, Wo, Cout;                 // output tensor [B][Ho][Wo][NQ][Cout]
-  int Wt, Ht, Bt, tiles_w, tiles_h;    // 128-pixel tile = Bt x Ht x Wt (w fastest), tiles per image plane
-  int ntiles_n, units;                 // N tiles; work units = (pixel tile [pair], N tile), N fastest
-  int kH, kW, sH, sW, pH, pW, dH, dW;
+  int Wt, Ht, Bt, tiles_w, tiles_h;    // 128-pixel tile = Bt x Ht x Wt (w fastest) of the class grid, tiles per image plane
+  int ntiles_n, units, units_per_cls;  // N tiles; work units = (class, pixel tile [pair], N tile), N fastest
+  int in_sW, in_sH;                    // input coordinate of class-grid pixel (i,j) = (i*in_sH + dh, j*in_sW + dw)
+  int out_sW, out_sH;                  // output coordinate = (i*out_sH + oh, j*out_sW + ow)
+  TapTable tt;
   int kblocks, bk_elems;               // k-blocks per tap, elements per k-block row
   int sub;                             // (tap, k-block) sub-steps bundled into one pipeline stage (1 or 2)
   int BN, stages;
@@ -180,8 +196,6 @@ qconv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  const int taps = p.kH * p.kW;
-  const int iters_per_q = taps * p.kblocks;          // (tap, k-block) steps per component
   const int tiles_per_b = p.tiles_w * p.tiles_h;
 
   if (warp == 0) {
@@ -190,14 +204,17 @@ qconv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     int s = 0;
     uint32_t phase = 0;
     for (int unit = cluster; unit < p.units; unit += nclusters) {
-      const int nt = unit % p.ntiles_n, tile = (unit / p.ntiles_n) * CG + (int)cta_rank;
+      const int cls = unit / p.units_per_cls, ucls = unit - cls * p.units_per_cls;
+      const int nt = ucls % p.ntiles_n, tile = (ucls / p.ntiles_n) * CG + (int)cta_rank;
       const int tw = tile % p.tiles_w, th = (tile / p.tiles_w) % p.tiles_h, tb = tile / tiles_per_b;
       const int b0 = tb * p.Bt;
-      const int wbase = tw * p.Wt * p.sW - p.pW, hbase = th * p.Ht * p.sH - p.pH;
+      const int wbase = tw * p.Wt * p.in_sW, hbase = th * p.Ht * p.in_sH;
       const int n0 = nt * p.BN;
       const int nb0 = n0 + (int)cta_rank * (p.BN / CG);             // this CTA's slice of the weight tile
+      const int e0 = p.tt.start[cls];
+      const int iters_per_q = (p.tt.start[cls + 1] - e0) * p.kblocks;   // (tap, k-block) steps per component
       for (int q = 0; q < NQ; ++q) {
-        int tap = 0, kh = 0, kw = 0, kb = 0;
+        int e = e0, kb = 0;
         for (int i = 0; i < iters_per_q; i += p.sub) {
           const int nsub = min(p.sub, iters_per_q - i);
           ptx::mbar_wait(empty_bar + s, phase ^ 1);
@@ -207,7 +224,7 @@ qconv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             if (leader) {
               uint8_t* a_dst = smem_a + (size_t)s * a_stage_bytes + (size_t)u * p.a_sub_bytes;
               uint8_t* b_dst = smem_b + (size_t)s * b_stage_bytes + (size_t)u * p.b_sub_bytes;
-              const int wc = wbase + kw * p.dW, hc = hbase + kh * p.dH, kc = kb * p.bk_elems;
+              const int wc = wbase + p.tt.dw[e], hc = hbase + p.tt.dh[e], kc = kb * p.bk_elems, tap = p.tt.tap[e];
               if constexpr (CG == 2) {
                 ptx::tma_load_5d_2cta(a_dst, &map_a, full_bar + s, kc, q, wc, hc, b0);
                 ptx::tma_load_4d_2cta(b_dst, &map_b, full_bar + s, kc, nb0, tap, q);
@@ -216,7 +233,7 @@ qconv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                 ptx::tma_load_4d(b_dst, &map_b, full_bar + s, kc, n0, tap, q);
               }
             }
-            if (++kb == p.kblocks) { kb = 0; ++tap; if (++kw == p.kW) { kw = 0; ++kh; } }
+            if (++kb == p.kblocks) { kb = 0; ++e; }
           }
           __syncwarp();
           if (++s == p.stages) { s = 0; phase ^= 1; }
@@ -236,6 +253,8 @@ qconv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       uint64_t da = da0, db = db0;
       uint32_t t_local = 0;
       for (int unit = cluster; unit < p.units; unit += nclusters, ++t_local) {
+        const int cls = unit / p.units_per_cls;
+        const int iters_per_q = (p.tt.start[cls + 1] - p.tt.start[cls]) * p.kblocks;
         for (int q = 0; q < NQ; ++q) {
           // accumulator a is reused every NACC/NQ units: wait until the epilogue warps (of both CTAs) have read it out
           const uint32_t a = NQ == 4 ? (uint32_t)q : (t_local & 1u);
@@ -298,9 +317,11 @@ qconv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       __syncwarp();
     };
     for (int unit = cluster; unit < p.units; unit += nclusters, ++t_local) {
-      const int nt = unit % p.ntiles_n, tile = (unit / p.ntiles_n) * CG + (int)cta_rank;
+      const int cls = unit / p.units_per_cls, ucls = unit - cls * p.units_per_cls;
+      const int nt = ucls % p.ntiles_n, tile = (ucls / p.ntiles_n) * CG + (int)cta_rank;
       const int tw = tile % p.tiles_w, th = (tile / p.tiles_w) % p.tiles_h, tb = tile / tiles_per_b;
-      const int wo = tw * p.Wt + wt, ho = th * p.Ht + ht, b = tb * p.Bt + bt;
+      const int wo = (tw * p.Wt + wt) * p.out_sW + p.tt.ow[cls], ho = (th * p.Ht + ht) * p.out_sH + p.tt.oh[cls];
+      const int b = tb * p.Bt + bt;
       const int n0 = nt * p.BN;
       const bool valid = (wo < p.Wo) && (ho < p.Ho) && (b < p.B);
       T* yrow = y + ((((int64_t)b * p.Ho + ho) * p.Wo + wo) * NQ) * p.Cout + n0;
@@ -565,50 +586,61 @@ qconv_wgrad_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_const
   }
 }
 
-// dW_q[co][ci][tap] = sum_split partial[split][q][tap][co][ci]
+// Split-K fold.  Block = 32 consecutive outputs (ci fastest, so a warp reads 128 contiguous bytes of one split) x 8 split
+// lanes; each lane sums every 8th split, shared memory folds the 8 lanes in a fixed order (deterministic).
+//   separable: dW_q[co][ci][tap] = sum_split partial[split][q][tap][co][ci]
+//   dense    : partial[split][tap][p*Co + co][q*Ci + ci] holds sum_pix dY_p[co] x_q[ci]; the mixing matrix is applied
+//              here: dW_q[co][ci][tap] = sum_p M[p][q] sum_split partial[...]   (G = M^T dY never materialises)
+template <bool DENSE>
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw0,
                                                            float* __restrict__ dw1, float* __restrict__ dw2,
-                                                           float* __restrict__ dw3, int splits, int taps, int Co, int Ci) {
+                                                           float* __restrict__ dw3, int splits, int taps, int Co, int Ci,
+                                                           const Mix16 mix) {
+  __shared__ float red[8][33];
   const int64_t per_q = (int64_t)taps * Co * Ci;
   const int64_t total = 4 * per_q;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    float s = 0.f;
-    for (int sp = 0; sp < splits; ++sp) s += __ldg(partial + (int64_t)sp * total + i);
-    const int q = (int)(i / per_q);
+  const int64_t split_stride = DENSE ? 16 * per_q : total;
+  const int ol = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const int64_t i = (int64_t)blockIdx.x * 32 + ol;
+  float s = 0.f;
+  int q = 0, ci = 0, co = 0, tap = 0;
+  if (i < total) {
+    q = (int)(i / per_q);
     int64_t r = i - q * per_q;
-    const int ci = (int)(r % Ci);
+    ci = (int)(r % Ci);
     r /= Ci;
-    const int co = (int)(r % Co);
-    const int tap = (int)(r / Co);
-    float* dw = q == 0 ? dw0 : q == 1 ? dw1 : q == 2 ? dw2 : dw3;
-    dw[((int64_t)co * Ci + ci) * taps + tap] = s;
-  }
-}
-
-// dense form: partial[split][tap][p*Co + co][q*Ci + ci] holds sum_pix dY_p[co] x_q[ci]; the mixing matrix is applied here:
-// dW_q[co][ci][tap] = sum_p M[p][q] sum_split partial[...]      (G = M^T dY never materialises)
-__global__ void __launch_bounds__(256) wgrad_reduce_dense_kernel(const float* __restrict__ partial, float* __restrict__ dw0,
-                                                                 float* __restrict__ dw1, float* __restrict__ dw2,
-                                                                 float* __restrict__ dw3, int splits, int taps, int Co, int Ci,
-                                                                 const Mix16 mix) {
-  const int64_t per_q = (int64_t)taps * Co * Ci;
-  const int64_t total = 4 * per_q;
-  const int64_t split_stride = (int64_t)taps * 16 * Co * Ci;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int q = (int)(i / per_q);
-    int64_t r = i - q * per_q;
-    const int ci = (int)(r % Ci);
-    r /= Ci;
-    const int co = (int)(r % Co);
-    const int tap = (int)(r / Co);
-    float s = 0.f;
+    co = (int)(r % Co);
+    tap = (int)(r / Co);
+    if constexpr (DENSE) {
 #pragma unroll
-    for (int pc = 0; pc < 4; ++pc) {
-      const float* src = partial + (((int64_t)tap * 4 * Co + pc * Co + co) * 4 * Ci + q * Ci + ci);
-      float t = 0.f;
-      for (int sp = 0; sp < splits; ++sp) t += __ldg(src + sp * split_stride);
-      s += mix.m[pc * 4 + q] * t;
+      for (int pc = 0; pc < 4; ++pc) {
+        const float* src = partial + (((int64_t)tap * 4 * Co + pc * Co + co) * 4 * Ci + q * Ci + ci);
+        float t0 = 0.f, t1 = 0.f;
+        int sp = sl;
+        for (; sp + 8 < splits; sp += 16) {
+          t0 += __ldg(src + sp * split_stride);
+          t1 += __ldg(src + (sp + 8) * split_stride);
+        }
+        if (sp < splits) t0 += __ldg(src + sp * split_stride);
+        s += mix.m[pc * 4 + q] * (t0 + t1);
+      }
+    } else {
+      const float* src = partial + i;
+      float t0 = 0.f, t1 = 0.f;
+      int sp = sl;
+      for (; sp + 8 < splits; sp += 16) {
+        t0 += __ldg(src + sp * split_stride);
+        t1 += __ldg(src + (sp + 8) * split_stride);
+      }
+      if (sp < splits) t0 += __ldg(src + sp * split_stride);
+      s = t0 + t1;
     }
+  }
+  red[sl][ol] = s;
+  __syncthreads();
+  if (sl == 0 && i < total) {
+#pragma unroll
+    for (int g = 1; g < 8; ++g) s += red[g][ol];
     float* dw = q == 0 ? dw0 : q == 1 ? dw1 : q == 2 ? dw2 : dw3;
     dw[((int64_t)co * Ci + ci) * taps + tap] = s;
   }
@@ -685,9 +717,48 @@ static bool plan_tiles(int B, int Ho, int Wo, int sH, int sW, TilePlan& t) {
 
 // geometry of a conv expressed as "output [B,Ho,Wo,N] from input [B,Hi,Wi,K]" (dgrad swaps the roles)
 // nq = 4: separable form, tensors [B][H][W][4][K or N]; nq = 1: dense Hamilton form, K and N count all 4*C_q real channels
+// scat > 1: stride-`scat` dgrad — (sH,sW) are 1, the output grid is visited in scat*scat parity classes (TapTable)
 struct IgemmShape {
-  int B, Hi, Wi, K, Ho, Wo, N, kH, kW, sH, sW, pH, pW, dH, dW, nq;
+  int B, Hi, Wi, K, Ho, Wo, N, kH, kW, sH, sW, pH, pW, dH, dW, nq, scatH, scatW;
 };
+static bool build_taps(const IgemmShape& s, TapTable& t) {
+  if (s.kH * s.kW > TC_MAX_TAPS || s.scatH * s.scatW > 4) return false;
+  t = TapTable{};
+  int n = 0;
+  if (s.scatH == 1 && s.scatW == 1) {
+    t.ncls = 1;
+    for (int kh = 0; kh < s.kH; ++kh)
+      for (int kw = 0; kw < s.kW; ++kw) {
+        const int dh = kh * s.dH - s.pH, dw = kw * s.dW - s.pW;
+        if (dh < -128 || dh > 127 || dw < -128 || dw > 127) return false;
+        t.dh[n] = (int8_t)dh; t.dw[n] = (int8_t)dw; t.tap[n] = (uint8_t)(kh * s.kW + kw);
+        ++n;
+      }
+    t.start[1] = n;
+    return true;
+  }
+  // strided dgrad: s.pH/pW hold the conv's own padding, weights are packed tap-flipped (pack_weights*<DGRAD>)
+  t.ncls = s.scatH * s.scatW;
+  for (int ph = 0; ph < s.scatH; ++ph)
+    for (int pw = 0; pw < s.scatW; ++pw) {
+      const int c = ph * s.scatW + pw;
+      t.start[c] = n;
+      t.oh[c] = (int8_t)ph; t.ow[c] = (int8_t)pw;
+      for (int kh = 0; kh < s.kH; ++kh)
+        for (int kw = 0; kw < s.kW; ++kw) {
+          const int nh = ph + s.pH - kh * s.dH, nw = pw + s.pW - kw * s.dW;
+          if (((nh % s.scatH) + s.scatH) % s.scatH != 0 || ((nw % s.scatW) + s.scatW) % s.scatW != 0) continue;
+          const int dh = nh / s.scatH, dw = nw / s.scatW;   // exact
+          if (dh < -128 || dh > 127 || dw < -128 || dw > 127) return false;
+          t.dh[n] = (int8_t)dh; t.dw[n] = (int8_t)dw;
+          t.tap[n] = (uint8_t)((s.kH - 1 - kh) * s.kW + (s.kW - 1 - kw));
+          ++n;
+        }
+      if (n == t.start[c]) return false;   // a class without taps (e.g. 1x1 stride 2) would need a zero fill: direct engine
+    }
+  t.start[t.ncls] = n;
+  return true;
+}
 static int bn_cap(int nq) { return nq == 4 ? 128 : 256; }   // TMEM: 4 accumulators of BN, or 2 of BN
 
 static bool igemm_supported(const IgemmShape& s, int dtype) {
@@ -697,9 +768,10 @@ static bool igemm_supported(const IgemmShape& s, int dtype) {
   if ((s.N * esz) % 16 != 0 || (s.K * esz) % 16 != 0) return false;
   if (s.sH > 8 || s.sW > 8) return false;             // TMA element-stride limit
   TilePlan t;
-  if (!plan_tiles(s.B, s.Ho, s.Wo, s.sH, s.sW, t)) return false;
-  if ((int64_t)t.tiles_w * t.tiles_h * t.tiles_b > 0x7fffffff) return false;
-  return true;
+  if (!plan_tiles(s.B, (s.Ho + s.scatH - 1) / s.scatH, (s.Wo + s.scatW - 1) / s.scatW, s.sH, s.sW, t)) return false;
+  if ((int64_t)t.tiles_w * t.tiles_h * t.tiles_b * s.scatH * s.scatW > 0x3fffffff) return false;
+  TapTable tt;
+  return build_taps(s, tt);
 }
 
 
@@ -748,12 +820,13 @@ static int launch_igemm(const void* in, const void* wpacked, const float* bias, 
   const int esz = sizeof(T);
   const int row_bytes = pick_row_bytes(s.K, esz);
   TilePlan t;
-  QUAN_REQUIRE(row_bytes != 0 && s.nq == NQ && plan_tiles(s.B, s.Ho, s.Wo, s.sH, s.sW, t), QUAN_E_UNSUPPORTED,
-               "tcgen05 conv: shape does not qualify");
   TcConvParams p = {};
+  QUAN_REQUIRE(row_bytes != 0 && s.nq == NQ && build_taps(s, p.tt) &&
+                   plan_tiles(s.B, (s.Ho + s.scatH - 1) / s.scatH, (s.Wo + s.scatW - 1) / s.scatW, s.sH, s.sW, t),
+               QUAN_E_UNSUPPORTED, "tcgen05 conv: shape does not qualify");
   p.B = s.B; p.Ho = s.Ho; p.Wo = s.Wo; p.Cout = s.N;
   p.Wt = t.Wt; p.Ht = t.Ht; p.Bt = t.Bt; p.tiles_w = t.tiles_w; p.tiles_h = t.tiles_h;
-  p.kH = s.kH; p.kW = s.kW; p.sH = s.sH; p.sW = s.sW; p.pH = s.pH; p.pW = s.pW; p.dH = s.dH; p.dW = s.dW;
+  p.in_sW = s.sW; p.in_sH = s.sH; p.out_sW = s.scatW; p.out_sH = s.scatH;
   p.bk_elems = row_bytes / esz;
   p.kblocks = s.K / p.bk_elems;
   const int ksteps = row_bytes / 32;
@@ -764,7 +837,8 @@ static int launch_igemm(const void* in, const void* wpacked, const float* bias, 
   int cg = (p.BN % 32 == 0 && mtiles >= 2) ? 2 : 1;
   if (const char* e = getenv("QUAN_TC_CG")) { if (atoi(e) == 1) cg = 1; }
   p.ntiles_n = s.N / p.BN;
-  p.units = (int)((mtiles + cg - 1) / cg) * p.ntiles_n;   // whole pairs; a spare tile is masked (TMA zero fill + row mask)
+  p.units_per_cls = (int)((mtiles + cg - 1) / cg) * p.ntiles_n;   // whole pairs; a spare tile is masked (TMA zero fill + row mask)
+  p.units = p.units_per_cls * p.tt.ncls;
   p.a_sub_bytes = 128u * row_bytes;
   p.b_sub_bytes = (uint32_t)(p.BN / cg) * row_bytes;
   p.sbo_bytes = 8u * row_bytes;
@@ -774,7 +848,11 @@ static int launch_igemm(const void* in, const void* wpacked, const float* bias, 
   p.tmem_cols = (uint32_t)pow2_ceil(acc_cols < 32 ? 32 : acc_cols);
   p.bias = bias;
   p.mix = mix;
-  const int iters_per_q = s.kH * s.kW * p.kblocks;
+  int iters_per_q = 1 << 30;                         // of the smallest class
+  for (int c = 0; c < p.tt.ncls; ++c) {
+    const int it = (p.tt.start[c + 1] - p.tt.start[c]) * p.kblocks;
+    if (it < iters_per_q) iters_per_q = it;
+  }
   p.sub = iters_per_q >= 2 ? 2 : 1;                  // 8 MMAs per barrier round trip when there is enough K
   if (const char* e = getenv("QUAN_TC_SUB")) { int v = atoi(e); if (v >= 1 && v <= 4 && v <= iters_per_q) p.sub = v; }
   const size_t stage_bytes = (size_t)(p.a_sub_bytes + p.b_sub_bytes) * p.sub;
@@ -850,9 +928,11 @@ static IgemmShape fwd_shape(const quan_conv_dims& d, int dense) {
   s.Wo = conv_out(d.W, d.kW, d.sW, d.pW, d.dW);
   s.kH = d.kH; s.kW = d.kW; s.sH = d.sH; s.sW = d.sW; s.pH = d.pH; s.pW = d.pW; s.dH = d.dH; s.dW = d.dW;
   s.nq = dense ? 1 : 4;
+  s.scatH = s.scatW = 1;
   return s;
 }
-// stride-1 dgrad as a forward conv of G (Co channels, Ho x Wo) with flipped kernels and padding d*(k-1)-p
+// stride-1 dgrad as a forward conv of G (Co channels, Ho x Wo) with flipped kernels and padding d*(k-1)-p;
+// strided dgrad as stride*stride parity classes of stride-1 reads (build_taps)
 static IgemmShape dgrad_shape(const quan_conv_dims& d, int dense) {
   IgemmShape s;
   const int f = dense ? 4 : 1;
@@ -861,9 +941,11 @@ static IgemmShape dgrad_shape(const quan_conv_dims& d, int dense) {
   s.Wi = conv_out(d.W, d.kW, d.sW, d.pW, d.dW);
   s.Ho = d.H; s.Wo = d.W;
   s.kH = d.kH; s.kW = d.kW; s.sH = 1; s.sW = 1;
-  s.pH = d.dH * (d.kH - 1) - d.pH; s.pW = d.dW * (d.kW - 1) - d.pW;
   s.dH = d.dH; s.dW = d.dW;
   s.nq = dense ? 1 : 4;
+  s.scatH = d.sH; s.scatW = d.sW;
+  if (d.sH == 1 && d.sW == 1) { s.pH = d.dH * (d.kH - 1) - d.pH; s.pW = d.dW * (d.kW - 1) - d.pW; }
+  else { s.pH = d.pH; s.pW = d.pW; }
   return s;
 }
 
@@ -1026,15 +1108,12 @@ static int launch_wgrad(const void* gq, const void* x, float* const dw[4], const
   kern<<<grid, TC_THREADS, w.smem, st>>>(map_g, map_x, p);
   QUAN_CHECK_LAUNCH("qconv_wgrad_kernel");
   const int64_t total = (int64_t)4 * p.taps * d.Co * d.Ci;
-  if (dense) {
-    wgrad_reduce_dense_kernel<<<grid_for(total, 256, 4), 256, 0, st>>>(p.partial, dw[0], dw[1], dw[2], dw[3], w.splits, p.taps,
-                                                                        d.Co, d.Ci, mix);
-    QUAN_CHECK_LAUNCH("wgrad_reduce_dense_kernel");
-  } else {
-    wgrad_reduce_kernel<<<grid_for(total, 256, 4), 256, 0, st>>>(p.partial, dw[0], dw[1], dw[2], dw[3], w.splits, p.taps,
-                                                                  d.Co, d.Ci);
-    QUAN_CHECK_LAUNCH("wgrad_reduce_kernel");
-  }
+  const unsigned rgrid = (unsigned)((total + 31) / 32);
+  if (dense)
+    wgrad_reduce_kernel<true><<<rgrid, 256, 0, st>>>(p.partial, dw[0], dw[1], dw[2], dw[3], w.splits, p.taps, d.Co, d.Ci, mix);
+  else
+    wgrad_reduce_kernel<false><<<rgrid, 256, 0, st>>>(p.partial, dw[0], dw[1], dw[2], dw[3], w.splits, p.taps, d.Co, d.Ci, mix);
+  QUAN_CHECK_LAUNCH("wgrad_reduce_kernel");
   return QUAN_OK;
 }
 
@@ -1062,7 +1141,6 @@ int qconv_tc_mode(const quan_conv_dims& d, int dtype, int layout, int pass) {
     sep = igemm_supported(fwd_shape(d, 0), dtype);
     dense = igemm_supported(fwd_shape(d, 1), dtype);
   } else if (pass == PASS_DGRAD) {
-    if (d.sH != 1 || d.sW != 1) return TC_NONE;
     sep = igemm_supported(dgrad_shape(d, 0), dtype);
     dense = igemm_supported(dgrad_shape(d, 1), dtype);
     kch = d.Co;

@@ -42,6 +42,10 @@ CASES = [
     ("bf16_c16_c4_dense", "bf16", 4, 16, 4, 32, 32, 3, 1, 1, 1, True, "B"),
     ("tf32_c8_dense", "f32", 4, 8, 8, 32, 32, 3, 1, 1, 1, True, "B"),
     ("bf16_c16_persist_dense", "bf16", 40, 16, 16, 64, 64, 3, 1, 1, 1, False, "A"),
+    # strided dgrad as parity classes: odd image sizes (ragged class grids), dense and separable forms
+    ("bf16_s2_odd", "bf16", 3, 32, 64, 15, 13, 3, 2, 1, 1, False, "A"),
+    ("bf16_c64_s2_odd", "bf16", 5, 64, 128, 17, 19, 3, 2, 1, 1, True, "B"),
+    ("bf16_c16_s2_k5", "bf16", 6, 16, 16, 32, 32, 5, 2, 2, 1, False, "A"),
 ]
 
 

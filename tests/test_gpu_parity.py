@@ -183,12 +183,17 @@ def test_conv_block_golden(golden, layout):
         x = to_dev(g("x")).requires_grad_(True)
         y = blk(x)
         assert y.shape == (2, 8, 6, 6, 4)
-        assert rel_err(y, g("y")) <= 1e-4
+        # BCHWQ runs the true-fp32 direct engine; BHWQC the tf32 tensor-core engine (dense form at 4 -> 8 channels),
+        # whose budget is BASELINE.json's 1e-3 (2x on gradients, which chain two tf32 GEMMs and the IQBN backward)
+        tc = layout == ops.LAYOUT_BHWQC
+        assert rel_err(y, g("y")) <= (TOL_F32 if tc else 1e-4)
         y.backward(to_dev(g("dy")))
-        assert rel_err(x.grad, g("dx")) <= 1e-3
-        assert rel_err(blk.conv.weight_r.grad, g("dw_r")) <= 1e-3 and rel_err(blk.conv.weight_k.grad, g("dw_k")) <= 1e-3
-        assert rel_err(blk.bn.gamma.grad, g("dgamma")) <= 1e-3 and rel_err(blk.bn.beta.grad, g("dbeta")) <= 1e-3
-        assert rel_err(blk.bn.running_mean, g("rm1")) <= 1e-5 and rel_err(blk.bn.running_var, g("rv1")) <= 1e-5
+        tg = 2 * TOL_F32 if tc else 1e-3
+        assert rel_err(x.grad, g("dx")) <= tg
+        assert rel_err(blk.conv.weight_r.grad, g("dw_r")) <= tg and rel_err(blk.conv.weight_k.grad, g("dw_k")) <= tg
+        assert rel_err(blk.bn.gamma.grad, g("dgamma")) <= tg and rel_err(blk.bn.beta.grad, g("dbeta")) <= tg
+        assert rel_err(blk.bn.running_mean, g("rm1")) <= (TOL_F32 if tc else 1e-5)
+        assert rel_err(blk.bn.running_var, g("rv1")) <= (TOL_F32 if tc else 1e-5)
     finally:
         Q.set_internal_layout("bhwqc")
 

@@ -1,1 +1,4 @@
-for i in 3 8 17 18 19 20 21 22 23 24; do timeout 120 python tests/tc_probe.py $i 2>&1 | grep -v "^\[.*pick_algo\|sample\|mismatches" | tail -5; done
+for i in 5 11 12 21 25 26 27; do timeout 120 python tests/tc_probe.py $i 2>&1 | grep -v "sample\|mismatches" | tail -5; done
+python -m pytest tests -m gpu -q 2>&1 | tail -3
+python bench.py --workload yolo11n_trace --steps 5 --warmup 3 --graph 2>&1 | tail -1 | cut -c1-200
+python bench.py --workload yolo11n_trace --steps 5 --warmup 3 2>&1 | tail -1 | cut -c1-200

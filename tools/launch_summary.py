@@ -1,0 +1,22 @@
+"""Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list: time and launch count per kernel."""
+import collections
+import csv
+import re
+import sys
+
+rows = list(csv.reader(open(sys.argv[1])))
+hdr = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
+h = rows[hdr]
+ki, vi = h.index("Kernel Name"), h.index("Metric Value")
+agg = collections.defaultdict(lambda: [0, 0.0])
+for r in rows[hdr + 2:]:
+    if len(r) <= vi:
+        continue
+    name = re.sub(r"\(.*", "", r[ki])[:90]
+    agg[name][0] += 1
+    agg[name][1] += float(r[vi].replace(",", ""))
+tot = sum(v[1] for v in agg.values())
+n = int(sys.argv[2]) if len(sys.argv) > 2 else 30
+for k, v in sorted(agg.items(), key=lambda x: -x[1][1])[:n]:
+    print(f"{v[1] / 1e3:10.1f} us {v[0]:5d} {100 * v[1] / tot:5.1f}% {k}")
+print(f"{tot / 1e3:10.1f} us total, {sum(v[0] for v in agg.values())} launches")
