@@ -58,7 +58,7 @@ typedef struct quan_conv_dims {
 } quan_conv_dims;
 
 /* Which engine a conv call should use.  AUTO picks tcgen05 when the shape qualifies. */
-enum quan_conv_algo { QUAN_ALGO_AUTO = 0, QUAN_ALGO_DIRECT = 1, QUAN_ALGO_TCGEN05 = 2 };
+enum quan_conv_algo { QUAN_ALGO_AUTO = 0, QUAN_ALGO_DIRECT = 1, QUAN_ALGO_TCGEN05 = 2, QUAN_ALGO_DEPTHWISE = 3 };
 
 /* ---- library ------------------------------------------------------------------------------- */
 int         quan_version(void);                 /* QUAN_ABI_VERSION */
@@ -168,7 +168,7 @@ int quan_qconv2d_fwd(const void* x, const float* const w[4], const float* bias_r
 int quan_qconv2d_bwd(const void* dy, const void* x, const float* const w[4], void* dx, float* const dw[4],
                      float* dbias_r, const quan_conv_dims* d, int dtype, int layout, const float* mix,
                      int algo, void* workspace, size_t ws_bytes, void* stream);
-/* reports which engine AUTO would pick for this shape: QUAN_ALGO_DIRECT or QUAN_ALGO_TCGEN05 */
+/* reports which engine AUTO would pick for this shape: QUAN_ALGO_DIRECT, QUAN_ALGO_TCGEN05 or QUAN_ALGO_DEPTHWISE */
 int quan_qconv2d_pick_algo(const quan_conv_dims* d, int dtype, int layout, int pass /*0 fwd,1 dgrad,2 wgrad*/);
 
 #ifdef __cplusplus

@@ -13,6 +13,7 @@
 //
 // Two physical layouts (include/quan_sm100.h): BCHWQ (reference) and BHWQC (channels_last_3d, tensor-core path).
 #include "common.cuh"
+#include <cooperative_groups.h>
 #include <stdlib.h>
 
 namespace quan {
@@ -101,7 +102,18 @@ __device__ __forceinline__ void write_bwd_sums(const TailArgs& t, int i, double 
   }
 }
 
-// Second kernel of every reduction: fold the per-split partials of accumulator i = c*4+q and finish.
+__device__ __forceinline__ void finish_accumulator(const TailArgs& t, int i, double s0, double s1) {
+  if (t.mode == TAIL_RAW_SUMS) {
+    t.sums_out[i] = s0;
+    t.sums_out[4 * t.C + i] = s1;
+  } else if (t.mode == TAIL_FWD_STATS) {
+    write_fwd_stats(t, i, s0, s1);
+  } else {
+    write_bwd_sums(t, i, s0, s1);
+  }
+}
+
+// Second kernel of every reduction (when the reduction kernel could not be launched cooperatively): fold the per-split partials of accumulator i = c*4+q and finish.
 // block = 8 accumulators x 32 split-groups (4 independent loads in flight per thread); grid = ceil(4C / 8).
 __global__ void __launch_bounds__(256) iqbn_fold_kernel(const double* __restrict__ part, int nparts, TailArgs t) {
   __shared__ double red[2][32][9];
@@ -131,14 +143,7 @@ __global__ void __launch_bounds__(256) iqbn_fold_kernel(const double* __restrict
       s0 += red[0][g][il];
       s1 += red[1][g][il];
     }
-    if (t.mode == TAIL_RAW_SUMS) {
-      t.sums_out[i] = s0;
-      t.sums_out[n + i] = s1;
-    } else if (t.mode == TAIL_FWD_STATS) {
-      write_fwd_stats(t, i, s0, s1);
-    } else {
-      write_bwd_sums(t, i, s0, s1);
-    }
+    finish_accumulator(t, i, s0, s1);
   }
 }
 
@@ -184,16 +189,19 @@ __device__ __forceinline__ void colvec_param_index(int cv, int C, int (&idx)[V])
 }
 
 // MODE 0: sums of x and x^2.  MODE 1: sums of dz and dz*x (dz = dy*act'(x*scale+shift)).
-template <typename T, int V, int MODE, int ACT, int U>
-__global__ void __launch_bounds__(256) iqbn_reduce_b(const T* __restrict__ x, const T* __restrict__ dy, GeomB g,
-                                                     const float* __restrict__ gamma,
-                                                     const float* __restrict__ beta, IqbnWs ws, TailArgs tail) {
+// Memory-level parallelism is what bounds a read-only stream (Little: ~40 KB must be in flight per SM for 6.5 TB/s):
+// U raw 16-byte loads per stream are issued back to back before any of them is converted, 1024 threads per SM.
+constexpr int IQBN_RED_THREADS = 512;
+// FUSE: cooperative launch (all blocks co-resident) — after a grid-wide barrier every warp of the grid folds one
+// accumulator's partials and finishes it, so the statistics cost one launch and no atomics.
+template <typename T, int V, int MODE, int ACT, int U, bool FUSE>
+__global__ void __launch_bounds__(IQBN_RED_THREADS, 2) iqbn_reduce_b(const T* __restrict__ x, const T* __restrict__ dy, GeomB g,
+                                                                      const float* __restrict__ gamma,
+                                                                      const float* __restrict__ beta, IqbnWs ws, TailArgs tail) {
+  using VecT = Vec<T, V>;
   const int cvl = threadIdx.x % g.cvpg;
   const int rl = threadIdx.x / g.cvpg;
   const int cv = blockIdx.y * g.cvpg + cvl;
-  int pidx[V];
-  colvec_param_index<V>(cv, g.C, pidx);
-
   const int64_t coloff = (int64_t)cv * V;
   float scale[V], shift[V];
   if constexpr (MODE == 1 && ACT != QUAN_ACT_NONE) {   // coefficient table in column order: vector loads
@@ -202,75 +210,114 @@ __global__ void __launch_bounds__(256) iqbn_reduce_b(const T* __restrict__ x, co
   }
 
   float s0[V], s1[V], k[V];
-  int cnt = 0;
 #pragma unroll
   for (int i = 0; i < V; ++i) s0[i] = s1[i] = k[i] = 0.f;
 
-  const int64_t rstride = (int64_t)gridDim.x * g.rpb;
-  for (int64_t r = (int64_t)blockIdx.x * g.rpb + rl; r < g.R; r += rstride * U) {
-    float xv[U][V], gv[U][V];
+  const VecT* xr = reinterpret_cast<const VecT*>(x + coloff);
+  const VecT* gr = reinterpret_cast<const VecT*>(dy + coloff);
+  const int64_t rsv = g.L / V;                                  // row stride in vectors
+  const int64_t rs = (int64_t)gridDim.x * g.rpb;                // rows between two visits of this thread
+  int64_t r = (int64_t)blockIdx.x * g.rpb + rl;
+  const bool lane_on = rl < g.rpb;
+  int cnt = 0;
+  if (lane_on && r < g.R) {
+    cnt = (int)((g.R - 1 - r) / rs) + 1;
+    if constexpr (MODE == 0) {                                  // local shift: keeps fp32 partials well conditioned
+      const VecT t = xr[r * rsv];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t rr = r + u * rstride;
-      if (rr < g.R) {
-        load_vec<T, V>(x + rr * g.L + coloff, xv[u]);
-        if constexpr (MODE == 1) load_vec<T, V>(dy + rr * g.L + coloff, gv[u]);
+      for (int i = 0; i < V; ++i) k[i] = to_f32(t.v[i]);
+    }
+  }
+  auto accumulate = [&](const VecT& xa, const VecT& ga) {
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const float xv = to_f32(xa.v[i]);
+      if constexpr (MODE == 0) {
+        const float d = xv - k[i];
+        s0[i] += d;
+        s1[i] = fmaf(d, d, s1[i]);
+      } else {
+        float dz = to_f32(ga.v[i]);
+        if constexpr (ACT != QUAN_ACT_NONE) dz *= act_grad<ACT, sizeof(T) == 2>(fmaf(xv, scale[i], shift[i]));
+        s0[i] += dz;
+        s1[i] = fmaf(dz, xv, s1[i]);
       }
     }
+  };
+  if (lane_on) {
+    for (; r + (U - 1) * rs < g.R; r += U * rs) {
+      VecT xa[U], ga[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t rr = r + u * rstride;
-      if (rr < g.R) {
-        if constexpr (MODE == 0) {
-          if (cnt == 0) {
-#pragma unroll
-            for (int i = 0; i < V; ++i) k[i] = xv[u][i];  // local shift: keeps fp32 partials well conditioned
-          }
-#pragma unroll
-          for (int i = 0; i < V; ++i) {
-            float d = xv[u][i] - k[i];
-            s0[i] += d;
-            s1[i] = fmaf(d, d, s1[i]);
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < V; ++i) {
-            float dz = gv[u][i];
-            if constexpr (ACT != QUAN_ACT_NONE) dz *= act_grad<ACT>(fmaf(xv[u][i], scale[i], shift[i]));
-            s0[i] += dz;
-            s1[i] = fmaf(dz, xv[u][i], s1[i]);
-          }
-        }
-        ++cnt;
+      for (int u = 0; u < U; ++u) {
+        xa[u] = xr[(r + u * rs) * rsv];
+        if constexpr (MODE == 1) ga[u] = gr[(r + u * rs) * rsv];
       }
+#pragma unroll
+      for (int u = 0; u < U; ++u) accumulate(xa[u], ga[u]);
+    }
+    for (; r < g.R; r += rs) {
+      VecT xa = xr[r * rsv], ga;
+      if constexpr (MODE == 1) ga = gr[r * rsv];
+      accumulate(xa, ga);
     }
   }
 
-  // thread partials -> fp64 raw sums -> shared memory; row lane 0 of every column vector folds the other lanes and
-  // issues the block's single atomic per accumulator
-  extern __shared__ double red[];   // [blockDim.x][2V]
-  double* mine = red + (size_t)threadIdx.x * (2 * V);
+  // thread partials -> fp64 raw sums, folded over the row lanes through shared memory one column element at a time
+  // (2 doubles per thread: 8 KB), then the block's own slot of the partials buffer: plain stores, no atomics
+  __shared__ double red[IQBN_RED_THREADS][2];
+  int half = 1;
+  while (half * 2 < g.rpb) half *= 2;          // largest power of two below rpb (>= rpb/2)
 #pragma unroll
   for (int i = 0; i < V; ++i) {
+    double a0, a1;
     if constexpr (MODE == 0) {  // un-shift in fp64: sum x = sum d + n k ; sum x^2 = sum d^2 + 2k sum d + n k^2
-      double kd = (double)k[i], nd = (double)cnt;
-      mine[2 * i] = (double)s0[i] + nd * kd;
-      mine[2 * i + 1] = (double)s1[i] + 2.0 * kd * (double)s0[i] + nd * kd * kd;
+      const double kd = (double)k[i], nd = (double)cnt;
+      a0 = (double)s0[i] + nd * kd;
+      a1 = (double)s1[i] + 2.0 * kd * (double)s0[i] + nd * kd * kd;
     } else {
-      mine[2 * i] = (double)s0[i];
-      mine[2 * i + 1] = (double)s1[i];
+      a0 = (double)s0[i];
+      a1 = (double)s1[i];
+    }
+    __syncthreads();
+    red[threadIdx.x][0] = lane_on ? a0 : 0.0;
+    red[threadIdx.x][1] = lane_on ? a1 : 0.0;
+    __syncthreads();
+    for (int st = half; st >= 1; st >>= 1) {      // tree over the row lanes (fixed order: deterministic)
+      if (rl < st && rl + st < g.rpb) {
+        red[threadIdx.x][0] += red[threadIdx.x + st * g.cvpg][0];
+        red[threadIdx.x][1] += red[threadIdx.x + st * g.cvpg][1];
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x < g.cvpg) {
+      const int col = (blockIdx.y * g.cvpg + threadIdx.x) * V + i;
+      const int q = col / g.C, c = col - q * g.C;
+      ws.part[((size_t)blockIdx.x * 2 + 0) * 4 * g.C + c * 4 + q] = red[threadIdx.x][0];
+      ws.part[((size_t)blockIdx.x * 2 + 1) * 4 * g.C + c * 4 + q] = red[threadIdx.x][1];
     }
   }
-  __syncthreads();
-  // 2V values per column vector, cvpg column vectors: spread the folding over all threads of the block
-  const int nval = g.cvpg * 2 * V;
-  for (int e = threadIdx.x; e < nval; e += blockDim.x) {
-    const int c_v = e / (2 * V), j = e - c_v * (2 * V);      // column vector, value index (2*i + which)
-    double acc = 0.0;
-    for (int l = 0; l < g.rpb; ++l) acc += red[(size_t)(l * g.cvpg + c_v) * (2 * V) + j];
-    const int col = (blockIdx.y * g.cvpg + c_v) * V + (j >> 1);
-    const int q = col / g.C, c = col - q * g.C;
-    ws.part[((size_t)blockIdx.x * 2 + (j & 1)) * 4 * g.C + c * 4 + q] = acc;   // this block's slot: plain store
+  if constexpr (FUSE) {
+    __threadfence();
+    cooperative_groups::this_grid().sync();
+    const int n = 4 * g.C, lane = threadIdx.x & 31;
+    const int full_warps = blockDim.x >> 5;                      // a trailing partial warp sits this out
+    const int wib = threadIdx.x >> 5;
+    if (wib < full_warps) {
+      const int total_warps = gridDim.x * gridDim.y * full_warps;
+      for (int i = (blockIdx.y * gridDim.x + blockIdx.x) * full_warps + wib; i < n; i += total_warps) {
+        double a0 = 0.0, a1 = 0.0;
+        for (int sp = lane; sp < (int)gridDim.x; sp += 32) {     // written by other blocks of this launch: L2 loads
+          a0 += __ldcg(ws.part + ((size_t)sp * 2 + 0) * n + i);
+          a1 += __ldcg(ws.part + ((size_t)sp * 2 + 1) * n + i);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+          a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+        }
+        if (lane == 0) finish_accumulator(tail, i, a0, a1);
+      }
+    }
   }
 }
 
@@ -339,7 +386,7 @@ __device__ __forceinline__ void write_param_grads(const ApplyArgs& a) {
 }
 
 template <typename T, int V, int ACT, bool BWD, int U>
-__global__ void __launch_bounds__(256) iqbn_apply_b(const T* __restrict__ x, const T* __restrict__ dy,
+__global__ void __launch_bounds__(256, BWD ? 3 : 4) iqbn_apply_b(const T* __restrict__ x, const T* __restrict__ dy,
                                                     T* __restrict__ out, GeomB g, ApplyArgs a) {
   const int cvl = threadIdx.x % g.cvpg;
   const int rl = threadIdx.x / g.cvpg;
@@ -366,35 +413,43 @@ __global__ void __launch_bounds__(256) iqbn_apply_b(const T* __restrict__ x, con
   }
   if constexpr (BWD) write_param_grads(a);
 
-  const int64_t rstride = (int64_t)gridDim.x * g.rpb;
-  for (int64_t r = (int64_t)blockIdx.x * g.rpb + rl; r < g.R; r += rstride * U) {
-    float xv[U][V], gv[U][V];
+  using VecT = Vec<T, V>;
+  const VecT* xr = reinterpret_cast<const VecT*>(x + coloff);
+  const VecT* gr = reinterpret_cast<const VecT*>(dy + coloff);
+  VecT* orow = reinterpret_cast<VecT*>(out + coloff);
+  const int64_t rsv = g.L / V;
+  const int64_t rs = (int64_t)gridDim.x * g.rpb;
+  auto apply = [&](const VecT& xa, const VecT& ga) {
+    VecT o;
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t rr = r + u * rstride;
-      if (rr < g.R) {
-        load_vec<T, V>(x + rr * g.L + coloff, xv[u]);
-        if constexpr (BWD) load_vec<T, V>(dy + rr * g.L + coloff, gv[u]);
+    for (int i = 0; i < V; ++i) {
+      const float xv = to_f32(xa.v[i]);
+      if constexpr (!BWD) {
+        o.v[i] = from_f32<T>(act_fwd<ACT, sizeof(T) == 2>(fmaf(xv, scale[i], shift[i])));
+      } else {
+        float dz = to_f32(ga.v[i]);
+        if constexpr (ACT != QUAN_ACT_NONE) dz *= act_grad<ACT, sizeof(T) == 2>(fmaf(xv, scale[i], shift[i]));
+        o.v[i] = from_f32<T>(fmaf(k1[i], dz, fmaf(k2[i], xv, k3[i])));
       }
     }
+    return o;
+  };
+  if (rl < g.rpb) {
+    int64_t r = (int64_t)blockIdx.x * g.rpb + rl;
+    for (; r + (U - 1) * rs < g.R; r += U * rs) {
+      VecT xa[U], ga[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t rr = r + u * rstride;
-      if (rr < g.R) {
-        float ov[V];
-        if constexpr (!BWD) {
-#pragma unroll
-          for (int i = 0; i < V; ++i) ov[i] = act_fwd<ACT>(fmaf(xv[u][i], scale[i], shift[i]));
-        } else {
-#pragma unroll
-          for (int i = 0; i < V; ++i) {
-            float dz = gv[u][i];
-            if constexpr (ACT != QUAN_ACT_NONE) dz *= act_grad<ACT>(fmaf(xv[u][i], scale[i], shift[i]));
-            ov[i] = fmaf(k1[i], dz, fmaf(k2[i], xv[u][i], k3[i]));
-          }
-        }
-        store_vec<T, V>(out + rr * g.L + coloff, ov);
+      for (int u = 0; u < U; ++u) {
+        xa[u] = xr[(r + u * rs) * rsv];
+        if constexpr (BWD) ga[u] = gr[(r + u * rs) * rsv];
       }
+#pragma unroll
+      for (int u = 0; u < U; ++u) orow[(r + u * rs) * rsv] = apply(xa[u], ga[u]);
+    }
+    for (; r < g.R; r += rs) {
+      VecT xa = xr[r * rsv], ga;
+      if constexpr (BWD) ga = gr[r * rsv];
+      orow[r * rsv] = apply(xa, ga);
     }
   }
 }
@@ -557,15 +612,14 @@ static int env_int(const char* name, int dflt) {
 }
 
 template <typename T>
-static bool plan_b(int B, int C, int H, int W, int unroll, int blocks_per_sm, LaunchB& p) {
-  if (blocks_per_sm >= 8) blocks_per_sm = env_int("QUAN_IQBN_BPS", blocks_per_sm);   // apply kernels only
+static bool plan_b(int B, int C, int H, int W, int unroll, int blocks_per_sm, int threads, LaunchB& p) {
   p.V = largest_pow2_divisor(C, VecTraits<T>::kMaxVec);
   const int colvecs = 4 * C / p.V;
   int cg = (colvecs + 255) / 256;                   // column groups (wide rows only)
   while (colvecs % cg) ++cg;
   const int cvpg = colvecs / cg;
   if (cvpg > 256 || cg > 65535) return false;
-  const int rpb = 256 / cvpg;
+  const int rpb = threads / cvpg;
   p.g.R = (int64_t)B * H * W;
   p.g.L = 4 * C;
   p.g.C = C;
@@ -611,6 +665,37 @@ static void plan_a(int B, int C, int H, int W, LaunchA& p) {
     default: { constexpr int kV = 1; __VA_ARGS__; } break; \
   }
 
+// cooperative (fused fold) launch when the whole grid is co-resident, else the plain kernel (the caller adds the fold)
+template <typename T, int V, int MODE, int ACT, int U>
+static int launch_reduce_b(dim3 grid, dim3 block, cudaStream_t st, const T* xp, const T* dyp, GeomB g, const float* gamma,
+                           const float* beta, IqbnWs ws, TailArgs tail, bool* fused) {
+  static thread_local int blocks_per_sm = -1, sms = 0;
+  auto coop = iqbn_reduce_b<T, V, MODE, ACT, U, true>;
+  if (blocks_per_sm < 0) {
+    int dev = 0;
+    QUAN_CUDA(cudaGetDevice(&dev));
+    QUAN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    int supported = 0;
+    QUAN_CUDA(cudaDeviceGetAttribute(&supported, cudaDevAttrCooperativeLaunch, dev));
+    int nb = 0;
+    QUAN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, coop, IQBN_RED_THREADS, 0));
+    blocks_per_sm = supported ? nb : 0;
+    // measured on B200 (C=256, 134 MB): one cooperative launch 46.9 us vs reduce + fold kernels 41.9 us — a cooperative
+    // launch cannot overlap the previous kernel's tail and its grid barrier costs more than the second launch: opt-in only
+    if (env_int("QUAN_IQBN_FUSE", 0) == 0) blocks_per_sm = 0;
+  }
+  if ((int64_t)grid.x * grid.y <= (int64_t)blocks_per_sm * sms) {
+    void* args[] = {(void*)&xp, (void*)&dyp, (void*)&g, (void*)&gamma, (void*)&beta, (void*)&ws, (void*)&tail};
+    QUAN_CUDA(cudaLaunchCooperativeKernel((const void*)coop, grid, block, args, 0, st));
+    count_launch();
+    *fused = true;
+    return QUAN_OK;
+  }
+  iqbn_reduce_b<T, V, MODE, ACT, U, false><<<grid, block, 0, st>>>(xp, dyp, g, gamma, beta, ws, tail);
+  *fused = false;
+  return QUAN_OK;
+}
+
 template <typename T, int MODE, int ACT>
 static int launch_reduce(const void* x, const void* dy, int B, int C, int H, int W, int layout,
                          const float* gamma, const float* beta, IqbnWs ws, TailArgs tail, cudaStream_t st) {
@@ -619,26 +704,25 @@ static int launch_reduce(const void* x, const void* dy, int B, int C, int H, int
   int nparts = 1;
   if (layout == QUAN_LAYOUT_BHWQC && C > 1) {
     LaunchB p;
-    // measured (profiles/r01_iqbn_tune5.log): many light warps beat unrolled ones — U = 1 at 4 blocks/SM is the best
-    // point for both reductions (stats 46 us, bwd-reduce 80 us on 134 MB tensors); U > 1 only costs registers
-    const int U = env_int("QUAN_IQBN_RU", 1);
-    int bps = env_int("QUAN_IQBN_RBPS", 4);
-    if (bps > 4) bps = 4;
-    if (!plan_b<T>(B, C, H, W, U, bps, p)) {
+    // 2 blocks of 512 threads per SM, U independent 16-byte loads per stream and thread in flight (>= 64 KB per SM)
+    const int U = env_int("QUAN_IQBN_RU", MODE == 0 ? 4 : 2);
+    const int bps = env_int("QUAN_IQBN_RBPS", 2);
+    if (!plan_b<T>(B, C, H, W, U, bps, IQBN_RED_THREADS, p)) {
       set_error("iqbn: C=%d too large for the BHWQC kernels", C);
       return QUAN_E_UNSUPPORTED;
     }
     if (p.grid.x > (unsigned)IQBN_MAX_PARTS) p.grid.x = IQBN_MAX_PARTS;
     nparts = (int)p.grid.x;
-#define QUAN_REDUCE_B(UU) QUAN_DISPATCH_V(p.V, (iqbn_reduce_b<T, (sizeof(T) == 4 && kV == 8) ? 4 : kV, MODE, ACT, UU> \
-                          <<<p.grid, p.block, (size_t)p.block.x * 2 * kV * sizeof(double), st>>>(xp, dyp, p.g, gamma, beta, ws, tail)))
+    bool fused = false;
+#define QUAN_REDUCE_B(UU) QUAN_DISPATCH_V(p.V, { int rc_ = launch_reduce_b<T, (sizeof(T) == 4 && kV == 8) ? 4 : kV, MODE, ACT, UU>( \
+                          p.grid, p.block, st, xp, dyp, p.g, gamma, beta, ws, tail, &fused); if (rc_) return rc_; })
     switch (U) {
       case 1: QUAN_REDUCE_B(1); break;
       case 2: QUAN_REDUCE_B(2); break;
-      case 8: QUAN_REDUCE_B(8); break;
       default: QUAN_REDUCE_B(4); break;
     }
 #undef QUAN_REDUCE_B
+    if (fused) return QUAN_OK;
   } else {
     LaunchA p;
     plan_a<T>(B, C, H, W, p);
@@ -665,10 +749,9 @@ static int launch_apply(const void* x, const void* dy, void* out, int B, int C, 
   T* op = reinterpret_cast<T*>(out);
   if (layout == QUAN_LAYOUT_BHWQC && C > 1) {
     LaunchB p;
-    // measured on B200 (profiles/r01_iqbn_tune.log): the per-thread coefficient prologue makes many light blocks lose to
-    // few blocks; U = 1 with 4 (fwd) / 2 (bwd) blocks per SM is the best point of the sweep
-    const int U = env_int("QUAN_IQBN_U", BWD ? 1 : 2);
-    if (!plan_b<T>(B, C, H, W, U, 8, p)) {
+    // 4 blocks of 256 threads per SM; U rows (16-byte vectors) per stream in flight per thread
+    const int U = env_int("QUAN_IQBN_U", BWD ? 2 : 4);
+    if (!plan_b<T>(B, C, H, W, U, env_int("QUAN_IQBN_BPS", BWD ? 3 : 4), 256, p)) {
       set_error("iqbn: C=%d too large for the BHWQC kernels", C);
       return QUAN_E_UNSUPPORTED;
     }
@@ -677,7 +760,6 @@ static int launch_apply(const void* x, const void* dy, void* out, int B, int C, 
     switch (U) {
       case 1: QUAN_APPLY_B(1); break;
       case 2: QUAN_APPLY_B(2); break;
-      case 8: QUAN_APPLY_B(8); break;
       default: QUAN_APPLY_B(4); break;
     }
 #undef QUAN_APPLY_B

@@ -30,9 +30,11 @@ static size_t g_bytes(const quan_conv_dims& d, int dtype) {
 
 static int resolve_algo(const quan_conv_dims& d, int dtype, int layout, int pass, int algo) {
   if (algo == QUAN_ALGO_DIRECT) return QUAN_ALGO_DIRECT;
+  if (algo == QUAN_ALGO_DEPTHWISE) return qconv_dw_supported(d, dtype, layout, pass) ? QUAN_ALGO_DEPTHWISE : -1;
   const bool ok = qconv_tc_supported(d, dtype, layout, pass);
   if (algo == QUAN_ALGO_TCGEN05) return ok ? QUAN_ALGO_TCGEN05 : -1;
-  return ok ? QUAN_ALGO_TCGEN05 : QUAN_ALGO_DIRECT;
+  if (ok) return QUAN_ALGO_TCGEN05;
+  return qconv_dw_supported(d, dtype, layout, pass) ? QUAN_ALGO_DEPTHWISE : QUAN_ALGO_DIRECT;
 }
 
 }  // namespace quan
@@ -68,7 +70,8 @@ int quan_qconv2d_fwd(const void* x, const float* const w[4], const float* bias_r
                "qconv2d_fwd: null tensor pointer");
   cudaStream_t st = (cudaStream_t)stream;
   const int a = resolve_algo(*d, dtype, layout, PASS_FWD, algo);
-  QUAN_REQUIRE(a > 0, QUAN_E_UNSUPPORTED, "qconv2d_fwd: tcgen05 engine requested but shape/layout does not qualify");
+  QUAN_REQUIRE(a > 0, QUAN_E_UNSUPPORTED, "qconv2d_fwd: requested engine does not serve this shape/layout");
+  if (a == QUAN_ALGO_DEPTHWISE) return qconv_dw_fwd(x, w, bias_r, y, *d, dtype, mix, st);
   if (a == QUAN_ALGO_TCGEN05) {
     const size_t need = qconv_tc_workspace_bytes(*d, dtype, layout, PASS_FWD);
     QUAN_REQUIRE(workspace != nullptr && ws_bytes >= need, QUAN_E_WORKSPACE,
@@ -98,16 +101,17 @@ int quan_qconv2d_bwd(const void* dy, const void* x, const float* const w[4], voi
   int a_dx = 0, a_dw = 0, m_dx = TC_NONE, m_dw = TC_NONE;
   if (dx != nullptr) {
     a_dx = resolve_algo(*d, dtype, layout, PASS_DGRAD, algo);
-    QUAN_REQUIRE(a_dx > 0, QUAN_E_UNSUPPORTED, "qconv2d_bwd: tcgen05 dgrad requested but shape/layout does not qualify");
+    QUAN_REQUIRE(a_dx > 0, QUAN_E_UNSUPPORTED, "qconv2d_bwd: requested engine does not serve this dgrad shape/layout");
     if (a_dx == QUAN_ALGO_TCGEN05) m_dx = qconv_tc_mode(*d, dtype, layout, PASS_DGRAD);
   }
   if (dw != nullptr) {
     a_dw = resolve_algo(*d, dtype, layout, PASS_WGRAD, algo);
-    QUAN_REQUIRE(a_dw > 0, QUAN_E_UNSUPPORTED, "qconv2d_bwd: tcgen05 wgrad requested but shape/layout does not qualify");
+    QUAN_REQUIRE(a_dw > 0, QUAN_E_UNSUPPORTED, "qconv2d_bwd: requested engine does not serve this wgrad shape/layout");
     if (a_dw == QUAN_ALGO_TCGEN05) m_dw = qconv_tc_mode(*d, dtype, layout, PASS_WGRAD);
   }
   // G = M^T dY, once, shared by every consumer that needs it (separable dgrad / wgrad, direct engine, bias grad)
-  const bool need_g = (dx != nullptr && m_dx != TC_DENSE) || (dw != nullptr && m_dw != TC_DENSE) || dbias_r != nullptr;
+  const bool need_g = (dx != nullptr && m_dx != TC_DENSE && a_dx != QUAN_ALGO_DEPTHWISE) ||
+                      (dw != nullptr && m_dw != TC_DENSE && a_dw != QUAN_ALGO_DEPTHWISE) || dbias_r != nullptr;
   if (need_g) {
     float mix_t[16];
     for (int p = 0; p < 4; ++p)
@@ -122,6 +126,8 @@ int quan_qconv2d_bwd(const void* dy, const void* x, const float* const w[4], voi
       const size_t need = qconv_tc_workspace_bytes(*d, dtype, layout, PASS_DGRAD);
       QUAN_REQUIRE(tc_ws_bytes >= need, QUAN_E_WORKSPACE, "qconv2d_bwd: dgrad needs %zu more workspace bytes", need);
       rc = qconv_tc_dgrad(m_dx == TC_DENSE ? dy : gq, w, dx, *d, dtype, m_dx, mix, tc_ws, tc_ws_bytes, st);
+    } else if (a_dx == QUAN_ALGO_DEPTHWISE) {
+      rc = qconv_dw_dgrad(dy, w, dx, *d, dtype, mix, st);
     } else {
       rc = qconv_dgrad_direct_launch(gq, w, dx, *d, dtype, layout, st);
     }
@@ -132,6 +138,8 @@ int quan_qconv2d_bwd(const void* dy, const void* x, const float* const w[4], voi
       const size_t need = qconv_tc_workspace_bytes(*d, dtype, layout, PASS_WGRAD);
       QUAN_REQUIRE(tc_ws_bytes >= need, QUAN_E_WORKSPACE, "qconv2d_bwd: wgrad needs %zu more workspace bytes", need);
       rc = qconv_tc_wgrad(m_dw == TC_DENSE ? dy : gq, x, dw, *d, dtype, m_dw, mix, tc_ws, tc_ws_bytes, st);
+    } else if (a_dw == QUAN_ALGO_DEPTHWISE) {
+      rc = qconv_dw_wgrad(dy, x, dw, *d, dtype, mix, st);
     } else {
       rc = qconv_wgrad_direct_launch(gq, x, dw, *d, dtype, layout, st);
     }

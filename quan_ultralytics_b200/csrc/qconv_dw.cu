@@ -1,0 +1,257 @@
+// qconv_dw.cu — depthwise QConv2D (groups == C_i == C_o, the DWConv blocks of QUAN-YOLO11: conv.py:918-923) in the
+// BHWQC layout.  HBM-bound streaming kernels: a pixel is 4 rows of C contiguous channels, a thread owns one 16-byte
+// channel vector (fwd / dgrad) or one channel pair (wgrad) of ALL FOUR components, so the mixing matrix is applied in
+// registers on the way out (fwd: y = M S) or on the way in (dgrad / wgrad: G = M^T dY) and neither S nor G touches HBM.
+//
+// Math (reference semantics): ultralytics/nn/modules/conv.py:472-499 with groups = C; backward = autograd of it.
+//   S_q[c] = sum_tap x_q[c](pix (+) tap) w_q[c][tap] (+ b_r[c] on q = r);   y_p = sum_q M[p][q] S_q
+//   dX_q[c] = sum_tap G_q[c](pix (-) tap) w_q[c][tap];   dW_q[c][tap] = sum_pix G_q[c](pix) x_q[c](pix (+) tap)
+#include "qconv_internal.cuh"
+
+namespace quan {
+
+struct DwGeom {
+  int B, C, H, W, Ho, Wo;          // x [B][H][W][4][C], y / dY [B][Ho][Wo][4][C]
+  int kH, kW, sH, sW, pH, pW, dH, dW;
+};
+
+static DwGeom make_dw_geom(const quan_conv_dims& d) {
+  DwGeom g;
+  g.B = d.B; g.C = d.Ci; g.H = d.H; g.W = d.W;
+  g.Ho = conv_out(d.H, d.kH, d.sH, d.pH, d.dH);
+  g.Wo = conv_out(d.W, d.kW, d.sW, d.pW, d.dW);
+  g.kH = d.kH; g.kW = d.kW; g.sH = d.sH; g.sW = d.sW; g.pH = d.pH; g.pW = d.pW; g.dH = d.dH; g.dW = d.dW;
+  return g;
+}
+
+struct W4p {
+  const float* w[4];
+};
+
+// TRANSPOSED = false: forward (one thread = one output pixel x V channels x 4 components, final mix with M).
+// TRANSPOSED = true : dgrad (one thread = one input pixel; dY is mixed with M^T as it is loaded, taps that do not
+//                     land on the stride grid are skipped).
+// Weights are staged once per block in shared memory as [tap][q][C] so a thread's V coefficients are contiguous.
+template <typename T, int V, bool TRANSPOSED>
+__global__ void __launch_bounds__(256) qconv_dw_kernel(const T* __restrict__ in, W4p w, const float* __restrict__ bias_r,
+                                                       T* __restrict__ out, DwGeom g, Mix16 M) {
+  extern __shared__ float wsm[];   // [taps][4][C]
+  const int taps = g.kH * g.kW;
+  for (int e = threadIdx.x; e < taps * 4 * g.C; e += blockDim.x) {
+    const int c = e % g.C, q = (e / g.C) & 3, tap = e / (4 * g.C);
+    wsm[e] = __ldg(w.w[q] + (int64_t)c * taps + tap);
+  }
+  __syncthreads();
+  const int cvs = g.C / V;
+  const int Hout = TRANSPOSED ? g.H : g.Ho, Wout = TRANSPOSED ? g.W : g.Wo;   // grid this kernel writes
+  const int Hin = TRANSPOSED ? g.Ho : g.H, Win = TRANSPOSED ? g.Wo : g.W;     // grid it reads
+  const int64_t items = (int64_t)g.B * Hout * Wout * cvs;
+  for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < items; it += (int64_t)gridDim.x * blockDim.x) {
+    const int cv = (int)(it % cvs);
+    int64_t pix = it / cvs;
+    const int wo = (int)(pix % Wout);
+    pix /= Wout;
+    const int ho = (int)(pix % Hout);
+    const int b = (int)(pix / Hout);
+    float acc[4][V];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int v = 0; v < V; ++v) acc[q][v] = 0.f;
+    if constexpr (!TRANSPOSED) {
+      if (bias_r != nullptr) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) acc[0][v] = __ldg(bias_r + cv * V + v);   // conv.py:480: bias joins S_r before the mix
+      }
+    }
+    for (int kh = 0; kh < g.kH; ++kh) {
+      int hi;
+      if constexpr (TRANSPOSED) {
+        const int th = ho + g.pH - kh * g.dH;
+        if (th < 0 || th % g.sH != 0) continue;
+        hi = th / g.sH;
+      } else {
+        hi = ho * g.sH - g.pH + kh * g.dH;
+      }
+      if (hi < 0 || hi >= Hin) continue;
+      for (int kw = 0; kw < g.kW; ++kw) {
+        int wi;
+        if constexpr (TRANSPOSED) {
+          const int tw = wo + g.pW - kw * g.dW;
+          if (tw < 0 || tw % g.sW != 0) continue;
+          wi = tw / g.sW;
+        } else {
+          wi = wo * g.sW - g.pW + kw * g.dW;
+        }
+        if (wi < 0 || wi >= Win) continue;
+        const T* src = in + ((((int64_t)b * Hin + hi) * Win + wi) * 4) * g.C + cv * V;
+        float xv[4][V];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) load_vec<T, V>(src + (int64_t)q * g.C, xv[q]);
+        const float* wt = wsm + (size_t)(kh * g.kW + kw) * 4 * g.C + cv * V;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+#pragma unroll
+          for (int v = 0; v < V; ++v) {
+            float a;
+            if constexpr (TRANSPOSED)   // G_q = sum_p M[p][q] dY_p
+              a = M.m[0 * 4 + q] * xv[0][v] + M.m[1 * 4 + q] * xv[1][v] + M.m[2 * 4 + q] * xv[2][v] + M.m[3 * 4 + q] * xv[3][v];
+            else
+              a = xv[q][v];
+            acc[q][v] = fmaf(a, wt[q * g.C + v], acc[q][v]);
+          }
+        }
+      }
+    }
+    T* dst = out + ((((int64_t)b * Hout + ho) * Wout + wo) * 4) * g.C + cv * V;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      float o[V];
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        if constexpr (TRANSPOSED) o[v] = acc[p][v];
+        else o[v] = M.m[p * 4 + 0] * acc[0][v] + M.m[p * 4 + 1] * acc[1][v] + M.m[p * 4 + 2] * acc[2][v] + M.m[p * 4 + 3] * acc[3][v];
+      }
+      store_vec<T, V>(dst + (int64_t)p * g.C, o);
+    }
+  }
+}
+
+// wgrad: one thread = one channel pair x 4 components, a block covers 256 / (C/2) output pixels per step and strides
+// over the image; per-thread accumulators [taps][4][2], folded over the block's pixel lanes through shared memory, then
+// one fp32 atomicAdd per (q, c, tap) and block into the zero-initialised dW (atomic order is not deterministic).
+template <typename T, int TAPS>
+__global__ void __launch_bounds__(256) qconv_dw_wgrad_kernel(const T* __restrict__ dy, const T* __restrict__ x, float* dw0,
+                                                             float* dw1, float* dw2, float* dw3, DwGeom g, Mix16 M) {
+  __shared__ float red[256][9];
+  const int tpp = g.C / 2;                       // threads per pixel
+  const int ppb = blockDim.x / tpp;              // pixel lanes per block
+  const int cp = threadIdx.x % tpp, pl = threadIdx.x / tpp;
+  const int64_t npix = (int64_t)g.B * g.Ho * g.Wo;
+  float acc[TAPS][4][2];
+#pragma unroll
+  for (int t = 0; t < TAPS; ++t)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[t][q][0] = acc[t][q][1] = 0.f;
+  if (pl < ppb) {
+    for (int64_t pix = (int64_t)blockIdx.x * ppb + pl; pix < npix; pix += (int64_t)gridDim.x * ppb) {
+      const int wo = (int)(pix % g.Wo);
+      const int64_t r = pix / g.Wo;
+      const int ho = (int)(r % g.Ho);
+      const int b = (int)(r / g.Ho);
+      float gy[4][2], gq[4][2];
+      const T* gsrc = dy + (pix * 4) * g.C + cp * 2;
+#pragma unroll
+      for (int p = 0; p < 4; ++p) load_vec<T, 2>(gsrc + (int64_t)p * g.C, gy[p]);
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int v = 0; v < 2; ++v)
+          gq[q][v] = M.m[0 * 4 + q] * gy[0][v] + M.m[1 * 4 + q] * gy[1][v] + M.m[2 * 4 + q] * gy[2][v] + M.m[3 * 4 + q] * gy[3][v];
+#pragma unroll
+      for (int t = 0; t < TAPS; ++t) {
+        const int kh = t / g.kW, kw = t - kh * g.kW;
+        const int hi = ho * g.sH - g.pH + kh * g.dH, wi = wo * g.sW - g.pW + kw * g.dW;
+        if (t < g.kH * g.kW && hi >= 0 && hi < g.H && wi >= 0 && wi < g.W) {
+          const T* xs = x + ((((int64_t)b * g.H + hi) * g.W + wi) * 4) * g.C + cp * 2;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float xv[2];
+            load_vec<T, 2>(xs + (int64_t)q * g.C, xv);
+            acc[t][q][0] = fmaf(gq[q][0], xv[0], acc[t][q][0]);
+            acc[t][q][1] = fmaf(gq[q][1], xv[1], acc[t][q][1]);
+          }
+        }
+      }
+    }
+  }
+  const int taps = g.kH * g.kW;
+  for (int t = 0; t < TAPS; ++t) {
+    if (t >= taps) break;
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      red[threadIdx.x][q * 2 + 0] = acc[t][q][0];
+      red[threadIdx.x][q * 2 + 1] = acc[t][q][1];
+    }
+    __syncthreads();
+    if (pl == 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float s = 0.f;
+        for (int l = 0; l < ppb; ++l) s += red[l * tpp + cp][j];
+        const int q = j >> 1, c = cp * 2 + (j & 1);
+        float* dw = q == 0 ? dw0 : q == 1 ? dw1 : q == 2 ? dw2 : dw3;
+        atomicAdd(dw + (int64_t)c * taps + t, s);
+      }
+    }
+  }
+}
+
+// ---- host ------------------------------------------------------------------------------------------------------------
+bool qconv_dw_supported(const quan_conv_dims& d, int dtype, int layout, int pass) {
+  if (layout != QUAN_LAYOUT_BHWQC || d.groups != d.Ci || d.Ci != d.Co || d.groups < 2) return false;
+  const int V = dtype == QUAN_BF16 ? 8 : 4;
+  if (d.Ci % V != 0 && d.Ci % (V / 2) != 0) return false;
+  if ((size_t)d.kH * d.kW * 4 * d.Ci * sizeof(float) > 40 * 1024) return false;
+  if (pass == PASS_WGRAD) return d.kH * d.kW <= 9 && d.Ci % 2 == 0 && d.Ci / 2 <= 256;
+  return true;
+}
+
+template <typename T, bool TRANSPOSED>
+static int dw_launch_t(const void* in, const float* const w[4], const float* bias_r, void* out, const DwGeom& g, const Mix16& M,
+                       cudaStream_t st) {
+  constexpr int VMAX = 16 / (int)sizeof(T);
+  const size_t smem = (size_t)g.kH * g.kW * 4 * g.C * sizeof(float);
+  const int64_t opix = (int64_t)g.B * (TRANSPOSED ? g.H * g.W : g.Ho * g.Wo);
+  W4p w4 = {{w[0], w[1], w[2], w[3]}};
+  if (g.C % VMAX == 0) {
+    const int grid = grid_for(opix * (g.C / VMAX), 256, 8);
+    qconv_dw_kernel<T, VMAX, TRANSPOSED><<<grid, 256, smem, st>>>((const T*)in, w4, bias_r, (T*)out, g, M);
+  } else {
+    const int grid = grid_for(opix * (g.C / (VMAX / 2)), 256, 8);
+    qconv_dw_kernel<T, VMAX / 2, TRANSPOSED><<<grid, 256, smem, st>>>((const T*)in, w4, bias_r, (T*)out, g, M);
+  }
+  QUAN_CHECK_LAUNCH("qconv_dw_kernel");
+  return QUAN_OK;
+}
+
+int qconv_dw_fwd(const void* x, const float* const w[4], const float* bias_r, void* y, const quan_conv_dims& d, int dtype,
+                 const float* mix, cudaStream_t st) {
+  const DwGeom g = make_dw_geom(d);
+  const Mix16 M = make_mix(mix);
+  if (dtype == QUAN_BF16) return dw_launch_t<__nv_bfloat16, false>(x, w, bias_r, y, g, M, st);
+  return dw_launch_t<float, false>(x, w, bias_r, y, g, M, st);
+}
+
+// dy is the raw output gradient (mix = forward mixing matrix; M^T is applied on load)
+int qconv_dw_dgrad(const void* dy, const float* const w[4], void* dx, const quan_conv_dims& d, int dtype, const float* mix,
+                   cudaStream_t st) {
+  const DwGeom g = make_dw_geom(d);
+  const Mix16 M = make_mix(mix);
+  if (dtype == QUAN_BF16) return dw_launch_t<__nv_bfloat16, true>(dy, w, nullptr, dx, g, M, st);
+  return dw_launch_t<float, true>(dy, w, nullptr, dx, g, M, st);
+}
+
+int qconv_dw_wgrad(const void* dy, const void* x, float* const dw[4], const quan_conv_dims& d, int dtype, const float* mix,
+                   cudaStream_t st) {
+  const DwGeom g = make_dw_geom(d);
+  const Mix16 M = make_mix(mix);
+  const int taps = d.kH * d.kW;
+  for (int q = 0; q < 4; ++q) QUAN_CUDA(cudaMemsetAsync(dw[q], 0, (size_t)d.Co * taps * sizeof(float), st));
+  const int tpp = g.C / 2, ppb = 256 / tpp;
+  const int64_t npix = (int64_t)g.B * g.Ho * g.Wo;
+  int64_t blocks = ceil_div64(npix, (int64_t)ppb * 16);          // >= 16 pixels per pixel lane
+  if (blocks > QUAN_NUM_SMS * 4) blocks = QUAN_NUM_SMS * 4;
+  if (blocks < 1) blocks = 1;
+  if (dtype == QUAN_BF16)
+    qconv_dw_wgrad_kernel<__nv_bfloat16, 9><<<(unsigned)blocks, 256, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x,
+                                                                               dw[0], dw[1], dw[2], dw[3], g, M);
+  else
+    qconv_dw_wgrad_kernel<float, 9><<<(unsigned)blocks, 256, 0, st>>>((const float*)dy, (const float*)x, dw[0], dw[1], dw[2],
+                                                                       dw[3], g, M);
+  QUAN_CHECK_LAUNCH("qconv_dw_wgrad_kernel");
+  return QUAN_OK;
+}
+
+}  // namespace quan

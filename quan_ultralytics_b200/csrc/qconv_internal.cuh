@@ -13,6 +13,15 @@ int qconv_wgrad_direct_launch(const void* gq, const void* x, float* const dw[4],
                               int layout, cudaStream_t st);
 int qconv_bias_grad_launch(const void* gq, float* db, const quan_conv_dims& d, int dtype, int layout, cudaStream_t st);
 
+// ---- depthwise streaming kernels (BHWQC, groups == C), qconv_dw.cu: take dY itself (M^T applied on load) ----------
+bool qconv_dw_supported(const quan_conv_dims& d, int dtype, int layout, int pass);
+int qconv_dw_fwd(const void* x, const float* const w[4], const float* bias_r, void* y, const quan_conv_dims& d, int dtype,
+                 const float* mix, cudaStream_t st);
+int qconv_dw_dgrad(const void* dy, const float* const w[4], void* dx, const quan_conv_dims& d, int dtype, const float* mix,
+                   cudaStream_t st);
+int qconv_dw_wgrad(const void* dy, const void* x, float* const dw[4], const quan_conv_dims& d, int dtype, const float* mix,
+                   cudaStream_t st);
+
 // ---- tcgen05 (tensor-core) engine, qconv_tc.cu ----------------------------------------------------
 enum { PASS_FWD = 0, PASS_DGRAD = 1, PASS_WGRAD = 2 };
 // how the implicit-GEMM kernels serve a shape: not at all, one GEMM per quaternion component (mix in the epilogue),

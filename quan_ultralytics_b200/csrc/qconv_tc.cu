@@ -67,32 +67,62 @@ static int encode_map(CUtensorMap* map, int dtype, int rank, const void* base, c
 // ---------------------------------------------------------------------------------------------------------------
 // weight packing: fp32 master W_q[co][ci][tap] -> T Wp[q][tap][n][k]
 //   FWD  : n = co, k = ci, tap kept          DGRAD: n = ci, k = co, tap flipped (taps-1-tap)
+// Both are transposes (tap moves from innermost to outermost, DGRAD also swaps co and ci), staged through shared memory
+// so that global reads and writes are both contiguous (the first, one-thread-per-element version took 17 us for the
+// 2.4 M weights of a C_q = 256 3x3 layer: 6% of the forward pass).
 // ---------------------------------------------------------------------------------------------------------------
-template <typename T, bool DGRAD>
-__global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restrict__ w0, const float* __restrict__ w1,
-                                                           const float* __restrict__ w2, const float* __restrict__ w3,
-                                                           T* __restrict__ out, int Co, int Ci, int taps) {
-  const int64_t per_q = (int64_t)Co * Ci * taps;
-  const int64_t total = 4 * per_q;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int q = (int)(i / per_q);
-    int64_t r = i - q * per_q;
-    const int N = DGRAD ? Ci : Co, K = DGRAD ? Co : Ci;
-    const int k = (int)(r % K);
-    r /= K;
-    const int n = (int)(r % N);
-    const int t = (int)(r / N);
-    const int co = DGRAD ? k : n, ci = DGRAD ? n : k, tap = DGRAD ? taps - 1 - t : t;
-    const float* w = q == 0 ? w0 : q == 1 ? w1 : q == 2 ? w2 : w3;
-    float v = __ldg(w + ((int64_t)co * Ci + ci) * taps + tap);
-    if constexpr (sizeof(T) == 4) {
-      // the tensor core truncates fp32 operands to tf32; round the weights to nearest here so only the activation
-      // operand carries truncation bias (measured: halves the systematic error of the tf32 path)
-      uint32_t r32;
-      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r32) : "f"(v));
-      v = __uint_as_float(r32);
-    }
-    out[i] = from_f32<T>(v);
+__device__ __forceinline__ float round_operand(float v, int esz) {
+  if (esz == 4) {
+    // the tensor core truncates fp32 operands to tf32; round the weights to nearest here so only the activation
+    // operand carries truncation bias (measured: halves the systematic error of the tf32 path)
+    uint32_t r32;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r32) : "f"(v));
+    v = __uint_as_float(r32);
+  }
+  return v;
+}
+constexpr int PACK_SMEM_FLOATS = 8192;   // 32 KB staging tile
+
+// FWD: block = (q, co, ci chunk): reads chunk*taps contiguous floats, writes one contiguous ci-row per tap
+template <typename T>
+__global__ void __launch_bounds__(256) pack_weights_fwd_kernel(const float* __restrict__ w0, const float* __restrict__ w1,
+                                                               const float* __restrict__ w2, const float* __restrict__ w3,
+                                                               T* __restrict__ out, int Co, int Ci, int taps, int cchunk) {
+  __shared__ float tile[PACK_SMEM_FLOATS];
+  const int q = blockIdx.y / Co, co = blockIdx.y % Co;
+  const int ci0 = blockIdx.x * cchunk, nci = min(cchunk, Ci - ci0);
+  const float* w = (q == 0 ? w0 : q == 1 ? w1 : q == 2 ? w2 : w3) + ((int64_t)co * Ci + ci0) * taps;
+  for (int e = threadIdx.x; e < nci * taps; e += blockDim.x) tile[e] = __ldg(w + e);
+  __syncthreads();
+  for (int e = threadIdx.x; e < nci * taps; e += blockDim.x) {
+    const int tap = e / nci, ci = e - tap * nci;
+    out[(((int64_t)q * taps + tap) * Co + co) * Ci + ci0 + ci] = from_f32<T>(round_operand(tile[ci * taps + tap], sizeof(T)));
+  }
+}
+
+// DGRAD: block = (q, 32-wide co tile, ci tile): tile[co][ci*taps] in shared memory, output rows contiguous in co
+template <typename T>
+__global__ void __launch_bounds__(256) pack_weights_dgrad_kernel(const float* __restrict__ w0, const float* __restrict__ w1,
+                                                                 const float* __restrict__ w2, const float* __restrict__ w3,
+                                                                 T* __restrict__ out, int Co, int Ci, int taps, int tci) {
+  __shared__ float tile[PACK_SMEM_FLOATS];
+  const int q = blockIdx.z;
+  const int co0 = blockIdx.y * 32, nco = min(32, Co - co0);
+  const int ci0 = blockIdx.x * tci, nci = min(tci, Ci - ci0);
+  const float* w = q == 0 ? w0 : q == 1 ? w1 : q == 2 ? w2 : w3;
+  const int row = nci * taps;                       // contiguous floats per co
+  const int pitch = tci * taps + 1;                 // +1: the transposed reads below walk down a column
+  for (int e = threadIdx.x; e < nco * row; e += blockDim.x) {
+    const int co = e / row, r = e - co * row;
+    tile[co * pitch + r] = __ldg(w + ((int64_t)(co0 + co) * Ci + ci0) * taps + r);
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < nco * row; e += blockDim.x) {
+    const int co = e % nco;
+    const int r = e / nco;
+    const int ci = r % nci, t = r / nci;            // t: packed (flipped) tap index
+    out[(((int64_t)q * taps + t) * Ci + ci0 + ci) * Co + co0 + co] =
+        from_f32<T>(round_operand(tile[co * pitch + ci * taps + (taps - 1 - t)], sizeof(T)));
   }
 }
 
@@ -586,8 +616,10 @@ qconv_wgrad_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_const
   }
 }
 
-// Split-K fold.  Block = 32 consecutive outputs (ci fastest, so a warp reads 128 contiguous bytes of one split) x 8 split
-// lanes; each lane sums every 8th split, shared memory folds the 8 lanes in a fixed order (deterministic).
+// Split-K fold + transpose to the master layout.  Block = (q, co, ci chunk): for every tap it sums the splits of a
+// contiguous ci-row of the partials (SL split lanes per element when the row is short and the splits are many — narrow
+// layers), stages [ci][tap] in shared memory and writes the chunk*taps contiguous floats of dW_q[co].  Fixed summation
+// order: deterministic.
 //   separable: dW_q[co][ci][tap] = sum_split partial[split][q][tap][co][ci]
 //   dense    : partial[split][tap][p*Co + co][q*Ci + ci] holds sum_pix dY_p[co] x_q[ci]; the mixing matrix is applied
 //              here: dW_q[co][ci][tap] = sum_p M[p][q] sum_split partial[...]   (G = M^T dY never materialises)
@@ -595,54 +627,48 @@ template <bool DENSE>
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw0,
                                                            float* __restrict__ dw1, float* __restrict__ dw2,
                                                            float* __restrict__ dw3, int splits, int taps, int Co, int Ci,
-                                                           const Mix16 mix) {
-  __shared__ float red[8][33];
-  const int64_t per_q = (int64_t)taps * Co * Ci;
-  const int64_t total = 4 * per_q;
-  const int64_t split_stride = DENSE ? 16 * per_q : total;
-  const int ol = threadIdx.x & 31, sl = threadIdx.x >> 5;
-  const int64_t i = (int64_t)blockIdx.x * 32 + ol;
-  float s = 0.f;
-  int q = 0, ci = 0, co = 0, tap = 0;
-  if (i < total) {
-    q = (int)(i / per_q);
-    int64_t r = i - q * per_q;
-    ci = (int)(r % Ci);
-    r /= Ci;
-    co = (int)(r % Co);
-    tap = (int)(r / Co);
+                                                           int cchunk, int SL, const Mix16 mix) {
+  __shared__ float tile[PACK_SMEM_FLOATS];            // [SL][nci*taps] partial sums, folded into lane 0's slice
+  const int q = blockIdx.y / Co, co = blockIdx.y % Co;
+  const int ci0 = blockIdx.x * cchunk, nci = min(cchunk, Ci - ci0);
+  const int items = nci * taps;
+  const int64_t split_stride = (int64_t)(DENSE ? 16 : 4) * taps * Co * Ci;
+  for (int e = threadIdx.x; e < items * SL; e += blockDim.x) {
+    const int sl = e / items, it = e - sl * items;
+    const int tap = it / nci, ci = it - tap * nci;
+    float s = 0.f;
     if constexpr (DENSE) {
 #pragma unroll
       for (int pc = 0; pc < 4; ++pc) {
-        const float* src = partial + (((int64_t)tap * 4 * Co + pc * Co + co) * 4 * Ci + q * Ci + ci);
+        const float* src = partial + (((int64_t)tap * 4 * Co + pc * Co + co) * 4 * Ci + q * Ci + ci0 + ci);
         float t0 = 0.f, t1 = 0.f;
         int sp = sl;
-        for (; sp + 8 < splits; sp += 16) {
+        for (; sp + SL < splits; sp += 2 * SL) {
           t0 += __ldg(src + sp * split_stride);
-          t1 += __ldg(src + (sp + 8) * split_stride);
+          t1 += __ldg(src + (sp + SL) * split_stride);
         }
         if (sp < splits) t0 += __ldg(src + sp * split_stride);
         s += mix.m[pc * 4 + q] * (t0 + t1);
       }
     } else {
-      const float* src = partial + i;
+      const float* src = partial + ((((int64_t)q * taps + tap) * Co + co) * Ci + ci0 + ci);
       float t0 = 0.f, t1 = 0.f;
       int sp = sl;
-      for (; sp + 8 < splits; sp += 16) {
+      for (; sp + SL < splits; sp += 2 * SL) {
         t0 += __ldg(src + sp * split_stride);
-        t1 += __ldg(src + (sp + 8) * split_stride);
+        t1 += __ldg(src + (sp + SL) * split_stride);
       }
       if (sp < splits) t0 += __ldg(src + sp * split_stride);
       s = t0 + t1;
     }
+    tile[sl * items + ci * taps + tap] = s;
   }
-  red[sl][ol] = s;
   __syncthreads();
-  if (sl == 0 && i < total) {
-#pragma unroll
-    for (int g = 1; g < 8; ++g) s += red[g][ol];
-    float* dw = q == 0 ? dw0 : q == 1 ? dw1 : q == 2 ? dw2 : dw3;
-    dw[((int64_t)co * Ci + ci) * taps + tap] = s;
+  float* dw = (q == 0 ? dw0 : q == 1 ? dw1 : q == 2 ? dw2 : dw3) + ((int64_t)co * Ci + ci0) * taps;
+  for (int e = threadIdx.x; e < items; e += blockDim.x) {
+    float s = tile[e];
+    for (int g = 1; g < SL; ++g) s += tile[g * items + e];
+    dw[e] = s;
   }
 }
 
@@ -900,9 +926,19 @@ static int launch_igemm(const void* in, const void* wpacked, const float* bias, 
 template <typename T, bool DGRAD>
 static int pack_weights(const float* const w[4], void* out, const quan_conv_dims& d, cudaStream_t st) {
   const int taps = d.kH * d.kW;
-  const int64_t total = (int64_t)4 * d.Co * d.Ci * taps;
-  int grid = grid_for(total, 256, 4);
-  pack_weights_kernel<T, DGRAD><<<grid, 256, 0, st>>>(w[0], w[1], w[2], w[3], reinterpret_cast<T*>(out), d.Co, d.Ci, taps);
+  QUAN_REQUIRE(taps <= PACK_SMEM_FLOATS / 32 && d.Co <= 16383, QUAN_E_UNSUPPORTED, "tcgen05 conv: kernel %dx%d too large to pack", d.kH, d.kW);
+  if (DGRAD) {
+    int tci = PACK_SMEM_FLOATS / (32 * taps + 32);        // 32 co rows of tci*taps + 1 floats
+    if (tci > 32) tci = 32;
+    if (tci < 1) tci = 1;
+    dim3 grid((unsigned)((d.Ci + tci - 1) / tci), (unsigned)((d.Co + 31) / 32), 4);
+    pack_weights_dgrad_kernel<T><<<grid, 256, 0, st>>>(w[0], w[1], w[2], w[3], reinterpret_cast<T*>(out), d.Co, d.Ci, taps, tci);
+  } else {
+    int cchunk = PACK_SMEM_FLOATS / taps;
+    if (cchunk > d.Ci) cchunk = d.Ci;
+    dim3 grid((unsigned)((d.Ci + cchunk - 1) / cchunk), (unsigned)(4 * d.Co));
+    pack_weights_fwd_kernel<T><<<grid, 256, 0, st>>>(w[0], w[1], w[2], w[3], reinterpret_cast<T*>(out), d.Co, d.Ci, taps, cchunk);
+  }
   QUAN_CHECK_LAUNCH("pack_weights_kernel");
   return QUAN_OK;
 }
@@ -1107,12 +1143,20 @@ static int launch_wgrad(const void* gq, const void* x, float* const dw[4], const
   dim3 grid((unsigned)w.splits, (unsigned)(nq * w.tap_groups * w.co_blocks * w.ci_blocks));
   kern<<<grid, TC_THREADS, w.smem, st>>>(map_g, map_x, p);
   QUAN_CHECK_LAUNCH("qconv_wgrad_kernel");
-  const int64_t total = (int64_t)4 * p.taps * d.Co * d.Ci;
-  const unsigned rgrid = (unsigned)((total + 31) / 32);
-  if (dense)
-    wgrad_reduce_kernel<true><<<rgrid, 256, 0, st>>>(p.partial, dw[0], dw[1], dw[2], dw[3], w.splits, p.taps, d.Co, d.Ci, mix);
-  else
-    wgrad_reduce_kernel<false><<<rgrid, 256, 0, st>>>(p.partial, dw[0], dw[1], dw[2], dw[3], w.splits, p.taps, d.Co, d.Ci, mix);
+  {
+    int cchunk = PACK_SMEM_FLOATS / p.taps;
+    if (cchunk > d.Ci) cchunk = d.Ci;
+    // split lanes per element: short rows with many splits (narrow layers) spread the split loop over the idle threads
+    int SL = 256 / (cchunk * p.taps);
+    if (SL > 8) SL = 8;
+    if (SL > w.splits) SL = w.splits;
+    if (SL < 1) SL = 1;
+    dim3 rgrid((unsigned)((d.Ci + cchunk - 1) / cchunk), (unsigned)(4 * d.Co));
+    if (dense)
+      wgrad_reduce_kernel<true><<<rgrid, 256, 0, st>>>(p.partial, dw[0], dw[1], dw[2], dw[3], w.splits, p.taps, d.Co, d.Ci, cchunk, SL, mix);
+    else
+      wgrad_reduce_kernel<false><<<rgrid, 256, 0, st>>>(p.partial, dw[0], dw[1], dw[2], dw[3], w.splits, p.taps, d.Co, d.Ci, cchunk, SL, mix);
+  }
   QUAN_CHECK_LAUNCH("wgrad_reduce_kernel");
   return QUAN_OK;
 }

@@ -12,7 +12,7 @@ from typing import Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import (ACT_NONE, ACT_SILU, ALGO_AUTO, ALGO_DIRECT, ALGO_TCGEN05, BF16, F32, LAYOUT_BCHWQ, LAYOUT_BHWQC,
+from ._lib import (ACT_NONE, ACT_SILU, ALGO_AUTO, ALGO_DEPTHWISE, ALGO_DIRECT, ALGO_TCGEN05, BF16, F32, LAYOUT_BCHWQ, LAYOUT_BHWQC,
                    ConvDims, PtrArray4, check)
 
 # Mixing matrices of the reference
@@ -75,6 +75,8 @@ def _memory_format(layout: int):
 def as_layout(x: torch.Tensor, layout: Optional[int] = None) -> Tuple[torch.Tensor, int]:
     """Return (tensor, layout code) with the tensor dense in one of the two layouts (converting only if needed)."""
     cur = layout_of(x)
+    if cur is not None and layout is not None and x.size(1) == 1:
+        cur = layout          # one quaternion channel (the Poincare output): both layouts are the same bytes
     if cur is not None and (layout is None or cur == layout) and x.data_ptr() % 16 == 0:
         return x, cur
     target = layout if layout is not None else (cur if cur is not None else LAYOUT_BCHWQ)

@@ -85,6 +85,8 @@ def test_tc_is_what_auto_picks_for_the_sweep_shapes():
     assert ops.qconv2d_pick_algo((16, 64, 32, 32, 4), (64, 64, 3, 3), (1, 1), (1, 1), (1, 1), 1, torch.bfloat16,
                                  ops.LAYOUT_BCHWQ, 0) == ops.ALGO_DIRECT
     assert ops.qconv2d_pick_algo((16, 64, 32, 32, 4), (64, 1, 3, 3), (1, 1), (1, 1), (1, 1), 64, torch.bfloat16, L, 0) \
+        == ops.ALGO_DEPTHWISE
+    assert ops.qconv2d_pick_algo((16, 64, 32, 32, 4), (64, 2, 3, 3), (1, 1), (1, 1), (1, 1), 32, torch.bfloat16, L, 0) \
         == ops.ALGO_DIRECT
     assert ops.qconv2d_pick_algo((16, 2, 32, 32, 4), (4, 2, 3, 3), (1, 1), (1, 1), (1, 1), 1, torch.bfloat16, L, 0) \
         == ops.ALGO_DIRECT
@@ -100,3 +102,42 @@ def test_tc_linearity_at_sweep_size():
     args = ((1, 1), (1, 1), (1, 1), 1, ops.M_B)
     f = lambda t: ops.qconv2d_fwd(t, w, None, *args, ops.ALGO_TCGEN05, L)
     assert rel(f(a + 2 * b), f(a) + 2 * f(b)) <= 2e-3
+
+
+# name: (dtype, B, C, H, W, k, s, p, d, bias, mix)
+DW_CASES = [
+    ("bf16_c16", "bf16", 3, 16, 20, 24, 3, 1, 1, 1, False, "A"),
+    ("bf16_c64_bias", "bf16", 2, 64, 16, 16, 3, 1, 1, 1, True, "B"),
+    ("bf16_c12_s2", "bf16", 2, 12, 17, 15, 3, 2, 1, 1, False, "A"),
+    ("f32_c8_dil2", "f32", 2, 8, 14, 14, 3, 1, 2, 2, True, "A"),
+    ("f32_c6_k5", "f32", 2, 6, 12, 12, 5, 1, 2, 1, False, "B"),
+    ("bf16_c32_yolo", "bf16", 4, 32, 64, 64, 3, 1, 1, 1, False, "A"),
+]
+
+
+@pytest.mark.parametrize("case", DW_CASES, ids=[c[0] for c in DW_CASES])
+def test_depthwise_engine_matches_direct_engine(case):
+    """The streaming depthwise kernels (qconv_dw.cu; DWConv, conv.py:918-923) against the golden-validated generic engine."""
+    name, dt, B, Cq, H, W, k, s, p, d, bias, mix = case
+    dtype = torch.bfloat16 if dt == "bf16" else torch.float32
+    tol = 1e-2 if dtype == torch.bfloat16 else 2e-5      # both engines are true fp32 FMA: only summation order differs
+    torch.manual_seed(5)
+    x = torch.randn(B, Cq, H, W, 4, device=DEV).to(dtype).contiguous(memory_format=torch.channels_last_3d)
+    w = [torch.randn(Cq, 1, k, k, device=DEV) / k for _ in range(4)]
+    b = torch.randn(Cq, device=DEV) if bias else None
+    args = ((s, s), (p, p), (d, d), Cq, ops.MIX[mix])
+    picks = [ops.qconv2d_pick_algo(x.shape, w[0].shape, *args[:4], dtype, L, ps) for ps in range(3)]
+    assert picks[0] == ops.ALGO_DEPTHWISE and picks[1] == ops.ALGO_DEPTHWISE
+    assert picks[2] == (ops.ALGO_DEPTHWISE if k * k <= 9 else ops.ALGO_DIRECT)
+    y_ref = ops.qconv2d_fwd(x, w, b, *args, ops.ALGO_DIRECT, L)
+    y = ops.qconv2d_fwd(x, w, b, *args, ops.ALGO_AUTO, L)
+    assert rel(y, y_ref) <= tol
+    dy = torch.randn_like(y_ref)
+    dx_ref, dw_ref, db_ref = ops.qconv2d_bwd(dy, x, w, *args, True, True, bias, ops.ALGO_DIRECT)
+    dx, dw, db = ops.qconv2d_bwd(dy, x, w, *args, True, True, bias, ops.ALGO_AUTO)
+    # the generic engine rounds G = M^T dY to bf16 before using it; the depthwise kernels keep it in fp32
+    assert rel(dx, dx_ref) <= 2 * tol
+    for a, r in zip(dw, dw_ref):
+        assert rel(a, r) <= 2 * tol
+    if bias:
+        assert rel(db, db_ref) <= 1e-4
