@@ -182,6 +182,52 @@ def time_op(fn, iters, flush=None):
     return tot / iters
 
 
+def kernels_in_step(lib, step_fn, steps, a, dtype, peaks):
+    """Device time of every library kernel inside the training step itself: the library brackets each launch with a
+    CUDA-event pair on its own stream (quan_kernel_timing_*), over `steps` extra steps run right after the timed region
+    (same clocks / power state).  Peaks here are the SUSTAINED figures: these kernels run inside a long step."""
+    import ctypes
+    lib.quan_kernel_timing_enable(1)
+    for _ in range(steps):
+        step_fn()
+    torch.cuda.synchronize()
+    lib.quan_kernel_timing_enable(0)
+    n = lib.quan_kernel_timing_report(None, 0)
+    buf = ctypes.create_string_buffer(n + 16)
+    lib.quan_kernel_timing_report(buf, n + 16)
+    S = a.n * a.cq * a.hw * a.hw * 4 * (2 if dtype == torch.bfloat16 else 4)
+    conv_flops = 4 * 2 * a.n * a.hw * a.hw * a.cq * a.cq * 9
+    tpeak = peaks["bf16_tflops_sustained"] * (1.0 if dtype == torch.bfloat16 else 0.5)
+    # algorithmic work per launch (SURVEY §8(d)): separable conv FLOPs; bytes of the streams a kernel must touch
+    work = {"qconv_igemm_fwd": ("tensor", conv_flops), "qconv_igemm_dgrad": ("tensor", conv_flops),
+            "qconv_wgrad_kernel": ("tensor", conv_flops), "iqbn_reduce_fwd": ("hbm", S), "iqbn_apply_fwd": ("hbm", 2 * S),
+            "iqbn_reduce_bwd": ("hbm", 2 * S), "iqbn_apply_bwd": ("hbm", 3 * S), "mix": ("hbm", 2 * S)}
+    rows = {}
+    for ln in buf.value.decode().splitlines():
+        name, cnt, total = ln.split()
+        cnt, total = int(cnt), float(total)
+        if cnt == 0:
+            continue
+        r = {"launches_per_step": cnt / steps, "ms_per_launch": total / cnt, "ms_per_step": total / steps}
+        if name in work:
+            kind, wk = work[name]
+            if kind == "tensor":
+                ach = wk / (total / cnt) / 1e9
+                r.update({"bound": "tensor", "achieved": ach, "peak": tpeak, "unit": "TFLOP/s", "frac": ach / tpeak})
+            else:
+                ach = wk / (total / cnt) / 1e6
+                r.update({"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"]})
+        rows[name] = r
+    return rows
+
+
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the bench-shape kernels, from the committed
+    `ncu --set full` captures (profiles/r01_ncu_traffic.json); None when a kernel has no capture."""
+    p = ROOT / "profiles" / "r01_ncu_traffic.json"
+    return json.loads(p.read_text()) if p.exists() else {}
+
+
 def kernel_table(a, dev, dtype, peaks):
     """Per-op device times for one block of the stack, each timed alone with the L2 flushed between launches."""
     import quan_ultralytics_b200 as Q
@@ -419,11 +465,36 @@ def main():
         y.backward(dy_dev)
         opt.step()
 
+    # e2e leg: every step copies ITS input batch from pinned host memory and reads its result back.  The copies run on
+    # a side stream into two staging buffers, so the H2D of step i+1 overlaps the compute of step i (what any input
+    # pipeline does); every byte still moves inside the timed region, including the first batch.
+    copy_stream = torch.cuda.Stream(device=dev)
+    x_stage2 = [x_stage, torch.empty_like(x_stage, memory_format=torch.preserve_format)]
+    copied = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+    e2e_state = {"i": 0, "primed": False}
+
+    def prefetch(slot):
+        copy_stream.wait_event(consumed[slot])            # the step that last read this buffer has finished
+        with torch.cuda.stream(copy_stream):
+            x_stage2[slot].copy_(x_host, non_blocking=True)
+            copied[slot].record(copy_stream)
+
     def e2e_step():
-        x_stage.copy_(x_host, non_blocking=True)          # H2D of this step's inputs
-        step(x_stage)
+        i = e2e_state["i"]
+        cur = i & 1
+        if not e2e_state["primed"]:
+            consumed[0].record()
+            consumed[1].record()
+            prefetch(cur)                                  # H2D of this step's inputs (first step: not overlapped)
+            e2e_state["primed"] = True
+        prefetch(cur ^ 1)                                  # next step's inputs, overlapping this step's compute
+        torch.cuda.current_stream().wait_event(copied[cur])
+        step(x_stage2[cur])
+        consumed[cur].record()
         g_host.copy_(net[0].conv.weight_r.grad, non_blocking=True)   # D2H of the step's result
         torch.cuda.current_stream().synchronize()
+        e2e_state["i"] = i + 1
 
     def barrier():
         if world > 1:
@@ -454,6 +525,8 @@ def main():
     launches = lib.quan_launch_count() - n0
     for _ in range(2):
         e2e_step()
+    torch.cuda.synchronize()
+    e2e_state["primed"] = False                            # the timed region starts with nothing staged
     ms_e2e = timed(e2e_step, a.steps)
     clocks = sampler.stop() if rank == 0 else None
 
@@ -478,14 +551,19 @@ def main():
             "step_tflops": flops_per_image(a) * a.n * world / (ms / a.steps) / 1e9,
         }
         if not a.no_kernel_table:
-            table = kernel_table(a, dev, dtype, peaks)
-            # dominant kernel = largest share of one block's step
-            dom = max(table, key=lambda k: table[k]["ms"])
-            r = dict(table[dom])
-            r.update({"kernel": dom, "peak_src": peaks["src"], "traffic": None,
-                      "share_of_block": r["ms"] / sum(v["ms"] for v in table.values())})
+            # (1) every library kernel timed inside the training step; the dominant one carries the roofline
+            ks = kernels_in_step(lib, lambda: step(x_dev), a.steps, a, dtype, peaks)
+            step_ms = sum(v["ms_per_step"] for v in ks.values())
+            dom = max((k for k in ks if "frac" in ks[k]), key=lambda k: ks[k]["ms_per_step"])
+            r = {k: ks[dom][k] for k in ("bound", "achieved", "peak", "unit", "frac")}
+            tr = ncu_traffic().get(dom)
+            r.update({"kernel": dom, "peak_src": peaks["src"] + (" (sustained: kernel timed inside the step)" if r["bound"] == "tensor" else ""),
+                      "traffic": tr, "ms_per_launch": ks[dom]["ms_per_launch"],
+                      "share_of_step_kernel_time": ks[dom]["ms_per_step"] / step_ms})
             line["roofline"] = r
-            line["kernels"] = table
+            line["kernels_in_step"] = ks
+            # (2) each op of one block timed ALONE (L2 swept between launches), against the burst peak
+            line["ops_isolated"] = kernel_table(a, dev, dtype, peaks)
         if world == 1 and not a.no_cpu_baseline:
             ips, sec, cores = run_cpu_port(a, a.cpu_n, a.cpu_steps, 1)
             line["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",

@@ -171,6 +171,13 @@ int quan_qconv2d_bwd(const void* dy, const void* x, const float* const w[4], voi
 /* reports which engine AUTO would pick for this shape: QUAN_ALGO_DIRECT, QUAN_ALGO_TCGEN05 or QUAN_ALGO_DEPTHWISE */
 int quan_qconv2d_pick_algo(const quan_conv_dims* d, int dtype, int layout, int pass /*0 fwd,1 dgrad,2 wgrad*/);
 
+/* Optional per-kernel device timing for benchmarks (no reference counterpart): while enabled, every kernel the library
+ * launches outside stream capture is bracketed by a CUDA-event pair on its own stream.  `enable(1)` clears earlier
+ * records.  `report` synchronises the recorded events and writes one "kernel_name launches total_ms" line per kernel
+ * into buf (NUL-terminated, truncated to cap); returns the bytes a complete report needs. */
+int quan_kernel_timing_enable(int on);
+size_t quan_kernel_timing_report(char* buf, size_t cap);
+
 #ifdef __cplusplus
 }
 #endif

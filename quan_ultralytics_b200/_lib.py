@@ -35,6 +35,8 @@ PROTOTYPES = {
     "quan_last_error": (C.c_char_p, []),
     "quan_build_info": (C.c_char_p, []),
     "quan_launch_count": (C.c_uint64, []),
+    "quan_kernel_timing_enable": (_int, [_int]),
+    "quan_kernel_timing_report": (_sz, [C.c_char_p, _sz]),
     "quan_poincare_fwd": (_int, [_vp, _vp, _i32, _i32, _i32, _int, _vp]),
     "quan_poincare_bwd": (_int, [_vp, _vp, _vp, _i32, _i32, _i32, _int, _vp]),
     "quan_iqbn_workspace_bytes": (_sz, [_i32]),

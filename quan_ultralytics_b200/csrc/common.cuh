@@ -27,8 +27,14 @@ void set_error(const char* fmt, ...);   // defined in api.cu (thread-local buffe
 // Always check the launch (the reference never does: quaternion_ops.cu:777-799).
 void count_launch();                    // defined in api.cu (process-wide atomic counter)
 
+// optional per-kernel timing (api.cu): QUAN_TIMED(st) before a launch, QUAN_CHECK_LAUNCH(name) after it
+void timing_begin(cudaStream_t st);
+void timing_end(const char* name);
+#define QUAN_TIMED(st) ::quan::timing_begin(st)
+
 #define QUAN_CHECK_LAUNCH(name)                                                     \
   do {                                                                              \
+    ::quan::timing_end(name);                                                       \
     ::quan::count_launch();                                                         \
     cudaError_t e__ = cudaGetLastError();                                           \
     if (e__ != cudaSuccess) {                                                       \

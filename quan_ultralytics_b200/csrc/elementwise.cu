@@ -213,6 +213,7 @@ int quan_poincare_fwd(const float* rgb, void* out, int32_t B, int32_t H, int32_t
   const int64_t HW = (int64_t)H * W, total = HW * B;
   int grid = grid_for(total, 256, 8);
   cudaStream_t st = (cudaStream_t)stream;
+  QUAN_TIMED(st);
   if (out_dtype == QUAN_F32) poincare_fwd_kernel<float><<<grid, 256, 0, st>>>(rgb, (float*)out, HW, total);
   else poincare_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(rgb, (__nv_bfloat16*)out, HW, total);
   QUAN_CHECK_LAUNCH("poincare_fwd");
@@ -262,6 +263,7 @@ int quan_mix(const void* in, void* out, int32_t B, int32_t C, int32_t H, int32_t
   QUAN_REQUIRE(mix != nullptr, QUAN_E_ARG, "mix: null matrix");
   Mix16 M = make_mix(mix);
   cudaStream_t st = (cudaStream_t)stream;
+  QUAN_TIMED(st);
   const int64_t rows = (int64_t)B * H * W;
   if (layout == QUAN_LAYOUT_BCHWQ || C == 1) {
     const int64_t nquat = rows * C;
@@ -297,6 +299,7 @@ int quan_layout_convert(const void* src, int src_layout, void* dst, int dst_layo
   QUAN_REQUIRE(dst_layout == QUAN_LAYOUT_BCHWQ || dst_layout == QUAN_LAYOUT_BHWQC, QUAN_E_ARG, "layout_convert: bad dst layout");
   QUAN_REQUIRE(src != dst, QUAN_E_ARG, "layout_convert: in-place conversion is not supported");
   cudaStream_t st = (cudaStream_t)stream;
+  QUAN_TIMED(st);
   const size_t esz = dtype == QUAN_F32 ? 4 : 2;
   const int HW = H * W;
   if (src_layout == dst_layout || C == 1) {

@@ -714,6 +714,7 @@ static int launch_reduce(const void* x, const void* dy, int B, int C, int H, int
     if (p.grid.x > (unsigned)IQBN_MAX_PARTS) p.grid.x = IQBN_MAX_PARTS;
     nparts = (int)p.grid.x;
     bool fused = false;
+    QUAN_TIMED(st);
 #define QUAN_REDUCE_B(UU) QUAN_DISPATCH_V(p.V, { int rc_ = launch_reduce_b<T, (sizeof(T) == 4 && kV == 8) ? 4 : kV, MODE, ACT, UU>( \
                           p.grid, p.block, st, xp, dyp, p.g, gamma, beta, ws, tail, &fused); if (rc_) return rc_; })
     switch (U) {
@@ -735,7 +736,8 @@ static int launch_reduce(const void* x, const void* dy, int B, int C, int H, int
       iqbn_reduce_a<T, 4, MODE, ACT><<<p.grid, p.block, 0, st>>>(xp, dyp, p.g, gamma, beta, ws, tail);
     }
   }
-  QUAN_CHECK_LAUNCH("iqbn_reduce");
+  QUAN_CHECK_LAUNCH(MODE == 0 ? "iqbn_reduce_fwd" : "iqbn_reduce_bwd");
+  QUAN_TIMED(st);
   iqbn_fold_kernel<<<(4 * C + 7) / 8, 256, 0, st>>>(ws.part, nparts, tail);
   QUAN_CHECK_LAUNCH("iqbn_fold");
   return QUAN_OK;
@@ -755,6 +757,7 @@ static int launch_apply(const void* x, const void* dy, void* out, int B, int C, 
       set_error("iqbn: C=%d too large for the BHWQC kernels", C);
       return QUAN_E_UNSUPPORTED;
     }
+    QUAN_TIMED(st);
 #define QUAN_APPLY_B(UU) QUAN_DISPATCH_V(p.V, (iqbn_apply_b<T, (sizeof(T) == 4 && kV == 8) ? 4 : kV, ACT, BWD, UU> \
                           <<<p.grid, p.block, 0, st>>>(xp, dyp, op, p.g, a)))
     switch (U) {
@@ -763,7 +766,7 @@ static int launch_apply(const void* x, const void* dy, void* out, int B, int C, 
       default: QUAN_APPLY_B(4); break;
     }
 #undef QUAN_APPLY_B
-    QUAN_CHECK_LAUNCH("iqbn_apply_b");
+    QUAN_CHECK_LAUNCH(BWD ? "iqbn_apply_bwd" : "iqbn_apply_fwd");
     if (BWD && mix_t != nullptr) {  // G = M^T dY for the producing QConv2D: second in-place pass in this layout
       int rc = quan_mix(out, out, B, C, H, W, sizeof(T) == 4 ? QUAN_F32 : QUAN_BF16, layout, mix_t, st);
       if (rc) return rc;

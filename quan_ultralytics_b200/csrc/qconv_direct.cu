@@ -313,6 +313,7 @@ static int fwd_direct_t(const void* x, const float* const w[4], const float* bia
   QUAN_REQUIRE((int64_t)g.groups * chunks <= 65535, QUAN_E_UNSUPPORTED, "qconv direct fwd: too many channel chunks");
   dim3 grid((unsigned)ceil_div64(npix, 128), (unsigned)(g.groups * chunks));
   W4 w4 = {{w[0], w[1], w[2], w[3]}};
+  QUAN_TIMED(st);
   const T* xp = (const T*)x;
   T* yp = (T*)y;
   switch (cot) {
@@ -339,6 +340,7 @@ static int dgrad_direct_t(const void* gq, const float* const w[4], void* dx, con
   QUAN_REQUIRE((int64_t)g.groups * chunks <= 65535, QUAN_E_UNSUPPORTED, "qconv direct dgrad: too many channel chunks");
   dim3 grid((unsigned)ceil_div64(npix, 128), (unsigned)(g.groups * chunks));
   W4 w4 = {{w[0], w[1], w[2], w[3]}};
+  QUAN_TIMED(st);
   const T* gp = (const T*)gq;
   T* dp = (T*)dx;
   switch (cit) {
@@ -367,6 +369,7 @@ static int wgrad_direct_t(const void* gq, const void* x, float* const dw[4], con
   const int64_t pps = ceil_div64(npix, splits);
   splits = ceil_div64(npix, pps);
   dim3 grid((unsigned)eblocks, (unsigned)splits);
+  QUAN_TIMED(st);
   qconv_wgrad_direct<T, LAYOUT><<<grid, 128, 0, st>>>((const T*)gq, (const T*)x, dw[0], dw[1], dw[2], dw[3], g, pps);
   QUAN_CHECK_LAUNCH("qconv_wgrad_direct");
   return QUAN_OK;

@@ -205,6 +205,7 @@ static int dw_launch_t(const void* in, const float* const w[4], const float* bia
   const size_t smem = (size_t)g.kH * g.kW * 4 * g.C * sizeof(float);
   const int64_t opix = (int64_t)g.B * (TRANSPOSED ? g.H * g.W : g.Ho * g.Wo);
   W4p w4 = {{w[0], w[1], w[2], w[3]}};
+  QUAN_TIMED(st);
   if (g.C % VMAX == 0) {
     const int grid = grid_for(opix * (g.C / VMAX), 256, 8);
     qconv_dw_kernel<T, VMAX, TRANSPOSED><<<grid, 256, smem, st>>>((const T*)in, w4, bias_r, (T*)out, g, M);
@@ -212,7 +213,7 @@ static int dw_launch_t(const void* in, const float* const w[4], const float* bia
     const int grid = grid_for(opix * (g.C / (VMAX / 2)), 256, 8);
     qconv_dw_kernel<T, VMAX / 2, TRANSPOSED><<<grid, 256, smem, st>>>((const T*)in, w4, bias_r, (T*)out, g, M);
   }
-  QUAN_CHECK_LAUNCH("qconv_dw_kernel");
+  QUAN_CHECK_LAUNCH(TRANSPOSED ? "qconv_dw_dgrad" : "qconv_dw_fwd");
   return QUAN_OK;
 }
 
@@ -244,6 +245,7 @@ int qconv_dw_wgrad(const void* dy, const void* x, float* const dw[4], const quan
   int64_t blocks = ceil_div64(npix, (int64_t)ppb * 16);          // >= 16 pixels per pixel lane
   if (blocks > QUAN_NUM_SMS * 4) blocks = QUAN_NUM_SMS * 4;
   if (blocks < 1) blocks = 1;
+  QUAN_TIMED(st);
   if (dtype == QUAN_BF16)
     qconv_dw_wgrad_kernel<__nv_bfloat16, 9><<<(unsigned)blocks, 256, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x,
                                                                                dw[0], dw[1], dw[2], dw[3], g, M);

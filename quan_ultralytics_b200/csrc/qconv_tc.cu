@@ -92,8 +92,10 @@ __global__ void __launch_bounds__(256) pack_weights_fwd_kernel(const float* __re
   const int q = blockIdx.y / Co, co = blockIdx.y % Co;
   const int ci0 = blockIdx.x * cchunk, nci = min(cchunk, Ci - ci0);
   const float* w = (q == 0 ? w0 : q == 1 ? w1 : q == 2 ? w2 : w3) + ((int64_t)co * Ci + ci0) * taps;
+#pragma unroll 8
   for (int e = threadIdx.x; e < nci * taps; e += blockDim.x) tile[e] = __ldg(w + e);
   __syncthreads();
+#pragma unroll 4
   for (int e = threadIdx.x; e < nci * taps; e += blockDim.x) {
     const int tap = e / nci, ci = e - tap * nci;
     out[(((int64_t)q * taps + tap) * Co + co) * Ci + ci0 + ci] = from_f32<T>(round_operand(tile[ci * taps + tap], sizeof(T)));
@@ -112,11 +114,13 @@ __global__ void __launch_bounds__(256) pack_weights_dgrad_kernel(const float* __
   const float* w = q == 0 ? w0 : q == 1 ? w1 : q == 2 ? w2 : w3;
   const int row = nci * taps;                       // contiguous floats per co
   const int pitch = tci * taps + 1;                 // +1: the transposed reads below walk down a column
+#pragma unroll 8
   for (int e = threadIdx.x; e < nco * row; e += blockDim.x) {
     const int co = e / row, r = e - co * row;
     tile[co * pitch + r] = __ldg(w + ((int64_t)(co0 + co) * Ci + ci0) * taps + r);
   }
   __syncthreads();
+#pragma unroll 4
   for (int e = threadIdx.x; e < nco * row; e += blockDim.x) {
     const int co = e % nco;
     const int r = e / nco;
@@ -633,6 +637,7 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
   const int ci0 = blockIdx.x * cchunk, nci = min(cchunk, Ci - ci0);
   const int items = nci * taps;
   const int64_t split_stride = (int64_t)(DENSE ? 16 : 4) * taps * Co * Ci;
+#pragma unroll 2
   for (int e = threadIdx.x; e < items * SL; e += blockDim.x) {
     const int sl = e / items, it = e - sl * items;
     const int tap = it / nci, ci = it - tap * nci;
@@ -746,6 +751,7 @@ static bool plan_tiles(int B, int Ho, int Wo, int sH, int sW, TilePlan& t) {
 // scat > 1: stride-`scat` dgrad — (sH,sW) are 1, the output grid is visited in scat*scat parity classes (TapTable)
 struct IgemmShape {
   int B, Hi, Wi, K, Ho, Wo, N, kH, kW, sH, sW, pH, pW, dH, dW, nq, scatH, scatW;
+  const char* name;   // kernel label for the launch log / timing table
 };
 static bool build_taps(const IgemmShape& s, TapTable& t) {
   if (s.kH * s.kW > TC_MAX_TAPS || s.scatH * s.scatW > 4) return false;
@@ -803,7 +809,7 @@ static bool igemm_supported(const IgemmShape& s, int dtype) {
 
 template <typename T, bool MIX, int CG, int KSTEPS, int NQ>
 static int launch_igemm_inst(const CUtensorMap& map_a, const CUtensorMap& map_b, void* out, const TcConvParams& p, size_t smem,
-                             cudaStream_t st) {
+                             const char* name, cudaStream_t st) {
   auto kern = qconv_igemm_kernel<T, MIX, CG, KSTEPS, NQ>;
   // persistent grid: one CTA (pair) per SM, as many as can be co-resident (queried once per instantiation)
   static thread_local int max_groups = 0;
@@ -835,8 +841,9 @@ static int launch_igemm_inst(const CUtensorMap& map_a, const CUtensorMap& map_b,
   }
   const int groups = p.units < max_groups ? p.units : max_groups;
   cfg.gridDim = dim3((unsigned)(groups * CG));
+  QUAN_TIMED(st);
   QUAN_CUDA(cudaLaunchKernelEx(&cfg, kern, map_a, map_b, reinterpret_cast<T*>(out), p));
-  QUAN_CHECK_LAUNCH("qconv_igemm_kernel");
+  QUAN_CHECK_LAUNCH(name);
   return QUAN_OK;
 }
 
@@ -911,7 +918,7 @@ static int launch_igemm(const void* in, const void* wpacked, const float* bias, 
     int rc = encode_map(&map_b, dtype, 4, wpacked, dims, str, box, est, row_bytes);
     if (rc) return rc;
   }
-#define QUAN_IGEMM_CASE(CGV, KS) return launch_igemm_inst<T, MIX, CGV, KS, NQ>(map_a, map_b, out, p, smem, st)
+#define QUAN_IGEMM_CASE(CGV, KS) return launch_igemm_inst<T, MIX, CGV, KS, NQ>(map_a, map_b, out, p, smem, s.name, st)
   if (cg == 2) {
     if (ksteps == 4) { QUAN_IGEMM_CASE(2, 4); }
     if (ksteps == 2) { QUAN_IGEMM_CASE(2, 2); }
@@ -929,14 +936,16 @@ static int pack_weights(const float* const w[4], void* out, const quan_conv_dims
   QUAN_REQUIRE(taps <= PACK_SMEM_FLOATS / 32 && d.Co <= 16383, QUAN_E_UNSUPPORTED, "tcgen05 conv: kernel %dx%d too large to pack", d.kH, d.kW);
   if (DGRAD) {
     int tci = PACK_SMEM_FLOATS / (32 * taps + 32);        // 32 co rows of tci*taps + 1 floats
-    if (tci > 32) tci = 32;
+    if (tci > 8) tci = 8;                                 // ~2.3 K elements per block: many blocks, few serial steps
     if (tci < 1) tci = 1;
     dim3 grid((unsigned)((d.Ci + tci - 1) / tci), (unsigned)((d.Co + 31) / 32), 4);
+    QUAN_TIMED(st);
     pack_weights_dgrad_kernel<T><<<grid, 256, 0, st>>>(w[0], w[1], w[2], w[3], reinterpret_cast<T*>(out), d.Co, d.Ci, taps, tci);
   } else {
     int cchunk = PACK_SMEM_FLOATS / taps;
     if (cchunk > d.Ci) cchunk = d.Ci;
     dim3 grid((unsigned)((d.Ci + cchunk - 1) / cchunk), (unsigned)(4 * d.Co));
+    QUAN_TIMED(st);
     pack_weights_fwd_kernel<T><<<grid, 256, 0, st>>>(w[0], w[1], w[2], w[3], reinterpret_cast<T*>(out), d.Co, d.Ci, taps, cchunk);
   }
   QUAN_CHECK_LAUNCH("pack_weights_kernel");
@@ -948,6 +957,7 @@ static int pack_weights_dense(const float* const w[4], const float* bias_r, void
   const int taps = d.kH * d.kW;
   const int64_t total = (int64_t)16 * d.Co * d.Ci * taps;
   int grid = grid_for(total, 256, 4);
+  QUAN_TIMED(st);
   pack_weights_dense_kernel<T, DGRAD><<<grid, 256, 0, st>>>(w[0], w[1], w[2], w[3], bias_r, reinterpret_cast<T*>(out), bias_out,
                                                             d.Co, d.Ci, taps, mix);
   QUAN_CHECK_LAUNCH("pack_weights_dense_kernel");
@@ -965,6 +975,7 @@ static IgemmShape fwd_shape(const quan_conv_dims& d, int dense) {
   s.kH = d.kH; s.kW = d.kW; s.sH = d.sH; s.sW = d.sW; s.pH = d.pH; s.pW = d.pW; s.dH = d.dH; s.dW = d.dW;
   s.nq = dense ? 1 : 4;
   s.scatH = s.scatW = 1;
+  s.name = dense ? "qconv_igemm_fwd_dense" : "qconv_igemm_fwd";
   return s;
 }
 // stride-1 dgrad as a forward conv of G (Co channels, Ho x Wo) with flipped kernels and padding d*(k-1)-p;
@@ -982,6 +993,7 @@ static IgemmShape dgrad_shape(const quan_conv_dims& d, int dense) {
   s.scatH = d.sH; s.scatW = d.sW;
   if (d.sH == 1 && d.sW == 1) { s.pH = d.dH * (d.kH - 1) - d.pH; s.pW = d.dW * (d.kW - 1) - d.pW; }
   else { s.pH = d.pH; s.pW = d.pW; }
+  s.name = dense ? "qconv_igemm_dgrad_dense" : "qconv_igemm_dgrad";
   return s;
 }
 
@@ -1141,8 +1153,9 @@ static int launch_wgrad(const void* gq, const void* x, float* const dw[4], const
     attr_set = true;
   }
   dim3 grid((unsigned)w.splits, (unsigned)(nq * w.tap_groups * w.co_blocks * w.ci_blocks));
+  QUAN_TIMED(st);
   kern<<<grid, TC_THREADS, w.smem, st>>>(map_g, map_x, p);
-  QUAN_CHECK_LAUNCH("qconv_wgrad_kernel");
+  QUAN_CHECK_LAUNCH(dense ? "qconv_wgrad_kernel_dense" : "qconv_wgrad_kernel");
   {
     int cchunk = PACK_SMEM_FLOATS / p.taps;
     if (cchunk > d.Ci) cchunk = d.Ci;
@@ -1152,6 +1165,7 @@ static int launch_wgrad(const void* gq, const void* x, float* const dw[4], const
     if (SL > w.splits) SL = w.splits;
     if (SL < 1) SL = 1;
     dim3 rgrid((unsigned)((d.Ci + cchunk - 1) / cchunk), (unsigned)(4 * d.Co));
+    QUAN_TIMED(st);
     if (dense)
       wgrad_reduce_kernel<true><<<rgrid, 256, 0, st>>>(p.partial, dw[0], dw[1], dw[2], dw[3], w.splits, p.taps, d.Co, d.Ci, cchunk, SL, mix);
     else
