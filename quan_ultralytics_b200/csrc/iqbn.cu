@@ -164,6 +164,7 @@ struct GeomB {
   int C;
   int cvpg;       // column vectors per group (per block row)
   int rpb;        // row lanes per block
+  int rev;        // 1: visit the rows last-to-first (reductions: the producer's most recent rows are still in L2)
 };
 
 // V consecutive fp32 coefficients (V <= 8) as 16-byte loads where alignment allows
@@ -219,11 +220,15 @@ __global__ void __launch_bounds__(IQBN_RED_THREADS, 2) iqbn_reduce_b(const T* __
   const int64_t rs = (int64_t)gridDim.x * g.rpb;                // rows between two visits of this thread
   int64_t r = (int64_t)blockIdx.x * g.rpb + rl;
   const bool lane_on = rl < g.rpb;
+  // Reductions walk the tensor back to front: the kernel that produced it (conv epilogue, the next layer's dgrad) wrote
+  // front to back, so its last ~100 MB are still in the 126 MB L2, and the apply kernel that follows walks front to back
+  // again over what this kernel touched last.
+  auto rowi = [&](int64_t rr) { return g.rev ? g.R - 1 - rr : rr; };
   int cnt = 0;
   if (lane_on && r < g.R) {
     cnt = (int)((g.R - 1 - r) / rs) + 1;
     if constexpr (MODE == 0) {                                  // local shift: keeps fp32 partials well conditioned
-      const VecT t = xr[r * rsv];
+      const VecT t = xr[rowi(r) * rsv];
 #pragma unroll
       for (int i = 0; i < V; ++i) k[i] = to_f32(t.v[i]);
     }
@@ -249,15 +254,15 @@ __global__ void __launch_bounds__(IQBN_RED_THREADS, 2) iqbn_reduce_b(const T* __
       VecT xa[U], ga[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        xa[u] = xr[(r + u * rs) * rsv];
-        if constexpr (MODE == 1) ga[u] = gr[(r + u * rs) * rsv];
+        xa[u] = xr[rowi(r + u * rs) * rsv];
+        if constexpr (MODE == 1) ga[u] = gr[rowi(r + u * rs) * rsv];
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) accumulate(xa[u], ga[u]);
     }
     for (; r < g.R; r += rs) {
-      VecT xa = xr[r * rsv], ga;
-      if constexpr (MODE == 1) ga = gr[r * rsv];
+      VecT xa = xr[rowi(r) * rsv], ga;
+      if constexpr (MODE == 1) ga = gr[rowi(r) * rsv];
       accumulate(xa, ga);
     }
   }
@@ -625,6 +630,7 @@ static bool plan_b(int B, int C, int H, int W, int unroll, int blocks_per_sm, in
   p.g.C = C;
   p.g.cvpg = cvpg;
   p.g.rpb = rpb;
+  p.g.rev = 0;
   p.block = dim3(rpb * cvpg);
   int64_t want = ceil_div64(p.g.R, (int64_t)rpb * unroll);
   int64_t cap = ceil_div64((int64_t)QUAN_NUM_SMS * blocks_per_sm, cg);
@@ -713,6 +719,7 @@ static int launch_reduce(const void* x, const void* dy, int B, int C, int H, int
     }
     if (p.grid.x > (unsigned)IQBN_MAX_PARTS) p.grid.x = IQBN_MAX_PARTS;
     nparts = (int)p.grid.x;
+    p.g.rev = env_int("QUAN_IQBN_REV", 1);
     bool fused = false;
     QUAN_TIMED(st);
 #define QUAN_REDUCE_B(UU) QUAN_DISPATCH_V(p.V, { int rc_ = launch_reduce_b<T, (sizeof(T) == 4 && kV == 8) ? 4 : kV, MODE, ACT, UU>( \

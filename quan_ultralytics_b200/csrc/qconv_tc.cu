@@ -81,14 +81,15 @@ __device__ __forceinline__ float round_operand(float v, int esz) {
   }
   return v;
 }
-constexpr int PACK_SMEM_FLOATS = 8192;   // 32 KB staging tile
+constexpr int PACK_SMEM_FLOATS = 8192;   // staging tile upper bound (32 KB); kernels get dynamic smem sized to their tile:
+                                         // a 32 KB static array let only ~3 blocks share an SM under the default carveout
 
 // FWD: block = (q, co, ci chunk): reads chunk*taps contiguous floats, writes one contiguous ci-row per tap
 template <typename T>
 __global__ void __launch_bounds__(256) pack_weights_fwd_kernel(const float* __restrict__ w0, const float* __restrict__ w1,
                                                                const float* __restrict__ w2, const float* __restrict__ w3,
                                                                T* __restrict__ out, int Co, int Ci, int taps, int cchunk) {
-  __shared__ float tile[PACK_SMEM_FLOATS];
+  extern __shared__ float tile[];
   const int q = blockIdx.y / Co, co = blockIdx.y % Co;
   const int ci0 = blockIdx.x * cchunk, nci = min(cchunk, Ci - ci0);
   const float* w = (q == 0 ? w0 : q == 1 ? w1 : q == 2 ? w2 : w3) + ((int64_t)co * Ci + ci0) * taps;
@@ -107,7 +108,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) pack_weights_dgrad_kernel(const float* __restrict__ w0, const float* __restrict__ w1,
                                                                  const float* __restrict__ w2, const float* __restrict__ w3,
                                                                  T* __restrict__ out, int Co, int Ci, int taps, int tci) {
-  __shared__ float tile[PACK_SMEM_FLOATS];
+  extern __shared__ float tile[];
   const int q = blockIdx.z;
   const int co0 = blockIdx.y * 32, nco = min(32, Co - co0);
   const int ci0 = blockIdx.x * tci, nci = min(tci, Ci - ci0);
@@ -632,7 +633,7 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
                                                            float* __restrict__ dw1, float* __restrict__ dw2,
                                                            float* __restrict__ dw3, int splits, int taps, int Co, int Ci,
                                                            int cchunk, int SL, const Mix16 mix) {
-  __shared__ float tile[PACK_SMEM_FLOATS];            // [SL][nci*taps] partial sums, folded into lane 0's slice
+  extern __shared__ float tile[];                     // [SL][nci*taps] partial sums, folded into lane 0's slice
   const int q = blockIdx.y / Co, co = blockIdx.y % Co;
   const int ci0 = blockIdx.x * cchunk, nci = min(cchunk, Ci - ci0);
   const int items = nci * taps;
@@ -940,13 +941,14 @@ static int pack_weights(const float* const w[4], void* out, const quan_conv_dims
     if (tci < 1) tci = 1;
     dim3 grid((unsigned)((d.Ci + tci - 1) / tci), (unsigned)((d.Co + 31) / 32), 4);
     QUAN_TIMED(st);
-    pack_weights_dgrad_kernel<T><<<grid, 256, 0, st>>>(w[0], w[1], w[2], w[3], reinterpret_cast<T*>(out), d.Co, d.Ci, taps, tci);
+    pack_weights_dgrad_kernel<T><<<grid, 256, (size_t)32 * (tci * taps + 1) * sizeof(float), st>>>(w[0], w[1], w[2], w[3], reinterpret_cast<T*>(out), d.Co, d.Ci, taps, tci);
   } else {
-    int cchunk = PACK_SMEM_FLOATS / taps;
+    int cchunk = 2304 / taps;                             // ~9 KB tiles: many resident blocks
+    if (cchunk < 1) cchunk = 1;
     if (cchunk > d.Ci) cchunk = d.Ci;
     dim3 grid((unsigned)((d.Ci + cchunk - 1) / cchunk), (unsigned)(4 * d.Co));
     QUAN_TIMED(st);
-    pack_weights_fwd_kernel<T><<<grid, 256, 0, st>>>(w[0], w[1], w[2], w[3], reinterpret_cast<T*>(out), d.Co, d.Ci, taps, cchunk);
+    pack_weights_fwd_kernel<T><<<grid, 256, (size_t)cchunk * taps * sizeof(float), st>>>(w[0], w[1], w[2], w[3], reinterpret_cast<T*>(out), d.Co, d.Ci, taps, cchunk);
   }
   QUAN_CHECK_LAUNCH("pack_weights_kernel");
   return QUAN_OK;
@@ -1157,7 +1159,8 @@ static int launch_wgrad(const void* gq, const void* x, float* const dw[4], const
   kern<<<grid, TC_THREADS, w.smem, st>>>(map_g, map_x, p);
   QUAN_CHECK_LAUNCH(dense ? "qconv_wgrad_kernel_dense" : "qconv_wgrad_kernel");
   {
-    int cchunk = PACK_SMEM_FLOATS / p.taps;
+    int cchunk = 2304 / p.taps;
+    if (cchunk < 1) cchunk = 1;
     if (cchunk > d.Ci) cchunk = d.Ci;
     // split lanes per element: short rows with many splits (narrow layers) spread the split loop over the idle threads
     int SL = 256 / (cchunk * p.taps);
@@ -1165,11 +1168,12 @@ static int launch_wgrad(const void* gq, const void* x, float* const dw[4], const
     if (SL > w.splits) SL = w.splits;
     if (SL < 1) SL = 1;
     dim3 rgrid((unsigned)((d.Ci + cchunk - 1) / cchunk), (unsigned)(4 * d.Co));
+    const size_t rsmem = (size_t)(SL > 1 ? 256 : cchunk * p.taps) * sizeof(float) + 16;
     QUAN_TIMED(st);
     if (dense)
-      wgrad_reduce_kernel<true><<<rgrid, 256, 0, st>>>(p.partial, dw[0], dw[1], dw[2], dw[3], w.splits, p.taps, d.Co, d.Ci, cchunk, SL, mix);
+      wgrad_reduce_kernel<true><<<rgrid, 256, rsmem, st>>>(p.partial, dw[0], dw[1], dw[2], dw[3], w.splits, p.taps, d.Co, d.Ci, cchunk, SL, mix);
     else
-      wgrad_reduce_kernel<false><<<rgrid, 256, 0, st>>>(p.partial, dw[0], dw[1], dw[2], dw[3], w.splits, p.taps, d.Co, d.Ci, cchunk, SL, mix);
+      wgrad_reduce_kernel<false><<<rgrid, 256, rsmem, st>>>(p.partial, dw[0], dw[1], dw[2], dw[3], w.splits, p.taps, d.Co, d.Ci, cchunk, SL, mix);
   }
   QUAN_CHECK_LAUNCH("wgrad_reduce_kernel");
   return QUAN_OK;
