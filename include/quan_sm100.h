@@ -168,6 +168,14 @@ int quan_qconv2d_fwd(const void* x, const float* const w[4], const float* bias_r
 int quan_qconv2d_bwd(const void* dy, const void* x, const float* const w[4], void* dx, float* const dw[4],
                      float* dbias_r, const quan_conv_dims* d, int dtype, int layout, const float* mix,
                      int algo, void* workspace, size_t ws_bytes, void* stream);
+/* The Conv block's backward (conv -> IQBN, ultralytics/nn/modules/conv.py:805-809) can skip the G = M^T dY pass:
+ * quan_iqbn_bwd_apply(mix_t = M^T) emits G directly and quan_qconv2d_bwd_premixed consumes it.  Only the passes that
+ * read G qualify (separable tensor-core form, direct engine, bias gradient); the dense Hamilton form and the depthwise
+ * kernels take dY itself — quan_qconv2d_bwd_wants_mixed() returns 1 when every requested pass reads G, else 0. */
+int quan_qconv2d_bwd_premixed(const void* g, const void* x, const float* const w[4], void* dx, float* const dw[4],
+                              float* dbias_r, const quan_conv_dims* d, int dtype, int layout, const float* mix, int algo,
+                              void* workspace, size_t ws_bytes, void* stream);
+int quan_qconv2d_bwd_wants_mixed(const quan_conv_dims* d, int dtype, int layout, int algo, int need_dx, int need_dw);
 /* reports which engine AUTO would pick for this shape: QUAN_ALGO_DIRECT, QUAN_ALGO_TCGEN05 or QUAN_ALGO_DEPTHWISE */
 int quan_qconv2d_pick_algo(const quan_conv_dims* d, int dtype, int layout, int pass /*0 fwd,1 dgrad,2 wgrad*/);
 

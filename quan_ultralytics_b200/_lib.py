@@ -59,6 +59,8 @@ PROTOTYPES = {
     "quan_qconv2d_fwd": (_int, [_vp, _vp, _vp, _vp, _pdims, _int, _int, _vp, _int, _vp, _sz, _vp]),
     "quan_qconv2d_bwd": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _pdims, _int, _int, _vp, _int, _vp, _sz, _vp]),
     "quan_qconv2d_pick_algo": (_int, [_pdims, _int, _int, _int]),
+    "quan_qconv2d_bwd_premixed": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _pdims, _int, _int, _vp, _int, _vp, _sz, _vp]),
+    "quan_qconv2d_bwd_wants_mixed": (_int, [_pdims, _int, _int, _int, _int, _int]),
 }
 
 _lib = None

@@ -459,6 +459,76 @@ __global__ void __launch_bounds__(256, BWD ? 3 : 4) iqbn_apply_b(const T* __rest
   }
 }
 
+// Backward apply that emits G = M^T dx for the QConv2D that produced x (the Conv block's conv -> IQBN order, conv.py:805-
+// 809), so the separate mix pass over the gradient (one full read + write) disappears and G is rounded to bf16 once.
+// Thread mapping: the four components of a channel vector sit in ONE warp — a slot of 4*gl lanes = 4 components x gl
+// consecutive column vectors, lane = q*gl + j — so every global access still covers gl*16 contiguous bytes per component
+// and the other three components of a thread's channels arrive by three xor-shuffles per element (lane ^ gl, ^ 2gl,
+// ^ 3gl).  No shared memory, no block barrier; U rows per thread in flight as in iqbn_apply_b.
+struct GeomW {
+  int64_t R;      // rows
+  int L, C;
+  int cpq;        // column vectors per component (C / V)
+  int gl;         // column vectors per component and slot (power of two, <= 8, divides cpq)
+  int nb;         // channel blocks per row (cpq / gl)
+  int rpb;        // rows per block step ((256 / (4*gl)) / nb)
+};
+template <typename T, int V, int ACT, int U>
+__global__ void __launch_bounds__(256, 2) iqbn_apply_bwd_mix_b(const T* __restrict__ x, const T* __restrict__ dy,
+                                                              T* __restrict__ out, GeomW g, ApplyArgs a, Mix16 mt) {
+  using VecT = Vec<T, V>;
+  const int slot = threadIdx.x / (4 * g.gl), ls = threadIdx.x % (4 * g.gl);
+  const int q = ls / g.gl, j = ls - q * g.gl;
+  const int rl = slot / g.nb, cb = slot - rl * g.nb;
+  const bool lane_on = rl < g.rpb;
+  const int cv = q * g.cpq + cb * g.gl + j;            // this thread's column vector (fixed for the whole kernel)
+  const int64_t coloff = lane_on ? (int64_t)cv * V : 0;
+  float scale[V], shift[V], k1[V], k2[V], k3[V];
+  load_coef<float, V>(a.stats + 12 * g.C + coloff, scale);
+  load_coef<float, V>(a.stats + 16 * g.C + coloff, shift);
+  load_coef<float, V>(a.coefT + coloff, k1);
+  load_coef<float, V>(a.coefT + 4 * g.C + coloff, k2);
+  load_coef<float, V>(a.coefT + 8 * g.C + coloff, k3);
+  write_param_grads(a);
+  float m1 = mt.m[q * 4 + q], mx1 = mt.m[q * 4 + (q ^ 1)], mx2 = mt.m[q * 4 + (q ^ 2)], mx3 = mt.m[q * 4 + (q ^ 3)];
+  const VecT* xr = reinterpret_cast<const VecT*>(x + coloff);
+  const VecT* gr = reinterpret_cast<const VecT*>(dy + coloff);
+  VecT* orow = reinterpret_cast<VecT*>(out + coloff);
+  const int64_t rsv = g.L / V;
+  const int64_t rs = (int64_t)gridDim.x * g.rpb;
+  for (int64_t base = (int64_t)blockIdx.x * g.rpb; base < g.R; base += U * rs) {   // warp-uniform trip count (shuffles below)
+    VecT xa[U], ga[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t r = base + u * rs + rl;
+      if (lane_on && r < g.R) {
+        xa[u] = xr[r * rsv];
+        ga[u] = gr[r * rsv];
+      } else {
+        xa[u] = VecT{};
+        ga[u] = VecT{};
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t r = base + u * rs + rl;
+      VecT o;
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const float xv = to_f32(xa[u].v[i]);
+        float dz = to_f32(ga[u].v[i]);
+        if constexpr (ACT != QUAN_ACT_NONE) dz *= act_grad<ACT, sizeof(T) == 2>(fmaf(xv, scale[i], shift[i]));
+        const float d = fmaf(k1[i], dz, fmaf(k2[i], xv, k3[i]));
+        const float d1 = __shfl_xor_sync(0xffffffffu, d, g.gl);
+        const float d2 = __shfl_xor_sync(0xffffffffu, d, 2 * g.gl);
+        const float d3 = __shfl_xor_sync(0xffffffffu, d, 3 * g.gl);
+        o.v[i] = from_f32<T>(m1 * d + mx1 * d1 + mx2 * d2 + mx3 * d3);
+      }
+      if (lane_on && r < g.R) orow[r * rsv] = o;
+    }
+  }
+}
+
 // =================================================================================================
 // Layout BCHWQ: for a fixed (b,c) the plane is HW*4 contiguous elements, q = element & 3.
 // grid = (splits, C); a thread walks vectors v of channel c: b = v / vpp, i = v % vpp.
@@ -758,6 +828,29 @@ static int launch_apply(const void* x, const void* dy, void* out, int B, int C, 
   T* op = reinterpret_cast<T*>(out);
   if (layout == QUAN_LAYOUT_BHWQC && C > 1) {
     LaunchB p;
+    if constexpr (BWD) {
+      // train-mode backward that also emits G = M^T dx (fused Conv block): one kernel when a row fits one block
+      const int Vw = largest_pow2_divisor(C, VecTraits<T>::kMaxVec);
+      const int cpq = C / Vw;
+      int gl = 1;
+      while (gl < 8 && cpq % (gl * 2) == 0) gl *= 2;
+      const int nb = cpq / gl, spb = 256 / (4 * gl);
+      if (mix_t != nullptr && a.stats != nullptr && a.coefT != nullptr && nb <= spb) {
+        GeomW gw;
+        gw.R = (int64_t)B * H * W; gw.L = 4 * C; gw.C = C; gw.cpq = cpq; gw.gl = gl; gw.nb = nb; gw.rpb = spb / nb;
+        const Mix16 mt = make_mix(mix_t);
+        const int bps = env_int("QUAN_IQBN_MBPS", 2);
+        int64_t want = ceil_div64(gw.R, (int64_t)gw.rpb * 2);
+        const int64_t cap = (int64_t)QUAN_NUM_SMS * bps;
+        if (want > cap) want = cap;
+        if (want < 1) want = 1;
+        QUAN_TIMED(st);
+        QUAN_DISPATCH_V(Vw, (iqbn_apply_bwd_mix_b<T, (sizeof(T) == 4 && kV == 8) ? 4 : kV, ACT, 2>
+                             <<<(unsigned)want, 256, 0, st>>>(xp, dyp, op, gw, a, mt)));
+        QUAN_CHECK_LAUNCH("iqbn_apply_bwd_mix");
+        return QUAN_OK;
+      }
+    }
     // 4 blocks of 256 threads per SM; U rows (16-byte vectors) per stream in flight per thread
     const int U = env_int("QUAN_IQBN_U", BWD ? 2 : 4);
     if (!plan_b<T>(B, C, H, W, U, env_int("QUAN_IQBN_BPS", BWD ? 3 : 4), 256, p)) {
@@ -774,7 +867,7 @@ static int launch_apply(const void* x, const void* dy, void* out, int B, int C, 
     }
 #undef QUAN_APPLY_B
     QUAN_CHECK_LAUNCH(BWD ? "iqbn_apply_bwd" : "iqbn_apply_fwd");
-    if (BWD && mix_t != nullptr) {  // G = M^T dY for the producing QConv2D: second in-place pass in this layout
+    if (BWD && mix_t != nullptr) {  // rows wider than one block: G = M^T dx as a second, in-place pass
       int rc = quan_mix(out, out, B, C, H, W, sizeof(T) == 4 ? QUAN_F32 : QUAN_BF16, layout, mix_t, st);
       if (rc) return rc;
     }

@@ -81,9 +81,13 @@ int quan_qconv2d_fwd(const void* x, const float* const w[4], const float* bias_r
   return qconv_fwd_direct_launch(x, w, bias_r, y, *d, dtype, layout, mix, st);
 }
 
-int quan_qconv2d_bwd(const void* dy, const void* x, const float* const w[4], void* dx, float* const dw[4],
-                     float* dbias_r, const quan_conv_dims* d, int dtype, int layout, const float* mix, int algo,
-                     void* workspace, size_t ws_bytes, void* stream) {
+}  // extern "C"
+
+// premixed: `dy` already holds G = M^T dY (emitted by quan_iqbn_bwd_apply with mix_t); only legal when no selected pass
+// wants the raw gradient (quan_qconv2d_bwd_wants_mixed)
+static int qconv2d_bwd_impl(const void* dy, const void* x, const float* const w[4], void* dx, float* const dw[4],
+                            float* dbias_r, const quan_conv_dims* d, int dtype, int layout, const float* mix, int algo,
+                            void* workspace, size_t ws_bytes, void* stream, bool premixed) {
   int rc = validate(d, dtype, layout, mix);
   if (rc) return rc;
   QUAN_REQUIRE(dy != nullptr && w != nullptr && w[0] && w[1] && w[2] && w[3], QUAN_E_ARG, "qconv2d_bwd: null tensor pointer");
@@ -93,7 +97,7 @@ int quan_qconv2d_bwd(const void* dy, const void* x, const float* const w[4], voi
   const size_t gb = g_bytes(*d, dtype);
   QUAN_REQUIRE(workspace != nullptr && ws_bytes >= gb, QUAN_E_WORKSPACE,
                "qconv2d_bwd: workspace needs >= %zu bytes (see quan_qconv2d_workspace_bytes), got %zu", gb, ws_bytes);
-  void* gq = workspace;
+  const void* gq = premixed ? dy : workspace;
   void* tc_ws = (char*)workspace + gb;
   const size_t tc_ws_bytes = ws_bytes - gb;
 
@@ -112,12 +116,15 @@ int quan_qconv2d_bwd(const void* dy, const void* x, const float* const w[4], voi
   // G = M^T dY, once, shared by every consumer that needs it (separable dgrad / wgrad, direct engine, bias grad)
   const bool need_g = (dx != nullptr && m_dx != TC_DENSE && a_dx != QUAN_ALGO_DEPTHWISE) ||
                       (dw != nullptr && m_dw != TC_DENSE && a_dw != QUAN_ALGO_DEPTHWISE) || dbias_r != nullptr;
-  if (need_g) {
+  QUAN_REQUIRE(!premixed || ((dx == nullptr || (m_dx != TC_DENSE && a_dx != QUAN_ALGO_DEPTHWISE)) &&
+                             (dw == nullptr || (m_dw != TC_DENSE && a_dw != QUAN_ALGO_DEPTHWISE))),
+               QUAN_E_UNSUPPORTED, "qconv2d_bwd_premixed: this shape's dgrad/wgrad consume the raw gradient (dense / depthwise form)");
+  if (need_g && !premixed) {
     float mix_t[16];
     for (int p = 0; p < 4; ++p)
       for (int q = 0; q < 4; ++q) mix_t[q * 4 + p] = mix[p * 4 + q];
     const int Ho = conv_out(d->H, d->kH, d->sH, d->pH, d->dH), Wo = conv_out(d->W, d->kW, d->sW, d->pW, d->dW);
-    rc = quan_mix(dy, gq, d->B, d->Co, Ho, Wo, dtype, layout, mix_t, stream);
+    rc = quan_mix(dy, workspace, d->B, d->Co, Ho, Wo, dtype, layout, mix_t, stream);
     if (rc) return rc;
   }
 
@@ -150,6 +157,32 @@ int quan_qconv2d_bwd(const void* dy, const void* x, const float* const w[4], voi
     if (rc) return rc;
   }
   return QUAN_OK;
+}
+
+extern "C" {
+
+int quan_qconv2d_bwd(const void* dy, const void* x, const float* const w[4], void* dx, float* const dw[4],
+                     float* dbias_r, const quan_conv_dims* d, int dtype, int layout, const float* mix, int algo,
+                     void* workspace, size_t ws_bytes, void* stream) {
+  return qconv2d_bwd_impl(dy, x, w, dx, dw, dbias_r, d, dtype, layout, mix, algo, workspace, ws_bytes, stream, false);
+}
+
+int quan_qconv2d_bwd_premixed(const void* g, const void* x, const float* const w[4], void* dx, float* const dw[4],
+                              float* dbias_r, const quan_conv_dims* d, int dtype, int layout, const float* mix, int algo,
+                              void* workspace, size_t ws_bytes, void* stream) {
+  return qconv2d_bwd_impl(g, x, w, dx, dw, dbias_r, d, dtype, layout, mix, algo, workspace, ws_bytes, stream, true);
+}
+
+int quan_qconv2d_bwd_wants_mixed(const quan_conv_dims* d, int dtype, int layout, int algo, int need_dx, int need_dw) {
+  if (d == nullptr) return QUAN_E_ARG;
+  for (int pass = PASS_DGRAD; pass <= PASS_WGRAD; ++pass) {
+    if (pass == PASS_DGRAD ? !need_dx : !need_dw) continue;
+    const int a = resolve_algo(*d, dtype, layout, pass, algo);
+    if (a <= 0) return 0;
+    if (a == QUAN_ALGO_DEPTHWISE) return 0;
+    if (a == QUAN_ALGO_TCGEN05 && qconv_tc_mode(*d, dtype, layout, pass) == TC_DENSE) return 0;
+  }
+  return 1;
 }
 
 }  // extern "C"

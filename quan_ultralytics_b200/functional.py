@@ -127,6 +127,60 @@ class _IQBNTrain(torch.autograd.Function):
         return dx, dgamma, dbeta, None, None, None, None, None, None
 
 
+class _ConvBlock(torch.autograd.Function):
+    """QConv2D -> IQBN(batch statistics) -> act as ONE autograd node (the reference's `Conv.forward`, conv.py:805-809).
+    Same kernels as the separate nodes, but the backward knows that the conv is the only consumer of the IQBN input
+    gradient: when the conv's backward reads G = M^T dY (separable tensor-core form / direct engine) the IQBN backward
+    emits G itself and the mix pass over the gradient disappears."""
+
+    @staticmethod
+    def forward(ctx, x, w_r, w_i, w_j, w_k, gamma, beta, running_mean, running_var, stride, padding, dilation, groups, mix,
+                algo, eps, momentum, act):
+        x, layout = ops.as_layout(x, _state["layout"])
+        ws = (w_r, w_i, w_j, w_k)
+        y = ops.qconv2d_fwd(x, ws, None, stride, padding, dilation, groups, mix, algo, layout)
+        g32, b32 = ops._f32c(gamma), ops._f32c(beta)
+        B, C_, H, W, _ = y.shape
+        stats = ops.iqbn_train_stats(y, layout, g32, b32, eps, momentum, running_mean, running_var)
+        out = ops.iqbn_apply_fwd(y, layout, stats, g32, b32, act)
+        ctx.save_for_backward(x, y, stats, g32, b32, w_r, w_i, w_j, w_k)
+        ctx.conf = (tuple(stride), tuple(padding), tuple(dilation), int(groups), tuple(mix), algo, layout, act,
+                    float(B * H * W), gamma.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, y, stats, g32, b32, w_r, w_i, w_j, w_k = ctx.saved_tensors
+        stride, padding, dilation, groups, mix, algo, layout, act, count, pdtype = ctx.conf
+        ws = (w_r, w_i, w_j, w_k)
+        dout, _ = ops.as_layout(dout, layout)
+        if dout.dtype != y.dtype:
+            dout = dout.to(y.dtype)
+        need_dx = ctx.needs_input_grad[0]
+        need_dw = any(ctx.needs_input_grad[1:5])
+        sums = ops.iqbn_bwd_reduce(dout, y, layout, stats, g32, b32, act, count)
+        mixed = (need_dx or need_dw) and ops.qconv2d_bwd_wants_mixed(x.shape, w_r.shape, stride, padding, dilation, groups,
+                                                                    x.dtype, layout, algo, need_dx, need_dw)
+        dy, dgamma, dbeta = ops.iqbn_bwd_apply(dout, y, layout, stats, g32, b32, act, sums, count,
+                                               mix_t=ops._mix_t(mix) if mixed else None)
+        dx, dws, _ = ops.qconv2d_bwd(dy, x, ws, stride, padding, dilation, groups, mix, need_dx, need_dw, False, algo,
+                                     premixed=mixed)
+        if dws is None:
+            dws = [None] * 4
+        else:
+            dws = [g.to(w.dtype) if g.dtype != w.dtype else g for g, w in zip(dws, ws)]
+        if pdtype != torch.float32:
+            dgamma, dbeta = dgamma.to(pdtype), dbeta.to(pdtype)
+        return (dx, dws[0], dws[1], dws[2], dws[3], dgamma, dbeta) + (None,) * 11
+
+
+def conv_iqbn_act(x, w_r, w_i, w_j, w_k, gamma, beta, running_mean, running_var, stride, padding, dilation, groups, mix,
+                  algo=ALGO_AUTO, eps: float = 1e-5, momentum: float = 0.1, act: int = ACT_SILU) -> torch.Tensor:
+    """Training-mode `Conv` block (bias-free QConv2D -> IQBN with batch statistics -> act) as one autograd node."""
+    return _ConvBlock.apply(x, w_r, w_i, w_j, w_k, gamma, beta, running_mean, running_var, stride, padding, dilation, groups,
+                            mix, algo, eps, momentum, act)
+
+
 class _IQBNEval(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, gamma, beta, running_mean, running_var, eps, act):

@@ -209,6 +209,7 @@ class Conv(nn.Module):
 
     default_act = nn.SiLU()
     conv_cls = QConv2D
+    fuse_block = True      # training: run conv + IQBN + act as one autograd node (functional.conv_iqbn_act)
 
     def __init__(self, c1, c2, k=1, s=1, p=None, g=1, d=1, act=True):
         super().__init__()
@@ -217,6 +218,16 @@ class Conv(nn.Module):
         self.act = self.default_act if act is True else act if isinstance(act, nn.Module) else nn.Identity()
 
     def forward(self, x):
+        fused_act = ACT_SILU if isinstance(self.act, nn.SiLU) else ACT_NONE if isinstance(self.act, nn.Identity) else None
+        c, bn = self.conv, self.bn
+        if (self.fuse_block and fused_act is not None and bn.training and not bn.sync and c.bias_r is None
+                and not c.is_first_layer and x.dim() == 5 and x.is_cuda):
+            # conv -> IQBN -> act as one autograd node: the IQBN backward hands G = M^T dY straight to the conv backward
+            with torch.no_grad():
+                bn.num_batches_tracked += 1
+            return QF.conv_iqbn_act(x, c.weight_r, c.weight_i, c.weight_j, c.weight_k, bn.gamma, bn.beta, bn.running_mean,
+                                    bn.running_var, c.stride, c.padding, c.dilation, c.groups, ops.MIX[c.mix], c.algo,
+                                    bn.eps, bn.momentum, fused_act)
         y = self.conv(x)
         if isinstance(self.act, nn.SiLU):
             return self.bn(y, ACT_SILU)

@@ -346,8 +346,9 @@ def qconv2d_fwd(x: torch.Tensor, weights: Sequence[torch.Tensor], bias_r: Option
 
 def qconv2d_bwd(dy: torch.Tensor, x: torch.Tensor, weights: Sequence[torch.Tensor], stride, padding, dilation,
                 groups: int, mix_matrix: Sequence[float], need_dx: bool = True, need_dw: bool = True,
-                need_db: bool = False, algo: int = ALGO_AUTO):
-    """Returns (dx or None, [dw_r, dw_i, dw_j, dw_k] or None, db_r or None)."""
+                need_db: bool = False, algo: int = ALGO_AUTO, premixed: bool = False):
+    """Returns (dx or None, [dw_r, dw_i, dw_j, dw_k] or None, db_r or None).  `premixed`: dy already holds G = M^T dY
+    (emitted by iqbn_bwd_apply(mix_t=...)); legal only when qconv2d_bwd_wants_mixed() says so."""
     _require_cuda(dy, x, *weights)
     x, layout = as_layout(x)
     dy, _ = as_layout(dy, layout)
@@ -361,11 +362,20 @@ def qconv2d_bwd(dy: torch.Tensor, x: torch.Tensor, weights: Sequence[torch.Tenso
     wsb = _workspace(nws, x.device)
     wa = _weights_arg(ws)
     dwa = None if dws is None else _weights_arg(dws)
-    check(lib.quan_qconv2d_bwd(dy.data_ptr(), x.data_ptr(), C.cast(wa, C.c_void_p), _ptr(dx),
-                               None if dwa is None else C.cast(dwa, C.c_void_p), _ptr(db), C.byref(d), _dtype_code(x),
-                               layout, C.cast(_mix_arg(mix_matrix), C.c_void_p), algo, wsb.data_ptr(), wsb.numel(),
-                               _stream(x)), "quan_qconv2d_bwd")
+    fn = lib.quan_qconv2d_bwd_premixed if premixed else lib.quan_qconv2d_bwd
+    check(fn(dy.data_ptr(), x.data_ptr(), C.cast(wa, C.c_void_p), _ptr(dx),
+             None if dwa is None else C.cast(dwa, C.c_void_p), _ptr(db), C.byref(d), _dtype_code(x),
+             layout, C.cast(_mix_arg(mix_matrix), C.c_void_p), algo, wsb.data_ptr(), wsb.numel(),
+             _stream(x)), "quan_qconv2d_bwd")
     return dx, dws, db
+
+
+def qconv2d_bwd_wants_mixed(x_shape, w_shape, stride, padding, dilation, groups, dtype: torch.dtype, layout: int,
+                            algo: int = ALGO_AUTO, need_dx: bool = True, need_dw: bool = True) -> bool:
+    """True when every requested backward pass of this conv reads G = M^T dY (so the IQBN backward can emit G directly)."""
+    d = conv_dims(x_shape, w_shape, stride, padding, dilation, groups)
+    return _lib.load().quan_qconv2d_bwd_wants_mixed(C.byref(d), F32 if dtype == torch.float32 else BF16, layout, algo,
+                                                    int(need_dx), int(need_dw)) == 1
 
 
 def qconv2d_pick_algo(x_shape, w_shape, stride, padding, dilation, groups, dtype: torch.dtype, layout: int,

@@ -141,3 +141,34 @@ def test_depthwise_engine_matches_direct_engine(case):
         assert rel(a, r) <= 2 * tol
     if bias:
         assert rel(db, db_ref) <= 1e-4
+
+
+@pytest.mark.parametrize("cfg", [("sep_bf16", torch.bfloat16, 64, 64, 1), ("sep_f32", torch.float32, 64, 128, 1),
+                                 ("dense_bf16", torch.bfloat16, 16, 16, 1), ("dw_bf16", torch.bfloat16, 32, 32, 32),
+                                 ("sep_bf16_s2", torch.bfloat16, 64, 64, 1)], ids=lambda c: c[0])
+def test_fused_conv_block_matches_separate_nodes(cfg):
+    """`Conv` as one autograd node (IQBN backward emits G = M^T dY for the conv backward) against the three separate
+    nodes, same kernels otherwise: outputs identical, gradients equal up to the bf16 rounding of the intermediate."""
+    import quan_ultralytics_b200 as Q
+    name, dtype, ci, co, g = cfg
+    s = 2 if name.endswith("s2") else 1
+    torch.manual_seed(11)
+    blk = (Q.DWConv(ci * 4, co * 4, 3, s) if g > 1 else Q.Conv(ci * 4, co * 4, 3, s)).to(DEV).train()
+    x = torch.randn(4, ci, 24, 24, 4, device=DEV).to(dtype).contiguous(memory_format=torch.channels_last_3d)
+    outs = {}
+    for fused in (True, False):
+        blk.fuse_block = fused
+        blk.zero_grad(set_to_none=True)
+        blk.bn.running_mean.zero_(); blk.bn.running_var.fill_(1.0)
+        xi = x.clone().requires_grad_(True)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=dtype == torch.bfloat16):
+            y = blk(xi)
+        torch.manual_seed(12)
+        y.backward(torch.randn_like(y))
+        outs[fused] = (y.detach(), xi.grad, blk.conv.weight_r.grad.clone(), blk.conv.weight_k.grad.clone(),
+                       blk.bn.gamma.grad.clone(), blk.bn.beta.grad.clone(), blk.bn.running_var.clone())
+    # fp32: G is the same value up to FMA grouping, then truncated to tf32 by the tensor core
+    tol = 1e-2 if dtype == torch.bfloat16 else 1e-4
+    assert torch.equal(outs[True][0], outs[False][0]) and torch.equal(outs[True][6], outs[False][6])
+    for a, b in zip(outs[True][1:6], outs[False][1:6]):
+        assert rel(a, b) <= tol
