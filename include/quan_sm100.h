@@ -168,6 +168,19 @@ int quan_qconv2d_fwd(const void* x, const float* const w[4], const float* bias_r
 int quan_qconv2d_bwd(const void* dy, const void* x, const float* const w[4], void* dx, float* const dw[4],
                      float* dbias_r, const quan_conv_dims* d, int dtype, int layout, const float* mix,
                      int algo, void* workspace, size_t ws_bytes, void* stream);
+/* Forward conv that also emits the IQBN batch statistics of its OUTPUT as per-CTA partial sums (the Conv block's
+ * conv -> IQBN order, conv.py:805-809): the tensor-core epilogue adds every output value and its square into shared-memory
+ * accumulators and each CTA writes its slot of the IQBN partials buffer (`iqbn_workspace`, quan_iqbn_workspace_bytes(Co)
+ * bytes).  *nparts = slots written; 0 means this shape/engine produced none and the caller runs quan_iqbn_train_stats on y.
+ * quan_iqbn_finalize_partials folds the slots exactly like the second launch of quan_iqbn_train_stats (mean, var + 1e-8,
+ * rstd, coefficient tables, running statistics); count = B*Ho*Wo. */
+int quan_qconv2d_fwd_stats(const void* x, const float* const w[4], const float* bias_r, void* y, const quan_conv_dims* d,
+                           int dtype, int layout, const float* mix, int algo, void* workspace, size_t ws_bytes,
+                           void* iqbn_workspace, size_t iqbn_ws_bytes, int* nparts, void* stream);
+int quan_iqbn_finalize_partials(const void* iqbn_workspace, int32_t nparts, double count, int32_t C, const float* gamma,
+                                const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                                float* stats /* [20*C] */, void* stream);
+
 /* The Conv block's backward (conv -> IQBN, ultralytics/nn/modules/conv.py:805-809) can skip the G = M^T dY pass:
  * quan_iqbn_bwd_apply(mix_t = M^T) emits G directly and quan_qconv2d_bwd_premixed consumes it.  Only the passes that
  * read G qualify (separable tensor-core form, direct engine, bias gradient); the dense Hamilton form and the depthwise

@@ -6,9 +6,10 @@ Python/PyTorch (memory, streams, autograd, torch.distributed); all arithmetic ru
 C ABI in include/quan_sm100.h (libquan_sm100.so).  There is no CPU / PyTorch fallback.
 """
 from . import _lib, ops  # noqa: F401
-from ._lib import ACT_NONE, ACT_SILU, ALGO_AUTO, ALGO_DIRECT, ALGO_TCGEN05, LAYOUT_BCHWQ, LAYOUT_BHWQC  # noqa: F401
-from .functional import (iqbn, internal_layout, poincare_map, qconv2d, qupsample_nearest,  # noqa: F401
-                         set_internal_layout)
+from ._lib import (ACT_NONE, ACT_SILU, ALGO_AUTO, ALGO_DEPTHWISE, ALGO_DIRECT, ALGO_TCGEN05, LAYOUT_BCHWQ,  # noqa: F401
+                   LAYOUT_BHWQC)
+from .functional import (conv_iqbn_act, iqbn, internal_layout, poincare_map, qconv2d, qupsample_nearest,  # noqa: F401
+                         set_epilogue_stats, set_internal_layout)
 from .modules import IQBN, Conv, DWConv, QConv2D, QConv2D_B, QUpsample, autopad  # noqa: F401
 
 __version__ = "0.1.0"

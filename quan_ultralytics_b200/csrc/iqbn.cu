@@ -930,6 +930,33 @@ static int reduce_entry(int mode, const void* x, const void* dy, int B, int C, i
   return launch_reduce<__nv_bfloat16, 1, QUAN_ACT_NONE>(x, dy, B, C, H, W, layout, gamma, beta, ws, tail, st);
 }
 
+int quan_iqbn_finalize_partials(const void* workspace, int32_t nparts, double count, int32_t C, const float* gamma,
+                                const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                                float* stats, void* stream) {
+  QUAN_REQUIRE(workspace != nullptr && stats != nullptr && gamma != nullptr && beta != nullptr, QUAN_E_ARG,
+               "iqbn_finalize_partials: null pointer");
+  QUAN_REQUIRE(nparts > 0 && nparts <= IQBN_MAX_PARTS && C > 0 && count > 0, QUAN_E_ARG,
+               "iqbn_finalize_partials: bad nparts=%d / C=%d / count", nparts, C);
+  QUAN_REQUIRE((running_mean == nullptr) == (running_var == nullptr), QUAN_E_ARG,
+               "iqbn_finalize_partials: running_mean/var must both be given or both NULL");
+  TailArgs t = {};
+  t.mode = TAIL_FWD_STATS;
+  t.C = C;
+  t.count = count;
+  t.eps = eps;
+  t.momentum = momentum;
+  t.running_mean = running_mean;
+  t.running_var = running_var;
+  t.stats = stats;
+  t.gamma = gamma;
+  t.beta = beta;
+  cudaStream_t st = (cudaStream_t)stream;
+  QUAN_TIMED(st);
+  iqbn_fold_kernel<<<(4 * C + 7) / 8, 256, 0, st>>>(reinterpret_cast<const double*>(workspace), nparts, t);
+  QUAN_CHECK_LAUNCH("iqbn_fold");
+  return QUAN_OK;
+}
+
 int quan_iqbn_train_stats(const void* x, int32_t B, int32_t C, int32_t H, int32_t W, int dtype, int layout,
                           const float* gamma, const float* beta, float eps, float momentum, float* running_mean,
                           float* running_var, float* stats, void* workspace, size_t ws_bytes, void* stream) {

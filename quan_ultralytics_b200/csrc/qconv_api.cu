@@ -61,9 +61,10 @@ size_t quan_qconv2d_workspace_bytes(const quan_conv_dims* d, int dtype, int layo
   return g_bytes(*d, dtype) + align_up(tc, 1024);
 }
 
-int quan_qconv2d_fwd(const void* x, const float* const w[4], const float* bias_r, void* y, const quan_conv_dims* d,
-                     int dtype, int layout, const float* mix, int algo, void* workspace, size_t ws_bytes,
-                     void* stream) {
+static int qconv2d_fwd_impl(const void* x, const float* const w[4], const float* bias_r, void* y, const quan_conv_dims* d,
+                            int dtype, int layout, const float* mix, int algo, void* workspace, size_t ws_bytes,
+                            void* stream, double* stat_part, int* stat_nparts) {
+  if (stat_nparts != nullptr) *stat_nparts = 0;
   int rc = validate(d, dtype, layout, mix);
   if (rc) return rc;
   QUAN_REQUIRE(x != nullptr && y != nullptr && w != nullptr && w[0] && w[1] && w[2] && w[3], QUAN_E_ARG,
@@ -76,9 +77,25 @@ int quan_qconv2d_fwd(const void* x, const float* const w[4], const float* bias_r
     const size_t need = qconv_tc_workspace_bytes(*d, dtype, layout, PASS_FWD);
     QUAN_REQUIRE(workspace != nullptr && ws_bytes >= need, QUAN_E_WORKSPACE,
                  "qconv2d_fwd: tcgen05 engine needs %zu workspace bytes, got %zu", need, ws_bytes);
-    return qconv_tc_fwd(x, w, bias_r, y, *d, dtype, qconv_tc_mode(*d, dtype, layout, PASS_FWD), mix, workspace, ws_bytes, st);
+    return qconv_tc_fwd(x, w, bias_r, y, *d, dtype, qconv_tc_mode(*d, dtype, layout, PASS_FWD), mix, workspace, ws_bytes, st,
+                        stat_part, stat_nparts);
   }
   return qconv_fwd_direct_launch(x, w, bias_r, y, *d, dtype, layout, mix, st);
+}
+
+int quan_qconv2d_fwd(const void* x, const float* const w[4], const float* bias_r, void* y, const quan_conv_dims* d,
+                     int dtype, int layout, const float* mix, int algo, void* workspace, size_t ws_bytes,
+                     void* stream) {
+  return qconv2d_fwd_impl(x, w, bias_r, y, d, dtype, layout, mix, algo, workspace, ws_bytes, stream, nullptr, nullptr);
+}
+
+int quan_qconv2d_fwd_stats(const void* x, const float* const w[4], const float* bias_r, void* y, const quan_conv_dims* d,
+                           int dtype, int layout, const float* mix, int algo, void* workspace, size_t ws_bytes,
+                           void* iqbn_workspace, size_t iqbn_ws_bytes, int* nparts, void* stream) {
+  QUAN_REQUIRE(nparts != nullptr && d != nullptr, QUAN_E_ARG, "qconv2d_fwd_stats: null pointer");
+  const bool room = iqbn_workspace != nullptr && iqbn_ws_bytes >= quan_iqbn_workspace_bytes(d->Co);
+  return qconv2d_fwd_impl(x, w, bias_r, y, d, dtype, layout, mix, algo, workspace, ws_bytes, stream,
+                          room ? (double*)iqbn_workspace : nullptr, nparts);
 }
 
 }  // extern "C"

@@ -33,8 +33,11 @@ bool qconv_tc_supported(const quan_conv_dims& d, int dtype, int layout, int pass
 size_t qconv_tc_workspace_bytes(const quan_conv_dims& d, int dtype, int layout, int pass);
 // `mode` is qconv_tc_mode()'s answer for the pass.  dgrad / wgrad take G = M^T dY in the separable form and dY itself
 // in the dense form (`mix` is always the forward mixing matrix).
+// stat_part (or NULL): the IQBN partials buffer — every CTA writes the partial sums / sums of squares of the outputs it
+// produced to its own slot [2][4*C_o]; *stat_nparts = slots written (0: this launch produced none, run the stats kernel)
 int qconv_tc_fwd(const void* x, const float* const w[4], const float* bias_r, void* y, const quan_conv_dims& d,
-                 int dtype, int mode, const float* mix, void* ws, size_t ws_bytes, cudaStream_t st);
+                 int dtype, int mode, const float* mix, void* ws, size_t ws_bytes, cudaStream_t st,
+                 double* stat_part = nullptr, int* stat_nparts = nullptr);
 int qconv_tc_dgrad(const void* g, const float* const w[4], void* dx, const quan_conv_dims& d, int dtype, int mode,
                    const float* mix, void* ws, size_t ws_bytes, cudaStream_t st);
 int qconv_tc_wgrad(const void* g, const void* x, float* const dw[4], const quan_conv_dims& d, int dtype, int mode,

@@ -161,8 +161,32 @@ struct TcConvParams {
   uint32_t a_sub_bytes, b_sub_bytes;   // one sub-step's A / B tile (per CTA)
   uint32_t sbo_bytes, layout_type, idesc, tmem_cols;
   const float* bias;                   // NQ = 4: [Cout], joins S_r before the mix; NQ = 1: [Cout] added to the output
+  double* stat_part;                   // or NULL: per-CTA partial IQBN sums of the OUTPUT, [grid][2][C_q*4] (index c*4+q)
+  int stat_cq;                         // quaternion output channels C_o (NQ = 4: Cout; NQ = 1: Cout / 4)
   Mix16 mix;
 };
+
+// Fused IQBN statistics in the conv epilogue: a thread holds 16 output values of one pixel row; the warp needs the 16
+// column sums (and sums of squares) over its 32 rows.  Halving butterfly: 32 values per lane -> 5 exchange steps in which
+// every lane sends half of what it still holds (16+8+4+2+1 = 31 shuffles instead of 32 x 5), after which lane L holds the
+// total of value L (L < 16: sum of column L, L >= 16: sum of squares of column L-16) and adds it to the CTA's shared
+// accumulators sacc[which][col] (4 quarter-warps x 2 column halves share an address at most 4 ways).
+__device__ __forceinline__ void stat_add(float* sacc, int cq, int col0, const float (&o)[16], int lane) {
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) { v[j] = o[j]; v[16 + j] = o[j] * o[j]; }
+#pragma unroll
+  for (int n = 16, off = 16; n >= 1; n >>= 1, off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+      const float send = up ? v[i] : v[i + n];
+      const float keep = up ? v[i + n] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  atomicAdd(sacc + (lane >> 4) * 4 * cq + col0 + (lane & 15), v[0]);
+}
 
 constexpr int TC_THREADS = 192;    // wgrad kernel: warp 0 TMA producer, warp 1 TMEM alloc + MMA issuer, warps 2-5 epilogue
 constexpr int EPI_WARPS = 8;       // igemm kernel: two epilogue warps per TMEM lane quarter (they split the columns)
@@ -202,6 +226,7 @@ qconv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   uint64_t* tile_full = empty_bar + p.stages;     // [2]  MMA -> epilogue: all accumulators of a unit are complete
   uint64_t* acc_empty = tile_full + 2;            // [4]  epilogue -> MMA: accumulator a has been read out
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 4);
+  float* sacc = reinterpret_cast<float*>(tmem_ptr + 4);   // [2][4][C_o] sum / sum of squares of this CTA's outputs (fused IQBN stats)
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform
   const int lane = threadIdx.x & 31;
@@ -225,6 +250,8 @@ qconv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     if constexpr (CG == 2) ptx::tmem_alloc_2cta(tmem_ptr, p.tmem_cols);
     else ptx::tmem_alloc(tmem_ptr, p.tmem_cols);
   }
+  if (p.stat_part != nullptr && warp >= 2)
+    for (int e = threadIdx.x - 64; e < 8 * p.stat_cq; e += 32 * EPI_WARPS) sacc[e] = 0.f;
   ptx::tc_fence_before();
   if constexpr (CG == 2) ptx::cluster_sync_all();   // peer's barriers must be initialised before anything signals them
   else __syncthreads();
@@ -404,6 +431,20 @@ qconv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                 }
               }
             }
+            if constexpr (MIX) {
+              if (p.stat_part != nullptr) {   // fused IQBN statistics: column sums of this warp's 32 rows (warp-uniform branch)
+#pragma unroll
+                for (int pc = 0; pc < 4; ++pc) {
+                  float o[16];
+#pragma unroll
+                  for (int j = 0; j < 16; ++j)
+                    o[j] = valid ? p.mix.m[pc * 4 + 0] * st[ci][j] + p.mix.m[pc * 4 + 1] * acc[0][j] + p.mix.m[pc * 4 + 2] * acc[1][j] +
+                                       p.mix.m[pc * 4 + 3] * acc[2][j]
+                                 : 0.f;
+                  stat_add(sacc, p.stat_cq, pc * p.stat_cq + n0 + c0, o, lane);
+                }
+              }
+            }
           }
         }
         ptx::tc_fence_before();
@@ -438,8 +479,26 @@ qconv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
               store_vec<T, VW>(yrow + c0 + v * VW, part);
             }
           }
+          if (p.stat_part != nullptr) {      // dense form: column n = p*C_o + co is already the (component, channel) pair
+            if (!valid) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+            }
+            stat_add(sacc, p.stat_cq, n0 + c0, acc, lane);
+          }
         }
         release(acc_empty + a);
+      }
+    }
+    if (p.stat_part != nullptr) {
+      // this CTA's slot of the IQBN partials buffer (what iqbn_reduce_b writes): [2][C_o*4], index c*4 + q
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");   // the 8 epilogue warps only
+      const int n4 = 4 * p.stat_cq;
+      double* slot = p.stat_part + (size_t)blockIdx.x * 2 * n4;
+      for (int e = threadIdx.x - 64; e < 2 * n4; e += 32 * EPI_WARPS) {
+        const int which = e / n4, r = e - which * n4;
+        const int pc = r / p.stat_cq, co = r - pc * p.stat_cq;
+        slot[which * n4 + co * 4 + pc] = (double)sacc[e];
       }
     }
     ptx::tc_fence_before();
@@ -810,7 +869,7 @@ static bool igemm_supported(const IgemmShape& s, int dtype) {
 
 template <typename T, bool MIX, int CG, int KSTEPS, int NQ>
 static int launch_igemm_inst(const CUtensorMap& map_a, const CUtensorMap& map_b, void* out, const TcConvParams& p, size_t smem,
-                             const char* name, cudaStream_t st) {
+                             const char* name, cudaStream_t st, int* ctas) {
   auto kern = qconv_igemm_kernel<T, MIX, CG, KSTEPS, NQ>;
   // persistent grid: one CTA (pair) per SM, as many as can be co-resident (queried once per instantiation)
   static thread_local int max_groups = 0;
@@ -842,6 +901,7 @@ static int launch_igemm_inst(const CUtensorMap& map_a, const CUtensorMap& map_b,
   }
   const int groups = p.units < max_groups ? p.units : max_groups;
   cfg.gridDim = dim3((unsigned)(groups * CG));
+  *ctas = groups * CG;
   QUAN_TIMED(st);
   QUAN_CUDA(cudaLaunchKernelEx(&cfg, kern, map_a, map_b, reinterpret_cast<T*>(out), p));
   QUAN_CHECK_LAUNCH(name);
@@ -850,7 +910,7 @@ static int launch_igemm_inst(const CUtensorMap& map_a, const CUtensorMap& map_b,
 
 template <typename T, bool MIX, int NQ>
 static int launch_igemm(const void* in, const void* wpacked, const float* bias, void* out, const IgemmShape& s, int dtype,
-                        const Mix16& mix, cudaStream_t st) {
+                        const Mix16& mix, cudaStream_t st, double* stat_part = nullptr, int* stat_nparts = nullptr) {
   const int esz = sizeof(T);
   const int row_bytes = pick_row_bytes(s.K, esz);
   TilePlan t;
@@ -881,6 +941,15 @@ static int launch_igemm(const void* in, const void* wpacked, const float* bias, 
   const int acc_cols = (NQ == 4 ? 4 : 2) * p.BN;
   p.tmem_cols = (uint32_t)pow2_ceil(acc_cols < 32 ? 32 : acc_cols);
   p.bias = bias;
+  p.stat_cq = NQ == 4 ? s.N : s.N / 4;
+  // fused IQBN partial statistics: needs the [2][4][C_o] fp32 accumulators next to the pipeline stages in shared memory
+  // Measured on B200 (bench shape, separable form): the 31-shuffle column reduction per 16 outputs makes the epilogue
+  // longer than the q = 0 mainloop it hides behind — igemm 220 -> 293 us, more than the 38 + 11 us statistics pass it
+  // replaces — so the wide layers keep the streaming statistics kernel; the dense form (narrow, HBM-bound layers with an
+  // idle tensor pipe) emits them.  QUAN_TC_EPI_STATS=2 forces, =0 disables.
+  static const int epi_stats = [] { const char* e = getenv("QUAN_TC_EPI_STATS"); return e ? atoi(e) : 1; }();
+  const bool want_stats = epi_stats == 2 || (epi_stats == 1 && NQ == 1);
+  p.stat_part = (stat_part != nullptr && want_stats && (size_t)32 * p.stat_cq <= 24 * 1024) ? stat_part : nullptr;
   p.mix = mix;
   int iters_per_q = 1 << 30;                         // of the smallest class
   for (int c = 0; c < p.tt.ncls; ++c) {
@@ -896,7 +965,8 @@ static int launch_igemm(const void* in, const void* wpacked, const float* bias, 
   if (const char* e = getenv("QUAN_TC_STAGES")) { int v = atoi(e); if (v >= 1 && v < stages) stages = v; }
   QUAN_REQUIRE(stages >= 2, QUAN_E_UNSUPPORTED, "tcgen05 conv: stage too large");
   p.stages = stages;
-  const size_t smem = 1024 + stages * stage_bytes + (2 * stages + 6) * sizeof(uint64_t) + 16;
+  const size_t smem = 1024 + stages * stage_bytes + (2 * stages + 6) * sizeof(uint64_t) + 16 +
+                      (p.stat_part != nullptr ? (size_t)8 * p.stat_cq * sizeof(float) : 0);
 
   // A: input activations [B][Hi][Wi][nq][K] -> 5-D map {K, nq, Wi, Hi, B}
   CUtensorMap map_a, map_b;
@@ -919,15 +989,19 @@ static int launch_igemm(const void* in, const void* wpacked, const float* bias, 
     int rc = encode_map(&map_b, dtype, 4, wpacked, dims, str, box, est, row_bytes);
     if (rc) return rc;
   }
-#define QUAN_IGEMM_CASE(CGV, KS) return launch_igemm_inst<T, MIX, CGV, KS, NQ>(map_a, map_b, out, p, smem, s.name, st)
+  int ctas = 0, rc = QUAN_OK;
+#define QUAN_IGEMM_CASE(CGV, KS) rc = launch_igemm_inst<T, MIX, CGV, KS, NQ>(map_a, map_b, out, p, smem, s.name, st, &ctas)
   if (cg == 2) {
     if (ksteps == 4) { QUAN_IGEMM_CASE(2, 4); }
-    if (ksteps == 2) { QUAN_IGEMM_CASE(2, 2); }
-    QUAN_IGEMM_CASE(2, 1);
+    else if (ksteps == 2) { QUAN_IGEMM_CASE(2, 2); }
+    else { QUAN_IGEMM_CASE(2, 1); }
+  } else {
+    if (ksteps == 4) { QUAN_IGEMM_CASE(1, 4); }
+    else if (ksteps == 2) { QUAN_IGEMM_CASE(1, 2); }
+    else { QUAN_IGEMM_CASE(1, 1); }
   }
-  if (ksteps == 4) { QUAN_IGEMM_CASE(1, 4); }
-  if (ksteps == 2) { QUAN_IGEMM_CASE(1, 2); }
-  QUAN_IGEMM_CASE(1, 1);
+  if (stat_nparts != nullptr) *stat_nparts = (rc == QUAN_OK && p.stat_part != nullptr) ? ctas : 0;
+  return rc;
 #undef QUAN_IGEMM_CASE
 }
 
@@ -1231,25 +1305,25 @@ size_t qconv_tc_workspace_bytes(const quan_conv_dims& d, int dtype, int layout, 
 
 template <typename T>
 static int tc_fwd_t(const void* x, const float* const w[4], const float* bias_r, void* y, const quan_conv_dims& d, int dtype,
-                    int dense, const Mix16& M, void* ws, cudaStream_t st) {
+                    int dense, const Mix16& M, void* ws, cudaStream_t st, double* stat_part, int* stat_nparts) {
   if (dense) {
     float* bias_out = reinterpret_cast<float*>((char*)ws + packed_weight_bytes(d, dtype, 1) - (size_t)4 * d.Co * sizeof(float) - 1024);
     int rc = pack_weights_dense<T, false>(w, bias_r, ws, bias_out, d, M, st);
     if (rc) return rc;
-    return launch_igemm<T, false, 1>(x, ws, bias_r ? bias_out : nullptr, y, fwd_shape(d, 1), dtype, M, st);
+    return launch_igemm<T, false, 1>(x, ws, bias_r ? bias_out : nullptr, y, fwd_shape(d, 1), dtype, M, st, stat_part, stat_nparts);
   }
   int rc = pack_weights<T, false>(w, ws, d, st);
   if (rc) return rc;
-  return launch_igemm<T, true, 4>(x, ws, bias_r, y, fwd_shape(d, 0), dtype, M, st);
+  return launch_igemm<T, true, 4>(x, ws, bias_r, y, fwd_shape(d, 0), dtype, M, st, stat_part, stat_nparts);
 }
 
 int qconv_tc_fwd(const void* x, const float* const w[4], const float* bias_r, void* y, const quan_conv_dims& d, int dtype,
-                 int mode, const float* mix, void* ws, size_t ws_bytes, cudaStream_t st) {
+                 int mode, const float* mix, void* ws, size_t ws_bytes, cudaStream_t st, double* stat_part, int* stat_nparts) {
   const int dense = mode == TC_DENSE;
   QUAN_REQUIRE(ws_bytes >= packed_weight_bytes(d, dtype, dense), QUAN_E_WORKSPACE, "tcgen05 fwd: workspace too small");
   const Mix16 M = make_mix(mix);
-  if (dtype == QUAN_BF16) return tc_fwd_t<__nv_bfloat16>(x, w, bias_r, y, d, dtype, dense, M, ws, st);
-  return tc_fwd_t<float>(x, w, bias_r, y, d, dtype, dense, M, ws, st);
+  if (dtype == QUAN_BF16) return tc_fwd_t<__nv_bfloat16>(x, w, bias_r, y, d, dtype, dense, M, ws, st, stat_part, stat_nparts);
+  return tc_fwd_t<float>(x, w, bias_r, y, d, dtype, dense, M, ws, st, stat_part, stat_nparts);
 }
 
 template <typename T>

@@ -14,7 +14,12 @@ import torch.distributed as dist
 from . import ops
 from ._lib import ACT_NONE, ACT_SILU, ALGO_AUTO
 
-_state = {"layout": ops.LAYOUT_BHWQC}
+_state = {"layout": ops.LAYOUT_BHWQC, "epilogue_stats": True}
+
+
+def set_epilogue_stats(on: bool) -> None:
+    """Fused `Conv` node: take the IQBN batch statistics from the conv epilogue (default) or from a pass over y."""
+    _state["epilogue_stats"] = bool(on)
 
 
 def set_internal_layout(name: str) -> None:
@@ -138,10 +143,16 @@ class _ConvBlock(torch.autograd.Function):
                 algo, eps, momentum, act):
         x, layout = ops.as_layout(x, _state["layout"])
         ws = (w_r, w_i, w_j, w_k)
-        y = ops.qconv2d_fwd(x, ws, None, stride, padding, dilation, groups, mix, algo, layout)
+        # the tensor-core epilogue also leaves per-CTA partial IQBN sums of y in the IQBN workspace: no statistics pass over y
+        y, nparts = ops.qconv2d_fwd(x, ws, None, stride, padding, dilation, groups, mix, algo, layout,
+                                    with_stats=_state["epilogue_stats"])
         g32, b32 = ops._f32c(gamma), ops._f32c(beta)
         B, C_, H, W, _ = y.shape
-        stats = ops.iqbn_train_stats(y, layout, g32, b32, eps, momentum, running_mean, running_var)
+        if nparts > 0:
+            stats = ops.iqbn_finalize_partials(nparts, float(B * H * W), C_, g32, b32, eps, momentum, running_mean,
+                                               running_var)
+        else:
+            stats = ops.iqbn_train_stats(y, layout, g32, b32, eps, momentum, running_mean, running_var)
         out = ops.iqbn_apply_fwd(y, layout, stats, g32, b32, act)
         ctx.save_for_backward(x, y, stats, g32, b32, w_r, w_i, w_j, w_k)
         ctx.conf = (tuple(stride), tuple(padding), tuple(dilation), int(groups), tuple(mix), algo, layout, act,

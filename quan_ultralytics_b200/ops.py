@@ -321,7 +321,9 @@ def _weights_arg(ws: Sequence[torch.Tensor]):
 
 def qconv2d_fwd(x: torch.Tensor, weights: Sequence[torch.Tensor], bias_r: Optional[torch.Tensor], stride, padding,
                 dilation, groups: int, mix_matrix: Sequence[float], algo: int = ALGO_AUTO,
-                layout: Optional[int] = None) -> torch.Tensor:
+                layout: Optional[int] = None, with_stats: bool = False):
+    """y = M (W_sep * x).  with_stats=True returns (y, nparts): the tensor-core epilogue also wrote per-CTA partial IQBN
+    sums of y into the IQBN workspace of C_o (nparts slots; 0 = not produced, run iqbn_train_stats on y instead)."""
     _require_cuda(x, *weights, bias_r)
     x, layout = as_layout(x, layout)
     ws = [_f32c(w) for w in weights]
@@ -338,10 +340,29 @@ def qconv2d_fwd(x: torch.Tensor, weights: Sequence[torch.Tensor], bias_r: Option
     nws = lib.quan_qconv2d_workspace_bytes(C.byref(d), _dtype_code(x), layout, algo)
     wsb = _workspace(nws, x.device)
     wa = _weights_arg(ws)
+    if with_stats:
+        iws = _iqbn_workspace(d.Co, x.device)
+        nparts = C.c_int(0)
+        check(lib.quan_qconv2d_fwd_stats(x.data_ptr(), C.cast(wa, C.c_void_p), _ptr(bias_r), y.data_ptr(), C.byref(d),
+                                         _dtype_code(x), layout, C.cast(_mix_arg(mix_matrix), C.c_void_p), algo,
+                                         wsb.data_ptr(), wsb.numel(), iws.data_ptr(), iws.numel(), C.byref(nparts),
+                                         _stream(x)), "quan_qconv2d_fwd_stats")
+        return y, nparts.value
     check(lib.quan_qconv2d_fwd(x.data_ptr(), C.cast(wa, C.c_void_p), _ptr(bias_r), y.data_ptr(), C.byref(d),
                                _dtype_code(x), layout, C.cast(_mix_arg(mix_matrix), C.c_void_p), algo, wsb.data_ptr(),
                                wsb.numel(), _stream(x)), "quan_qconv2d_fwd")
     return y
+
+
+def iqbn_finalize_partials(nparts: int, count: float, C_: int, gamma, beta, eps: float, momentum: float,
+                           running_mean: Optional[torch.Tensor], running_var: Optional[torch.Tensor]) -> torch.Tensor:
+    """Second half of iqbn_train_stats on partial sums a conv epilogue left in the IQBN workspace (qconv2d_fwd with_stats)."""
+    stats = torch.empty(20 * C_, dtype=torch.float32, device=gamma.device)
+    ws = _iqbn_workspace(C_, gamma.device)
+    check(_lib.load().quan_iqbn_finalize_partials(ws.data_ptr(), int(nparts), float(count), C_, gamma.data_ptr(),
+                                                  beta.data_ptr(), eps, momentum, _ptr(running_mean), _ptr(running_var),
+                                                  stats.data_ptr(), _stream(gamma)), "quan_iqbn_finalize_partials")
+    return stats
 
 
 def qconv2d_bwd(dy: torch.Tensor, x: torch.Tensor, weights: Sequence[torch.Tensor], stride, padding, dilation,

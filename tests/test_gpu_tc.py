@@ -169,6 +169,40 @@ def test_fused_conv_block_matches_separate_nodes(cfg):
                        blk.bn.gamma.grad.clone(), blk.bn.beta.grad.clone(), blk.bn.running_var.clone())
     # fp32: G is the same value up to FMA grouping, then truncated to tf32 by the tensor core
     tol = 1e-2 if dtype == torch.bfloat16 else 1e-4
-    assert torch.equal(outs[True][0], outs[False][0]) and torch.equal(outs[True][6], outs[False][6])
+    # the fused node takes the batch statistics from the conv epilogue (fp32 accumulators, before y is rounded to bf16)
+    assert rel(outs[True][0], outs[False][0]) <= tol and rel(outs[True][6], outs[False][6]) <= tol
     for a, b in zip(outs[True][1:6], outs[False][1:6]):
         assert rel(a, b) <= tol
+
+
+@pytest.mark.parametrize("cfg", [("sep_bf16", "bf16", 9, 64, 128, 30, 26, 3, 1), ("sep_f32", "f32", 5, 64, 64, 17, 19, 3, 2),
+                                 ("dense_bf16", "bf16", 40, 16, 32, 64, 64, 3, 1), ("dense_k1", "bf16", 7, 8, 16, 33, 31, 1, 1),
+                                 ("sep_persist", "bf16", 70, 64, 64, 32, 32, 3, 1)], ids=lambda c: c[0])
+def test_conv_epilogue_emits_iqbn_statistics(cfg):
+    """quan_qconv2d_fwd_stats: per-CTA partial sums from the tensor-core epilogue, folded by quan_iqbn_finalize_partials,
+    against the streaming statistics kernel on the stored output (ragged tiles, masked spare tiles, multi-unit CTAs)."""
+    name, dt, B, ci, co, H, W, k, s_ = cfg
+    dtype = torch.bfloat16 if dt == "bf16" else torch.float32
+    torch.manual_seed(21)
+    x = (torch.randn(B, ci, H, W, 4, device=DEV) + 0.3).to(dtype).contiguous(memory_format=torch.channels_last_3d)
+    w = [torch.randn(co, ci, k, k, device=DEV) / (ci * k * k) ** 0.5 for _ in range(4)]
+    args = ((s_, s_), (k // 2, k // 2), (1, 1), 1, ops.M_A)
+    y, nparts = ops.qconv2d_fwd(x, w, None, *args, ops.ALGO_AUTO, L, with_stats=True)
+    if name.startswith("sep"):
+        # the separable (wide) form only emits statistics when forced (QUAN_TC_EPI_STATS=2): its epilogue has no slack
+        import os
+        if os.environ.get("QUAN_TC_EPI_STATS") != "2":
+            assert nparts == 0
+            pytest.skip("separable-form epilogue statistics are opt-in (QUAN_TC_EPI_STATS=2)")
+    assert nparts > 0, "the dense form emits the partial sums"
+    g, b = torch.rand(co, 4, device=DEV) + 0.5, torch.randn(co, 4, device=DEV)
+    rm, rv = torch.zeros(co, 4, device=DEV), torch.ones(co, 4, device=DEV)
+    cnt = float(y.shape[0] * y.shape[2] * y.shape[3])
+    st = ops.iqbn_finalize_partials(nparts, cnt, co, g, b, 1e-5, 0.1, rm, rv)
+    rm2, rv2 = torch.zeros(co, 4, device=DEV), torch.ones(co, 4, device=DEV)
+    st_ref = ops.iqbn_train_stats(y, L, g, b, 1e-5, 0.1, rm2, rv2)
+    tol = 4e-3 if dtype == torch.bfloat16 else 1e-5      # bf16: the reference pass sees y after rounding to bf16
+    n = 4 * co
+    for lo, hi in ((0, n), (n, 2 * n), (2 * n, 3 * n), (3 * n, 4 * n), (4 * n, 5 * n)):   # mean | var | rstd | scaleT | shiftT
+        assert rel(st[lo:hi], st_ref[lo:hi]) <= tol
+    assert rel(rm, rm2) <= tol and rel(rv, rv2) <= tol
