@@ -358,6 +358,23 @@ def run_yolo11n_trace(a):
         tot = sum(r[0] for r in rows)
         for t, txt in sorted(rows, reverse=True):
             print(f"{100 * t / tot:5.1f}%  {txt}", flush=True)
+    if os.environ.get("QUAN_TRACE_KERNELS"):
+        # warm per-kernel device times inside the (eager) step, from the library's event pairs
+        import ctypes
+        lib.quan_kernel_timing_enable(1)
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        lib.quan_kernel_timing_enable(0)
+        n = lib.quan_kernel_timing_report(None, 0)
+        buf = ctypes.create_string_buffer(n + 16)
+        lib.quan_kernel_timing_report(buf, n + 16)
+        rows = [ln.split() for ln in buf.value.decode().splitlines()]
+        tot = sum(float(r[2]) for r in rows)
+        for name, cnt, ms in sorted(rows, key=lambda r: -float(r[2])):
+            print(f"{float(ms) / 3:8.3f} ms/step {int(cnt) // 3:5d} launches {100 * float(ms) / tot:5.1f}%  "
+                  f"{1e3 * float(ms) / int(cnt):7.1f} us avg  {name}", flush=True)
+        print(f"{tot / 3:8.3f} ms/step in library kernels", flush=True)
     run = step
     launches_per_step = None
     if a.graph:

@@ -58,7 +58,8 @@ typedef struct quan_conv_dims {
 } quan_conv_dims;
 
 /* Which engine a conv call should use.  AUTO picks tcgen05 when the shape qualifies. */
-enum quan_conv_algo { QUAN_ALGO_AUTO = 0, QUAN_ALGO_DIRECT = 1, QUAN_ALGO_TCGEN05 = 2, QUAN_ALGO_DEPTHWISE = 3 };
+enum quan_conv_algo { QUAN_ALGO_AUTO = 0, QUAN_ALGO_DIRECT = 1, QUAN_ALGO_TCGEN05 = 2, QUAN_ALGO_DEPTHWISE = 3,
+                      QUAN_ALGO_SMALLC = 4 /* 1..8 quaternion channels: one thread per pixel */ };
 
 /* ---- library ------------------------------------------------------------------------------- */
 int         quan_version(void);                 /* QUAN_ABI_VERSION */
@@ -189,7 +190,7 @@ int quan_qconv2d_bwd_premixed(const void* g, const void* x, const float* const w
                               float* dbias_r, const quan_conv_dims* d, int dtype, int layout, const float* mix, int algo,
                               void* workspace, size_t ws_bytes, void* stream);
 int quan_qconv2d_bwd_wants_mixed(const quan_conv_dims* d, int dtype, int layout, int algo, int need_dx, int need_dw);
-/* reports which engine AUTO would pick for this shape: QUAN_ALGO_DIRECT, QUAN_ALGO_TCGEN05 or QUAN_ALGO_DEPTHWISE */
+/* reports which engine AUTO would pick for this shape: QUAN_ALGO_DIRECT, QUAN_ALGO_TCGEN05, QUAN_ALGO_DEPTHWISE or QUAN_ALGO_SMALLC */
 int quan_qconv2d_pick_algo(const quan_conv_dims* d, int dtype, int layout, int pass /*0 fwd,1 dgrad,2 wgrad*/);
 
 /* Optional per-kernel device timing for benchmarks (no reference counterpart): while enabled, every kernel the library

@@ -15,7 +15,7 @@ LIB_PATH = _PKG / "libquan_sm100.so"
 F32, BF16 = 0, 1
 LAYOUT_BCHWQ, LAYOUT_BHWQC = 0, 1
 ACT_NONE, ACT_SILU = 0, 1
-ALGO_AUTO, ALGO_DIRECT, ALGO_TCGEN05, ALGO_DEPTHWISE = 0, 1, 2, 3
+ALGO_AUTO, ALGO_DIRECT, ALGO_TCGEN05, ALGO_DEPTHWISE, ALGO_SMALLC = 0, 1, 2, 3, 4
 
 
 class ConvDims(C.Structure):

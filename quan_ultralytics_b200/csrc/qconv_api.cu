@@ -21,6 +21,9 @@ static int validate(const quan_conv_dims* d, int dtype, int layout, const float*
   return QUAN_OK;
 }
 
+// engines whose backward kernels read the raw output gradient (M^T applied on load)
+static bool raw_dy(int algo) { return algo == QUAN_ALGO_DEPTHWISE || algo == QUAN_ALGO_SMALLC; }
+
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 static size_t g_bytes(const quan_conv_dims& d, int dtype) {
@@ -31,10 +34,12 @@ static size_t g_bytes(const quan_conv_dims& d, int dtype) {
 static int resolve_algo(const quan_conv_dims& d, int dtype, int layout, int pass, int algo) {
   if (algo == QUAN_ALGO_DIRECT) return QUAN_ALGO_DIRECT;
   if (algo == QUAN_ALGO_DEPTHWISE) return qconv_dw_supported(d, dtype, layout, pass) ? QUAN_ALGO_DEPTHWISE : -1;
+  if (algo == QUAN_ALGO_SMALLC) return qconv_small_supported(d, dtype, layout, pass) ? QUAN_ALGO_SMALLC : -1;
   const bool ok = qconv_tc_supported(d, dtype, layout, pass);
   if (algo == QUAN_ALGO_TCGEN05) return ok ? QUAN_ALGO_TCGEN05 : -1;
   if (ok) return QUAN_ALGO_TCGEN05;
-  return qconv_dw_supported(d, dtype, layout, pass) ? QUAN_ALGO_DEPTHWISE : QUAN_ALGO_DIRECT;
+  if (qconv_dw_supported(d, dtype, layout, pass)) return QUAN_ALGO_DEPTHWISE;
+  return qconv_small_supported(d, dtype, layout, pass) ? QUAN_ALGO_SMALLC : QUAN_ALGO_DIRECT;
 }
 
 }  // namespace quan
@@ -73,6 +78,7 @@ static int qconv2d_fwd_impl(const void* x, const float* const w[4], const float*
   const int a = resolve_algo(*d, dtype, layout, PASS_FWD, algo);
   QUAN_REQUIRE(a > 0, QUAN_E_UNSUPPORTED, "qconv2d_fwd: requested engine does not serve this shape/layout");
   if (a == QUAN_ALGO_DEPTHWISE) return qconv_dw_fwd(x, w, bias_r, y, *d, dtype, mix, st);
+  if (a == QUAN_ALGO_SMALLC) return qconv_small_fwd(x, w, bias_r, y, *d, dtype, mix, st);
   if (a == QUAN_ALGO_TCGEN05) {
     const size_t need = qconv_tc_workspace_bytes(*d, dtype, layout, PASS_FWD);
     QUAN_REQUIRE(workspace != nullptr && ws_bytes >= need, QUAN_E_WORKSPACE,
@@ -131,10 +137,10 @@ static int qconv2d_bwd_impl(const void* dy, const void* x, const float* const w[
     if (a_dw == QUAN_ALGO_TCGEN05) m_dw = qconv_tc_mode(*d, dtype, layout, PASS_WGRAD);
   }
   // G = M^T dY, once, shared by every consumer that needs it (separable dgrad / wgrad, direct engine, bias grad)
-  const bool need_g = (dx != nullptr && m_dx != TC_DENSE && a_dx != QUAN_ALGO_DEPTHWISE) ||
-                      (dw != nullptr && m_dw != TC_DENSE && a_dw != QUAN_ALGO_DEPTHWISE) || dbias_r != nullptr;
-  QUAN_REQUIRE(!premixed || ((dx == nullptr || (m_dx != TC_DENSE && a_dx != QUAN_ALGO_DEPTHWISE)) &&
-                             (dw == nullptr || (m_dw != TC_DENSE && a_dw != QUAN_ALGO_DEPTHWISE))),
+  const bool need_g = (dx != nullptr && m_dx != TC_DENSE && !raw_dy(a_dx)) ||
+                      (dw != nullptr && m_dw != TC_DENSE && !raw_dy(a_dw)) || dbias_r != nullptr;
+  QUAN_REQUIRE(!premixed || ((dx == nullptr || (m_dx != TC_DENSE && !raw_dy(a_dx))) &&
+                             (dw == nullptr || (m_dw != TC_DENSE && !raw_dy(a_dw)))),
                QUAN_E_UNSUPPORTED, "qconv2d_bwd_premixed: this shape's dgrad/wgrad consume the raw gradient (dense / depthwise form)");
   if (need_g && !premixed) {
     float mix_t[16];
@@ -152,6 +158,8 @@ static int qconv2d_bwd_impl(const void* dy, const void* x, const float* const w[
       rc = qconv_tc_dgrad(m_dx == TC_DENSE ? dy : gq, w, dx, *d, dtype, m_dx, mix, tc_ws, tc_ws_bytes, st);
     } else if (a_dx == QUAN_ALGO_DEPTHWISE) {
       rc = qconv_dw_dgrad(dy, w, dx, *d, dtype, mix, st);
+    } else if (a_dx == QUAN_ALGO_SMALLC) {
+      rc = qconv_small_dgrad(dy, w, dx, *d, dtype, mix, st);
     } else {
       rc = qconv_dgrad_direct_launch(gq, w, dx, *d, dtype, layout, st);
     }
@@ -164,6 +172,8 @@ static int qconv2d_bwd_impl(const void* dy, const void* x, const float* const w[
       rc = qconv_tc_wgrad(m_dw == TC_DENSE ? dy : gq, x, dw, *d, dtype, m_dw, mix, tc_ws, tc_ws_bytes, st);
     } else if (a_dw == QUAN_ALGO_DEPTHWISE) {
       rc = qconv_dw_wgrad(dy, x, dw, *d, dtype, mix, st);
+    } else if (a_dw == QUAN_ALGO_SMALLC) {
+      rc = qconv_small_wgrad(dy, x, dw, *d, dtype, mix, st);
     } else {
       rc = qconv_wgrad_direct_launch(gq, x, dw, *d, dtype, layout, st);
     }
@@ -196,7 +206,7 @@ int quan_qconv2d_bwd_wants_mixed(const quan_conv_dims* d, int dtype, int layout,
     if (pass == PASS_DGRAD ? !need_dx : !need_dw) continue;
     const int a = resolve_algo(*d, dtype, layout, pass, algo);
     if (a <= 0) return 0;
-    if (a == QUAN_ALGO_DEPTHWISE) return 0;
+    if (a == QUAN_ALGO_DEPTHWISE || a == QUAN_ALGO_SMALLC) return 0;
     if (a == QUAN_ALGO_TCGEN05 && qconv_tc_mode(*d, dtype, layout, pass) == TC_DENSE) return 0;
   }
   return 1;

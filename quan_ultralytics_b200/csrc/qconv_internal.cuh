@@ -22,6 +22,15 @@ int qconv_dw_dgrad(const void* dy, const float* const w[4], void* dx, const quan
 int qconv_dw_wgrad(const void* dy, const void* x, float* const dw[4], const quan_conv_dims& d, int dtype, const float* mix,
                    cudaStream_t st);
 
+// ---- small-channel streaming kernels (BHWQC, 1..8 quaternion channels), qconv_small.cu: take dY itself -----------
+bool qconv_small_supported(const quan_conv_dims& d, int dtype, int layout, int pass);
+int qconv_small_fwd(const void* x, const float* const w[4], const float* bias_r, void* y, const quan_conv_dims& d, int dtype,
+                    const float* mix, cudaStream_t st);
+int qconv_small_dgrad(const void* dy, const float* const w[4], void* dx, const quan_conv_dims& d, int dtype, const float* mix,
+                      cudaStream_t st);
+int qconv_small_wgrad(const void* dy, const void* x, float* const dw[4], const quan_conv_dims& d, int dtype, const float* mix,
+                      cudaStream_t st);
+
 // ---- tcgen05 (tensor-core) engine, qconv_tc.cu ----------------------------------------------------
 enum { PASS_FWD = 0, PASS_DGRAD = 1, PASS_WGRAD = 2 };
 // how the implicit-GEMM kernels serve a shape: not at all, one GEMM per quaternion component (mix in the epilogue),

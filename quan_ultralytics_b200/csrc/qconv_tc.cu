@@ -538,6 +538,8 @@ struct TcWgradParams {
   uint32_t sbo_bytes, layout_type;   // bf16: 8-row groups, SWIZZLE_128B; tf32: 4-row groups, SWIZZLE_128B_BASE32B
   uint32_t a_stage_bytes, b_stage_bytes, idesc, tmem_cols;
   float* partial;              // [splits][nq][taps][Co][Ci]
+  int atomic;                  // 1: every split adds into ONE zero-initialised partial set with vector atomics (narrow
+                               // layers: many splits of a tiny dW — the fold of 64 partial sets cost more than the GEMM)
 };
 
 constexpr int WG_PIX = 64;     // pixels (K) per pipeline stage
@@ -657,7 +659,7 @@ qconv_wgrad_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_const
     const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
     for (int t = 0; t < p.TG; ++t) {
       const int tap = kh * p.kW + t;
-      float* dst = p.partial + ((((int64_t)split * p.nq + q) * p.taps + tap) * p.Co + co) * p.Ci + ci0;
+      float* dst = p.partial + ((((int64_t)(p.atomic ? 0 : split) * p.nq + q) * p.taps + tap) * p.Co + co) * p.Ci + ci0;
       for (int c0 = 0; c0 < N; c0 += 16) {
         float acc[16];
         ptx::tmem_ld16(lane_base + (uint32_t)(t * N + c0), acc);
@@ -666,7 +668,8 @@ qconv_wgrad_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_const
 #pragma unroll
           for (int v = 0; v < 4; ++v) {
             float part[4] = {acc[v * 4], acc[v * 4 + 1], acc[v * 4 + 2], acc[v * 4 + 3]};
-            store_vec<float, 4>(dst + c0 + v * 4, part);
+            if (p.atomic) atomicAdd(reinterpret_cast<float4*>(dst + c0 + v * 4), make_float4(part[0], part[1], part[2], part[3]));
+            else store_vec<float, 4>(dst + c0 + v * 4, part);
           }
         }
       }
@@ -1202,6 +1205,10 @@ static int launch_wgrad(const void* gq, const void* x, float* const dw[4], const
   p.idesc = ptx::make_idesc(sizeof(T) == 2 ? 1u : 2u, 1u, 1u, 128u, (uint32_t)(w.NA * w.NB));
   p.tmem_cols = (uint32_t)pow2_ceil(w.TG * w.NA * w.NB < 32 ? 32 : w.TG * w.NA * w.NB);
   p.partial = reinterpret_cast<float*>(ws);
+  // dense form with many splits: accumulate with atomics (summation order is then not deterministic, as in the direct engine)
+  p.atomic = (dense && w.splits > 4) ? 1 : 0;
+  if (p.atomic) QUAN_CUDA(cudaMemsetAsync(ws, 0, w.partial_bytes / w.splits, st));
+  const int fold_splits = p.atomic ? 1 : w.splits;
 
   CUtensorMap map_g, map_x;
   {
@@ -1239,15 +1246,15 @@ static int launch_wgrad(const void* gq, const void* x, float* const dw[4], const
     // split lanes per element: short rows with many splits (narrow layers) spread the split loop over the idle threads
     int SL = 256 / (cchunk * p.taps);
     if (SL > 8) SL = 8;
-    if (SL > w.splits) SL = w.splits;
+    if (SL > fold_splits) SL = fold_splits;
     if (SL < 1) SL = 1;
     dim3 rgrid((unsigned)((d.Ci + cchunk - 1) / cchunk), (unsigned)(4 * d.Co));
     const size_t rsmem = (size_t)(SL > 1 ? 256 : cchunk * p.taps) * sizeof(float) + 16;
     QUAN_TIMED(st);
     if (dense)
-      wgrad_reduce_kernel<true><<<rgrid, 256, rsmem, st>>>(p.partial, dw[0], dw[1], dw[2], dw[3], w.splits, p.taps, d.Co, d.Ci, cchunk, SL, mix);
+      wgrad_reduce_kernel<true><<<rgrid, 256, rsmem, st>>>(p.partial, dw[0], dw[1], dw[2], dw[3], fold_splits, p.taps, d.Co, d.Ci, cchunk, SL, mix);
     else
-      wgrad_reduce_kernel<false><<<rgrid, 256, rsmem, st>>>(p.partial, dw[0], dw[1], dw[2], dw[3], w.splits, p.taps, d.Co, d.Ci, cchunk, SL, mix);
+      wgrad_reduce_kernel<false><<<rgrid, 256, rsmem, st>>>(p.partial, dw[0], dw[1], dw[2], dw[3], fold_splits, p.taps, d.Co, d.Ci, cchunk, SL, mix);
   }
   QUAN_CHECK_LAUNCH("wgrad_reduce_kernel");
   return QUAN_OK;

@@ -12,7 +12,7 @@ from typing import Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import (ACT_NONE, ACT_SILU, ALGO_AUTO, ALGO_DEPTHWISE, ALGO_DIRECT, ALGO_TCGEN05, BF16, F32, LAYOUT_BCHWQ, LAYOUT_BHWQC,
+from ._lib import (ACT_NONE, ACT_SILU, ALGO_AUTO, ALGO_DEPTHWISE, ALGO_DIRECT, ALGO_SMALLC, ALGO_TCGEN05, BF16, F32, LAYOUT_BCHWQ, LAYOUT_BHWQC,
                    ConvDims, PtrArray4, check)
 
 # Mixing matrices of the reference
@@ -371,8 +371,9 @@ def qconv2d_bwd(dy: torch.Tensor, x: torch.Tensor, weights: Sequence[torch.Tenso
     """Returns (dx or None, [dw_r, dw_i, dw_j, dw_k] or None, db_r or None).  `premixed`: dy already holds G = M^T dY
     (emitted by iqbn_bwd_apply(mix_t=...)); legal only when qconv2d_bwd_wants_mixed() says so."""
     _require_cuda(dy, x, *weights)
-    x, layout = as_layout(x)
-    dy, _ = as_layout(dy, layout)
+    # the gradient decides the layout: a C_q = 1 input (first layer) is the same bytes in both layouts
+    dy, layout = as_layout(dy)
+    x, _ = as_layout(x, layout)
     ws = [_f32c(w) for w in weights]
     d = conv_dims(x.shape, ws[0].shape, stride, padding, dilation, groups)
     lib = _lib.load()

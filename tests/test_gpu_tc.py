@@ -89,6 +89,8 @@ def test_tc_is_what_auto_picks_for_the_sweep_shapes():
     assert ops.qconv2d_pick_algo((16, 64, 32, 32, 4), (64, 2, 3, 3), (1, 1), (1, 1), (1, 1), 32, torch.bfloat16, L, 0) \
         == ops.ALGO_DIRECT
     assert ops.qconv2d_pick_algo((16, 2, 32, 32, 4), (4, 2, 3, 3), (1, 1), (1, 1), (1, 1), 1, torch.bfloat16, L, 0) \
+        == ops.ALGO_SMALLC
+    assert ops.qconv2d_pick_algo((16, 3, 32, 32, 4), (5, 3, 3, 3), (1, 1), (1, 1), (1, 1), 1, torch.bfloat16, L, 0) \
         == ops.ALGO_DIRECT
 
 
@@ -206,3 +208,44 @@ def test_conv_epilogue_emits_iqbn_statistics(cfg):
     for lo, hi in ((0, n), (n, 2 * n), (2 * n, 3 * n), (3 * n, 4 * n), (4 * n, 5 * n)):   # mean | var | rstd | scaleT | shiftT
         assert rel(st[lo:hi], st_ref[lo:hi]) <= tol
     assert rel(rm, rm2) <= tol and rel(rv, rv2) <= tol
+
+
+# name: (dtype, B, Ci, Co, H, W, k, s, p, d, bias, mix)
+SMALL_CASES = [
+    ("stem_1_4_s2", "bf16", 2, 1, 4, 64, 64, 3, 2, 1, 1, False, "A"),
+    ("yolo_4_2", "bf16", 2, 4, 2, 33, 31, 3, 1, 1, 1, False, "A"),
+    ("yolo_2_4", "bf16", 2, 2, 4, 32, 32, 3, 1, 1, 1, True, "B"),
+    ("f32_8_2_k5", "f32", 2, 8, 2, 20, 20, 5, 1, 2, 1, True, "A"),
+    ("f32_1_8_dil2_s2", "f32", 3, 1, 8, 21, 23, 3, 2, 2, 2, False, "B"),
+    ("f32_2_2_k1", "f32", 2, 2, 2, 16, 16, 1, 1, 0, 1, False, "A"),
+]
+
+
+@pytest.mark.parametrize("case", SMALL_CASES, ids=[c[0] for c in SMALL_CASES])
+def test_small_channel_engine_matches_direct_engine(case):
+    """One-thread-per-pixel kernels for 1..8 quaternion channels (qconv_small.cu; the QUAN-YOLO11n stem) against the
+    golden-validated generic engine."""
+    name, dt, B, Ci, Co, H, W, k, s, p, d, bias, mix = case
+    dtype = torch.bfloat16 if dt == "bf16" else torch.float32
+    tol = 1e-2 if dtype == torch.bfloat16 else 2e-5
+    torch.manual_seed(9)
+    x = torch.randn(B, Ci, H, W, 4, device=DEV).to(dtype).contiguous(memory_format=torch.channels_last_3d)
+    w = [torch.randn(Co, Ci, k, k, device=DEV) / (Ci * k * k) ** 0.5 for _ in range(4)]
+    b = torch.randn(Co, device=DEV) if bias else None
+    args = ((s, s), (p, p), (d, d), 1, ops.MIX[mix])
+    picks = [ops.qconv2d_pick_algo(x.shape, w[0].shape, *args[:4], dtype, L, ps) for ps in range(3)]
+    # the tensor-core dense form has priority where its row / N granularity allows (e.g. fp32 dgrad with 4*C_o*4 B = 32 B rows)
+    assert picks[0] == ops.ALGO_SMALLC and all(pk in (ops.ALGO_SMALLC, ops.ALGO_TCGEN05) for pk in picks)
+    if dtype == torch.float32 and ops.ALGO_TCGEN05 in picks:
+        tol = 1e-3
+    y_ref = ops.qconv2d_fwd(x, w, b, *args, ops.ALGO_DIRECT, L)
+    y = ops.qconv2d_fwd(x, w, b, *args, ops.ALGO_AUTO, L)
+    assert rel(y, y_ref) <= tol
+    dy = torch.randn_like(y_ref)
+    dx_ref, dw_ref, db_ref = ops.qconv2d_bwd(dy, x, w, *args, True, True, bias, ops.ALGO_DIRECT)
+    dx, dw, db = ops.qconv2d_bwd(dy, x, w, *args, True, True, bias, ops.ALGO_AUTO)
+    assert rel(dx, dx_ref) <= 2 * tol
+    for a, r in zip(dw, dw_ref):
+        assert rel(a, r) <= 2 * tol
+    if bias:
+        assert rel(db, db_ref) <= 1e-4
