@@ -158,6 +158,7 @@ struct TcConvParams {
   int kblocks, bk_elems;               // k-blocks per tap, elements per k-block row
   int sub;                             // (tap, k-block) sub-steps bundled into one pipeline stage (1 or 2)
   int BN, stages;
+  int dbuf;                            // NQ = 4 with 8*BN <= 512: two sets of four accumulators alternate between units
   uint32_t a_sub_bytes, b_sub_bytes;   // one sub-step's A / B tile (per CTA)
   uint32_t sbo_bytes, layout_type, idesc, tmem_cols;
   const float* bias;                   // NQ = 4: [Cout], joins S_r before the mix; NQ = 1: [Cout] added to the output
@@ -224,8 +225,8 @@ qconv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + (size_t)p.stages * b_stage_bytes);
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* tile_full = empty_bar + p.stages;     // [2]  MMA -> epilogue: all accumulators of a unit are complete
-  uint64_t* acc_empty = tile_full + 2;            // [4]  epilogue -> MMA: accumulator a has been read out
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 4);
+  uint64_t* acc_empty = tile_full + 2;            // [8]  epilogue -> MMA: accumulator a has been read out
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 8);
   float* sacc = reinterpret_cast<float*>(tmem_ptr + 4);   // [2][4][C_o] sum / sum of squares of this CTA's outputs (fused IQBN stats)
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform
@@ -243,7 +244,7 @@ qconv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       ptx::mbar_init(empty_bar + s, 1);
     }
     for (int i = 0; i < 2; ++i) ptx::mbar_init(tile_full + i, 1);
-    for (int i = 0; i < 4; ++i) ptx::mbar_init(acc_empty + i, EPI_WARPS * CG);
+    for (int i = 0; i < 8; ++i) ptx::mbar_init(acc_empty + i, EPI_WARPS * CG);
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
@@ -319,8 +320,8 @@ qconv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         const int iters_per_q = (p.tt.start[cls + 1] - p.tt.start[cls]) * p.kblocks;
         for (int q = 0; q < NQ; ++q) {
           // accumulator a is reused every NACC/NQ units: wait until the epilogue warps (of both CTAs) have read it out
-          const uint32_t a = NQ == 4 ? (uint32_t)q : (t_local & 1u);
-          const uint32_t use = NQ == 4 ? t_local : (t_local >> 1);
+          const uint32_t a = NQ == 4 ? (uint32_t)q + (p.dbuf ? 4u * (t_local & 1u) : 0u) : (t_local & 1u);
+          const uint32_t use = (NQ == 4 && !p.dbuf) ? t_local : (t_local >> 1);
           ptx::mbar_wait(acc_empty + a, (use & 1u) ^ 1u);
           ptx::tc_fence_after();
           const uint32_t d_tmem = tmem_u + a * (uint32_t)p.BN;
@@ -352,7 +353,7 @@ qconv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         }
         // every accumulator of this unit is complete once the MMAs issued so far have retired
         if (ptx::elect_one()) {
-          uint64_t* tf = tile_full + (NTB == 2 ? (t_local & 1u) : 0u);
+          uint64_t* tf = tile_full + ((NTB == 2 || p.dbuf) ? (t_local & 1u) : 0u);
           if constexpr (CG == 2) ptx::umma_commit_2cta(tf, 3);
           else ptx::umma_commit(tf);
         }
@@ -388,22 +389,26 @@ qconv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       const bool valid = (wo < p.Wo) && (ho < p.Ho) && (b < p.B);
       T* yrow = y + ((((int64_t)b * p.Ho + ho) * p.Wo + wo) * NQ) * p.Cout + n0;
       if constexpr (NQ == 4) {
-        ptx::mbar_wait(tile_full, t_local & 1u);
+        // dbuf (BN <= 64): the unit's accumulator set alternates, the whole epilogue overlaps the next unit's mainloop
+        const uint32_t set = p.dbuf ? (t_local & 1u) : 0u;
+        const uint32_t set_base = lane_base + set * 4u * (uint32_t)p.BN;
+        uint64_t* set_empty = acc_empty + 4 * set;
+        ptx::mbar_wait(tile_full + set, (p.dbuf ? (t_local >> 1) : t_local) & 1u);
         ptx::tc_fence_after();
         // stash this warp's chunks of S_0, then hand accumulator 0 back to the MMA thread
         float st[4][16];
 #pragma unroll
         for (int ci = 0; ci < 4; ++ci)
-          if (ci * 2 + half < nchunks) ptx::tmem_ld16(lane_base + (uint32_t)((ci * 2 + half) * 16), st[ci]);
+          if (ci * 2 + half < nchunks) ptx::tmem_ld16(set_base + (uint32_t)((ci * 2 + half) * 16), st[ci]);
         ptx::tmem_ld_wait();
-        release(acc_empty + 0);
+        release(set_empty + 0);
 #pragma unroll
         for (int ci = 0; ci < 4; ++ci) {
           const int c0 = (ci * 2 + half) * 16;
           if (ci * 2 + half < nchunks) {
             float acc[3][16];
 #pragma unroll
-            for (int q = 1; q < 4; ++q) ptx::tmem_ld16(lane_base + (uint32_t)(q * p.BN + c0), acc[q - 1]);
+            for (int q = 1; q < 4; ++q) ptx::tmem_ld16(set_base + (uint32_t)(q * p.BN + c0), acc[q - 1]);
             ptx::tmem_ld_wait();
             if (p.bias != nullptr) {
 #pragma unroll
@@ -452,8 +457,8 @@ qconv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         if (ptx::elect_one()) {
 #pragma unroll
           for (int a = 1; a < 4; ++a) {
-            if constexpr (CG == 2) ptx::mbar_arrive_cluster(acc_empty + a, 0);
-            else ptx::mbar_arrive(acc_empty + a);
+            if constexpr (CG == 2) ptx::mbar_arrive_cluster(set_empty + a, 0);
+            else ptx::mbar_arrive(set_empty + a);
           }
         }
         __syncwarp();
@@ -941,7 +946,9 @@ static int launch_igemm(const void* in, const void* wpacked, const float* bias, 
   p.sbo_bytes = 8u * row_bytes;
   p.layout_type = row_bytes == 128 ? 2u : row_bytes == 64 ? 4u : 6u;
   p.idesc = ptx::make_idesc(sizeof(T) == 2 ? 1u : 2u, 0u, 0u, 128u * cg, (uint32_t)p.BN);
-  const int acc_cols = (NQ == 4 ? 4 : 2) * p.BN;
+  p.dbuf = (NQ == 4 && 8 * p.BN <= 512) ? 1 : 0;
+  if (const char* e = getenv("QUAN_TC_DBUF")) { if (atoi(e) == 0) p.dbuf = 0; }
+  const int acc_cols = (NQ == 4 ? (p.dbuf ? 8 : 4) : 2) * p.BN;
   p.tmem_cols = (uint32_t)pow2_ceil(acc_cols < 32 ? 32 : acc_cols);
   p.bias = bias;
   p.stat_cq = NQ == 4 ? s.N : s.N / 4;
@@ -968,7 +975,7 @@ static int launch_igemm(const void* in, const void* wpacked, const float* bias, 
   if (const char* e = getenv("QUAN_TC_STAGES")) { int v = atoi(e); if (v >= 1 && v < stages) stages = v; }
   QUAN_REQUIRE(stages >= 2, QUAN_E_UNSUPPORTED, "tcgen05 conv: stage too large");
   p.stages = stages;
-  const size_t smem = 1024 + stages * stage_bytes + (2 * stages + 6) * sizeof(uint64_t) + 16 +
+  const size_t smem = 1024 + stages * stage_bytes + (2 * stages + 10) * sizeof(uint64_t) + 16 +
                       (p.stat_part != nullptr ? (size_t)8 * p.stat_cq * sizeof(float) : 0);
 
   // A: input activations [B][Hi][Wi][nq][K] -> 5-D map {K, nq, Wi, Hi, B}

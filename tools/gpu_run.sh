@@ -1,4 +1,4 @@
-timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q -x 2>&1 | tail -2
-python tests/iqbn_probe.py | tail -1
-QUAN_IQBN_RBPS=2 python tests/iqbn_probe.py | tail -1
-QUAN_IQBN_RU=1 python tests/iqbn_probe.py | tail -1
+timeout 600 python -m pytest tests -m gpu -q -x 2>&1 | tail -3
+C=64 HW=128 python tests/conv_probe.py | tail -1
+QUAN_TC_DBUF=0 C=64 HW=128 python tests/conv_probe.py | tail -1
+python tests/conv_probe.py | tail -1
