@@ -159,6 +159,14 @@ struct TcConvParams {
   int sub;                             // (tap, k-block) sub-steps bundled into one pipeline stage (1 or 2)
   int BN, stages;
   int dbuf;                            // NQ = 4 with 8*BN <= 512: two sets of four accumulators alternate between units
+  // halo mode (stride-1, 128-byte rows, tile = 16 rows x 8 pixels of one image): ONE TMA box per (component, k-block)
+  // brings the tile's whole receptive field (halo_h x 16 pixels) and every filter tap is a UMMA descriptor that starts
+  // `arow` rows into it — the activation tile crosses L2 -> SM once instead of once per tap.
+  int halo, halo_dw, halo_dh;          // box origin relative to the tile origin (most negative tap offset)
+  int a_stages, tg;                    // A ring slots; taps per B ring slot (one filter row)
+  int halo_bo;                         // bring-up switch: put the swizzle phase of the window start into the descriptor
+  uint32_t a_halo_bytes;
+  uint16_t arow[TC_MAX_TAPS];          // tap -> first row of its window inside the halo tile ((dh - halo_dh)*16 + dw - halo_dw)
   uint32_t a_sub_bytes, b_sub_bytes;   // one sub-step's A / B tile (per CTA)
   uint32_t sbo_bytes, layout_type, idesc, tmem_cols;
   const float* bias;                   // NQ = 4: [Cout], joins S_r before the mix; NQ = 1: [Cout] added to the output
@@ -221,10 +229,12 @@ qconv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t a_stage_bytes = p.a_sub_bytes * p.sub, b_stage_bytes = p.b_sub_bytes * p.sub;
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + (size_t)p.stages * a_stage_bytes;
+  uint8_t* smem_b = smem + (p.halo ? (size_t)p.a_stages * p.a_halo_bytes : (size_t)p.stages * a_stage_bytes);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + (size_t)p.stages * b_stage_bytes);
   uint64_t* empty_bar = full_bar + p.stages;
-  uint64_t* tile_full = empty_bar + p.stages;     // [2]  MMA -> epilogue: all accumulators of a unit are complete
+  uint64_t* a_full = empty_bar + p.stages;        // [4]  halo mode: the A ring has its own barriers (B ring uses full/empty_bar)
+  uint64_t* a_empty = a_full + 4;                 // [4]
+  uint64_t* tile_full = a_empty + 4;              // [2]  MMA -> epilogue: all accumulators of a unit are complete
   uint64_t* acc_empty = tile_full + 2;            // [8]  epilogue -> MMA: accumulator a has been read out
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 8);
   float* sacc = reinterpret_cast<float*>(tmem_ptr + 4);   // [2][4][C_o] sum / sum of squares of this CTA's outputs (fused IQBN stats)
@@ -242,6 +252,10 @@ qconv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     for (int s = 0; s < p.stages; ++s) {
       ptx::mbar_init(full_bar + s, 1);
       ptx::mbar_init(empty_bar + s, 1);
+    }
+    for (int i = 0; i < 4; ++i) {
+      ptx::mbar_init(a_full + i, 1);
+      ptx::mbar_init(a_empty + i, 1);
     }
     for (int i = 0; i < 2; ++i) ptx::mbar_init(tile_full + i, 1);
     for (int i = 0; i < 8; ++i) ptx::mbar_init(acc_empty + i, EPI_WARPS * CG);
@@ -266,6 +280,47 @@ qconv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     const uint32_t sub_tx = (p.a_sub_bytes + p.b_sub_bytes) * CG;   // CG = 2: the leader's barrier counts both CTAs' bytes
     int s = 0;
     uint32_t phase = 0;
+    if (p.halo) {
+      int sa = 0;
+      uint32_t pa = 0;
+      const int ntaps = p.tt.start[1];
+      for (int unit = cluster; unit < p.units; unit += nclusters) {
+        const int nt = unit % p.ntiles_n, tile = (unit / p.ntiles_n) * CG + (int)cta_rank;
+        const int tw = tile % p.tiles_w, th = (tile / p.tiles_w) % p.tiles_h, tb = tile / tiles_per_b;
+        const int wc = tw * p.Wt + p.halo_dw, hc = th * p.Ht + p.halo_dh;
+        const int n0 = nt * p.BN;
+        const int nb0 = n0 + (int)cta_rank * (p.BN / CG);
+        for (int q = 0; q < NQ; ++q) {
+          for (int kb = 0; kb < p.kblocks; ++kb) {
+            const int kc = kb * p.bk_elems;
+            ptx::mbar_wait(a_empty + sa, pa ^ 1);
+            if (ptx::elect_one()) {
+              if (CG == 1 || cta_rank == 0) ptx::mbar_arrive_expect_tx(a_full + sa, p.a_halo_bytes * CG);
+              uint8_t* a_dst = smem_a + (size_t)sa * p.a_halo_bytes;
+              if constexpr (CG == 2) ptx::tma_load_5d_2cta(a_dst, &map_a, a_full + sa, kc, q, wc, hc, tb);
+              else ptx::tma_load_5d(a_dst, &map_a, a_full + sa, kc, q, wc, hc, tb);
+            }
+            __syncwarp();
+            if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
+            for (int t0 = 0; t0 < ntaps; t0 += p.tg) {
+              const int nt_g = min(p.tg, ntaps - t0);
+              ptx::mbar_wait(empty_bar + s, phase ^ 1);
+              if (ptx::elect_one()) {
+                if (CG == 1 || cta_rank == 0) ptx::mbar_arrive_expect_tx(full_bar + s, p.b_sub_bytes * CG * nt_g);
+                for (int t = 0; t < nt_g; ++t) {
+                  uint8_t* b_dst = smem_b + (size_t)s * b_stage_bytes + (size_t)t * p.b_sub_bytes;
+                  const int tap = p.tt.tap[t0 + t];
+                  if constexpr (CG == 2) ptx::tma_load_4d_2cta(b_dst, &map_b, full_bar + s, kc, nb0, tap, q);
+                  else ptx::tma_load_4d(b_dst, &map_b, full_bar + s, kc, n0, tap, q);
+                }
+              }
+              __syncwarp();
+              if (++s == p.stages) { s = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+    } else
     for (int unit = cluster; unit < p.units; unit += nclusters) {
       const int cls = unit / p.units_per_cls, ucls = unit - cls * p.units_per_cls;
       const int nt = ucls % p.ntiles_n, tile = (ucls / p.ntiles_n) * CG + (int)cta_rank;
@@ -315,6 +370,65 @@ qconv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       uint32_t phase = 0;
       uint64_t da = da0, db = db0;
       uint32_t t_local = 0;
+      if (p.halo) {
+        // halo mode: A descriptors walk over ONE resident tile — tap (dh,dw) starts arow = dh'*16 + dw' rows into it; the
+        // 8-row groups of the 16 image rows are 16 rows (2048 B) apart; the hardware swizzle works on absolute address bits,
+        // so an unaligned window start needs nothing else (base-offset field stays 0)
+        const uint64_t da_h = ptx::make_smem_desc(ptx::smem_u32(smem_a), 16, 16u * 128u, p.layout_type);
+        const uint64_t a_slot = (uint64_t)(p.a_halo_bytes >> 4);
+        const int ntaps = p.tt.start[1];
+        int sa = 0;
+        uint32_t pa = 0;
+        for (int unit = cluster; unit < p.units; unit += nclusters, ++t_local) {
+          for (int q = 0; q < NQ; ++q) {
+            const uint32_t a = NQ == 4 ? (uint32_t)q + (p.dbuf ? 4u * (t_local & 1u) : 0u) : (t_local & 1u);
+            const uint32_t use = (NQ == 4 && !p.dbuf) ? t_local : (t_local >> 1);
+            ptx::mbar_wait(acc_empty + a, (use & 1u) ^ 1u);
+            ptx::tc_fence_after();
+            const uint32_t d_tmem = tmem_u + a * (uint32_t)p.BN;
+            for (int kb = 0; kb < p.kblocks; ++kb) {
+              ptx::mbar_wait(a_full + sa, pa);
+              const uint64_t da_s = da_h + (uint64_t)sa * a_slot;
+              for (int t0 = 0; t0 < ntaps; t0 += p.tg) {
+                const int nt_g = min(p.tg, ntaps - t0);
+                ptx::mbar_wait(full_bar + s, phase);
+                ptx::tc_fence_after();
+                if (ptx::elect_one()) {
+                  for (int t = 0; t < nt_g; ++t) {
+                    const uint32_t ar = p.arow[t0 + t];
+                    const uint64_t dat = da_s + (uint64_t)(ar * 8u) + ((uint64_t)((ar & 7u) * (uint32_t)p.halo_bo) << 49);
+                    const uint64_t dbt = db + (uint64_t)t * b_sub;
+#pragma unroll
+                    for (int k = 0; k < KSTEPS; ++k) {
+                      if constexpr (CG == 2)
+                        ptx::umma_2cta<KIND>(d_tmem, dat + (uint64_t)(2 * k), dbt + (uint64_t)(2 * k), p.idesc, (kb | t0 | t | k) ? 1u : 0u);
+                      else
+                        ptx::umma<KIND>(d_tmem, dat + (uint64_t)(2 * k), dbt + (uint64_t)(2 * k), p.idesc, (kb | t0 | t | k) ? 1u : 0u);
+                    }
+                  }
+                  if constexpr (CG == 2) ptx::umma_commit_2cta(empty_bar + s, 3);
+                  else ptx::umma_commit(empty_bar + s);
+                }
+                __syncwarp();
+                db += b_step;
+                if (++s == p.stages) { s = 0; phase ^= 1; db = db0; }
+              }
+              if (ptx::elect_one()) {           // every tap of this (q, k-block) has been issued: the A tile may be refilled
+                if constexpr (CG == 2) ptx::umma_commit_2cta(a_empty + sa, 3);
+                else ptx::umma_commit(a_empty + sa);
+              }
+              __syncwarp();
+              if (++sa == p.a_stages) { sa = 0; pa ^= 1; }
+            }
+          }
+          if (ptx::elect_one()) {
+            uint64_t* tf = tile_full + ((NTB == 2 || p.dbuf) ? (t_local & 1u) : 0u);
+            if constexpr (CG == 2) ptx::umma_commit_2cta(tf, 3);
+            else ptx::umma_commit(tf);
+          }
+          __syncwarp();
+        }
+      } else
       for (int unit = cluster; unit < p.units; unit += nclusters, ++t_local) {
         const int cls = unit / p.units_per_cls;
         const int iters_per_q = (p.tt.start[cls + 1] - p.tt.start[cls]) * p.kblocks;
@@ -926,6 +1040,38 @@ static int launch_igemm(const void* in, const void* wpacked, const float* bias, 
   QUAN_REQUIRE(row_bytes != 0 && s.nq == NQ && build_taps(s, p.tt) &&
                    plan_tiles(s.B, (s.Ho + s.scatH - 1) / s.scatH, (s.Wo + s.scatW - 1) / s.scatW, s.sH, s.sW, t),
                QUAN_E_UNSUPPORTED, "tcgen05 conv: shape does not qualify");
+  // halo mode (see TcConvParams): stride 1, one class, 128-byte K rows, 16 x 8-pixel tiles of one image that cover the
+  // output without much waste, receptive field within a 16-pixel-wide box.  QUAN_TC_HALO=0 disables, =1 default.
+  int halo_h = 0;
+  {
+    static const int env_halo = [] { const char* e = getenv("QUAN_TC_HALO"); return e ? atoi(e) : 1; }();
+    int dwmin = 0, dwmax = 0, dhmin = 0, dhmax = 0;
+    for (int i = 0; i < p.tt.start[1]; ++i) {
+      dwmin = i ? (p.tt.dw[i] < dwmin ? p.tt.dw[i] : dwmin) : p.tt.dw[i];
+      dwmax = i ? (p.tt.dw[i] > dwmax ? p.tt.dw[i] : dwmax) : p.tt.dw[i];
+      dhmin = i ? (p.tt.dh[i] < dhmin ? p.tt.dh[i] : dhmin) : p.tt.dh[i];
+      dhmax = i ? (p.tt.dh[i] > dhmax ? p.tt.dh[i] : dhmax) : p.tt.dh[i];
+    }
+    const int tw8 = (s.Wo + 7) / 8, th16 = (s.Ho + 15) / 16;
+    const double cover = (double)s.Ho * s.Wo / ((double)tw8 * 8 * th16 * 16);
+    halo_h = 16 + dhmax - dhmin;
+    const size_t a_bytes = (size_t)halo_h * 16 * 128;
+    p.halo = env_halo && NQ == 4 && row_bytes == 128 && p.tt.ncls == 1 && s.sH == 1 && s.sW == 1 && p.tt.start[1] > 1 &&
+             8 + dwmax - dwmin <= 16 && halo_h <= 256 && 2 * a_bytes <= 96 * 1024 && cover >= 0.8;
+    if (p.halo) {
+      t.Wt = 8; t.Ht = 16; t.Bt = 1; t.tiles_w = tw8; t.tiles_h = th16; t.tiles_b = s.B;
+      p.halo_dw = dwmin; p.halo_dh = dhmin;
+      p.a_stages = 2;
+      p.a_halo_bytes = (uint32_t)a_bytes;
+      p.tg = s.kW;                                      // one filter row of taps per B ring slot
+      // measured on B200: the 128B swizzle XOR is taken from the absolute shared-memory address bits, for TMA writes and
+      // UMMA reads alike — a window that starts on any 128-byte row is read correctly with base offset 0 (setting the
+      // descriptor's base-offset field to the row phase gives wrong results: tests/tc_probe.py, QUAN_TC_HALO_BO=1)
+      p.halo_bo = 0;
+      if (const char* e = getenv("QUAN_TC_HALO_BO")) p.halo_bo = atoi(e) != 0;
+      for (int i = 0; i < p.tt.start[1]; ++i) p.arow[i] = (uint16_t)((p.tt.dh[i] - dhmin) * 16 + (p.tt.dw[i] - dwmin));
+    }
+  }
   p.B = s.B; p.Ho = s.Ho; p.Wo = s.Wo; p.Cout = s.N;
   p.Wt = t.Wt; p.Ht = t.Ht; p.Bt = t.Bt; p.tiles_w = t.tiles_w; p.tiles_h = t.tiles_h;
   p.in_sW = s.sW; p.in_sH = s.sH; p.out_sW = s.scatW; p.out_sH = s.scatH;
@@ -968,14 +1114,16 @@ static int launch_igemm(const void* in, const void* wpacked, const float* bias, 
   }
   p.sub = iters_per_q >= 2 ? 2 : 1;                  // 8 MMAs per barrier round trip when there is enough K
   if (const char* e = getenv("QUAN_TC_SUB")) { int v = atoi(e); if (v >= 1 && v <= 4 && v <= iters_per_q) p.sub = v; }
-  const size_t stage_bytes = (size_t)(p.a_sub_bytes + p.b_sub_bytes) * p.sub;
-  const size_t budget = 200 * 1024;
+  if (p.halo) p.sub = p.tg;                          // halo mode: a B ring slot holds one filter row of taps; A has its own ring
+  const size_t a_ring = p.halo ? (size_t)p.a_stages * p.a_halo_bytes : 0;
+  const size_t stage_bytes = p.halo ? (size_t)p.b_sub_bytes * p.sub : (size_t)(p.a_sub_bytes + p.b_sub_bytes) * p.sub;
+  const size_t budget = 200 * 1024 - a_ring;
   int stages = (int)(budget / stage_bytes);
   if (stages > 8) stages = 8;
   if (const char* e = getenv("QUAN_TC_STAGES")) { int v = atoi(e); if (v >= 1 && v < stages) stages = v; }
   QUAN_REQUIRE(stages >= 2, QUAN_E_UNSUPPORTED, "tcgen05 conv: stage too large");
   p.stages = stages;
-  const size_t smem = 1024 + stages * stage_bytes + (2 * stages + 10) * sizeof(uint64_t) + 16 +
+  const size_t smem = 1024 + a_ring + stages * stage_bytes + (2 * stages + 18) * sizeof(uint64_t) + 16 +
                       (p.stat_part != nullptr ? (size_t)8 * p.stat_cq * sizeof(float) : 0);
 
   // A: input activations [B][Hi][Wi][nq][K] -> 5-D map {K, nq, Wi, Hi, B}
@@ -984,7 +1132,8 @@ static int launch_igemm(const void* in, const void* wpacked, const float* bias, 
     const uint64_t dims[5] = {(uint64_t)s.K, (uint64_t)NQ, (uint64_t)s.Wi, (uint64_t)s.Hi, (uint64_t)s.B};
     const uint64_t str[4] = {(uint64_t)s.K * esz, (uint64_t)NQ * s.K * esz, (uint64_t)s.Wi * NQ * s.K * esz,
                              (uint64_t)s.Hi * s.Wi * NQ * s.K * esz};
-    const uint32_t box[5] = {(uint32_t)p.bk_elems, 1, (uint32_t)(t.Wt * s.sW), (uint32_t)(t.Ht * s.sH), (uint32_t)t.Bt};
+    uint32_t box[5] = {(uint32_t)p.bk_elems, 1, (uint32_t)(t.Wt * s.sW), (uint32_t)(t.Ht * s.sH), (uint32_t)t.Bt};
+    if (p.halo) { box[2] = 16; box[3] = (uint32_t)halo_h; box[4] = 1; }
     const uint32_t est[5] = {1, 1, (uint32_t)s.sW, (uint32_t)s.sH, 1};
     int rc = encode_map(&map_a, dtype, 5, in, dims, str, box, est, row_bytes);
     if (rc) return rc;

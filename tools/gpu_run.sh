@@ -1,4 +1,5 @@
 timeout 600 python -m pytest tests -m gpu -q -x 2>&1 | tail -3
-C=64 HW=128 python tests/conv_probe.py | tail -1
-QUAN_TC_DBUF=0 C=64 HW=128 python tests/conv_probe.py | tail -1
 python tests/conv_probe.py | tail -1
+QUAN_TC_HALO=0 python tests/conv_probe.py | tail -1
+for c in 64 128 512; do C=$c HW=$((8192/c)) python tests/conv_probe.py | tail -1; done
+DT=f32 python tests/conv_probe.py | tail -1
