@@ -659,6 +659,11 @@ struct TcWgradParams {
   float* partial;              // [splits][nq][taps][Co][Ci]
   int atomic;                  // 1: every split adds into ONE zero-initialised partial set with vector atomics (narrow
                                // layers: many splits of a tiny dW — the fold of 64 partial sets cost more than the GEMM)
+  // halo mode (stride 1 along W): ONE box per ci atom holds the chunk's pixels for all kW taps (Wt + (kW-1)*dW wide rows);
+  // tap kw / K-step k are UMMA descriptors starting kw*dW + brow[k] pixel rows into it (absolute-address swizzle)
+  int halo;
+  uint32_t b_atom_bytes;       // slot pitch of one ci atom in the B stage (1024-byte multiple)
+  uint16_t brow[8];            // K-step -> first pixel row inside the halo box
 };
 
 constexpr int WG_PIX = 64;     // pixels (K) per pipeline stage
@@ -712,7 +717,9 @@ qconv_wgrad_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_const
     // ===== TMA producer: warp-uniform loop, one elected lane issues =====
     // co atoms past C_o are not loaded (their accumulator rows are never stored)
     const int ma_load = min(p.MA, (p.Co - co0 + p.NA - 1) / p.NA);
-    const uint32_t tx = (uint32_t)ma_load * p.atom_bytes + p.b_stage_bytes;
+    const uint32_t halo_rows = (uint32_t)(p.Bt * p.Ht * (p.Wt + (p.kW - 1) * p.dW));
+    const uint32_t tx = (uint32_t)ma_load * p.atom_bytes +
+                        (p.halo ? (uint32_t)p.NB * halo_rows * (p.atom_bytes / WG_PIX) : p.b_stage_bytes);
     // chunk -> (tb, th, tw) once, then incrementally (no div/mod on the producer's critical path)
     int tw = chunk0 % p.tiles_w;
     int th = (chunk0 / p.tiles_w) % p.tiles_h;
@@ -729,10 +736,15 @@ qconv_wgrad_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_const
           ptx::tma_load_5d(a_dst + (size_t)a * p.atom_bytes, &map_g, full_bar + s, co0 + a * p.NA, q, w0, h0, b0);
         uint8_t* b_dst = smem_b + (size_t)s * p.b_stage_bytes;
         const int wc = w0 * p.sW - p.pW, hc = h0 * p.sH - p.pH + kh * p.dH;
-        for (int t = 0; t < p.TG; ++t)
+        if (p.halo) {
           for (int a = 0; a < p.NB; ++a)
-            ptx::tma_load_5d(b_dst + (size_t)(t * p.NB + a) * p.atom_bytes, &map_x, full_bar + s, ci0 + a * p.NA, q,
-                             wc + t * p.dW, hc, b0);
+            ptx::tma_load_5d(b_dst + (size_t)a * p.b_atom_bytes, &map_x, full_bar + s, ci0 + a * p.NA, q, wc, hc, b0);
+        } else {
+          for (int t = 0; t < p.TG; ++t)
+            for (int a = 0; a < p.NB; ++a)
+              ptx::tma_load_5d(b_dst + (size_t)(t * p.NB + a) * p.atom_bytes, &map_x, full_bar + s, ci0 + a * p.NA, q,
+                               wc + t * p.dW, hc, b0);
+        }
       }
       __syncwarp();
       if (++s == p.stages) { s = 0; phase ^= 1; }
@@ -743,9 +755,11 @@ qconv_wgrad_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_const
     // MN-major, 128B swizzle: LBO = distance between 128-byte column atoms, SBO = one K-row group
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint64_t da0 = ptx::make_smem_desc(ptx::smem_u32(smem_a), p.atom_bytes, p.sbo_bytes, p.layout_type);
-    const uint64_t db0 = ptx::make_smem_desc(ptx::smem_u32(smem_b), p.atom_bytes, p.sbo_bytes, p.layout_type);
+    const uint64_t db0 = ptx::make_smem_desc(ptx::smem_u32(smem_b), p.halo ? p.b_atom_bytes : p.atom_bytes, p.sbo_bytes, p.layout_type);
     const uint64_t a_step = (uint64_t)(p.a_stage_bytes >> 4), b_step = (uint64_t)(p.b_stage_bytes >> 4);
-    const uint64_t tap_step = (uint64_t)((p.atom_bytes * p.NB) >> 4);
+    // per tap: the next NB atoms (plain mode) or kw*dW pixel rows further into the halo box (halo mode)
+    const uint32_t row16 = (p.atom_bytes / WG_PIX) >> 4;                  // one pixel row in 16-byte units
+    const uint64_t tap_step = p.halo ? (uint64_t)(p.dW * row16) : (uint64_t)((p.atom_bytes * p.NB) >> 4);
     int s = 0;
     uint32_t phase = 0;
     uint64_t da = da0, db = db0;
@@ -758,7 +772,8 @@ qconv_wgrad_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_const
           const uint32_t d_tmem = tmem_u + (uint32_t)(t * N);
 #pragma unroll
           for (int k = 0; k < KSTEPS; ++k)
-            ptx::umma<KIND>(d_tmem, da + (uint64_t)(k * p.kadv), dbt + (uint64_t)(k * p.kadv), p.idesc, (it | k) ? 1u : 0u);
+            ptx::umma<KIND>(d_tmem, da + (uint64_t)(k * p.kadv), dbt + (uint64_t)(p.halo ? p.brow[k] * row16 : k * p.kadv), p.idesc,
+                            (it | k) ? 1u : 0u);
         }
         ptx::umma_commit(empty_bar + s);
       }
@@ -1243,6 +1258,8 @@ struct WgradPlan {
   int Co, Ci;                  // channel counts of the GEMM (dense: 4x the quaternion counts)
   int row_bytes;               // swizzle atom row: 128 / 64 / 32 bytes of channels
   int nchunks, TG, NA, NB, MA, co_blocks, ci_blocks, tap_groups, splits, chunks_per_split, stages;
+  int halo;                    // B operand as one halo box per ci atom (stride 1 along W)
+  size_t b_atom_bytes;         // halo: slot pitch of a ci atom
   size_t smem, partial_bytes;
 };
 
@@ -1285,10 +1302,20 @@ static bool plan_wgrad(const quan_conv_dims& d, int dtype, int dense, WgradPlan&
   // N = NB atoms of ci per CTA: as wide as TMEM (TG accumulators of N columns), UMMA (N <= 256, multiple of 16) and a
   // >= 3-stage smem ring allow — wider N means fewer, longer MMAs per barrier round trip and fewer re-reads of the G tile
   const size_t atom = (size_t)WG_PIX * w.row_bytes;
+  // halo mode: the kW taps of a filter row read the same pixels shifted by dW — one box per ci atom, (kW-1)*dW pixels
+  // wider than the chunk, serves them all (B operand traffic / kW); needs stride 1 along W and K-steps that stay inside
+  // an image row.  QUAN_TC_WG_HALO=0 disables.
+  {
+    static const int env_halo = [] { const char* e = getenv("QUAN_TC_WG_HALO"); return e ? atoi(e) : 1; }();
+    const int umma_k = 32 / esz, wbox = w.t.Wt + (d.kW - 1) * d.dW;
+    w.halo = env_halo && d.sW == 1 && d.kW > 1 && w.t.Wt % umma_k == 0 && wbox <= 256;
+    w.b_atom_bytes = w.halo ? ((size_t)w.t.Bt * w.t.Ht * wbox * w.row_bytes + 1023) / 1024 * 1024 : atom;
+  }
+  auto b_stage = [&](int nb) { return w.halo ? (size_t)nb * w.b_atom_bytes : (size_t)w.TG * nb * atom; };
   w.NB = 0;
   for (int nb = 1; nb * w.NA <= 256; ++nb) {
     const int n = nb * w.NA;
-    const size_t stage_nb = (size_t)(w.MA + w.TG * nb) * atom;
+    const size_t stage_nb = (size_t)w.MA * atom + b_stage(nb);
     if (w.Ci % n != 0 || n % 16 != 0 || w.TG * n > 512) continue;
     if (w.NB != 0 && (200 * 1024) / stage_nb < 3) continue;
     w.NB = nb;
@@ -1319,7 +1346,7 @@ static bool plan_wgrad(const quan_conv_dims& d, int dtype, int dense, WgradPlan&
   }
   w.chunks_per_split = (int)((w.nchunks + splits - 1) / splits);
   w.splits = (w.nchunks + w.chunks_per_split - 1) / w.chunks_per_split;
-  const size_t stage = (size_t)(w.MA + w.TG * w.NB) * atom;
+  const size_t stage = (size_t)w.MA * atom + b_stage(w.NB);
   int stages = (int)((200 * 1024) / stage);
   if (stages > 8) stages = 8;
   if (stages < 2) return false;
@@ -1357,7 +1384,14 @@ static int launch_wgrad(const void* gq, const void* x, float* const dw[4], const
   p.layout_type = sizeof(T) == 2 ? (w.row_bytes == 128 ? 2u : w.row_bytes == 64 ? 4u : 6u) : 1u;
   const uint32_t swz = sizeof(T) == 2 ? (uint32_t)w.row_bytes : SWZ_128B_ATOM32;
   p.a_stage_bytes = (uint32_t)w.MA * p.atom_bytes;
-  p.b_stage_bytes = (uint32_t)(w.TG * w.NB) * p.atom_bytes;
+  p.halo = w.halo;
+  p.b_atom_bytes = (uint32_t)w.b_atom_bytes;
+  p.b_stage_bytes = w.halo ? (uint32_t)(w.NB * w.b_atom_bytes) : (uint32_t)(w.TG * w.NB) * p.atom_bytes;
+  if (w.halo)
+    for (int k = 0; k < p.ksteps && k < 8; ++k) {
+      const int p0 = k * umma_k;
+      p.brow[k] = (uint16_t)((p0 / w.t.Wt) * (w.t.Wt + (d.kW - 1) * d.dW) + p0 % w.t.Wt);
+    }
   p.idesc = ptx::make_idesc(sizeof(T) == 2 ? 1u : 2u, 1u, 1u, 128u, (uint32_t)(w.NA * w.NB));
   p.tmem_cols = (uint32_t)pow2_ceil(w.TG * w.NA * w.NB < 32 ? 32 : w.TG * w.NA * w.NB);
   p.partial = reinterpret_cast<float*>(ws);
@@ -1380,7 +1414,8 @@ static int launch_wgrad(const void* gq, const void* x, float* const dw[4], const
     const uint64_t dims[5] = {(uint64_t)w.Ci, (uint64_t)nq, (uint64_t)d.W, (uint64_t)d.H, (uint64_t)d.B};
     const uint64_t str[4] = {(uint64_t)w.Ci * esz, (uint64_t)nq * w.Ci * esz, (uint64_t)d.W * nq * w.Ci * esz,
                              (uint64_t)d.H * d.W * nq * w.Ci * esz};
-    const uint32_t box[5] = {(uint32_t)w.NA, 1, (uint32_t)(w.t.Wt * d.sW), (uint32_t)(w.t.Ht * d.sH), (uint32_t)w.t.Bt};
+    const uint32_t box[5] = {(uint32_t)w.NA, 1, (uint32_t)(w.halo ? w.t.Wt + (d.kW - 1) * d.dW : w.t.Wt * d.sW),
+                             (uint32_t)(w.t.Ht * d.sH), (uint32_t)w.t.Bt};
     const uint32_t est[5] = {1, 1, (uint32_t)d.sW, (uint32_t)d.sH, 1};
     int rc = encode_map(&map_x, dtype, 5, x, dims, str, box, est, swz);
     if (rc) return rc;
