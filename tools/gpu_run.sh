@@ -1,5 +1,5 @@
-timeout 600 python -m pytest tests -m gpu -q 2>&1 | tail -5
-python tests/conv_probe.py | tail -1
-QUAN_TC_WG_HALO=0 WHICH=dw python tests/conv_probe.py | tail -1
-for c in 64 128 512; do WHICH=dw C=$c HW=$((8192/c)) python tests/conv_probe.py | tail -1; done
-WHICH=dw DT=f32 python tests/conv_probe.py | tail -1
+timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench16.log 2>/dev/null; python -c "
+import json,sys;d=json.loads(open('gpurun_out/bench16.log').read().strip().splitlines()[-1]);print(d['value'],d['ms_per_step'],d['e2e']['value'],d['roofline']);
+print(' '.join(f\"{k}={v['ms_per_launch']*1e3:.1f}\" for k,v in d['kernels_in_step'].items()))
+[print(k,round(v['ms'],4),round(v['achieved'],1),round(v['frac'],3)) for k,v in d['ops_isolated'].items()]"
+timeout 300 python bench.py --workload yolo11n_trace --steps 5 --warmup 3 --graph 2>&1 | tail -1 | cut -c1-200
