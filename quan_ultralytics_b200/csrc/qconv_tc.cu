@@ -96,10 +96,9 @@ __global__ void __launch_bounds__(256) pack_weights_fwd_kernel(const float* __re
 #pragma unroll 8
   for (int e = threadIdx.x; e < nci * taps; e += blockDim.x) tile[e] = __ldg(w + e);
   __syncthreads();
-#pragma unroll 4
-  for (int e = threadIdx.x; e < nci * taps; e += blockDim.x) {
-    const int tap = e / nci, ci = e - tap * nci;
-    out[(((int64_t)q * taps + tap) * Co + co) * Ci + ci0 + ci] = from_f32<T>(round_operand(tile[ci * taps + tap], sizeof(T)));
+  for (int tap = 0; tap < taps; ++tap) {            // (tap, ci) nested: no integer division per element
+    T* orow = out + (((int64_t)q * taps + tap) * Co + co) * Ci + ci0;
+    for (int ci = threadIdx.x; ci < nci; ci += blockDim.x) orow[ci] = from_f32<T>(round_operand(tile[ci * taps + tap], sizeof(T)));
   }
 }
 
@@ -834,15 +833,29 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
   const int ci0 = blockIdx.x * cchunk, nci = min(cchunk, Ci - ci0);
   const int items = nci * taps;
   const int64_t split_stride = (int64_t)(DENSE ? 16 : 4) * taps * Co * Ci;
-#pragma unroll 2
-  for (int e = threadIdx.x; e < items * SL; e += blockDim.x) {
-    const int sl = e / items, it = e - sl * items;
-    const int tap = it / nci, ci = it - tap * nci;
-    float s = 0.f;
-    if constexpr (DENSE) {
+  // thread -> (split lane sl, channel ci) once; the tap loop needs no integer division
+  const int lanes_ci = SL > 1 ? nci : blockDim.x;                // SL > 1 only when nci * taps * SL <= blockDim.x
+  const int sl = SL > 1 ? (int)threadIdx.x / (nci * taps) : 0;
+  const int rem = SL > 1 ? (int)threadIdx.x % (nci * taps) : 0;
+  for (int tap = SL > 1 ? rem / nci : 0; tap < taps; tap += SL > 1 ? taps : 1) {
+    if (SL > 1 && sl >= SL) break;
+    for (int ci = SL > 1 ? rem % nci : (int)threadIdx.x; ci < nci; ci += lanes_ci) {
+      float s = 0.f;
+      if constexpr (DENSE) {
 #pragma unroll
-      for (int pc = 0; pc < 4; ++pc) {
-        const float* src = partial + (((int64_t)tap * 4 * Co + pc * Co + co) * 4 * Ci + q * Ci + ci0 + ci);
+        for (int pc = 0; pc < 4; ++pc) {
+          const float* src = partial + (((int64_t)tap * 4 * Co + pc * Co + co) * 4 * Ci + q * Ci + ci0 + ci);
+          float t0 = 0.f, t1 = 0.f;
+          int sp = sl;
+          for (; sp + SL < splits; sp += 2 * SL) {
+            t0 += __ldg(src + sp * split_stride);
+            t1 += __ldg(src + (sp + SL) * split_stride);
+          }
+          if (sp < splits) t0 += __ldg(src + sp * split_stride);
+          s += mix.m[pc * 4 + q] * (t0 + t1);
+        }
+      } else {
+        const float* src = partial + ((((int64_t)q * taps + tap) * Co + co) * Ci + ci0 + ci);
         float t0 = 0.f, t1 = 0.f;
         int sp = sl;
         for (; sp + SL < splits; sp += 2 * SL) {
@@ -850,20 +863,10 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
           t1 += __ldg(src + (sp + SL) * split_stride);
         }
         if (sp < splits) t0 += __ldg(src + sp * split_stride);
-        s += mix.m[pc * 4 + q] * (t0 + t1);
+        s = t0 + t1;
       }
-    } else {
-      const float* src = partial + ((((int64_t)q * taps + tap) * Co + co) * Ci + ci0 + ci);
-      float t0 = 0.f, t1 = 0.f;
-      int sp = sl;
-      for (; sp + SL < splits; sp += 2 * SL) {
-        t0 += __ldg(src + sp * split_stride);
-        t1 += __ldg(src + (sp + SL) * split_stride);
-      }
-      if (sp < splits) t0 += __ldg(src + sp * split_stride);
-      s = t0 + t1;
+      tile[sl * items + ci * taps + tap] = s;
     }
-    tile[sl * items + ci * taps + tap] = s;
   }
   __syncthreads();
   float* dw = (q == 0 ? dw0 : q == 1 ? dw1 : q == 2 ? dw2 : dw3) + ((int64_t)co * Ci + ci0) * taps;
