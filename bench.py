@@ -479,7 +479,8 @@ def main():
     x_host = torch.empty(x_dev.shape, dtype=dtype).contiguous(memory_format=fmt).pin_memory()
     x_host.copy_(x_dev)
     x_stage = torch.empty_like(x_dev, memory_format=torch.preserve_format)
-    g_host = torch.empty_like(net[0].conv.weight_r, device="cpu").pin_memory()
+    g_host = [torch.empty_like(net[0].conv.weight_r, device="cpu").pin_memory() for _ in range(2)]
+    step_done = [torch.cuda.Event(), torch.cuda.Event()]
 
     def step(xin):
         opt.zero_grad(set_to_none=True)
@@ -514,8 +515,10 @@ def main():
         torch.cuda.current_stream().wait_event(copied[cur])
         step(x_stage2[cur])
         consumed[cur].record()
-        g_host.copy_(net[0].conv.weight_r.grad, non_blocking=True)   # D2H of the step's result
-        torch.cuda.current_stream().synchronize()
+        g_host[cur].copy_(net[0].conv.weight_r.grad, non_blocking=True)   # D2H of this step's result
+        step_done[cur].record()
+        if i > 0:
+            step_done[cur ^ 1].synchronize()               # the host consumes step i-1's result while step i runs
         e2e_state["i"] = i + 1
 
     def barrier():
@@ -572,7 +575,7 @@ def main():
                        "train_gflop_per_image": flops_per_image(a) / 1e9},
             "e2e": {"value": e2e_value, "unit": "images/s",
                     "h2d_bytes_per_step": x_host.numel() * x_host.element_size(),
-                    "d2h_bytes_per_step": g_host.numel() * g_host.element_size()},
+                    "d2h_bytes_per_step": g_host[0].numel() * g_host[0].element_size()},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "step_tflops": flops_per_image(a) * a.n * world / (ms / a.steps) / 1e9,

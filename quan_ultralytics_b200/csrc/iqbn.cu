@@ -13,6 +13,7 @@
 //
 // Two physical layouts (include/quan_sm100.h): BCHWQ (reference) and BHWQC (channels_last_3d, tensor-core path).
 #include "common.cuh"
+#include "tc_ptx.cuh"
 #include <cooperative_groups.h>
 #include <stdlib.h>
 
@@ -322,6 +323,170 @@ __global__ void __launch_bounds__(IQBN_RED_THREADS, 2) iqbn_reduce_b(const T* __
         }
         if (lane == 0) finish_accumulator(tail, i, a0, a1);
       }
+    }
+  }
+}
+
+// -------------------------------------------------------------------------------------------------------------------
+// Reductions fed by the TMA engine.  ncu on iqbn_reduce_b (profiles/r01_iqbn_tune5.log): 64 registers x 1024 threads fill
+// the register file, so at most 4 x 16 bytes per thread are in flight and a warp alternates between waiting for its loads
+// and reducing them (issue-active 52 %, long-scoreboard stalls) — 3.4-4.4 TB/s.  Here memory-level parallelism does not
+// live in registers: one producer lane streams contiguous row tiles (cp.async.bulk, 1-D) into a shared-memory ring of
+// NS stages per block, two blocks per SM (~190 KB in flight per SM), and 256 consumer threads reduce from shared memory
+// with the same thread -> column mapping (16-byte LDS, conflict-free).  Same partials format and fold kernel.
+// -------------------------------------------------------------------------------------------------------------------
+constexpr int IQBN_TMA_CONSUMERS = 256;
+constexpr int IQBN_TMA_THREADS = IQBN_TMA_CONSUMERS + 32;
+
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(ptx::smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(ptx::smem_u32(bar))
+               : "memory");
+}
+
+struct GeomT {
+  int64_t R;        // rows
+  int L, C;
+  int cvpg, rpb;    // column vectors per row, rows per consumer pass (256 / cvpg)
+  int tile_rows;    // rows per stage (multiple of rpb)
+  int ntiles;       // ceil(R / tile_rows)
+  int stages;
+};
+
+template <typename T, int V, int MODE, int ACT>
+__global__ void __launch_bounds__(IQBN_TMA_THREADS, 2) iqbn_reduce_tma(const T* __restrict__ x, const T* __restrict__ dy,
+                                                                        GeomT g, IqbnWs ws, TailArgs tail) {
+  extern __shared__ __align__(128) uint8_t tsm[];
+  using VecT = Vec<T, V>;
+  constexpr int NSTREAM = MODE == 1 ? 2 : 1;
+  const uint32_t tile_bytes = (uint32_t)g.tile_rows * g.L * sizeof(T);
+  uint8_t* ring = tsm;                                                        // [stages][NSTREAM][tile_bytes]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + (size_t)g.stages * NSTREAM * tile_bytes);
+  uint64_t* empty_bar = full_bar + g.stages;
+  double (*red)[2] = reinterpret_cast<double (*)[2]>(empty_bar + g.stages);  // [256][2]
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < g.stages; ++i) {
+      ptx::mbar_init(full_bar + i, 1);
+      ptx::mbar_init(empty_bar + i, IQBN_TMA_CONSUMERS / 32);
+    }
+    ptx::fence_barrier_init();
+  }
+  __syncthreads();
+  // tiles of this block, last to first (the producer of x wrote front to back: its tail is still in L2)
+  const int my_tiles = (g.ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + ((int)blockIdx.x < g.ntiles ? 1 : 0);
+
+  if (warp == IQBN_TMA_CONSUMERS / 32) {
+    // ===== producer =====
+    int s = 0;
+    uint32_t phase = 0;
+    for (int i = 0; i < my_tiles; ++i) {
+      const int tile = g.ntiles - 1 - ((int)blockIdx.x + i * (int)gridDim.x);
+      const int64_t r0 = (int64_t)tile * g.tile_rows;
+      const int64_t rows = g.R - r0 < g.tile_rows ? g.R - r0 : g.tile_rows;
+      const uint32_t bytes = (uint32_t)(rows * g.L * sizeof(T));
+      ptx::mbar_wait(empty_bar + s, phase ^ 1);
+      if (ptx::elect_one()) {
+        ptx::mbar_arrive_expect_tx(full_bar + s, bytes * NSTREAM);
+        uint8_t* dst = ring + (size_t)s * NSTREAM * tile_bytes;
+        bulk_load_1d(dst, x + r0 * g.L, bytes, full_bar + s);
+        if constexpr (MODE == 1) bulk_load_1d(dst + tile_bytes, dy + r0 * g.L, bytes, full_bar + s);
+      }
+      __syncwarp();
+      if (++s == g.stages) { s = 0; phase ^= 1; }
+    }
+    return;
+  }
+
+  // ===== consumers: thread owns column vector cvl of every row it visits =====
+  const int cvl = threadIdx.x % g.cvpg;
+  const int rl = threadIdx.x / g.cvpg;
+  const bool lane_on = rl < g.rpb;
+  const int64_t coloff = (int64_t)cvl * V;
+  float scale[V], shift[V];
+  if constexpr (MODE == 1 && ACT != QUAN_ACT_NONE) {
+    load_coef<float, V>(tail.stats + 12 * g.C + coloff, scale);
+    load_coef<float, V>(tail.stats + 16 * g.C + coloff, shift);
+  }
+  float s0[V], s1[V], k[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) s0[i] = s1[i] = k[i] = 0.f;
+  int cnt = 0;
+  bool have_k = false;
+  int s = 0;
+  uint32_t phase = 0;
+  for (int it = 0; it < my_tiles; ++it) {
+    const int tile = g.ntiles - 1 - ((int)blockIdx.x + it * (int)gridDim.x);
+    const int64_t r0 = (int64_t)tile * g.tile_rows;
+    const int rows = (int)(g.R - r0 < g.tile_rows ? g.R - r0 : g.tile_rows);
+    ptx::mbar_wait(full_bar + s, phase);
+    const T* xt = reinterpret_cast<const T*>(ring + (size_t)s * NSTREAM * tile_bytes);
+    const T* gt = xt + (size_t)g.tile_rows * g.L;
+    if (lane_on) {
+      for (int r = rl; r < rows; r += g.rpb) {
+        const VecT xa = *reinterpret_cast<const VecT*>(xt + (size_t)r * g.L + coloff);
+        VecT ga;
+        if constexpr (MODE == 1) ga = *reinterpret_cast<const VecT*>(gt + (size_t)r * g.L + coloff);
+        if constexpr (MODE == 0) {
+          if (!have_k) {                       // local shift: keeps fp32 partials well conditioned
+#pragma unroll
+            for (int i = 0; i < V; ++i) k[i] = to_f32(xa.v[i]);
+            have_k = true;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          const float xv = to_f32(xa.v[i]);
+          if constexpr (MODE == 0) {
+            const float d = xv - k[i];
+            s0[i] += d;
+            s1[i] = fmaf(d, d, s1[i]);
+          } else {
+            float dz = to_f32(ga.v[i]);
+            if constexpr (ACT != QUAN_ACT_NONE) dz *= act_grad<ACT, sizeof(T) == 2>(fmaf(xv, scale[i], shift[i]));
+            s0[i] += dz;
+            s1[i] = fmaf(dz, xv, s1[i]);
+          }
+        }
+        ++cnt;
+      }
+    }
+    __syncwarp();
+    if (ptx::elect_one()) ptx::mbar_arrive(empty_bar + s);
+    __syncwarp();
+    if (++s == g.stages) { s = 0; phase ^= 1; }
+  }
+
+  // fold over the row lanes (consumer threads only: named barrier 1) and write this block's slot of the partials
+  int half = 1;
+  while (half * 2 < g.rpb) half *= 2;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    double a0, a1;
+    if constexpr (MODE == 0) {
+      const double kd = (double)k[i], nd = (double)cnt;
+      a0 = (double)s0[i] + nd * kd;
+      a1 = (double)s1[i] + 2.0 * kd * (double)s0[i] + nd * kd * kd;
+    } else {
+      a0 = (double)s0[i];
+      a1 = (double)s1[i];
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(IQBN_TMA_CONSUMERS) : "memory");
+    red[threadIdx.x][0] = lane_on ? a0 : 0.0;
+    red[threadIdx.x][1] = lane_on ? a1 : 0.0;
+    asm volatile("bar.sync 1, %0;" ::"n"(IQBN_TMA_CONSUMERS) : "memory");
+    for (int st = half; st >= 1; st >>= 1) {
+      if (rl < st && rl + st < g.rpb) {
+        red[threadIdx.x][0] += red[threadIdx.x + st * g.cvpg][0];
+        red[threadIdx.x][1] += red[threadIdx.x + st * g.cvpg][1];
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(IQBN_TMA_CONSUMERS) : "memory");
+    }
+    if ((int)threadIdx.x < g.cvpg) {
+      const int col = threadIdx.x * V + i;
+      const int q = col / g.C, c = col - q * g.C;
+      ws.part[((size_t)blockIdx.x * 2 + 0) * 4 * g.C + c * 4 + q] = red[threadIdx.x][0];
+      ws.part[((size_t)blockIdx.x * 2 + 1) * 4 * g.C + c * 4 + q] = red[threadIdx.x][1];
     }
   }
 }
@@ -780,6 +945,43 @@ static int launch_reduce(const void* x, const void* dy, int B, int C, int H, int
   int nparts = 1;
   if (layout == QUAN_LAYOUT_BHWQC && C > 1) {
     LaunchB p;
+    {
+      // TMA-fed variant: whole rows per block (<= 256 column vectors), 16-byte multiples
+      const int Vt = largest_pow2_divisor(C, VecTraits<T>::kMaxVec);
+      const int colvecs = 4 * C / Vt;
+      const size_t row_bytes = (size_t)4 * C * sizeof(T);
+      if (env_int("QUAN_IQBN_TMA", 1) && colvecs <= IQBN_TMA_CONSUMERS && row_bytes % 16 == 0 && Vt * sizeof(T) >= 8) {
+        GeomT g;
+        g.R = (int64_t)B * H * W; g.L = 4 * C; g.C = C; g.cvpg = colvecs; g.rpb = IQBN_TMA_CONSUMERS / colvecs;
+        const size_t target = MODE == 1 ? 8 * 1024 : 16 * 1024;
+        int tr = (int)(target / row_bytes) / g.rpb * g.rpb;
+        if (tr < g.rpb) tr = g.rpb;
+        g.tile_rows = tr;
+        g.ntiles = (int)ceil_div64(g.R, tr);
+        const size_t tile_bytes = (size_t)tr * row_bytes * (MODE == 1 ? 2 : 1);
+        int stages = (int)((96 * 1024) / tile_bytes);
+        if (stages > 8) stages = 8;
+        if (stages >= 2) {
+          g.stages = stages;
+          const size_t smem = stages * tile_bytes + 2 * stages * sizeof(uint64_t) + IQBN_TMA_CONSUMERS * 2 * sizeof(double) + 128;
+          int grid = g.ntiles < 2 * QUAN_NUM_SMS ? g.ntiles : 2 * QUAN_NUM_SMS;
+          nparts = grid;
+          QUAN_TIMED(st);
+#define QUAN_REDUCE_T(VV) { auto kern = iqbn_reduce_tma<T, VV, MODE, ACT>;                                                  \
+            static thread_local bool attr = false;                                                                        \
+            if (!attr) { QUAN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)); attr = true; } \
+            kern<<<grid, IQBN_TMA_THREADS, smem, st>>>(xp, dyp, g, ws, tail); }
+          if (Vt * sizeof(T) == 16) { if constexpr (sizeof(T) == 2) QUAN_REDUCE_T(8) else QUAN_REDUCE_T(4) }
+          else { if constexpr (sizeof(T) == 2) QUAN_REDUCE_T(4) else QUAN_REDUCE_T(2) }
+#undef QUAN_REDUCE_T
+          QUAN_CHECK_LAUNCH(MODE == 0 ? "iqbn_reduce_fwd" : "iqbn_reduce_bwd");
+          QUAN_TIMED(st);
+          iqbn_fold_kernel<<<(4 * C + 7) / 8, 256, 0, st>>>(ws.part, nparts, tail);
+          QUAN_CHECK_LAUNCH("iqbn_fold");
+          return QUAN_OK;
+        }
+      }
+    }
     // 2 blocks of 512 threads per SM, U independent 16-byte loads per stream and thread in flight (>= 64 KB per SM)
     const int U = env_int("QUAN_IQBN_RU", MODE == 0 ? 4 : 2);
     const int bps = env_int("QUAN_IQBN_RBPS", 2);
