@@ -694,6 +694,115 @@ __global__ void __launch_bounds__(256, 2) iqbn_apply_bwd_mix_b(const T* __restri
   }
 }
 
+// TMA-fed backward apply (same ring as iqbn_reduce_tma, two input streams) with the warp-local quaternion mapping of
+// iqbn_apply_bwd_mix_b: consumers read x / dy rows from shared memory, form dx, optionally exchange the four components
+// by xor-shuffles to emit G = M^T dx, and store 16-byte vectors straight to global memory.
+struct GeomTW {
+  int64_t R;
+  int L, C;
+  int cpq, gl, nb, rpb;   // as GeomW: column vectors per component, per slot; channel blocks per row; rows per pass
+  int tile_rows, ntiles, stages;
+};
+template <typename T, int V, int ACT, bool MIX>
+__global__ void __launch_bounds__(IQBN_TMA_THREADS, 2) iqbn_apply_bwd_tma(const T* __restrict__ x, const T* __restrict__ dy,
+                                                                           T* __restrict__ out, GeomTW g, ApplyArgs a, Mix16 mt) {
+  extern __shared__ __align__(128) uint8_t tsm[];
+  using VecT = Vec<T, V>;
+  const uint32_t tile_bytes = (uint32_t)g.tile_rows * g.L * sizeof(T);
+  uint8_t* ring = tsm;                                                        // [stages][2][tile_bytes]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + (size_t)g.stages * 2 * tile_bytes);
+  uint64_t* empty_bar = full_bar + g.stages;
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < g.stages; ++i) {
+      ptx::mbar_init(full_bar + i, 1);
+      ptx::mbar_init(empty_bar + i, IQBN_TMA_CONSUMERS / 32);
+    }
+    ptx::fence_barrier_init();
+  }
+  __syncthreads();
+  const int my_tiles = (g.ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + ((int)blockIdx.x < g.ntiles ? 1 : 0);
+  if (warp == IQBN_TMA_CONSUMERS / 32) {
+    int s = 0;
+    uint32_t phase = 0;
+    for (int i = 0; i < my_tiles; ++i) {
+      const int tile = (int)blockIdx.x + i * (int)gridDim.x;      // front to back (the reduction before it went back to front)
+      const int64_t r0 = (int64_t)tile * g.tile_rows;
+      const int64_t rows = g.R - r0 < g.tile_rows ? g.R - r0 : g.tile_rows;
+      const uint32_t bytes = (uint32_t)(rows * g.L * sizeof(T));
+      ptx::mbar_wait(empty_bar + s, phase ^ 1);
+      if (ptx::elect_one()) {
+        ptx::mbar_arrive_expect_tx(full_bar + s, bytes * 2);
+        uint8_t* dst = ring + (size_t)s * 2 * tile_bytes;
+        bulk_load_1d(dst, x + r0 * g.L, bytes, full_bar + s);
+        bulk_load_1d(dst + tile_bytes, dy + r0 * g.L, bytes, full_bar + s);
+      }
+      __syncwarp();
+      if (++s == g.stages) { s = 0; phase ^= 1; }
+    }
+    return;
+  }
+  const int slot = threadIdx.x / (4 * g.gl), ls = threadIdx.x % (4 * g.gl);
+  const int q = ls / g.gl, j = ls - q * g.gl;
+  const int rl = slot / g.nb, cb = slot - rl * g.nb;
+  const bool lane_on = rl < g.rpb;
+  const int cv = q * g.cpq + cb * g.gl + j;
+  const int64_t coloff = lane_on ? (int64_t)cv * V : 0;
+  float scale[V], shift[V], k1[V], k2[V], k3[V];
+  load_coef<float, V>(a.stats + 12 * g.C + coloff, scale);
+  load_coef<float, V>(a.stats + 16 * g.C + coloff, shift);
+  load_coef<float, V>(a.coefT + coloff, k1);
+  load_coef<float, V>(a.coefT + 4 * g.C + coloff, k2);
+  load_coef<float, V>(a.coefT + 8 * g.C + coloff, k3);
+  if (a.dgamma != nullptr && a.sums != nullptr && blockIdx.x == 0) {   // consumers only: stride 256, not blockDim.x
+    for (int i = threadIdx.x; i < 4 * a.C; i += IQBN_TMA_CONSUMERS) {
+      a.dbeta[i] = (float)a.sums[i];
+      a.dgamma[i] = (float)a.sums[4 * a.C + i];
+    }
+  }
+  const float m1 = mt.m[q * 4 + q], mx1 = mt.m[q * 4 + (q ^ 1)], mx2 = mt.m[q * 4 + (q ^ 2)], mx3 = mt.m[q * 4 + (q ^ 3)];
+  int s = 0;
+  uint32_t phase = 0;
+  for (int it = 0; it < my_tiles; ++it) {
+    const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+    const int64_t r0 = (int64_t)tile * g.tile_rows;
+    const int rows = (int)(g.R - r0 < g.tile_rows ? g.R - r0 : g.tile_rows);
+    ptx::mbar_wait(full_bar + s, phase);
+    const T* xt = reinterpret_cast<const T*>(ring + (size_t)s * 2 * tile_bytes);
+    const T* gt = xt + (size_t)g.tile_rows * g.L;
+    for (int rb = 0; rb < rows; rb += g.rpb) {                    // warp-uniform trip count (shuffles below)
+      const int r = rb + rl;
+      const bool on = lane_on && r < rows;
+      VecT xa = VecT{}, ga = VecT{};
+      if (on) {
+        xa = *reinterpret_cast<const VecT*>(xt + (size_t)r * g.L + coloff);
+        ga = *reinterpret_cast<const VecT*>(gt + (size_t)r * g.L + coloff);
+      }
+      VecT o;
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const float xv = to_f32(xa.v[i]);
+        float dz = to_f32(ga.v[i]);
+        if constexpr (ACT != QUAN_ACT_NONE) dz *= act_grad<ACT, sizeof(T) == 2>(fmaf(xv, scale[i], shift[i]));
+        const float d = fmaf(k1[i], dz, fmaf(k2[i], xv, k3[i]));
+        if constexpr (MIX) {
+          const float d1 = __shfl_xor_sync(0xffffffffu, d, g.gl);
+          const float d2 = __shfl_xor_sync(0xffffffffu, d, 2 * g.gl);
+          const float d3 = __shfl_xor_sync(0xffffffffu, d, 3 * g.gl);
+          o.v[i] = from_f32<T>(m1 * d + mx1 * d1 + mx2 * d2 + mx3 * d3);
+        } else {
+          o.v[i] = from_f32<T>(d);
+        }
+      }
+      if (on) *reinterpret_cast<VecT*>(out + (r0 + r) * g.L + coloff) = o;
+    }
+    __syncwarp();
+    if (ptx::elect_one()) ptx::mbar_arrive(empty_bar + s);
+    __syncwarp();
+    if (++s == g.stages) { s = 0; phase ^= 1; }
+  }
+}
+
 // =================================================================================================
 // Layout BCHWQ: for a fixed (b,c) the plane is HW*4 contiguous elements, q = element & 3.
 // grid = (splits, C); a thread walks vectors v of channel c: b = v / vpp, i = v % vpp.
@@ -1037,6 +1146,41 @@ static int launch_apply(const void* x, const void* dy, void* out, int B, int C, 
       int gl = 1;
       while (gl < 8 && cpq % (gl * 2) == 0) gl *= 2;
       const int nb = cpq / gl, spb = 256 / (4 * gl);
+      const size_t row_bytes_t = (size_t)4 * C * sizeof(T);
+      if (env_int("QUAN_IQBN_TMA", 1) && a.stats != nullptr && a.coefT != nullptr && nb <= spb && row_bytes_t % 16 == 0 &&
+          Vw * sizeof(T) == 16) {
+        // TMA-fed variant (with or without the fused mix)
+        GeomTW g;
+        g.R = (int64_t)B * H * W; g.L = 4 * C; g.C = C; g.cpq = cpq; g.gl = gl; g.nb = nb; g.rpb = spb / nb;
+        int tr = (int)((8 * 1024) / row_bytes_t) / g.rpb * g.rpb;
+        if (tr < g.rpb) tr = g.rpb;
+        g.tile_rows = tr;
+        g.ntiles = (int)ceil_div64(g.R, tr);
+        const size_t tile_bytes = (size_t)tr * row_bytes_t * 2;
+        int stages = (int)((96 * 1024) / tile_bytes);
+        if (stages > 8) stages = 8;
+        if (stages >= 2) {
+          g.stages = stages;
+          const size_t smem = stages * tile_bytes + 2 * stages * sizeof(uint64_t) + 128;
+          const int grid = g.ntiles < 2 * QUAN_NUM_SMS ? g.ntiles : 2 * QUAN_NUM_SMS;
+          const Mix16 mt = mix_t != nullptr ? make_mix(mix_t) : Mix16{};
+          constexpr int VT = 16 / (int)sizeof(T);
+          QUAN_TIMED(st);
+          if (mix_t != nullptr) {
+            auto kern = iqbn_apply_bwd_tma<T, VT, ACT, true>;
+            static thread_local bool attr = false;
+            if (!attr) { QUAN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)); attr = true; }
+            kern<<<grid, IQBN_TMA_THREADS, smem, st>>>(xp, dyp, op, g, a, mt);
+          } else {
+            auto kern = iqbn_apply_bwd_tma<T, VT, ACT, false>;
+            static thread_local bool attr = false;
+            if (!attr) { QUAN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)); attr = true; }
+            kern<<<grid, IQBN_TMA_THREADS, smem, st>>>(xp, dyp, op, g, a, mt);
+          }
+          QUAN_CHECK_LAUNCH(mix_t != nullptr ? "iqbn_apply_bwd_mix" : "iqbn_apply_bwd");
+          return QUAN_OK;
+        }
+      }
       if (mix_t != nullptr && a.stats != nullptr && a.coefT != nullptr && nb <= spb) {
         GeomW gw;
         gw.R = (int64_t)B * H * W; gw.L = 4 * C; gw.C = C; gw.cpq = cpq; gw.gl = gl; gw.nb = nb; gw.rpb = spb / nb;

@@ -249,3 +249,40 @@ def test_small_channel_engine_matches_direct_engine(case):
         assert rel(a, r) <= 2 * tol
     if bias:
         assert rel(db, db_ref) <= 1e-4
+
+
+@pytest.mark.parametrize("cfg", [("bf16_c160", "bf16", 3, 160, 9, 11), ("f32_c96", "f32", 2, 96, 10, 7),
+                                 ("bf16_c24", "bf16", 5, 24, 17, 13), ("bf16_c512", "bf16", 2, 512, 6, 5)], ids=lambda c: c[0])
+def test_iqbn_streaming_kernels_vs_oracle_wide_rows(cfg):
+    """TMA-fed IQBN reductions / backward apply (rows of 4*C_q > 256 parameters, ragged last tile, fused G = M^T dx) against
+    the fp64 oracle on the same (rounded) inputs."""
+    import quan_ultralytics_b200 as Q
+    name, dt, B, C_, H, W = cfg
+    dtype = torch.bfloat16 if dt == "bf16" else torch.float32
+    tol = TOL = 1e-2 if dtype == torch.bfloat16 else 1e-4
+    rng = np.random.default_rng(7)
+    x = rng.normal(size=(B, C_, H, W, 4)) * 1.5 + 0.4
+    dy = rng.normal(size=(B, C_, H, W, 4))
+    gamma = rng.uniform(0.5, 1.5, size=(C_, 4))
+    beta = rng.normal(size=(C_, 4))
+    xt = torch.from_numpy(x).to(DEV, dtype).contiguous(memory_format=torch.channels_last_3d)
+    dyt = torch.from_numpy(dy).to(DEV, dtype).contiguous(memory_format=torch.channels_last_3d)
+    xr, dyr = xt.double().cpu().numpy(), dyt.double().cpu().numpy()      # what the kernels actually read
+    g32 = torch.from_numpy(gamma).to(DEV, torch.float32)
+    b32 = torch.from_numpy(beta).to(DEV, torch.float32)
+    cnt = float(B * H * W)
+    stats = ops.iqbn_train_stats(xt, L, g32, b32, 1e-5, 0.1, None, None)
+    y = ops.iqbn_apply_fwd(xt, L, stats, g32, b32, Q.ACT_SILU)
+    y_ref, _, _, _ = O.iqbn_train_fwd(xr, gamma, beta, act=True)
+    assert float(np.max(np.abs(y.double().cpu().numpy() - y_ref)) / np.max(np.abs(y_ref))) <= tol
+    sums = ops.iqbn_bwd_reduce(dyt, xt, L, stats, g32, b32, Q.ACT_SILU, cnt)
+    dx, dg, db = ops.iqbn_bwd_apply(dyt, xt, L, stats, g32, b32, Q.ACT_SILU, sums, cnt)
+    dx_ref, dg_ref, db_ref = O.iqbn_train_bwd(dyr, xr, gamma, beta, act=True)
+    nerr = lambda a, r: float(np.max(np.abs(a.double().cpu().numpy() - r)) / np.max(np.abs(r)))
+    assert nerr(dx, dx_ref) <= 2 * tol and nerr(dg, dg_ref) <= 2 * tol and nerr(db, db_ref) <= 2 * tol
+    # fused G = M^T dx
+    sums2 = ops.iqbn_bwd_reduce(dyt, xt, L, stats, g32, b32, Q.ACT_SILU, cnt)
+    gmix, dg2, db2 = ops.iqbn_bwd_apply(dyt, xt, L, stats, g32, b32, Q.ACT_SILU, sums2, cnt, mix_t=ops._mix_t(ops.M_A))
+    MT = np.array(ops.M_A).reshape(4, 4).T
+    g_ref = np.einsum("qp,bchwp->bchwq", MT, dx_ref)
+    assert nerr(gmix, g_ref) <= 2 * tol and nerr(dg2, dg_ref) <= 2 * tol and nerr(db2, db_ref) <= 2 * tol
