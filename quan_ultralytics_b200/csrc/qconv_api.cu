@@ -53,17 +53,46 @@ int quan_qconv2d_pick_algo(const quan_conv_dims* d, int dtype, int layout, int p
   return resolve_algo(*d, dtype, layout, pass, QUAN_ALGO_AUTO);
 }
 
+// workspace layout: [ G = M^T dY | packed weights (fwd / dgrad) | wgrad split-K partials ] — dgrad and wgrad get disjoint
+// regions because the backward of a narrow layer runs them concurrently (fork / join on a side stream)
+static size_t pack_region_bytes(const quan_conv_dims& d, int dtype, int layout) {
+  size_t b = 0;
+  for (int pass = PASS_FWD; pass <= PASS_DGRAD; ++pass)
+    if (qconv_tc_supported(d, dtype, layout, pass)) {
+      const size_t v = qconv_tc_workspace_bytes(d, dtype, layout, pass);
+      if (v > b) b = v;
+    }
+  return align_up(b, 1024);
+}
+
 size_t quan_qconv2d_workspace_bytes(const quan_conv_dims* d, int dtype, int layout, int algo) {
   if (d == nullptr) return 0;
   size_t tc = 0;
   if (algo != QUAN_ALGO_DIRECT && layout == QUAN_LAYOUT_BHWQC) {
-    for (int pass = 0; pass < 3; ++pass)
-      if (qconv_tc_supported(*d, dtype, layout, pass)) {
-        size_t b = qconv_tc_workspace_bytes(*d, dtype, layout, pass);
-        if (b > tc) tc = b;
-      }
+    tc = pack_region_bytes(*d, dtype, layout);
+    if (qconv_tc_supported(*d, dtype, layout, PASS_WGRAD)) tc += align_up(qconv_tc_workspace_bytes(*d, dtype, layout, PASS_WGRAD), 1024);
   }
-  return g_bytes(*d, dtype) + align_up(tc, 1024);
+  return g_bytes(*d, dtype) + tc;
+}
+
+// side stream + events for the dgrad || wgrad fork (one set per host thread and device)
+struct ForkJoin {
+  cudaStream_t side = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+static int get_fork_join(ForkJoin** out) {
+  static thread_local ForkJoin fj[16];
+  int dev = 0;
+  QUAN_CUDA(cudaGetDevice(&dev));
+  QUAN_REQUIRE(dev >= 0 && dev < 16, QUAN_E_UNSUPPORTED, "qconv2d_bwd: device index %d out of range", dev);
+  ForkJoin& f = fj[dev];
+  if (f.side == nullptr) {
+    QUAN_CUDA(cudaStreamCreateWithFlags(&f.side, cudaStreamNonBlocking));
+    QUAN_CUDA(cudaEventCreateWithFlags(&f.fork, cudaEventDisableTiming));
+    QUAN_CUDA(cudaEventCreateWithFlags(&f.join, cudaEventDisableTiming));
+  }
+  *out = &f;
+  return QUAN_OK;
 }
 
 static int qconv2d_fwd_impl(const void* x, const float* const w[4], const float* bias_r, void* y, const quan_conv_dims* d,
@@ -121,8 +150,12 @@ static int qconv2d_bwd_impl(const void* dy, const void* x, const float* const w[
   QUAN_REQUIRE(workspace != nullptr && ws_bytes >= gb, QUAN_E_WORKSPACE,
                "qconv2d_bwd: workspace needs >= %zu bytes (see quan_qconv2d_workspace_bytes), got %zu", gb, ws_bytes);
   const void* gq = premixed ? dy : workspace;
+  // [ G | packed weights | wgrad partials ]
+  const size_t pack_bytes = layout == QUAN_LAYOUT_BHWQC ? pack_region_bytes(*d, dtype, layout) : 0;
   void* tc_ws = (char*)workspace + gb;
   const size_t tc_ws_bytes = ws_bytes - gb;
+  void* wg_ws = ws_bytes >= gb + pack_bytes ? (char*)workspace + gb + pack_bytes : nullptr;
+  const size_t wg_ws_bytes = ws_bytes >= gb + pack_bytes ? ws_bytes - gb - pack_bytes : 0;
 
   // engine per pass; the dense tensor-core form consumes dY directly (M is folded into its weights / reduce step)
   int a_dx = 0, a_dw = 0, m_dx = TC_NONE, m_dw = TC_NONE;
@@ -151,6 +184,21 @@ static int qconv2d_bwd_impl(const void* dy, const void* x, const float* const w[
     if (rc) return rc;
   }
 
+  // Narrow layers (dense tensor-core form, depthwise, small-channel kernels) do not fill the GPU with one kernel: their
+  // dgrad and wgrad chains are independent and run concurrently — wgrad forks onto a side stream and joins at the end
+  // (captured as parallel branches under CUDA graphs).  QUAN_BWD_CONCURRENT=0 disables.
+  static const int env_conc = [] { const char* e = getenv("QUAN_BWD_CONCURRENT"); return e ? atoi(e) : 1; }();
+  const bool narrow = (m_dx == TC_DENSE || raw_dy(a_dx)) && (m_dw == TC_DENSE || raw_dy(a_dw));
+  ForkJoin* fj = nullptr;
+  cudaStream_t st_w = st;
+  if (env_conc && dx != nullptr && dw != nullptr && narrow) {
+    rc = get_fork_join(&fj);
+    if (rc) return rc;
+    QUAN_CUDA(cudaEventRecord(fj->fork, st));
+    QUAN_CUDA(cudaStreamWaitEvent(fj->side, fj->fork, 0));
+    st_w = fj->side;
+  }
+
   if (dx != nullptr) {
     if (a_dx == QUAN_ALGO_TCGEN05) {
       const size_t need = qconv_tc_workspace_bytes(*d, dtype, layout, PASS_DGRAD);
@@ -163,19 +211,29 @@ static int qconv2d_bwd_impl(const void* dy, const void* x, const float* const w[
     } else {
       rc = qconv_dgrad_direct_launch(gq, w, dx, *d, dtype, layout, st);
     }
-    if (rc) return rc;
+    if (rc) {
+      if (fj != nullptr) {                     // nothing was launched on the side stream yet: close the fork
+        cudaEventRecord(fj->join, fj->side);
+        cudaStreamWaitEvent(st, fj->join, 0);
+      }
+      return rc;
+    }
   }
   if (dw != nullptr) {
     if (a_dw == QUAN_ALGO_TCGEN05) {
       const size_t need = qconv_tc_workspace_bytes(*d, dtype, layout, PASS_WGRAD);
-      QUAN_REQUIRE(tc_ws_bytes >= need, QUAN_E_WORKSPACE, "qconv2d_bwd: wgrad needs %zu more workspace bytes", need);
-      rc = qconv_tc_wgrad(m_dw == TC_DENSE ? dy : gq, x, dw, *d, dtype, m_dw, mix, tc_ws, tc_ws_bytes, st);
+      QUAN_REQUIRE(wg_ws != nullptr && wg_ws_bytes >= need, QUAN_E_WORKSPACE, "qconv2d_bwd: wgrad needs %zu more workspace bytes", need);
+      rc = qconv_tc_wgrad(m_dw == TC_DENSE ? dy : gq, x, dw, *d, dtype, m_dw, mix, wg_ws, wg_ws_bytes, st_w);
     } else if (a_dw == QUAN_ALGO_DEPTHWISE) {
-      rc = qconv_dw_wgrad(dy, x, dw, *d, dtype, mix, st);
+      rc = qconv_dw_wgrad(dy, x, dw, *d, dtype, mix, st_w);
     } else if (a_dw == QUAN_ALGO_SMALLC) {
-      rc = qconv_small_wgrad(dy, x, dw, *d, dtype, mix, st);
+      rc = qconv_small_wgrad(dy, x, dw, *d, dtype, mix, st_w);
     } else {
-      rc = qconv_wgrad_direct_launch(gq, x, dw, *d, dtype, layout, st);
+      rc = qconv_wgrad_direct_launch(gq, x, dw, *d, dtype, layout, st_w);
+    }
+    if (fj != nullptr) {                       // join even when the wgrad launch failed: the side stream must not dangle
+      cudaEventRecord(fj->join, fj->side);
+      cudaStreamWaitEvent(st, fj->join, 0);
     }
     if (rc) return rc;
   }
