@@ -286,3 +286,61 @@ def test_iqbn_streaming_kernels_vs_oracle_wide_rows(cfg):
     MT = np.array(ops.M_A).reshape(4, 4).T
     g_ref = np.einsum("qp,bchwp->bchwq", MT, dx_ref)
     assert nerr(gmix, g_ref) <= 2 * tol and nerr(dg2, dg_ref) <= 2 * tol and nerr(db2, db_ref) <= 2 * tol
+
+
+@pytest.mark.parametrize("cfg", [("wide", 64, 64, 1), ("narrow", 16, 16, 1), ("depthwise", 32, 32, 32)], ids=lambda c: c[0])
+def test_conv_block_step_captures_in_a_cuda_graph(cfg):
+    """The whole Conv block step (weight packing, TMA descriptors, memsets, the dgrad || wgrad fork / join on the side
+    stream) captures into a CUDA graph and replays to the same result as eager execution."""
+    import quan_ultralytics_b200 as Q
+    name, ci, co, g = cfg
+    torch.manual_seed(3)
+    blk = (Q.DWConv(ci * 4, co * 4, 3, 1) if g > 1 else Q.Conv(ci * 4, co * 4, 3, 1)).to(DEV).train()
+    x = torch.randn(4, ci, 32, 32, 4, device=DEV).to(torch.bfloat16).contiguous(memory_format=torch.channels_last_3d)
+    x.requires_grad_(True)
+    dy = torch.randn(4, co, 32, 32, 4, device=DEV).to(torch.bfloat16).contiguous(memory_format=torch.channels_last_3d)
+
+    def step():
+        x.grad = None
+        blk.zero_grad(set_to_none=True)
+        y = blk(x)
+        y.backward(dy)
+        return y
+
+    for _ in range(3):
+        y_eager = step()
+    ref = (y_eager.detach().clone(), x.grad.clone(), blk.conv.weight_r.grad.clone(), blk.bn.gamma.grad.clone())
+    del y_eager      # a live autograd graph would pin its AccumulateGrad nodes to the default stream and break the capture
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        step()
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        y_static = step()
+    for _ in range(2):
+        graph.replay()
+    torch.cuda.synchronize()
+    got = (y_static.detach(), x.grad, blk.conv.weight_r.grad, blk.bn.gamma.grad)
+    for a, b in zip(got, ref):
+        assert rel(a, b) <= 2e-3          # atomics in the narrow / depthwise wgrad make the last bits order-dependent
+
+
+def test_kernel_timing_facility_reports_library_kernels():
+    import ctypes
+    from quan_ultralytics_b200 import _lib
+    lib = _lib.load()
+    x = torch.randn(2, 64, 16, 16, 4, device=DEV).to(torch.bfloat16).contiguous(memory_format=torch.channels_last_3d)
+    w = [torch.randn(64, 64, 3, 3, device=DEV) * 0.05 for _ in range(4)]
+    lib.quan_kernel_timing_enable(1)
+    for _ in range(3):
+        ops.qconv2d_fwd(x, w, None, (1, 1), (1, 1), (1, 1), 1, ops.M_A, ops.ALGO_AUTO, L)
+    torch.cuda.synchronize()
+    lib.quan_kernel_timing_enable(0)
+    n = lib.quan_kernel_timing_report(None, 0)
+    buf = ctypes.create_string_buffer(n + 8)
+    lib.quan_kernel_timing_report(buf, n + 8)
+    rows = {ln.split()[0]: (int(ln.split()[1]), float(ln.split()[2])) for ln in buf.value.decode().splitlines()}
+    assert rows["qconv_igemm_fwd"][0] == 3 and rows["qconv_igemm_fwd"][1] > 0.0
+    assert rows["pack_weights_kernel"][0] == 3
