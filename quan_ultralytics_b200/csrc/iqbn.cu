@@ -1068,12 +1068,16 @@ static int launch_reduce(const void* x, const void* dy, int B, int C, int H, int
         g.tile_rows = tr;
         g.ntiles = (int)ceil_div64(g.R, tr);
         const size_t tile_bytes = (size_t)tr * row_bytes * (MODE == 1 ? 2 : 1);
-        int stages = (int)((96 * 1024) / tile_bytes);
+        // ncu (profiles/r01_iqbn_tune5.log): fed by TMA the reduction is issue-bound (62-68 % issue-active, 9.4 thread
+        // instructions per element); 3 or 4 smaller blocks per SM measured no better (42.6 / 50.1 vs 40.3 us with fold)
+        const int bps = env_int("QUAN_IQBN_TMA_BPS", 2);
+        const size_t ring = (size_t)env_int("QUAN_IQBN_TMA_KB", bps >= 3 ? 64 : 96) * 1024;
+        int stages = (int)(ring / tile_bytes);
         if (stages > 8) stages = 8;
         if (stages >= 2) {
           g.stages = stages;
           const size_t smem = stages * tile_bytes + 2 * stages * sizeof(uint64_t) + IQBN_TMA_CONSUMERS * 2 * sizeof(double) + 128;
-          int grid = g.ntiles < 2 * QUAN_NUM_SMS ? g.ntiles : 2 * QUAN_NUM_SMS;
+          int grid = g.ntiles < bps * QUAN_NUM_SMS ? g.ntiles : bps * QUAN_NUM_SMS;
           nparts = grid;
           QUAN_TIMED(st);
 #define QUAN_REDUCE_T(VV) { auto kern = iqbn_reduce_tma<T, VV, MODE, ACT>;                                                  \
