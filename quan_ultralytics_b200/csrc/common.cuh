@@ -111,6 +111,39 @@ template <int ACT, bool FAST = false> __device__ __forceinline__ float act_grad(
   return 1.0f;
 }
 
+// ---- packed fp32x2 arithmetic (sm_100: one instruction for two fp32 lanes in a 64-bit register pair) -------------------
+// The TMA-fed IQBN kernels are issue-bound (ncu: 62-68 % issue-active, memory stalls gone), so halving the FP32
+// instruction count per element is what moves them.
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+// two consecutive elements of a vector as an fp32 pair (bf16: one 32-bit word -> shift / mask; fp32: the two floats)
+__device__ __forceinline__ uint64_t f2_from(const __nv_bfloat16* p) {
+  const uint32_t w = *reinterpret_cast<const uint32_t*>(p);
+  return f2_pack(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
+__device__ __forceinline__ uint64_t f2_from(const float* p) { return f2_pack(p[0], p[1]); }
+
 // ---- small host helpers -----------------------------------------------------------------------
 static inline int conv_out(int in, int k, int s, int p, int d) { return (in + 2 * p - d * (k - 1) - 1) / s + 1; }
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -403,14 +403,24 @@ __global__ void __launch_bounds__(IQBN_TMA_THREADS, 2) iqbn_reduce_tma(const T* 
   const int rl = threadIdx.x / g.cvpg;
   const bool lane_on = rl < g.rpb;
   const int64_t coloff = (int64_t)cvl * V;
-  float scale[V], shift[V];
+  static_assert(V % 2 == 0, "packed fp32x2 lanes");
+  constexpr int P = V / 2;
+  // all per-element arithmetic runs on fp32 pairs (add / mul / fma .f32x2)
+  uint64_t hscale[P], hshift[P];            // 0.5*scale, 0.5*shift: z/2 feeds tanh directly (sigmoid = 0.5 tanh(z/2) + 0.5)
   if constexpr (MODE == 1 && ACT != QUAN_ACT_NONE) {
-    load_coef<float, V>(tail.stats + 12 * g.C + coloff, scale);
-    load_coef<float, V>(tail.stats + 16 * g.C + coloff, shift);
-  }
-  float s0[V], s1[V], k[V];
+    float sc[V], sh[V];
+    load_coef<float, V>(tail.stats + 12 * g.C + coloff, sc);
+    load_coef<float, V>(tail.stats + 16 * g.C + coloff, sh);
 #pragma unroll
-  for (int i = 0; i < V; ++i) s0[i] = s1[i] = k[i] = 0.f;
+    for (int i = 0; i < P; ++i) {
+      hscale[i] = f2_pack(0.5f * sc[2 * i], 0.5f * sc[2 * i + 1]);
+      hshift[i] = f2_pack(0.5f * sh[2 * i], 0.5f * sh[2 * i + 1]);
+    }
+  }
+  const uint64_t c_half = f2_pack(0.5f, 0.5f), c_nhalf = f2_pack(-0.5f, -0.5f), c_one = f2_pack(1.f, 1.f), c_two = f2_pack(2.f, 2.f);
+  uint64_t s0p[P], s1p[P], nk[P];           // sums, and MINUS the local shift k
+#pragma unroll
+  for (int i = 0; i < P; ++i) s0p[i] = s1p[i] = nk[i] = 0ull;
   int cnt = 0;
   bool have_k = false;
   int s = 0;
@@ -430,22 +440,39 @@ __global__ void __launch_bounds__(IQBN_TMA_THREADS, 2) iqbn_reduce_tma(const T* 
         if constexpr (MODE == 0) {
           if (!have_k) {                       // local shift: keeps fp32 partials well conditioned
 #pragma unroll
-            for (int i = 0; i < V; ++i) k[i] = to_f32(xa.v[i]);
+            for (int i = 0; i < P; ++i) nk[i] = f2_pack(-to_f32(xa.v[2 * i]), -to_f32(xa.v[2 * i + 1]));
             have_k = true;
           }
         }
 #pragma unroll
-        for (int i = 0; i < V; ++i) {
-          const float xv = to_f32(xa.v[i]);
+        for (int i = 0; i < P; ++i) {
+          const uint64_t xv = f2_from(&xa.v[2 * i]);
           if constexpr (MODE == 0) {
-            const float d = xv - k[i];
-            s0[i] += d;
-            s1[i] = fmaf(d, d, s1[i]);
+            const uint64_t d = f2_add(xv, nk[i]);
+            s0p[i] = f2_add(s0p[i], d);
+            s1p[i] = f2_fma(d, d, s1p[i]);
           } else {
-            float dz = to_f32(ga.v[i]);
-            if constexpr (ACT != QUAN_ACT_NONE) dz *= act_grad<ACT, sizeof(T) == 2>(fmaf(xv, scale[i], shift[i]));
-            s0[i] += dz;
-            s1[i] = fmaf(dz, xv, s1[i]);
+            uint64_t dz = f2_from(&ga.v[2 * i]);
+            if constexpr (ACT != QUAN_ACT_NONE) {
+              // dz *= s (1 + z (1 - s)),  s = 0.5 t + 0.5,  t = tanh(z/2):  1 - s = 0.5 - 0.5 t,  z (1 - s) = 2 zh (1 - s)
+              const uint64_t zh = f2_fma(xv, hscale[i], hshift[i]);
+              float z0, z1, t0, t1;
+              f2_unpack(zh, z0, z1);
+              if constexpr (sizeof(T) == 2) {
+                asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(z0));
+                asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(z1));
+              } else {                              // fp32 tensors keep the exact sigmoid (ex2 + rcp)
+                t0 = 2.f * sigmoid_f(2.f * z0) - 1.f;
+                t1 = 2.f * sigmoid_f(2.f * z1) - 1.f;
+              }
+              const uint64_t t = f2_pack(t0, t1);
+              const uint64_t sg = f2_fma(c_half, t, c_half);
+              const uint64_t oms = f2_fma(c_nhalf, t, c_half);
+              const uint64_t u = f2_fma(f2_mul(zh, oms), c_two, c_one);
+              dz = f2_mul(dz, f2_mul(sg, u));
+            }
+            s0p[i] = f2_add(s0p[i], dz);
+            s1p[i] = f2_fma(dz, xv, s1p[i]);
           }
         }
         ++cnt;
@@ -455,6 +482,16 @@ __global__ void __launch_bounds__(IQBN_TMA_THREADS, 2) iqbn_reduce_tma(const T* 
     if (ptx::elect_one()) ptx::mbar_arrive(empty_bar + s);
     __syncwarp();
     if (++s == g.stages) { s = 0; phase ^= 1; }
+  }
+  float s0[V], s1[V], k[V];
+#pragma unroll
+  for (int i = 0; i < P; ++i) {
+    f2_unpack(s0p[i], s0[2 * i], s0[2 * i + 1]);
+    f2_unpack(s1p[i], s1[2 * i], s1[2 * i + 1]);
+    float a, b;
+    f2_unpack(nk[i], a, b);
+    k[2 * i] = -a;
+    k[2 * i + 1] = -b;
   }
 
   // fold over the row lanes (consumer threads only: named barrier 1) and write this block's slot of the partials
