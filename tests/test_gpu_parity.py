@@ -334,3 +334,57 @@ def test_full_size_properties():
     lhs = conv(x32 + 2 * x2)
     rhs = conv(x32) + 2 * conv(x2)
     assert rel_err(lhs, rhs.detach().double().cpu().numpy()) <= TOL_F32
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# BASELINE config[0]: layers of the reference's Q-WRN-16-2 training step (tests/golden/make_qwrn_trace.py)
+@pytest.fixture(scope="module")
+def qwrn():
+    from pathlib import Path
+    return np.load(Path(__file__).resolve().parent / "golden" / "qwrn_trace.npz")
+
+
+@pytest.mark.parametrize("tag", ["conv_first", "conv_s2", "conv_deep"])
+def test_qwrn_trace_conv_layers(qwrn, tag):
+    """A QConv2D of the reference's Q-WRN-16-2 (classification flavour: M_B, bias) replayed with its recorded input,
+    weights and output gradient: output, input gradient, weight and bias gradients against the reference's autograd."""
+    g = lambda k: qwrn[f"{tag}/{k}"]
+    k, s, p, d, grp, has_bias = [int(v) for v in g("conf")]
+    co, ci = g("w_r").shape[:2]
+    first = g("x").ndim == 4
+    m = Q.QConv2D_B(3 if first else ci * grp * 4, co * 4, k, stride=s, padding=p, dilation=d, groups=grp, bias=bool(has_bias)).to(DEV)
+    with torch.no_grad():
+        for c in "rijk":
+            getattr(m, f"weight_{c}").copy_(to_dev(g(f"w_{c}")))
+        if has_bias:
+            m.bias_r.copy_(to_dev(g("bias_r")))
+    x = to_dev(g("x")).requires_grad_(not first)
+    y = m(x)
+    assert y.shape == g("y").shape
+    assert rel_err(y, g("y")) <= TOL_F32
+    y.backward(to_dev(g("dy")))
+    if not first:
+        assert rel_err(x.grad, g("dx")) <= 2 * TOL_F32
+    for c in "rijk":
+        assert rel_err(getattr(m, f"weight_{c}").grad, g(f"dw_{c}")) <= 2 * TOL_F32
+    if has_bias:
+        # every conv of the model feeds an IQBN, which removes the per-channel mean: the true bias gradient is ~1e-17, a
+        # sum of thousands of cancelling terms — compare on the scale of what is being summed
+        scale = float(np.abs(g("dy")).sum(axis=(0, 2, 3)).max())
+        assert float(np.abs(m.bias_r.grad.cpu().numpy() - g("db_r")).max()) <= 2 * TOL_F32 * scale
+
+
+@pytest.mark.parametrize("tag", ["bn_first", "bn_last"])
+def test_qwrn_trace_iqbn_layers(qwrn, tag):
+    g = lambda k: qwrn[f"{tag}/{k}"]
+    C_ = g("gamma").shape[0]
+    bn = Q.IQBN(C_ * 4, eps=float(g("eps"))).to(DEV).train()
+    with torch.no_grad():
+        bn.gamma.copy_(to_dev(g("gamma")))
+        bn.beta.copy_(to_dev(g("beta")))
+    x = to_dev(g("x")).requires_grad_(True)
+    y = bn(x)
+    assert rel_err(y, g("y")) <= 1e-4
+    y.backward(to_dev(g("dy")))
+    assert rel_err(x.grad, g("dx")) <= 1e-3
+    assert rel_err(bn.gamma.grad, g("dgamma")) <= 1e-3 and rel_err(bn.beta.grad, g("dbeta")) <= 1e-3

@@ -117,3 +117,26 @@ def test_eval_bwd_matches_autograd():
     z = (xt - v(rm)) / torch.sqrt(v(rv) + 1e-5) * v(gam) + v(bet)
     torch.nn.functional.silu(z).backward(torch.from_numpy(dy))
     np.testing.assert_allclose(O.iqbn_eval_bwd(dy, x, gam, bet, rm, rv, act=True), xt.grad.numpy(), rtol=1e-9, atol=1e-10)
+
+
+def test_oracle_matches_reference_qwrn_trace():
+    """BASELINE config[0]: layers recorded from the reference's Q-WRN-16-2 training step (make_qwrn_trace.py) through the
+    numpy oracle (classification flavour: mixing matrix M_B, bias on S_r)."""
+    from pathlib import Path
+    t = np.load(Path(__file__).resolve().parent / "golden" / "qwrn_trace.npz")
+    for tag in ("conv_s2", "conv_deep"):
+        g = lambda k: t[f"{tag}/{k}"].astype(np.float64)
+        k, s, p, d, grp, has_bias = [int(v) for v in t[f"{tag}/conf"]]
+        w = [g("w_r"), g("w_i"), g("w_j"), g("w_k")]
+        y = O.qconv2d_fwd(g("x"), w, g("bias_r") if has_bias else None, s, p, d, grp, O.M_B)
+        assert np.max(np.abs(y - g("y"))) / np.max(np.abs(g("y"))) <= 1e-5      # fixtures are stored in fp32
+        dx, dw, db = O.qconv2d_bwd(g("dy"), g("x"), w, s, p, d, grp, O.M_B, has_bias=bool(has_bias))
+        assert np.max(np.abs(dx - g("dx"))) / np.max(np.abs(g("dx"))) <= 1e-5
+        assert np.max(np.abs(dw[2] - g("dw_j"))) / np.max(np.abs(g("dw_j"))) <= 1e-5
+    for tag in ("bn_first", "bn_last"):
+        g = lambda k: t[f"{tag}/{k}"].astype(np.float64)
+        y, _, _, _ = O.iqbn_train_fwd(g("x"), g("gamma"), g("beta"), eps=float(t[f"{tag}/eps"]))
+        assert np.max(np.abs(y - g("y"))) / np.max(np.abs(g("y"))) <= 1e-5
+        dx, dg, db = O.iqbn_train_bwd(g("dy"), g("x"), g("gamma"), g("beta"), eps=float(t[f"{tag}/eps"]))
+        assert np.max(np.abs(dx - g("dx"))) / np.max(np.abs(g("dx"))) <= 2e-4
+        assert np.max(np.abs(dg - g("dgamma"))) / np.max(np.abs(g("dgamma"))) <= 2e-4
