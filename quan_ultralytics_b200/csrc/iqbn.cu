@@ -433,49 +433,64 @@ __global__ void __launch_bounds__(IQBN_TMA_THREADS, 2) iqbn_reduce_tma(const T* 
     const T* xt = reinterpret_cast<const T*>(ring + (size_t)s * NSTREAM * tile_bytes);
     const T* gt = xt + (size_t)g.tile_rows * g.L;
     if (lane_on) {
-      for (int r = rl; r < rows; r += g.rpb) {
-        const VecT xa = *reinterpret_cast<const VecT*>(xt + (size_t)r * g.L + coloff);
-        VecT ga;
-        if constexpr (MODE == 1) ga = *reinterpret_cast<const VecT*>(gt + (size_t)r * g.L + coloff);
-        if constexpr (MODE == 0) {
-          if (!have_k) {                       // local shift: keeps fp32 partials well conditioned
+      // UR rows per trip, all shared-memory loads first: ncu showed the one-row loop stalled on the LDS it had just issued
+      // (short-scoreboard on the first use, 4 warps per scheduler cannot hide 30 cycles per row)
+      constexpr int UR = MODE == 0 ? 4 : 2;
+      for (int r = rl; r < rows; r += UR * g.rpb) {
+        VecT xs[UR], gs[UR];
 #pragma unroll
-            for (int i = 0; i < P; ++i) nk[i] = f2_pack(-to_f32(xa.v[2 * i]), -to_f32(xa.v[2 * i + 1]));
-            have_k = true;
+        for (int u = 0; u < UR; ++u) {
+          const int ru = r + u * g.rpb;
+          if (ru < rows) {
+            xs[u] = *reinterpret_cast<const VecT*>(xt + (size_t)ru * g.L + coloff);
+            if constexpr (MODE == 1) gs[u] = *reinterpret_cast<const VecT*>(gt + (size_t)ru * g.L + coloff);
           }
         }
 #pragma unroll
-        for (int i = 0; i < P; ++i) {
-          const uint64_t xv = f2_from(&xa.v[2 * i]);
+        for (int u = 0; u < UR; ++u) {
+          if (r + u * g.rpb >= rows) break;
+          const VecT& xa = xs[u];
+          const VecT& ga = gs[u];
           if constexpr (MODE == 0) {
-            const uint64_t d = f2_add(xv, nk[i]);
-            s0p[i] = f2_add(s0p[i], d);
-            s1p[i] = f2_fma(d, d, s1p[i]);
-          } else {
-            uint64_t dz = f2_from(&ga.v[2 * i]);
-            if constexpr (ACT != QUAN_ACT_NONE) {
-              // dz *= s (1 + z (1 - s)),  s = 0.5 t + 0.5,  t = tanh(z/2):  1 - s = 0.5 - 0.5 t,  z (1 - s) = 2 zh (1 - s)
-              const uint64_t zh = f2_fma(xv, hscale[i], hshift[i]);
-              float z0, z1, t0, t1;
-              f2_unpack(zh, z0, z1);
-              if constexpr (sizeof(T) == 2) {
-                asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(z0));
-                asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(z1));
-              } else {                              // fp32 tensors keep the exact sigmoid (ex2 + rcp)
-                t0 = 2.f * sigmoid_f(2.f * z0) - 1.f;
-                t1 = 2.f * sigmoid_f(2.f * z1) - 1.f;
-              }
-              const uint64_t t = f2_pack(t0, t1);
-              const uint64_t sg = f2_fma(c_half, t, c_half);
-              const uint64_t oms = f2_fma(c_nhalf, t, c_half);
-              const uint64_t u = f2_fma(f2_mul(zh, oms), c_two, c_one);
-              dz = f2_mul(dz, f2_mul(sg, u));
+            if (!have_k) {                       // local shift: keeps fp32 partials well conditioned
+#pragma unroll
+              for (int i = 0; i < P; ++i) nk[i] = f2_pack(-to_f32(xa.v[2 * i]), -to_f32(xa.v[2 * i + 1]));
+              have_k = true;
             }
-            s0p[i] = f2_add(s0p[i], dz);
-            s1p[i] = f2_fma(dz, xv, s1p[i]);
           }
+#pragma unroll
+          for (int i = 0; i < P; ++i) {
+            const uint64_t xv = f2_from(&xa.v[2 * i]);
+            if constexpr (MODE == 0) {
+              const uint64_t d = f2_add(xv, nk[i]);
+              s0p[i] = f2_add(s0p[i], d);
+              s1p[i] = f2_fma(d, d, s1p[i]);
+            } else {
+              uint64_t dz = f2_from(&ga.v[2 * i]);
+              if constexpr (ACT != QUAN_ACT_NONE) {
+                // dz *= s (1 + z (1 - s)),  s = 0.5 t + 0.5,  t = tanh(z/2):  1 - s = 0.5 - 0.5 t,  z (1 - s) = 2 zh (1 - s)
+                const uint64_t zh = f2_fma(xv, hscale[i], hshift[i]);
+                float z0, z1, t0, t1;
+                f2_unpack(zh, z0, z1);
+                if constexpr (sizeof(T) == 2) {
+                  asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(z0));
+                  asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(z1));
+                } else {                              // fp32 tensors keep the exact sigmoid (ex2 + rcp)
+                  t0 = 2.f * sigmoid_f(2.f * z0) - 1.f;
+                  t1 = 2.f * sigmoid_f(2.f * z1) - 1.f;
+                }
+                const uint64_t t = f2_pack(t0, t1);
+                const uint64_t sg = f2_fma(c_half, t, c_half);
+                const uint64_t oms = f2_fma(c_nhalf, t, c_half);
+                const uint64_t u2 = f2_fma(f2_mul(zh, oms), c_two, c_one);
+                dz = f2_mul(dz, f2_mul(sg, u2));
+              }
+              s0p[i] = f2_add(s0p[i], dz);
+              s1p[i] = f2_fma(dz, xv, s1p[i]);
+            }
+          }
+          ++cnt;
         }
-        ++cnt;
       }
     }
     __syncwarp();

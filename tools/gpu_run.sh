@@ -1,1 +1,1 @@
-timeout 600 python -m pytest tests -m gpu -q 2>&1 | tail -8
+timeout 200 python tools/read_bw.py
