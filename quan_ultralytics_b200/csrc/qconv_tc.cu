@@ -1303,7 +1303,7 @@ static bool plan_wgrad(const quan_conv_dims& d, int dtype, int dense, WgradPlan&
   w.tap_groups = d.kH;
   w.MA = 128 / w.NA;                                 // atom slots that make M = 128
   // N = NB atoms of ci per CTA: as wide as TMEM (TG accumulators of N columns), UMMA (N <= 256, multiple of 16) and a
-  // >= 3-stage smem ring allow — wider N means fewer, longer MMAs per barrier round trip and fewer re-reads of the G tile
+  // >= 2-stage smem ring allow — wider N means fewer, longer MMAs per barrier round trip and fewer re-reads of the G tile
   const size_t atom = (size_t)WG_PIX * w.row_bytes;
   // halo mode: the kW taps of a filter row read the same pixels shifted by dW — one box per ci atom, (kW-1)*dW pixels
   // wider than the chunk, serves them all (B operand traffic / kW); needs stride 1 along W and K-steps that stay inside
@@ -1320,7 +1320,9 @@ static bool plan_wgrad(const quan_conv_dims& d, int dtype, int dense, WgradPlan&
     const int n = nb * w.NA;
     const size_t stage_nb = (size_t)w.MA * atom + b_stage(nb);
     if (w.Ci % n != 0 || n % 16 != 0 || w.TG * n > 512) continue;
-    if (w.NB != 0 && (200 * 1024) / stage_nb < 3) continue;
+    static const int min_stages = [] { const char* e = getenv("QUAN_TC_WG_MINSTAGES"); return e ? atoi(e) : 2; }();
+    // measured (tf32, C_q = 256): N = 128 with 2 stages 489 us vs N = 64 with 4 stages 631 us — wider N wins over ring depth
+    if (w.NB != 0 && (int)((200 * 1024) / stage_nb) < min_stages) continue;
     w.NB = nb;
   }
   if (w.NB == 0) return false;
