@@ -114,35 +114,47 @@ __device__ __forceinline__ void finish_accumulator(const TailArgs& t, int i, dou
   }
 }
 
-// Second kernel of every reduction (when the reduction kernel could not be launched cooperatively): fold the per-split partials of accumulator i = c*4+q and finish.
-// block = 8 accumulators x 32 split-groups (4 independent loads in flight per thread); grid = ceil(4C / 8).
-__global__ void __launch_bounds__(256) iqbn_fold_kernel(const double* __restrict__ part, int nparts, TailArgs t) {
-  __shared__ double red[2][32][9];
+// Second kernel of every reduction: fold the per-block partials of accumulator i = c*4+q and finish.  Pure latency:
+// block = 2 accumulators x 128 split lanes, so a thread walks only nparts / 128 (<= 5) partials, two at a time; the lanes
+// fold by shuffle (16 per warp) and a 16-entry shared-memory pass.  grid = ceil(4C / 2).
+constexpr int FOLD_ACC = 2, FOLD_LANES = 128;
+__global__ void __launch_bounds__(FOLD_ACC * FOLD_LANES) iqbn_fold_kernel(const double* __restrict__ part, int nparts, TailArgs t) {
+  __shared__ double red[2][FOLD_ACC * FOLD_LANES / 32][FOLD_ACC];
   const int n = 4 * t.C;
-  const int il = threadIdx.x & 7, gl = threadIdx.x >> 3;
-  const int i = blockIdx.x * 8 + il;
+  const int il = threadIdx.x % FOLD_ACC, gl = threadIdx.x / FOLD_ACC;
+  const int i = blockIdx.x * FOLD_ACC + il;
   double s0 = 0.0, s1 = 0.0;
   if (i < n) {
     int sp = gl;
-    for (; sp + 32 < nparts; sp += 64) {
+    for (; sp + FOLD_LANES < nparts; sp += 2 * FOLD_LANES) {
       const double a0 = part[((size_t)sp * 2 + 0) * n + i], a1 = part[((size_t)sp * 2 + 1) * n + i];
-      const double b0 = part[((size_t)(sp + 32) * 2 + 0) * n + i], b1 = part[((size_t)(sp + 32) * 2 + 1) * n + i];
+      const double b0 = part[((size_t)(sp + FOLD_LANES) * 2 + 0) * n + i], b1 = part[((size_t)(sp + FOLD_LANES) * 2 + 1) * n + i];
       s0 += a0 + b0;
       s1 += a1 + b1;
     }
-    for (; sp < nparts; sp += 32) {
+    if (sp < nparts) {
       s0 += part[((size_t)sp * 2 + 0) * n + i];
       s1 += part[((size_t)sp * 2 + 1) * n + i];
     }
   }
-  red[0][gl][il] = s0;
-  red[1][gl][il] = s1;
-  __syncthreads();
-  if (gl == 0 && i < n) {
+  // lanes of a warp: tid = gl*2 + il -> xor over bits 1..4 folds the warp's 16 split lanes of each accumulator
 #pragma unroll
-    for (int g = 1; g < 32; ++g) {
-      s0 += red[0][g][il];
-      s1 += red[1][g][il];
+  for (int o = FOLD_ACC; o < 32; o <<= 1) {
+    s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane < FOLD_ACC) {
+    red[0][warp][lane] = s0;
+    red[1][warp][lane] = s1;
+  }
+  __syncthreads();
+  if (threadIdx.x < FOLD_ACC && i < n) {
+    s0 = s1 = 0.0;
+#pragma unroll
+    for (int w = 0; w < FOLD_ACC * FOLD_LANES / 32; ++w) {
+      s0 += red[0][w][threadIdx.x];
+      s1 += red[1][w][threadIdx.x];
     }
     finish_accumulator(t, i, s0, s1);
   }
@@ -1141,7 +1153,7 @@ static int launch_reduce(const void* x, const void* dy, int B, int C, int H, int
 #undef QUAN_REDUCE_T
           QUAN_CHECK_LAUNCH(MODE == 0 ? "iqbn_reduce_fwd" : "iqbn_reduce_bwd");
           QUAN_TIMED(st);
-          iqbn_fold_kernel<<<(4 * C + 7) / 8, 256, 0, st>>>(ws.part, nparts, tail);
+          iqbn_fold_kernel<<<(4 * C + FOLD_ACC - 1) / FOLD_ACC, FOLD_ACC * FOLD_LANES, 0, st>>>(ws.part, nparts, tail);
           QUAN_CHECK_LAUNCH("iqbn_fold");
           return QUAN_OK;
         }
@@ -1182,7 +1194,7 @@ static int launch_reduce(const void* x, const void* dy, int B, int C, int H, int
   }
   QUAN_CHECK_LAUNCH(MODE == 0 ? "iqbn_reduce_fwd" : "iqbn_reduce_bwd");
   QUAN_TIMED(st);
-  iqbn_fold_kernel<<<(4 * C + 7) / 8, 256, 0, st>>>(ws.part, nparts, tail);
+  iqbn_fold_kernel<<<(4 * C + FOLD_ACC - 1) / FOLD_ACC, FOLD_ACC * FOLD_LANES, 0, st>>>(ws.part, nparts, tail);
   QUAN_CHECK_LAUNCH("iqbn_fold");
   return QUAN_OK;
 }
@@ -1354,7 +1366,7 @@ int quan_iqbn_finalize_partials(const void* workspace, int32_t nparts, double co
   t.beta = beta;
   cudaStream_t st = (cudaStream_t)stream;
   QUAN_TIMED(st);
-  iqbn_fold_kernel<<<(4 * C + 7) / 8, 256, 0, st>>>(reinterpret_cast<const double*>(workspace), nparts, t);
+  iqbn_fold_kernel<<<(4 * C + FOLD_ACC - 1) / FOLD_ACC, FOLD_ACC * FOLD_LANES, 0, st>>>(reinterpret_cast<const double*>(workspace), nparts, t);
   QUAN_CHECK_LAUNCH("iqbn_fold");
   return QUAN_OK;
 }
