@@ -117,72 +117,67 @@ __global__ void __launch_bounds__(256) qconv_dw_kernel(const T* __restrict__ in,
   }
 }
 
-// wgrad: one thread = one channel pair x 4 components, a block covers 256 / (C/2) output pixels per step and strides
-// over the image; per-thread accumulators [taps][4][2], folded over the block's pixel lanes through shared memory, then
-// one fp32 atomicAdd per (q, c, tap) and block into the zero-initialised dW (atomic order is not deterministic).
-template <typename T, int TAPS>
+// wgrad: one thread = one 16-byte channel vector of ONE component (q); a block covers blockDim / (4 * C/V) output pixels per
+// step and strides over the image.  Per pixel the thread loads dY of all four components of its channels (G_q = sum_p
+// M[p][q] dY_p) and the TAPS shifted x vectors of its own component: 4 + TAPS 16-byte loads (the first version used 4-byte
+// channel pairs, 40 loads per pixel, and was load-issue bound).  Accumulators [TAPS][V] in registers, folded over the
+// block's pixel lanes through shared memory, one fp32 atomic per (q, c, tap) and block into the zero-initialised dW
+// (atomic order is not deterministic).
+template <typename T, int V, int TAPS>
 __global__ void __launch_bounds__(256) qconv_dw_wgrad_kernel(const T* __restrict__ dy, const T* __restrict__ x, float* dw0,
                                                              float* dw1, float* dw2, float* dw3, DwGeom g, Mix16 M) {
-  __shared__ float red[256][9];
-  const int tpp = g.C / 2;                       // threads per pixel
+  __shared__ float red[256][V + 1];
+  const int cvs = g.C / V;
+  const int tpp = 4 * cvs;                       // threads per pixel: (q, channel vector)
   const int ppb = blockDim.x / tpp;              // pixel lanes per block
-  const int cp = threadIdx.x % tpp, pl = threadIdx.x / tpp;
+  const int tl = threadIdx.x % tpp, pl = threadIdx.x / tpp;
+  const int q = tl / cvs, cv = tl - q * cvs;
   const int64_t npix = (int64_t)g.B * g.Ho * g.Wo;
-  float acc[TAPS][4][2];
+  const int taps = g.kH * g.kW;
+  float acc[TAPS][V];
 #pragma unroll
   for (int t = 0; t < TAPS; ++t)
 #pragma unroll
-    for (int q = 0; q < 4; ++q) acc[t][q][0] = acc[t][q][1] = 0.f;
+    for (int v = 0; v < V; ++v) acc[t][v] = 0.f;
   if (pl < ppb) {
+    const float m0 = M.m[0 * 4 + q], m1 = M.m[1 * 4 + q], m2 = M.m[2 * 4 + q], m3 = M.m[3 * 4 + q];
     for (int64_t pix = (int64_t)blockIdx.x * ppb + pl; pix < npix; pix += (int64_t)gridDim.x * ppb) {
       const int wo = (int)(pix % g.Wo);
       const int64_t r = pix / g.Wo;
       const int ho = (int)(r % g.Ho);
       const int b = (int)(r / g.Ho);
-      float gy[4][2], gq[4][2];
-      const T* gsrc = dy + (pix * 4) * g.C + cp * 2;
+      float gy[4][V], gq[V];
+      const T* gsrc = dy + (pix * 4) * g.C + cv * V;
 #pragma unroll
-      for (int p = 0; p < 4; ++p) load_vec<T, 2>(gsrc + (int64_t)p * g.C, gy[p]);
+      for (int p = 0; p < 4; ++p) load_vec<T, V>(gsrc + (int64_t)p * g.C, gy[p]);
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
-#pragma unroll
-        for (int v = 0; v < 2; ++v)
-          gq[q][v] = M.m[0 * 4 + q] * gy[0][v] + M.m[1 * 4 + q] * gy[1][v] + M.m[2 * 4 + q] * gy[2][v] + M.m[3 * 4 + q] * gy[3][v];
+      for (int v = 0; v < V; ++v) gq[v] = m0 * gy[0][v] + m1 * gy[1][v] + m2 * gy[2][v] + m3 * gy[3][v];
 #pragma unroll
       for (int t = 0; t < TAPS; ++t) {
         const int kh = t / g.kW, kw = t - kh * g.kW;
         const int hi = ho * g.sH - g.pH + kh * g.dH, wi = wo * g.sW - g.pW + kw * g.dW;
-        if (t < g.kH * g.kW && hi >= 0 && hi < g.H && wi >= 0 && wi < g.W) {
-          const T* xs = x + ((((int64_t)b * g.H + hi) * g.W + wi) * 4) * g.C + cp * 2;
+        if (t < taps && hi >= 0 && hi < g.H && wi >= 0 && wi < g.W) {
+          float xv[V];
+          load_vec<T, V>(x + ((((int64_t)b * g.H + hi) * g.W + wi) * 4 + q) * g.C + cv * V, xv);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float xv[2];
-            load_vec<T, 2>(xs + (int64_t)q * g.C, xv);
-            acc[t][q][0] = fmaf(gq[q][0], xv[0], acc[t][q][0]);
-            acc[t][q][1] = fmaf(gq[q][1], xv[1], acc[t][q][1]);
-          }
+          for (int v = 0; v < V; ++v) acc[t][v] = fmaf(gq[v], xv[v], acc[t][v]);
         }
       }
     }
   }
-  const int taps = g.kH * g.kW;
-  for (int t = 0; t < TAPS; ++t) {
-    if (t >= taps) break;
+  float* dw = q == 0 ? dw0 : q == 1 ? dw1 : q == 2 ? dw2 : dw3;
+#pragma unroll
+  for (int t = 0; t < TAPS; ++t) {               // unrolled: acc[][] must stay in registers (no dynamic indexing)
     __syncthreads();
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      red[threadIdx.x][q * 2 + 0] = acc[t][q][0];
-      red[threadIdx.x][q * 2 + 1] = acc[t][q][1];
-    }
+    for (int v = 0; v < V; ++v) red[threadIdx.x][v] = pl < ppb ? acc[t][v] : 0.f;
     __syncthreads();
-    if (pl == 0) {
+    if (pl == 0 && t < taps) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int v = 0; v < V; ++v) {
         float s = 0.f;
-        for (int l = 0; l < ppb; ++l) s += red[l * tpp + cp][j];
-        const int q = j >> 1, c = cp * 2 + (j & 1);
-        float* dw = q == 0 ? dw0 : q == 1 ? dw1 : q == 2 ? dw2 : dw3;
-        atomicAdd(dw + (int64_t)c * taps + t, s);
+        for (int l = 0; l < ppb; ++l) s += red[l * tpp + tl][v];
+        atomicAdd(dw + (int64_t)(cv * V + v) * taps + t, s);
       }
     }
   }
@@ -194,7 +189,7 @@ bool qconv_dw_supported(const quan_conv_dims& d, int dtype, int layout, int pass
   const int V = dtype == QUAN_BF16 ? 8 : 4;
   if (d.Ci % V != 0 && d.Ci % (V / 2) != 0) return false;
   if ((size_t)d.kH * d.kW * 4 * d.Ci * sizeof(float) > 40 * 1024) return false;
-  if (pass == PASS_WGRAD) return d.kH * d.kW <= 9 && d.Ci % 2 == 0 && d.Ci / 2 <= 256;
+  if (pass == PASS_WGRAD) return d.kH * d.kW <= 9 && 4 * (d.Ci / (d.Ci % V == 0 ? V : V / 2)) <= 256;
   return true;
 }
 
@@ -240,18 +235,23 @@ int qconv_dw_wgrad(const void* dy, const void* x, float* const dw[4], const quan
   const Mix16 M = make_mix(mix);
   const int taps = d.kH * d.kW;
   for (int q = 0; q < 4; ++q) QUAN_CUDA(cudaMemsetAsync(dw[q], 0, (size_t)d.Co * taps * sizeof(float), st));
-  const int tpp = g.C / 2, ppb = 256 / tpp;
+  const int VMAX = dtype == QUAN_BF16 ? 8 : 4;
+  const int V = g.C % VMAX == 0 ? VMAX : VMAX / 2;
+  const int tpp = 4 * (g.C / V), ppb = 256 / tpp;
   const int64_t npix = (int64_t)g.B * g.Ho * g.Wo;
   int64_t blocks = ceil_div64(npix, (int64_t)ppb * 16);          // >= 16 pixels per pixel lane
   if (blocks > QUAN_NUM_SMS * 4) blocks = QUAN_NUM_SMS * 4;
   if (blocks < 1) blocks = 1;
   QUAN_TIMED(st);
-  if (dtype == QUAN_BF16)
-    qconv_dw_wgrad_kernel<__nv_bfloat16, 9><<<(unsigned)blocks, 256, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x,
-                                                                               dw[0], dw[1], dw[2], dw[3], g, M);
-  else
-    qconv_dw_wgrad_kernel<float, 9><<<(unsigned)blocks, 256, 0, st>>>((const float*)dy, (const float*)x, dw[0], dw[1], dw[2],
-                                                                       dw[3], g, M);
+  if (dtype == QUAN_BF16) {
+    const __nv_bfloat16 *dyp = (const __nv_bfloat16*)dy, *xp = (const __nv_bfloat16*)x;
+    if (V == 8) qconv_dw_wgrad_kernel<__nv_bfloat16, 8, 9><<<(unsigned)blocks, 256, 0, st>>>(dyp, xp, dw[0], dw[1], dw[2], dw[3], g, M);
+    else qconv_dw_wgrad_kernel<__nv_bfloat16, 4, 9><<<(unsigned)blocks, 256, 0, st>>>(dyp, xp, dw[0], dw[1], dw[2], dw[3], g, M);
+  } else {
+    const float *dyp = (const float*)dy, *xp = (const float*)x;
+    if (V == 4) qconv_dw_wgrad_kernel<float, 4, 9><<<(unsigned)blocks, 256, 0, st>>>(dyp, xp, dw[0], dw[1], dw[2], dw[3], g, M);
+    else qconv_dw_wgrad_kernel<float, 2, 9><<<(unsigned)blocks, 256, 0, st>>>(dyp, xp, dw[0], dw[1], dw[2], dw[3], g, M);
+  }
   QUAN_CHECK_LAUNCH("qconv_dw_wgrad_kernel");
   return QUAN_OK;
 }

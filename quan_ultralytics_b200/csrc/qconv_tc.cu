@@ -833,13 +833,15 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
   const int ci0 = blockIdx.x * cchunk, nci = min(cchunk, Ci - ci0);
   const int items = nci * taps;
   const int64_t split_stride = (int64_t)(DENSE ? 16 : 4) * taps * Co * Ci;
-  // thread -> (split lane sl, channel ci) once; the tap loop needs no integer division
-  const int lanes_ci = SL > 1 ? nci : blockDim.x;                // SL > 1 only when nci * taps * SL <= blockDim.x
-  const int sl = SL > 1 ? (int)threadIdx.x / (nci * taps) : 0;
-  const int rem = SL > 1 ? (int)threadIdx.x % (nci * taps) : 0;
-  for (int tap = SL > 1 ? rem / nci : 0; tap < taps; tap += SL > 1 ? taps : 1) {
-    if (SL > 1 && sl >= SL) break;
-    for (int ci = SL > 1 ? rem % nci : (int)threadIdx.x; ci < nci; ci += lanes_ci) {
+  // small blocks (items * SL <= blockDim: narrow layers): one (split lane, tap, ci) per thread, one division per thread;
+  // large blocks (wide layers, SL = 1): nested tap / ci loops, no division per element
+  const bool small = items * SL <= (int)blockDim.x;
+  const int lanes_ci = small ? nci : (int)blockDim.x;
+  const int sl = small ? (int)threadIdx.x / items : 0;
+  const int rem = small ? (int)threadIdx.x % items : 0;
+  for (int tap = small ? rem / nci : 0; tap < taps; tap += small ? taps : 1) {
+    if (small && sl >= SL) break;
+    for (int ci = small ? rem % nci : (int)threadIdx.x; ci < nci; ci += lanes_ci) {
       float s = 0.f;
       if constexpr (DENSE) {
 #pragma unroll

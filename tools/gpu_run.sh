@@ -1,2 +1,3 @@
-python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-kernel-table > gpurun_out/plain_b.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -s 400 -c 300 --csv --log-file gpurun_out/launches_bench_final.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-kernel-table > gpurun_out/ncu_b.log 2>&1
-python bench.py --workload yolo11n_trace --steps 1 --warmup 3 > gpurun_out/plain_t.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -s 2700 -c 950 --csv --log-file gpurun_out/launches_trace_final.csv python bench.py --workload yolo11n_trace --steps 1 --warmup 3 > gpurun_out/ncu_t.log 2>&1
+timeout 600 python -m pytest tests -m gpu -q 2>&1 | tail -3
+timeout 300 python bench.py --workload yolo11n_trace --steps 5 --warmup 3 --graph 2>&1 | tail -1 | cut -c1-200
+QUAN_TRACE_KERNELS=1 timeout 300 python bench.py --workload yolo11n_trace --steps 3 --warmup 3 2>&1 | grep -E "ms/step" | head -14
