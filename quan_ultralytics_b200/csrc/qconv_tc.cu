@@ -18,6 +18,8 @@
 #include "tc_ptx.cuh"
 #include <mutex>
 #include <stdlib.h>
+#include <string.h>
+#include <unordered_map>
 
 namespace quan {
 
@@ -1472,7 +1474,25 @@ static bool prefer_dense(int k_channels, int dtype) {   // k_channels: per-compo
   return k_channels * (dtype == QUAN_BF16 ? 2 : 4) <= 64;
 }
 
-int qconv_tc_mode(const quan_conv_dims& d, int dtype, int layout, int pass) {
+// shape -> answer memo (per host thread): the API layer asks for the mode / workspace of a shape several times per call
+// and planning walks the tap table and the split-K cost model each time
+struct ShapeKey {
+  int v[18];
+  bool operator==(const ShapeKey& o) const { return memcmp(v, o.v, sizeof(v)) == 0; }
+};
+struct ShapeKeyHash {
+  size_t operator()(const ShapeKey& k) const {
+    uint64_t h = 1469598103934665603ull;
+    for (int i = 0; i < 18; ++i) { h ^= (uint32_t)k.v[i]; h *= 1099511628211ull; }
+    return (size_t)h;
+  }
+};
+static ShapeKey shape_key(const quan_conv_dims& d, int dtype, int layout, int pass, int what) {
+  ShapeKey k = {{d.B, d.Ci, d.Co, d.H, d.W, d.kH, d.kW, d.sH, d.sW, d.pH, d.pW, d.dH, d.dW, d.groups, dtype, layout, pass, what}};
+  return k;
+}
+
+static int qconv_tc_mode_uncached(const quan_conv_dims& d, int dtype, int layout, int pass) {
   if (layout != QUAN_LAYOUT_BHWQC || d.groups != 1) return TC_NONE;
   if (get_encode_fn() == nullptr) return TC_NONE;
   const int e = env_dense();
@@ -1496,16 +1516,39 @@ int qconv_tc_mode(const quan_conv_dims& d, int dtype, int layout, int pass) {
   return sep ? TC_SEPARABLE : TC_NONE;
 }
 
+int qconv_tc_mode(const quan_conv_dims& d, int dtype, int layout, int pass) {
+  static thread_local std::unordered_map<ShapeKey, int, ShapeKeyHash> memo;
+  const ShapeKey k = shape_key(d, dtype, layout, pass, 0);
+  auto it = memo.find(k);
+  if (it != memo.end()) return it->second;
+  const int m = qconv_tc_mode_uncached(d, dtype, layout, pass);
+  if (memo.size() > 4096) memo.clear();
+  memo[k] = m;
+  return m;
+}
+
 bool qconv_tc_supported(const quan_conv_dims& d, int dtype, int layout, int pass) {
   return qconv_tc_mode(d, dtype, layout, pass) != TC_NONE;
 }
 
 size_t qconv_tc_workspace_bytes(const quan_conv_dims& d, int dtype, int layout, int pass) {
+  static thread_local std::unordered_map<ShapeKey, size_t, ShapeKeyHash> memo;
+  const ShapeKey k = shape_key(d, dtype, layout, pass, 1);
+  auto it = memo.find(k);
+  if (it != memo.end()) return it->second;
   const int mode = qconv_tc_mode(d, dtype, layout, pass);
-  if (mode == TC_NONE) return 0;
-  if (pass == PASS_FWD || pass == PASS_DGRAD) return packed_weight_bytes(d, dtype, mode == TC_DENSE);
-  WgradPlan w;
-  return plan_wgrad(d, dtype, mode == TC_DENSE, w) ? w.partial_bytes : 0;
+  size_t bytes = 0;
+  if (mode != TC_NONE) {
+    if (pass == PASS_FWD || pass == PASS_DGRAD) {
+      bytes = packed_weight_bytes(d, dtype, mode == TC_DENSE);
+    } else {
+      WgradPlan w;
+      bytes = plan_wgrad(d, dtype, mode == TC_DENSE, w) ? w.partial_bytes : 0;
+    }
+  }
+  if (memo.size() > 4096) memo.clear();
+  memo[k] = bytes;
+  return bytes;
 }
 
 template <typename T>

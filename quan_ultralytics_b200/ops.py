@@ -23,9 +23,17 @@ MIX = {"A": M_A, "B": M_B}
 _FloatArr16 = C.c_float * 16
 
 
+_mix_cache = {}
+
+
 def _mix_arg(mix: Sequence[float]):
-    assert len(mix) == 16
-    return _FloatArr16(*[float(v) for v in mix])
+    """ctypes float[16] of a mixing matrix (cached: the same two or three matrices are passed on every call)."""
+    key = tuple(mix)
+    arr = _mix_cache.get(key)
+    if arr is None:
+        assert len(key) == 16
+        arr = _mix_cache[key] = _FloatArr16(*[float(v) for v in key])
+    return arr
 
 
 def _mix_t(mix: Sequence[float]) -> Tuple[float, ...]:
@@ -302,6 +310,19 @@ def iqbn_eval_bwd(dy, x, layout: int, gamma, beta, running_mean, running_var, ep
 
 
 # ---- QConv2D ---------------------------------------------------------------------------------------------------------
+_ws_bytes_cache = {}
+_wants_mixed_cache = {}
+
+
+def _conv_ws_bytes(lib, d: ConvDims, dtype_code: int, layout: int, algo: int) -> int:
+    """quan_qconv2d_workspace_bytes, cached per shape (the C side plans all three passes to answer)."""
+    key = (d.B, d.Ci, d.Co, d.H, d.W, d.kH, d.kW, d.sH, d.sW, d.pH, d.pW, d.dH, d.dW, d.groups, dtype_code, layout, algo)
+    n = _ws_bytes_cache.get(key)
+    if n is None:
+        n = _ws_bytes_cache[key] = lib.quan_qconv2d_workspace_bytes(C.byref(d), dtype_code, layout, algo)
+    return n
+
+
 def conv_dims(x_shape, w_shape, stride, padding, dilation, groups) -> ConvDims:
     B, Ci, H, W, _ = x_shape
     Co, _, kH, kW = w_shape
@@ -337,7 +358,7 @@ def qconv2d_fwd(x: torch.Tensor, weights: Sequence[torch.Tensor], bias_r: Option
         raise RuntimeError(f"qconv2d_fwd: empty output for input {tuple(x.shape)} and kernel {tuple(ws[0].shape)}")
     y = empty_q((d.B, d.Co, Ho, Wo, 4), x.dtype, x.device, layout)
     lib = _lib.load()
-    nws = lib.quan_qconv2d_workspace_bytes(C.byref(d), _dtype_code(x), layout, algo)
+    nws = _conv_ws_bytes(lib, d, _dtype_code(x), layout, algo)
     wsb = _workspace(nws, x.device)
     wa = _weights_arg(ws)
     if with_stats:
@@ -380,7 +401,7 @@ def qconv2d_bwd(dy: torch.Tensor, x: torch.Tensor, weights: Sequence[torch.Tenso
     dx = torch.empty_like(x, memory_format=torch.preserve_format) if need_dx else None
     dws = [torch.empty_like(w) for w in ws] if need_dw else None
     db = torch.empty(d.Co, dtype=torch.float32, device=x.device) if need_db else None
-    nws = lib.quan_qconv2d_workspace_bytes(C.byref(d), _dtype_code(x), layout, algo)
+    nws = _conv_ws_bytes(lib, d, _dtype_code(x), layout, algo)
     wsb = _workspace(nws, x.device)
     wa = _weights_arg(ws)
     dwa = None if dws is None else _weights_arg(dws)
@@ -395,9 +416,14 @@ def qconv2d_bwd(dy: torch.Tensor, x: torch.Tensor, weights: Sequence[torch.Tenso
 def qconv2d_bwd_wants_mixed(x_shape, w_shape, stride, padding, dilation, groups, dtype: torch.dtype, layout: int,
                             algo: int = ALGO_AUTO, need_dx: bool = True, need_dw: bool = True) -> bool:
     """True when every requested backward pass of this conv reads G = M^T dY (so the IQBN backward can emit G directly)."""
-    d = conv_dims(x_shape, w_shape, stride, padding, dilation, groups)
-    return _lib.load().quan_qconv2d_bwd_wants_mixed(C.byref(d), F32 if dtype == torch.float32 else BF16, layout, algo,
-                                                    int(need_dx), int(need_dw)) == 1
+    key = (tuple(x_shape), tuple(w_shape), tuple(stride), tuple(padding), tuple(dilation), groups, dtype, layout, algo,
+           bool(need_dx), bool(need_dw))
+    r = _wants_mixed_cache.get(key)
+    if r is None:
+        d = conv_dims(x_shape, w_shape, stride, padding, dilation, groups)
+        r = _wants_mixed_cache[key] = _lib.load().quan_qconv2d_bwd_wants_mixed(
+            C.byref(d), F32 if dtype == torch.float32 else BF16, layout, algo, int(need_dx), int(need_dw)) == 1
+    return r
 
 
 def qconv2d_pick_algo(x_shape, w_shape, stride, padding, dilation, groups, dtype: torch.dtype, layout: int,
