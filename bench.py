@@ -32,8 +32,8 @@ import torch  # noqa: E402
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="block_stack", choices=["block_stack", "yolo11n_trace"],
                     help="block_stack: BASELINE config[1] sweep point (default, the bench line); yolo11n_trace: replay of "
