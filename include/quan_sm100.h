@@ -193,6 +193,20 @@ int quan_qconv2d_bwd_wants_mixed(const quan_conv_dims* d, int dtype, int layout,
 /* reports which engine AUTO would pick for this shape: QUAN_ALGO_DIRECT, QUAN_ALGO_TCGEN05, QUAN_ALGO_DEPTHWISE or QUAN_ALGO_SMALLC */
 int quan_qconv2d_pick_algo(const quan_conv_dims* d, int dtype, int layout, int pass /*0 fwd,1 dgrad,2 wgrad*/);
 
+/* ---- the reference's Conv block in one call per direction ---------------------------------------------------------------
+ * QConv2D (bias-free) -> IQBN with batch statistics -> act (ultralytics/nn/modules/conv.py:805-809 `Conv.forward`, and its
+ * autograd).  Sequences the entry points above (same kernels, same results); exists because the eager step of a narrow layer
+ * is bound by host time per call.  y: conv output (kept for the backward), out: activated output, stats: [20*Co];
+ * g: scratch tensor shaped like y; sums: [14*Co] doubles; dx / dw may be NULL; workspaces as for the separate calls. */
+int quan_conv_block_fwd(const void* x, const float* const w[4], const float* gamma, const float* beta, float* running_mean,
+                        float* running_var, void* y, void* out, float* stats, const quan_conv_dims* d, int dtype, int layout,
+                        const float* mix, int algo, float eps, float momentum, int act, int epilogue_stats, void* conv_ws,
+                        size_t conv_ws_bytes, void* iqbn_ws, size_t iqbn_ws_bytes, void* stream);
+int quan_conv_block_bwd(const void* dout, const void* x, const void* y, const float* const w[4], const float* stats,
+                        const float* gamma, const float* beta, void* g, void* dx, float* const dw[4], float* dgamma,
+                        float* dbeta, double* sums, const quan_conv_dims* d, int dtype, int layout, const float* mix, int algo,
+                        int act, void* conv_ws, size_t conv_ws_bytes, void* iqbn_ws, size_t iqbn_ws_bytes, void* stream);
+
 /* Optional per-kernel device timing for benchmarks (no reference counterpart): while enabled, every kernel the library
  * launches outside stream capture is bracketed by a CUDA-event pair on its own stream.  `enable(1)` clears earlier
  * records.  `report` synchronises the recorded events and writes one "kernel_name launches total_ms" line per kernel

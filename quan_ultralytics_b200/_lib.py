@@ -61,6 +61,10 @@ PROTOTYPES = {
     "quan_qconv2d_pick_algo": (_int, [_pdims, _int, _int, _int]),
     "quan_qconv2d_fwd_stats": (_int, [_vp, _vp, _vp, _vp, _pdims, _int, _int, _vp, _int, _vp, _sz, _vp, _sz, C.POINTER(C.c_int), _vp]),
     "quan_iqbn_finalize_partials": (_int, [_vp, _i32, _d, _i32, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp]),
+    "quan_conv_block_fwd": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _pdims, _int, _int, _vp, _int, _f, _f, _int, _int,
+                                   _vp, _sz, _vp, _sz, _vp]),
+    "quan_conv_block_bwd": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _pdims, _int, _int, _vp, _int,
+                                   _int, _vp, _sz, _vp, _sz, _vp]),
     "quan_qconv2d_bwd_premixed": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _pdims, _int, _int, _vp, _int, _vp, _sz, _vp]),
     "quan_qconv2d_bwd_wants_mixed": (_int, [_pdims, _int, _int, _int, _int, _int]),
 }

@@ -143,39 +143,27 @@ class _ConvBlock(torch.autograd.Function):
                 algo, eps, momentum, act):
         x, layout = ops.as_layout(x, _state["layout"])
         ws = (w_r, w_i, w_j, w_k)
-        # the tensor-core epilogue also leaves per-CTA partial IQBN sums of y in the IQBN workspace: no statistics pass over y
-        y, nparts = ops.qconv2d_fwd(x, ws, None, stride, padding, dilation, groups, mix, algo, layout,
-                                    with_stats=_state["epilogue_stats"])
         g32, b32 = ops._f32c(gamma), ops._f32c(beta)
-        B, C_, H, W, _ = y.shape
-        if nparts > 0:
-            stats = ops.iqbn_finalize_partials(nparts, float(B * H * W), C_, g32, b32, eps, momentum, running_mean,
-                                               running_var)
-        else:
-            stats = ops.iqbn_train_stats(y, layout, g32, b32, eps, momentum, running_mean, running_var)
-        out = ops.iqbn_apply_fwd(y, layout, stats, g32, b32, act)
+        # one C call: conv (its tensor-core epilogue may already leave the partial IQBN sums) -> statistics -> apply + act
+        y, out, stats = ops.conv_block_fwd(x, ws, g32, b32, running_mean, running_var, stride, padding, dilation, groups, mix,
+                                           algo, eps, momentum, act, layout, _state["epilogue_stats"])
         ctx.save_for_backward(x, y, stats, g32, b32, w_r, w_i, w_j, w_k)
-        ctx.conf = (tuple(stride), tuple(padding), tuple(dilation), int(groups), tuple(mix), algo, layout, act,
-                    float(B * H * W), gamma.dtype)
+        ctx.conf = (tuple(stride), tuple(padding), tuple(dilation), int(groups), tuple(mix), algo, layout, act, gamma.dtype)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         x, y, stats, g32, b32, w_r, w_i, w_j, w_k = ctx.saved_tensors
-        stride, padding, dilation, groups, mix, algo, layout, act, count, pdtype = ctx.conf
+        stride, padding, dilation, groups, mix, algo, layout, act, pdtype = ctx.conf
         ws = (w_r, w_i, w_j, w_k)
         dout, _ = ops.as_layout(dout, layout)
         if dout.dtype != y.dtype:
             dout = dout.to(y.dtype)
         need_dx = ctx.needs_input_grad[0]
         need_dw = any(ctx.needs_input_grad[1:5])
-        sums = ops.iqbn_bwd_reduce(dout, y, layout, stats, g32, b32, act, count)
-        mixed = (need_dx or need_dw) and ops.qconv2d_bwd_wants_mixed(x.shape, w_r.shape, stride, padding, dilation, groups,
-                                                                    x.dtype, layout, algo, need_dx, need_dw)
-        dy, dgamma, dbeta = ops.iqbn_bwd_apply(dout, y, layout, stats, g32, b32, act, sums, count,
-                                               mix_t=ops._mix_t(mix) if mixed else None)
-        dx, dws, _ = ops.qconv2d_bwd(dy, x, ws, stride, padding, dilation, groups, mix, need_dx, need_dw, False, algo,
-                                     premixed=mixed)
+        # one C call: IQBN backward sums -> apply (emitting G = M^T dY when the conv backward reads G) -> dgrad / wgrad
+        dx, dws, dgamma, dbeta = ops.conv_block_bwd(dout, x, y, ws, stats, g32, b32, stride, padding, dilation, groups, mix,
+                                                    algo, act, layout, need_dx, need_dw)
         if dws is None:
             dws = [None] * 4
         else:

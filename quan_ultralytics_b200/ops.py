@@ -430,3 +430,54 @@ def qconv2d_pick_algo(x_shape, w_shape, stride, padding, dilation, groups, dtype
                       pass_: int = 0) -> int:
     d = conv_dims(x_shape, w_shape, stride, padding, dilation, groups)
     return _lib.load().quan_qconv2d_pick_algo(C.byref(d), F32 if dtype == torch.float32 else BF16, layout, pass_)
+
+
+# ---- Conv block (conv -> IQBN(batch stats) -> act) in one C call per direction ------------------------------------------
+def conv_block_fwd(x: torch.Tensor, weights: Sequence[torch.Tensor], gamma, beta, running_mean, running_var, stride, padding,
+                   dilation, groups: int, mix_matrix: Sequence[float], algo: int, eps: float, momentum: float, act: int,
+                   layout: int, epilogue_stats: bool = True):
+    """Returns (y = conv output, out = act(IQBN(y)), stats[20*C_o]); x must already be dense in `layout`."""
+    ws = [_f32c(w) for w in weights]
+    d = conv_dims(x.shape, ws[0].shape, stride, padding, dilation, groups)
+    Ho, Wo = conv_out_shape(d)
+    if Ho <= 0 or Wo <= 0 or x.size(1) != ws[0].size(1) * groups:
+        raise RuntimeError(f"conv_block_fwd: input {tuple(x.shape)} does not fit weight {tuple(ws[0].shape)} (groups={groups})")
+    y = empty_q((d.B, d.Co, Ho, Wo, 4), x.dtype, x.device, layout)
+    out = torch.empty_like(y, memory_format=torch.preserve_format)
+    stats = torch.empty(20 * d.Co, dtype=torch.float32, device=x.device)
+    lib = _lib.load()
+    code = _dtype_code(x)
+    wsb = _workspace(_conv_ws_bytes(lib, d, code, layout, algo), x.device)
+    iws = _iqbn_workspace(d.Co, x.device)
+    wa = _weights_arg(ws)
+    check(lib.quan_conv_block_fwd(x.data_ptr(), C.cast(wa, C.c_void_p), gamma.data_ptr(), beta.data_ptr(), _ptr(running_mean),
+                                  _ptr(running_var), y.data_ptr(), out.data_ptr(), stats.data_ptr(), C.byref(d), code, layout,
+                                  C.cast(_mix_arg(mix_matrix), C.c_void_p), algo, eps, momentum, act, int(epilogue_stats),
+                                  wsb.data_ptr(), wsb.numel(), iws.data_ptr(), iws.numel(), _stream(x)), "quan_conv_block_fwd")
+    return y, out, stats
+
+
+def conv_block_bwd(dout: torch.Tensor, x: torch.Tensor, y: torch.Tensor, weights: Sequence[torch.Tensor], stats, gamma, beta,
+                   stride, padding, dilation, groups: int, mix_matrix: Sequence[float], algo: int, act: int, layout: int,
+                   need_dx: bool, need_dw: bool):
+    """Returns (dx or None, [dw x4] or None, dgamma, dbeta); dout / x / y dense in `layout`."""
+    ws = [_f32c(w) for w in weights]
+    d = conv_dims(x.shape, ws[0].shape, stride, padding, dilation, groups)
+    lib = _lib.load()
+    code = _dtype_code(x)
+    g = torch.empty_like(y, memory_format=torch.preserve_format)
+    dx = torch.empty_like(x, memory_format=torch.preserve_format) if need_dx else None
+    dws = [torch.empty_like(w) for w in ws] if need_dw else None
+    dgamma = torch.empty(d.Co, 4, dtype=torch.float32, device=x.device)
+    dbeta = torch.empty(d.Co, 4, dtype=torch.float32, device=x.device)
+    sums = torch.empty(14 * d.Co, dtype=torch.float64, device=x.device)
+    wsb = _workspace(_conv_ws_bytes(lib, d, code, layout, algo), x.device)
+    iws = _iqbn_workspace(d.Co, x.device)
+    wa = _weights_arg(ws)
+    dwa = None if dws is None else _weights_arg(dws)
+    check(lib.quan_conv_block_bwd(dout.data_ptr(), x.data_ptr(), y.data_ptr(), C.cast(wa, C.c_void_p), stats.data_ptr(),
+                                  gamma.data_ptr(), beta.data_ptr(), g.data_ptr(), _ptr(dx),
+                                  None if dwa is None else C.cast(dwa, C.c_void_p), dgamma.data_ptr(), dbeta.data_ptr(),
+                                  sums.data_ptr(), C.byref(d), code, layout, C.cast(_mix_arg(mix_matrix), C.c_void_p), algo, act,
+                                  wsb.data_ptr(), wsb.numel(), iws.data_ptr(), iws.numel(), _stream(x)), "quan_conv_block_bwd")
+    return dx, dws, dgamma, dbeta
