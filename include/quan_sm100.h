@@ -161,7 +161,14 @@ int quan_layout_convert(const void* src, int src_layout, void* dst, int dst_layo
  *   the reference extension's `sum dY_r`, quaternion_ops.cu:500, is a documented defect — SURVEY §8(c)).
  * w[4]: fp32 master weights, each [Co, Ci/groups, kH, kW] contiguous (conv.py:133-141); bias_r fp32 [Co] or NULL.
  * dw[4]: fp32 grads, same shape, OVERWRITTEN.  Any of dx / dw / dbias may be NULL to skip that product.
- * Workspace sized by quan_qconv2d_workspace_bytes (0 allowed for the direct engine's fwd). */
+ * Workspace sized by quan_qconv2d_workspace_bytes (0 allowed for the direct engine's fwd); layout
+ *   [ G = M^T dY | packed weights (fwd / dgrad) | wgrad split-K partials ].
+ * Engines (quan_conv_algo; AUTO picks the first that serves the shape): TCGEN05 — tcgen05/TMEM/TMA implicit GEMM, layout
+ *   BHWQC, groups = 1, in its separable form (one GEMM per component, 4x4 mix in the epilogue) for wide layers and its dense
+ *   Hamilton form (one GEMM over 4*C channels, mix folded into the packed weights) for narrow ones; DEPTHWISE (groups = C)
+ *   and SMALLC (1..8 channels) — streaming kernels that apply the mix in registers; DIRECT — every other shape and the
+ *   BCHWQ layout.  The backward of a narrow layer runs dgrad and wgrad concurrently on an internal side stream and joins
+ *   before returning (stream order towards the caller is unchanged; works under CUDA graph capture). */
 size_t quan_qconv2d_workspace_bytes(const quan_conv_dims* d, int dtype, int layout, int algo);
 int quan_qconv2d_fwd(const void* x, const float* const w[4], const float* bias_r, void* y,
                      const quan_conv_dims* d, int dtype, int layout, const float* mix, int algo,

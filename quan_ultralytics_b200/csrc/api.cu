@@ -97,7 +97,7 @@ size_t quan_kernel_timing_report(char* buf, size_t cap) {
 
 const char* quan_build_info(void) {
   return "libquan_sm100 abi=1 arch=sm_100a nvcc=" QUAN_STR(__CUDACC_VER_MAJOR__) "." QUAN_STR(__CUDACC_VER_MINOR__)
-         " engines=direct,tcgen05";
+         " engines=direct,tcgen05,depthwise,smallc";
 }
 
 }  // extern "C"
