@@ -214,6 +214,15 @@ int quan_conv_block_bwd(const void* dout, const void* x, const void* y, const fl
                         float* dbeta, double* sums, const quan_conv_dims* d, int dtype, int layout, const float* mix, int algo,
                         int act, void* conv_ws, size_t conv_ws_bytes, void* iqbn_ws, size_t iqbn_ws_bytes, void* stream);
 
+/* Inference form of the block: IQBN uses the running statistics (conv.py:546-552) and, on the tensor-core engine, runs with
+ * the activation inside the conv epilogue (one kernel).  stats: [20*Co] scratch for the coefficient table; y_scratch: tensor
+ * shaped like the output, only used by the engines without an epilogue hook (may be NULL when quan_qconv2d_pick_algo says
+ * QUAN_ALGO_TCGEN05). */
+int quan_conv_block_eval_fwd(const void* x, const float* const w[4], const float* gamma, const float* beta,
+                             const float* running_mean, const float* running_var, void* out, float* stats, void* y_scratch,
+                             const quan_conv_dims* d, int dtype, int layout, const float* mix, int algo, float eps, int act,
+                             void* conv_ws, size_t conv_ws_bytes, void* stream);
+
 /* Optional per-kernel device timing for benchmarks (no reference counterpart): while enabled, every kernel the library
  * launches outside stream capture is bracketed by a CUDA-event pair on its own stream.  `enable(1)` clears earlier
  * records.  `report` synchronises the recorded events and writes one "kernel_name launches total_ms" line per kernel

@@ -65,6 +65,8 @@ PROTOTYPES = {
                                    _vp, _sz, _vp, _sz, _vp]),
     "quan_conv_block_bwd": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _pdims, _int, _int, _vp, _int,
                                    _int, _vp, _sz, _vp, _sz, _vp]),
+    "quan_conv_block_eval_fwd": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _pdims, _int, _int, _vp, _int, _f, _int,
+                                        _vp, _sz, _vp]),
     "quan_qconv2d_bwd_premixed": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _pdims, _int, _int, _vp, _int, _vp, _sz, _vp]),
     "quan_qconv2d_bwd_wants_mixed": (_int, [_pdims, _int, _int, _int, _int, _int]),
 }

@@ -56,4 +56,30 @@ int quan_conv_block_bwd(const void* dout, const void* x, const void* y, const fl
                : quan_qconv2d_bwd(g, x, w, dx, dw, nullptr, d, dtype, layout, mix, algo, conv_ws, conv_ws_bytes, stream);
 }
 
+// Inference: QConv2D -> IQBN with running statistics -> act (`Conv.forward` in eval mode, conv.py:546-552 + :805-809).  On
+// the tensor-core engine the normalisation and the activation run in the conv epilogue (one kernel after the tiny
+// coefficient-table kernel and the weight packing); other engines write the conv output to `y_scratch` and apply.
+int quan_conv_block_eval_fwd(const void* x, const float* const w[4], const float* gamma, const float* beta,
+                             const float* running_mean, const float* running_var, void* out, float* stats, void* y_scratch,
+                             const quan_conv_dims* d, int dtype, int layout, const float* mix, int algo, float eps, int act,
+                             void* conv_ws, size_t conv_ws_bytes, void* stream) {
+  QUAN_REQUIRE(d != nullptr && x != nullptr && out != nullptr && stats != nullptr && mix != nullptr && w != nullptr, QUAN_E_ARG,
+               "conv_block_eval_fwd: null pointer");
+  int rc = quan_iqbn_eval_stats(gamma, beta, running_mean, running_var, eps, d->Co, stats, stream);
+  if (rc) return rc;
+  const int Ho = conv_out(d->H, d->kH, d->sH, d->pH, d->dH), Wo = conv_out(d->W, d->kW, d->sW, d->pW, d->dW);
+  const int picked = algo == QUAN_ALGO_AUTO ? quan_qconv2d_pick_algo(d, dtype, layout, PASS_FWD) : algo;
+  if (picked == QUAN_ALGO_TCGEN05 && qconv_tc_supported(*d, dtype, layout, PASS_FWD) && Ho > 0 && Wo > 0) {
+    const size_t need = qconv_tc_workspace_bytes(*d, dtype, layout, PASS_FWD);
+    QUAN_REQUIRE(conv_ws != nullptr && conv_ws_bytes >= need, QUAN_E_WORKSPACE,
+                 "conv_block_eval_fwd: tcgen05 engine needs %zu workspace bytes, got %zu", need, conv_ws_bytes);
+    return qconv_tc_fwd(x, w, nullptr, out, *d, dtype, qconv_tc_mode(*d, dtype, layout, PASS_FWD), mix, conv_ws, conv_ws_bytes,
+                        (cudaStream_t)stream, nullptr, nullptr, stats + 12 * (size_t)d->Co, stats + 16 * (size_t)d->Co, act);
+  }
+  QUAN_REQUIRE(y_scratch != nullptr, QUAN_E_ARG, "conv_block_eval_fwd: this shape needs the y scratch tensor");
+  rc = quan_qconv2d_fwd(x, w, nullptr, y_scratch, d, dtype, layout, mix, algo, conv_ws, conv_ws_bytes, stream);
+  if (rc) return rc;
+  return quan_iqbn_apply_fwd(y_scratch, out, d->B, d->Co, Ho, Wo, dtype, layout, stats, gamma, beta, act, stream);
+}
+
 }  // extern "C"

@@ -46,7 +46,9 @@ size_t qconv_tc_workspace_bytes(const quan_conv_dims& d, int dtype, int layout, 
 // produced to its own slot [2][4*C_o]; *stat_nparts = slots written (0: this launch produced none, run the stats kernel)
 int qconv_tc_fwd(const void* x, const float* const w[4], const float* bias_r, void* y, const quan_conv_dims& d,
                  int dtype, int mode, const float* mix, void* ws, size_t ws_bytes, cudaStream_t st,
-                 double* stat_part = nullptr, int* stat_nparts = nullptr);
+                 double* stat_part = nullptr, int* stat_nparts = nullptr,
+                 // eval-mode IQBN + activation in the epilogue: y = act(y * scale + shift), tables [4][C_o] (component, channel)
+                 const float* post_scale = nullptr, const float* post_shift = nullptr, int post_act = 0);
 int qconv_tc_dgrad(const void* g, const float* const w[4], void* dx, const quan_conv_dims& d, int dtype, int mode,
                    const float* mix, void* ws, size_t ws_bytes, cudaStream_t st);
 int qconv_tc_wgrad(const void* g, const void* x, float* const dw[4], const quan_conv_dims& d, int dtype, int mode,

@@ -172,6 +172,9 @@ struct TcConvParams {
   uint32_t sbo_bytes, layout_type, idesc, tmem_cols;
   const float* bias;                   // NQ = 4: [Cout], joins S_r before the mix; NQ = 1: [Cout] added to the output
   double* stat_part;                   // or NULL: per-CTA partial IQBN sums of the OUTPUT, [grid][2][C_q*4] (index c*4+q)
+  const float* post_scale;             // or NULL: eval-mode IQBN folded into the epilogue, y = act(y * scale + shift); tables
+  const float* post_shift;             //   [4][C_o] in (component, channel) order (stats[12C..20C) of quan_iqbn_eval_stats)
+  int post_act;
   int stat_cq;                         // quaternion output channels C_o (NQ = 4: Cout; NQ = 1: Cout / 4)
   Mix16 mix;
 };
@@ -541,6 +544,17 @@ qconv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                   else
                     o[j] = pc == 0 ? st[ci][j] : acc[pc == 0 ? 0 : pc - 1][j];
                 }
+                if constexpr (MIX) {
+                  if (p.post_scale != nullptr) {      // inference: IQBN (running statistics) + activation in the epilogue
+                    const float* sc = p.post_scale + pc * p.Cout + n0 + c0;
+                    const float* sh = p.post_shift + pc * p.Cout + n0 + c0;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                      const float z = fmaf(o[j], __ldg(sc + j), __ldg(sh + j));
+                      o[j] = p.post_act == QUAN_ACT_SILU ? act_fwd<QUAN_ACT_SILU, sizeof(T) == 2>(z) : z;
+                    }
+                  }
+                }
                 T* dst = yrow + (int64_t)pc * p.Cout + c0;
 #pragma unroll
                 for (int v = 0; v < 16 / VW; ++v) {
@@ -589,6 +603,13 @@ qconv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           if (p.bias != nullptr) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) acc[j] += __ldg(p.bias + n0 + c0 + j);
+          }
+          if (p.post_scale != nullptr) {              // inference: column n = p*C_o + co is the table index
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float z = fmaf(acc[j], __ldg(p.post_scale + n0 + c0 + j), __ldg(p.post_shift + n0 + c0 + j));
+              acc[j] = p.post_act == QUAN_ACT_SILU ? act_fwd<QUAN_ACT_SILU, sizeof(T) == 2>(z) : z;
+            }
           }
           if (valid) {
 #pragma unroll
@@ -1052,9 +1073,15 @@ static int launch_igemm_inst(const CUtensorMap& map_a, const CUtensorMap& map_b,
   return QUAN_OK;
 }
 
+struct PostOp {                        // eval-mode IQBN + activation folded into the forward epilogue
+  const float* scale = nullptr;
+  const float* shift = nullptr;
+  int act = QUAN_ACT_NONE;
+};
 template <typename T, bool MIX, int NQ>
 static int launch_igemm(const void* in, const void* wpacked, const float* bias, void* out, const IgemmShape& s, int dtype,
-                        const Mix16& mix, cudaStream_t st, double* stat_part = nullptr, int* stat_nparts = nullptr) {
+                        const Mix16& mix, cudaStream_t st, double* stat_part = nullptr, int* stat_nparts = nullptr,
+                        const PostOp* post = nullptr) {
   const int esz = sizeof(T);
   const int row_bytes = pick_row_bytes(s.K, esz);
   TilePlan t;
@@ -1119,6 +1146,7 @@ static int launch_igemm(const void* in, const void* wpacked, const float* bias, 
   const int acc_cols = (NQ == 4 ? (p.dbuf ? 8 : 4) : 2) * p.BN;
   p.tmem_cols = (uint32_t)pow2_ceil(acc_cols < 32 ? 32 : acc_cols);
   p.bias = bias;
+  if (post != nullptr) { p.post_scale = post->scale; p.post_shift = post->shift; p.post_act = post->act; }
   p.stat_cq = NQ == 4 ? s.N : s.N / 4;
   // fused IQBN partial statistics: needs the [2][4][C_o] fp32 accumulators next to the pipeline stages in shared memory
   // Measured on B200 (bench shape, separable form): the 31-shuffle column reduction per 16 outputs makes the epilogue
@@ -1553,25 +1581,29 @@ size_t qconv_tc_workspace_bytes(const quan_conv_dims& d, int dtype, int layout, 
 
 template <typename T>
 static int tc_fwd_t(const void* x, const float* const w[4], const float* bias_r, void* y, const quan_conv_dims& d, int dtype,
-                    int dense, const Mix16& M, void* ws, cudaStream_t st, double* stat_part, int* stat_nparts) {
+                    int dense, const Mix16& M, void* ws, cudaStream_t st, double* stat_part, int* stat_nparts, const PostOp* post) {
   if (dense) {
     float* bias_out = reinterpret_cast<float*>((char*)ws + packed_weight_bytes(d, dtype, 1) - (size_t)4 * d.Co * sizeof(float) - 1024);
     int rc = pack_weights_dense<T, false>(w, bias_r, ws, bias_out, d, M, st);
     if (rc) return rc;
-    return launch_igemm<T, false, 1>(x, ws, bias_r ? bias_out : nullptr, y, fwd_shape(d, 1), dtype, M, st, stat_part, stat_nparts);
+    return launch_igemm<T, false, 1>(x, ws, bias_r ? bias_out : nullptr, y, fwd_shape(d, 1), dtype, M, st, stat_part, stat_nparts, post);
   }
   int rc = pack_weights<T, false>(w, ws, d, st);
   if (rc) return rc;
-  return launch_igemm<T, true, 4>(x, ws, bias_r, y, fwd_shape(d, 0), dtype, M, st, stat_part, stat_nparts);
+  return launch_igemm<T, true, 4>(x, ws, bias_r, y, fwd_shape(d, 0), dtype, M, st, stat_part, stat_nparts, post);
 }
 
 int qconv_tc_fwd(const void* x, const float* const w[4], const float* bias_r, void* y, const quan_conv_dims& d, int dtype,
-                 int mode, const float* mix, void* ws, size_t ws_bytes, cudaStream_t st, double* stat_part, int* stat_nparts) {
+                 int mode, const float* mix, void* ws, size_t ws_bytes, cudaStream_t st, double* stat_part, int* stat_nparts,
+                 const float* post_scale, const float* post_shift, int post_act) {
   const int dense = mode == TC_DENSE;
   QUAN_REQUIRE(ws_bytes >= packed_weight_bytes(d, dtype, dense), QUAN_E_WORKSPACE, "tcgen05 fwd: workspace too small");
   const Mix16 M = make_mix(mix);
-  if (dtype == QUAN_BF16) return tc_fwd_t<__nv_bfloat16>(x, w, bias_r, y, d, dtype, dense, M, ws, st, stat_part, stat_nparts);
-  return tc_fwd_t<float>(x, w, bias_r, y, d, dtype, dense, M, ws, st, stat_part, stat_nparts);
+  PostOp post;
+  post.scale = post_scale; post.shift = post_shift; post.act = post_act;
+  const PostOp* pp = post_scale != nullptr ? &post : nullptr;
+  if (dtype == QUAN_BF16) return tc_fwd_t<__nv_bfloat16>(x, w, bias_r, y, d, dtype, dense, M, ws, st, stat_part, stat_nparts, pp);
+  return tc_fwd_t<float>(x, w, bias_r, y, d, dtype, dense, M, ws, st, stat_part, stat_nparts, pp);
 }
 
 template <typename T>

@@ -228,6 +228,14 @@ class Conv(nn.Module):
             return QF.conv_iqbn_act(x, c.weight_r, c.weight_i, c.weight_j, c.weight_k, bn.gamma, bn.beta, bn.running_mean,
                                     bn.running_var, c.stride, c.padding, c.dilation, c.groups, ops.MIX[c.mix], c.algo,
                                     bn.eps, bn.momentum, fused_act)
+        if (self.fuse_block and fused_act is not None and not bn.training and c.bias_r is None and not c.is_first_layer
+                and x.dim() == 5 and x.is_cuda and not torch.is_grad_enabled()):
+            # inference (eval mode under no_grad): one C call; on the tensor-core engine IQBN(running stats) + act run in the
+            # conv epilogue.  With autograd enabled the separate nodes below keep every gradient path.
+            xl, layout = ops.as_layout(x, QF.internal_layout())
+            return ops.conv_block_eval_fwd(xl, (c.weight_r, c.weight_i, c.weight_j, c.weight_k), ops._f32c(bn.gamma),
+                                           ops._f32c(bn.beta), ops._f32c(bn.running_mean), ops._f32c(bn.running_var), c.stride,
+                                           c.padding, c.dilation, c.groups, ops.MIX[c.mix], c.algo, bn.eps, fused_act, layout)
         y = self.conv(x)
         if isinstance(self.act, nn.SiLU):
             return self.bn(y, ACT_SILU)

@@ -481,3 +481,27 @@ def conv_block_bwd(dout: torch.Tensor, x: torch.Tensor, y: torch.Tensor, weights
                                   sums.data_ptr(), C.byref(d), code, layout, C.cast(_mix_arg(mix_matrix), C.c_void_p), algo, act,
                                   wsb.data_ptr(), wsb.numel(), iws.data_ptr(), iws.numel(), _stream(x)), "quan_conv_block_bwd")
     return dx, dws, dgamma, dbeta
+
+
+def conv_block_eval_fwd(x: torch.Tensor, weights: Sequence[torch.Tensor], gamma, beta, running_mean, running_var, stride,
+                        padding, dilation, groups: int, mix_matrix: Sequence[float], algo: int, eps: float, act: int,
+                        layout: int) -> torch.Tensor:
+    """Inference `Conv` block: act(IQBN_eval(QConv2D(x))); x must already be dense in `layout`."""
+    ws = [_f32c(w) for w in weights]
+    d = conv_dims(x.shape, ws[0].shape, stride, padding, dilation, groups)
+    Ho, Wo = conv_out_shape(d)
+    if Ho <= 0 or Wo <= 0 or x.size(1) != ws[0].size(1) * groups:
+        raise RuntimeError(f"conv_block_eval_fwd: input {tuple(x.shape)} does not fit weight {tuple(ws[0].shape)} (groups={groups})")
+    lib = _lib.load()
+    code = _dtype_code(x)
+    out = empty_q((d.B, d.Co, Ho, Wo, 4), x.dtype, x.device, layout)
+    stats = torch.empty(20 * d.Co, dtype=torch.float32, device=x.device)
+    fused = algo in (ALGO_AUTO, ALGO_TCGEN05) and lib.quan_qconv2d_pick_algo(C.byref(d), code, layout, 0) == ALGO_TCGEN05
+    y = None if fused else torch.empty_like(out, memory_format=torch.preserve_format)
+    wsb = _workspace(_conv_ws_bytes(lib, d, code, layout, algo), x.device)
+    wa = _weights_arg(ws)
+    check(lib.quan_conv_block_eval_fwd(x.data_ptr(), C.cast(wa, C.c_void_p), gamma.data_ptr(), beta.data_ptr(),
+                                       running_mean.data_ptr(), running_var.data_ptr(), out.data_ptr(), stats.data_ptr(),
+                                       _ptr(y), C.byref(d), code, layout, C.cast(_mix_arg(mix_matrix), C.c_void_p), algo, eps,
+                                       act, wsb.data_ptr(), wsb.numel(), _stream(x)), "quan_conv_block_eval_fwd")
+    return out

@@ -344,3 +344,40 @@ def test_kernel_timing_facility_reports_library_kernels():
     rows = {ln.split()[0]: (int(ln.split()[1]), float(ln.split()[2])) for ln in buf.value.decode().splitlines()}
     assert rows["qconv_igemm_fwd"][0] == 3 and rows["qconv_igemm_fwd"][1] > 0.0
     assert rows["pack_weights_kernel"][0] == 3
+
+
+@pytest.mark.parametrize("cfg", [("sep_bf16", torch.bfloat16, 64, 128, 1, 3), ("sep_f32", torch.float32, 64, 64, 1, 3),
+                                 ("dense_bf16", torch.bfloat16, 16, 32, 1, 1), ("dw_bf16", torch.bfloat16, 32, 32, 32, 3),
+                                 ("small_bf16", torch.bfloat16, 4, 2, 1, 3)], ids=lambda c: c[0])
+def test_inference_conv_block_epilogue_fusion(cfg):
+    """eval-mode `Conv` under no_grad (IQBN with running statistics + SiLU folded into the tensor-core epilogue, one C call)
+    against the separate eval-mode nodes (conv.py:546-552 semantics, golden-checked elsewhere)."""
+    import quan_ultralytics_b200 as Q
+    name, dtype, ci, co, g, k = cfg
+    torch.manual_seed(17)
+    blk = (Q.DWConv(ci * 4, co * 4, k, 1) if g > 1 else Q.Conv(ci * 4, co * 4, k, 1)).to(DEV)
+    with torch.no_grad():
+        blk.bn.running_mean.normal_(0, 0.3)
+        blk.bn.running_var.uniform_(0.5, 2.0)
+        blk.bn.gamma.uniform_(0.5, 1.5)
+        blk.bn.beta.normal_(0, 0.5)
+    blk.eval()
+    x = torch.randn(3, ci, 21, 19, 4, device=DEV).to(dtype).contiguous(memory_format=torch.channels_last_3d)
+    with torch.no_grad():
+        blk.fuse_block = True
+        y_fused = blk(x)
+        blk.fuse_block = False
+        y_sep = blk(x)
+    # the fused epilogue normalises the fp32 accumulator; the separate path rounds the conv output to bf16 first
+    tol = 1.5e-2 if dtype == torch.bfloat16 else 1e-5
+    assert y_fused.shape == y_sep.shape and rel(y_fused, y_sep) <= tol
+    # against the oracle in fp64 on the same inputs
+    xn = x.double().cpu().numpy()
+    n64 = lambda t: t.detach().double().cpu().numpy()
+    wn = [n64(getattr(blk.conv, f"weight_{c}")) for c in "rijk"]
+    if dtype == torch.bfloat16:
+        wn = [n64(getattr(blk.conv, f"weight_{c}").detach().to(torch.bfloat16)) for c in "rijk"]
+    s_ = O.qconv2d_fwd(xn, wn, None, 1, k // 2, 1, g, O.M_A)
+    y_ref = O.iqbn_eval_fwd(s_, n64(blk.bn.gamma), n64(blk.bn.beta), n64(blk.bn.running_mean), n64(blk.bn.running_var), act=True)
+    err = float(np.max(np.abs(y_fused.double().cpu().numpy() - y_ref)) / np.max(np.abs(y_ref)))
+    assert err <= (1e-2 if dtype == torch.bfloat16 else 1e-3)
