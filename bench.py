@@ -56,6 +56,9 @@ def parse_args():
     ap.add_argument("--broadcast-buffers", action="store_true",
                     help="DDP: re-broadcast the IQBN running statistics from rank 0 before every forward (torch's default; "
                          "measured 0.3 ms/step at N=2 — off here: the batch-statistics training step does not read them)")
+    ap.add_argument("--infer", action="store_true",
+                    help="yolo11n_trace: eval-mode forward only under no_grad (IQBN running statistics + SiLU in the conv epilogue); "
+                         "reports forward latency per batch of --n images (BASELINE config 5 asks for batch-1 latency)")
     ap.add_argument("--graph", action="store_true", help="yolo11n_trace: capture the step in a CUDA graph (removes host launch overhead)")
     return ap.parse_args()
 
@@ -328,7 +331,7 @@ def run_yolo11n_trace(a):
             bn_elems += 0 if bare else co * ho * ho * 4
     params = [p for m, _, _ in layers for p in m.parameters()]
 
-    def step():
+    def train_step():
         for p in params:
             p.grad = None
         for mod, x, dy in layers:
@@ -337,6 +340,16 @@ def run_yolo11n_trace(a):
             with torch.autocast("cuda", dtype=torch.bfloat16, enabled=(dtype == torch.bfloat16)):
                 y = mod(x)
             y.backward(dy)
+
+    def infer_step():
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=(dtype == torch.bfloat16)):
+            for mod, x, _ in layers:
+                mod(x)
+
+    if a.infer:
+        for mod, _, _ in layers:
+            mod.eval()
+    step = infer_step if a.infer else train_step
 
     for _ in range(max(a.warmup, 3)):
         step()
@@ -419,13 +432,15 @@ def run_yolo11n_trace(a):
     flops_img = 3 * fwd_flops
     bytes_img = 8 * bn_elems * esz                     # IQBN 3S fwd + 5S bwd; conv traffic comes on top
     line = {
-        "metric": "train_images_per_sec", "value": B * a.steps / (ms / 1e3), "unit": "images/s", "n_gpus": 1,
+        "metric": "infer_images_per_sec" if a.infer else "train_images_per_sec", "value": B * a.steps / (ms / 1e3),
+        "unit": "images/s", "n_gpus": 1,
         "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": a.dtype, "data": "synthetic",
-        "config": {"workload": f"yolo11n_obb_quan_hotpath_trace(1024x1024,B={B}): 87 QConv2D + 84 IQBN.SiLU fwd+bwd, per-layer replay",
+        "config": {"workload": f"yolo11n_obb_quan_hotpath_trace(1024x1024,B={B}): 87 QConv2D + 84 IQBN.SiLU " +
+                               ("eval-mode forward (no_grad)" if a.infer else "fwd+bwd") + ", per-layer replay",
                    "qconv_gflop_per_image_train": flops_img / 1e9, "iqbn_melems_per_image": bn_elems / 1e6},
         "gpu_launches": int(launches), "clocks": clocks, "cuda_graph": bool(a.graph),
-        "hotpath_tflops": flops_img * B / t_step / 1e12,
+        "hotpath_tflops": (fwd_flops if a.infer else flops_img) * B / t_step / 1e12,
         "roofline_floor_ms_per_step": 1e3 * B * max(flops_img / (peaks["bf16_tflops"] * 1e12), bytes_img / (peaks["hbm_gbs"] * 1e9)),
     }
     print(json.dumps(line))
