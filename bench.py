@@ -35,9 +35,11 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="block_stack", choices=["block_stack", "yolo11n_trace"],
+    ap.add_argument("--workload", default="block_stack", choices=["block_stack", "yolo11n_trace", "yolo11s_trace", "qresnet34_trace"],
                     help="block_stack: BASELINE config[1] sweep point (default, the bench line); yolo11n_trace: replay of "
-                         "the 87 QConv2D / 84 IQBN+SiLU calls of QUAN-YOLO11n-OBB at 1024^2 (SURVEY 8(a) histogram)")
+                         "the 87 QConv2D / 84 IQBN+SiLU calls of QUAN-YOLO11n-OBB at 1024^2 (SURVEY 8(a) histogram); "
+                         "yolo11s_trace (config[4], default 8 images) and qresnet34_trace (config[3], 224^2, M_B, biased convs, "
+                         "default 256 images): the same replay from tests/golden/model_traces.json (tools/probe_model_trace.py)")
     ap.add_argument("--cq", type=int, default=256, help="quaternion channels per component")
     ap.add_argument("--hw", type=int, default=32)
     ap.add_argument("--n", type=int, default=64, help="images per GPU per step")
@@ -280,55 +282,68 @@ def kernel_table(a, dev, dtype, peaks):
     return rows
 
 
-# (C_i, C_o, k, s, groups, H_o, count): QConv2D calls of yolo11n-obb-quan @1024^2 per image (probed from the
-# reference with forward hooks); H_in = H_o * s.  The first row is the RGB first layer (Poincare map + C_i = 1 conv).
-YOLO11N_TRACE = [
-    (1, 4, 3, 2, 1, 512, 1), (4, 8, 3, 2, 1, 256, 1), (8, 8, 1, 1, 1, 256, 1), (4, 2, 3, 1, 1, 256, 1), (2, 4, 3, 1, 1, 256, 1),
-    (12, 16, 1, 1, 1, 256, 1), (16, 16, 3, 2, 1, 128, 1), (16, 16, 1, 1, 1, 128, 3), (8, 4, 3, 1, 1, 128, 2),
-    (4, 8, 3, 1, 1, 128, 2), (24, 32, 1, 1, 1, 128, 1), (24, 16, 1, 1, 1, 128, 1), (64, 16, 1, 1, 1, 128, 1),
-    (16, 16, 3, 1, 1, 128, 2), (16, 4, 3, 1, 1, 128, 1), (4, 4, 3, 1, 1, 128, 1), (16, 16, 3, 1, 16, 128, 2),
-    (32, 32, 3, 2, 1, 64, 1), (16, 16, 3, 2, 1, 64, 1), (32, 32, 1, 1, 1, 64, 1), (16, 8, 1, 1, 1, 64, 2), (8, 8, 3, 1, 1, 64, 4),
-    (16, 16, 1, 1, 1, 64, 2), (48, 32, 1, 1, 1, 64, 4), (96, 32, 1, 1, 1, 64, 1), (16, 8, 3, 1, 1, 64, 2), (8, 16, 3, 1, 1, 64, 2),
-    (32, 16, 3, 1, 1, 64, 1), (16, 16, 3, 1, 1, 64, 1), (32, 16, 1, 1, 1, 64, 1), (32, 4, 3, 1, 1, 64, 1), (4, 4, 3, 1, 1, 64, 1),
-    (32, 32, 3, 1, 32, 64, 1), (16, 16, 3, 1, 16, 64, 1), (32, 64, 3, 2, 1, 32, 1), (32, 32, 3, 2, 1, 32, 1),
-    (64, 64, 1, 1, 1, 32, 3), (32, 16, 1, 1, 1, 32, 4), (16, 16, 3, 1, 1, 32, 9), (32, 32, 1, 1, 1, 32, 3), (96, 64, 1, 1, 1, 32, 3),
-    (64, 32, 1, 1, 1, 32, 2), (128, 64, 1, 1, 1, 32, 1), (32, 64, 1, 1, 1, 32, 2), (32, 32, 3, 1, 32, 32, 1),
-    (64, 16, 3, 1, 1, 32, 1), (64, 16, 1, 1, 1, 32, 1), (64, 4, 3, 1, 1, 32, 1), (4, 4, 3, 1, 1, 32, 1), (64, 64, 3, 1, 64, 32, 1),
-    (16, 16, 1, 1, 1, 32, 1), (16, 16, 3, 1, 16, 32, 1),
-]
+def load_model_trace(name):
+    """(rows, meta) of a model's QConv2D call histogram: rows = (C_i, C_o, k, s, groups, H_o, iqbn, bias, count), recorded
+    from the real reference by tools/probe_model_trace.py and committed as tests/golden/model_traces.json."""
+    t = json.loads((ROOT / "tests" / "golden" / "model_traces.json").read_text())[name]
+    rows = [tuple(r) for r in t["rows"]]
+    return rows, t
 
 
-def run_yolo11n_trace(a):
-    """Hot-path replay of one QUAN-YOLO11n-OBB training step at 1024^2: every QConv2D (+ IQBN + SiLU) call of the model
-    with its real shape, forward + backward, on synthetic activations.  Glue the reference does in Python (concat, split,
-    attention matmuls, heads, loss) is not part of the path and not replayed."""
+def run_model_trace(a, name):
+    """Hot-path replay of one training step of a reference model (QUAN-YOLO11n/s-OBB at 1024^2, Q-ResNet-34 at 224^2): every
+    QConv2D (+ IQBN + SiLU) call of the model with its real shape, forward + backward, on synthetic activations.  Glue
+    the reference does in Python (concat, split, attention matmuls, pooling, heads, loss) is not part of the path and
+    not replayed."""
     import quan_ultralytics_b200 as Q
     lib = Q._lib.load()
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
     dtype = torch.bfloat16 if a.dtype == "bf16" else torch.float32
     B = a.n
-    assert sum(r[6] for r in YOLO11N_TRACE) == 87
+    rows, meta = load_model_trace(name)
+    image = meta["image"]
+    mixB = meta["mix"] == "B"
     torch.manual_seed(0)
     layers = []
     fwd_flops = 0
     bn_elems = 0
-    for ci, co, k, s, g, ho, cnt in YOLO11N_TRACE:
+    n_bn = 0
+
+    class ConvB(Q.Conv):                                        # classification flavour: M_B (qconv.py:546-612)
+        conv_cls = Q.QConv2D_B
+
+    class BiasedBlock(torch.nn.Module):                         # Q-ResNet: biased QConv2D -> IQBN -> SiLU (QSiLU == SiLU)
+        def __init__(self, c1, c2, k, s, g):
+            super().__init__()
+            self.conv = (Q.QConv2D_B if mixB else Q.QConv2D)(c1, c2, k, s, k // 2, groups=g, bias=True)
+            self.bn = Q.IQBN(c2)
+
+        def forward(self, x):
+            return self.bn(self.conv(x), Q.ACT_SILU)
+
+    for ci, co, k, s, g, ho, has_bn, has_bias, cnt in rows:
         hin = ho * s
         for rep in range(cnt):
-            bare = (ci, co, k, ho) == (64, 64, 1, 32)              # the three BN-less QConv2Ds of QAttention
-            if ci == 1:
-                mod = Q.Conv(3, co * 4, k, s).to(dev).train()
-                x = torch.rand(B, 3, hin, hin, device=dev)
+            cin = 3 if ci == 1 and hin == image else ci * 4
+            if has_bn and has_bias:
+                mod = BiasedBlock(cin, co * 4, k, s, g)
+            elif has_bn:
+                mod = (ConvB if mixB else Q.Conv)(cin, co * 4, k, s, g=g)
+            else:                                               # e.g. the three BN-less QConv2Ds of QAttention, shortcuts
+                mod = (Q.QConv2D_B if mixB else Q.QConv2D)(cin, co * 4, k, s, k // 2, groups=g, bias=bool(has_bias))
+            mod = mod.to(dev).train()
+            if cin == 3:
+                x = torch.rand(B, 3, hin, hin, device=dev) if not mixB else torch.randn(B, 3, hin, hin, device=dev)
             else:
-                mod = (Q.QConv2D(ci * 4, co * 4, k, s, k // 2, groups=g, bias=False) if bare
-                       else Q.Conv(ci * 4, co * 4, k, s, g=g)).to(dev).train()
                 x = torch.randn(B, ci, hin, hin, 4, device=dev).to(dtype).contiguous(memory_format=torch.channels_last_3d)
                 x.requires_grad_(True)
             dy = torch.randn(B, co, ho, ho, 4, device=dev).to(dtype).contiguous(memory_format=torch.channels_last_3d)
             layers.append((mod, x, dy))
             fwd_flops += 4 * 2 * ho * ho * co * (ci // g) * k * k
-            bn_elems += 0 if bare else co * ho * ho * 4
+            bn_elems += co * ho * ho * 4 if has_bn else 0
+            n_bn += 1 if has_bn else 0
+    n_conv = len(layers)
     params = [p for m, _, _ in layers for p in m.parameters()]
 
     def train_step():
@@ -355,9 +370,9 @@ def run_yolo11n_trace(a):
         step()
     torch.cuda.synchronize()
     if os.environ.get("QUAN_TRACE_DETAIL"):
-        rows = []
+        rows_in, rows = rows, []
         i = 0
-        for ci, co, k, s, g, ho, cnt in YOLO11N_TRACE:
+        for ci, co, k, s, g, ho, _bn, _bias, cnt in rows_in:
             mod, x, dy = layers[i]
             i += cnt
 
@@ -436,7 +451,7 @@ def run_yolo11n_trace(a):
         "unit": "images/s", "n_gpus": 1,
         "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": a.dtype, "data": "synthetic",
-        "config": {"workload": f"yolo11n_obb_quan_hotpath_trace(1024x1024,B={B}): 87 QConv2D + 84 IQBN.SiLU " +
+        "config": {"workload": f"{name}_quan_hotpath_trace({image}x{image},B={B}): {n_conv} QConv2D + {n_bn} IQBN.SiLU " +
                                ("eval-mode forward (no_grad)" if a.infer else "fwd+bwd") + ", per-layer replay",
                    "qconv_gflop_per_image_train": flops_img / 1e9, "iqbn_melems_per_image": bn_elems / 1e6},
         "gpu_launches": int(launches), "clocks": clocks, "cuda_graph": bool(a.graph),
@@ -448,10 +463,11 @@ def run_yolo11n_trace(a):
 
 def main():
     a = parse_args()
-    if a.workload == "yolo11n_trace" and a.impl == "ours":
-        if a.n == 64:
-            a.n = 16
-        run_yolo11n_trace(a)
+    if a.workload.endswith("_trace") and a.impl == "ours":
+        name = a.workload[:-len("_trace")]
+        if a.n == 64:                                           # per-GPU batch of the BASELINE config that names the model
+            a.n = {"yolo11n": 16, "yolo11s": 8, "qresnet34": 256}[name]
+        run_model_trace(a, name)
         return
     if a.impl == "reference":
         reference_arm(a)
