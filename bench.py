@@ -402,9 +402,9 @@ def run_model_trace(a, name):
         lib.quan_kernel_timing_report(buf, n + 16)
         rows = [ln.split() for ln in buf.value.decode().splitlines()]
         tot = sum(float(r[2]) for r in rows)
-        for name, cnt, ms in sorted(rows, key=lambda r: -float(r[2])):
+        for kname, cnt, ms in sorted(rows, key=lambda r: -float(r[2])):
             print(f"{float(ms) / 3:8.3f} ms/step {int(cnt) // 3:5d} launches {100 * float(ms) / tot:5.1f}%  "
-                  f"{1e3 * float(ms) / int(cnt):7.1f} us avg  {name}", flush=True)
+                  f"{1e3 * float(ms) / int(cnt):7.1f} us avg  {kname}", flush=True)
         print(f"{tot / 3:8.3f} ms/step in library kernels", flush=True)
     run = step
     launches_per_step = None

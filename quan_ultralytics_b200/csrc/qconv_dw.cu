@@ -183,6 +183,89 @@ __global__ void __launch_bounds__(256) qconv_dw_wgrad_kernel(const T* __restrict
   }
 }
 
+// wgrad, second form (filters up to 3x3): a thread owns (q, channel vector, FILTER ROW kh) of its pixel lane — [KW][V]
+// accumulators instead of [9][V] — so three times as many threads fit a pixel, two blocks fit an SM (the first form needs
+// 150 registers: one 256-thread block per SM, 362 GB/s on the 128^2 DWConv of QUAN-YOLO11n, 185 us under ncu), U pixels
+// are in flight per loop trip and the index arithmetic is 32-bit.  The dY vectors a pixel's 12 threads share come
+// from L1.  Same fold: block lanes through shared memory, one fp32 atomic per (q, c, tap) and block.
+template <typename T, int V, int KW, int U>
+__global__ void __launch_bounds__(256, 2) qconv_dw_wgrad_rows_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+                                                                     float* dw0, float* dw1, float* dw2, float* dw3,
+                                                                     DwGeom g, Mix16 M) {
+  __shared__ float red[256][V + 1];
+  const int cvs = g.C / V;
+  const int tpp = 4 * cvs * g.kH;                // threads per pixel: (kh, q, channel vector)
+  const int ppb = blockDim.x / tpp;              // pixel lanes per block
+  const int tl = threadIdx.x % tpp, pl = threadIdx.x / tpp;
+  const int cv = tl % cvs, q = (tl / cvs) & 3, kh = tl / (4 * cvs);
+  const int npix = g.B * g.Ho * g.Wo;            // < 2^31 (qconv_dw_supported)
+  const int stride = (int)gridDim.x * ppb;
+  const int taps = g.kH * g.kW;
+  float acc[KW][V];
+#pragma unroll
+  for (int t = 0; t < KW; ++t)
+#pragma unroll
+    for (int v = 0; v < V; ++v) acc[t][v] = 0.f;
+  if (pl < ppb) {
+    const float m0 = M.m[0 * 4 + q], m1 = M.m[1 * 4 + q], m2 = M.m[2 * 4 + q], m3 = M.m[3 * 4 + q];
+    for (int pix0 = (int)blockIdx.x * ppb + pl; pix0 < npix; pix0 += U * stride) {
+      Vec<T, V> gy[U][4], xv[U][KW];              // raw 16-byte registers: converted after all loads are issued
+      bool row[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int pix = pix0 + u * stride;
+        const int wo = pix % g.Wo, r = pix / g.Wo;
+        const int ho = r % g.Ho, b = r / g.Ho;
+        const int hi = ho * g.sH - g.pH + kh * g.dH;
+        row[u] = pix < npix && hi >= 0 && hi < g.H;
+        if (row[u]) {
+          const T* gsrc = dy + ((int64_t)pix * 4) * g.C + cv * V;
+#pragma unroll
+          for (int p = 0; p < 4; ++p) gy[u][p] = *reinterpret_cast<const Vec<T, V>*>(gsrc + (int64_t)p * g.C);
+          const T* xrow = x + ((((int64_t)b * g.H + hi) * g.W) * 4 + q) * g.C + cv * V;
+#pragma unroll
+          for (int kw = 0; kw < KW; ++kw) {
+            const int wi = wo * g.sW - g.pW + kw * g.dW;
+            if (kw < g.kW && wi >= 0 && wi < g.W) {
+              xv[u][kw] = *reinterpret_cast<const Vec<T, V>*>(xrow + (int64_t)wi * 4 * g.C);
+            } else {
+#pragma unroll
+              for (int v = 0; v < V; ++v) xv[u][kw].v[v] = from_f32<T>(0.f);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (!row[u]) continue;
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          const float gq = m0 * to_f32(gy[u][0].v[v]) + m1 * to_f32(gy[u][1].v[v]) + m2 * to_f32(gy[u][2].v[v]) +
+                           m3 * to_f32(gy[u][3].v[v]);
+#pragma unroll
+          for (int kw = 0; kw < KW; ++kw) acc[kw][v] = fmaf(gq, to_f32(xv[u][kw].v[v]), acc[kw][v]);
+        }
+      }
+    }
+  }
+  float* dw = q == 0 ? dw0 : q == 1 ? dw1 : q == 2 ? dw2 : dw3;
+#pragma unroll
+  for (int kw = 0; kw < KW; ++kw) {              // unrolled: acc[][] must stay in registers (no dynamic indexing)
+    __syncthreads();
+#pragma unroll
+    for (int v = 0; v < V; ++v) red[threadIdx.x][v] = pl < ppb ? acc[kw][v] : 0.f;
+    __syncthreads();
+    if (pl == 0 && kw < g.kW && threadIdx.x < tpp) {
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        float s = 0.f;
+        for (int l = 0; l < ppb; ++l) s += red[l * tpp + tl][v];
+        atomicAdd(dw + (int64_t)(cv * V + v) * taps + kh * g.kW + kw, s);
+      }
+    }
+  }
+}
+
 // ---- host ------------------------------------------------------------------------------------------------------------
 bool qconv_dw_supported(const quan_conv_dims& d, int dtype, int layout, int pass) {
   if (layout != QUAN_LAYOUT_BHWQC || d.groups != d.Ci || d.Ci != d.Co || d.groups < 2) return false;
@@ -237,8 +320,26 @@ int qconv_dw_wgrad(const void* dy, const void* x, float* const dw[4], const quan
   for (int q = 0; q < 4; ++q) QUAN_CUDA(cudaMemsetAsync(dw[q], 0, (size_t)d.Co * taps * sizeof(float), st));
   const int VMAX = dtype == QUAN_BF16 ? 8 : 4;
   const int V = g.C % VMAX == 0 ? VMAX : VMAX / 2;
-  const int tpp = 4 * (g.C / V), ppb = 256 / tpp;
   const int64_t npix = (int64_t)g.B * g.Ho * g.Wo;
+  static const int env_rows = [] { const char* e = getenv("QUAN_DW_WGRAD_ROWS"); return e ? atoi(e) : 1; }();
+  // measured (tools/narrow_wgrad_probe.py, B200, bf16, 16 images): rows form 171 vs 241 us at 16 ch x 128^2, 104 vs 112 us at
+  // 32 ch x 64^2, but 85 vs 61 us at 64 ch x 32^2 (three times the blocks' fold + atomics tail on few pixels)
+  if ((env_rows == 2 || (env_rows == 1 && npix >= 32768)) && d.kH <= 3 && d.kW <= 3 && 4 * (g.C / V) * d.kH <= 256 &&
+      npix < (1ll << 31)) {
+    const int ppb = 256 / (4 * (g.C / V) * d.kH);
+    int64_t blocks = ceil_div64(npix, (int64_t)ppb * 16);        // >= 16 pixels (8 loop trips) per pixel lane
+    if (blocks > QUAN_NUM_SMS * 4) blocks = QUAN_NUM_SMS * 4;
+    if (blocks < 1) blocks = 1;
+    QUAN_TIMED(st);
+#define QUAN_DW_ROWS(TT, VV) qconv_dw_wgrad_rows_kernel<TT, VV, 3, 2><<<(unsigned)blocks, 256, 0, st>>>( \
+    (const TT*)dy, (const TT*)x, dw[0], dw[1], dw[2], dw[3], g, M)
+    if (dtype == QUAN_BF16) { if (V == 8) QUAN_DW_ROWS(__nv_bfloat16, 8); else QUAN_DW_ROWS(__nv_bfloat16, 4); }
+    else { if (V == 4) QUAN_DW_ROWS(float, 4); else QUAN_DW_ROWS(float, 2); }
+#undef QUAN_DW_ROWS
+    QUAN_CHECK_LAUNCH("qconv_dw_wgrad_rows_kernel");
+    return QUAN_OK;
+  }
+  const int tpp = 4 * (g.C / V), ppb = 256 / tpp;
   int64_t blocks = ceil_div64(npix, (int64_t)ppb * 16);          // >= 16 pixels per pixel lane
   if (blocks > QUAN_NUM_SMS * 4) blocks = QUAN_NUM_SMS * 4;
   if (blocks < 1) blocks = 1;

@@ -147,6 +147,8 @@ struct TapTable {
   int8_t dw[TC_MAX_TAPS], dh[TC_MAX_TAPS];
   uint8_t tap[TC_MAX_TAPS];
   int8_t ow[4], oh[4];                 // output offset of the class
+  int zero_fill;                       // host only: some output parity receives no tap (e.g. 1x1 stride 2: three of the four
+                                       // classes) — those classes are left out and the output is cleared before the launch
 };
 
 struct TcConvParams {
@@ -902,6 +904,45 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
   }
 }
 
+// Fold for small dW (narrow layers, few splits left after the atomic accumulation): one thread per dW element in output
+// order (q, co, ci, tap), all of its loads independent — the blocked kernel above spends ~25 us of load latency per
+// launch there (ncu launch list of the yolo11n trace: 23-28 us for 3x3 layers whatever the grid size).
+template <bool DENSE>
+__global__ void __launch_bounds__(256) wgrad_reduce_flat_kernel(const float* __restrict__ partial, float* __restrict__ dw0,
+                                                                float* __restrict__ dw1, float* __restrict__ dw2,
+                                                                float* __restrict__ dw3, int splits, int taps, int Co, int Ci,
+                                                                const Mix16 mix) {
+  const int per_q = Co * Ci * taps;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= 4 * per_q) return;
+  const int q = e / per_q, r = e - q * per_q;
+  const int tap = r % taps, cc = r / taps;
+  const int ci = cc % Ci, co = cc / Ci;
+  const int64_t split_stride = (int64_t)(DENSE ? 16 : 4) * taps * Co * Ci;
+  float s;
+  if constexpr (DENSE) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const float* src = partial + (((int64_t)tap * 4 * Co + co) * 4 * Ci + q * Ci + ci);
+    const int64_t pc_stride = (int64_t)Co * 4 * Ci;
+    for (int sp = 0; sp < splits; ++sp) {
+#pragma unroll
+      for (int pc = 0; pc < 4; ++pc) acc[pc] += __ldg(src + sp * split_stride + pc * pc_stride);
+    }
+    s = mix.m[q] * acc[0] + mix.m[4 + q] * acc[1] + mix.m[8 + q] * acc[2] + mix.m[12 + q] * acc[3];
+  } else {
+    const float* src = partial + ((((int64_t)q * taps + tap) * Co + co) * Ci + ci);
+    float t0 = 0.f, t1 = 0.f;
+    int sp = 0;
+    for (; sp + 1 < splits; sp += 2) {
+      t0 += __ldg(src + sp * split_stride);
+      t1 += __ldg(src + (sp + 1) * split_stride);
+    }
+    if (sp < splits) t0 += __ldg(src + sp * split_stride);
+    s = t0 + t1;
+  }
+  (q == 0 ? dw0 : q == 1 ? dw1 : q == 2 ? dw2 : dw3)[r] = s;
+}
+
 // dense Hamilton weights for narrow layers: one real conv over all 4*C_q channels with the mixing matrix folded in,
 //   FWD  : Wp[tap][n = p*Co + co][k = q*Ci + ci] = M[p][q] W_q[co][ci][tap];  bias'[p*Co + co] = M[p][0] b_r[co]
 //   DGRAD: Wp[tap][n = q*Ci + ci][k = p*Co + co] = M[p][q] W_q[co][ci][taps-1-tap]      (input is dY itself)
@@ -995,10 +1036,9 @@ static bool build_taps(const IgemmShape& s, TapTable& t) {
     return true;
   }
   // strided dgrad: s.pH/pW hold the conv's own padding, weights are packed tap-flipped (pack_weights*<DGRAD>)
-  t.ncls = s.scatH * s.scatW;
+  int c = 0;
   for (int ph = 0; ph < s.scatH; ++ph)
     for (int pw = 0; pw < s.scatW; ++pw) {
-      const int c = ph * s.scatW + pw;
       t.start[c] = n;
       t.oh[c] = (int8_t)ph; t.ow[c] = (int8_t)pw;
       for (int kh = 0; kh < s.kH; ++kh)
@@ -1011,8 +1051,11 @@ static bool build_taps(const IgemmShape& s, TapTable& t) {
           t.tap[n] = (uint8_t)((s.kH - 1 - kh) * s.kW + (s.kW - 1 - kw));
           ++n;
         }
-      if (n == t.start[c]) return false;   // a class without taps (e.g. 1x1 stride 2) would need a zero fill: direct engine
+      if (n == t.start[c]) t.zero_fill = 1;   // a parity without taps (e.g. 1x1 stride 2) is all zeros: no class for it
+      else ++c;
     }
+  if (c == 0) return false;
+  t.ncls = c;
   t.start[t.ncls] = n;
   return true;
 }
@@ -1198,6 +1241,7 @@ static int launch_igemm(const void* in, const void* wpacked, const float* bias, 
     int rc = encode_map(&map_b, dtype, 4, wpacked, dims, str, box, est, row_bytes);
     if (rc) return rc;
   }
+  if (p.tt.zero_fill) QUAN_CUDA(cudaMemsetAsync(out, 0, (size_t)s.B * s.Ho * s.Wo * NQ * s.N * esz, st));
   int ctas = 0, rc = QUAN_OK;
 #define QUAN_IGEMM_CASE(CGV, KS) rc = launch_igemm_inst<T, MIX, CGV, KS, NQ>(map_a, map_b, out, p, smem, s.name, st, &ctas)
   if (cg == 2) {
@@ -1479,7 +1523,15 @@ static int launch_wgrad(const void* gq, const void* x, float* const dw[4], const
     dim3 rgrid((unsigned)((d.Ci + cchunk - 1) / cchunk), (unsigned)(4 * d.Co));
     const size_t rsmem = (size_t)(SL > 1 ? 256 : cchunk * p.taps) * sizeof(float) + 16;
     QUAN_TIMED(st);
-    if (dense)
+    static const int env_flat = [] { const char* e = getenv("QUAN_TC_WG_FLATFOLD"); return e ? atoi(e) : 1; }();
+    const int64_t dw_elems = (int64_t)4 * d.Co * d.Ci * p.taps;
+    if (env_flat && fold_splits <= 4 && dw_elems <= (1 << 18)) {
+      const unsigned fgrid = (unsigned)((dw_elems + 255) / 256);
+      if (dense)
+        wgrad_reduce_flat_kernel<true><<<fgrid, 256, 0, st>>>(p.partial, dw[0], dw[1], dw[2], dw[3], fold_splits, p.taps, d.Co, d.Ci, mix);
+      else
+        wgrad_reduce_flat_kernel<false><<<fgrid, 256, 0, st>>>(p.partial, dw[0], dw[1], dw[2], dw[3], fold_splits, p.taps, d.Co, d.Ci, mix);
+    } else if (dense)
       wgrad_reduce_kernel<true><<<rgrid, 256, rsmem, st>>>(p.partial, dw[0], dw[1], dw[2], dw[3], fold_splits, p.taps, d.Co, d.Ci, cchunk, SL, mix);
     else
       wgrad_reduce_kernel<false><<<rgrid, 256, rsmem, st>>>(p.partial, dw[0], dw[1], dw[2], dw[3], fold_splits, p.taps, d.Co, d.Ci, cchunk, SL, mix);

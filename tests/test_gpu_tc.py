@@ -94,6 +94,39 @@ def test_tc_is_what_auto_picks_for_the_sweep_shapes():
         == ops.ALGO_DIRECT
 
 
+# name: (dtype, B, C_i, C_o, H, W, k, s, p)
+SPARSE_PARITY_CASES = [
+    ("qresnet_shortcut_dense", "bf16", 5, 16, 32, 28, 28, 1, 2, 0),
+    ("qresnet_shortcut_sep", "bf16", 3, 64, 128, 14, 14, 1, 2, 0),
+    ("k1_s2_odd_f32", "f32", 2, 64, 64, 15, 13, 1, 2, 0),
+    ("k1_s2_dense_ragged", "bf16", 2, 8, 16, 21, 17, 1, 2, 0),
+]
+
+
+@pytest.mark.parametrize("case", SPARSE_PARITY_CASES, ids=[c[0] for c in SPARSE_PARITY_CASES])
+def test_strided_dgrad_with_empty_parity_classes(case):
+    """Strided dgrad whose filter misses some output parities (1x1 stride 2, the Q-ResNet-34 shortcut convs,
+    classification/models/quaternion_models.py): those classes are dropped, dX is cleared first.  Against the direct engine."""
+    name, dt, B, ci, co, H, W, k, s, p = case
+    dtype = torch.bfloat16 if dt == "bf16" else torch.float32
+    tol = 1e-2 if dtype == torch.bfloat16 else 1e-3
+    torch.manual_seed(3)
+    x = torch.randn(B, ci, H, W, 4, device=DEV).to(dtype).contiguous(memory_format=torch.channels_last_3d)
+    w = [torch.randn(co, ci, k, k, device=DEV) / (ci * k * k) ** 0.5 for _ in range(4)]
+    args = ((s, s), (p, p), (1, 1), 1, ops.M_B)
+    assert ops.qconv2d_pick_algo(x.shape, w[0].shape, *args[:4], dtype, L, 1) == ops.ALGO_TCGEN05
+    y = ops.qconv2d_fwd(x, w, None, *args, ops.ALGO_AUTO, L)
+    dy = torch.randn_like(y)
+    dx_ref, dw_ref, _ = ops.qconv2d_bwd(dy, x, w, *args, True, True, False, ops.ALGO_DIRECT)
+    dx, dw, _ = ops.qconv2d_bwd(dy, x, w, *args, True, True, False, ops.ALGO_AUTO)
+    assert rel(dx, dx_ref) <= 2 * tol
+    # rows / columns no tap reaches are exactly zero
+    if k == 1:
+        assert float(dx[:, :, 1::2].abs().max()) == 0.0 and float(dx[:, :, :, 1::2].abs().max()) == 0.0
+    for a, r in zip(dw, dw_ref):
+        assert rel(a, r) <= 2 * tol
+
+
 def test_tc_linearity_at_sweep_size():
     """BASELINE-size property (no oracle): conv(a + 2b) == conv(a) + 2 conv(b) through the tensor-core path."""
     torch.manual_seed(0)
@@ -218,6 +251,9 @@ SMALL_CASES = [
     ("f32_8_2_k5", "f32", 2, 8, 2, 20, 20, 5, 1, 2, 1, True, "A"),
     ("f32_1_8_dil2_s2", "f32", 3, 1, 8, 21, 23, 3, 2, 2, 2, False, "B"),
     ("f32_2_2_k1", "f32", 2, 2, 2, 16, 16, 1, 1, 0, 1, False, "A"),
+    # wide outputs behind 1..2 input channels run forward / wgrad in chunks of 8 output channels (Q-ResNet-34 stem)
+    ("qresnet_stem_1_16_k7", "bf16", 2, 1, 16, 40, 36, 7, 2, 3, 1, True, "B"),
+    ("chunk_2_24_bf16", "bf16", 2, 2, 24, 19, 17, 3, 1, 1, 1, False, "A"),
 ]
 
 
@@ -235,7 +271,11 @@ def test_small_channel_engine_matches_direct_engine(case):
     args = ((s, s), (p, p), (d, d), 1, ops.MIX[mix])
     picks = [ops.qconv2d_pick_algo(x.shape, w[0].shape, *args[:4], dtype, L, ps) for ps in range(3)]
     # the tensor-core dense form has priority where its row / N granularity allows (e.g. fp32 dgrad with 4*C_o*4 B = 32 B rows)
-    assert picks[0] == ops.ALGO_SMALLC and all(pk in (ops.ALGO_SMALLC, ops.ALGO_TCGEN05) for pk in picks)
+    chunked = Co > 8
+    assert picks[0] == ops.ALGO_SMALLC and all(pk in (ops.ALGO_SMALLC, ops.ALGO_TCGEN05) for pk in picks[::2])
+    assert picks[1] in ((ops.ALGO_DIRECT, ops.ALGO_TCGEN05) if chunked else (ops.ALGO_SMALLC, ops.ALGO_TCGEN05))
+    if chunked:
+        assert picks[2] == ops.ALGO_SMALLC
     if dtype == torch.float32 and ops.ALGO_TCGEN05 in picks:
         tol = 1e-3
     y_ref = ops.qconv2d_fwd(x, w, b, *args, ops.ALGO_DIRECT, L)
