@@ -1,4 +1,7 @@
-"""Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list: time and launch count per kernel."""
+"""Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list: time and launch count per kernel.
+    python tools/launch_summary.py launches.csv [top_n] [--step MARKER]
+--step MARKER keeps only the launches from the first kernel whose name contains MARKER up to (not including) the second
+one, i.e. exactly one step of a trace whose first kernel is MARKER (the stem's `poincare_fwd_kernel`)."""
 import collections
 import csv
 import re
@@ -8,8 +11,14 @@ rows = list(csv.reader(open(sys.argv[1])))
 hdr = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
 h = rows[hdr]
 ki, vi = h.index("Kernel Name"), h.index("Metric Value")
+body = [r for r in rows[hdr + 2:] if len(r) > vi]
+if "--step" in sys.argv:
+    marker = sys.argv[sys.argv.index("--step") + 1]
+    hits = [i for i, r in enumerate(body) if marker in r[ki]]
+    body = body[hits[0]:hits[1]] if len(hits) >= 2 else body[hits[0]:]
+    sys.argv = [a for a in sys.argv if a not in ("--step", marker)]
 agg = collections.defaultdict(lambda: [0, 0.0])
-for r in rows[hdr + 2:]:
+for r in body:
     if len(r) <= vi:
         continue
     name = re.sub(r"\(.*", "", r[ki])[:90]
