@@ -142,6 +142,20 @@ int quan_qupsample_nearest_fwd(const void* x, void* y, int32_t B, int32_t C, int
 int quan_qupsample_nearest_bwd(const void* dy, void* dx, int32_t B, int32_t C, int32_t H, int32_t W,
                                int32_t scale, int dtype, int layout, void* stream);
 
+/* ---- QuaternionMaxPool ---------------------------------------------------------------------
+ * Replaces QuaternionMaxPool.forward, ultralytics/nn/modules/block.py:85-109 (== classification/models/blocks/
+ * quaternion_blocks.py:236-260): nn.MaxPool2d(kernel, stride, padding) on each of the four components, stacked back
+ * (users: QSPPF block.py:270-302, the Q-ResNet stems quaternion_models.py:193,236).  x [B,C,H,W,4] ->
+ * y [B,C,Ho,Wo,4], Ho = (H + 2p - k)/s + 1; padding counts as -inf, the first maximum of the row-major window scan wins
+ * ties, NaN propagates (nn.MaxPool2d).  idx: one byte per output element holding the winning tap kh*kW + kw (what the
+ * backward routes the gradient by); NULL for inference.  bwd: dx = gather of dy over the windows whose tap points at
+ * the element (autograd of the reference; deterministic).  kH*kW <= 255, 2*pad <= kernel. */
+int quan_qmaxpool_fwd(const void* x, void* y, uint8_t* idx, int32_t B, int32_t C, int32_t H, int32_t W, int32_t kH,
+                      int32_t kW, int32_t sH, int32_t sW, int32_t pH, int32_t pW, int dtype, int layout, void* stream);
+int quan_qmaxpool_bwd(const void* dy, const uint8_t* idx, void* dx, int32_t B, int32_t C, int32_t H, int32_t W,
+                      int32_t kH, int32_t kW, int32_t sH, int32_t sW, int32_t pH, int32_t pW, int dtype, int layout,
+                      void* stream);
+
 /* ---- helpers ---------------------------------------------------------------------------------
  * quan_mix: out_p = sum_q mix[4p+q] in_q per quaternion (qmix_forward/backward kernels,
  *   ultralytics/nn/cuda/quaternion_ops_head.cu:8-95).  n_quat = B*C*H*W.

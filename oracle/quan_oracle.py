@@ -195,5 +195,45 @@ def qupsample_bwd(dy, scale=2):
     return dy.reshape(B, C, Ho // scale, scale, Wo // scale, scale, Q).sum(axis=(3, 5))
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# QuaternionMaxPool — block.py:85-109 (nn.MaxPool2d per component + stack); backward = autograd of it.
+# nn.MaxPool2d: padding is -inf, the window is scanned row-major and a later element replaces the running maximum only
+# if strictly greater (or NaN): the first maximum wins ties and alone receives the gradient.
+# ---------------------------------------------------------------------------------------------------------------
+def _pool_windows(H, W, k, s, p):
+    (kh, kw), (sh, sw), (ph, pw) = [(v, v) if isinstance(v, int) else tuple(v) for v in (k, s, p)]
+    Ho, Wo = (H + 2 * ph - kh) // sh + 1, (W + 2 * pw - kw) // sw + 1
+    return kh, kw, sh, sw, ph, pw, Ho, Wo
+
+
+def qmaxpool_fwd(x, kernel_size, stride, padding):
+    """x [B,C,H,W,4] -> (y [B,C,Ho,Wo,4], arg [B,C,Ho,Wo,4] flat input index hi*W + wi of the winner)."""
+    B, C, H, W, Q = x.shape
+    kh, kw, sh, sw, ph, pw, Ho, Wo = _pool_windows(H, W, kernel_size, stride, padding)
+    y = np.full((B, C, Ho, Wo, Q), -np.inf, dtype=x.dtype)
+    arg = np.full((B, C, Ho, Wo, Q), -1, dtype=np.int64)
+    ho, wo = np.meshgrid(np.arange(Ho), np.arange(Wo), indexing="ij")
+    for a in range(kh):
+        for b in range(kw):
+            hi, wi = ho * sh - ph + a, wo * sw - pw + b
+            ok = (hi >= 0) & (hi < H) & (wi >= 0) & (wi < W)
+            v = x[:, :, np.clip(hi, 0, H - 1), np.clip(wi, 0, W - 1), :]            # [B,C,Ho,Wo,Q]
+            take = ok[None, None, :, :, None] & ((arg < 0) | (v > y) | np.isnan(v))
+            y = np.where(take, v, y)
+            arg = np.where(take, (hi * W + wi)[None, None, :, :, None], arg)
+    return y, arg
+
+
+def qmaxpool_bwd(dy, arg, in_hw):
+    B, C, Ho, Wo, Q = dy.shape
+    H, W = in_hw
+    dx = np.zeros((B, C, H * W, Q), dtype=dy.dtype)
+    bi, ci, qi = np.meshgrid(np.arange(B), np.arange(C), np.arange(Q), indexing="ij")
+    for ho in range(Ho):
+        for wo in range(Wo):
+            np.add.at(dx, (bi, ci, arg[:, :, ho, wo, :], qi), dy[:, :, ho, wo, :])
+    return dx.reshape(B, C, H, W, Q)
+
+
 def mix_apply(x, mix):
     return np.einsum("pq,bchwq->bchwp", np.asarray(mix, dtype=x.dtype), x)

@@ -53,6 +53,8 @@ PROTOTYPES = {
     "quan_iqbn_eval_bwd": (_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _int, _int, _vp, _vp, _vp, _vp, _f, _int, _vp]),
     "quan_qupsample_nearest_fwd": (_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _int, _int, _vp]),
     "quan_qupsample_nearest_bwd": (_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _int, _int, _vp]),
+    "quan_qmaxpool_fwd": (_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _int, _int, _vp]),
+    "quan_qmaxpool_bwd": (_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _int, _int, _vp]),
     "quan_mix": (_int, [_vp, _vp, _i32, _i32, _i32, _i32, _int, _int, _vp, _vp]),
     "quan_layout_convert": (_int, [_vp, _int, _vp, _int, _i32, _i32, _i32, _i32, _int, _vp]),
     "quan_qconv2d_workspace_bytes": (_sz, [_pdims, _int, _int, _int]),

@@ -1,0 +1,202 @@
+// qpool.cu — QuaternionMaxPool forward / backward.
+//
+// Reference: ultralytics/nn/modules/block.py:85-109 ≡ classification/models/blocks/quaternion_blocks.py:236-260 — a
+// Python loop of four nn.MaxPool2d calls on strided component slices plus a torch.stack copy (≈ 4 slice copies + 4 pool
+// kernels + 1 stack: 3 extra full-tensor HBM round trips); backward = autograd of that (4 scatter kernels).  Users: QSPPF
+// (block.py:270-302: k=5, s=1, p=2, three times on the P5 map) and the Q-ResNet stems (quaternion_models.py:193,236:
+// k=3, s=2, p=1 on 112^2).
+//
+// Here: the four components of every channel are independent real planes, so in either layout the tensor is
+// [outer][H][W][inner] with `inner` contiguous elements pooled element-wise (BCHWQ: outer = B*C, inner = 4;
+// BHWQC: outer = B, inner = 4C).  A thread owns one 16-byte vector of `inner` at one output pixel: HBM-bound,
+// algorithmic bytes fwd = S_in + S_out (+ S_out/sizeof(T) index bytes when training), bwd = S_dy + idx + S_dx.
+//
+// nn.MaxPool2d semantics kept exactly (aten/native/cuda/DilatedMaxPool2d.cu behaviour): padding counts as -inf,
+// window scanned row-major, a later element replaces the running maximum only if it is strictly greater or NaN — so
+// the FIRST maximum wins ties (frequent in bf16) and the gradient goes to that element alone.  The forward stores the
+// winning tap (kh*kW + kw, one byte per element); the backward is a gather — each input element sums dy over the
+// windows that contain it and whose stored tap points at it — deterministic, no atomics.
+#include <cstdint>
+
+#include "common.cuh"
+#include "quan_sm100.h"
+
+namespace quan {
+
+struct PoolGeom {
+  int64_t outer;
+  int H, W, Ho, Wo, inner_vecs;
+  int kH, kW, sH, sW, pH, pW;
+};
+
+template <typename T, int V, bool WITH_IDX>
+__global__ void __launch_bounds__(256) qmaxpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y,
+                                                           uint8_t* __restrict__ idx, PoolGeom g) {
+  const int64_t total = g.outer * g.Ho * g.Wo * g.inner_vecs;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int iv = (int)(i % g.inner_vecs);
+    int64_t r = i / g.inner_vecs;
+    const int wo = (int)(r % g.Wo);
+    r /= g.Wo;
+    const int ho = (int)(r % g.Ho);
+    const int64_t o = r / g.Ho;
+    float best[V];
+    uint8_t arg[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) { best[v] = -INFINITY; arg[v] = 0; }
+    bool first = true;
+    const int h0 = ho * g.sH - g.pH, w0 = wo * g.sW - g.pW;
+    for (int kh = 0; kh < g.kH; ++kh) {
+      const int hi = h0 + kh;
+      if (hi < 0 || hi >= g.H) continue;
+      for (int kw = 0; kw < g.kW; ++kw) {
+        const int wi = w0 + kw;
+        if (wi < 0 || wi >= g.W) continue;
+        float xv[V];
+        load_vec<T, V>(x + (((o * g.H + hi) * g.W + wi) * g.inner_vecs + iv) * V, xv);
+        const uint8_t tap = (uint8_t)(kh * g.kW + kw);
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          // the first valid element always seeds the maximum (PyTorch starts from it: -inf inputs keep their own index)
+          if (first || xv[v] > best[v] || xv[v] != xv[v]) { best[v] = xv[v]; arg[v] = tap; }
+        }
+        first = false;
+      }
+    }
+    store_vec<T, V>(y + i * V, best);
+    if constexpr (WITH_IDX) {
+      Vec<uint8_t, V> a;
+#pragma unroll
+      for (int v = 0; v < V; ++v) a.v[v] = arg[v];
+      *reinterpret_cast<Vec<uint8_t, V>*>(idx + i * V) = a;
+    }
+  }
+}
+
+template <typename T, int V>
+__global__ void __launch_bounds__(256) qmaxpool_bwd_kernel(const T* __restrict__ dy, const uint8_t* __restrict__ idx,
+                                                           T* __restrict__ dx, PoolGeom g) {
+  const int64_t total = g.outer * g.H * g.W * g.inner_vecs;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int iv = (int)(i % g.inner_vecs);
+    int64_t r = i / g.inner_vecs;
+    const int wi = (int)(r % g.W);
+    r /= g.W;
+    const int hi = (int)(r % g.H);
+    const int64_t o = r / g.H;
+    float acc[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) acc[v] = 0.f;
+    // output rows whose window holds hi: ho*sH - pH <= hi <= ho*sH - pH + kH - 1
+    int ho_lo = hi + g.pH - g.kH + 1;
+    ho_lo = ho_lo <= 0 ? 0 : (ho_lo + g.sH - 1) / g.sH;
+    int ho_hi = (hi + g.pH) / g.sH;
+    if (ho_hi > g.Ho - 1) ho_hi = g.Ho - 1;
+    int wo_lo = wi + g.pW - g.kW + 1;
+    wo_lo = wo_lo <= 0 ? 0 : (wo_lo + g.sW - 1) / g.sW;
+    int wo_hi = (wi + g.pW) / g.sW;
+    if (wo_hi > g.Wo - 1) wo_hi = g.Wo - 1;
+    for (int ho = ho_lo; ho <= ho_hi; ++ho) {
+      const int kh = hi - (ho * g.sH - g.pH);
+      for (int wo = wo_lo; wo <= wo_hi; ++wo) {
+        const int tap = kh * g.kW + (wi - (wo * g.sW - g.pW));
+        const int64_t e = (((o * g.Ho + ho) * g.Wo + wo) * g.inner_vecs + iv) * V;
+        const Vec<uint8_t, V> a = *reinterpret_cast<const Vec<uint8_t, V>*>(idx + e);
+        bool any = false;
+#pragma unroll
+        for (int v = 0; v < V; ++v) any |= (a.v[v] == tap);
+        if (!any) continue;
+        float gv[V];
+        load_vec<T, V>(dy + e, gv);
+#pragma unroll
+        for (int v = 0; v < V; ++v)
+          if (a.v[v] == tap) acc[v] += gv[v];
+      }
+    }
+    store_vec<T, V>(dx + i * V, acc);
+  }
+}
+
+static int pool_geom(const char* who, int B, int C, int H, int W, int kH, int kW, int sH, int sW, int pH, int pW, int dtype,
+                     int layout, PoolGeom& g, int& V) {
+  QUAN_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, QUAN_E_ARG, "%s: non-positive dims", who);
+  QUAN_REQUIRE(dtype == QUAN_F32 || dtype == QUAN_BF16, QUAN_E_ARG, "%s: bad dtype %d", who, dtype);
+  QUAN_REQUIRE(layout == QUAN_LAYOUT_BCHWQ || layout == QUAN_LAYOUT_BHWQC, QUAN_E_ARG, "%s: bad layout %d", who, layout);
+  QUAN_REQUIRE(kH >= 1 && kW >= 1 && sH >= 1 && sW >= 1 && pH >= 0 && pW >= 0, QUAN_E_SHAPE, "%s: bad window", who);
+  QUAN_REQUIRE(kH * kW <= 255, QUAN_E_UNSUPPORTED, "%s: window %dx%d exceeds the one-byte tap index", who, kH, kW);
+  // nn.MaxPool2d: "pad should be at most half of effective kernel size"
+  QUAN_REQUIRE(2 * pH <= kH && 2 * pW <= kW, QUAN_E_SHAPE, "%s: padding (%d,%d) exceeds half the window (%d,%d)", who, pH, pW, kH, kW);
+  g.H = H; g.W = W;
+  g.Ho = (H + 2 * pH - kH) / sH + 1;
+  g.Wo = (W + 2 * pW - kW) / sW + 1;
+  QUAN_REQUIRE(H + 2 * pH >= kH && W + 2 * pW >= kW && g.Ho > 0 && g.Wo > 0, QUAN_E_SHAPE, "%s: window larger than the padded input", who);
+  g.kH = kH; g.kW = kW; g.sH = sH; g.sW = sW; g.pH = pH; g.pW = pW;
+  int inner;
+  if (layout == QUAN_LAYOUT_BCHWQ) { g.outer = (int64_t)B * C; inner = 4; }
+  else { g.outer = B; inner = 4 * C; }
+  V = largest_pow2_divisor(inner, dtype == QUAN_BF16 ? 8 : 4);
+  g.inner_vecs = inner / V;
+  return QUAN_OK;
+}
+
+template <typename T>
+static int launch_pool_fwd(const void* x, void* y, uint8_t* idx, const PoolGeom& g, int V, cudaStream_t st) {
+  const T* xp = reinterpret_cast<const T*>(x);
+  T* yp = reinterpret_cast<T*>(y);
+  const int grid = grid_for(g.outer * g.Ho * g.Wo * g.inner_vecs, 256, 8);
+  QUAN_TIMED(st);
+#define QUAN_POOL_FWD(VV)                                                                       \
+  do {                                                                                          \
+    if (idx != nullptr) qmaxpool_fwd_kernel<T, VV, true><<<grid, 256, 0, st>>>(xp, yp, idx, g); \
+    else qmaxpool_fwd_kernel<T, VV, false><<<grid, 256, 0, st>>>(xp, yp, idx, g);               \
+  } while (0)
+  if (V == 8) { if constexpr (sizeof(T) == 2) QUAN_POOL_FWD(8); }
+  else QUAN_POOL_FWD(4);
+#undef QUAN_POOL_FWD
+  QUAN_CHECK_LAUNCH("qmaxpool_fwd");
+  return QUAN_OK;
+}
+
+template <typename T>
+static int launch_pool_bwd(const void* dy, const uint8_t* idx, void* dx, const PoolGeom& g, int V, cudaStream_t st) {
+  const T* gp = reinterpret_cast<const T*>(dy);
+  T* dp = reinterpret_cast<T*>(dx);
+  const int grid = grid_for(g.outer * g.H * g.W * g.inner_vecs, 256, 8);
+  QUAN_TIMED(st);
+  if (V == 8) { if constexpr (sizeof(T) == 2) qmaxpool_bwd_kernel<T, 8><<<grid, 256, 0, st>>>(gp, idx, dp, g); }
+  else qmaxpool_bwd_kernel<T, 4><<<grid, 256, 0, st>>>(gp, idx, dp, g);
+  QUAN_CHECK_LAUNCH("qmaxpool_bwd");
+  return QUAN_OK;
+}
+
+}  // namespace quan
+
+using namespace quan;
+
+extern "C" {
+
+int quan_qmaxpool_fwd(const void* x, void* y, uint8_t* idx, int32_t B, int32_t C, int32_t H, int32_t W, int32_t kH, int32_t kW,
+                      int32_t sH, int32_t sW, int32_t pH, int32_t pW, int dtype, int layout, void* stream) {
+  QUAN_REQUIRE(x != nullptr && y != nullptr, QUAN_E_ARG, "qmaxpool_fwd: null pointer");
+  PoolGeom g;
+  int V = 0;
+  int rc = pool_geom("qmaxpool_fwd", B, C, H, W, kH, kW, sH, sW, pH, pW, dtype, layout, g, V);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == QUAN_F32) return launch_pool_fwd<float>(x, y, idx, g, V, st);
+  return launch_pool_fwd<__nv_bfloat16>(x, y, idx, g, V, st);
+}
+
+int quan_qmaxpool_bwd(const void* dy, const uint8_t* idx, void* dx, int32_t B, int32_t C, int32_t H, int32_t W, int32_t kH,
+                      int32_t kW, int32_t sH, int32_t sW, int32_t pH, int32_t pW, int dtype, int layout, void* stream) {
+  QUAN_REQUIRE(dy != nullptr && idx != nullptr && dx != nullptr, QUAN_E_ARG, "qmaxpool_bwd: null pointer");
+  PoolGeom g;
+  int V = 0;
+  int rc = pool_geom("qmaxpool_bwd", B, C, H, W, kH, kW, sH, sW, pH, pW, dtype, layout, g, V);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == QUAN_F32) return launch_pool_bwd<float>(dy, idx, dx, g, V, st);
+  return launch_pool_bwd<__nv_bfloat16>(dy, idx, dx, g, V, st);
+}
+
+}  // extern "C"

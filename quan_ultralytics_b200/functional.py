@@ -224,3 +224,26 @@ class _QUpsample(torch.autograd.Function):
 
 def qupsample_nearest(x: torch.Tensor, scale: int = 2) -> torch.Tensor:
     return _QUpsample.apply(x, int(scale))
+
+
+class _QMaxPool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, kernel, stride, padding):
+        y, idx = ops.qmaxpool_fwd(x, kernel, stride, padding, with_idx=True)
+        ctx.save_for_backward(idx)
+        ctx.cfg = (tuple(x.shape[2:4]), kernel, stride, padding)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (idx,) = ctx.saved_tensors
+        in_hw, kernel, stride, padding = ctx.cfg
+        return ops.qmaxpool_bwd(dy, idx, in_hw, kernel, stride, padding), None, None, None
+
+
+def qmaxpool(x: torch.Tensor, kernel_size=2, stride=2, padding=0) -> torch.Tensor:
+    """QuaternionMaxPool (block.py:85-109): max pooling of every quaternion component; first maximum wins ties."""
+    if not (x.requires_grad and torch.is_grad_enabled()):
+        return ops.qmaxpool_fwd(x, kernel_size, stride, padding, with_idx=False)[0]
+    return _QMaxPool.apply(x, kernel_size, stride, padding)
+

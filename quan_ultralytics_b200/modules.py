@@ -204,6 +204,22 @@ class QUpsample(nn.Module):
         return QF.qupsample_nearest(x, self.scale_factor)
 
 
+class QuaternionMaxPool(nn.Module):
+    """Max pooling of every quaternion component (ultralytics/nn/modules/block.py:85-109 ==
+    classification/models/blocks/quaternion_blocks.py:236-260); constructor as the reference's."""
+
+    def __init__(self, kernel_size=2, stride=2, padding=0):
+        super().__init__()
+        self.kernel_size, self.stride, self.padding = kernel_size, stride, padding
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        assert x.dim() == 5 and x.size(4) == 4, "Expected quaternion format with 4 components"
+        return QF.qmaxpool(x, self.kernel_size, self.stride, self.padding)
+
+    def extra_repr(self) -> str:
+        return f"kernel_size={self.kernel_size}, stride={self.stride}, padding={self.padding}"
+
+
 class Conv(nn.Module):
     """QConv2D -> IQBN -> SiLU (conv.py:788-813); IQBN-apply and SiLU run as one fused kernel."""
 

@@ -203,6 +203,44 @@ def qupsample_bwd(dy: torch.Tensor, scale: int) -> torch.Tensor:
     return out
 
 
+# ---- QuaternionMaxPool -------------------------------------------------------------------------------------------
+def _pair(v):
+    return (int(v), int(v)) if isinstance(v, int) else (int(v[0]), int(v[1]))
+
+
+def qmaxpool_out_hw(H: int, W: int, kernel, stride, padding) -> Tuple[int, int]:
+    (kh, kw), (sh, sw), (ph, pw) = _pair(kernel), _pair(stride), _pair(padding)
+    return (H + 2 * ph - kh) // sh + 1, (W + 2 * pw - kw) // sw + 1
+
+
+def qmaxpool_fwd(x: torch.Tensor, kernel, stride, padding, with_idx: bool = True):
+    """nn.MaxPool2d on each quaternion component (block.py:85-109).  Returns (y, idx); idx (uint8, the winning tap per
+    output element, laid out like y) is None when with_idx is False."""
+    _require_cuda(x)
+    x, layout = as_layout(x)
+    B, C_, H, W, _ = x.shape
+    (kh, kw), (sh, sw), (ph, pw) = _pair(kernel), _pair(stride), _pair(padding)
+    Ho, Wo = qmaxpool_out_hw(H, W, kernel, stride, padding)
+    out = empty_q((B, C_, max(Ho, 1), max(Wo, 1), 4), x.dtype, x.device, layout)
+    idx = empty_q((B, C_, max(Ho, 1), max(Wo, 1), 4), torch.uint8, x.device, layout) if with_idx else None
+    check(_lib.load().quan_qmaxpool_fwd(x.data_ptr(), out.data_ptr(), idx.data_ptr() if with_idx else None, B, C_, H, W,
+                                        kh, kw, sh, sw, ph, pw, _dtype_code(x), layout, _stream(x)), "quan_qmaxpool_fwd")
+    return out, idx
+
+
+def qmaxpool_bwd(dy: torch.Tensor, idx: torch.Tensor, in_hw, kernel, stride, padding) -> torch.Tensor:
+    _require_cuda(dy, idx)
+    layout = layout_of(idx)
+    dy, _ = as_layout(dy, layout)
+    B, C_, Ho, Wo, _ = dy.shape
+    H, W = in_hw
+    (kh, kw), (sh, sw), (ph, pw) = _pair(kernel), _pair(stride), _pair(padding)
+    out = empty_q((B, C_, H, W, 4), dy.dtype, dy.device, layout)
+    check(_lib.load().quan_qmaxpool_bwd(dy.data_ptr(), idx.data_ptr(), out.data_ptr(), B, C_, H, W, kh, kw, sh, sw, ph, pw,
+                                        _dtype_code(dy), layout, _stream(dy)), "quan_qmaxpool_bwd")
+    return out
+
+
 # ---- IQBN ----------------------------------------------------------------------------------------------------------
 def iqbn_train_stats(x: torch.Tensor, layout: int, gamma: torch.Tensor, beta: torch.Tensor, eps: float, momentum: float,
                      running_mean: Optional[torch.Tensor], running_var: Optional[torch.Tensor]) -> torch.Tensor:
