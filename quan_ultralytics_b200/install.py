@@ -16,7 +16,7 @@ import types
 from . import modules as M
 from . import quaternion_ops as shim
 
-_SWAP = ("QConv2D", "IQBN", "Conv", "DWConv", "QUpsample")
+_SWAP = ("QConv2D", "IQBN", "Conv", "DWConv", "QUpsample", "QuaternionMaxPool")
 
 
 def install_extension_shim(mixing: str = "A") -> types.ModuleType:
@@ -55,5 +55,8 @@ def install(ultralytics: bool = True, classification: bool = True) -> dict:
             if hasattr(mod, "IQBN"):
                 mod.IQBN = M.IQBN
                 names.append("IQBN")
+            if hasattr(mod, "QuaternionMaxPool"):        # models/blocks/quaternion_blocks.py:236-260 (Q-ResNet stems)
+                mod.QuaternionMaxPool = M.QuaternionMaxPool
+                names.append("QuaternionMaxPool")
             done[modname] = names
     return done

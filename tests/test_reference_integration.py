@@ -77,8 +77,11 @@ def test_class_swap_builds_reference_graphs_with_b200_modules(reference):
     uconv, cconv = reference
     import ultralytics.nn.tasks as tasks
     import yaml
-    saved = {(m, n): getattr(m, n) for m in (uconv, tasks) for n in ("QConv2D", "IQBN", "Conv", "DWConv", "QUpsample")
-             if hasattr(m, n)}
+    import ultralytics.nn.modules.block as ublock
+    import models.blocks.quaternion_blocks as cblocks
+    import models.quaternion_models as cmodels
+    saved = {(m, n): getattr(m, n) for m in (uconv, tasks, ublock, cblocks, cmodels)
+             for n in ("QConv2D", "IQBN", "Conv", "DWConv", "QUpsample", "QuaternionMaxPool") if hasattr(m, n)}
     saved_c = (cconv.QConv2D, cconv.IQBN)
     try:
         cfg = yaml.safe_load((REF / "ultralytics/cfg/models/11/yolo11-obb-quan.yaml").read_text())
@@ -95,6 +98,9 @@ def test_class_swap_builds_reference_graphs_with_b200_modules(reference):
         n_up = sum(isinstance(m, Q.QUpsample) for m in our_model.modules())
         # blocks that import QConv2D/IQBN by name at module scope keep building (87 convs / 84 norms in YOLO11n)
         assert n_q >= 60 and n_bn >= 60 and n_up == 2, (n_q, n_bn, n_up)
+        # QSPPF (block.py:270-302) pools with the B200 QuaternionMaxPool; so does the Q-ResNet-34 stem
+        assert sum(isinstance(m, Q.QuaternionMaxPool) for m in our_model.modules()) >= 1
+        assert isinstance(cmodels.create_qrn34_imagenet(10).maxpool, Q.QuaternionMaxPool)
         our_model.load_state_dict(ref_model.state_dict())
         assert cconv.QConv2D is Q.QConv2D_B and cconv.IQBN is Q.IQBN
     finally:
