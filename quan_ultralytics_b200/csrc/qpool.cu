@@ -87,6 +87,87 @@ __global__ void __launch_bounds__(256) qmaxpool_fwd_kernel(const T* __restrict__
   }
 }
 
+// bf16 forward with packed arithmetic: per bf16x2 pair and tap one compare-mask (strictly greater: the first maximum keeps
+// its tap), one max and one LOP3 that merges the tap number under the mask — 3 instructions where the scalar kernel above
+// spends ~16 (two conversions, two compares, four selects); 283 -> see DESIGN §4.5.  NaN: __hmax2_nan carries it into the
+// value; the tap of a NaN result then comes from the scalar rule (last NaN of the scan) on a rare slow path.
+template <int V, bool WITH_IDX, typename I>
+__global__ void __launch_bounds__(256) qmaxpool_fwd_bf16_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                                                uint8_t* __restrict__ idx, PoolGeom g) {
+  constexpr int NP = V / 2;
+  using T = __nv_bfloat16;
+  const I total = (I)(g.outer * g.Ho * g.Wo * g.inner_vecs);
+  const int taps = g.kH * g.kW;
+  for (I i = (I)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (I)gridDim.x * blockDim.x) {
+    const int iv = (int)(i % g.inner_vecs);
+    I r = i / g.inner_vecs;
+    const int wo = (int)(r % g.Wo);
+    r /= g.Wo;
+    const int ho = (int)(r % g.Ho);
+    const I o = r / g.Ho;
+    const int h0 = ho * g.sH - g.pH, w0 = wo * g.sW - g.pW;
+    // the first valid tap seeds the index (an all -inf window keeps it, like PyTorch)
+    const uint32_t t_first = (uint32_t)((h0 < 0 ? -h0 : 0) * g.kW + (w0 < 0 ? -w0 : 0));
+    __nv_bfloat162 best[NP];
+    uint32_t arg[NP];
+    const __nv_bfloat162 ninf = __float2bfloat162_rn(-INFINITY);
+#pragma unroll
+    for (int p = 0; p < NP; ++p) { best[p] = ninf; arg[p] = t_first * 0x00010001u; }
+    const T* base = x + ((int64_t)o * g.H * g.W * g.inner_vecs + iv) * V;
+    int kh = 0, kw = 0;
+    for (int t0 = 0; t0 < taps; t0 += POOL_CH) {
+      Vec<T, V> raw[POOL_CH];
+      bool ok[POOL_CH];
+#pragma unroll
+      for (int j = 0; j < POOL_CH; ++j) {
+        const int hi = h0 + kh, wi = w0 + kw;
+        ok[j] = (t0 + j < taps) && hi >= 0 && hi < g.H && wi >= 0 && wi < g.W;
+        if (ok[j]) raw[j] = *reinterpret_cast<const Vec<T, V>*>(base + ((int64_t)hi * g.W + wi) * g.inner_vecs * V);
+        if (++kw == g.kW) { kw = 0; ++kh; }
+      }
+#pragma unroll
+      for (int j = 0; j < POOL_CH; ++j) {
+        if (!ok[j]) continue;
+        const uint32_t tap2 = (uint32_t)(t0 + j) * 0x00010001u;
+        const __nv_bfloat162* xv = reinterpret_cast<const __nv_bfloat162*>(&raw[j]);
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+          const uint32_t gt = __hgt2_mask(xv[p], best[p]);
+          best[p] = __hmax2_nan(best[p], xv[p]);
+          arg[p] = (tap2 & gt) | (arg[p] & ~gt);
+        }
+      }
+    }
+    bool has_nan = false;
+#pragma unroll
+    for (int p = 0; p < NP; ++p) has_nan |= (__hneu2_mask(best[p], best[p]) != 0u);   // unordered compare: true for NaN
+    Vec<uint8_t, V> a;
+#pragma unroll
+    for (int p = 0; p < NP; ++p) { a.v[2 * p] = (uint8_t)(arg[p] & 0xffu); a.v[2 * p + 1] = (uint8_t)((arg[p] >> 16) & 0xffu); }
+    if (WITH_IDX && has_nan) {
+      // scalar rule for the lanes whose result is NaN: the last NaN of the row-major scan holds the index
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        const float bvf = (v & 1) ? __high2float(best[v / 2]) : __low2float(best[v / 2]);
+        if (!(bvf != bvf)) continue;
+        uint8_t last = a.v[v];
+        for (int t = 0; t < taps; ++t) {
+          const int hi = h0 + t / g.kW, wi = w0 + t % g.kW;
+          if (hi < 0 || hi >= g.H || wi < 0 || wi >= g.W) continue;
+          const float xs = __bfloat162float(base[((int64_t)hi * g.W + wi) * g.inner_vecs * V + v]);
+          if (xs != xs) last = (uint8_t)t;
+        }
+        a.v[v] = last;
+      }
+    }
+    Vec<T, V> out;
+#pragma unroll
+    for (int p = 0; p < NP; ++p) { out.v[2 * p] = __low2bfloat16(best[p]); out.v[2 * p + 1] = __high2bfloat16(best[p]); }
+    *reinterpret_cast<Vec<T, V>*>(y + (int64_t)i * V) = out;
+    if constexpr (WITH_IDX) *reinterpret_cast<Vec<uint8_t, V>*>(idx + (int64_t)i * V) = a;
+  }
+}
+
 template <typename T, int V, typename I>
 __global__ void __launch_bounds__(256) qmaxpool_bwd_kernel(const T* __restrict__ dy, const uint8_t* __restrict__ idx,
                                                            T* __restrict__ dx, PoolGeom g) {
@@ -110,9 +191,9 @@ __global__ void __launch_bounds__(256) qmaxpool_bwd_kernel(const T* __restrict__
     wo_lo = wo_lo <= 0 ? 0 : (wo_lo + g.sW - 1) / g.sW;
     int wo_hi = (wi + g.pW) / g.sW;
     if (wo_hi > g.Wo - 1) wo_hi = g.Wo - 1;
-    // the index byte decides whether the gradient vector is needed at all: on average one window in kH*kW/(sH*sW) points
-    // here.  (Requesting index + gradient of all windows up front was measured slower: 1359 vs 636 us on the Q-ResNet stem
-    // pool — the extra dy traffic costs more than the dependent load.)
+    // one window at a time; the index byte decides whether the gradient vector is loaded at all.  Measured on the Q-ResNet
+    // stem pool (256x16x112^2, bf16): this loop 636 us; index + gradient of ALL windows requested up front 1359 us; index
+    // vectors of a batch first, then the needed gradient vectors 976 us — the simple dependent form stays.
     const int64_t obase = ((int64_t)o * g.Ho * g.Wo * g.inner_vecs + iv) * V;
     for (int ho = ho_lo; ho <= ho_hi; ++ho) {
       const int kh = hi - (ho * g.sH - g.pH);
@@ -171,9 +252,25 @@ static int launch_pool_fwd(const void* x, void* y, uint8_t* idx, const PoolGeom&
     else if (small) qmaxpool_fwd_kernel<T, VV, false, int><<<grid, 256, 0, st>>>(xp, yp, idx, g);                 \
     else qmaxpool_fwd_kernel<T, VV, false, int64_t><<<grid, 256, 0, st>>>(xp, yp, idx, g);                        \
   } while (0)
+#define QUAN_POOL_FWD_BF16(VV)                                                                                   \
+  do {                                                                                                           \
+    if (idx != nullptr && small) qmaxpool_fwd_bf16_kernel<VV, true, int><<<grid, 256, 0, st>>>(xp, yp, idx, g);   \
+    else if (idx != nullptr) qmaxpool_fwd_bf16_kernel<VV, true, int64_t><<<grid, 256, 0, st>>>(xp, yp, idx, g);   \
+    else if (small) qmaxpool_fwd_bf16_kernel<VV, false, int><<<grid, 256, 0, st>>>(xp, yp, idx, g);               \
+    else qmaxpool_fwd_bf16_kernel<VV, false, int64_t><<<grid, 256, 0, st>>>(xp, yp, idx, g);                      \
+  } while (0)
+  static const int env_packed = [] { const char* e = getenv("QUAN_POOL_PACKED"); return e ? atoi(e) : 1; }();
+  if constexpr (sizeof(T) == 2) {
+    if (env_packed) {
+      if (V == 8) QUAN_POOL_FWD_BF16(8); else QUAN_POOL_FWD_BF16(4);
+      QUAN_CHECK_LAUNCH("qmaxpool_fwd");
+      return QUAN_OK;
+    }
+  }
   if (V == 8) { if constexpr (sizeof(T) == 2) QUAN_POOL_FWD(8); }
   else QUAN_POOL_FWD(4);
 #undef QUAN_POOL_FWD
+#undef QUAN_POOL_FWD_BF16
   QUAN_CHECK_LAUNCH("qmaxpool_fwd");
   return QUAN_OK;
 }

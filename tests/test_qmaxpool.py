@@ -109,6 +109,26 @@ def test_cuda_matches_oracle_random(cfg, layout, dtype):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_nan_propagates_and_takes_the_gradient(dtype):
+    """nn.MaxPool2d: a NaN in the window is the result, and the LAST NaN of the row-major scan receives the gradient."""
+    from quan_ultralytics_b200 import functional as QF
+    torch.manual_seed(1)
+    x = torch.randn(1, 2, 6, 6, 4, device=DEV).to(dtype)
+    x[0, 0, 1, 1, 0] = float("nan")
+    x[0, 0, 2, 3, 0] = float("nan")
+    x = x.contiguous(memory_format=torch.channels_last_3d).requires_grad_(True)
+    y = QF.qmaxpool(x, 3, 1, 1)
+    y.backward(torch.ones_like(y))
+    xr = x.detach().float().cpu().requires_grad_(True)
+    yr = torch.stack([torch.nn.functional.max_pool2d(xr[..., q], 3, 1, 1) for q in range(4)], -1)
+    yr.backward(torch.ones_like(yr))
+    assert torch.equal(torch.isnan(y).cpu(), torch.isnan(yr)) and bool(torch.isnan(y).any())
+    assert torch.equal(torch.nan_to_num(y.float().cpu()), torch.nan_to_num(yr.detach()))
+    assert torch.equal(x.grad.float().cpu(), xr.grad)
+
+
+@pytest.mark.gpu
 def test_full_size_properties():
     """Model-size checks without the oracle: the Q-ResNet-34 stem pool (k3 s2 p1 on 112^2) and QSPPF's k5 s1 p2."""
     from quan_ultralytics_b200 import functional as QF
