@@ -27,7 +27,17 @@ struct PoolGeom {
   int64_t outer;
   int H, W, Ho, Wo, inner_vecs;
   int kH, kW, sH, sW, pH, pW;
+  int iv_shift;   // log2(inner_vecs) when it is a power of two, else -1
+  int rb;         // row kernels: consecutive rows per block
 };
+
+// row kernels: one block per (outer, row) — the row / image split is block-uniform scalar work, a thread only splits its
+// element index into (pixel, vector) and divides by the stride.  The flat kernels spend ~7 integer divisions per thread.
+__device__ __forceinline__ void split_iv(int e, const PoolGeom& g, int& pix, int& iv) {
+  if (g.iv_shift >= 0) { pix = e >> g.iv_shift; iv = e & (g.inner_vecs - 1); }
+  else { pix = e / g.inner_vecs; iv = e - pix * g.inner_vecs; }
+}
+__device__ __forceinline__ int div_stride(int a, int s) { return s == 1 ? a : s == 2 ? a >> 1 : a / s; }   // a >= 0
 
 // I = int (tensors below 2^31 vectors: 32-bit index arithmetic) or int64_t.  Loads go out in batches of POOL_CH before
 // anything is compared: the first version walked the window with one dependent load per tap (9 serial latencies for the
@@ -216,6 +226,138 @@ __global__ void __launch_bounds__(256) qmaxpool_bwd_kernel(const T* __restrict__
   }
 }
 
+template <int V, bool WITH_IDX>
+__global__ void __launch_bounds__(256) qmaxpool_fwd_bf16_rows_kernel(const __nv_bfloat16* __restrict__ x,
+                                                                     __nv_bfloat16* __restrict__ y, uint8_t* __restrict__ idx,
+                                                                     PoolGeom g) {
+  constexpr int NP = V / 2;
+  using T = __nv_bfloat16;
+  const int taps = g.kH * g.kW;
+  const int rowlen = g.Wo * g.inner_vecs;
+  const __nv_bfloat162 ninf = __float2bfloat162_rn(-INFINITY);
+  const int64_t nrows = g.outer * g.Ho;
+  // g.rb consecutive output rows per block: consecutive windows share kH - sH input rows through L1
+  for (int64_t row = (int64_t)blockIdx.x * g.rb; row < nrows && row < ((int64_t)blockIdx.x + 1) * g.rb; ++row) {
+  const int ho = (int)(row % g.Ho);               // row = o * Ho + ho
+  const int64_t o = row / g.Ho;
+  const int h0 = ho * g.sH - g.pH;
+  const T* img = x + (int64_t)o * g.H * g.W * g.inner_vecs * V;
+  for (int e = threadIdx.x; e < rowlen; e += blockDim.x) {
+    int wo, iv;
+    split_iv(e, g, wo, iv);
+    const int w0 = wo * g.sW - g.pW;
+    const uint32_t t_first = (uint32_t)((h0 < 0 ? -h0 : 0) * g.kW + (w0 < 0 ? -w0 : 0));
+    __nv_bfloat162 best[NP];
+    uint32_t arg[NP];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) { best[p] = ninf; arg[p] = t_first * 0x00010001u; }
+    const T* base = img + (int64_t)iv * V;
+    int kh = 0, kw = 0;
+    for (int t0 = 0; t0 < taps; t0 += POOL_CH) {
+      Vec<T, V> raw[POOL_CH];
+      bool ok[POOL_CH];
+#pragma unroll
+      for (int j = 0; j < POOL_CH; ++j) {
+        const int hi = h0 + kh, wi = w0 + kw;
+        ok[j] = (t0 + j < taps) && hi >= 0 && hi < g.H && wi >= 0 && wi < g.W;
+        if (ok[j]) raw[j] = *reinterpret_cast<const Vec<T, V>*>(base + ((int64_t)hi * g.W + wi) * g.inner_vecs * V);
+        if (++kw == g.kW) { kw = 0; ++kh; }
+      }
+#pragma unroll
+      for (int j = 0; j < POOL_CH; ++j) {
+        if (!ok[j]) continue;
+        const uint32_t tap2 = (uint32_t)(t0 + j) * 0x00010001u;
+        const __nv_bfloat162* xv = reinterpret_cast<const __nv_bfloat162*>(&raw[j]);
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+          const uint32_t gt = __hgt2_mask(xv[p], best[p]);
+          best[p] = __hmax2_nan(best[p], xv[p]);
+          arg[p] = (tap2 & gt) | (arg[p] & ~gt);
+        }
+      }
+    }
+    bool has_nan = false;
+#pragma unroll
+    for (int p = 0; p < NP; ++p) has_nan |= (__hneu2_mask(best[p], best[p]) != 0u);
+    Vec<uint8_t, V> a;
+#pragma unroll
+    for (int p = 0; p < NP; ++p) { a.v[2 * p] = (uint8_t)(arg[p] & 0xffu); a.v[2 * p + 1] = (uint8_t)((arg[p] >> 16) & 0xffu); }
+    if (WITH_IDX && has_nan) {
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        const float bvf = (v & 1) ? __high2float(best[v / 2]) : __low2float(best[v / 2]);
+        if (!(bvf != bvf)) continue;
+        uint8_t last = a.v[v];
+        for (int t = 0; t < taps; ++t) {
+          const int hi = h0 + t / g.kW, wi = w0 + t % g.kW;
+          if (hi < 0 || hi >= g.H || wi < 0 || wi >= g.W) continue;
+          const float xs = __bfloat162float(base[((int64_t)hi * g.W + wi) * g.inner_vecs * V + v]);
+          if (xs != xs) last = (uint8_t)t;
+        }
+        a.v[v] = last;
+      }
+    }
+    Vec<T, V> out;
+#pragma unroll
+    for (int p = 0; p < NP; ++p) { out.v[2 * p] = __low2bfloat16(best[p]); out.v[2 * p + 1] = __high2bfloat16(best[p]); }
+    const int64_t oi = (row * rowlen + e) * V;
+    *reinterpret_cast<Vec<T, V>*>(y + oi) = out;
+    if constexpr (WITH_IDX) *reinterpret_cast<Vec<uint8_t, V>*>(idx + oi) = a;
+  }
+  }
+}
+
+constexpr int POOL_RB = 8;
+
+template <typename T, int V>
+__global__ void __launch_bounds__(256) qmaxpool_bwd_rows_kernel(const T* __restrict__ dy, const uint8_t* __restrict__ idx,
+                                                                T* __restrict__ dx, PoolGeom g) {
+  // g.rb (<= POOL_RB) consecutive input rows per block: the 1 + (kH-1)/sH output rows a row needs are the next row's too, so the
+  // index / gradient vectors come from L1 instead of L2 (one row per block: 1348 us on the Q-ResNet stem pool — three
+  // blocks on three SMs each pulled the same output rows through L2)
+  const int64_t nrows = g.outer * g.H;
+  const int rowlen = g.W * g.inner_vecs;
+  for (int64_t row = (int64_t)blockIdx.x * g.rb; row < nrows && row < ((int64_t)blockIdx.x + 1) * g.rb; ++row) {
+  const int hi = (int)(row % g.H);
+  const int64_t o = row / g.H;
+  int ho_lo = hi + g.pH - g.kH + 1;
+  ho_lo = ho_lo <= 0 ? 0 : (ho_lo + g.sH - 1) / g.sH;
+  int ho_hi = (hi + g.pH) / g.sH;
+  if (ho_hi > g.Ho - 1) ho_hi = g.Ho - 1;
+  const int64_t img = (int64_t)o * g.Ho * g.Wo * g.inner_vecs * V;
+  for (int e = threadIdx.x; e < rowlen; e += blockDim.x) {
+    int wi, iv;
+    split_iv(e, g, wi, iv);
+    float acc[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) acc[v] = 0.f;
+    int wo_lo = wi + g.pW - g.kW + 1;
+    wo_lo = wo_lo <= 0 ? 0 : div_stride(wo_lo + g.sW - 1, g.sW);
+    int wo_hi = div_stride(wi + g.pW, g.sW);
+    if (wo_hi > g.Wo - 1) wo_hi = g.Wo - 1;
+    const int64_t obase = img + (int64_t)iv * V;
+    for (int ho = ho_lo; ho <= ho_hi; ++ho) {
+      const int kh = hi - (ho * g.sH - g.pH);
+      for (int wo = wo_lo; wo <= wo_hi; ++wo) {
+        const int tap = kh * g.kW + (wi - (wo * g.sW - g.pW));
+        const int64_t oe = obase + ((int64_t)ho * g.Wo + wo) * g.inner_vecs * V;
+        const Vec<uint8_t, V> a = *reinterpret_cast<const Vec<uint8_t, V>*>(idx + oe);
+        bool any = false;
+#pragma unroll
+        for (int v = 0; v < V; ++v) any |= (a.v[v] == tap);
+        if (!any) continue;
+        float gv[V];
+        load_vec<T, V>(dy + oe, gv);
+#pragma unroll
+        for (int v = 0; v < V; ++v)
+          if (a.v[v] == tap) acc[v] += gv[v];
+      }
+    }
+    store_vec<T, V>(dx + (row * rowlen + e) * V, acc);
+  }
+  }
+}
+
 static int pool_geom(const char* who, int B, int C, int H, int W, int kH, int kW, int sH, int sW, int pH, int pW, int dtype,
                      int layout, PoolGeom& g, int& V) {
   QUAN_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, QUAN_E_ARG, "%s: non-positive dims", who);
@@ -235,6 +377,10 @@ static int pool_geom(const char* who, int B, int C, int H, int W, int kH, int kW
   else { g.outer = B; inner = 4 * C; }
   V = largest_pow2_divisor(inner, dtype == QUAN_BF16 ? 8 : 4);
   g.inner_vecs = inner / V;
+  g.iv_shift = -1;
+  g.rb = 1;
+  for (int b = 0; b < 31; ++b)
+    if ((1 << b) == g.inner_vecs) g.iv_shift = b;
   return QUAN_OK;
 }
 
@@ -260,7 +406,26 @@ static int launch_pool_fwd(const void* x, void* y, uint8_t* idx, const PoolGeom&
     else qmaxpool_fwd_bf16_kernel<VV, false, int64_t><<<grid, 256, 0, st>>>(xp, yp, idx, g);                      \
   } while (0)
   static const int env_packed = [] { const char* e = getenv("QUAN_POOL_PACKED"); return e ? atoi(e) : 1; }();
+  static const int env_rows = [] { const char* e = getenv("QUAN_POOL_ROWS"); return e ? atoi(e) : 1; }();
   if constexpr (sizeof(T) == 2) {
+    if (env_packed && env_rows && g.Wo * g.inner_vecs >= 128 && g.outer * g.Ho >= 2048 && g.outer * g.Ho < (1ll << 31)) {
+      // rows per block: as many as keep >= 8 blocks per SM in the grid (small maps: the flat kernel fills the GPU better —
+      // 18.6 vs 23.0 us on the 16 x 32 ch x 32^2 QSPPF pool)
+      PoolGeom gr = g;
+      gr.rb = (int)(g.outer * g.Ho / (8 * QUAN_NUM_SMS));
+      gr.rb = gr.rb < 1 ? 1 : gr.rb > 4 ? 4 : gr.rb;
+      const PoolGeom& g = gr;
+      const unsigned rows = (unsigned)((g.outer * g.Ho + g.rb - 1) / g.rb);
+      if (V == 8) {
+        if (idx != nullptr) qmaxpool_fwd_bf16_rows_kernel<8, true><<<rows, 256, 0, st>>>(xp, yp, idx, g);
+        else qmaxpool_fwd_bf16_rows_kernel<8, false><<<rows, 256, 0, st>>>(xp, yp, idx, g);
+      } else {
+        if (idx != nullptr) qmaxpool_fwd_bf16_rows_kernel<4, true><<<rows, 256, 0, st>>>(xp, yp, idx, g);
+        else qmaxpool_fwd_bf16_rows_kernel<4, false><<<rows, 256, 0, st>>>(xp, yp, idx, g);
+      }
+      QUAN_CHECK_LAUNCH("qmaxpool_fwd");
+      return QUAN_OK;
+    }
     if (env_packed) {
       if (V == 8) QUAN_POOL_FWD_BF16(8); else QUAN_POOL_FWD_BF16(4);
       QUAN_CHECK_LAUNCH("qmaxpool_fwd");
@@ -282,6 +447,20 @@ static int launch_pool_bwd(const void* dy, const uint8_t* idx, void* dx, const P
   const int grid = grid_for(g.outer * g.H * g.W * g.inner_vecs, 256, 8);
   QUAN_TIMED(st);
   const bool small = g.outer * g.H * g.W * g.inner_vecs < (1ll << 31) - (1 << 20);   // i + grid stride stays below 2^31
+  static const int env_rows = [] { const char* e = getenv("QUAN_POOL_ROWS"); return e ? atoi(e) : 1; }();
+  if (env_rows && g.W * g.inner_vecs >= 128 && g.outer * g.H >= 2048 && g.outer * g.H < (1ll << 31)) {
+    // measured on the Q-ResNet stem pool: 8 rows per block 348 us, flat kernel 550 us, 1 row per block 1348 us; small maps
+    // (512 rows: 64 blocks of 8 rows, 132 vs 37 us) stay on the flat kernel
+    PoolGeom gr = g;
+    gr.rb = (int)(g.outer * g.H / (8 * QUAN_NUM_SMS));
+    gr.rb = gr.rb < 1 ? 1 : gr.rb > POOL_RB ? POOL_RB : gr.rb;
+    const PoolGeom& g = gr;
+    const unsigned rows = (unsigned)((g.outer * g.H + g.rb - 1) / g.rb);
+    if (V == 8) { if constexpr (sizeof(T) == 2) qmaxpool_bwd_rows_kernel<T, 8><<<rows, 256, 0, st>>>(gp, idx, dp, g); }
+    else qmaxpool_bwd_rows_kernel<T, 4><<<rows, 256, 0, st>>>(gp, idx, dp, g);
+    QUAN_CHECK_LAUNCH("qmaxpool_bwd");
+    return QUAN_OK;
+  }
   if (V == 8) {
     if constexpr (sizeof(T) == 2) {
       if (small) qmaxpool_bwd_kernel<T, 8, int><<<grid, 256, 0, st>>>(gp, idx, dp, g);

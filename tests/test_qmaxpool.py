@@ -83,7 +83,9 @@ def test_cuda_matches_golden(case, layout, dtype):
 
 # (B, C, H, W, k, s, p): ragged sizes, every vector width (4C = 4 .. 8-aligned), the model shapes scaled down
 RANDOM_CASES = [(2, 1, 9, 7, 3, 2, 1), (3, 5, 13, 11, 5, 1, 2), (2, 32, 16, 16, 5, 1, 2), (2, 16, 28, 28, 3, 2, 1),
-                (1, 6, 10, 9, 2, 2, 0), (2, 3, 7, 8, (3, 2), (2, 1), (1, 0))]
+                (1, 6, 10, 9, 2, 2, 0), (2, 3, 7, 8, (3, 2), (2, 1), (1, 0)),
+                # >= 2048 rows of >= 128 vectors in BHWQC: the row-tiled kernels (several rows per block), images change mid-block
+                (80, 16, 56, 40, 3, 2, 1), (70, 8, 31, 33, 5, 1, 2)]
 
 
 @pytest.mark.gpu
