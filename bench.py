@@ -194,6 +194,62 @@ def time_op(fn, iters, flush=None):
     return tot / iters
 
 
+def reference_cuda_ext(a, dev):
+    """The reference's OWN CUDA extension (ultralytics/nn/cuda/quaternion_ops.cu, built by oracle/build_ref_ext.py into
+    oracle/_ref/) on a bounded sample of the bench layer, next to our drop-in for the same module API
+    (quan_ultralytics_b200/quaternion_ops.py): qconv_forward + qconv_backward of ONE QConv2D (C_q, 3x3, stride 1) in fp32,
+    contiguous BCHWQ tensors, mixing matrix M_B (what the extension computes).  A reported baseline; None when
+    the prebuilt .so is absent.  Its kernels are scalar (one block per weight element in wgrad), hence the small sample."""
+    try:
+        from oracle import build_ref_ext
+        ref = build_ref_ext.load()
+    except Exception as e:                                    # noqa: BLE001 — a baseline must never break the bench line
+        return {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+    if ref is None:
+        return None
+    from quan_ultralytics_b200 import quaternion_ops as ours
+    ours.set_mixing("B")
+    n, C, H = 2, a.cq, a.hw
+    torch.manual_seed(0)
+    x = torch.randn(n, C, H, H, 4, device=dev)
+    w = [torch.randn(C, C, 3, 3, device=dev) * 0.02 for _ in range(4)]
+    dy = torch.randn(n, C, H, H, 4, device=dev)
+    args = ([1, 1], [1, 1], [1, 1], 1)
+
+    def run(mod):
+        y = mod.qconv_forward(x, *w, None, None, None, None, *args)
+        g = mod.qconv_backward(dy, x, *w, False, *args)
+        return y, g
+
+    try:
+        y_ref, g_ref = run(ref)
+        y_our, g_our = run(ours)
+        rel = lambda p, q: float((p.double() - q.double()).abs().max() / q.double().abs().max())
+        t_ref = time_op(lambda: run(ref), 2)
+        t_our = time_op(lambda: run(ours), 10)
+        # the same layer the way the nn.Module path runs it: tensor-core layout (BHWQC), fp32 storage / tf32 MMA
+        from quan_ultralytics_b200 import ops as qops
+        xn, dyn = (t.contiguous(memory_format=torch.channels_last_3d) for t in (x, dy))
+        cargs = ((1, 1), (1, 1), (1, 1), 1, qops.M_B)
+
+        def run_native():
+            qops.qconv2d_fwd(xn, w, None, *cargs, qops.ALGO_AUTO, qops.LAYOUT_BHWQC)
+            qops.qconv2d_bwd(dyn, xn, w, *cargs, True, True, False)
+
+        t_nat = time_op(run_native, 10)
+        return {"op": f"QConv2D fwd+bwd (qconv_forward + qconv_backward), Cq={C} 3x3 s1 {H}x{H}, fp32, M_B", "images": n,
+                "reference_ms": t_ref, "reference_images_per_sec": n / t_ref * 1e3,
+                "ours_dropin_ms": t_our, "ours_dropin_images_per_sec": n / t_our * 1e3,
+                "ours_native_ms": t_nat, "ours_native_images_per_sec": n / t_nat * 1e3,
+                "max_rel_diff_dropin_vs_reference": {"y": rel(y_our, y_ref), "dx": rel(g_our[0], g_ref[0]),
+                                                     "dw_r": rel(g_our[1], g_ref[1])},
+                "note": "reference = the reference's own quaternion_ops.cu built for sm_100; dropin = our quaternion_ops shim, same "
+                        "contiguous-BCHWQ fp32 contract (CUDA-core engine, true fp32); native = the nn.Module path's BHWQC layout on "
+                        "the tcgen05 engine (tf32 MMA), host launch time included at this 2-image sample"}
+    except Exception as e:                                    # noqa: BLE001
+        return {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+
+
 def kernels_in_step(lib, step_fn, steps, a, dtype, peaks):
     """Device time of every library kernel inside the training step itself: the library brackets each launch with a
     CUDA-event pair on its own stream (quan_kernel_timing_*), over `steps` extra steps run right after the timed region
@@ -629,6 +685,10 @@ def main():
             line["kernels_in_step"] = ks
             # (2) each op of one block timed ALONE (L2 swept between launches), against the burst peak
             line["ops_isolated"] = kernel_table(a, dev, dtype, peaks)
+        if world == 1:
+            ext = reference_cuda_ext(a, dev)
+            if ext is not None:
+                line["reference_cuda_ext"] = ext
         if world == 1 and not a.no_cpu_baseline:
             ips, sec, cores = run_cpu_port(a, a.cpu_n, a.cpu_steps, 1)
             line["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
