@@ -244,7 +244,8 @@ def reference_cuda_ext(a, dev):
                 "max_rel_diff_dropin_vs_reference": {"y": rel(y_our, y_ref), "dx": rel(g_our[0], g_ref[0]),
                                                      "dw_r": rel(g_our[1], g_ref[1])},
                 "note": "reference = the reference's own quaternion_ops.cu built for sm_100; dropin = our quaternion_ops shim, same "
-                        "contiguous-BCHWQ fp32 contract (CUDA-core engine, true fp32); native = the nn.Module path's BHWQC layout on "
+                        "contiguous-BCHWQ fp32 contract (large layers: layout conversion in and out around the tcgen05 engine, tf32 "
+                        "MMA; set_fast_layout(False) = exact-fp32 CUDA-core engine, 5.3 ms here); native = the nn.Module path's BHWQC layout on "
                         "the tcgen05 engine (tf32 MMA), host launch time included at this 2-image sample"}
     except Exception as e:                                    # noqa: BLE001
         return {"unavailable": f"{type(e).__name__}: {e}"[:200]}

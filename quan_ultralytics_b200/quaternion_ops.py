@@ -16,7 +16,7 @@ from typing import List, Optional, Sequence
 import torch
 
 from . import ops
-from ._lib import ACT_NONE, ALGO_AUTO, LAYOUT_BCHWQ
+from ._lib import ACT_NONE, ALGO_AUTO, ALGO_TCGEN05, LAYOUT_BCHWQ, LAYOUT_BHWQC
 
 _mix = {"name": "B"}
 
@@ -29,6 +29,24 @@ def set_mixing(name: str) -> None:
 
 def get_mixing() -> str:
     return _mix["name"]
+
+
+# The extension's contract is contiguous BCHWQ in and out.  Large layers are still worth two layout conversions: the
+# tensor-core engine (BHWQC, tf32 MMA for fp32 tensors: within BASELINE.json's 1e-3) does the bench layer in 0.23 ms where
+# the CUDA-core engine that works on BCHWQ directly needs 5.3 ms (the reference's own kernels: 14.7 ms).  Small tensors
+# and shapes the tensor-core engine does not take stay on the exact-fp32 CUDA-core path.
+_fast = {"on": True, "min_numel": 1 << 18}
+
+
+def set_fast_layout(on: bool, min_numel: int = 1 << 18) -> None:
+    _fast["on"], _fast["min_numel"] = bool(on), int(min_numel)
+
+
+def _tensor_core_ok(x: torch.Tensor, w: torch.Tensor, stride, padding, dilation, groups, passes) -> bool:
+    if not _fast["on"] or x.numel() < _fast["min_numel"] or x.dtype not in (torch.float32, torch.bfloat16):
+        return False
+    return all(ops.qconv2d_pick_algo(x.shape, w.shape, tuple(stride), tuple(padding), tuple(dilation), int(groups), x.dtype,
+                                     LAYOUT_BHWQC, ps) == ALGO_TCGEN05 for ps in passes)
 
 
 def _check_cuda(name: str, t: torch.Tensor) -> None:
@@ -47,7 +65,12 @@ def qconv_forward(input: torch.Tensor, weight_r, weight_i, weight_j, weight_k, b
         raise RuntimeError("If bias_r is None, bias_i, bias_j, and bias_k must also be None.")
     if bias_r is not None:
         _check_cuda("bias_r", bias_r)
-    y = ops.qconv2d_fwd(input.contiguous(), (weight_r, weight_i, weight_j, weight_k), bias_r, tuple(stride),
+    x = input.contiguous()
+    if _tensor_core_ok(x, weight_r, stride, padding, dilation, groups, (0,)):
+        y = ops.qconv2d_fwd(ops.convert_layout(x, LAYOUT_BHWQC), (weight_r, weight_i, weight_j, weight_k), bias_r, tuple(stride),
+                            tuple(padding), tuple(dilation), int(groups), ops.MIX[_mix["name"]], ALGO_AUTO, LAYOUT_BHWQC)
+        return ops.convert_layout(y, LAYOUT_BCHWQ)
+    y = ops.qconv2d_fwd(x, (weight_r, weight_i, weight_j, weight_k), bias_r, tuple(stride),
                         tuple(padding), tuple(dilation), int(groups), ops.MIX[_mix["name"]], ALGO_AUTO, LAYOUT_BCHWQ)
     return y
 
@@ -62,8 +85,13 @@ def qconv_backward(grad_output: torch.Tensor, input: torch.Tensor, weight_r, wei
     dy = grad_output.contiguous()
     if dy.dtype != x.dtype:
         dy = dy.to(x.dtype)
+    fast = _tensor_core_ok(x, weight_r, stride, padding, dilation, groups, (1, 2))
+    if fast:
+        x, dy = ops.convert_layout(x, LAYOUT_BHWQC), ops.convert_layout(dy, LAYOUT_BHWQC)
     dx, dws, db = ops.qconv2d_bwd(dy, x, (weight_r, weight_i, weight_j, weight_k), tuple(stride), tuple(padding),
                                   tuple(dilation), int(groups), ops.MIX[_mix["name"]], True, True, bool(bias_defined))
+    if fast:
+        dx = ops.convert_layout(dx, LAYOUT_BCHWQ)
     dws = [g.to(w.dtype) for g, w in zip(dws, (weight_r, weight_i, weight_j, weight_k))]
     if db is not None:
         db = db.to(weight_r.dtype)

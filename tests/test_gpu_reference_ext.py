@@ -50,6 +50,33 @@ def test_qconv_forward_backward_match_the_reference_extension(ref, case):
         assert a.shape == r.shape and rel(a, r) <= 2e-5
 
 
+def test_large_layers_take_the_tensor_core_path_within_the_tf32_budget(ref):
+    """>= 2^18 elements and a tensor-core shape: the shim converts BCHWQ -> BHWQC, runs the tcgen05 engine (tf32 MMA on fp32
+    tensors) and converts back — same contract, BASELINE.json's 1e-3 instead of exact fp32."""
+    from quan_ultralytics_b200 import ops
+    from quan_ultralytics_b200 import quaternion_ops as ours
+    ours.set_mixing("B")
+    torch.manual_seed(23)
+    x = torch.randn(4, 64, 32, 32, 4, device=DEV)
+    w = [torch.randn(64, 64, 3, 3, device=DEV) / 24.0 for _ in range(4)]
+    args = ([1, 1], [1, 1], [1, 1], 1)
+    assert ours._tensor_core_ok(x, w[0], *args, (0, 1, 2))
+    y_ref = ref.qconv_forward(x, *w, None, None, None, None, *args)
+    y = ours.qconv_forward(x, *w, None, None, None, None, *args)
+    assert y.is_contiguous() and ops.layout_of(y) == ops.LAYOUT_BCHWQ and 1e-6 < rel(y, y_ref) <= 1e-3
+    dy = torch.randn_like(y_ref)
+    g_ref = ref.qconv_backward(dy, x, *w, False, *args)
+    g_our = ours.qconv_backward(dy, x, *w, False, *args)
+    assert g_our[0].is_contiguous()
+    for a, r in zip(g_our[:5], g_ref[:5]):
+        assert a.shape == r.shape and rel(a, r) <= 1e-3
+    ours.set_fast_layout(False)
+    try:
+        assert rel(ours.qconv_forward(x, *w, None, None, None, None, *args), y_ref) <= 1e-5      # exact-fp32 path on request
+    finally:
+        ours.set_fast_layout(True)
+
+
 def test_iqbn_forward_matches_the_reference_extension(ref):
     from quan_ultralytics_b200 import quaternion_ops as ours
     torch.manual_seed(3)
