@@ -52,3 +52,21 @@ def test_argument_errors_use_the_c_convention():
         _lib.check(-2, "quan_qconv2d_fwd")
     assert lib.quan_iqbn_workspace_bytes(16) == 592 * 8 * 16 * 8      # 4 x 148 row-split partials of [8C] fp64
     assert lib.quan_qconv2d_pick_algo(ctypes.byref(_lib.ConvDims(1, 4, 4, 8, 8, 3, 3, 1, 1, 1, 1, 1, 1, 1)), 1, 0, 0) == 1
+
+
+def test_engine_selection_is_host_logic():
+    """quan_qconv2d_pick_algo needs no GPU: the small-channel engine takes the stems, including the Q-ResNet-34 7x7 stem
+    (1 -> 16) in chunks of 8 output channels for forward and wgrad; its dgrad (never needed: the input is the image) and
+    everything the special engines refuse stay on the generic CUDA-core engine."""
+    from quan_ultralytics_b200 import _lib
+    lib = _lib.load()
+    pick = lambda dims, ps: lib.quan_qconv2d_pick_algo(ctypes.byref(_lib.ConvDims(*dims)), 1, 1, ps)   # bf16, BHWQC
+    stem34 = (256, 1, 16, 224, 224, 7, 7, 2, 2, 3, 3, 1, 1, 1)
+    assert [pick(stem34, ps) for ps in range(3)] == [4, 1, 4]
+    yolo_stem = (16, 1, 4, 1024, 1024, 3, 3, 2, 2, 1, 1, 1, 1, 1)
+    assert [pick(yolo_stem, ps) for ps in range(3)] == [4, 4, 4]
+    dw = (16, 32, 32, 64, 64, 3, 3, 1, 1, 1, 1, 1, 1, 32)
+    assert [pick(dw, ps) for ps in range(3)] == [3, 3, 3]
+    odd = (2, 3, 5, 16, 16, 3, 3, 1, 1, 1, 1, 1, 1, 1)
+    assert [pick(odd, ps) for ps in range(3)] == [1, 1, 1]
+
