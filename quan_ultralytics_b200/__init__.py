@@ -11,6 +11,6 @@ from ._lib import (ACT_NONE, ACT_SILU, ALGO_AUTO, ALGO_DEPTHWISE, ALGO_DIRECT, A
                    LAYOUT_BHWQC)
 from .functional import (conv_iqbn_act, iqbn, internal_layout, poincare_map, qconv2d, qmaxpool, qupsample_nearest,  # noqa: F401
                          set_epilogue_stats, set_internal_layout)
-from .modules import IQBN, Conv, DWConv, QConv2D, QConv2D_B, QuaternionMaxPool, QUpsample, autopad  # noqa: F401
+from .modules import IQBN, QER, Conv, DWConv, QConv2D, QConv2D_B, QuaternionMaxPool, QUpsample, autopad  # noqa: F401
 
 __version__ = "0.1.0"

@@ -16,7 +16,7 @@ import types
 from . import modules as M
 from . import quaternion_ops as shim
 
-_SWAP = ("QConv2D", "IQBN", "Conv", "DWConv", "QUpsample", "QuaternionMaxPool")
+_SWAP = ("QConv2D", "IQBN", "Conv", "DWConv", "QUpsample", "QuaternionMaxPool", "QER")
 
 
 def install_extension_shim(mixing: str = "A") -> types.ModuleType:

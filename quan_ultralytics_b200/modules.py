@@ -220,6 +220,31 @@ class QuaternionMaxPool(nn.Module):
         return f"kernel_size={self.kernel_size}, stride={self.stride}, padding={self.padding}"
 
 
+class QER(nn.Module):
+    """Quaternion -> real extraction of the detection heads (ultralytics/nn/modules/head.py:26-47): a real `nn.Conv2d` over
+    the 4C flattened quaternion channels (channel index c*4 + q).  The reference first materialises
+    `x.permute(0, 1, 4, 2, 3).contiguous()`; in the tensor-core layout (BHWQC) the activation already IS a channels-last
+    real tensor with channel index q*C + c, so the copy disappears: the (tiny) weight is re-ordered instead and the GEMM is
+    the library's (cuDNN / cuBLAS 1x1 convolution — plain library GEMM, no kernel of ours).  Same constructor, parameters
+    and state-dict keys (`output_proj.weight`, `output_proj.bias`, `bias`) as the reference; output is the same logical
+    [B, out, H, W] tensor (channels-last memory when the input was BHWQC).  SURVEY §8(f) rank 2, host side only."""
+
+    def __init__(self, in_channels, out_channels=None, kernel_size=None):
+        super().__init__()
+        self.output_proj = nn.Conv2d(in_channels, out_channels, kernel_size=kernel_size)
+        self.bias = self.output_proj.bias
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        B, C, H, W, Q = x.shape
+        conv = self.output_proj
+        if C > 1 and x.is_contiguous(memory_format=torch.channels_last_3d):
+            xr = x.permute(0, 4, 1, 2, 3).reshape(B, Q * C, H, W)            # a view: memory is [B][H][W][q*C + c]
+            w = conv.weight
+            w = w.view(w.size(0), C, Q, w.size(2), w.size(3)).transpose(1, 2).reshape(w.size(0), Q * C, w.size(2), w.size(3))
+            return torch.nn.functional.conv2d(xr, w, conv.bias, conv.stride, conv.padding, conv.dilation, conv.groups)
+        return conv(x.permute(0, 1, 4, 2, 3).contiguous().view(B, C * Q, H, W))  # BCHWQ input: the reference's own path
+
+
 class Conv(nn.Module):
     """QConv2D -> IQBN -> SiLU (conv.py:788-813); IQBN-apply and SiLU run as one fused kernel."""
 

@@ -388,3 +388,25 @@ def test_qwrn_trace_iqbn_layers(qwrn, tag):
     y.backward(to_dev(g("dy")))
     assert rel_err(x.grad, g("dx")) <= 1e-3
     assert rel_err(bn.gamma.grad, g("dgamma")) <= 1e-3 and rel_err(bn.beta.grad, g("dbeta")) <= 1e-3
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_qer_on_the_tensor_core_layout(dtype):
+    """QER (head.py:26-47) on a BHWQC activation: a view + re-ordered weight + the library's 1x1 conv, against the
+    reference's permute + contiguous + conv formulation on the same device."""
+    torch.manual_seed(2)
+    B, C, H, W, O = 4, 16, 32, 32, 64
+    m = Q.QER(4 * C, O, 1).to(DEV, dtype)
+    x = torch.randn(B, C, H, W, 4, device=DEV).to(dtype).contiguous(memory_format=torch.channels_last_3d).requires_grad_(True)
+    y = m(x)
+    ref_in = x.detach().clone().requires_grad_(True)
+    ref = m.output_proj(ref_in.permute(0, 1, 4, 2, 3).contiguous().view(B, 4 * C, H, W))
+    tol = 1e-4 if dtype == torch.float32 else TOL_BF16
+    assert y.shape == ref.shape == (B, O, H, W) and rel_err(y, ref.detach().double().cpu().numpy()) <= tol
+    dy = torch.randn_like(ref)
+    y.backward(dy)
+    gw = m.output_proj.weight.grad.clone()
+    m.zero_grad(set_to_none=True)
+    ref.backward(dy)
+    assert rel_err(x.grad, ref_in.grad.double().cpu().numpy()) <= tol
+    assert rel_err(gw, m.output_proj.weight.grad.double().cpu().numpy()) <= tol

@@ -90,3 +90,32 @@ def test_unsupported_options_fail_loudly():
         Q.QUpsample(2, "bilinear")
     with pytest.raises(NotImplementedError):
         Q.QConv2D(16, 16, 3, padding_mode="reflect")
+
+
+def test_qer_reads_the_tensor_core_layout_without_a_copy():
+    """QER (head.py:26-47): in BHWQC the activation is already a channels-last real tensor; only the weight is re-ordered.
+    Pure torch ops, so it is checked on CPU against the reference's formulation (permute + contiguous + view + conv)."""
+    import quan_ultralytics_b200 as Q
+    torch.manual_seed(0)
+    B, C, H, W, O = 2, 6, 5, 7, 9
+    m = Q.QER(4 * C, O, 1).double()
+    assert set(m.state_dict()) == {"bias", "output_proj.weight", "output_proj.bias"}
+    x = torch.randn(B, C, H, W, 4, dtype=torch.float64)
+    ref_in = x.clone().requires_grad_(True)
+    ref = m.output_proj(ref_in.permute(0, 1, 4, 2, 3).contiguous().view(B, C * 4, H, W))
+    dy = torch.randn_like(ref)
+    ref.backward(dy)
+    gw, gb = m.output_proj.weight.grad.clone(), m.output_proj.bias.grad.clone()
+    for fmt in (torch.channels_last_3d, torch.contiguous_format):
+        m.zero_grad(set_to_none=True)
+        xi = x.clone().contiguous(memory_format=fmt).requires_grad_(True)
+        if fmt == torch.channels_last_3d:          # the fast branch really is a view of the activation
+            v = xi.detach().permute(0, 4, 1, 2, 3).reshape(B, 4 * C, H, W)
+            assert v.data_ptr() == xi.data_ptr() and v.is_contiguous(memory_format=torch.channels_last)
+        y = m(xi)
+        assert y.shape == (B, O, H, W)
+        torch.testing.assert_close(y, ref, rtol=1e-12, atol=1e-12)
+        y.backward(dy)
+        torch.testing.assert_close(xi.grad, ref_in.grad, rtol=1e-12, atol=1e-12)
+        torch.testing.assert_close(m.output_proj.weight.grad, gw, rtol=1e-12, atol=1e-12)
+        torch.testing.assert_close(m.output_proj.bias.grad, gb, rtol=1e-12, atol=1e-12)

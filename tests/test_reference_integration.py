@@ -80,8 +80,10 @@ def test_class_swap_builds_reference_graphs_with_b200_modules(reference):
     import ultralytics.nn.modules.block as ublock
     import models.blocks.quaternion_blocks as cblocks
     import models.quaternion_models as cmodels
-    saved = {(m, n): getattr(m, n) for m in (uconv, tasks, ublock, cblocks, cmodels)
-             for n in ("QConv2D", "IQBN", "Conv", "DWConv", "QUpsample", "QuaternionMaxPool") if hasattr(m, n)}
+    import ultralytics.nn.modules as umods
+    import ultralytics.nn.modules.head as uhead
+    saved = {(m, n): getattr(m, n) for m in (uconv, tasks, ublock, cblocks, cmodels, umods, uhead)
+             for n in ("QConv2D", "IQBN", "Conv", "DWConv", "QUpsample", "QuaternionMaxPool", "QER") if hasattr(m, n)}
     saved_c = (cconv.QConv2D, cconv.IQBN)
     try:
         cfg = yaml.safe_load((REF / "ultralytics/cfg/models/11/yolo11-obb-quan.yaml").read_text())
@@ -101,6 +103,7 @@ def test_class_swap_builds_reference_graphs_with_b200_modules(reference):
         # QSPPF (block.py:270-302) pools with the B200 QuaternionMaxPool; so does the Q-ResNet-34 stem
         assert sum(isinstance(m, Q.QuaternionMaxPool) for m in our_model.modules()) >= 1
         assert isinstance(cmodels.create_qrn34_imagenet(10).maxpool, Q.QuaternionMaxPool)
+        assert sum(isinstance(m, Q.QER) for m in our_model.modules()) == 9        # 3 scales x (box, cls, angle) extractions
         our_model.load_state_dict(ref_model.state_dict())
         assert cconv.QConv2D is Q.QConv2D_B and cconv.IQBN is Q.IQBN
     finally:
@@ -126,3 +129,30 @@ def test_extension_shim_is_importable_as_quaternion_ops(reference):
         sys.modules.pop("quaternion_ops", None)
         if old is not None:
             sys.modules["quaternion_ops"] = old
+
+
+def test_qer_matches_the_reference_head_module(reference):
+    """ultralytics/nn/modules/head.py:26-47 QER against ours: same state dict, same outputs and gradients for the
+    reference's BCHWQ input and for the tensor-core layout (where ours skips the permute copy)."""
+    import quan_ultralytics_b200 as Q
+    import ultralytics.nn.modules.head as uhead
+    torch.manual_seed(4)
+    assert uhead.QER is not Q.QER and uhead.QER.__module__ == "ultralytics.nn.modules.head"
+    r = uhead.QER(64, 15, 1).double()
+    o = Q.QER(64, 15, 1).double()
+    assert _keys(r) == _keys(o)
+    o.load_state_dict(r.state_dict())
+    x = torch.randn(2, 16, 6, 5, 4, dtype=torch.float64)
+    xr = x.clone().requires_grad_(True)
+    yr = r(xr)
+    dy = torch.randn_like(yr)
+    yr.backward(dy)
+    for fmt in (torch.contiguous_format, torch.channels_last_3d):
+        o.zero_grad(set_to_none=True)
+        xo = x.clone().contiguous(memory_format=fmt).requires_grad_(True)
+        yo = o(xo)
+        yo.backward(dy)
+        torch.testing.assert_close(yo, yr, rtol=1e-12, atol=1e-12)
+        torch.testing.assert_close(xo.grad, xr.grad, rtol=1e-12, atol=1e-12)
+        torch.testing.assert_close(o.output_proj.weight.grad, r.output_proj.weight.grad, rtol=1e-12, atol=1e-12)
+
