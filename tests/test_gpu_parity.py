@@ -401,7 +401,8 @@ def test_qer_on_the_tensor_core_layout(dtype):
     y = m(x)
     ref_in = x.detach().clone().requires_grad_(True)
     ref = m.output_proj(ref_in.permute(0, 1, 4, 2, 3).contiguous().view(B, 4 * C, H, W))
-    tol = 1e-4 if dtype == torch.float32 else TOL_BF16
+    # both sides are library convolutions (cuDNN: tf32 for fp32 tensors by default), only the operand order differs
+    tol = 3e-3 if dtype == torch.float32 else TOL_BF16
     assert y.shape == ref.shape == (B, O, H, W) and rel_err(y, ref.detach().double().cpu().numpy()) <= tol
     dy = torch.randn_like(ref)
     y.backward(dy)
