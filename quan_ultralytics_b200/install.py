@@ -17,6 +17,7 @@ from . import modules as M
 from . import quaternion_ops as shim
 
 _SWAP = ("QConv2D", "IQBN", "Conv", "DWConv", "QUpsample", "QuaternionMaxPool", "QER")
+_originals = []          # (module, attribute, reference class) of every swap, for uninstall()
 
 
 def install_extension_shim(mixing: str = "A") -> types.ModuleType:
@@ -24,6 +25,20 @@ def install_extension_shim(mixing: str = "A") -> types.ModuleType:
     shim.set_mixing(mixing)
     sys.modules["quaternion_ops"] = shim
     return shim
+
+
+def _swap(mod, name, new) -> None:
+    old = getattr(mod, name)
+    if old is not new:
+        _originals.append((mod, name, old))
+        setattr(mod, name, new)
+
+
+def uninstall() -> None:
+    """Put the reference's own classes back (tests build the swapped and the unswapped graph in one process)."""
+    while _originals:
+        mod, name, old = _originals.pop()
+        setattr(mod, name, old)
 
 
 def install(ultralytics: bool = True, classification: bool = True) -> dict:
@@ -39,7 +54,7 @@ def install(ultralytics: bool = True, classification: bool = True) -> dict:
                 continue
             names = [n for n in _SWAP if hasattr(mod, n)]
             for n in names:
-                setattr(mod, n, getattr(M, n))
+                _swap(mod, n, getattr(M, n))
             done[modname] = names
     if classification:
         for modname in ("quaternion.qconv", "quaternion", "models.quaternion_blocks", "models.quaternion_models",
@@ -50,13 +65,13 @@ def install(ultralytics: bool = True, classification: bool = True) -> dict:
                 continue
             names = []
             if hasattr(mod, "QConv2D"):
-                mod.QConv2D = M.QConv2D_B      # classification/quaternion/qconv.py:606-609 mixes with M_B
+                _swap(mod, "QConv2D", M.QConv2D_B)      # classification/quaternion/qconv.py:606-609 mixes with M_B
                 names.append("QConv2D")
             if hasattr(mod, "IQBN"):
-                mod.IQBN = M.IQBN
+                _swap(mod, "IQBN", M.IQBN)
                 names.append("IQBN")
             if hasattr(mod, "QuaternionMaxPool"):        # models/blocks/quaternion_blocks.py:236-260 (Q-ResNet stems)
-                mod.QuaternionMaxPool = M.QuaternionMaxPool
+                _swap(mod, "QuaternionMaxPool", M.QuaternionMaxPool)
                 names.append("QuaternionMaxPool")
             done[modname] = names
     return done

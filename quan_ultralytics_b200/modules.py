@@ -262,7 +262,7 @@ class Conv(nn.Module):
         fused_act = ACT_SILU if isinstance(self.act, nn.SiLU) else ACT_NONE if isinstance(self.act, nn.Identity) else None
         c, bn = self.conv, self.bn
         if (self.fuse_block and fused_act is not None and bn.training and not bn.sync and c.bias_r is None
-                and not c.is_first_layer and x.dim() == 5 and x.is_cuda):
+                and not c.is_first_layer and x.dim() == 5 and ops.on_device(x)):
             # conv -> IQBN -> act as one autograd node: the IQBN backward hands G = M^T dY straight to the conv backward
             with torch.no_grad():
                 bn.num_batches_tracked += 1
@@ -270,7 +270,7 @@ class Conv(nn.Module):
                                     bn.running_var, c.stride, c.padding, c.dilation, c.groups, ops.MIX[c.mix], c.algo,
                                     bn.eps, bn.momentum, fused_act)
         if (self.fuse_block and fused_act is not None and not bn.training and c.bias_r is None and not c.is_first_layer
-                and x.dim() == 5 and x.is_cuda and not torch.is_grad_enabled()):
+                and x.dim() == 5 and ops.on_device(x) and not torch.is_grad_enabled()):
             # inference (eval mode under no_grad): one C call; on the tensor-core engine IQBN(running stats) + act run in the
             # conv epilogue.  With autograd enabled the separate nodes below keep every gradient path.
             xl, layout = ops.as_layout(x, QF.internal_layout())

@@ -58,6 +58,11 @@ def _require_cuda(*ts: Optional[torch.Tensor]) -> None:
             raise RuntimeError("quan ops need CUDA tensors: there is no CPU fallback (oracle/ is test infrastructure only)")
 
 
+def on_device(x: torch.Tensor) -> bool:
+    """True when `x` lives where the library computes (a CUDA device)."""
+    return x.is_cuda
+
+
 def layout_of(x: torch.Tensor) -> Optional[int]:
     """Physical layout code of a logical [B,C,H,W,4] tensor, or None if it is neither supported layout."""
     if x.dim() != 5 or x.size(4) != 4:

