@@ -237,6 +237,31 @@ int quan_conv_block_eval_fwd(const void* x, const float* const w[4], const float
                              const quan_conv_dims* d, int dtype, int layout, const float* mix, int algo, float eps, int act,
                              void* conv_ws, size_t conv_ws_bytes, void* stream);
 
+/* ---- optimizer step -------------------------------------------------------------------------------
+ * Replaces `BaseTrainer.optimizer_step` ultralytics/engine/trainer.py:586-594 — torch.nn.utils.clip_grad_norm_(max_norm) followed by
+ * torch.optim.SGD(momentum, nesterov, per-group lr / weight_decay).step() and zero_grad(), built by trainer.py:766-806 — and
+ * classification/utils/training.py:78-79, for ALL parameter tensors in two launches.  The caller describes the tensors with a device
+ * table of chunks (<= 8192 consecutive fp32 elements of one tensor each; one thread block per chunk):
+ *   p / g     device pointers to the chunk's parameters and gradients (fp32, dense)
+ *   buf_off   element offset of the chunk in the caller-owned momentum buffer (zero-initialised: the first step then equals torch's)
+ *   group     index of the parameter group (selects lr / weight_decay)
+ * hyper (DEVICE, fp32): [lr_0, wd_0, ..., lr_{G-1}, wd_{G-1}, momentum, max_norm (<= 0: no clipping), nesterov (0/1), dampening] —
+ * device-resident so that a captured CUDA graph follows schedules.  partial: [nchunks] doubles of scratch.  total_norm_out (device,
+ * may be NULL) receives the pre-clip global gradient norm (what clip_grad_norm_ returns).  zero_grad != 0 clears the gradients
+ * (optimizer.zero_grad()); otherwise they are left scaled by the clip coefficient, as clip_grad_norm_ leaves them. */
+typedef struct quan_opt_chunk {
+  void* p;
+  void* g;
+  int64_t buf_off;
+  int32_t n;
+  int32_t group;
+} quan_opt_chunk;
+int quan_sgd_clip_step(const void* chunk_table, int nchunks, float* momentum_buf, const float* hyper, int ngroups, double* partial,
+                       float* total_norm_out, int zero_grad, void* stream);
+/* ModelEMA.update ultralytics/utils/torch_utils.py:514-525: ema = d * ema + (1 - d) * value over every chunk (p = the live value,
+ * buf_off = offset in ema_buf; g / group unused); decay: one DEVICE float (the reference ramps it with the update count). */
+int quan_ema_update(const void* chunk_table, int nchunks, float* ema_buf, const float* decay, void* stream);
+
 /* Optional per-kernel device timing for benchmarks (no reference counterpart): while enabled, every kernel the library
  * launches outside stream capture is bracketed by a CUDA-event pair on its own stream.  `enable(1)` clears earlier
  * records.  `report` synchronises the recorded events and writes one "kernel_name launches total_ms" line per kernel

@@ -237,3 +237,29 @@ def qmaxpool_bwd(dy, arg, in_hw):
 
 def mix_apply(x, mix):
     return np.einsum("pq,bchwq->bchwp", np.asarray(mix, dtype=x.dtype), x)
+
+
+# ---- optimizer step --------------------------------------------------------------------------------------
+def sgd_clip_step(params, grads, bufs, groups, lrs, wds, momentum, max_norm, nesterov=True, dampening=0.0):
+    """ultralytics/engine/trainer.py:586-594 optimizer_step: torch.nn.utils.clip_grad_norm_(parameters, max_norm) — total =
+    ||(||g_1||, ..., ||g_n||)||_2, every gradient scaled by min(1, max_norm / (total + 1e-6)) — then torch.optim.SGD.step():
+    g += wd p; buf = momentum buf + (1 - dampening) g (first step: buf = g, which a zero buffer reproduces for dampening = 0);
+    step = g + momentum buf if nesterov else buf; p -= lr step.  Lists of fp64 arrays in, (new params, new bufs, clipped grads,
+    total norm) out; `groups[i]` selects lrs / wds for tensor i; max_norm <= 0 disables clipping."""
+    total = float(np.sqrt(sum(float((g.astype(np.float64) ** 2).sum()) for g in grads)))
+    k = min(1.0, max_norm / (total + 1e-6)) if max_norm and max_norm > 0 else 1.0
+    out_p, out_b, out_g = [], [], []
+    for p, g, b, gi in zip(params, grads, bufs, groups):
+        gc = g * k
+        gg = gc + wds[gi] * p
+        nb = momentum * b + (1.0 - dampening) * gg
+        step = gg + momentum * nb if nesterov else nb
+        out_p.append(p - lrs[gi] * step)
+        out_b.append(nb)
+        out_g.append(gc)
+    return out_p, out_b, out_g, total
+
+
+def ema_update(ema, value, decay):
+    """ultralytics/utils/torch_utils.py:514-525 ModelEMA.update: v *= d; v += (1 - d) * model value."""
+    return decay * ema + (1.0 - decay) * value

@@ -159,6 +159,21 @@ static inline int grid_for(int64_t work_items, int threads, int blocks_per_sm) {
   return (int)(need < cap ? need : cap);
 }
 
+// Once-per-(host thread, device) latch.  cudaFuncSetAttribute and occupancy answers belong to the device that is current when they
+// are made; a process driving several GPUs (or a model on cuda:1) must repeat them per device.  All GPUs of a box are the same B200,
+// so cached VALUES (occupancy, SM count) are shared; only the latch is per device.
+struct DeviceOnce {
+  uint64_t mask = 0;
+  bool first() {
+    int d = 0;
+    cudaGetDevice(&d);
+    const uint64_t b = 1ull << (d & 63);
+    if (mask & b) return false;
+    mask |= b;
+    return true;
+  }
+};
+
 struct Mix16 {
   float m[16];
 };

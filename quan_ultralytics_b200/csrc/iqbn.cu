@@ -1145,8 +1145,8 @@ static int launch_reduce(const void* x, const void* dy, int B, int C, int H, int
           nparts = grid;
           QUAN_TIMED(st);
 #define QUAN_REDUCE_T(VV) { auto kern = iqbn_reduce_tma<T, VV, MODE, ACT>;                                                  \
-            static thread_local bool attr = false;                                                                        \
-            if (!attr) { QUAN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)); attr = true; } \
+            static thread_local DeviceOnce attr;                                                                        \
+            if (attr.first()) { QUAN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)); } \
             kern<<<grid, IQBN_TMA_THREADS, smem, st>>>(xp, dyp, g, ws, tail); }
           if (Vt * sizeof(T) == 16) { if constexpr (sizeof(T) == 2) QUAN_REDUCE_T(8) else QUAN_REDUCE_T(4) }
           else { if constexpr (sizeof(T) == 2) QUAN_REDUCE_T(4) else QUAN_REDUCE_T(2) }
@@ -1236,13 +1236,13 @@ static int launch_apply(const void* x, const void* dy, void* out, int B, int C, 
           QUAN_TIMED(st);
           if (mix_t != nullptr) {
             auto kern = iqbn_apply_bwd_tma<T, VT, ACT, true>;
-            static thread_local bool attr = false;
-            if (!attr) { QUAN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)); attr = true; }
+            static thread_local DeviceOnce attr;
+            if (attr.first()) { QUAN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)); }
             kern<<<grid, IQBN_TMA_THREADS, smem, st>>>(xp, dyp, op, g, a, mt);
           } else {
             auto kern = iqbn_apply_bwd_tma<T, VT, ACT, false>;
-            static thread_local bool attr = false;
-            if (!attr) { QUAN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)); attr = true; }
+            static thread_local DeviceOnce attr;
+            if (attr.first()) { QUAN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)); }
             kern<<<grid, IQBN_TMA_THREADS, smem, st>>>(xp, dyp, op, g, a, mt);
           }
           QUAN_CHECK_LAUNCH(mix_t != nullptr ? "iqbn_apply_bwd_mix" : "iqbn_apply_bwd");

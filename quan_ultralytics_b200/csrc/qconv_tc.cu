@@ -1092,8 +1092,9 @@ static int launch_igemm_inst(const CUtensorMap& map_a, const CUtensorMap& map_b,
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  static thread_local DeviceOnce attr_set;
+  if (attr_set.first()) QUAN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   if (max_groups == 0) {
-    QUAN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     int n = 0;
     if (CG == 2) {
       cfg.gridDim = dim3(QUAN_NUM_SMS);
@@ -1502,11 +1503,8 @@ static int launch_wgrad(const void* gq, const void* x, float* const dw[4], const
     if (rc) return rc;
   }
   auto kern = qconv_wgrad_kernel<T, WG_PIX / (32 / (int)sizeof(T))>;
-  static thread_local bool attr_set = false;
-  if (!attr_set) {
-    QUAN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
+  static thread_local DeviceOnce attr_set;
+  if (attr_set.first()) QUAN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   dim3 grid((unsigned)w.splits, (unsigned)(nq * w.tap_groups * w.co_blocks * w.ci_blocks));
   QUAN_TIMED(st);
   kern<<<grid, TC_THREADS, w.smem, st>>>(map_g, map_x, p);

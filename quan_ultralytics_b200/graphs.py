@@ -1,0 +1,176 @@
+"""CUDA-graphed training step: the whole forward, and the whole backward + gradient all-reduce + optimizer step, as two graph
+replays around the loss (which stays eager while it is the reference's own data-dependent Python — utils/loss.py:941-1033 reads
+`.item()`s and indexes with boolean masks — and joins the second graph when the loss function is capturable).
+
+The narrow QUAN models are launch-bound: QUAN-YOLO11n issues ~950 library kernels of 5-30 us per step plus the glue kernels of the
+reference's Python (cat / chunk copies, attention, heads); eager mode spends more host time than device time
+(tools/yolo_step_profile.py: 43 ms wall for 30 ms of kernels).  Capturing once and replaying removes the host from the step.
+
+    step = GraphedTrainStep(model, loss_fn, optimizer, example_inputs, autocast=torch.bfloat16)
+    loss, items = step(img, batch)            # img is copied into the static input buffer; everything else is replay
+
+Mechanics (PyTorch's own whole-network capture recipe, torch.cuda.graphs): warm-up iterations on a side stream, forward captured
+with gradients enabled (its autograd graph and saved activations live in the capture's private pool), backward captured into the
+same pool with `.grad = None` so that autograd's accumulators adopt pool-resident gradient tensors whose addresses stay fixed;
+the optimizer (optim.ClipSGD: chunk table of raw pointers, hyper-parameters in device memory) is captured behind it.  Multi-GPU:
+gradients are packed per bucket and all-reduced with NCCL on a side stream INSIDE the captured backward — hooks on the last
+gradient of each bucket fork the communication stream, so every replay overlaps bucket k's all-reduce with the rest of backward.
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+from torch.utils._pytree import tree_flatten, tree_unflatten
+
+
+class BucketedGradSync:
+    """Data-parallel gradient averaging for a captured backward: parameters are split (in reverse registration order = roughly the
+    order backward produces them) into `nbuckets` buckets of similar size; when the last gradient of a bucket has been accumulated
+    the bucket is flattened and all-reduced (NCCL, average) on `comm_stream`, and scattered back before the optimizer runs."""
+
+    def __init__(self, params: Sequence[torch.nn.Parameter], nbuckets: int = 3, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group)
+        ps = [p for p in params if p.requires_grad]
+        ps = list(reversed(ps))
+        total = sum(p.numel() for p in ps)
+        target = max(1, total // max(1, nbuckets))
+        self.buckets: List[List[torch.nn.Parameter]] = [[]]
+        acc = 0
+        for p in ps:
+            self.buckets[-1].append(p)
+            acc += p.numel()
+            if acc >= target and len(self.buckets) < nbuckets:
+                self.buckets.append([])
+                acc = 0
+        self.buckets = [b for b in self.buckets if b]
+        dev = ps[0].device
+        self.flat = [torch.zeros(sum(p.numel() for p in b), dtype=ps[0].dtype, device=dev) for b in self.buckets]
+        self.views = [list(torch._utils._unflatten_dense_tensors(f, b)) for f, b in zip(self.flat, self.buckets)]
+        self.comm_stream = torch.cuda.Stream(device=dev)
+        self._pending, self._launched, self._handles = [], set(), []
+
+    def attach(self) -> None:
+        for bi, bucket in enumerate(self.buckets):
+            self._handles.append(bucket[-1].register_post_accumulate_grad_hook(lambda p, bi=bi: self._launch(bi)))
+
+    def detach(self) -> None:
+        for h in self._handles:
+            h.remove()
+        self._handles = []
+
+    def _launch(self, bi: int) -> None:
+        if bi in self._launched:
+            return
+        self._launched.add(bi)
+        pairs = [(p.grad, v) for p, v in zip(self.buckets[bi], self.views[bi]) if p.grad is not None]
+        if not pairs:
+            return
+        grads, views = [g for g, _ in pairs], [v for _, v in pairs]
+        ev = torch.cuda.Event()
+        ev.record()                                    # the bucket's gradients are complete on the backward stream here
+        self.comm_stream.wait_event(ev)
+        with torch.cuda.stream(self.comm_stream):
+            torch._foreach_copy_(views, grads)         # pack
+            dist.all_reduce(self.flat[bi], op=dist.ReduceOp.AVG, group=self.group)
+            torch._foreach_copy_(grads, views)         # scatter the averages back where the optimizer reads them
+            done = torch.cuda.Event()
+            done.record()
+        self._pending.append(done)
+
+    def finish(self) -> None:
+        """Join the communication stream (call after backward, before the optimizer); buckets whose hook never fired — their last
+        parameter received no gradient — are reduced now."""
+        for bi in range(len(self.buckets)):
+            self._launch(bi)
+        for ev in self._pending:
+            torch.cuda.current_stream().wait_event(ev)
+        self._pending, self._launched = [], set()
+
+
+class GraphedTrainStep:
+    """forward graph -> loss -> backward (+ all-reduce) + optimizer graph.  `forward_fn(*static_inputs)` returns any pytree of
+    tensors; `loss_fn(outputs, *extra)` returns (loss, aux) with `loss` a scalar tensor that depends on the outputs."""
+
+    def __init__(self, forward_fn: Callable, loss_fn: Callable, optimizer, example_inputs: Sequence[torch.Tensor],
+                 params: Sequence[torch.nn.Parameter], autocast: Optional[torch.dtype] = None, warmup: int = 3,
+                 loss_args: Sequence = (), grad_sync: Optional[BucketedGradSync] = None, capture_loss: bool = False):
+        self.forward_fn, self.loss_fn, self.opt = forward_fn, loss_fn, optimizer
+        self.params = [p for p in params if p.requires_grad]
+        self.autocast = autocast
+        self.grad_sync = grad_sync
+        self.capture_loss = capture_loss
+        self.static_inputs = [torch.empty_like(t).copy_(t) for t in example_inputs]
+        dev = self.static_inputs[0].device
+
+        def ac():
+            return torch.autocast("cuda", dtype=autocast, enabled=autocast is not None)
+
+        self._ac = ac
+        # warm-up on a side stream (workspaces, library handles, allocator state)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):
+                self._eager(loss_args)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        for p in self.params:
+            p.grad = None
+        # ---- capture 1: forward (and the loss, when it is capturable)
+        self.g_fwd = torch.cuda.CUDAGraph()
+        self.loss = self.aux = None
+        with torch.cuda.graph(self.g_fwd):
+            with ac():
+                out = self.forward_fn(*self.static_inputs)
+                if capture_loss:
+                    self.loss, self.aux = self.loss_fn(out, *loss_args)
+        self.out_flat, self.out_spec = tree_flatten(out)
+        self.d_out = [torch.zeros_like(t) for t in self.out_flat]
+        # ---- capture 2: backward (+ gradient all-reduce) + optimizer, same memory pool
+        self.g_bwd = torch.cuda.CUDAGraph()
+        if grad_sync is not None:
+            grad_sync.attach()
+        with torch.cuda.graph(self.g_bwd, pool=self.g_fwd.pool()):
+            if capture_loss:
+                self.loss.backward()
+            else:
+                live = [(t, d) for t, d in zip(self.out_flat, self.d_out) if t.requires_grad]
+                torch.autograd.backward([t for t, _ in live], [d for _, d in live])
+            if grad_sync is not None:
+                grad_sync.finish()
+            self.opt.step()
+        if grad_sync is not None:
+            grad_sync.detach()
+
+    def _eager(self, loss_args):
+        for p in self.params:
+            p.grad = None
+        with self._ac():
+            out = self.forward_fn(*self.static_inputs)
+            loss, _ = self.loss_fn(out, *loss_args)
+        loss.backward()
+        # the optimizer is NOT stepped during warm-up: training state starts at the first replay
+
+    def __call__(self, inputs: Sequence[torch.Tensor], loss_args: Sequence = ()):
+        for s, t in zip(self.static_inputs, inputs):
+            if s.data_ptr() != t.data_ptr():
+                s.copy_(t, non_blocking=True)
+        self.g_fwd.replay()
+        if self.capture_loss:
+            self.g_bwd.replay()
+            return self.loss, self.aux
+        leaves = [t.detach().requires_grad_(t.requires_grad) for t in self.out_flat]
+        with self._ac():
+            loss, aux = self.loss_fn(tree_unflatten(leaves, self.out_spec), *loss_args)
+        live = [(l, d) for l, d in zip(leaves, self.d_out) if l.requires_grad]
+        grads = torch.autograd.grad(loss, [l for l, _ in live], allow_unused=True)
+        for (_, d), g in zip(live, grads):
+            if g is None:
+                d.zero_()
+            else:
+                d.copy_(g)
+        self.g_bwd.replay()
+        return loss, aux

@@ -27,22 +27,43 @@ def _device_ctx(device):
 
 def build_yolo_obb(scale: str = "n", nc: int = 15, device="cuda", swapped: bool = True, verbose: bool = False):
     """`OBBModel('yolo11{scale}-obb-quan.yaml', ch=3, nc=nc)` exactly as the reference builds it (the scale letter is parsed from the
-    file name, nn/tasks.py:1109-1132), `model.args = get_cfg(DEFAULT_CFG)` for the loss gains.  swapped=False also forces the
-    reference's `CUDA_EXT` flag on so that its IQBN takes the batch-statistics branch (conv.py:537)."""
+    file name, nn/tasks.py:1109-1132), `model.args = get_cfg(DEFAULT_CFG)` for the loss gains.  swapped=False: the untouched
+    reference with its IQBN on the batch-statistics branch (see reference_batch_stat_iqbn)."""
     refenv.activate()
     import ultralytics.nn.modules.conv as uconv
     if swapped:
         _install.install(ultralytics=True, classification=False)
     else:
         _install.uninstall()
-        uconv.CUDA_EXT = True
     from ultralytics.cfg import get_cfg
     from ultralytics.nn.tasks import OBBModel
     from ultralytics.utils import DEFAULT_CFG
     with _device_ctx(device):        # the reference runs a 1x3x256x256 probe forward while building (nn/tasks.py:341)
         model = OBBModel(f"yolo11{scale}-obb-quan.yaml", ch=3, nc=nc, verbose=verbose)
     model.args = get_cfg(DEFAULT_CFG)
+    if not swapped:
+        reference_batch_stat_iqbn(model)
     return model.to(device)
+
+
+def reference_batch_stat_iqbn(model) -> None:
+    """The untouched reference's IQBN only takes its batch-statistics branch when the module global `CUDA_EXT` is true
+    (conv.py:537, a defect — SURVEY §0.2), but the same global would send QConv2D into the compiled extension (conv.py:453).
+    The PyTorch path BASELINE.json names as the oracle = PyTorch QConv2D + batch-statistics IQBN: hooks flip the global around
+    every training-mode IQBN.forward and nothing else; no reference code is modified."""
+    import ultralytics.nn.modules.conv as uconv
+
+    def pre(mod, args):
+        if mod.training:
+            uconv.CUDA_EXT = True
+
+    def post(mod, args, out):
+        uconv.CUDA_EXT = False
+
+    for m in model.modules():
+        if type(m) is uconv.IQBN or type(m).__name__ == "IQBN" and type(m).__module__ == uconv.__name__:
+            m.register_forward_pre_hook(pre)
+            m.register_forward_hook(post)
 
 
 def synthetic_obb_batch(B: int, size: int, device="cpu", nc: int = 15, boxes_per_image: int = 40, seed: int = 1) -> Dict[str, torch.Tensor]:
@@ -84,15 +105,20 @@ def synthetic_classification_batch(B: int, size: int, num_classes: int, device="
     return torch.randn(B, 3, size, size, generator=g).to(device), torch.randint(0, num_classes, (B,), generator=g).to(device)
 
 
-def yolo_sgd(model, lr: float = 0.01, momentum: float = 0.937, decay: float = 5e-4):
-    """The reference's parameter groups (engine/trainer.py:766-806 build_optimizer with SGD): weights decay, biases and
-    normalisation weights do not — IQBN gamma/beta fall in the decayed group because the reference only exempts `nn.*Norm*`
-    classes (SURVEY §8(c) defect 5; reproduced, it is the reference's behaviour)."""
+def yolo_param_groups(model):
+    """The reference's parameter groups (engine/trainer.py:766-798 build_optimizer): (decayed weights, normalisation weights,
+    biases).  IQBN gamma / beta fall in the DECAYED group because the reference only exempts `nn.*Norm*` classes (SURVEY §8(c)
+    defect 5; reproduced, it is the reference's behaviour).  QER registers its bias twice (`bias` and `output_proj.bias`, head.py:38-39):
+    the reference hands the duplicate to torch (which warns); here every parameter appears once."""
     import torch.nn as nn
     g = [], [], []
+    seen = set()
     bn = tuple(v for k, v in nn.__dict__.items() if "Norm" in k)
     for module_name, module in model.named_modules():
         for param_name, param in module.named_parameters(recurse=False):
+            if id(param) in seen:
+                continue
+            seen.add(id(param))
             fullname = f"{module_name}.{param_name}" if module_name else param_name
             if "bias" in fullname:
                 g[2].append(param)
@@ -100,6 +126,13 @@ def yolo_sgd(model, lr: float = 0.01, momentum: float = 0.937, decay: float = 5e
                 g[1].append(param)
             else:
                 g[0].append(param)
+    return g
+
+
+def yolo_sgd(model, lr: float = 0.01, momentum: float = 0.937, decay: float = 5e-4):
+    """torch.optim.SGD over the reference's groups (trainer.py:799-806: SGD(nesterov) for the biases, then the two weight groups);
+    lr0 / momentum / weight_decay defaults of cfg/default.yaml."""
+    g = yolo_param_groups(model)
     opt = torch.optim.SGD(g[2], lr=lr, momentum=momentum, nesterov=True)
     opt.add_param_group({"params": g[0], "weight_decay": decay})
     opt.add_param_group({"params": g[1], "weight_decay": 0.0})
