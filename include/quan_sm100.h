@@ -237,6 +237,18 @@ int quan_conv_block_eval_fwd(const void* x, const float* const w[4], const float
                              const quan_conv_dims* d, int dtype, int layout, const float* mix, int algo, float eps, int act,
                              void* conv_ws, size_t conv_ws_bytes, void* stream);
 
+/* ---- QAttention core ---------------------------------------------------------------------------------
+ * Replaces the attention arithmetic of `QAttention.forward` ultralytics/nn/modules/block.py:1520-1540 (split of the qkv QConv2D output,
+ * per-component `matmul(q, k) * scale` -> `softmax` -> `matmul(attn, v)`) and its autograd, fused: the N x N score matrix never
+ * reaches HBM.  qkv: [B, heads*(2*key_dim + head_dim), H, W, 4] in QUAN_LAYOUT_BHWQC with the reference's channel order
+ * (q | k | v, each head-major); o: [B, heads*head_dim, H, W, 4]; lse: [B*4*heads*H*W] floats (log2-domain log-sum-exp per
+ * query, saved for the backward); N = H*W tokens; scale = key_dim^-0.5.  Built for (key_dim, head_dim) in {(1,2), (2,4), (4,8),
+ * (8,16)} — the QUAN yamls give (2,4) at every model scale; anything else returns QUAN_E_UNSUPPORTED. */
+int quan_qattention_fwd(const void* qkv, void* o, float* lse, int32_t B, int32_t H, int32_t W, int32_t heads, int32_t key_dim,
+                        int32_t head_dim, float scale, int dtype, int layout, void* stream);
+int quan_qattention_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, void* dqkv, int32_t B, int32_t H, int32_t W,
+                        int32_t heads, int32_t key_dim, int32_t head_dim, float scale, int dtype, int layout, void* stream);
+
 /* ---- optimizer step -------------------------------------------------------------------------------
  * Replaces `BaseTrainer.optimizer_step` ultralytics/engine/trainer.py:586-594 — torch.nn.utils.clip_grad_norm_(max_norm) followed by
  * torch.optim.SGD(momentum, nesterov, per-group lr / weight_decay).step() and zero_grad(), built by trainer.py:766-806 — and

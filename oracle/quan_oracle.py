@@ -263,3 +263,41 @@ def sgd_clip_step(params, grads, bufs, groups, lrs, wds, momentum, max_norm, nes
 def ema_update(ema, value, decay):
     """ultralytics/utils/torch_utils.py:514-525 ModelEMA.update: v *= d; v += (1 - d) * model value."""
     return decay * ema + (1.0 - decay) * value
+
+
+# ---- QAttention core (SURVEY §8(f) rank 3) --------------------------------------------------------------------------------------
+def qattention_fwd(qkv, heads, key_dim, head_dim, scale=None):
+    """ultralytics/nn/modules/block.py:1520-1540: qkv [B, heads*(2K+V), H, W, 4] -> [B, heads*V, H, W, 4].  split on dim 1 into
+    q | k | v (head-major inside each), tokens n = h*W + w, per (b, head, component): softmax(q k^T * K^-0.5) v."""
+    B, Cq, H, W, Q = qkv.shape
+    N = H * W
+    K, V = key_dim, head_dim
+    scale = K ** -0.5 if scale is None else scale
+    q = qkv[:, :heads * K].reshape(B, heads, K, N, Q)
+    k = qkv[:, heads * K:2 * heads * K].reshape(B, heads, K, N, Q)
+    v = qkv[:, 2 * heads * K:].reshape(B, heads, V, N, Q)
+    s = np.einsum("bhknq,bhkmq->bhqnm", q, k) * scale                 # [B, h, 4, N, N]
+    s = s - s.max(axis=-1, keepdims=True)
+    a = np.exp(s)
+    a /= a.sum(axis=-1, keepdims=True)
+    o = np.einsum("bhqnm,bhvmq->bhvnq", a, v)                         # [B, h, V, N, 4]
+    return o.reshape(B, heads * V, H, W, Q), a
+
+
+def qattention_bwd(d_o, qkv, heads, key_dim, head_dim, scale=None):
+    """Analytic VJP of qattention_fwd (what autograd computes for block.py:1530-1536)."""
+    B, Cq, H, W, Q = qkv.shape
+    N = H * W
+    K, V = key_dim, head_dim
+    scale = K ** -0.5 if scale is None else scale
+    _, a = qattention_fwd(qkv, heads, K, V, scale)
+    q = qkv[:, :heads * K].reshape(B, heads, K, N, Q)
+    k = qkv[:, heads * K:2 * heads * K].reshape(B, heads, K, N, Q)
+    v = qkv[:, 2 * heads * K:].reshape(B, heads, V, N, Q)
+    do = d_o.reshape(B, heads, V, N, Q)
+    dv = np.einsum("bhqnm,bhvnq->bhvmq", a, do)
+    da = np.einsum("bhvnq,bhvmq->bhqnm", do, v)
+    ds = a * (da - (a * da).sum(axis=-1, keepdims=True)) * scale
+    dq = np.einsum("bhqnm,bhkmq->bhknq", ds, k)
+    dk = np.einsum("bhqnm,bhknq->bhkmq", ds, q)
+    return np.concatenate([dq.reshape(B, heads * K, H, W, Q), dk.reshape(B, heads * K, H, W, Q), dv.reshape(B, heads * V, H, W, Q)], axis=1)

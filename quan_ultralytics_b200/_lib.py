@@ -71,6 +71,8 @@ PROTOTYPES = {
                                         _vp, _sz, _vp]),
     "quan_qconv2d_bwd_premixed": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _pdims, _int, _int, _vp, _int, _vp, _sz, _vp]),
     "quan_qconv2d_bwd_wants_mixed": (_int, [_pdims, _int, _int, _int, _int, _int]),
+    "quan_qattention_fwd": (_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f, _int, _int, _vp]),
+    "quan_qattention_bwd": (_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f, _int, _int, _vp]),
     "quan_sgd_clip_step": (_int, [_vp, _int, _vp, _vp, _int, _vp, _vp, _int, _vp]),
     "quan_ema_update": (_int, [_vp, _int, _vp, _vp, _vp]),
 }

@@ -226,6 +226,27 @@ def qupsample_nearest(x: torch.Tensor, scale: int = 2) -> torch.Tensor:
     return _QUpsample.apply(x, int(scale))
 
 
+class _QAttention(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, qkv, heads, key_dim, head_dim, scale):
+        qkv, _ = ops.as_layout(qkv, ops.LAYOUT_BHWQC)
+        o, lse = ops.qattention_fwd(qkv, heads, key_dim, head_dim, scale)
+        ctx.save_for_backward(qkv, o, lse)
+        ctx.conf = (heads, key_dim, head_dim, scale)
+        return o
+
+    @staticmethod
+    def backward(ctx, d_o):
+        qkv, o, lse = ctx.saved_tensors
+        return ops.qattention_bwd(qkv, o, d_o, lse, *ctx.conf), None, None, None, None
+
+
+def qattention(qkv: torch.Tensor, heads: int, key_dim: int, head_dim: int, scale: float) -> torch.Tensor:
+    """The attention arithmetic of QAttention.forward (block.py:1520-1540) on the qkv projection, fused: per quaternion component
+    and head, softmax(q k^T * scale) v over the H*W tokens.  Returns [B, heads*head_dim, H, W, 4] in the internal layout."""
+    return _QAttention.apply(qkv, int(heads), int(key_dim), int(head_dim), float(scale))
+
+
 class _QMaxPool(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, kernel, stride, padding):

@@ -41,6 +41,30 @@ def uninstall() -> None:
         setattr(mod, name, old)
 
 
+_SUPPORTED_HEADS = ((1, 2), (2, 4), (4, 8), (8, 16))       # (key_dim, head_dim) instantiations of quan_qattention_*
+
+
+def _qattention_forward(self, x):
+    """QAttention.forward (block.py:1511-1546) with the attention arithmetic fused (quan_qattention_fwd/bwd): the qkv / pe / proj
+    QConv2D layers are the module's own (already the B200 classes), the split / reshape / matmul / softmax / matmul / reshape between
+    them is one kernel.  Head shapes the library was not built for keep the reference's own forward."""
+    from . import functional as QF
+    from . import ops
+    if (self.key_dim, self.head_dim) not in _SUPPORTED_HEADS or not ops.on_device(x):
+        return self._reference_forward(x)
+    o = QF.qattention(self.qkv(x), self.num_heads, self.key_dim, self.head_dim, self.scale)
+    return self.proj(o + self.pe(o))
+
+
+def _make_qattention(ref_cls):
+    """Subclass of the REFERENCE's QAttention: its constructor (and therefore every parameter, buffer and state-dict key, including the
+    unused IQLN `norm`, block.py:1506) stays the reference's; only `forward` is ours."""
+    if getattr(ref_cls, "_quan_fused", False):
+        return ref_cls
+    return type("QAttention", (ref_cls,), {"forward": _qattention_forward, "_reference_forward": ref_cls.forward, "_quan_fused": True,
+                                           "__module__": __name__, "__doc__": _qattention_forward.__doc__})
+
+
 def install(ultralytics: bool = True, classification: bool = True) -> dict:
     """Level 2: replace the reference's layer classes with the B200 modules in every namespace that re-exports them.
     Returns {module_name: [swapped names]} for logging."""
@@ -55,6 +79,10 @@ def install(ultralytics: bool = True, classification: bool = True) -> dict:
             names = [n for n in _SWAP if hasattr(mod, n)]
             for n in names:
                 _swap(mod, n, getattr(M, n))
+            if hasattr(mod, "QAttention"):            # block.py:1485-1546: the reference's class with a fused forward
+                ref_cls = importlib.import_module("ultralytics.nn.modules.block").QAttention
+                _swap(mod, "QAttention", _make_qattention(ref_cls))
+                names.append("QAttention")
             done[modname] = names
     if classification:
         for modname in ("quaternion.qconv", "quaternion", "models.quaternion_blocks", "models.quaternion_models",

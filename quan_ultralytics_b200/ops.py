@@ -246,6 +246,35 @@ def qmaxpool_bwd(dy: torch.Tensor, idx: torch.Tensor, in_hw, kernel, stride, pad
     return out
 
 
+# ---- QAttention core ------------------------------------------------------------------------------------------------
+def qattention_fwd(qkv: torch.Tensor, heads: int, key_dim: int, head_dim: int, scale: float):
+    """block.py:1520-1540 fused: qkv [B, heads*(2K+V), H, W, 4] (BHWQC) -> (o [B, heads*V, H, W, 4], lse [B*4*heads*H*W])."""
+    _require_cuda(qkv)
+    qkv, layout = as_layout(qkv, LAYOUT_BHWQC)
+    B, Cq, H, W, _ = qkv.shape
+    if Cq != heads * (2 * key_dim + head_dim):
+        raise RuntimeError(f"qattention_fwd: {Cq} channels do not split into {heads} heads of q,k ({key_dim}) and v ({head_dim})")
+    o = empty_q((B, heads * head_dim, H, W, 4), qkv.dtype, qkv.device, LAYOUT_BHWQC)
+    lse = torch.empty(B * 4 * heads * H * W, dtype=torch.float32, device=qkv.device)
+    check(_lib.load().quan_qattention_fwd(qkv.data_ptr(), o.data_ptr(), lse.data_ptr(), B, H, W, heads, key_dim, head_dim, float(scale),
+                                          _dtype_code(qkv), layout, _stream(qkv)), "quan_qattention_fwd")
+    return o, lse
+
+
+def qattention_bwd(qkv: torch.Tensor, o: torch.Tensor, d_o: torch.Tensor, lse: torch.Tensor, heads: int, key_dim: int, head_dim: int,
+                   scale: float) -> torch.Tensor:
+    _require_cuda(qkv, o, d_o, lse)
+    d_o, _ = as_layout(d_o, LAYOUT_BHWQC)
+    if d_o.dtype != qkv.dtype:
+        d_o = d_o.to(qkv.dtype)
+    B, Cq, H, W, _ = qkv.shape
+    dqkv = torch.empty_like(qkv, memory_format=torch.preserve_format)
+    check(_lib.load().quan_qattention_bwd(qkv.data_ptr(), o.data_ptr(), d_o.data_ptr(), lse.data_ptr(), dqkv.data_ptr(), B, H, W, heads,
+                                          key_dim, head_dim, float(scale), _dtype_code(qkv), LAYOUT_BHWQC, _stream(qkv)),
+          "quan_qattention_bwd")
+    return dqkv
+
+
 # ---- IQBN ----------------------------------------------------------------------------------------------------------
 def iqbn_train_stats(x: torch.Tensor, layout: int, gamma: torch.Tensor, beta: torch.Tensor, eps: float, momentum: float,
                      running_mean: Optional[torch.Tensor], running_var: Optional[torch.Tensor]) -> torch.Tensor:

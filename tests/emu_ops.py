@@ -287,3 +287,30 @@ def emulated(on_device: bool = True):
     finally:
         for n, v in saved.items():
             setattr(ops, n, v)
+
+
+# ---- QAttention core (block.py:1520-1540) ----------------------------------------------------------------------------------------
+def _qattn_ref(qkv, heads, K, V, scale):
+    B, Cq, H, W, Q = qkv.shape
+    N = H * W
+    q, k, v = torch.split(qkv, [heads * K, heads * K, heads * V], dim=1)
+    q = q.reshape(B, heads, K, N, Q).permute(0, 1, 4, 3, 2)
+    k = k.reshape(B, heads, K, N, Q).permute(0, 1, 4, 2, 3)
+    v = v.reshape(B, heads, V, N, Q).permute(0, 1, 4, 3, 2)
+    attn = (torch.matmul(q, k) * scale).softmax(dim=-1)
+    return torch.matmul(attn, v).permute(0, 1, 4, 3, 2).reshape(B, heads * V, H, W, Q)
+
+
+def qattention_fwd(qkv, heads, key_dim, head_dim, scale):
+    o = _qattn_ref(qkv.float(), heads, key_dim, head_dim, scale).to(qkv.dtype)
+    return _fmt(o, L_BHWQC), torch.zeros(1)
+
+
+def qattention_bwd(qkv, o, d_o, lse, heads, key_dim, head_dim, scale):
+    with torch.enable_grad():
+        x = qkv.detach().float().requires_grad_(True)
+        _qattn_ref(x, heads, key_dim, head_dim, scale).backward(d_o.float())
+    return _fmt(x.grad.to(qkv.dtype), L_BHWQC)
+
+
+_NAMES += ["qattention_fwd", "qattention_bwd"]

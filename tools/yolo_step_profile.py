@@ -79,7 +79,22 @@ def main():
         with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
             step()
             torch.cuda.synchronize()
-        print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=a.table, max_name_column_width=70))
+        from torch.autograd import DeviceType
+        rows = []
+        for e in prof.key_averages():
+            if e.device_type != DeviceType.CUDA:
+                continue
+            t = getattr(e, "self_device_time_total", None)
+            if t is None:
+                t = e.self_cuda_time_total
+            rows.append((t, e.count, e.key))
+        rows.sort(reverse=True)
+        tot = sum(r[0] for r in rows)
+        ours = sum(r[0] for r in rows if "quan::" in r[2])
+        print(f"device kernels in one step: {tot / 1e3:.2f} ms in {sum(r[1] for r in rows)} launches; library (quan::) {ours / 1e3:.2f} ms in "
+              f"{sum(r[1] for r in rows if 'quan::' in r[2])} launches; everything else {(tot - ours) / 1e3:.2f} ms")
+        for t, c, k in rows[: a.table]:
+            print(f"{t / 1e3:8.3f} ms {100 * t / tot:5.1f}% {c:5d} x {t / max(c, 1):8.1f} us  {k[:150]}")
 
 
 if __name__ == "__main__":
