@@ -249,6 +249,20 @@ int quan_qattention_fwd(const void* qkv, void* o, float* lse, int32_t B, int32_t
 int quan_qattention_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, void* dqkv, int32_t B, int32_t H, int32_t W,
                         int32_t heads, int32_t key_dim, int32_t head_dim, float scale, int dtype, int layout, void* stream);
 
+/* ---- rotated task-aligned assigner (the non-differentiable half of v8OBBLoss) -------------------------
+ * Replaces `RotatedTaskAlignedAssigner.forward` ultralytics/utils/tal.py:298-330 (+ base class :40-296) as called by
+ * `v8OBBLoss.__call__` ultralytics/utils/loss.py:985-993: static shapes, no host synchronisation (graph-capturable).
+ * All tensors fp32, dense:  pd_scores [B,A,nc] (sigmoid of the class logits), pd_bboxes [B,A,5] (xywhr, pixels), anc_points [A,2]
+ * (pixels), gt_labels [B,n], gt_bboxes [B,n,5] (xywhr, pixels), mask_gt [B,n] (0/1: padding rows are 0).
+ * Outputs: target_bboxes [B,A,5] (the assigned box; box 0 of the image for background anchors, as tal.py:212-216 yields),
+ * target_scores [B,A,nc], fg_mask [B,A] (0/1 bytes), target_gt_idx [B,A] (int64).  Top-k ties resolve to the lowest anchor index
+ * (torch.topk leaves tie order unspecified).  workspace: quan_rotated_tal_workspace_bytes(B, A, n). */
+size_t quan_rotated_tal_workspace_bytes(int32_t B, int32_t A, int32_t n);
+int quan_rotated_tal_assign(const float* pd_scores, const float* pd_bboxes, const float* anc_points, const float* gt_labels,
+                            const float* gt_bboxes, const float* mask_gt, int32_t B, int32_t A, int32_t n, int32_t nc, int32_t topk,
+                            float alpha, float beta, float eps, float* target_bboxes, float* target_scores, uint8_t* fg_mask,
+                            int64_t* target_gt_idx, void* workspace, size_t ws_bytes, void* stream);
+
 /* ---- optimizer step -------------------------------------------------------------------------------
  * Replaces `BaseTrainer.optimizer_step` ultralytics/engine/trainer.py:586-594 — torch.nn.utils.clip_grad_norm_(max_norm) followed by
  * torch.optim.SGD(momentum, nesterov, per-group lr / weight_decay).step() and zero_grad(), built by trainer.py:766-806 — and

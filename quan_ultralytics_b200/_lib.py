@@ -73,6 +73,9 @@ PROTOTYPES = {
     "quan_qconv2d_bwd_wants_mixed": (_int, [_pdims, _int, _int, _int, _int, _int]),
     "quan_qattention_fwd": (_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f, _int, _int, _vp]),
     "quan_qattention_bwd": (_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f, _int, _int, _vp]),
+    "quan_rotated_tal_workspace_bytes": (_sz, [_i32, _i32, _i32]),
+    "quan_rotated_tal_assign": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _f, _f, _f, _vp, _vp, _vp, _vp,
+                                       _vp, _sz, _vp]),
     "quan_sgd_clip_step": (_int, [_vp, _int, _vp, _vp, _int, _vp, _vp, _int, _vp]),
     "quan_ema_update": (_int, [_vp, _int, _vp, _vp, _vp]),
 }

@@ -92,7 +92,9 @@ class BucketedGradSync:
 
 class GraphedTrainStep:
     """forward graph -> loss -> backward (+ all-reduce) + optimizer graph.  `forward_fn(*static_inputs)` returns any pytree of
-    tensors; `loss_fn(outputs, *extra)` returns (loss, aux) with `loss` a scalar tensor that depends on the outputs."""
+    tensors; `loss_fn(outputs, *static_inputs, *loss_args)` returns (loss, aux) with `loss` a scalar tensor that depends on the
+    outputs.  capture_loss=True puts the loss into the forward graph (it must then be free of host synchronisation, e.g.
+    loss.OBBLossStatic, and read its targets from the static inputs)."""
 
     def __init__(self, forward_fn: Callable, loss_fn: Callable, optimizer, example_inputs: Sequence[torch.Tensor],
                  params: Sequence[torch.nn.Parameter], autocast: Optional[torch.dtype] = None, warmup: int = 3,
@@ -126,7 +128,7 @@ class GraphedTrainStep:
             with ac():
                 out = self.forward_fn(*self.static_inputs)
                 if capture_loss:
-                    self.loss, self.aux = self.loss_fn(out, *loss_args)
+                    self.loss, self.aux = self.loss_fn(out, *self.static_inputs, *loss_args)
         self.out_flat, self.out_spec = tree_flatten(out)
         self.d_out = [torch.zeros_like(t) for t in self.out_flat]
         # ---- capture 2: backward (+ gradient all-reduce) + optimizer, same memory pool
@@ -150,7 +152,7 @@ class GraphedTrainStep:
             p.grad = None
         with self._ac():
             out = self.forward_fn(*self.static_inputs)
-            loss, _ = self.loss_fn(out, *loss_args)
+            loss, _ = self.loss_fn(out, *self.static_inputs, *loss_args)
         loss.backward()
         # the optimizer is NOT stepped during warm-up: training state starts at the first replay
 
@@ -164,7 +166,7 @@ class GraphedTrainStep:
             return self.loss, self.aux
         leaves = [t.detach().requires_grad_(t.requires_grad) for t in self.out_flat]
         with self._ac():
-            loss, aux = self.loss_fn(tree_unflatten(leaves, self.out_spec), *loss_args)
+            loss, aux = self.loss_fn(tree_unflatten(leaves, self.out_spec), *self.static_inputs, *loss_args)
         live = [(l, d) for l, d in zip(leaves, self.d_out) if l.requires_grad]
         grads = torch.autograd.grad(loss, [l for l, _ in live], allow_unused=True)
         for (_, d), g in zip(live, grads):

