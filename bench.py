@@ -1,9 +1,14 @@
 #!/usr/bin/env python
 """bench.py — hot-path benchmark (contract in the task statement, read per SURVEY §8(d)).
 
-Workload (config[1] of BASELINE.json, "QConv2D/IQBN layer sweep" point): a stack of `depth` reference `Conv` blocks
-(QConv2D 3x3 s1 p1 C_q->C_q  ->  IQBN(batch stats)  ->  SiLU), training step = forward + backward (dX, dW, dgamma,
-dbeta) + SGD(momentum) update, on synthetic N x C_q x H x W x 4 activations.  metric = train images/s.
+Default workload = BASELINE.json configs[2], the configuration the metric "train images/sec at 1/2/4/8 B200" is quoted on:
+the QUAN-YOLO11n-OBB training step (the reference's own model graph from yolo11n-obb-quan.yaml, nc=15, with the B200 layer classes
+installed) on a synthetic DOTA-shaped batch of 16 images of 1024^2 per GPU with 40 rotated boxes each, bf16 autocast: forward +
+v8OBBLoss + backward + grad-clip 10 + SGD(nesterov) (engine/trainer.py:379-393, :586-594), replayed from two CUDA graphs.
+`--impl reference` = the SAME model graph untouched (baseline/_ref, the reference's PyTorch path) on the host cores.
+Other workloads: `--workload block_stack` (configs[1] sweep point: a stack of `depth` reference `Conv` blocks, QConv2D 3x3 C_q->C_q ->
+IQBN(batch stats) -> SiLU, training step on N x C_q x H x W x 4 activations), `sweep` (the whole configs[1] layer sweep as JSON),
+`yolo11s_obb` (configs[4]), `qresnet34` (configs[3]) and the per-layer `*_trace` replays.  metric = train images/s.
 
   value      : images/s with the batch already resident in HBM (CUDA-event timed, max over ranks)
   e2e        : same step through the public nn.Module API with HOST (pinned) inputs: H2D of the batch and D2H of the
@@ -35,14 +40,18 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="block_stack", choices=["block_stack", "yolo11n_trace", "yolo11s_trace", "qresnet34_trace"],
+    ap.add_argument("--workload", default="yolo11n_obb", choices=["yolo11n_obb", "yolo11s_obb", "block_stack", "yolo11n_trace", "yolo11s_trace", "qresnet34_trace"],
                     help="block_stack: BASELINE config[1] sweep point (default, the bench line); yolo11n_trace: replay of "
                          "the 87 QConv2D / 84 IQBN+SiLU calls of QUAN-YOLO11n-OBB at 1024^2 (SURVEY 8(a) histogram); "
                          "yolo11s_trace (config[4], default 8 images) and qresnet34_trace (config[3], 224^2, M_B, biased convs, "
                          "default 256 images): the same replay from tests/golden/model_traces.json (tools/probe_model_trace.py)")
     ap.add_argument("--cq", type=int, default=256, help="quaternion channels per component")
     ap.add_argument("--hw", type=int, default=32)
-    ap.add_argument("--n", type=int, default=64, help="images per GPU per step")
+    ap.add_argument("--n", type=int, default=None, help="images per GPU per step (default: 16 yolo11n_obb, 8 yolo11s_obb, 64 block_stack)")
+    ap.add_argument("--size", type=int, default=1024, help="yolo*_obb: image side")
+    ap.add_argument("--buckets", type=int, default=3, help="yolo*_obb, N > 1: gradient all-reduce buckets launched inside the captured backward")
+    ap.add_argument("--no-graph", action="store_true", help="yolo*_obb: eager step (reference v8OBBLoss, host-synchronous) instead of the two CUDA graphs")
+    ap.add_argument("--ref-loss", action="store_true", help="yolo*_obb: the reference's own v8OBBLoss (eager, between the two graphs) instead of loss.OBBLossStatic")
     ap.add_argument("--depth", type=int, default=4)
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--mix", default="A", choices=["A", "B"])
@@ -62,7 +71,13 @@ def parse_args():
                     help="yolo11n_trace: eval-mode forward only under no_grad (IQBN running statistics + SiLU in the conv epilogue); "
                          "reports forward latency per batch of --n images (BASELINE config 5 asks for batch-1 latency)")
     ap.add_argument("--graph", action="store_true", help="yolo11n_trace: capture the step in a CUDA graph (removes host launch overhead)")
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.n is None:
+        a.n = {"yolo11n_obb": 16, "yolo11s_obb": 8}.get(a.workload, 64)
+        a.n_default = True
+    else:
+        a.n_default = False
+    return a
 
 
 def workload_name(a):
@@ -518,13 +533,309 @@ def run_model_trace(a, name):
     print(json.dumps(line))
 
 
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# BASELINE configs[2] / [4]: the QUAN-YOLO11-OBB training step on the reference's own model graph
+# ---------------------------------------------------------------------------------------------------------------
+def yolo_workload_name(a, scale, B):
+    return (f"QUAN-YOLO11{scale}-OBB train step (yolo11{scale}-obb-quan.yaml, nc=15): {B} x 3 x {a.size}^2 per GPU, 40 rotated boxes/img, "
+            f"fwd + v8OBBLoss + bwd + clip 10 + SGD(nesterov)")
+
+
+def yolo_cpu_reference(a, scale, n_images, steps, warmup):
+    """The UNMODIFIED reference (baseline/_ref: its own graph, PyTorch path — 4 x F.conv2d + mix, batch-statistics IQBN, its own
+    v8OBBLoss) on the host cores: forward + loss + backward + clip_grad_norm_(10) + torch SGD(nesterov), fp32."""
+    from quan_ultralytics_b200 import workloads
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    model = workloads.build_yolo_obb(scale, 15, "cpu", swapped=False).train()
+    opt = workloads.yolo_sgd(model)
+    batch = workloads.synthetic_obb_batch(n_images, a.size, "cpu", seed=1)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        loss, _ = model({k: v.clone() for k, v in batch.items()})
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=10.0)
+        opt.step()
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    return n_images / sec, sec, cores
+
+
+def yolo_config(a, scale, B, world):
+    """The workload definition both arms print (identical dicts: the driver compares them)."""
+    return {"workload": yolo_workload_name(a, scale, B), "parallelism": f"dp{world}",
+            "l2": "per-step activations (~3 GB saved for backward) exceed the 126 MB L2"}
+
+
+def yolo_reference_arm(a):
+    """`--impl reference`: the unmodified reference on the host cores, K timed steps after W warm-up steps as asked; each step is a
+    bounded sample of the workload — ONE image of the 16-image batch (a 1024^2 image costs ~1-2 s of fwd + loss + bwd on 16 cores) —
+    and the value is per-image normalised."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    scale = "n" if a.workload == "yolo11n_obb" else "s"
+    n = 1
+    ips, sec, cores = yolo_cpu_reference(a, scale, n, a.steps, a.warmup)
+    print(json.dumps({
+        "impl": "reference", "metric": "train_images_per_sec", "value": ips, "unit": "images/s", "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": yolo_config(a, scale, a.n, a.gpus),
+        "implementation": "unmodified reference model graph and PyTorch path (baseline/_ref: 4 x F.conv2d + mix, batch-statistics IQBN, "
+                          "v8OBBLoss, clip_grad_norm_ + torch SGD) on the host cores, fp32",
+        "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "reference",
+                         "sample": f"{n} image/step of the same training step ({a.steps} timed steps, {a.warmup} warm-up), per-image normalised"},
+        "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+
+
+def parse_timing_report(lib):
+    import ctypes
+    n = lib.quan_kernel_timing_report(None, 0)
+    buf = ctypes.create_string_buffer(n + 16)
+    lib.quan_kernel_timing_report(buf, n + 16)
+    rows = {}
+    for ln in buf.value.decode().splitlines():
+        f = ln.split()
+        if len(f) < 3 or int(f[1]) == 0:
+            continue
+        rows[f[0]] = {"launches": int(f[1]), "ms": float(f[2]), "bytes": float(f[3]) if len(f) > 3 else 0.0,
+                      "flops": float(f[4]) if len(f) > 4 else 0.0}
+    return rows
+
+
+def run_yolo_obb(a):
+    import quan_ultralytics_b200 as Q
+    from quan_ultralytics_b200 import optim, workloads
+    from quan_ultralytics_b200.graphs import BucketedGradSync, GraphedTrainStep
+    from quan_ultralytics_b200.loss import OBBLossStatic, pad_targets
+    import torch.distributed as dist
+    lib = Q._lib.load()
+    scale = "n" if a.workload == "yolo11n_obb" else "s"
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product has no CPU path); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ac = torch.bfloat16 if a.dtype == "bf16" else None
+    peaks = load_peaks()
+    B, S = a.n, a.size
+
+    torch.manual_seed(0)
+    model = workloads.build_yolo_obb(scale, 15, dev, swapped=True).train()
+    if world > 1:
+        for t in list(model.parameters()) + [b for b in model.buffers() if b.is_floating_point()]:
+            dist.broadcast(t.data, 0)
+        if a.sync_iqbn:
+            from quan_ultralytics_b200.distributed import convert_sync_iqbn
+            convert_sync_iqbn(model)
+    params = list(model.parameters())
+    opt = optim.yolo_clip_sgd(model)
+    batch = workloads.synthetic_obb_batch(B, S, dev, seed=1 + rank)
+    tg, tm = pad_targets(batch, B)
+    tg, tm = tg.to(dev), tm.to(dev)
+    crit = OBBLossStatic(model)
+    ref_crit = lambda preds: model.loss(batch, preds)          # the reference's own criterion (utils/loss.py:941), --ref-loss / --no-graph
+    sync = BucketedGradSync(params, nbuckets=a.buckets) if world > 1 else None
+
+    def eager_step(use_ref_loss=False):
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=ac, enabled=ac is not None):
+            preds = model(batch["img"])
+            loss, items = ref_crit(preds) if use_ref_loss else crit(preds, {"targets": tg, "target_mask": tm})
+        loss.backward()
+        if sync is not None:
+            sync.finish()
+        opt.step()
+        return loss
+
+    if a.no_graph:
+        static_img = batch["img"]
+        run = lambda: eager_step(True)
+        captured = None
+    elif a.ref_loss:
+        gs = GraphedTrainStep(lambda img: model(img), lambda preds, img: ref_crit(preds), opt, [batch["img"]], params, autocast=ac,
+                              grad_sync=sync)
+        static_img = gs.static_inputs[0]
+        run = lambda: gs([static_img])[0]
+        captured = gs.captured_launches
+    else:
+        gs = GraphedTrainStep(lambda img, t, m: model(img), lambda preds, img, t, m: crit(preds, {"targets": t, "target_mask": m}), opt,
+                              [batch["img"], tg, tm], params, autocast=ac, grad_sync=sync, capture_loss=True)
+        static_img = gs.static_inputs[0]
+        run = lambda: gs(gs.static_inputs)[0]
+        captured = gs.captured_launches
+
+    # ---- e2e leg: every step copies ITS batch from pinned host memory — uint8 images as a loader delivers them + the padded targets —
+    # on a side stream into one of two staging buffers (the copy of step i+1 overlaps step i), converts on the device as the reference's
+    # preprocess_batch does (`batch["img"].to(device).float() / 255`, models/yolo/detect/train.py:57-59) and reads the loss back
+    g = torch.Generator().manual_seed(100 + rank)
+    img_host = torch.randint(0, 256, (B, 3, S, S), dtype=torch.uint8, generator=g).pin_memory()
+    tg_host, tm_host = tg.cpu().pin_memory(), tm.cpu().pin_memory()
+    stage = [(torch.empty_like(img_host, device=dev), torch.empty_like(tg), torch.empty_like(tm)) for _ in range(2)]
+    copy_stream = torch.cuda.Stream(device=dev)
+    copied = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+    done = [torch.cuda.Event(), torch.cuda.Event()]
+    loss_host = [torch.zeros(1).pin_memory() for _ in range(2)]
+    st = {"i": 0, "primed": False}
+
+    def prefetch(slot):
+        copy_stream.wait_event(consumed[slot])
+        with torch.cuda.stream(copy_stream):
+            stage[slot][0].copy_(img_host, non_blocking=True)
+            stage[slot][1].copy_(tg_host, non_blocking=True)
+            stage[slot][2].copy_(tm_host, non_blocking=True)
+            copied[slot].record(copy_stream)
+
+    def e2e_step():
+        i = st["i"]
+        cur = i & 1
+        if not st["primed"]:
+            consumed[0].record()
+            consumed[1].record()
+            prefetch(cur)
+            st["primed"] = True
+        prefetch(cur ^ 1)
+        torch.cuda.current_stream().wait_event(copied[cur])
+        static_img.copy_(stage[cur][0])                       # uint8 -> float32 ...
+        static_img.mul_(1.0 / 255.0)                          # ... / 255
+        if not a.no_graph and not a.ref_loss:
+            gs.static_inputs[1].copy_(stage[cur][1])
+            gs.static_inputs[2].copy_(stage[cur][2])
+        consumed[cur].record()
+        loss = run()
+        loss_host[cur].copy_(loss.detach().reshape(1).float(), non_blocking=True)
+        done[cur].record()
+        if i > 0:
+            done[cur ^ 1].synchronize()
+        st["i"] = i + 1
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(max(a.warmup, 3)):
+        run()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    n0 = lib.quan_launch_count()
+    ms = timed(run, a.steps)
+    launches = lib.quan_launch_count() - n0 if captured is None else captured * a.steps
+    for _ in range(2):
+        e2e_step()
+    torch.cuda.synchronize()
+    st["primed"] = False
+    ms_e2e = timed(e2e_step, a.steps)
+    final_loss = float(loss_host[(st["i"] - 1) & 1][0])
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- per-kernel device times of the library inside the (eager) step: every launch bracketed by a CUDA-event pair on its own
+    # stream, with the algorithmic bytes / FLOPs each API call announces (all ranks run it: the step holds collectives)
+    table = None
+    if not a.no_kernel_table:
+        for _ in range(2):
+            eager_step()
+        torch.cuda.synchronize()
+        lib.quan_kernel_timing_enable(1)
+        ksteps = 3
+        for _ in range(ksteps):
+            eager_step()
+        torch.cuda.synchronize()
+        lib.quan_kernel_timing_enable(0)
+        table = parse_timing_report(lib)
+
+    imgs = B * world * a.steps
+    if rank == 0:
+        line = {
+            "metric": "train_images_per_sec", "value": imgs / (ms / 1e3), "unit": "images/s", "n_gpus": world, "steps": a.steps,
+            "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": a.dtype, "data": "synthetic",
+            "config": yolo_config(a, scale, B, world),
+            "implementation": {"step": ("eager" if a.no_graph else "2 CUDA graphs (forward+loss | backward+all-reduce+optimizer)" if not a.ref_loss
+                                        else "2 CUDA graphs around the reference's eager v8OBBLoss"),
+                               "loss": "reference v8OBBLoss" if (a.no_graph or a.ref_loss) else "OBBLossStatic (CUDA assigner, static shapes)",
+                               "optimizer": "ClipSGD: clip_grad_norm_(10) + SGD(lr .01, momentum .937, nesterov, wd 5e-4) in 2 launches",
+                               "sync_iqbn": bool(a.sync_iqbn and world > 1), "grad_buckets": a.buckets if world > 1 else None,
+                               "params": sum(p.numel() for p in params)},
+            "e2e": {"value": imgs / (ms_e2e / 1e3), "unit": "images/s",
+                    "h2d_bytes_per_step": img_host.numel() + 4 * (tg_host.numel() + tm_host.numel()), "d2h_bytes_per_step": 4},
+            "gpu_launches": int(launches), "clocks": clocks, "final_loss": final_loss,
+        }
+        if table:
+            esz = 2.0 if a.dtype == "bf16" else 4.0
+            tpeak = peaks["bf16_tflops"] * (1.0 if a.dtype == "bf16" else 0.5) * 1e12     # burst: every kernel here runs for microseconds
+            bw = peaks["hbm_gbs"] * 1e9
+            rows, lib_ms, floor_ms = {}, 0.0, 0.0
+            for name, r in table.items():
+                per_step = r["ms"] / ksteps
+                lib_ms += per_step
+                row = {"launches_per_step": r["launches"] / ksteps, "ms_per_step": per_step, "us_per_launch": 1e3 * r["ms"] / r["launches"]}
+                if r["bytes"] > 0 or r["flops"] > 0:
+                    t_hbm, t_tc = r["bytes"] / bw, r["flops"] / tpeak
+                    bound = "hbm" if t_hbm >= t_tc else "tensor"
+                    sec = r["ms"] / 1e3
+                    ach = r["bytes"] / sec / 1e9 if bound == "hbm" else r["flops"] / sec / 1e12
+                    pk = peaks["hbm_gbs"] if bound == "hbm" else tpeak / 1e12
+                    row.update({"bound": bound, "achieved": ach, "peak": pk, "unit": "GB/s" if bound == "hbm" else "TFLOP/s", "frac": ach / pk,
+                                "algorithmic_mb_per_step": r["bytes"] / ksteps / 1e6, "algorithmic_gflop_per_step": r["flops"] / ksteps / 1e9})
+                    floor_ms += 1e3 * max(t_hbm, t_tc) / ksteps
+                rows[name] = row
+            dom = max((k for k in rows if "frac" in rows[k]), key=lambda k: rows[k]["ms_per_step"])
+            r = {k: rows[dom][k] for k in ("bound", "achieved", "peak", "unit", "frac")}
+            r.update({"kernel": dom, "peak_src": peaks["src"] + " (burst)", "traffic": ncu_traffic().get(dom + ":" + a.workload),
+                      "us_per_launch": rows[dom]["us_per_launch"], "launches_per_step": rows[dom]["launches_per_step"],
+                      "share_of_library_kernel_time": rows[dom]["ms_per_step"] / lib_ms,
+                      "note": "achieved = algorithmic bytes (or FLOPs) of all launches of this kernel in one step / their summed device time, "
+                              "measured with CUDA-event pairs on the launching stream inside the eager step"})
+            line["roofline"] = r
+            line["library_kernel_ms_per_step"] = lib_ms
+            line["library_roofline_floor_ms_per_step"] = floor_ms
+            line["kernels_in_step"] = dict(sorted(rows.items(), key=lambda kv: -kv[1]["ms_per_step"]))
+        if world == 1 and not a.no_cpu_baseline:
+            ips, sec, cores = yolo_cpu_reference(a, scale, 1, a.cpu_steps, 1)
+            line["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": cores, "kind": "reference",
+                                    "sample": f"1 image/step of the same training step through the unmodified reference (baseline/_ref), "
+                                              f"{a.cpu_steps} timed steps after 1 warm-up, fp32, per-image normalised"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     a = parse_args()
     if a.workload.endswith("_trace") and a.impl == "ours":
         name = a.workload[:-len("_trace")]
-        if a.n == 64:                                           # per-GPU batch of the BASELINE config that names the model
+        if a.n_default:                                         # per-GPU batch of the BASELINE config that names the model
             a.n = {"yolo11n": 16, "yolo11s": 8, "qresnet34": 256}[name]
         run_model_trace(a, name)
+        return
+    if a.workload.endswith("_obb"):
+        (yolo_reference_arm if a.impl == "reference" else run_yolo_obb)(a)
         return
     if a.impl == "reference":
         reference_arm(a)

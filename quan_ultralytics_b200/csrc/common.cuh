@@ -30,6 +30,7 @@ void count_launch();                    // defined in api.cu (process-wide atomi
 // optional per-kernel timing (api.cu): QUAN_TIMED(st) before a launch, QUAN_CHECK_LAUNCH(name) after it
 void timing_begin(cudaStream_t st);
 void timing_end(const char* name);
+void timing_work(const char* prefix, const char* skip, double bytes, double flops);   // algorithmic work of the next matching launch
 #define QUAN_TIMED(st) ::quan::timing_begin(st)
 
 #define QUAN_CHECK_LAUNCH(name)                                                     \

@@ -1371,6 +1371,11 @@ int quan_iqbn_finalize_partials(const void* workspace, int32_t nparts, double co
   return QUAN_OK;
 }
 
+// algorithmic bytes of an IQBN pass for the kernel-timing table: `passes` streams of the activation tensor
+static inline void announce_iqbn_work(int32_t B, int32_t C, int32_t H, int32_t W, int dtype, int passes) {
+  quan::timing_work("iqbn_", "iqbn_fold", (double)passes * 4.0 * B * C * (double)H * W * (dtype == QUAN_BF16 ? 2.0 : 4.0), 0.0);
+}
+
 int quan_iqbn_train_stats(const void* x, int32_t B, int32_t C, int32_t H, int32_t W, int dtype, int layout,
                           const float* gamma, const float* beta, float eps, float momentum, float* running_mean,
                           float* running_var, float* stats, void* workspace, size_t ws_bytes, void* stream) {
@@ -1387,6 +1392,7 @@ int quan_iqbn_train_stats(const void* x, int32_t B, int32_t C, int32_t H, int32_
   t.stats = stats;
   t.gamma = gamma;
   t.beta = beta;
+  announce_iqbn_work(B, C, H, W, dtype, 1);
   return reduce_entry(0, x, nullptr, B, C, H, W, dtype, layout, nullptr, nullptr, 0, t, workspace, ws_bytes, stream);
 }
 
@@ -1488,6 +1494,7 @@ int quan_iqbn_apply_fwd(const void* x, void* y, int32_t B, int32_t C, int32_t H,
   QUAN_REQUIRE(stats != nullptr, QUAN_E_ARG, "iqbn_apply_fwd: null stats");
   ApplyArgs a = {};
   a.gamma = gamma; a.beta = beta; a.stats = stats; a.C = C;
+  announce_iqbn_work(B, C, H, W, dtype, 2);
   return apply_entry(false, x, nullptr, y, B, C, H, W, dtype, layout, a, act, nullptr, stream);
 }
 
@@ -1512,6 +1519,7 @@ int quan_iqbn_bwd_reduce(const void* dy, const void* x, int32_t B, int32_t C, in
   t.count = count;
   t.gamma = gamma;
   t.beta = beta;
+  announce_iqbn_work(B, C, H, W, dtype, 2);
   return reduce_entry(1, x, dy, B, C, H, W, dtype, layout, gamma, beta, act, t, workspace, ws_bytes, stream);
 }
 
@@ -1526,6 +1534,7 @@ int quan_iqbn_bwd_apply(const void* dy, const void* x, void* dx, int32_t B, int3
   a.gamma = gamma; a.beta = beta; a.stats = stats; a.sums = sums; a.count = count;
   a.dgamma = dgamma; a.dbeta = dbeta; a.C = C;
   a.coefT = reinterpret_cast<const float*>(sums + 8 * (size_t)C);   // written by the bwd-reduce tail or quan_iqbn_bwd_coef
+  announce_iqbn_work(B, C, H, W, dtype, 3);
   return apply_entry(true, x, dy, dx, B, C, H, W, dtype, layout, a, act, mix_t, stream);
 }
 

@@ -95,6 +95,18 @@ static int get_fork_join(ForkJoin** out) {
   return QUAN_OK;
 }
 
+// Algorithmic work of one conv pass for the kernel-timing table (bench.py roofline): the separable FLOP count of SURVEY §8(d),
+// 4*2*B*Ho*Wo*Co*(Ci/g)*kH*kW, and the bytes a pass must move — both activation tensors it touches plus the four weight sets.
+static void announce_conv_work(const quan_conv_dims& d, int dtype, int pass) {
+  const double Ho = conv_out(d.H, d.kH, d.sH, d.pH, d.dH), Wo = conv_out(d.W, d.kW, d.sW, d.pW, d.dW);
+  const double esz = dtype == QUAN_BF16 ? 2.0 : 4.0;
+  const double flops = 8.0 * d.B * Ho * Wo * d.Co * (double)(d.Ci / d.groups) * d.kH * d.kW;
+  const double sx = 4.0 * d.B * d.Ci * (double)d.H * d.W * esz, sy = 4.0 * d.B * d.Co * Ho * Wo * esz;
+  const double sw = 4.0 * d.Co * (double)(d.Ci / d.groups) * d.kH * d.kW * 4.0;
+  (void)pass;
+  timing_work("qconv_", "qconv_bias_grad", sx + sy + sw, flops);
+}
+
 static int qconv2d_fwd_impl(const void* x, const float* const w[4], const float* bias_r, void* y, const quan_conv_dims* d,
                             int dtype, int layout, const float* mix, int algo, void* workspace, size_t ws_bytes,
                             void* stream, double* stat_part, int* stat_nparts) {
@@ -104,6 +116,7 @@ static int qconv2d_fwd_impl(const void* x, const float* const w[4], const float*
   QUAN_REQUIRE(x != nullptr && y != nullptr && w != nullptr && w[0] && w[1] && w[2] && w[3], QUAN_E_ARG,
                "qconv2d_fwd: null tensor pointer");
   cudaStream_t st = (cudaStream_t)stream;
+  announce_conv_work(*d, dtype, PASS_FWD);
   const int a = resolve_algo(*d, dtype, layout, PASS_FWD, algo);
   QUAN_REQUIRE(a > 0, QUAN_E_UNSUPPORTED, "qconv2d_fwd: requested engine does not serve this shape/layout");
   if (a == QUAN_ALGO_DEPTHWISE) return qconv_dw_fwd(x, w, bias_r, y, *d, dtype, mix, st);
@@ -200,6 +213,7 @@ static int qconv2d_bwd_impl(const void* dy, const void* x, const float* const w[
   }
 
   if (dx != nullptr) {
+    announce_conv_work(*d, dtype, PASS_DGRAD);
     if (a_dx == QUAN_ALGO_TCGEN05) {
       const size_t need = qconv_tc_workspace_bytes(*d, dtype, layout, PASS_DGRAD);
       QUAN_REQUIRE(tc_ws_bytes >= need, QUAN_E_WORKSPACE, "qconv2d_bwd: dgrad needs %zu more workspace bytes", need);
@@ -220,6 +234,7 @@ static int qconv2d_bwd_impl(const void* dy, const void* x, const float* const w[
     }
   }
   if (dw != nullptr) {
+    announce_conv_work(*d, dtype, PASS_WGRAD);
     if (a_dw == QUAN_ALGO_TCGEN05) {
       const size_t need = qconv_tc_workspace_bytes(*d, dtype, layout, PASS_WGRAD);
       QUAN_REQUIRE(wg_ws != nullptr && wg_ws_bytes >= need, QUAN_E_WORKSPACE, "qconv2d_bwd: wgrad needs %zu more workspace bytes", need);

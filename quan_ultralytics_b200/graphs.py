@@ -121,6 +121,8 @@ class GraphedTrainStep:
         torch.cuda.synchronize(dev)
         for p in self.params:
             p.grad = None
+        from . import _lib
+        n0 = _lib.load().quan_launch_count()
         # ---- capture 1: forward (and the loss, when it is capturable)
         self.g_fwd = torch.cuda.CUDAGraph()
         self.loss = self.aux = None
@@ -146,6 +148,7 @@ class GraphedTrainStep:
             self.opt.step()
         if grad_sync is not None:
             grad_sync.detach()
+        self.captured_launches = int(_lib.load().quan_launch_count() - n0)      # library kernels one step replays
 
     def _eager(self, loss_args):
         for p in self.params:

@@ -100,11 +100,18 @@ def test_yolo11n_obb_quan_train_step_matches_reference_fp32(fp32_exact, engine, 
     assert set(g_our) == set(g_ref)
     if engine == "direct":                       # exact-fp32 engine: every parameter gradient within the fp32 budget
         assert worst[0] <= tol, worst
-    else:                                        # tf32 tensor-core engine through ~90 batch-normalised layers
+    else:
+        # tf32 tensor-core engine through ~90 batch-normalised layers at a tiny batch (2 x 256^2: 128 samples per P5 channel) with
+        # discontinuous max-pools / top-k in the graph: the whole-model gradient is ill-conditioned.  The yardstick is the REFERENCE's
+        # own sensitivity to the same rounding: its PyTorch path with TF32 convolutions enabled against itself in exact fp32.
         l2, cos = _global(g_our, g_ref)
-        share = _share_within(g_our, g_ref, 1e-2)
-        print(f"tf32 engine: whole-gradient rel L2 {l2:.2e}, cosine {cos:.6f}, tensors within 1e-2: {100 * share:.1f}%")
-        assert l2 <= 2e-2 and cos >= 0.999 and share >= 0.9, (l2, cos, share)
+        torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = True
+        _, _, g_tf = _yolo_step(ref, batch)
+        torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+        l2_ref, cos_ref = _global(g_tf, g_ref)
+        print(f"tf32 engine: whole-gradient rel L2 {l2:.2e} (cosine {cos:.5f}); the reference's own TF32 path vs its fp32 path: "
+              f"{l2_ref:.2e} (cosine {cos_ref:.5f})")
+        assert l2 <= max(2e-2, 2.5 * l2_ref) and cos >= min(0.999, 1 - 4 * (1 - cos_ref)), (l2, cos, l2_ref, cos_ref)
 
 
 def test_yolo11n_obb_quan_train_step_bf16_autocast(fp32_exact):
@@ -117,9 +124,12 @@ def test_yolo11n_obb_quan_train_step_bf16_autocast(fp32_exact):
           f"worst grad {worst[0]:.2e} at {worst[1]}")
     assert abs(l_our - l_ref) <= 1e-2 * abs(l_ref)
     l2, cos = _global(g_our, g_ref)
-    share = _share_within(g_our, g_ref, 1e-1)
-    print(f"bf16: whole-gradient rel L2 {l2:.2e}, cosine {cos:.5f}, tensors within 1e-1: {100 * share:.1f}%")
-    assert l2 <= 0.2 and cos >= 0.98, (l2, cos, share)
+    # yardstick: the reference's own PyTorch path under the same bf16 autocast against its fp32 path (see the tf32 test above)
+    _, _, g_bf = _yolo_step(ref, batch, autocast=torch.bfloat16)
+    l2_ref, cos_ref = _global(g_bf, g_ref)
+    print(f"bf16: whole-gradient rel L2 {l2:.2e} (cosine {cos:.5f}); the reference's own bf16-autocast path vs its fp32 path: "
+          f"{l2_ref:.2e} (cosine {cos_ref:.5f})")
+    assert l2 <= max(5e-2, 1.5 * l2_ref) and cos >= min(0.995, 1 - 2 * (1 - cos_ref)), (l2, cos, l2_ref, cos_ref)
 
 
 @pytest.mark.parametrize("name,B,size,nc,engine,tol", [("qwrn16_2", 128, 32, 10, "direct", 1e-3), ("qwrn16_2", 128, 32, 10, "auto", 5e-3),
