@@ -198,9 +198,16 @@ class _IQBNEval(torch.autograd.Function):
         dy, _ = ops.as_layout(dy, layout)
         if dy.dtype != x.dtype:
             dy = dy.to(x.dtype)
-        dx = ops.iqbn_eval_bwd(dy, x, layout, g32, b32, rm, rv, eps, act)
-        # gamma/beta grads in eval mode are not needed by any QUAN training path (IQBN trains in train mode)
-        return dx, None, None, None, None, None, None
+        dx = ops.iqbn_eval_bwd(dy, x, layout, g32, b32, rm, rv, eps, act) if ctx.needs_input_grad[0] else None
+        dgamma = dbeta = None
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            # frozen-statistics fine-tuning: the reference's eval branch is plain autograd (conv.py:546-552) and does give
+            # dgamma = sum dz * xhat, dbeta = sum dz — the two sums of the training backward, taken with the running statistics
+            C_ = x.size(1)
+            sums = ops.iqbn_bwd_reduce(dy, x, layout, ops.iqbn_eval_stats(g32, b32, rm, rv, eps), g32, b32, act, 0.0)
+            dbeta = sums[:4 * C_].to(torch.float32).view(C_, 4)
+            dgamma = sums[4 * C_:8 * C_].to(torch.float32).view(C_, 4)
+        return dx, dgamma, dbeta, None, None, None, None
 
 
 def iqbn(x: torch.Tensor, gamma, beta, running_mean, running_var, training: bool, eps: float = 1e-5,

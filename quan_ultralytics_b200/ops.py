@@ -106,8 +106,15 @@ _ws_cache = {}
 _iqbn_ws_cache = {}
 
 
+def _ws_key(device: torch.device):
+    """Workspaces hold live intermediate data between the kernels of one call (G = M^T dY, packed weights, split-K partials, the
+    conv epilogue's IQBN partial sums): they are private to the (device, stream) a call runs on, so that side streams, loader
+    threads or an overlapped evaluation never share scratch memory with the training stream."""
+    return (device.type, device.index, torch.cuda.current_stream(device).cuda_stream)
+
+
 def _workspace(nbytes: int, device: torch.device) -> torch.Tensor:
-    key = (device.type, device.index)
+    key = _ws_key(device)
     buf = _ws_cache.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
@@ -116,7 +123,7 @@ def _workspace(nbytes: int, device: torch.device) -> torch.Tensor:
 
 
 def _iqbn_workspace(C_: int, device: torch.device) -> torch.Tensor:
-    key = (device.type, device.index, C_)
+    key = _ws_key(device) + (C_,)
     buf = _iqbn_ws_cache.get(key)
     if buf is None:
         n = _lib.load().quan_iqbn_workspace_bytes(C_)
@@ -577,3 +584,32 @@ def conv_block_eval_fwd(x: torch.Tensor, weights: Sequence[torch.Tensor], gamma,
                                        _ptr(y), C.byref(d), code, layout, C.cast(_mix_arg(mix_matrix), C.c_void_p), algo, eps,
                                        act, wsb.data_ptr(), wsb.numel(), _stream(x)), "quan_conv_block_eval_fwd")
     return out
+
+
+# ---- device activation -------------------------------------------------------------------------------------------------------------
+# The library launches on the calling thread's CURRENT device (raw pointers + a stream handle carry no device); a tensor on cuda:1
+# handed over while cuda:0 is current would meet the wrong stream table.  Every entry point that launches therefore runs under the
+# device of its first CUDA tensor argument; when that already is the current device (one process per GPU — the normal case) the guard
+# costs one integer comparison.  (C side: function attributes / occupancy answers are latched per device, common.cuh DeviceOnce.)
+def _device_guarded(fn):
+    import functools
+
+    @functools.wraps(fn)
+    def run(*args, **kwargs):
+        for a in args:
+            if isinstance(a, torch.Tensor):
+                if a.is_cuda and a.device.index != torch.cuda.current_device():
+                    with torch.cuda.device(a.device):
+                        return fn(*args, **kwargs)
+                break
+        return fn(*args, **kwargs)
+
+    return run
+
+
+for _name in ("poincare_fwd", "poincare_bwd", "convert_layout", "mix", "qupsample_fwd", "qupsample_bwd", "qmaxpool_fwd", "qmaxpool_bwd",
+              "qattention_fwd", "qattention_bwd", "iqbn_train_stats", "iqbn_partial_sums", "iqbn_finalize_stats", "iqbn_eval_stats",
+              "iqbn_apply_fwd", "iqbn_eval_fwd", "iqbn_bwd_reduce", "iqbn_bwd_coef", "iqbn_bwd_apply", "iqbn_eval_bwd", "qconv2d_fwd",
+              "iqbn_finalize_partials", "qconv2d_bwd", "conv_block_fwd", "conv_block_bwd", "conv_block_eval_fwd", "as_layout"):
+    globals()[_name] = _device_guarded(globals()[_name])
+del _name

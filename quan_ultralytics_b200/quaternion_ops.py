@@ -49,6 +49,15 @@ def _tensor_core_ok(x: torch.Tensor, w: torch.Tensor, stride, padding, dilation,
                                      LAYOUT_BHWQC, ps) == ALGO_TCGEN05 for ps in passes)
 
 
+def _from_half(t: torch.Tensor) -> torch.Tensor:
+    """fp16 at the boundary: the reference's `QConvFunction` casts its inputs to float16 under autocast
+    (quaternion_autograd_cuda.py:19, `custom_fwd(cast_inputs=torch.float16)`) and its kernels dispatch on half
+    (quaternion_ops.cu:780).  fp16 values are widened to fp32 storage and run on the fp32 path: the tensor core's tf32 operand
+    keeps 10 mantissa bits — exactly fp16's — so no input bit is lost (bf16 would drop three), accumulation is fp32 as in the
+    reference kernels, and results are rounded back to fp16 on the way out."""
+    return t.float() if t is not None and t.dtype == torch.float16 else t
+
+
 def _check_cuda(name: str, t: torch.Tensor) -> None:
     if not t.is_cuda:
         raise RuntimeError(f"{name} must be a CUDA tensor")          # quaternion_ops_py.cpp:69-81
@@ -65,6 +74,10 @@ def qconv_forward(input: torch.Tensor, weight_r, weight_i, weight_j, weight_k, b
         raise RuntimeError("If bias_r is None, bias_i, bias_j, and bias_k must also be None.")
     if bias_r is not None:
         _check_cuda("bias_r", bias_r)
+    if input.dtype == torch.float16:
+        y = qconv_forward(input.float(), _from_half(weight_r), _from_half(weight_i), _from_half(weight_j), _from_half(weight_k),
+                          _from_half(bias_r), None, None, None, stride, padding, dilation, groups)
+        return y.half()
     x = input.contiguous()
     if _tensor_core_ok(x, weight_r, stride, padding, dilation, groups, (0,)):
         y = ops.qconv2d_fwd(ops.convert_layout(x, LAYOUT_BHWQC), (weight_r, weight_i, weight_j, weight_k), bias_r, tuple(stride),
@@ -81,6 +94,11 @@ def qconv_backward(grad_output: torch.Tensor, input: torch.Tensor, weight_r, wei
     db_r is the autograd-correct sum_p M[p,0]·dY_p, not the reference kernel's raw sum dY_r (SURVEY §8(c) defect 3)."""
     _check_cuda("grad_output", grad_output)
     _check_cuda("Input", input)
+    if input.dtype == torch.float16:
+        ws16 = (weight_r, weight_i, weight_j, weight_k)
+        out = qconv_backward(grad_output.float(), input.float(), *[_from_half(w) for w in ws16], bias_defined, stride, padding,
+                             dilation, groups)
+        return [out[0].half()] + [g.to(w.dtype) for g, w in zip(out[1:5], ws16)] + [None if out[5] is None else out[5].to(weight_r.dtype)]
     x = input.contiguous()
     dy = grad_output.contiguous()
     if dy.dtype != x.dtype:
@@ -103,6 +121,8 @@ def iqbn_forward(input: torch.Tensor, gamma, beta, running_mean, running_var, ep
     for n, t in (("Input", input), ("Gamma", gamma), ("Beta", beta), ("Running mean", running_mean),
                  ("Running variance", running_var)):
         _check_cuda(n, t)
+    if input.dtype == torch.float16:
+        return iqbn_forward(input.float(), gamma, beta, running_mean, running_var, eps).half()
     x, layout = ops.as_layout(input)
     f = ops._f32c
     return ops.iqbn_eval_fwd(x, layout, f(gamma), f(beta), f(running_mean), f(running_var), float(eps), ACT_NONE)

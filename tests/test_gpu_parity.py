@@ -411,3 +411,85 @@ def test_qer_on_the_tensor_core_layout(dtype):
     ref.backward(dy)
     assert rel_err(x.grad, ref_in.grad.double().cpu().numpy()) <= tol
     assert rel_err(gw, m.output_proj.weight.grad.double().cpu().numpy()) <= tol
+
+
+# ---- round-2 additions: fp16 at the extension boundary, eval-mode IQBN parameter gradients, a second device ---------------------------
+@pytest.mark.gpu
+def test_extension_shim_accepts_fp16_like_the_reference_autocast_path():
+    """quaternion_autograd_cuda.py:19 casts QConvFunction's inputs to float16 under autocast; the shim must take them, compute with
+    fp32 accumulation and hand fp16 back (checked against the fp64 oracle on the same fp16-rounded values)."""
+    import numpy as np
+    from oracle import quan_oracle as O
+    from quan_ultralytics_b200 import quaternion_ops as shim
+    shim.set_mixing("B")
+    rng = np.random.default_rng(3)
+    x = torch.from_numpy(rng.normal(size=(2, 8, 9, 7, 4))).half().cuda()
+    ws = [torch.from_numpy(rng.normal(size=(6, 8, 3, 3)) * 0.2).half().cuda() for _ in range(4)]
+    dy = torch.from_numpy(rng.normal(size=(2, 6, 9, 7, 4))).half().cuda()
+    y = shim.qconv_forward(x, *ws, None, None, None, None, [1, 1], [1, 1], [1, 1], 1)
+    assert y.dtype == torch.float16 and y.is_contiguous()
+    g = shim.qconv_backward(dy, x, *ws, False, [1, 1], [1, 1], [1, 1], 1)
+    assert g[0].dtype == torch.float16 and g[1].dtype == torch.float16
+    n = lambda t: t.double().cpu().numpy()
+    y_ref = O.qconv2d_fwd(n(x), [n(w) for w in ws], None, 1, 1, 1, 1, O.M_B)
+    dx_ref, dw_ref, _ = O.qconv2d_bwd(n(dy), n(x), [n(w) for w in ws], 1, 1, 1, 1, O.M_B)
+    rel = lambda a, b: float(np.abs(n(a) - b).max() / np.abs(b).max())
+    assert rel(y, y_ref) <= 2e-3 and rel(g[0], dx_ref) <= 2e-3 and rel(g[1], dw_ref[0]) <= 2e-3      # fp16 output rounding: 2^-11
+    # the reference's own autograd bridge under autocast, unmodified, on top of the shim
+    with torch.autocast("cuda", dtype=torch.float16):
+        xx = x.float().requires_grad_(True)
+        y2 = shim.qconv_forward(xx.half(), *ws, None, None, None, None, [1, 1], [1, 1], [1, 1], 1)
+    assert y2.dtype == torch.float16
+    e = shim.iqbn_forward(x, torch.ones(8, 4, device="cuda"), torch.zeros(8, 4, device="cuda"), torch.zeros(8, 4, device="cuda"),
+                          torch.ones(8, 4, device="cuda"), 1e-5)
+    assert e.dtype == torch.float16 and rel(e, n(x) / np.sqrt(1 + 1e-5)) <= 2e-3
+    shim.set_mixing("B")
+
+
+@pytest.mark.gpu
+def test_eval_mode_iqbn_gives_parameter_gradients():
+    """conv.py:546-552 (the eval branch is plain autograd in the reference): gamma / beta gradients with frozen statistics."""
+    import quan_ultralytics_b200 as Q
+    torch.manual_seed(0)
+    bn = Q.IQBN(24).cuda().eval()
+    with torch.no_grad():
+        bn.running_mean.normal_(0, 0.3)
+        bn.running_var.uniform_(0.5, 2.0)
+        bn.gamma.normal_(1, 0.2)
+        bn.beta.normal_(0, 0.2)
+    x = torch.randn(3, 6, 5, 7, 4, device="cuda", requires_grad=True)
+    dy = torch.randn(3, 6, 5, 7, 4, device="cuda")
+    bn(x).backward(dy)
+    v = lambda t: t.detach().view(1, 6, 1, 1, 4)
+    xr = x.detach().clone().requires_grad_(True)
+    g, b = bn.gamma.detach().clone().requires_grad_(True), bn.beta.detach().clone().requires_grad_(True)
+    yr = (xr - v(bn.running_mean)) / torch.sqrt(v(bn.running_var) + bn.eps) * g.view(1, 6, 1, 1, 4) + b.view(1, 6, 1, 1, 4)
+    yr.backward(dy)
+    torch.testing.assert_close(x.grad, xr.grad, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(bn.gamma.grad, g.grad, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(bn.beta.grad, b.grad, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.gpu
+def test_ops_follow_the_tensor_device_and_stream():
+    """A model on cuda:1 while cuda:0 is current (needs 2 GPUs), and two streams on one device with private workspaces."""
+    import quan_ultralytics_b200 as Q
+    torch.manual_seed(0)
+    blk = Q.Conv(64, 64, 3, 1).cuda().train()
+    x = torch.randn(2, 16, 12, 12, 4, device="cuda")
+    y0 = blk(x)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        y1 = blk(x)
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(y0, y1, rtol=0, atol=0)
+    from quan_ultralytics_b200 import ops
+    assert len({k[2] for k in ops._ws_cache}) >= 2                     # one workspace per stream
+    if torch.cuda.device_count() >= 2:
+        blk1 = Q.Conv(64, 64, 3, 1).to("cuda:1").train()
+        blk1.load_state_dict(blk.state_dict())
+        assert torch.cuda.current_device() == 0
+        y2 = blk1(x.to("cuda:1"))
+        torch.testing.assert_close(y2.cpu(), y0.cpu(), rtol=1e-5, atol=1e-5)
