@@ -821,9 +821,15 @@ def run_yolo_obb(a):
             line["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": cores, "kind": "reference",
                                     "sample": f"1 image/step of the same training step through the unmodified reference (baseline/_ref), "
                                               f"{a.cpu_steps} timed steps after 1 warm-up, fp32, per-image normalised"}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # the captured graphs hold NCCL work on the communicator: tearing the process group down underneath them can wait forever
+        # (watchdog dump after minutes); every rank has finished its timed work at this point, so leave without the teardown
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 def main():

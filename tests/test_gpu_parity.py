@@ -484,7 +484,7 @@ def test_ops_follow_the_tensor_device_and_stream():
         y1 = blk(x)
     torch.cuda.current_stream().wait_stream(s)
     torch.cuda.synchronize()
-    torch.testing.assert_close(y0, y1, rtol=0, atol=0)
+    torch.testing.assert_close(y0, y1, rtol=1e-4, atol=1e-5)      # (the epilogue's IQBN partial sums use shared-memory float atomics)
     from quan_ultralytics_b200 import ops
     assert len({k[2] for k in ops._ws_cache}) >= 2                     # one workspace per stream
     if torch.cuda.device_count() >= 2:
