@@ -1149,7 +1149,11 @@ static int launch_igemm(const void* in, const void* wpacked, const float* bias, 
     const double cover = (double)s.Ho * s.Wo / ((double)tw8 * 8 * th16 * 16);
     halo_h = 16 + dhmax - dhmin;
     const size_t a_bytes = (size_t)halo_h * 16 * 128;
-    p.halo = env_halo && NQ == 4 && row_bytes == 128 && p.tt.ncls == 1 && s.sH == 1 && s.sW == 1 && p.tt.start[1] > 1 &&
+    // NQ = 1 (dense form of the narrow layers, 4*C_q real channels per 128-byte row = C_q 16 in bf16, k-blocks beyond that): the
+    // same kernel path; per-tap mode re-reads the activation tile once per filter tap through L2 -> SM (9x for 3x3), which is
+    // what bounds these HBM-sized layers.  QUAN_TC_HALO_DENSE=0 keeps them on the per-tap path.
+    static const int env_halo_dense = [] { const char* e = getenv("QUAN_TC_HALO_DENSE"); return e ? atoi(e) : 1; }();
+    p.halo = env_halo && (NQ == 4 || env_halo_dense) && row_bytes == 128 && p.tt.ncls == 1 && s.sH == 1 && s.sW == 1 && p.tt.start[1] > 1 &&
              8 + dwmax - dwmin <= 16 && halo_h <= 256 && 2 * a_bytes <= 96 * 1024 && cover >= 0.8;
     if (p.halo) {
       t.Wt = 8; t.Ht = 16; t.Bt = 1; t.tiles_w = tw8; t.tiles_h = th16; t.tiles_b = s.B;

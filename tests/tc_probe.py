@@ -42,6 +42,11 @@ CASES = [
     ("bf16_c16_c4_dense", "bf16", 4, 16, 4, 32, 32, 3, 1, 1, 1, True, "B"),
     ("tf32_c8_dense", "f32", 4, 8, 8, 32, 32, 3, 1, 1, 1, True, "B"),
     ("bf16_c16_persist_dense", "bf16", 40, 16, 16, 64, 64, 3, 1, 1, 1, False, "A"),
+    # dense form in halo mode (128-byte rows: C_q = 16 bf16 / 8 tf32; two k-blocks at C_q = 32), ragged 16 x 8 tiles, N != K
+    ("bf16_c32_dense_halo_2kb", "bf16", 6, 32, 32, 40, 24, 3, 1, 1, 1, False, "A"),
+    ("bf16_c16_c32_dense_halo_ragged", "bf16", 3, 16, 32, 30, 28, 3, 1, 1, 1, True, "B"),
+    ("bf16_c32_c16_dense_halo_k5", "bf16", 5, 32, 16, 32, 32, 5, 1, 2, 1, False, "A"),
+    ("tf32_c8_c16_dense_halo", "f32", 9, 8, 16, 48, 48, 3, 1, 1, 1, False, "A"),
     # strided dgrad as parity classes: odd image sizes (ragged class grids), dense and separable forms
     ("bf16_s2_odd", "bf16", 3, 32, 64, 15, 13, 3, 2, 1, 1, False, "A"),
     ("bf16_c64_s2_odd", "bf16", 5, 64, 128, 17, 19, 3, 2, 1, 1, True, "B"),
