@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include "../../include/quan_sm100.h"
 
 #define QUAN_NUM_SMS 148  // B200: 2 dies x 74 SMs; grids are sized in multiples of this.
@@ -174,6 +175,41 @@ struct DeviceOnce {
     return true;
   }
 };
+
+// ---- programmatic dependent launch (PDL) --------------------------------------------------------------------------------------
+// The narrow QUAN layers are chains of ~1000 kernels of 3-40 us per training step; between two dependent kernels of a stream (or of
+// a captured graph) the grid-launch latency is exposed.  Every kernel of the library starts with pdl_prologue(): it waits until the
+// preceding grid has completed and its writes are visible (griddepcontrol.wait — a no-op when the kernel was launched without the
+// attribute) and then lets ITS dependents be launched (griddepcontrol.launch_dependents), so the next kernel's CTAs are scheduled
+// and parked at their own wait while this one runs.  No kernel touches global memory before the wait: ordering is exactly stream
+// order.  Host side: QUAN_LAUNCH(...) = cudaLaunchKernelEx with programmaticStreamSerializationAllowed.  QUAN_PDL=0 disables.
+__device__ __forceinline__ void pdl_prologue() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+
+inline bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("QUAN_PDL"); return e == nullptr || atoi(e) != 0; }();
+  return on;
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#define QUAN_LAUNCH(kern, grid, block, smem, st, ...) (void)::quan::launch_pdl(kern, grid, block, smem, st, __VA_ARGS__)
 
 struct Mix16 {
   float m[16];

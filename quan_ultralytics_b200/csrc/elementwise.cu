@@ -12,6 +12,7 @@ namespace quan {
 template <typename T>
 __global__ void __launch_bounds__(256) poincare_fwd_kernel(const float* __restrict__ rgb, T* __restrict__ out,
                                                            int64_t HW, int64_t total) {
+  pdl_prologue();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += stride) {
     const int64_t b = p / HW, i = p - b * HW;
@@ -30,6 +31,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) poincare_bwd_kernel(const float* __restrict__ rgb,
                                                            const T* __restrict__ gout, float* __restrict__ grgb,
                                                            int64_t HW, int64_t total) {
+  pdl_prologue();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += stride) {
     const int64_t b = p / HW, i = p - b * HW;
@@ -54,6 +56,7 @@ __global__ void __launch_bounds__(256) poincare_bwd_kernel(const float* __restri
 template <typename T, int V, bool BWD>
 __global__ void __launch_bounds__(256) upsample_kernel(const T* __restrict__ src, T* __restrict__ dst,
                                                        int64_t outer, int H, int W, int inner_vecs, int s) {
+  pdl_prologue();
   // src/dst roles: FWD reads the small tensor and writes the big one; BWD reads big, writes small.
   const int64_t total = outer * H * W * inner_vecs;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -95,6 +98,7 @@ __global__ void __launch_bounds__(256) upsample_kernel(const T* __restrict__ src
 template <typename T>
 __global__ void __launch_bounds__(256) mix_a_kernel(const T* __restrict__ in, T* __restrict__ out, int64_t nquat,
                                                     Mix16 M) {
+  pdl_prologue();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < nquat; t += stride) {
     float v[4], o[4];
@@ -107,6 +111,7 @@ __global__ void __launch_bounds__(256) mix_a_kernel(const T* __restrict__ in, T*
 template <typename T, int V>
 __global__ void __launch_bounds__(256) mix_b_kernel(const T* __restrict__ in, T* __restrict__ out, int64_t rows,
                                                     int C, Mix16 M) {
+  pdl_prologue();
   const int chunks = C / V;
   const int64_t total = rows * chunks;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -132,6 +137,7 @@ __global__ void __launch_bounds__(256) mix_b_kernel(const T* __restrict__ in, T*
 // Tile = 32 channels x 32 pixels (x4 components), staged through padded shared memory so both sides are coalesced.
 template <typename T, bool A2B>
 __global__ void __launch_bounds__(256) layout_kernel(const T* __restrict__ src, T* __restrict__ dst, int C, int HW) {
+  pdl_prologue();
   __shared__ float tile[32][4][33];  // [c][q][pix] (+1 pad)
   const int b = blockIdx.z;
   const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
@@ -191,9 +197,9 @@ static int launch_upsample(const void* src, void* dst, int B, int C, int H, int 
   int grid = grid_for(total, 256, 8);
   switch (V) {
     case 8:
-      if constexpr (sizeof(T) == 2) upsample_kernel<T, 8, BWD><<<grid, 256, 0, st>>>(sp, dp, outer, H, W, inner_vecs, s);
+      if constexpr (sizeof(T) == 2) QUAN_LAUNCH((upsample_kernel<T, 8, BWD>), grid, 256, 0, st, sp, dp, outer, H, W, inner_vecs, s);
       break;
-    case 4: upsample_kernel<T, 4, BWD><<<grid, 256, 0, st>>>(sp, dp, outer, H, W, inner_vecs, s); break;
+    case 4: QUAN_LAUNCH((upsample_kernel<T, 4, BWD>), grid, 256, 0, st, sp, dp, outer, H, W, inner_vecs, s); break;
     default: set_error("upsample: unreachable vector width %d", V); return QUAN_E_UNSUPPORTED;
   }
   QUAN_CHECK_LAUNCH("upsample");
@@ -214,8 +220,8 @@ int quan_poincare_fwd(const float* rgb, void* out, int32_t B, int32_t H, int32_t
   int grid = grid_for(total, 256, 8);
   cudaStream_t st = (cudaStream_t)stream;
   QUAN_TIMED(st);
-  if (out_dtype == QUAN_F32) poincare_fwd_kernel<float><<<grid, 256, 0, st>>>(rgb, (float*)out, HW, total);
-  else poincare_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(rgb, (__nv_bfloat16*)out, HW, total);
+  if (out_dtype == QUAN_F32) QUAN_LAUNCH((poincare_fwd_kernel<float>), grid, 256, 0, st, rgb, (float*)out, HW, total);
+  else QUAN_LAUNCH((poincare_fwd_kernel<__nv_bfloat16>), grid, 256, 0, st, rgb, (__nv_bfloat16*)out, HW, total);
   QUAN_CHECK_LAUNCH("poincare_fwd");
   return QUAN_OK;
 }
@@ -229,9 +235,9 @@ int quan_poincare_bwd(const float* rgb, const void* grad_out, float* grad_rgb, i
   int grid = grid_for(total, 256, 8);
   cudaStream_t st = (cudaStream_t)stream;
   if (out_dtype == QUAN_F32)
-    poincare_bwd_kernel<float><<<grid, 256, 0, st>>>(rgb, (const float*)grad_out, grad_rgb, HW, total);
+    QUAN_LAUNCH((poincare_bwd_kernel<float>), grid, 256, 0, st, rgb, (const float*)grad_out, grad_rgb, HW, total);
   else
-    poincare_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(rgb, (const __nv_bfloat16*)grad_out, grad_rgb, HW, total);
+    QUAN_LAUNCH((poincare_bwd_kernel<__nv_bfloat16>), grid, 256, 0, st, rgb, (const __nv_bfloat16*)grad_out, grad_rgb, HW, total);
   QUAN_CHECK_LAUNCH("poincare_bwd");
   return QUAN_OK;
 }
@@ -268,24 +274,24 @@ int quan_mix(const void* in, void* out, int32_t B, int32_t C, int32_t H, int32_t
   if (layout == QUAN_LAYOUT_BCHWQ || C == 1) {
     const int64_t nquat = rows * C;
     int grid = grid_for(nquat, 256, 8);
-    if (dtype == QUAN_F32) mix_a_kernel<float><<<grid, 256, 0, st>>>((const float*)in, (float*)out, nquat, M);
-    else mix_a_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, nquat, M);
+    if (dtype == QUAN_F32) QUAN_LAUNCH((mix_a_kernel<float>), grid, 256, 0, st, (const float*)in, (float*)out, nquat, M);
+    else QUAN_LAUNCH((mix_a_kernel<__nv_bfloat16>), grid, 256, 0, st, (const __nv_bfloat16*)in, (__nv_bfloat16*)out, nquat, M);
   } else {
     if (dtype == QUAN_F32) {
       int V = largest_pow2_divisor(C, 4);
       int grid = grid_for(rows * (C / V), 256, 8);
-      if (V == 4) mix_b_kernel<float, 4><<<grid, 256, 0, st>>>((const float*)in, (float*)out, rows, C, M);
-      else if (V == 2) mix_b_kernel<float, 2><<<grid, 256, 0, st>>>((const float*)in, (float*)out, rows, C, M);
-      else mix_b_kernel<float, 1><<<grid, 256, 0, st>>>((const float*)in, (float*)out, rows, C, M);
+      if (V == 4) QUAN_LAUNCH((mix_b_kernel<float, 4>), grid, 256, 0, st, (const float*)in, (float*)out, rows, C, M);
+      else if (V == 2) QUAN_LAUNCH((mix_b_kernel<float, 2>), grid, 256, 0, st, (const float*)in, (float*)out, rows, C, M);
+      else QUAN_LAUNCH((mix_b_kernel<float, 1>), grid, 256, 0, st, (const float*)in, (float*)out, rows, C, M);
     } else {
       int V = largest_pow2_divisor(C, 8);
       int grid = grid_for(rows * (C / V), 256, 8);
       const __nv_bfloat16* ip = (const __nv_bfloat16*)in;
       __nv_bfloat16* op = (__nv_bfloat16*)out;
-      if (V == 8) mix_b_kernel<__nv_bfloat16, 8><<<grid, 256, 0, st>>>(ip, op, rows, C, M);
-      else if (V == 4) mix_b_kernel<__nv_bfloat16, 4><<<grid, 256, 0, st>>>(ip, op, rows, C, M);
-      else if (V == 2) mix_b_kernel<__nv_bfloat16, 2><<<grid, 256, 0, st>>>(ip, op, rows, C, M);
-      else mix_b_kernel<__nv_bfloat16, 1><<<grid, 256, 0, st>>>(ip, op, rows, C, M);
+      if (V == 8) QUAN_LAUNCH((mix_b_kernel<__nv_bfloat16, 8>), grid, 256, 0, st, ip, op, rows, C, M);
+      else if (V == 4) QUAN_LAUNCH((mix_b_kernel<__nv_bfloat16, 4>), grid, 256, 0, st, ip, op, rows, C, M);
+      else if (V == 2) QUAN_LAUNCH((mix_b_kernel<__nv_bfloat16, 2>), grid, 256, 0, st, ip, op, rows, C, M);
+      else QUAN_LAUNCH((mix_b_kernel<__nv_bfloat16, 1>), grid, 256, 0, st, ip, op, rows, C, M);
     }
   }
   QUAN_CHECK_LAUNCH("mix");
@@ -310,11 +316,11 @@ int quan_layout_convert(const void* src, int src_layout, void* dst, int dst_layo
   dim3 grid((HW + 31) / 32, (C + 31) / 32, B);
   const bool a2b = src_layout == QUAN_LAYOUT_BCHWQ;
   if (dtype == QUAN_F32) {
-    if (a2b) layout_kernel<float, true><<<grid, 256, 0, st>>>((const float*)src, (float*)dst, C, HW);
-    else layout_kernel<float, false><<<grid, 256, 0, st>>>((const float*)src, (float*)dst, C, HW);
+    if (a2b) QUAN_LAUNCH((layout_kernel<float, true>), grid, 256, 0, st, (const float*)src, (float*)dst, C, HW);
+    else QUAN_LAUNCH((layout_kernel<float, false>), grid, 256, 0, st, (const float*)src, (float*)dst, C, HW);
   } else {
-    if (a2b) layout_kernel<__nv_bfloat16, true><<<grid, 256, 0, st>>>((const __nv_bfloat16*)src, (__nv_bfloat16*)dst, C, HW);
-    else layout_kernel<__nv_bfloat16, false><<<grid, 256, 0, st>>>((const __nv_bfloat16*)src, (__nv_bfloat16*)dst, C, HW);
+    if (a2b) QUAN_LAUNCH((layout_kernel<__nv_bfloat16, true>), grid, 256, 0, st, (const __nv_bfloat16*)src, (__nv_bfloat16*)dst, C, HW);
+    else QUAN_LAUNCH((layout_kernel<__nv_bfloat16, false>), grid, 256, 0, st, (const __nv_bfloat16*)src, (__nv_bfloat16*)dst, C, HW);
   }
   QUAN_CHECK_LAUNCH("layout_convert");
   return QUAN_OK;

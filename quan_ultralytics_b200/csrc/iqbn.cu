@@ -119,6 +119,7 @@ __device__ __forceinline__ void finish_accumulator(const TailArgs& t, int i, dou
 // fold by shuffle (16 per warp) and a 16-entry shared-memory pass.  grid = ceil(4C / 2).
 constexpr int FOLD_ACC = 2, FOLD_LANES = 128;
 __global__ void __launch_bounds__(FOLD_ACC * FOLD_LANES) iqbn_fold_kernel(const double* __restrict__ part, int nparts, TailArgs t) {
+  pdl_prologue();
   __shared__ double red[2][FOLD_ACC * FOLD_LANES / 32][FOLD_ACC];
   const int n = 4 * t.C;
   const int il = threadIdx.x % FOLD_ACC, gl = threadIdx.x / FOLD_ACC;
@@ -212,6 +213,7 @@ template <typename T, int V, int MODE, int ACT, int U, bool FUSE>
 __global__ void __launch_bounds__(IQBN_RED_THREADS, 2) iqbn_reduce_b(const T* __restrict__ x, const T* __restrict__ dy, GeomB g,
                                                                       const float* __restrict__ gamma,
                                                                       const float* __restrict__ beta, IqbnWs ws, TailArgs tail) {
+  pdl_prologue();
   using VecT = Vec<T, V>;
   const int cvl = threadIdx.x % g.cvpg;
   const int rl = threadIdx.x / g.cvpg;
@@ -368,6 +370,7 @@ struct GeomT {
 template <typename T, int V, int MODE, int ACT>
 __global__ void __launch_bounds__(IQBN_TMA_THREADS, 2) iqbn_reduce_tma(const T* __restrict__ x, const T* __restrict__ dy,
                                                                         GeomT g, IqbnWs ws, TailArgs tail) {
+  pdl_prologue();
   extern __shared__ __align__(128) uint8_t tsm[];
   using VecT = Vec<T, V>;
   constexpr int NSTREAM = MODE == 1 ? 2 : 1;
@@ -622,6 +625,7 @@ __device__ __forceinline__ void write_param_grads(const ApplyArgs& a) {
 template <typename T, int V, int ACT, bool BWD, int U>
 __global__ void __launch_bounds__(256, BWD ? 3 : 4) iqbn_apply_b(const T* __restrict__ x, const T* __restrict__ dy,
                                                     T* __restrict__ out, GeomB g, ApplyArgs a) {
+  pdl_prologue();
   const int cvl = threadIdx.x % g.cvpg;
   const int rl = threadIdx.x / g.cvpg;
   const int cv = blockIdx.y * g.cvpg + cvl;
@@ -705,6 +709,7 @@ struct GeomW {
 template <typename T, int V, int ACT, int U>
 __global__ void __launch_bounds__(256, 2) iqbn_apply_bwd_mix_b(const T* __restrict__ x, const T* __restrict__ dy,
                                                               T* __restrict__ out, GeomW g, ApplyArgs a, Mix16 mt) {
+  pdl_prologue();
   using VecT = Vec<T, V>;
   const int slot = threadIdx.x / (4 * g.gl), ls = threadIdx.x % (4 * g.gl);
   const int q = ls / g.gl, j = ls - q * g.gl;
@@ -770,6 +775,7 @@ struct GeomTW {
 template <typename T, int V, int ACT, bool MIX>
 __global__ void __launch_bounds__(IQBN_TMA_THREADS, 2) iqbn_apply_bwd_tma(const T* __restrict__ x, const T* __restrict__ dy,
                                                                            T* __restrict__ out, GeomTW g, ApplyArgs a, Mix16 mt) {
+  pdl_prologue();
   extern __shared__ __align__(128) uint8_t tsm[];
   using VecT = Vec<T, V>;
   const uint32_t tile_bytes = (uint32_t)g.tile_rows * g.L * sizeof(T);
@@ -882,6 +888,7 @@ template <typename T, int V, int MODE, int ACT>
 __global__ void __launch_bounds__(256) iqbn_reduce_a(const T* __restrict__ x, const T* __restrict__ dy, GeomA g,
                                                      const float* __restrict__ gamma,
                                                      const float* __restrict__ beta, IqbnWs ws, TailArgs tail) {
+  pdl_prologue();
   static_assert(V == 4 || V == 8, "a vector holds whole quaternions");
   const int c = blockIdx.y;
   float scale[4], shift[4];
@@ -966,6 +973,7 @@ __global__ void __launch_bounds__(256) iqbn_reduce_a(const T* __restrict__ x, co
 template <typename T, int V, int ACT, bool BWD, bool MIX>
 __global__ void __launch_bounds__(256) iqbn_apply_a(const T* __restrict__ x, const T* __restrict__ dy,
                                                     T* __restrict__ out, GeomA g, ApplyArgs a, Mix16 mix) {
+  pdl_prologue();
   const int c = blockIdx.y;
   float scale[4], shift[4], k1[4], k2[4], k3[4];
 #pragma unroll
@@ -1105,7 +1113,7 @@ static int launch_reduce_b(dim3 grid, dim3 block, cudaStream_t st, const T* xp, 
     *fused = true;
     return QUAN_OK;
   }
-  iqbn_reduce_b<T, V, MODE, ACT, U, false><<<grid, block, 0, st>>>(xp, dyp, g, gamma, beta, ws, tail);
+  QUAN_LAUNCH((iqbn_reduce_b<T, V, MODE, ACT, U, false>), grid, block, 0, st, xp, dyp, g, gamma, beta, ws, tail);
   *fused = false;
   return QUAN_OK;
 }
@@ -1147,13 +1155,13 @@ static int launch_reduce(const void* x, const void* dy, int B, int C, int H, int
 #define QUAN_REDUCE_T(VV) { auto kern = iqbn_reduce_tma<T, VV, MODE, ACT>;                                                  \
             static thread_local DeviceOnce attr;                                                                        \
             if (attr.first()) { QUAN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)); } \
-            kern<<<grid, IQBN_TMA_THREADS, smem, st>>>(xp, dyp, g, ws, tail); }
+            QUAN_LAUNCH((kern), grid, IQBN_TMA_THREADS, smem, st, xp, dyp, g, ws, tail); }
           if (Vt * sizeof(T) == 16) { if constexpr (sizeof(T) == 2) QUAN_REDUCE_T(8) else QUAN_REDUCE_T(4) }
           else { if constexpr (sizeof(T) == 2) QUAN_REDUCE_T(4) else QUAN_REDUCE_T(2) }
 #undef QUAN_REDUCE_T
           QUAN_CHECK_LAUNCH(MODE == 0 ? "iqbn_reduce_fwd" : "iqbn_reduce_bwd");
           QUAN_TIMED(st);
-          iqbn_fold_kernel<<<(4 * C + FOLD_ACC - 1) / FOLD_ACC, FOLD_ACC * FOLD_LANES, 0, st>>>(ws.part, nparts, tail);
+          QUAN_LAUNCH((iqbn_fold_kernel), (4 * C + FOLD_ACC - 1) / FOLD_ACC, FOLD_ACC * FOLD_LANES, 0, st, ws.part, nparts, tail);
           QUAN_CHECK_LAUNCH("iqbn_fold");
           return QUAN_OK;
         }
@@ -1187,14 +1195,14 @@ static int launch_reduce(const void* x, const void* dy, int B, int C, int H, int
     nparts = (int)p.grid.x;
     if (p.V == 8) {
       if constexpr (sizeof(T) == 2)
-        iqbn_reduce_a<T, 8, MODE, ACT><<<p.grid, p.block, 0, st>>>(xp, dyp, p.g, gamma, beta, ws, tail);
+        QUAN_LAUNCH((iqbn_reduce_a<T, 8, MODE, ACT>), p.grid, p.block, 0, st, xp, dyp, p.g, gamma, beta, ws, tail);
     } else {
-      iqbn_reduce_a<T, 4, MODE, ACT><<<p.grid, p.block, 0, st>>>(xp, dyp, p.g, gamma, beta, ws, tail);
+      QUAN_LAUNCH((iqbn_reduce_a<T, 4, MODE, ACT>), p.grid, p.block, 0, st, xp, dyp, p.g, gamma, beta, ws, tail);
     }
   }
   QUAN_CHECK_LAUNCH(MODE == 0 ? "iqbn_reduce_fwd" : "iqbn_reduce_bwd");
   QUAN_TIMED(st);
-  iqbn_fold_kernel<<<(4 * C + FOLD_ACC - 1) / FOLD_ACC, FOLD_ACC * FOLD_LANES, 0, st>>>(ws.part, nparts, tail);
+  QUAN_LAUNCH((iqbn_fold_kernel), (4 * C + FOLD_ACC - 1) / FOLD_ACC, FOLD_ACC * FOLD_LANES, 0, st, ws.part, nparts, tail);
   QUAN_CHECK_LAUNCH("iqbn_fold");
   return QUAN_OK;
 }
@@ -1238,12 +1246,12 @@ static int launch_apply(const void* x, const void* dy, void* out, int B, int C, 
             auto kern = iqbn_apply_bwd_tma<T, VT, ACT, true>;
             static thread_local DeviceOnce attr;
             if (attr.first()) { QUAN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)); }
-            kern<<<grid, IQBN_TMA_THREADS, smem, st>>>(xp, dyp, op, g, a, mt);
+            QUAN_LAUNCH((kern), grid, IQBN_TMA_THREADS, smem, st, xp, dyp, op, g, a, mt);
           } else {
             auto kern = iqbn_apply_bwd_tma<T, VT, ACT, false>;
             static thread_local DeviceOnce attr;
             if (attr.first()) { QUAN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024)); }
-            kern<<<grid, IQBN_TMA_THREADS, smem, st>>>(xp, dyp, op, g, a, mt);
+            QUAN_LAUNCH((kern), grid, IQBN_TMA_THREADS, smem, st, xp, dyp, op, g, a, mt);
           }
           QUAN_CHECK_LAUNCH(mix_t != nullptr ? "iqbn_apply_bwd_mix" : "iqbn_apply_bwd");
           return QUAN_OK;
@@ -1259,8 +1267,8 @@ static int launch_apply(const void* x, const void* dy, void* out, int B, int C, 
         if (want > cap) want = cap;
         if (want < 1) want = 1;
         QUAN_TIMED(st);
-        QUAN_DISPATCH_V(Vw, (iqbn_apply_bwd_mix_b<T, (sizeof(T) == 4 && kV == 8) ? 4 : kV, ACT, 2>
-                             <<<(unsigned)want, 256, 0, st>>>(xp, dyp, op, gw, a, mt)));
+        QUAN_DISPATCH_V(Vw, QUAN_LAUNCH((iqbn_apply_bwd_mix_b<T, (sizeof(T) == 4 && kV == 8) ? 4 : kV, ACT, 2>), (unsigned)want, 256, 0, st,
+                                        xp, dyp, op, gw, a, mt));
         QUAN_CHECK_LAUNCH("iqbn_apply_bwd_mix");
         return QUAN_OK;
       }
@@ -1272,8 +1280,8 @@ static int launch_apply(const void* x, const void* dy, void* out, int B, int C, 
       return QUAN_E_UNSUPPORTED;
     }
     QUAN_TIMED(st);
-#define QUAN_APPLY_B(UU) QUAN_DISPATCH_V(p.V, (iqbn_apply_b<T, (sizeof(T) == 4 && kV == 8) ? 4 : kV, ACT, BWD, UU> \
-                          <<<p.grid, p.block, 0, st>>>(xp, dyp, op, p.g, a)))
+#define QUAN_APPLY_B(UU) QUAN_DISPATCH_V(p.V, QUAN_LAUNCH((iqbn_apply_b<T, (sizeof(T) == 4 && kV == 8) ? 4 : kV, ACT, BWD, UU>), p.grid, \
+                                              p.block, 0, st, xp, dyp, op, p.g, a))
     switch (U) {
       case 1: QUAN_APPLY_B(1); break;
       case 2: QUAN_APPLY_B(2); break;
@@ -1293,12 +1301,12 @@ static int launch_apply(const void* x, const void* dy, void* out, int B, int C, 
     if (use_mix) m = make_mix(mix_t);
     if (p.V == 8) {
       if constexpr (sizeof(T) == 2) {
-        if (use_mix) iqbn_apply_a<T, 8, ACT, BWD, BWD><<<p.grid, p.block, 0, st>>>(xp, dyp, op, p.g, a, m);
-        else iqbn_apply_a<T, 8, ACT, BWD, false><<<p.grid, p.block, 0, st>>>(xp, dyp, op, p.g, a, m);
+        if (use_mix) QUAN_LAUNCH((iqbn_apply_a<T, 8, ACT, BWD, BWD>), p.grid, p.block, 0, st, xp, dyp, op, p.g, a, m);
+        else QUAN_LAUNCH((iqbn_apply_a<T, 8, ACT, BWD, false>), p.grid, p.block, 0, st, xp, dyp, op, p.g, a, m);
       }
     } else {
-      if (use_mix) iqbn_apply_a<T, 4, ACT, BWD, BWD><<<p.grid, p.block, 0, st>>>(xp, dyp, op, p.g, a, m);
-      else iqbn_apply_a<T, 4, ACT, BWD, false><<<p.grid, p.block, 0, st>>>(xp, dyp, op, p.g, a, m);
+      if (use_mix) QUAN_LAUNCH((iqbn_apply_a<T, 4, ACT, BWD, BWD>), p.grid, p.block, 0, st, xp, dyp, op, p.g, a, m);
+      else QUAN_LAUNCH((iqbn_apply_a<T, 4, ACT, BWD, false>), p.grid, p.block, 0, st, xp, dyp, op, p.g, a, m);
     }
     QUAN_CHECK_LAUNCH("iqbn_apply_a");
   }
@@ -1366,7 +1374,7 @@ int quan_iqbn_finalize_partials(const void* workspace, int32_t nparts, double co
   t.beta = beta;
   cudaStream_t st = (cudaStream_t)stream;
   QUAN_TIMED(st);
-  iqbn_fold_kernel<<<(4 * C + FOLD_ACC - 1) / FOLD_ACC, FOLD_ACC * FOLD_LANES, 0, st>>>(reinterpret_cast<const double*>(workspace), nparts, t);
+  QUAN_LAUNCH((iqbn_fold_kernel), (4 * C + FOLD_ACC - 1) / FOLD_ACC, FOLD_ACC * FOLD_LANES, 0, st, reinterpret_cast<const double*>(workspace), nparts, t);
   QUAN_CHECK_LAUNCH("iqbn_fold");
   return QUAN_OK;
 }
@@ -1410,6 +1418,7 @@ namespace quan {
 // 2: backward coefficient table from all-reduced backward sums
 __global__ void iqbn_small_kernel(int mode, const double* __restrict__ sums, const float* __restrict__ rm,
                                   const float* __restrict__ rv, TailArgs t) {
+  pdl_prologue();
   const int n = 4 * t.C;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     if (mode == 0) {
@@ -1437,7 +1446,7 @@ __global__ void iqbn_small_kernel(int mode, const double* __restrict__ sums, con
 }
 static int launch_small(int mode, const double* sums, const float* rm, const float* rv, const TailArgs& t, void* stream) {
   int threads = 128, blocks = (4 * t.C + threads - 1) / threads;
-  iqbn_small_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(mode, sums, rm, rv, t);
+  QUAN_LAUNCH((iqbn_small_kernel), blocks, threads, 0, (cudaStream_t)stream, mode, sums, rm, rv, t);
   QUAN_CHECK_LAUNCH("iqbn_small_kernel");
   return QUAN_OK;
 }

@@ -36,6 +36,7 @@ __device__ __forceinline__ double block_sum(double v, double* sh) {
 }
 
 __global__ void __launch_bounds__(OPT_THREADS) sgd_sqnorm_kernel(const quan_opt_chunk* __restrict__ tab, double* __restrict__ partial) {
+  pdl_prologue();
   __shared__ double sh[OPT_THREADS / 32];
   const quan_opt_chunk c = tab[blockIdx.x];
   const float* g = reinterpret_cast<const float*>(c.g);
@@ -60,6 +61,7 @@ __global__ void __launch_bounds__(OPT_THREADS) sgd_update_kernel(const quan_opt_
                                                                  float* __restrict__ mom, const float* __restrict__ hyper, int ngroups,
                                                                  const double* __restrict__ partial, float* __restrict__ total_norm_out,
                                                                  int zero_grad) {
+  pdl_prologue();
   __shared__ double sh[OPT_THREADS / 32];
   double s = 0.0;
   for (int i = threadIdx.x; i < nchunks; i += OPT_THREADS) s += partial[i];
@@ -93,6 +95,7 @@ __global__ void __launch_bounds__(OPT_THREADS) sgd_update_kernel(const quan_opt_
 // ---- EMA of the parameters / float buffers (ultralytics/utils/torch_utils.py:514-525 ModelEMA.update): e = d e + (1 - d) v
 __global__ void __launch_bounds__(OPT_THREADS) ema_update_kernel(const quan_opt_chunk* __restrict__ tab, float* __restrict__ ema,
                                                                  const float* __restrict__ decay) {
+  pdl_prologue();
   const quan_opt_chunk c = tab[blockIdx.x];
   const float d = *decay;
   const float* v = reinterpret_cast<const float*>(c.p);
@@ -113,10 +116,10 @@ int quan_sgd_clip_step(const void* chunk_table, int nchunks, float* momentum_buf
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const quan_opt_chunk* tab = reinterpret_cast<const quan_opt_chunk*>(chunk_table);
   QUAN_TIMED(st);
-  sgd_sqnorm_kernel<<<nchunks, OPT_THREADS, 0, st>>>(tab, partial);
+  QUAN_LAUNCH((sgd_sqnorm_kernel), nchunks, OPT_THREADS, 0, st, tab, partial);
   QUAN_CHECK_LAUNCH("sgd_sqnorm");
   QUAN_TIMED(st);
-  sgd_update_kernel<<<nchunks, OPT_THREADS, 0, st>>>(tab, nchunks, momentum_buf, hyper, ngroups, partial, total_norm_out, zero_grad);
+  QUAN_LAUNCH((sgd_update_kernel), nchunks, OPT_THREADS, 0, st, tab, nchunks, momentum_buf, hyper, ngroups, partial, total_norm_out, zero_grad);
   QUAN_CHECK_LAUNCH("sgd_update");
   return QUAN_OK;
 }
@@ -128,7 +131,7 @@ int quan_ema_update(const void* chunk_table, int nchunks, float* ema_buf, const 
   QUAN_REQUIRE(chunk_table && ema_buf && decay, QUAN_E_ARG, "quan_ema_update: null pointer");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   QUAN_TIMED(st);
-  ema_update_kernel<<<nchunks, OPT_THREADS, 0, st>>>(reinterpret_cast<const quan_opt_chunk*>(chunk_table), ema_buf, decay);
+  QUAN_LAUNCH((ema_update_kernel), nchunks, OPT_THREADS, 0, st, reinterpret_cast<const quan_opt_chunk*>(chunk_table), ema_buf, decay);
   QUAN_CHECK_LAUNCH("ema_update");
   return QUAN_OK;
 }

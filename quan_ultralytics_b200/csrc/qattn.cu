@@ -43,6 +43,7 @@ __device__ __forceinline__ float fast_exp2(float x) {
 template <typename T, int K, int V>
 __global__ void __launch_bounds__(QA_THREADS) qattn_fwd_kernel(const T* __restrict__ qkv, T* __restrict__ o, float* __restrict__ lse,
                                                                QaGeom g) {
+  pdl_prologue();
   constexpr int QA_TILE = QaTile<K, V>::n;
   __shared__ float Ks[QA_TILE * K];
   __shared__ float Vs[QA_TILE * V];
@@ -113,6 +114,7 @@ template <typename T, int K, int V>
 __global__ void __launch_bounds__(QA_THREADS) qattn_bwd_dq_kernel(const T* __restrict__ qkv, const T* __restrict__ o,
                                                                   const T* __restrict__ d_o, const float* __restrict__ lse,
                                                                   T* __restrict__ dqkv, QaGeom g) {
+  pdl_prologue();
   constexpr int QA_TILE = QaTile<K, V>::n;
   __shared__ float Ks[QA_TILE * K];
   __shared__ float Vs[QA_TILE * V];
@@ -164,6 +166,7 @@ template <typename T, int K, int V>
 __global__ void __launch_bounds__(QA_THREADS) qattn_bwd_dkv_kernel(const T* __restrict__ qkv, const T* __restrict__ o,
                                                                    const T* __restrict__ d_o, const float* __restrict__ lse,
                                                                    T* __restrict__ dqkv, QaGeom g) {
+  pdl_prologue();
   constexpr int R = K + V + 2;
   constexpr int QA_TILE = QaTile<K, V>::n;
   __shared__ float Qs[QA_TILE * R];      // per query: q[K] (pre-scaled), dO[V], lse, D
@@ -223,14 +226,14 @@ static int qattn_launch(bool bwd, const void* qkv, const void* o, const void* d_
   dim3 grid((g.N + QA_THREADS - 1) / QA_THREADS, g.B * 4 * g.heads);
   if (!bwd) {
     QUAN_TIMED(st);
-    qattn_fwd_kernel<T, K, V><<<grid, QA_THREADS, 0, st>>>((const T*)qkv, (T*)out, lse, g);
+    QUAN_LAUNCH((qattn_fwd_kernel<T, K, V>), grid, QA_THREADS, 0, st, (const T*)qkv, (T*)out, lse, g);
     QUAN_CHECK_LAUNCH("qattn_fwd");
   } else {
     QUAN_TIMED(st);
-    qattn_bwd_dq_kernel<T, K, V><<<grid, QA_THREADS, 0, st>>>((const T*)qkv, (const T*)o, (const T*)d_o, lse, (T*)out, g);
+    QUAN_LAUNCH((qattn_bwd_dq_kernel<T, K, V>), grid, QA_THREADS, 0, st, (const T*)qkv, (const T*)o, (const T*)d_o, lse, (T*)out, g);
     QUAN_CHECK_LAUNCH("qattn_bwd_dq");
     QUAN_TIMED(st);
-    qattn_bwd_dkv_kernel<T, K, V><<<grid, QA_THREADS, 0, st>>>((const T*)qkv, (const T*)o, (const T*)d_o, lse, (T*)out, g);
+    QUAN_LAUNCH((qattn_bwd_dkv_kernel<T, K, V>), grid, QA_THREADS, 0, st, (const T*)qkv, (const T*)o, (const T*)d_o, lse, (T*)out, g);
     QUAN_CHECK_LAUNCH("qattn_bwd_dkv");
   }
   return QUAN_OK;

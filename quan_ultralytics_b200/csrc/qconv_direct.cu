@@ -65,6 +65,7 @@ __device__ __forceinline__ void store_quat(T* __restrict__ p, int b, int c, int 
 template <typename T, int LAYOUT, int COT>
 __global__ void __launch_bounds__(128) qconv_fwd_direct(const T* __restrict__ x, W4 w, const float* __restrict__ bias_r,
                                                         T* __restrict__ y, ConvGeom g, Mix16 M, int cib) {
+  pdl_prologue();
   extern __shared__ float4 wsm[];  // [cib][taps][COT]
   const int taps = g.kH * g.kW;
   const int chunks_per_group = (g.Cog + COT - 1) / COT;
@@ -145,6 +146,7 @@ __global__ void __launch_bounds__(128) qconv_fwd_direct(const T* __restrict__ x,
 template <typename T, int LAYOUT, int CIT>
 __global__ void __launch_bounds__(128) qconv_dgrad_direct(const T* __restrict__ gq, W4 w, T* __restrict__ dx,
                                                           ConvGeom g, int cob) {
+  pdl_prologue();
   extern __shared__ float4 wsm[];  // [cob][taps][CIT]
   const int taps = g.kH * g.kW;
   const int chunks_per_group = (g.Cig + CIT - 1) / CIT;
@@ -228,6 +230,7 @@ __global__ void __launch_bounds__(128) qconv_wgrad_direct(const T* __restrict__ 
                                                           float* __restrict__ dw0, float* __restrict__ dw1,
                                                           float* __restrict__ dw2, float* __restrict__ dw3,
                                                           ConvGeom g, int64_t pix_per_split) {
+  pdl_prologue();
   const int taps = g.kH * g.kW;
   const int64_t nelem = (int64_t)g.Co * g.Cig * taps;
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -270,6 +273,7 @@ __global__ void __launch_bounds__(128) qconv_wgrad_direct(const T* __restrict__ 
 // bias grad: db_r[co] = sum over pixels of G_r.  grid = (Co, splits), fp32 atomics into zeroed db.
 template <typename T, int LAYOUT>
 __global__ void __launch_bounds__(256) qconv_bias_grad(const T* __restrict__ gq, float* __restrict__ db, ConvGeom g) {
+  pdl_prologue();
   const int co = blockIdx.x;
   const int64_t npix = (int64_t)g.B * g.Ho * g.Wo;
   const int64_t hw = (int64_t)g.Ho * g.Wo;
@@ -299,6 +303,7 @@ __global__ void __launch_bounds__(256) qconv_bias_grad(const T* __restrict__ gq,
 // per step under ncu.)
 template <typename T, int V>
 __global__ void __launch_bounds__(256) qconv_bias_grad_rows(const T* __restrict__ gq, float* __restrict__ db, int64_t npix, int Co) {
+  pdl_prologue();
   __shared__ float red[256][V + 1];
   const int cvs = Co / V;
   const int lanes = blockDim.x / cvs;
@@ -351,10 +356,10 @@ static int fwd_direct_t(const void* x, const float* const w[4], const float* bia
   const T* xp = (const T*)x;
   T* yp = (T*)y;
   switch (cot) {
-    case 8: qconv_fwd_direct<T, LAYOUT, 8><<<grid, 128, smem, st>>>(xp, w4, bias_r, yp, g, M, cib); break;
-    case 4: qconv_fwd_direct<T, LAYOUT, 4><<<grid, 128, smem, st>>>(xp, w4, bias_r, yp, g, M, cib); break;
-    case 2: qconv_fwd_direct<T, LAYOUT, 2><<<grid, 128, smem, st>>>(xp, w4, bias_r, yp, g, M, cib); break;
-    default: qconv_fwd_direct<T, LAYOUT, 1><<<grid, 128, smem, st>>>(xp, w4, bias_r, yp, g, M, cib); break;
+    case 8: QUAN_LAUNCH((qconv_fwd_direct<T, LAYOUT, 8>), grid, 128, smem, st, xp, w4, bias_r, yp, g, M, cib); break;
+    case 4: QUAN_LAUNCH((qconv_fwd_direct<T, LAYOUT, 4>), grid, 128, smem, st, xp, w4, bias_r, yp, g, M, cib); break;
+    case 2: QUAN_LAUNCH((qconv_fwd_direct<T, LAYOUT, 2>), grid, 128, smem, st, xp, w4, bias_r, yp, g, M, cib); break;
+    default: QUAN_LAUNCH((qconv_fwd_direct<T, LAYOUT, 1>), grid, 128, smem, st, xp, w4, bias_r, yp, g, M, cib); break;
   }
   QUAN_CHECK_LAUNCH("qconv_fwd_direct");
   return QUAN_OK;
@@ -378,10 +383,10 @@ static int dgrad_direct_t(const void* gq, const float* const w[4], void* dx, con
   const T* gp = (const T*)gq;
   T* dp = (T*)dx;
   switch (cit) {
-    case 8: qconv_dgrad_direct<T, LAYOUT, 8><<<grid, 128, smem, st>>>(gp, w4, dp, g, cob); break;
-    case 4: qconv_dgrad_direct<T, LAYOUT, 4><<<grid, 128, smem, st>>>(gp, w4, dp, g, cob); break;
-    case 2: qconv_dgrad_direct<T, LAYOUT, 2><<<grid, 128, smem, st>>>(gp, w4, dp, g, cob); break;
-    default: qconv_dgrad_direct<T, LAYOUT, 1><<<grid, 128, smem, st>>>(gp, w4, dp, g, cob); break;
+    case 8: QUAN_LAUNCH((qconv_dgrad_direct<T, LAYOUT, 8>), grid, 128, smem, st, gp, w4, dp, g, cob); break;
+    case 4: QUAN_LAUNCH((qconv_dgrad_direct<T, LAYOUT, 4>), grid, 128, smem, st, gp, w4, dp, g, cob); break;
+    case 2: QUAN_LAUNCH((qconv_dgrad_direct<T, LAYOUT, 2>), grid, 128, smem, st, gp, w4, dp, g, cob); break;
+    default: QUAN_LAUNCH((qconv_dgrad_direct<T, LAYOUT, 1>), grid, 128, smem, st, gp, w4, dp, g, cob); break;
   }
   QUAN_CHECK_LAUNCH("qconv_dgrad_direct");
   return QUAN_OK;
@@ -404,7 +409,7 @@ static int wgrad_direct_t(const void* gq, const void* x, float* const dw[4], con
   splits = ceil_div64(npix, pps);
   dim3 grid((unsigned)eblocks, (unsigned)splits);
   QUAN_TIMED(st);
-  qconv_wgrad_direct<T, LAYOUT><<<grid, 128, 0, st>>>((const T*)gq, (const T*)x, dw[0], dw[1], dw[2], dw[3], g, pps);
+  QUAN_LAUNCH((qconv_wgrad_direct<T, LAYOUT>), grid, 128, 0, st, (const T*)gq, (const T*)x, dw[0], dw[1], dw[2], dw[3], g, pps);
   QUAN_CHECK_LAUNCH("qconv_wgrad_direct");
   return QUAN_OK;
 }
@@ -422,8 +427,8 @@ static int bias_grad_t(const void* gq, float* db, const ConvGeom& g, cudaStream_
       if (blocks > QUAN_NUM_SMS * 4) blocks = QUAN_NUM_SMS * 4;
       if (blocks < 1) blocks = 1;
       QUAN_TIMED(st);
-      if (V == VMAX) qconv_bias_grad_rows<T, VMAX><<<(unsigned)blocks, 256, 0, st>>>((const T*)gq, db, npix, g.Co);
-      else qconv_bias_grad_rows<T, VMAX / 2><<<(unsigned)blocks, 256, 0, st>>>((const T*)gq, db, npix, g.Co);
+      if (V == VMAX) QUAN_LAUNCH((qconv_bias_grad_rows<T, VMAX>), (unsigned)blocks, 256, 0, st, (const T*)gq, db, npix, g.Co);
+      else QUAN_LAUNCH((qconv_bias_grad_rows<T, VMAX / 2>), (unsigned)blocks, 256, 0, st, (const T*)gq, db, npix, g.Co);
       QUAN_CHECK_LAUNCH("qconv_bias_grad");
       return QUAN_OK;
     }
@@ -433,7 +438,7 @@ static int bias_grad_t(const void* gq, float* db, const ConvGeom& g, cudaStream_
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
   dim3 grid((unsigned)g.Co, (unsigned)splits);
-  qconv_bias_grad<T, LAYOUT><<<grid, 256, 0, st>>>((const T*)gq, db, g);
+  QUAN_LAUNCH((qconv_bias_grad<T, LAYOUT>), grid, 256, 0, st, (const T*)gq, db, g);
   QUAN_CHECK_LAUNCH("qconv_bias_grad");
   return QUAN_OK;
 }

@@ -35,6 +35,7 @@ struct W4p {
 template <typename T, int V, bool TRANSPOSED>
 __global__ void __launch_bounds__(256) qconv_dw_kernel(const T* __restrict__ in, W4p w, const float* __restrict__ bias_r,
                                                        T* __restrict__ out, DwGeom g, Mix16 M) {
+  pdl_prologue();
   extern __shared__ float wsm[];   // [taps][4][C]
   const int taps = g.kH * g.kW;
   for (int e = threadIdx.x; e < taps * 4 * g.C; e += blockDim.x) {
@@ -126,6 +127,7 @@ __global__ void __launch_bounds__(256) qconv_dw_kernel(const T* __restrict__ in,
 template <typename T, int V, int TAPS>
 __global__ void __launch_bounds__(256) qconv_dw_wgrad_kernel(const T* __restrict__ dy, const T* __restrict__ x, float* dw0,
                                                              float* dw1, float* dw2, float* dw3, DwGeom g, Mix16 M) {
+  pdl_prologue();
   __shared__ float red[256][V + 1];
   const int cvs = g.C / V;
   const int tpp = 4 * cvs;                       // threads per pixel: (q, channel vector)
@@ -192,6 +194,7 @@ template <typename T, int V, int KW, int U>
 __global__ void __launch_bounds__(256, 2) qconv_dw_wgrad_rows_kernel(const T* __restrict__ dy, const T* __restrict__ x,
                                                                      float* dw0, float* dw1, float* dw2, float* dw3,
                                                                      DwGeom g, Mix16 M) {
+  pdl_prologue();
   __shared__ float red[256][V + 1];
   const int cvs = g.C / V;
   const int tpp = 4 * cvs * g.kH;                // threads per pixel: (kh, q, channel vector)
@@ -286,10 +289,10 @@ static int dw_launch_t(const void* in, const float* const w[4], const float* bia
   QUAN_TIMED(st);
   if (g.C % VMAX == 0) {
     const int grid = grid_for(opix * (g.C / VMAX), 256, 8);
-    qconv_dw_kernel<T, VMAX, TRANSPOSED><<<grid, 256, smem, st>>>((const T*)in, w4, bias_r, (T*)out, g, M);
+    QUAN_LAUNCH((qconv_dw_kernel<T, VMAX, TRANSPOSED>), grid, 256, smem, st, (const T*)in, w4, bias_r, (T*)out, g, M);
   } else {
     const int grid = grid_for(opix * (g.C / (VMAX / 2)), 256, 8);
-    qconv_dw_kernel<T, VMAX / 2, TRANSPOSED><<<grid, 256, smem, st>>>((const T*)in, w4, bias_r, (T*)out, g, M);
+    QUAN_LAUNCH((qconv_dw_kernel<T, VMAX / 2, TRANSPOSED>), grid, 256, smem, st, (const T*)in, w4, bias_r, (T*)out, g, M);
   }
   QUAN_CHECK_LAUNCH(TRANSPOSED ? "qconv_dw_dgrad" : "qconv_dw_fwd");
   return QUAN_OK;
@@ -331,7 +334,7 @@ int qconv_dw_wgrad(const void* dy, const void* x, float* const dw[4], const quan
     if (blocks > QUAN_NUM_SMS * 4) blocks = QUAN_NUM_SMS * 4;
     if (blocks < 1) blocks = 1;
     QUAN_TIMED(st);
-#define QUAN_DW_ROWS(TT, VV) qconv_dw_wgrad_rows_kernel<TT, VV, 3, 2><<<(unsigned)blocks, 256, 0, st>>>( \
+#define QUAN_DW_ROWS(TT, VV) QUAN_LAUNCH((qconv_dw_wgrad_rows_kernel<TT, VV, 3, 2>), (unsigned)blocks, 256, 0, st,  \
     (const TT*)dy, (const TT*)x, dw[0], dw[1], dw[2], dw[3], g, M)
     if (dtype == QUAN_BF16) { if (V == 8) QUAN_DW_ROWS(__nv_bfloat16, 8); else QUAN_DW_ROWS(__nv_bfloat16, 4); }
     else { if (V == 4) QUAN_DW_ROWS(float, 4); else QUAN_DW_ROWS(float, 2); }
@@ -346,12 +349,12 @@ int qconv_dw_wgrad(const void* dy, const void* x, float* const dw[4], const quan
   QUAN_TIMED(st);
   if (dtype == QUAN_BF16) {
     const __nv_bfloat16 *dyp = (const __nv_bfloat16*)dy, *xp = (const __nv_bfloat16*)x;
-    if (V == 8) qconv_dw_wgrad_kernel<__nv_bfloat16, 8, 9><<<(unsigned)blocks, 256, 0, st>>>(dyp, xp, dw[0], dw[1], dw[2], dw[3], g, M);
-    else qconv_dw_wgrad_kernel<__nv_bfloat16, 4, 9><<<(unsigned)blocks, 256, 0, st>>>(dyp, xp, dw[0], dw[1], dw[2], dw[3], g, M);
+    if (V == 8) QUAN_LAUNCH((qconv_dw_wgrad_kernel<__nv_bfloat16, 8, 9>), (unsigned)blocks, 256, 0, st, dyp, xp, dw[0], dw[1], dw[2], dw[3], g, M);
+    else QUAN_LAUNCH((qconv_dw_wgrad_kernel<__nv_bfloat16, 4, 9>), (unsigned)blocks, 256, 0, st, dyp, xp, dw[0], dw[1], dw[2], dw[3], g, M);
   } else {
     const float *dyp = (const float*)dy, *xp = (const float*)x;
-    if (V == 4) qconv_dw_wgrad_kernel<float, 4, 9><<<(unsigned)blocks, 256, 0, st>>>(dyp, xp, dw[0], dw[1], dw[2], dw[3], g, M);
-    else qconv_dw_wgrad_kernel<float, 2, 9><<<(unsigned)blocks, 256, 0, st>>>(dyp, xp, dw[0], dw[1], dw[2], dw[3], g, M);
+    if (V == 4) QUAN_LAUNCH((qconv_dw_wgrad_kernel<float, 4, 9>), (unsigned)blocks, 256, 0, st, dyp, xp, dw[0], dw[1], dw[2], dw[3], g, M);
+    else QUAN_LAUNCH((qconv_dw_wgrad_kernel<float, 2, 9>), (unsigned)blocks, 256, 0, st, dyp, xp, dw[0], dw[1], dw[2], dw[3], g, M);
   }
   QUAN_CHECK_LAUNCH("qconv_dw_wgrad_kernel");
   return QUAN_OK;

@@ -62,6 +62,7 @@ __device__ __forceinline__ void store_pixel(T* __restrict__ p, const float (&v)[
 template <typename T, int CIN, int COUT, bool TRANSPOSED>
 __global__ void __launch_bounds__(128) qconv_small_kernel(const T* __restrict__ in, W4s w, const float* __restrict__ bias_r,
                                                           T* __restrict__ out, SmallGeom g, Mix16 M) {
+  pdl_prologue();
   extern __shared__ float wsm[];   // [taps][4][COUT][CIN]
   const int taps = g.kH * g.kW;
   const int co0 = TRANSPOSED ? 0 : (int)blockIdx.y * COUT;   // forward: this block's chunk of output channels
@@ -169,6 +170,7 @@ constexpr int SW_TILE = 256;
 template <typename T, int CI, int CO, int U>
 __global__ void __launch_bounds__(256, 2) qconv_small_wgrad_kernel(const T* __restrict__ dy, const T* __restrict__ x, float* dw0,
                                                                 float* dw1, float* dw2, float* dw3, SmallGeom g, Mix16 M) {
+  pdl_prologue();
   constexpr int NACC = 4 * CO * CI;
   constexpr int GROW = 4 * CO + 4;                   // padded row: the pixel lanes of a warp hit different banks
   __shared__ __align__(16) float Gs[SW_TILE][GROW];
@@ -275,6 +277,7 @@ __global__ void __launch_bounds__(256, 2) qconv_small_wgrad_kernel(const T* __re
 template <typename T, int CI, int CO>
 __global__ void __launch_bounds__(256) qconv_small_wgrad_pertap_kernel(const T* __restrict__ dy, const T* __restrict__ x, float* dw0,
                                                                 float* dw1, float* dw2, float* dw3, SmallGeom g, Mix16 M) {
+  pdl_prologue();
   constexpr int NACC = 4 * CO * CI;
   __shared__ float red[256];
   const int taps = g.kH * g.kW;
@@ -373,7 +376,7 @@ static int small_launch_t(const void* in, const float* const w[4], const float* 
   const dim3 grid((unsigned)grid_for(opix, 128, 16), (unsigned)(d.Co / chunk));
   W4s w4 = {{w[0], w[1], w[2], w[3]}};
   QUAN_TIMED(st);
-  QUAN_SMALL_DISPATCH(cin, cout, (qconv_small_kernel<T, kA, kB, TRANSPOSED><<<grid, 128, smem, st>>>(
+  QUAN_SMALL_DISPATCH(cin, cout, (QUAN_LAUNCH((qconv_small_kernel<T, kA, kB, TRANSPOSED>), grid, 128, smem, st, 
                                      (const T*)in, w4, bias_r, (T*)out, g, M)));
   QUAN_CHECK_LAUNCH(TRANSPOSED ? "qconv_small_dgrad" : "qconv_small_fwd");
   return QUAN_OK;
@@ -408,7 +411,7 @@ static int small_wgrad_launch(const T* dy, const T* x, float* const dw[4], const
   if (cap < 1) cap = 1;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  kern<<<dim3((unsigned)blocks, (unsigned)nchunks), 256, 0, st>>>(dy, x, dw[0], dw[1], dw[2], dw[3], g, M);
+  QUAN_LAUNCH((kern), dim3((unsigned)blocks, (unsigned)nchunks), 256, 0, st, dy, x, dw[0], dw[1], dw[2], dw[3], g, M);
   return QUAN_OK;
 }
 
@@ -432,7 +435,7 @@ static int small_wgrad_t(const void* dy, const void* x, float* const dw[4], cons
     int64_t blocks = ceil_div64(npix, (int64_t)lanes * 32);
     if (blocks > QUAN_NUM_SMS * 4) blocks = QUAN_NUM_SMS * 4;
     if (blocks < 1) blocks = 1;
-    QUAN_SMALL_DISPATCH(d.Ci, d.Co, (qconv_small_wgrad_pertap_kernel<T, kA, kB><<<(unsigned)blocks, 256, 0, st>>>(
+    QUAN_SMALL_DISPATCH(d.Ci, d.Co, (QUAN_LAUNCH((qconv_small_wgrad_pertap_kernel<T, kA, kB>), (unsigned)blocks, 256, 0, st, 
                                         (const T*)dy, (const T*)x, dw[0], dw[1], dw[2], dw[3], g, M)));
     QUAN_CHECK_LAUNCH("qconv_small_wgrad");
     return QUAN_OK;

@@ -91,6 +91,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) pack_weights_fwd_kernel(const float* __restrict__ w0, const float* __restrict__ w1,
                                                                const float* __restrict__ w2, const float* __restrict__ w3,
                                                                T* __restrict__ out, int Co, int Ci, int taps, int cchunk) {
+  pdl_prologue();
   extern __shared__ float tile[];
   const int q = blockIdx.y / Co, co = blockIdx.y % Co;
   const int ci0 = blockIdx.x * cchunk, nci = min(cchunk, Ci - ci0);
@@ -109,6 +110,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) pack_weights_dgrad_kernel(const float* __restrict__ w0, const float* __restrict__ w1,
                                                                  const float* __restrict__ w2, const float* __restrict__ w3,
                                                                  T* __restrict__ out, int Co, int Ci, int taps, int tci) {
+  pdl_prologue();
   extern __shared__ float tile[];
   const int q = blockIdx.z;
   const int co0 = blockIdx.y * 32, nco = min(32, Co - co0);
@@ -228,6 +230,7 @@ template <typename T, bool MIX, int CG, int KSTEPS, int NQ>
 __global__ void __launch_bounds__(IG_THREADS, 1)
 qconv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, T* __restrict__ y,
                    const TcConvParams p) {
+  pdl_prologue();
   constexpr int NACC = NQ == 4 ? 4 : 2;   // TMEM accumulators of BN columns
   constexpr int NTB = NACC / NQ;          // units that can be in flight in TMEM (tile_full barriers)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -695,6 +698,7 @@ constexpr int WG_PIX = 64;     // pixels (K) per pipeline stage
 template <typename T, int KSTEPS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 qconv_wgrad_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant__ CUtensorMap map_x, const TcWgradParams p) {
+  pdl_prologue();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
@@ -853,6 +857,7 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
                                                            float* __restrict__ dw1, float* __restrict__ dw2,
                                                            float* __restrict__ dw3, int splits, int taps, int Co, int Ci,
                                                            int cchunk, int SL, const Mix16 mix) {
+  pdl_prologue();
   extern __shared__ float tile[];                     // [SL][nci*taps] partial sums, folded into lane 0's slice
   const int q = blockIdx.y / Co, co = blockIdx.y % Co;
   const int ci0 = blockIdx.x * cchunk, nci = min(cchunk, Ci - ci0);
@@ -912,6 +917,7 @@ __global__ void __launch_bounds__(256) wgrad_reduce_flat_kernel(const float* __r
                                                                 float* __restrict__ dw1, float* __restrict__ dw2,
                                                                 float* __restrict__ dw3, int splits, int taps, int Co, int Ci,
                                                                 const Mix16 mix) {
+  pdl_prologue();
   const int per_q = Co * Ci * taps;
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= 4 * per_q) return;
@@ -952,6 +958,7 @@ __global__ void __launch_bounds__(256) pack_weights_dense_kernel(const float* __
                                                                  const float* __restrict__ bias_r, T* __restrict__ out,
                                                                  float* __restrict__ bias_out, int Co, int Ci, int taps,
                                                                  const Mix16 mix) {
+  pdl_prologue();
   const int N = DGRAD ? 4 * Ci : 4 * Co, K = DGRAD ? 4 * Co : 4 * Ci;
   const int64_t total = (int64_t)taps * N * K;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -1085,11 +1092,13 @@ static int launch_igemm_inst(const CUtensorMap& map_a, const CUtensorMap& map_b,
   cfg.blockDim = dim3(IG_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;      // PDL, see common.cuh pdl_prologue()
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   static thread_local DeviceOnce attr_set;
@@ -1112,6 +1121,7 @@ static int launch_igemm_inst(const CUtensorMap& map_a, const CUtensorMap& map_b,
   cfg.gridDim = dim3((unsigned)(groups * CG));
   *ctas = groups * CG;
   QUAN_TIMED(st);
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   QUAN_CUDA(cudaLaunchKernelEx(&cfg, kern, map_a, map_b, reinterpret_cast<T*>(out), p));
   QUAN_CHECK_LAUNCH(name);
   return QUAN_OK;
@@ -1273,14 +1283,14 @@ static int pack_weights(const float* const w[4], void* out, const quan_conv_dims
     if (tci < 1) tci = 1;
     dim3 grid((unsigned)((d.Ci + tci - 1) / tci), (unsigned)((d.Co + 31) / 32), 4);
     QUAN_TIMED(st);
-    pack_weights_dgrad_kernel<T><<<grid, 256, (size_t)32 * (tci * taps + 1) * sizeof(float), st>>>(w[0], w[1], w[2], w[3], reinterpret_cast<T*>(out), d.Co, d.Ci, taps, tci);
+    QUAN_LAUNCH((pack_weights_dgrad_kernel<T>), grid, 256, (size_t)32 * (tci * taps + 1) * sizeof(float), st, w[0], w[1], w[2], w[3], reinterpret_cast<T*>(out), d.Co, d.Ci, taps, tci);
   } else {
     int cchunk = 2304 / taps;                             // ~9 KB tiles: many resident blocks
     if (cchunk < 1) cchunk = 1;
     if (cchunk > d.Ci) cchunk = d.Ci;
     dim3 grid((unsigned)((d.Ci + cchunk - 1) / cchunk), (unsigned)(4 * d.Co));
     QUAN_TIMED(st);
-    pack_weights_fwd_kernel<T><<<grid, 256, (size_t)cchunk * taps * sizeof(float), st>>>(w[0], w[1], w[2], w[3], reinterpret_cast<T*>(out), d.Co, d.Ci, taps, cchunk);
+    QUAN_LAUNCH((pack_weights_fwd_kernel<T>), grid, 256, (size_t)cchunk * taps * sizeof(float), st, w[0], w[1], w[2], w[3], reinterpret_cast<T*>(out), d.Co, d.Ci, taps, cchunk);
   }
   QUAN_CHECK_LAUNCH("pack_weights_kernel");
   return QUAN_OK;
@@ -1292,7 +1302,7 @@ static int pack_weights_dense(const float* const w[4], const float* bias_r, void
   const int64_t total = (int64_t)16 * d.Co * d.Ci * taps;
   int grid = grid_for(total, 256, 4);
   QUAN_TIMED(st);
-  pack_weights_dense_kernel<T, DGRAD><<<grid, 256, 0, st>>>(w[0], w[1], w[2], w[3], bias_r, reinterpret_cast<T*>(out), bias_out,
+  QUAN_LAUNCH((pack_weights_dense_kernel<T, DGRAD>), grid, 256, 0, st, w[0], w[1], w[2], w[3], bias_r, reinterpret_cast<T*>(out), bias_out,
                                                             d.Co, d.Ci, taps, mix);
   QUAN_CHECK_LAUNCH("pack_weights_dense_kernel");
   return QUAN_OK;
@@ -1511,7 +1521,7 @@ static int launch_wgrad(const void* gq, const void* x, float* const dw[4], const
   if (attr_set.first()) QUAN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   dim3 grid((unsigned)w.splits, (unsigned)(nq * w.tap_groups * w.co_blocks * w.ci_blocks));
   QUAN_TIMED(st);
-  kern<<<grid, TC_THREADS, w.smem, st>>>(map_g, map_x, p);
+  QUAN_LAUNCH((kern), grid, TC_THREADS, w.smem, st, map_g, map_x, p);
   QUAN_CHECK_LAUNCH(dense ? "qconv_wgrad_kernel_dense" : "qconv_wgrad_kernel");
   {
     int cchunk = 2304 / p.taps;
@@ -1530,13 +1540,13 @@ static int launch_wgrad(const void* gq, const void* x, float* const dw[4], const
     if (env_flat && fold_splits <= 4 && dw_elems <= (1 << 18)) {
       const unsigned fgrid = (unsigned)((dw_elems + 255) / 256);
       if (dense)
-        wgrad_reduce_flat_kernel<true><<<fgrid, 256, 0, st>>>(p.partial, dw[0], dw[1], dw[2], dw[3], fold_splits, p.taps, d.Co, d.Ci, mix);
+        QUAN_LAUNCH((wgrad_reduce_flat_kernel<true>), fgrid, 256, 0, st, p.partial, dw[0], dw[1], dw[2], dw[3], fold_splits, p.taps, d.Co, d.Ci, mix);
       else
-        wgrad_reduce_flat_kernel<false><<<fgrid, 256, 0, st>>>(p.partial, dw[0], dw[1], dw[2], dw[3], fold_splits, p.taps, d.Co, d.Ci, mix);
+        QUAN_LAUNCH((wgrad_reduce_flat_kernel<false>), fgrid, 256, 0, st, p.partial, dw[0], dw[1], dw[2], dw[3], fold_splits, p.taps, d.Co, d.Ci, mix);
     } else if (dense)
-      wgrad_reduce_kernel<true><<<rgrid, 256, rsmem, st>>>(p.partial, dw[0], dw[1], dw[2], dw[3], fold_splits, p.taps, d.Co, d.Ci, cchunk, SL, mix);
+      QUAN_LAUNCH((wgrad_reduce_kernel<true>), rgrid, 256, rsmem, st, p.partial, dw[0], dw[1], dw[2], dw[3], fold_splits, p.taps, d.Co, d.Ci, cchunk, SL, mix);
     else
-      wgrad_reduce_kernel<false><<<rgrid, 256, rsmem, st>>>(p.partial, dw[0], dw[1], dw[2], dw[3], fold_splits, p.taps, d.Co, d.Ci, cchunk, SL, mix);
+      QUAN_LAUNCH((wgrad_reduce_kernel<false>), rgrid, 256, rsmem, st, p.partial, dw[0], dw[1], dw[2], dw[3], fold_splits, p.taps, d.Co, d.Ci, cchunk, SL, mix);
   }
   QUAN_CHECK_LAUNCH("wgrad_reduce_kernel");
   return QUAN_OK;

@@ -47,6 +47,7 @@ constexpr int POOL_CH = 9;
 template <typename T, int V, bool WITH_IDX, typename I>
 __global__ void __launch_bounds__(256) qmaxpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y,
                                                            uint8_t* __restrict__ idx, PoolGeom g) {
+  pdl_prologue();
   const I total = (I)(g.outer * g.Ho * g.Wo * g.inner_vecs);
   const int taps = g.kH * g.kW;
   for (I i = (I)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (I)gridDim.x * blockDim.x) {
@@ -104,6 +105,7 @@ __global__ void __launch_bounds__(256) qmaxpool_fwd_kernel(const T* __restrict__
 template <int V, bool WITH_IDX, typename I>
 __global__ void __launch_bounds__(256) qmaxpool_fwd_bf16_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
                                                                 uint8_t* __restrict__ idx, PoolGeom g) {
+  pdl_prologue();
   constexpr int NP = V / 2;
   using T = __nv_bfloat16;
   const I total = (I)(g.outer * g.Ho * g.Wo * g.inner_vecs);
@@ -181,6 +183,7 @@ __global__ void __launch_bounds__(256) qmaxpool_fwd_bf16_kernel(const __nv_bfloa
 template <typename T, int V, typename I>
 __global__ void __launch_bounds__(256) qmaxpool_bwd_kernel(const T* __restrict__ dy, const uint8_t* __restrict__ idx,
                                                            T* __restrict__ dx, PoolGeom g) {
+  pdl_prologue();
   const I total = (I)(g.outer * g.H * g.W * g.inner_vecs);
   for (I i = (I)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (I)gridDim.x * blockDim.x) {
     const int iv = (int)(i % g.inner_vecs);
@@ -230,6 +233,7 @@ template <int V, bool WITH_IDX>
 __global__ void __launch_bounds__(256) qmaxpool_fwd_bf16_rows_kernel(const __nv_bfloat16* __restrict__ x,
                                                                      __nv_bfloat16* __restrict__ y, uint8_t* __restrict__ idx,
                                                                      PoolGeom g) {
+  pdl_prologue();
   constexpr int NP = V / 2;
   using T = __nv_bfloat16;
   const int taps = g.kH * g.kW;
@@ -312,6 +316,7 @@ constexpr int POOL_RB = 8;
 template <typename T, int V>
 __global__ void __launch_bounds__(256) qmaxpool_bwd_rows_kernel(const T* __restrict__ dy, const uint8_t* __restrict__ idx,
                                                                 T* __restrict__ dx, PoolGeom g) {
+  pdl_prologue();
   // g.rb (<= POOL_RB) consecutive input rows per block: the 1 + (kH-1)/sH output rows a row needs are the next row's too, so the
   // index / gradient vectors come from L1 instead of L2 (one row per block: 1348 us on the Q-ResNet stem pool — three
   // blocks on three SMs each pulled the same output rows through L2)
@@ -393,17 +398,17 @@ static int launch_pool_fwd(const void* x, void* y, uint8_t* idx, const PoolGeom&
   const bool small = g.outer * g.H * g.W * g.inner_vecs < (1ll << 31) - (1 << 20) && g.outer * g.Ho * g.Wo * g.inner_vecs < (1ll << 31) - (1 << 20);
 #define QUAN_POOL_FWD(VV)                                                                                        \
   do {                                                                                                           \
-    if (idx != nullptr && small) qmaxpool_fwd_kernel<T, VV, true, int><<<grid, 256, 0, st>>>(xp, yp, idx, g);     \
-    else if (idx != nullptr) qmaxpool_fwd_kernel<T, VV, true, int64_t><<<grid, 256, 0, st>>>(xp, yp, idx, g);     \
-    else if (small) qmaxpool_fwd_kernel<T, VV, false, int><<<grid, 256, 0, st>>>(xp, yp, idx, g);                 \
-    else qmaxpool_fwd_kernel<T, VV, false, int64_t><<<grid, 256, 0, st>>>(xp, yp, idx, g);                        \
+    if (idx != nullptr && small) QUAN_LAUNCH((qmaxpool_fwd_kernel<T, VV, true, int>), grid, 256, 0, st, xp, yp, idx, g);     \
+    else if (idx != nullptr) QUAN_LAUNCH((qmaxpool_fwd_kernel<T, VV, true, int64_t>), grid, 256, 0, st, xp, yp, idx, g);     \
+    else if (small) QUAN_LAUNCH((qmaxpool_fwd_kernel<T, VV, false, int>), grid, 256, 0, st, xp, yp, idx, g);                 \
+    else QUAN_LAUNCH((qmaxpool_fwd_kernel<T, VV, false, int64_t>), grid, 256, 0, st, xp, yp, idx, g);                        \
   } while (0)
 #define QUAN_POOL_FWD_BF16(VV)                                                                                   \
   do {                                                                                                           \
-    if (idx != nullptr && small) qmaxpool_fwd_bf16_kernel<VV, true, int><<<grid, 256, 0, st>>>(xp, yp, idx, g);   \
-    else if (idx != nullptr) qmaxpool_fwd_bf16_kernel<VV, true, int64_t><<<grid, 256, 0, st>>>(xp, yp, idx, g);   \
-    else if (small) qmaxpool_fwd_bf16_kernel<VV, false, int><<<grid, 256, 0, st>>>(xp, yp, idx, g);               \
-    else qmaxpool_fwd_bf16_kernel<VV, false, int64_t><<<grid, 256, 0, st>>>(xp, yp, idx, g);                      \
+    if (idx != nullptr && small) QUAN_LAUNCH((qmaxpool_fwd_bf16_kernel<VV, true, int>), grid, 256, 0, st, xp, yp, idx, g);   \
+    else if (idx != nullptr) QUAN_LAUNCH((qmaxpool_fwd_bf16_kernel<VV, true, int64_t>), grid, 256, 0, st, xp, yp, idx, g);   \
+    else if (small) QUAN_LAUNCH((qmaxpool_fwd_bf16_kernel<VV, false, int>), grid, 256, 0, st, xp, yp, idx, g);               \
+    else QUAN_LAUNCH((qmaxpool_fwd_bf16_kernel<VV, false, int64_t>), grid, 256, 0, st, xp, yp, idx, g);                      \
   } while (0)
   static const int env_packed = [] { const char* e = getenv("QUAN_POOL_PACKED"); return e ? atoi(e) : 1; }();
   static const int env_rows = [] { const char* e = getenv("QUAN_POOL_ROWS"); return e ? atoi(e) : 1; }();
@@ -417,11 +422,11 @@ static int launch_pool_fwd(const void* x, void* y, uint8_t* idx, const PoolGeom&
       const PoolGeom& g = gr;
       const unsigned rows = (unsigned)((g.outer * g.Ho + g.rb - 1) / g.rb);
       if (V == 8) {
-        if (idx != nullptr) qmaxpool_fwd_bf16_rows_kernel<8, true><<<rows, 256, 0, st>>>(xp, yp, idx, g);
-        else qmaxpool_fwd_bf16_rows_kernel<8, false><<<rows, 256, 0, st>>>(xp, yp, idx, g);
+        if (idx != nullptr) QUAN_LAUNCH((qmaxpool_fwd_bf16_rows_kernel<8, true>), rows, 256, 0, st, xp, yp, idx, g);
+        else QUAN_LAUNCH((qmaxpool_fwd_bf16_rows_kernel<8, false>), rows, 256, 0, st, xp, yp, idx, g);
       } else {
-        if (idx != nullptr) qmaxpool_fwd_bf16_rows_kernel<4, true><<<rows, 256, 0, st>>>(xp, yp, idx, g);
-        else qmaxpool_fwd_bf16_rows_kernel<4, false><<<rows, 256, 0, st>>>(xp, yp, idx, g);
+        if (idx != nullptr) QUAN_LAUNCH((qmaxpool_fwd_bf16_rows_kernel<4, true>), rows, 256, 0, st, xp, yp, idx, g);
+        else QUAN_LAUNCH((qmaxpool_fwd_bf16_rows_kernel<4, false>), rows, 256, 0, st, xp, yp, idx, g);
       }
       QUAN_CHECK_LAUNCH("qmaxpool_fwd");
       return QUAN_OK;
@@ -456,19 +461,19 @@ static int launch_pool_bwd(const void* dy, const uint8_t* idx, void* dx, const P
     gr.rb = gr.rb < 1 ? 1 : gr.rb > POOL_RB ? POOL_RB : gr.rb;
     const PoolGeom& g = gr;
     const unsigned rows = (unsigned)((g.outer * g.H + g.rb - 1) / g.rb);
-    if (V == 8) { if constexpr (sizeof(T) == 2) qmaxpool_bwd_rows_kernel<T, 8><<<rows, 256, 0, st>>>(gp, idx, dp, g); }
-    else qmaxpool_bwd_rows_kernel<T, 4><<<rows, 256, 0, st>>>(gp, idx, dp, g);
+    if (V == 8) { if constexpr (sizeof(T) == 2) QUAN_LAUNCH((qmaxpool_bwd_rows_kernel<T, 8>), rows, 256, 0, st, gp, idx, dp, g); }
+    else QUAN_LAUNCH((qmaxpool_bwd_rows_kernel<T, 4>), rows, 256, 0, st, gp, idx, dp, g);
     QUAN_CHECK_LAUNCH("qmaxpool_bwd");
     return QUAN_OK;
   }
   if (V == 8) {
     if constexpr (sizeof(T) == 2) {
-      if (small) qmaxpool_bwd_kernel<T, 8, int><<<grid, 256, 0, st>>>(gp, idx, dp, g);
-      else qmaxpool_bwd_kernel<T, 8, int64_t><<<grid, 256, 0, st>>>(gp, idx, dp, g);
+      if (small) QUAN_LAUNCH((qmaxpool_bwd_kernel<T, 8, int>), grid, 256, 0, st, gp, idx, dp, g);
+      else QUAN_LAUNCH((qmaxpool_bwd_kernel<T, 8, int64_t>), grid, 256, 0, st, gp, idx, dp, g);
     }
   } else {
-    if (small) qmaxpool_bwd_kernel<T, 4, int><<<grid, 256, 0, st>>>(gp, idx, dp, g);
-    else qmaxpool_bwd_kernel<T, 4, int64_t><<<grid, 256, 0, st>>>(gp, idx, dp, g);
+    if (small) QUAN_LAUNCH((qmaxpool_bwd_kernel<T, 4, int>), grid, 256, 0, st, gp, idx, dp, g);
+    else QUAN_LAUNCH((qmaxpool_bwd_kernel<T, 4, int64_t>), grid, 256, 0, st, gp, idx, dp, g);
   }
   QUAN_CHECK_LAUNCH("qmaxpool_bwd");
   return QUAN_OK;

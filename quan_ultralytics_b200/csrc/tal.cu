@@ -81,6 +81,7 @@ struct TalArgs {
 };
 
 __global__ void tal_clear_kernel(TalArgs t) {
+  pdl_prologue();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < (int64_t)t.B * t.A) t.cnt[i] = 0;
   if (i < (int64_t)t.B * t.n) { t.pos_align[i] = 0u; t.pos_over[i] = 0u; }
@@ -88,6 +89,7 @@ __global__ void tal_clear_kernel(TalArgs t) {
 
 // grid (n, B), one block per ground-truth box
 __global__ void __launch_bounds__(TAL_THREADS) tal_metrics_topk_kernel(TalArgs t) {
+  pdl_prologue();
   extern __shared__ float row_s[];
   __shared__ float red_v[TAL_THREADS / 32];
   __shared__ int red_i[TAL_THREADS / 32];
@@ -164,6 +166,7 @@ __global__ void __launch_bounds__(TAL_THREADS) tal_metrics_topk_kernel(TalArgs t
 
 // one thread per (b, a): tal.py:271-296 select_highest_overlaps, then the per-box maxima of tal.py:109-110
 __global__ void tal_resolve_kernel(TalArgs t) {
+  pdl_prologue();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)t.B * t.A) return;
   const int b = (int)(i / t.A), a = (int)(i % t.A);
@@ -189,6 +192,7 @@ __global__ void tal_resolve_kernel(TalArgs t) {
 
 // one thread per (b, a): tal.py:188-236 get_targets and the normalisation :108-113
 __global__ void tal_targets_kernel(TalArgs t) {
+  pdl_prologue();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)t.B * t.A) return;
   const int b = (int)(i / t.A), a = (int)(i % t.A);
@@ -251,16 +255,16 @@ int quan_rotated_tal_assign(const float* pd_scores, const float* pd_bboxes, cons
   const int64_t na = (int64_t)B * A;
   const int blocks = (int)((na + 255) / 256);
   QUAN_TIMED(st);
-  tal_clear_kernel<<<blocks, 256, 0, st>>>(t);
+  QUAN_LAUNCH((tal_clear_kernel), blocks, 256, 0, st, t);
   QUAN_CHECK_LAUNCH("tal_clear");
   QUAN_TIMED(st);
-  kern<<<dim3(n, B), TAL_THREADS, t.use_smem ? smem : 0, st>>>(t);
+  QUAN_LAUNCH((kern), dim3(n, B), TAL_THREADS, t.use_smem ? smem : 0, st, t);
   QUAN_CHECK_LAUNCH("tal_metrics_topk");
   QUAN_TIMED(st);
-  tal_resolve_kernel<<<blocks, 256, 0, st>>>(t);
+  QUAN_LAUNCH((tal_resolve_kernel), blocks, 256, 0, st, t);
   QUAN_CHECK_LAUNCH("tal_resolve");
   QUAN_TIMED(st);
-  tal_targets_kernel<<<blocks, 256, 0, st>>>(t);
+  QUAN_LAUNCH((tal_targets_kernel), blocks, 256, 0, st, t);
   QUAN_CHECK_LAUNCH("tal_targets");
   return QUAN_OK;
 }
