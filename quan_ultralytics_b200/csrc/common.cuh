@@ -182,7 +182,9 @@ struct DeviceOnce {
 // preceding grid has completed and its writes are visible (griddepcontrol.wait — a no-op when the kernel was launched without the
 // attribute) and then lets ITS dependents be launched (griddepcontrol.launch_dependents), so the next kernel's CTAs are scheduled
 // and parked at their own wait while this one runs.  No kernel touches global memory before the wait: ordering is exactly stream
-// order.  Host side: QUAN_LAUNCH(...) = cudaLaunchKernelEx with programmaticStreamSerializationAllowed.  QUAN_PDL=0 disables.
+// order.  Host side: QUAN_LAUNCH(...) = cudaLaunchKernelEx with programmaticStreamSerializationAllowed when QUAN_PDL=1.
+// Measured on B200 (bench.py default workload, CUDA-graph replay): 17.32 ms/step with PDL, 17.17 ms without — a replayed graph
+// already keeps the GPU 99 % busy (tools/graph_step_profile.py), the dependents only park on SMs earlier — so it is OFF by default.
 __device__ __forceinline__ void pdl_prologue() {
 #if defined(__CUDA_ARCH__)
   asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -191,7 +193,7 @@ __device__ __forceinline__ void pdl_prologue() {
 }
 
 inline bool pdl_enabled() {
-  static const bool on = [] { const char* e = getenv("QUAN_PDL"); return e == nullptr || atoi(e) != 0; }();
+  static const bool on = [] { const char* e = getenv("QUAN_PDL"); return e != nullptr && atoi(e) != 0; }();
   return on;
 }
 
