@@ -612,7 +612,7 @@ def run_yolo_obb(a):
     import quan_ultralytics_b200 as Q
     from quan_ultralytics_b200 import optim, workloads
     from quan_ultralytics_b200.graphs import BucketedGradSync, GraphedTrainStep
-    from quan_ultralytics_b200.loss import OBBLossStatic, pad_targets
+    from quan_ultralytics_b200.loss import OBBLossFused, OBBLossStatic, pad_targets
     import torch.distributed as dist
     lib = Q._lib.load()
     scale = "n" if a.workload == "yolo11n_obb" else "s"
@@ -642,7 +642,7 @@ def run_yolo_obb(a):
     batch = workloads.synthetic_obb_batch(B, S, dev, seed=1 + rank)
     tg, tm = pad_targets(batch, B)
     tg, tm = tg.to(dev), tm.to(dev)
-    crit = OBBLossStatic(model)
+    crit = OBBLossFused(model)
     ref_crit = lambda preds: model.loss(batch, preds)          # the reference's own criterion (utils/loss.py:941), --ref-loss / --no-graph
     sync = BucketedGradSync(params, nbuckets=a.buckets) if world > 1 else None
 
@@ -778,7 +778,7 @@ def run_yolo_obb(a):
             "config": yolo_config(a, scale, B, world),
             "implementation": {"step": ("eager" if a.no_graph else "2 CUDA graphs (forward+loss | backward+all-reduce+optimizer)" if not a.ref_loss
                                         else "2 CUDA graphs around the reference's eager v8OBBLoss"),
-                               "loss": "reference v8OBBLoss" if (a.no_graph or a.ref_loss) else "OBBLossStatic (CUDA assigner, static shapes)",
+                               "loss": "reference v8OBBLoss" if (a.no_graph or a.ref_loss) else "OBBLossFused (decode + rotated TAL assigner + loss/gradient kernels, 9 launches)",
                                "optimizer": "ClipSGD: clip_grad_norm_(10) + SGD(lr .01, momentum .937, nesterov, wd 5e-4) in 2 launches",
                                "sync_iqbn": bool(a.sync_iqbn and world > 1), "grad_buckets": a.buckets if world > 1 else None,
                                "params": sum(p.numel() for p in params)},

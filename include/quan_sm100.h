@@ -263,6 +263,25 @@ int quan_rotated_tal_assign(const float* pd_scores, const float* pd_bboxes, cons
                             float alpha, float beta, float eps, float* target_bboxes, float* target_scores, uint8_t* fg_mask,
                             int64_t* target_gt_idx, void* workspace, size_t ws_bytes, void* stream);
 
+/* ---- OBB loss, differentiable half ----------------------------------------------------------------------
+ * Replaces ultralytics/utils/loss.py:941-1033 around the assigner.  The OBB head's training outputs are read where they lie:
+ * feats[l] = the level-l output [B, no, H_l, W_l] in channels-last memory ([B][H_l][W_l][no], no = 4*reg_max + nc: the DFL logits of
+ * the four sides, then the class logits), pred_angle = [B][1][A] (A = sum H_l*W_l, levels concatenated in order), both of `dtype`.
+ * hw = {H_0, W_0, H_1, W_1, H_2, W_2}; strides = the three level strides.
+ *   quan_obb_decode       -> pd_scores [B][A][nc] = sigmoid(class logits), pd_bboxes [B][A][5] = decoded xywhr in pixels (fp32):
+ *                            the assigner's inputs (loss.py:978-993; decode :1035-1050, tal.py:366-385).
+ *   quan_obb_loss_fwd_bwd -> items[4] = (box, cls, dfl, angle) with the gains applied, total = sum(items) * B (loss.py:1027-1033),
+ *                            AND d(total)/d(feats[l]), d(total)/d(pred_angle) in the layouts / dtype of the inputs, from the assigner's
+ *                            target_bboxes [B][A][5] (pixels), target_scores [B][A][nc], fg_mask [B][A] (bytes).  Terms: BCE with logits
+ *                            (:998), (1 - ProbIoU) * weight (:366-368, metrics.py:198-233), DFL (:306-329), quaternion geodesic angle
+ *                            (:870-903); all divided by max(sum target_scores, 1).  scratch: 5 doubles. */
+int quan_obb_decode(const void* const feats[3], const void* pred_angle, const int32_t* hw, const float* strides, int32_t B, int32_t nc,
+                    int32_t reg_max, float* pd_scores, float* pd_bboxes, int dtype, void* stream);
+int quan_obb_loss_fwd_bwd(const void* const feats[3], const void* pred_angle, const int32_t* hw, const float* strides, int32_t B, int32_t nc,
+                          int32_t reg_max, const float* target_bboxes, const float* target_scores, const uint8_t* fg_mask, float box_gain,
+                          float cls_gain, float dfl_gain, float angle_gain, void* const d_feats[3], void* d_angle, double* scratch,
+                          float* items, float* total, int dtype, void* stream);
+
 /* ---- optimizer step -------------------------------------------------------------------------------
  * Replaces `BaseTrainer.optimizer_step` ultralytics/engine/trainer.py:586-594 — torch.nn.utils.clip_grad_norm_(max_norm) followed by
  * torch.optim.SGD(momentum, nesterov, per-group lr / weight_decay).step() and zero_grad(), built by trainer.py:766-806 — and

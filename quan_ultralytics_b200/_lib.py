@@ -76,6 +76,8 @@ PROTOTYPES = {
     "quan_rotated_tal_workspace_bytes": (_sz, [_i32, _i32, _i32]),
     "quan_rotated_tal_assign": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _f, _f, _f, _vp, _vp, _vp, _vp,
                                        _vp, _sz, _vp]),
+    "quan_obb_decode": (_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _int, _vp]),
+    "quan_obb_loss_fwd_bwd": (_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _f, _f, _f, _f, _vp, _vp, _vp, _vp, _vp, _int, _vp]),
     "quan_sgd_clip_step": (_int, [_vp, _int, _vp, _vp, _int, _vp, _vp, _int, _vp]),
     "quan_ema_update": (_int, [_vp, _int, _vp, _vp, _vp]),
 }

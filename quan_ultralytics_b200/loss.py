@@ -182,3 +182,72 @@ class OBBLossStatic:
 
         loss = torch.stack([loss_iou * self.hyp.box, loss_cls * self.hyp.cls, loss_dfl * self.hyp.dfl, loss_ang * self.lambda_angular])
         return loss.sum() * B, loss.detach()
+
+
+# ---- fully fused criterion: decode -> assigner -> loss + gradients, 9 kernel launches ---------------------------------------------
+class _ObbLossFusedFn(torch.autograd.Function):
+    """(feat_0, feat_1, feat_2, pred_angle) -> (total, items).  The forward kernel already leaves d(total)/d(input) in tensors shaped
+    and laid out like the inputs; backward scales them by the incoming gradient of `total`."""
+
+    @staticmethod
+    def forward(ctx, f0, f1, f2, angle, crit, targets, target_mask):
+        feats = [f.contiguous(memory_format=torch.channels_last) for f in (f0, f1, f2)]
+        angle = angle.contiguous()
+        total, items, grads = crit._run(feats, angle, targets, target_mask)
+        ctx.save_for_backward(*grads)
+        ctx.mark_non_differentiable(items)
+        return total, items
+
+    @staticmethod
+    def backward(ctx, g_total, g_items):
+        grads = ctx.saved_tensors
+        out = torch._foreach_mul(list(grads), g_total.to(grads[0].dtype))
+        return out[0], out[1], out[2], out[3], None, None, None
+
+
+class OBBLossFused(OBBLossStatic):
+    """v8OBBLoss (ultralytics/utils/loss.py:853-1050) in nine launches of libquan_sm100.so: quan_obb_decode (sigmoid scores + decoded
+    boxes for the assigner) -> quan_rotated_tal_assign -> quan_obb_loss_fwd_bwd (loss items AND the gradients w.r.t. the head outputs,
+    read / written in the head's channels-last memory).  Same call interface and return values as OBBLossStatic / the reference."""
+
+    def _run(self, feats, angle, targets, target_mask):
+        import ctypes as C
+        lib = _lib.load()
+        dev = angle.device
+        B = angle.shape[0]
+        shapes = [tuple(f.shape[2:]) for f in feats]
+        _, _, anc_px, imgsz, scale = self._make_anchors(shapes)
+        A = anc_px.shape[0]
+        dt = 1 if angle.dtype == torch.bfloat16 else 0
+        if angle.dtype not in (torch.bfloat16, torch.float32) or any(f.dtype != angle.dtype for f in feats):
+            raise RuntimeError("OBBLossFused: head outputs must all be float32 or all bfloat16")
+        hw = (C.c_int32 * 6)(*[v for s in shapes for v in s])
+        st = (C.c_float * 3)(*self.stride)
+        fp = (C.c_void_p * 3)(*[f.data_ptr() for f in feats])
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        # targets (loss.py:959-968)
+        tg, tmask = targets.float(), target_mask.float()
+        gt_labels = tg[..., 0].contiguous()
+        gt_bboxes = torch.cat([tg[..., 1:5] * scale, tg[..., 5:6]], -1)
+        keep = ((tg[..., 3] * imgsz[0]) >= 2) & ((tg[..., 4] * imgsz[1]) >= 2)
+        mask_gt = (tmask * keep * (gt_bboxes.sum(2) > 0)).contiguous()
+        gt_bboxes = (gt_bboxes * mask_gt.unsqueeze(-1)).contiguous()
+        pd_scores = torch.empty(B, A, self.nc, dtype=torch.float32, device=dev)
+        pd_bboxes = torch.empty(B, A, 5, dtype=torch.float32, device=dev)
+        check(lib.quan_obb_decode(fp, angle.data_ptr(), hw, st, B, self.nc, self.reg_max, pd_scores.data_ptr(), pd_bboxes.data_ptr(), dt,
+                                  stream), "quan_obb_decode")
+        t_boxes, t_scores, fg, _ = self._assign(pd_scores, pd_bboxes, anc_px, gt_labels, gt_bboxes, mask_gt)
+        grads = [torch.empty_like(f, memory_format=torch.preserve_format) for f in feats] + [torch.empty_like(angle)]
+        gp = (C.c_void_p * 3)(*[g.data_ptr() for g in grads[:3]])
+        scratch = torch.empty(5, dtype=torch.float64, device=dev)
+        items = torch.empty(4, dtype=torch.float32, device=dev)
+        total = torch.empty((), dtype=torch.float32, device=dev)
+        check(lib.quan_obb_loss_fwd_bwd(fp, angle.data_ptr(), hw, st, B, self.nc, self.reg_max, t_boxes.data_ptr(), t_scores.data_ptr(),
+                                        fg.data_ptr(), float(self.hyp.box), float(self.hyp.cls), float(self.hyp.dfl), float(self.lambda_angular),
+                                        gp, grads[3].data_ptr(), scratch.data_ptr(), items.data_ptr(), total.data_ptr(), dt, stream),
+              "quan_obb_loss_fwd_bwd")
+        return total, items, grads
+
+    def __call__(self, preds, batch):
+        feats, pred_angle = preds if isinstance(preds[0], list) else preds[1]
+        return _ObbLossFusedFn.apply(feats[0], feats[1], feats[2], pred_angle, self, batch["targets"], batch["target_mask"])

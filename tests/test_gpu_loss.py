@@ -77,3 +77,57 @@ def test_static_loss_vs_live_reference_at_model_size():
     for a, b in zip(g_our, g_ref):
         err = float((a - b).abs().max() / b.abs().max())
         assert err <= 1e-3, err
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 3e-4), (torch.bfloat16, 2e-2)])
+def test_fused_loss_matches_reference_golden(dtype, tol):
+    """quan_obb_decode + quan_rotated_tal_assign + quan_obb_loss_fwd_bwd against the reference criterion's recorded loss and gradients."""
+    from quan_ultralytics_b200.loss import OBBLossFused, pad_targets
+    import types
+    Bz, S, nc, reg_max = (int(v) for v in G["loss_meta"])
+    h = G["loss_hyp"]
+    crit = OBBLossFused(stride=[8.0, 16.0, 32.0], nc=nc, reg_max=reg_max, hyp=types.SimpleNamespace(box=h[0], cls=h[1], dfl=h[2]), device="cuda")
+    ins = [torch.from_numpy(G[f"loss_in{i}"]).cuda().to(dtype) for i in range(4)]
+    ins = [t.contiguous(memory_format=torch.channels_last).requires_grad_(True) if t.dim() == 4 else t.requires_grad_(True) for t in ins]
+    batch = {k: torch.from_numpy(G["loss_" + k]) for k in ("batch_idx", "cls", "bboxes")}
+    tg, tm = pad_targets(batch, Bz)
+    total, items = crit((ins[:3], ins[3]), {"targets": tg.cuda(), "target_mask": tm.cuda()})
+    grads = torch.autograd.grad(total, ins)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(items.cpu().numpy(), G["loss_items"], rtol=tol)
+    np.testing.assert_allclose(float(total), float(G["loss_total"]), rtol=tol)
+    for i, g in enumerate(grads):
+        ref = G[f"loss_grad{i}"]
+        err = np.abs(g.float().cpu().numpy() - ref).max() / np.abs(ref).max()
+        assert err <= (tol if dtype == torch.float32 else 5e-2), (i, err)
+
+
+def test_fused_loss_vs_live_reference_at_model_size():
+    from quan_ultralytics_b200 import refenv
+    if refenv.find_reference() is None:
+        pytest.skip("no reference tree (baseline/_ref)")
+    import math
+    from quan_ultralytics_b200 import workloads
+    from quan_ultralytics_b200.loss import OBBLossFused, pad_targets
+    refenv.activate()
+    from ultralytics.utils.loss import v8OBBLoss
+    torch.manual_seed(0)
+    model = workloads.build_yolo_obb("n", 15, "cuda", swapped=False)
+    ref, ours = v8OBBLoss(model), OBBLossFused(model)
+    Bz, S = 4, 1024
+    batch = workloads.synthetic_obb_batch(Bz, S, "cuda", seed=4)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    feats = [(torch.randn(Bz, ref.no, S // s, S // s, device="cuda", generator=g) * 0.5).contiguous(memory_format=torch.channels_last)
+             .requires_grad_(True) for s in (8, 16, 32)]
+    angle = ((torch.rand(Bz, 1, sum((S // s) ** 2 for s in (8, 16, 32)), device="cuda", generator=g) - 0.25) * math.pi).requires_grad_(True)
+    t_ref, i_ref = ref(([f for f in feats], angle), {k: v.clone() for k, v in batch.items()})
+    g_ref = torch.autograd.grad(t_ref, feats + [angle])
+    tg, tm = pad_targets(batch, Bz)
+    t_our, i_our = ours(([f for f in feats], angle), {"targets": tg.cuda(), "target_mask": tm.cuda()})
+    g_our = torch.autograd.grad(t_our, feats + [angle])
+    torch.cuda.synchronize()
+    print(f"\nfused loss {float(t_our):.4f} vs {float(t_ref):.4f}; items {i_our.tolist()} vs {i_ref.tolist()}")
+    torch.testing.assert_close(i_our, i_ref, rtol=5e-4, atol=1e-6)
+    for a, b in zip(g_our, g_ref):
+        err = float((a - b).abs().max() / b.abs().max())
+        assert err <= 1e-3, err

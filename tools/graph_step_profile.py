@@ -11,7 +11,7 @@ import torch  # noqa: E402
 
 from quan_ultralytics_b200 import optim, workloads  # noqa: E402
 from quan_ultralytics_b200.graphs import GraphedTrainStep  # noqa: E402
-from quan_ultralytics_b200.loss import OBBLossStatic, pad_targets  # noqa: E402
+from quan_ultralytics_b200.loss import OBBLossFused, OBBLossStatic, pad_targets  # noqa: E402
 
 
 def family(name):
@@ -40,7 +40,7 @@ def main():
     model = workloads.build_yolo_obb("n", 15, "cuda", swapped=True).train()
     opt = optim.yolo_clip_sgd(model)
     batch = workloads.synthetic_obb_batch(a.batch, a.size, "cuda")
-    crit = OBBLossStatic(model)
+    crit = OBBLossFused(model)
     tg, tm = pad_targets(batch, a.batch)
     gs = GraphedTrainStep(lambda img, t, m: model(img), lambda preds, img, t, m: crit(preds, {"targets": t, "target_mask": m}), opt,
                           [batch["img"], tg.cuda(), tm.cuda()], list(model.parameters()), autocast=torch.bfloat16, capture_loss=True)

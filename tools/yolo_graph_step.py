@@ -26,8 +26,8 @@ def main():
     batch = workloads.synthetic_obb_batch(a.batch, a.size, "cuda")
     t0 = time.perf_counter()
     if a.static_loss:
-        from quan_ultralytics_b200.loss import OBBLossStatic, pad_targets
-        crit = OBBLossStatic(model)
+        from quan_ultralytics_b200.loss import OBBLossFused, OBBLossStatic, pad_targets
+        crit = OBBLossFused(model)
         tg, tm = pad_targets(batch, a.batch)
         step = GraphedTrainStep(lambda img, t, m: model(img), lambda preds, img, t, m: crit(preds, {"targets": t, "target_mask": m}), opt,
                                 [batch["img"], tg.cuda(), tm.cuda()], list(model.parameters()), autocast=torch.bfloat16, capture_loss=True)
