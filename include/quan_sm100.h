@@ -237,6 +237,10 @@ int quan_conv_block_eval_fwd(const void* x, const float* const w[4], const float
                              const quan_conv_dims* d, int dtype, int layout, const float* mix, int algo, float eps, int act,
                              void* conv_ws, size_t conv_ws_bytes, void* stream);
 
+/* Channel-slice gather: the dense copy of a channel `chunk` / `split` of a BHWQC tensor (what `.contiguous()` at conv.py:441 does for the
+ * strided halves C2f / C3k2 / QC2PSA pass on, block.py:350-352): dst row r (row_bytes bytes) = src + r * src_ld_bytes. */
+int quan_rows_gather(const void* src, void* dst, int64_t nrows, int32_t row_bytes, int64_t src_ld_bytes, void* stream);
+
 /* ---- QAttention core ---------------------------------------------------------------------------------
  * Replaces the attention arithmetic of `QAttention.forward` ultralytics/nn/modules/block.py:1520-1540 (split of the qkv QConv2D output,
  * per-component `matmul(q, k) * scale` -> `softmax` -> `matmul(attn, v)`) and its autograd, fused: the N x N score matrix never

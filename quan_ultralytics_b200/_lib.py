@@ -71,6 +71,7 @@ PROTOTYPES = {
                                         _vp, _sz, _vp]),
     "quan_qconv2d_bwd_premixed": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _pdims, _int, _int, _vp, _int, _vp, _sz, _vp]),
     "quan_qconv2d_bwd_wants_mixed": (_int, [_pdims, _int, _int, _int, _int, _int]),
+    "quan_rows_gather": (_int, [_vp, _vp, C.c_int64, _i32, C.c_int64, _vp]),
     "quan_qattention_fwd": (_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f, _int, _int, _vp]),
     "quan_qattention_bwd": (_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f, _int, _int, _vp]),
     "quan_rotated_tal_workspace_bytes": (_sz, [_i32, _i32, _i32]),

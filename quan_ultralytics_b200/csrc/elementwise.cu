@@ -327,3 +327,43 @@ int quan_layout_convert(const void* src, int src_layout, void* dst, int dst_layo
 }
 
 }  // extern "C"
+
+
+// ---- channel-slice gather ---------------------------------------------------------------------------------------------------------
+// A `chunk` / `split` along the channel axis of a BHWQC tensor (C2f / C3k2 / QC2PSA in block.py:337-365, :1548-1600 hand one half of a
+// Conv output to the next layer) is a strided view: rows of C' contiguous elements, one per (pixel, component), `src_ld` elements
+// apart.  Kernels of this library read dense tensors; torch's generic strided copy takes ~15 us for these (103 per YOLO11n step).
+// This is the same copy with 16-byte vectors: row r of the dense destination = src[r * src_ld .. + row_elems).
+namespace quan {
+template <int VB>
+__global__ void __launch_bounds__(256) rows_gather_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int64_t nrows, int row_bytes,
+                                                          int64_t src_ld_bytes) {
+  pdl_prologue();
+  const int vpr = row_bytes / VB;
+  const int64_t n = nrows * vpr;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / vpr;
+    const int v = (int)(i - r * vpr);
+    if constexpr (VB == 16) *reinterpret_cast<uint4*>(dst + r * row_bytes + v * 16) = *reinterpret_cast<const uint4*>(src + r * src_ld_bytes + v * 16);
+    else if constexpr (VB == 8) *reinterpret_cast<uint2*>(dst + r * row_bytes + v * 8) = *reinterpret_cast<const uint2*>(src + r * src_ld_bytes + v * 8);
+    else *reinterpret_cast<uint32_t*>(dst + r * row_bytes + v * 4) = *reinterpret_cast<const uint32_t*>(src + r * src_ld_bytes + v * 4);
+  }
+}
+}  // namespace quan
+
+extern "C" int quan_rows_gather(const void* src, void* dst, int64_t nrows, int32_t row_bytes, int64_t src_ld_bytes, void* stream) {
+  using namespace quan;
+  QUAN_REQUIRE(src != nullptr && dst != nullptr && nrows > 0 && row_bytes > 0 && src_ld_bytes >= row_bytes, QUAN_E_ARG, "rows_gather: bad argument");
+  QUAN_REQUIRE(row_bytes % 4 == 0 && src_ld_bytes % 4 == 0, QUAN_E_UNSUPPORTED, "rows_gather: rows must be multiples of 4 bytes");
+  cudaStream_t st = (cudaStream_t)stream;
+  const uintptr_t al = reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst) | (uintptr_t)row_bytes | (uintptr_t)src_ld_bytes;
+  const int vb = (al % 16 == 0) ? 16 : (al % 8 == 0) ? 8 : 4;
+  const int64_t n = nrows * (row_bytes / vb);
+  const int grid = grid_for(n, 256, 8);
+  QUAN_TIMED(st);
+  if (vb == 16) QUAN_LAUNCH((rows_gather_kernel<16>), grid, 256, 0, st, (const uint8_t*)src, (uint8_t*)dst, nrows, row_bytes, src_ld_bytes);
+  else if (vb == 8) QUAN_LAUNCH((rows_gather_kernel<8>), grid, 256, 0, st, (const uint8_t*)src, (uint8_t*)dst, nrows, row_bytes, src_ld_bytes);
+  else QUAN_LAUNCH((rows_gather_kernel<4>), grid, 256, 0, st, (const uint8_t*)src, (uint8_t*)dst, nrows, row_bytes, src_ld_bytes);
+  QUAN_CHECK_LAUNCH("rows_gather");
+  return QUAN_OK;
+}

@@ -95,10 +95,29 @@ def as_layout(x: torch.Tensor, layout: Optional[int] = None) -> Tuple[torch.Tens
     target = layout if layout is not None else (cur if cur is not None else LAYOUT_BCHWQ)
     if cur is not None and x.data_ptr() % 16 == 0:
         return convert_layout(x, target), target
+    if cur is None and layout in (None, LAYOUT_BHWQC):        # a strided channel chunk of a BHWQC tensor: vectorised gather
+        g = _gather_channel_slice(x)
+        if g is not None:
+            return g, LAYOUT_BHWQC
     y = x.contiguous(memory_format=_memory_format(target))
     if y.data_ptr() % 16 != 0:
         y = y.clone(memory_format=_memory_format(target))
     return y, target
+
+
+def _gather_channel_slice(x: torch.Tensor) -> Optional[torch.Tensor]:
+    """A channel chunk of a BHWQC tensor (strides: channel 1, component C_total, then W, H, B multiples of 4*C_total) copied into a
+    dense BHWQC tensor by quan_rows_gather; None when `x` is some other kind of view."""
+    B, C_, H, W, _ = x.shape
+    sb, sc, sh, sw, sq = x.stride()
+    if not (x.is_cuda and sc == 1 and sq > C_ and sw == 4 * sq and sh == W * sw and sb == H * sh):
+        return None
+    esz = x.element_size()
+    if (C_ * esz) % 4 or (sq * esz) % 4:
+        return None
+    out = torch.empty(x.shape, dtype=x.dtype, device=x.device, memory_format=torch.channels_last_3d)
+    check(_lib.load().quan_rows_gather(x.data_ptr(), out.data_ptr(), B * H * W * 4, C_ * esz, sq * esz, _stream(x)), "quan_rows_gather")
+    return out
 
 
 # ---- workspaces ------------------------------------------------------------------------------------------------

@@ -493,3 +493,18 @@ def test_ops_follow_the_tensor_device_and_stream():
         assert torch.cuda.current_device() == 0
         y2 = blk1(x.to("cuda:1"))
         torch.testing.assert_close(y2.cpu(), y0.cpu(), rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_channel_chunks_of_bhwqc_tensors_are_gathered_exactly(dtype):
+    """C2f / C3k2 hand `conv(x).chunk(2, 1)` halves to the next Conv (block.py:350-352): strided channel slices of a BHWQC tensor go
+    through quan_rows_gather — bit-identical to torch's own dense copy, for vector widths 16 / 8 / 4 bytes and odd channel counts."""
+    from quan_ultralytics_b200 import ops
+    for C_total, lo, hi in [(32, 16, 32), (32, 0, 16), (24, 8, 20), (10, 3, 9), (6, 1, 4)]:
+        x = torch.randn(3, C_total, 7, 5, 4, device="cuda").to(dtype).contiguous(memory_format=torch.channels_last_3d)
+        sl = x[:, lo:hi]
+        assert ops.layout_of(sl) is None or (hi - lo) == C_total
+        y, layout = ops.as_layout(sl, ops.LAYOUT_BHWQC)
+        assert layout == ops.LAYOUT_BHWQC and y.is_contiguous(memory_format=torch.channels_last_3d)
+        torch.testing.assert_close(y, sl.contiguous(memory_format=torch.channels_last_3d), rtol=0, atol=0)
