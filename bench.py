@@ -40,7 +40,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="yolo11n_obb", choices=["yolo11n_obb", "yolo11s_obb", "block_stack", "yolo11n_trace", "yolo11s_trace", "qresnet34_trace"],
+    ap.add_argument("--workload", default="yolo11n_obb", choices=["yolo11n_obb", "yolo11s_obb", "block_stack", "sweep", "yolo11n_trace", "yolo11s_trace", "qresnet34_trace"],
                     help="block_stack: BASELINE config[1] sweep point (default, the bench line); yolo11n_trace: replay of "
                          "the 87 QConv2D / 84 IQBN+SiLU calls of QUAN-YOLO11n-OBB at 1024^2 (SURVEY 8(a) histogram); "
                          "yolo11s_trace (config[4], default 8 images) and qresnet34_trace (config[3], 224^2, M_B, biased convs, "
@@ -832,6 +832,92 @@ def run_yolo_obb(a):
         os._exit(0)
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# BASELINE configs[1]: the QConv2D / IQBN layer sweep, machine-readable
+# ---------------------------------------------------------------------------------------------------------------
+def measure_matmul_peak(dtype, tf32):
+    """cuBLAS GEMM 8192^3 on this device, best of 10 (burst): the tensor-pipe denominator for `dtype` (bf16, or fp32 with TF32 MMA)."""
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = tf32
+    a = torch.randn(8192, 8192, device="cuda", dtype=dtype)
+    b = torch.randn(8192, 8192, device="cuda", dtype=dtype)
+    for _ in range(3):
+        a @ b
+    best = 1e9
+    for _ in range(10):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        a @ b
+        e1.record()
+        e1.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    torch.backends.cuda.matmul.allow_tf32 = old
+    return 2 * 8192 ** 3 / best / 1e9
+
+
+def run_sweep(a):
+    """C_q in {64,128,256,512} x stride {1,2} x N in {16,64,256} x {bf16, tf32}: QConv2D fwd / dgrad / wgrad (3x3, pad 1, M_A, no bias) and the
+    IQBN kernels on the conv's output shape, each op alone with the L2 swept between launches.  One JSON object on stdout:
+    {"peaks": {...}, "rows": [{C, stride, N, HW, dtype, op, ms, achieved, unit, peak, frac}, ...]}."""
+    import quan_ultralytics_b200 as Q
+    from quan_ultralytics_b200 import ops
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    L = ops.LAYOUT_BHWQC
+    peaks = load_peaks()
+    peaks["bf16_tflops_cublas_now"] = measure_matmul_peak(torch.bfloat16, False)
+    peaks["tf32_tflops_cublas_now"] = measure_matmul_peak(torch.float32, True)
+    flush = torch.zeros(64 << 20, dtype=torch.int32, device=dev)
+    rows = []
+    Cs = [int(v) for v in os.environ.get("QUAN_SWEEP_C", "64,128,256,512").split(",")]
+    Ns = [int(v) for v in os.environ.get("QUAN_SWEEP_N", "16,64,256").split(",")]
+    for dt in ("bf16", "tf32"):
+        dtype = torch.bfloat16 if dt == "bf16" else torch.float32
+        esz = 2 if dt == "bf16" else 4
+        tpeak = peaks["bf16_tflops"] if dt == "bf16" else peaks["tf32_tflops_cublas_now"]
+        for C in Cs:
+            H = 64 if C <= 128 else 32 if C == 256 else 16
+            for s_ in (1, 2):
+                for N in Ns:
+                    torch.manual_seed(1234)
+                    x = torch.randn(N, C, H, H, 4, device=dev).to(dtype).contiguous(memory_format=torch.channels_last_3d)
+                    w = [torch.randn(C, C, 3, 3, device=dev) / (C * 9) ** 0.5 for _ in range(4)]
+                    args = ((s_, s_), (1, 1), (1, 1), 1, ops.M_A)
+                    y = ops.qconv2d_fwd(x, w, None, *args, ops.ALGO_AUTO, L)
+                    dy = torch.randn_like(y)
+                    Ho = y.shape[2]
+                    flops = 8.0 * N * Ho * Ho * C * C * 9
+                    Sy = y.numel() * esz
+                    gamma, beta = torch.ones(C, 4, device=dev), torch.zeros(C, 4, device=dev)
+                    stats = ops.iqbn_train_stats(y, L, gamma, beta, 1e-5, 0.1, None, None)
+                    cnt = float(N * Ho * Ho)
+                    sums = ops.iqbn_bwd_reduce(dy, y, L, stats, gamma, beta, Q.ACT_SILU, cnt)
+                    todo = [
+                        ("qconv2d_fwd", lambda: ops.qconv2d_fwd(x, w, None, *args, ops.ALGO_AUTO, L), "tensor", flops),
+                        ("qconv2d_dgrad", lambda: ops.qconv2d_bwd(dy, x, w, *args, True, False, False), "tensor", flops),
+                        ("qconv2d_wgrad", lambda: ops.qconv2d_bwd(dy, x, w, *args, False, True, False), "tensor", flops),
+                    ]
+                    if s_ == 1:          # the IQBN kernels do not depend on the stride: once per (C, N, dtype)
+                        todo += [
+                            ("iqbn_train_stats", lambda: ops.iqbn_train_stats(y, L, gamma, beta, 1e-5, 0.1, None, None), "hbm", Sy),
+                            ("iqbn_apply_fwd_silu", lambda: ops.iqbn_apply_fwd(y, L, stats, gamma, beta, Q.ACT_SILU), "hbm", 2 * Sy),
+                            ("iqbn_bwd_reduce", lambda: ops.iqbn_bwd_reduce(dy, y, L, stats, gamma, beta, Q.ACT_SILU, cnt), "hbm", 2 * Sy),
+                            ("iqbn_bwd_apply", lambda: ops.iqbn_bwd_apply(dy, y, L, stats, gamma, beta, Q.ACT_SILU, sums, cnt), "hbm", 3 * Sy),
+                        ]
+                    for name, fn, kind, work in todo:
+                        ms = time_op(fn, 6, flush)
+                        ach = work / ms / 1e9 if kind == "tensor" else work / ms / 1e6
+                        pk = tpeak if kind == "tensor" else peaks["hbm_gbs"]
+                        rows.append({"C": C, "stride": s_, "N": N, "HW": H, "dtype": dt, "op": name, "ms": ms, "bound": kind,
+                                     "achieved": ach, "unit": "TFLOP/s" if kind == "tensor" else "GB/s", "peak": pk, "frac": ach / pk})
+                    del x, y, dy, w
+                    torch.cuda.empty_cache()
+    print(json.dumps({"workload": "QConv2D/IQBN layer sweep (BASELINE configs[1])", "peaks": peaks,
+                      "note": "ops timed alone, L2 swept between launches; conv ms include the weight-packing / mix pre-pass / split-K fold "
+                              "kernels of the call; tensor fractions against the measured bf16 burst peak (MEASURED_PEAKS.json) and, for tf32, "
+                              "against cuBLAS TF32 8192^3 measured in this run", "rows": rows}))
+
+
 def main():
     a = parse_args()
     if a.workload.endswith("_trace") and a.impl == "ours":
@@ -842,6 +928,9 @@ def main():
         return
     if a.workload.endswith("_obb"):
         (yolo_reference_arm if a.impl == "reference" else run_yolo_obb)(a)
+        return
+    if a.workload == "sweep":
+        run_sweep(a)
         return
     if a.impl == "reference":
         reference_arm(a)
