@@ -357,6 +357,7 @@ extern "C" int quan_rows_gather(const void* src, void* dst, int64_t nrows, int32
   QUAN_REQUIRE(row_bytes % 4 == 0 && src_ld_bytes % 4 == 0, QUAN_E_UNSUPPORTED, "rows_gather: rows must be multiples of 4 bytes");
   cudaStream_t st = (cudaStream_t)stream;
   const uintptr_t al = reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst) | (uintptr_t)row_bytes | (uintptr_t)src_ld_bytes;
+  QUAN_REQUIRE(al % 4 == 0, QUAN_E_UNSUPPORTED, "rows_gather: pointers must be 4-byte aligned");
   const int vb = (al % 16 == 0) ? 16 : (al % 8 == 0) ? 8 : 4;
   const int64_t n = nrows * (row_bytes / vb);
   const int grid = grid_for(n, 256, 8);

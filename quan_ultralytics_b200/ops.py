@@ -113,7 +113,7 @@ def _gather_channel_slice(x: torch.Tensor) -> Optional[torch.Tensor]:
     if not (x.is_cuda and sc == 1 and sq > C_ and sw == 4 * sq and sh == W * sw and sb == H * sh):
         return None
     esz = x.element_size()
-    if (C_ * esz) % 4 or (sq * esz) % 4:
+    if (C_ * esz) % 4 or (sq * esz) % 4 or x.data_ptr() % 4:
         return None
     out = torch.empty(x.shape, dtype=x.dtype, device=x.device, memory_format=torch.channels_last_3d)
     check(_lib.load().quan_rows_gather(x.data_ptr(), out.data_ptr(), B * H * W * 4, C_ * esz, sq * esz, _stream(x)), "quan_rows_gather")

@@ -18,6 +18,7 @@ def main():
     ap.add_argument("--size", type=int, default=1024)
     ap.add_argument("--scale", default="n")
     ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--nvtx", action="store_true", help="wrap ONE replayed step in the NVTX range 'quanstep' (ncu --nvtx --nvtx-include quanstep/)")
     ap.add_argument("--static-loss", action="store_true", help="loss.OBBLossStatic captured inside the forward graph (whole step = two replays)")
     a = ap.parse_args()
     torch.manual_seed(0)
@@ -41,6 +42,12 @@ def main():
     for _ in range(3):
         step(inputs, largs)
     torch.cuda.synchronize()
+    if a.nvtx:
+        torch.cuda.nvtx.range_push("quanstep")
+        step(inputs, largs)
+        torch.cuda.synchronize()
+        torch.cuda.nvtx.range_pop()
+        return
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps + 1)]
     t0 = time.perf_counter()
     ev[0].record()
