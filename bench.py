@@ -40,7 +40,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="yolo11n_obb", choices=["yolo11n_obb", "yolo11s_obb", "block_stack", "sweep", "yolo11n_trace", "yolo11s_trace", "qresnet34_trace"],
+    ap.add_argument("--workload", default="yolo11n_obb", choices=["yolo11n_obb", "yolo11s_obb", "qresnet34", "qwrn16_2", "block_stack", "sweep", "yolo11n_trace", "yolo11s_trace", "qresnet34_trace"],
                     help="block_stack: BASELINE config[1] sweep point (default, the bench line); yolo11n_trace: replay of "
                          "the 87 QConv2D / 84 IQBN+SiLU calls of QUAN-YOLO11n-OBB at 1024^2 (SURVEY 8(a) histogram); "
                          "yolo11s_trace (config[4], default 8 images) and qresnet34_trace (config[3], 224^2, M_B, biased convs, "
@@ -73,7 +73,7 @@ def parse_args():
     ap.add_argument("--graph", action="store_true", help="yolo11n_trace: capture the step in a CUDA graph (removes host launch overhead)")
     a = ap.parse_args()
     if a.n is None:
-        a.n = {"yolo11n_obb": 16, "yolo11s_obb": 8}.get(a.workload, 64)
+        a.n = {"yolo11n_obb": 16, "yolo11s_obb": 8, "qresnet34": 256, "qwrn16_2": 128}.get(a.workload, 64)
         a.n_default = True
     else:
         a.n_default = False
@@ -918,6 +918,185 @@ def run_sweep(a):
                               "against cuBLAS TF32 8192^3 measured in this run", "rows": rows}))
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# BASELINE configs[0] / [3]: Q-WRN-16-2 (128 x 3 x 32 x 32) and Q-ResNet-34 (256 x 3 x 224 x 224 per GPU, DDP + synced IQBN) training steps
+# ---------------------------------------------------------------------------------------------------------------
+CLASSIFIERS = {"qresnet34": dict(size=224, classes=1000, title="Q-ResNet-34 (create_qrn34_imagenet)", lr=0.1, wd=1e-4, clip=1.0),
+               "qwrn16_2": dict(size=32, classes=10, title="Q-WRN-16-2 (create_qwrn_16_2, Poincare mapping)", lr=0.1, wd=1e-4, clip=1.0)}
+
+
+def classifier_config(a, world):
+    c = CLASSIFIERS[a.workload]
+    return {"workload": f"{c['title']} train step: {a.n} x 3 x {c['size']}^2 per GPU, cross-entropy, clip {c['clip']} + SGD(lr .1, momentum .9, wd 1e-4, nesterov)",
+            "parallelism": f"dp{world}"}
+
+
+def classifier_cpu_reference(a, n_images, steps, warmup):
+    """The unmodified reference model (baseline/_ref/classification, PyTorch path) on the host cores: forward + CE + backward +
+    clip_grad_norm_(1.0) + torch SGD (classification.py:202-203, utils/training.py:77-79), fp32."""
+    from quan_ultralytics_b200 import workloads
+    c = CLASSIFIERS[a.workload]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    model = workloads.build_classifier(a.workload, c["classes"], "cpu", swapped=False).train()
+    opt = torch.optim.SGD(model.parameters(), lr=c["lr"], momentum=0.9, weight_decay=c["wd"], nesterov=True)
+    x, y = workloads.synthetic_classification_batch(n_images, c["size"], c["classes"])
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad(set_to_none=True)
+        torch.nn.functional.cross_entropy(model(x), y).backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), c["clip"])
+        opt.step()
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    return n_images / sec, sec, cores
+
+
+def classifier_reference_arm(a):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    n = 8 if a.workload == "qresnet34" else 128
+    ips, sec, cores = classifier_cpu_reference(a, n, a.steps, a.warmup)
+    print(json.dumps({
+        "impl": "reference", "metric": "train_images_per_sec", "value": ips, "unit": "images/s", "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": classifier_config(a, a.gpus),
+        "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "reference",
+                         "sample": f"{n} images/step of the same training step through the unmodified reference, per-image normalised"},
+        "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+
+
+def run_classifier(a):
+    import quan_ultralytics_b200 as Q
+    from quan_ultralytics_b200 import optim, workloads
+    from quan_ultralytics_b200.graphs import BucketedGradSync, GraphedTrainStep
+    import torch.distributed as dist
+    lib = Q._lib.load()
+    c = CLASSIFIERS[a.workload]
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product has no CPU path); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ac = torch.bfloat16 if a.dtype == "bf16" else None
+    B, S = a.n, c["size"]
+    torch.manual_seed(0)
+    model = workloads.build_classifier(a.workload, c["classes"], dev, swapped=True).train()
+    sync_iqbn = world > 1 and (a.sync_iqbn or a.workload == "qresnet34")      # configs[3] asks for synced IQBN
+    if world > 1:
+        for t in list(model.parameters()) + [b for b in model.buffers() if b.is_floating_point()]:
+            dist.broadcast(t.data, 0)
+        if sync_iqbn:
+            from quan_ultralytics_b200.distributed import convert_sync_iqbn
+            convert_sync_iqbn(model)
+    params = list(model.parameters())
+    opt = optim.ClipSGD([{"params": params, "lr": c["lr"], "weight_decay": c["wd"]}], momentum=0.9, nesterov=True, max_norm=c["clip"])
+    x, y = workloads.synthetic_classification_batch(B, S, c["classes"], dev, seed=1 + rank)
+    sync = BucketedGradSync(params, nbuckets=a.buckets) if world > 1 else None
+    gs = GraphedTrainStep(lambda xx, yy: model(xx), lambda out, xx, yy: (torch.nn.functional.cross_entropy(out.float(), yy), None), opt, [x, y],
+                          params, autocast=ac, grad_sync=sync, capture_loss=True)
+    run = lambda: gs(gs.static_inputs)[0]
+    # e2e: uint8 images + labels from pinned host memory, normalised on the device (classification/utils/data_loading.py:90 mean / std)
+    g = torch.Generator().manual_seed(100 + rank)
+    img_host = torch.randint(0, 256, (B, 3, S, S), dtype=torch.uint8, generator=g).pin_memory()
+    y_host = y.cpu().pin_memory()
+    mean = torch.tensor([0.485, 0.456, 0.406], device=dev).view(1, 3, 1, 1) * 255
+    inv_std = 1.0 / (torch.tensor([0.229, 0.224, 0.225], device=dev).view(1, 3, 1, 1) * 255)
+    stage = [(torch.empty_like(img_host, device=dev), torch.empty_like(y)) for _ in range(2)]
+    copy_stream = torch.cuda.Stream(device=dev)
+    copied, consumed, done = ([torch.cuda.Event(), torch.cuda.Event()] for _ in range(3))
+    loss_host = [torch.zeros(1).pin_memory() for _ in range(2)]
+    st = {"i": 0, "primed": False}
+
+    def prefetch(slot):
+        copy_stream.wait_event(consumed[slot])
+        with torch.cuda.stream(copy_stream):
+            stage[slot][0].copy_(img_host, non_blocking=True)
+            stage[slot][1].copy_(y_host, non_blocking=True)
+            copied[slot].record(copy_stream)
+
+    def e2e_step():
+        i = st["i"]
+        cur = i & 1
+        if not st["primed"]:
+            consumed[0].record()
+            consumed[1].record()
+            prefetch(cur)
+            st["primed"] = True
+        prefetch(cur ^ 1)
+        torch.cuda.current_stream().wait_event(copied[cur])
+        gs.static_inputs[0].copy_(stage[cur][0])
+        gs.static_inputs[0].sub_(mean).mul_(inv_std)
+        gs.static_inputs[1].copy_(stage[cur][1])
+        consumed[cur].record()
+        loss = run()
+        loss_host[cur].copy_(loss.detach().reshape(1).float(), non_blocking=True)
+        done[cur].record()
+        if i > 0:
+            done[cur ^ 1].synchronize()
+        st["i"] = i + 1
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(max(a.warmup, 3)):
+        run()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    ms = timed(run, a.steps)
+    for _ in range(2):
+        e2e_step()
+    torch.cuda.synchronize()
+    st["primed"] = False
+    ms_e2e = timed(e2e_step, a.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    imgs = B * world * a.steps
+    if rank == 0:
+        line = {"metric": "train_images_per_sec", "value": imgs / (ms / 1e3), "unit": "images/s", "n_gpus": world, "steps": a.steps,
+                "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": a.dtype, "data": "synthetic", "config": classifier_config(a, world),
+                "implementation": {"step": "2 CUDA graphs (forward+loss | backward+all-reduce+optimizer)", "sync_iqbn": bool(sync_iqbn),
+                                   "grad_buckets": a.buckets if world > 1 else None, "params": sum(p.numel() for p in params)},
+                "e2e": {"value": imgs / (ms_e2e / 1e3), "unit": "images/s", "h2d_bytes_per_step": img_host.numel() + 8 * B, "d2h_bytes_per_step": 4},
+                "gpu_launches": int(gs.captured_launches * a.steps), "clocks": clocks, "final_loss": float(loss_host[(st["i"] - 1) & 1][0])}
+        if world == 1 and not a.no_cpu_baseline:
+            n = 8 if a.workload == "qresnet34" else 128
+            ips, sec, cores = classifier_cpu_reference(a, n, min(a.cpu_steps, 2), 1)
+            line["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": cores, "kind": "reference",
+                                    "sample": f"{n} images/step through the unmodified reference model (baseline/_ref), fp32"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        os._exit(0)
+
+
 def main():
     a = parse_args()
     if a.workload.endswith("_trace") and a.impl == "ours":
@@ -931,6 +1110,9 @@ def main():
         return
     if a.workload == "sweep":
         run_sweep(a)
+        return
+    if a.workload in ("qresnet34", "qwrn16_2"):
+        (classifier_reference_arm if a.impl == "reference" else run_classifier)(a)
         return
     if a.impl == "reference":
         reference_arm(a)
