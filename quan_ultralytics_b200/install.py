@@ -35,10 +35,45 @@ def _swap(mod, name, new) -> None:
 
 
 def uninstall() -> None:
-    """Put the reference's own classes back (tests build the swapped and the unswapped graph in one process)."""
+    """Put the reference's own classes back (tests build the swapped and the unswapped graph in one process).  A module that was
+    first imported AFTER a swap (`from quaternion.qconv import QConv2D` in models/quaternion_blocks.py) bound our class as its
+    "original": every loaded module that still holds one of the installed classes gets the reference class back too."""
+    restored = {}
     while _originals:
         mod, name, old = _originals.pop()
+        restored[id(getattr(mod, name))] = old
         setattr(mod, name, old)
+    _rebind(restored)
+
+
+_REF_PREFIXES = ("ultralytics", "quaternion", "models")
+
+
+def _rebind(mapping: dict) -> None:
+    """Replace classes by identity (`mapping`: id(class) -> replacement) wherever the reference's loaded modules still hold them:
+    module globals bound by `from x import Y` before / after a swap, and DEFAULT ARGUMENTS evaluated at import time
+    (`norm_class: nn.Module = IQBN`, classification/models/quaternion_blocks.py:91)."""
+    if not mapping:
+        return
+    for modname, mod in list(sys.modules.items()):
+        d = getattr(mod, "__dict__", None)
+        if not isinstance(d, dict) or not modname.split(".")[0] in _REF_PREFIXES:
+            continue
+        for name, val in list(d.items()):
+            if not isinstance(val, type):
+                continue
+            if id(val) in mapping:
+                setattr(mod, name, mapping[id(val)])
+                continue
+            if getattr(val, "__module__", None) != modname:
+                continue
+            init = val.__dict__.get("__init__")
+            if init is None:
+                continue
+            if init.__defaults__ and any(id(v) in mapping for v in init.__defaults__):
+                init.__defaults__ = tuple(mapping.get(id(v), v) for v in init.__defaults__)
+            if init.__kwdefaults__ and any(id(v) in mapping for v in init.__kwdefaults__.values()):
+                init.__kwdefaults__ = {k: mapping.get(id(v), v) for k, v in init.__kwdefaults__.items()}
 
 
 _SUPPORTED_HEADS = ((1, 2), (2, 4), (4, 8), (8, 16))       # (key_dim, head_dim) instantiations of quan_qattention_*
@@ -102,4 +137,5 @@ def install(ultralytics: bool = True, classification: bool = True) -> dict:
                 _swap(mod, "QuaternionMaxPool", M.QuaternionMaxPool)
                 names.append("QuaternionMaxPool")
             done[modname] = names
+    _rebind({id(old): getattr(mod, name) for mod, name, old in _originals})
     return done
