@@ -10,14 +10,18 @@ Nothing here is needed on a box without the reference; it is plumbing, not compu
 from __future__ import annotations
 
 import importlib
+import os
 import sys
 import types
+
+import torch
 
 from . import modules as M
 from . import quaternion_ops as shim
 
 _SWAP = ("QConv2D", "IQBN", "Conv", "DWConv", "QUpsample", "QuaternionMaxPool", "QER")
 _originals = []          # (module, attribute, reference class) of every swap, for uninstall()
+_derived = {}            # reference class -> our subclass of it (QAttention, OBB): one subclass per reference class
 
 
 def install_extension_shim(mixing: str = "A") -> types.ModuleType:
@@ -96,8 +100,62 @@ def _make_qattention(ref_cls):
     unused IQLN `norm`, block.py:1506) stays the reference's; only `forward` is ours."""
     if getattr(ref_cls, "_quan_fused", False):
         return ref_cls
-    return type("QAttention", (ref_cls,), {"forward": _qattention_forward, "_reference_forward": ref_cls.forward, "_quan_fused": True,
-                                           "__module__": __name__, "__doc__": _qattention_forward.__doc__})
+    if ref_cls not in _derived:
+        _derived[ref_cls] = type("QAttention", (ref_cls,), {"forward": _qattention_forward, "_reference_forward": ref_cls.forward,
+                                                            "_quan_fused": True, "__module__": __name__,
+                                                            "__doc__": _qattention_forward.__doc__})
+    return _derived[ref_cls]
+
+
+_branch_streams = {}
+
+
+def _head_streams(device, n):
+    key = (device.type, device.index)
+    pool = _branch_streams.setdefault(key, [])
+    while len(pool) < n:
+        pool.append(torch.cuda.Stream(device=device))
+    return pool[:n]
+
+
+def _obb_forward(self, x):
+    """OBB.forward / Detect.forward in training mode (head.py:137-147, :338-350) with the nine independent branches — box (cv2), class
+    (cv3) and angle (cv4) towers of the three pyramid levels, each two or four `Conv` blocks and a QER — issued on nine streams:
+    the P4 / P5 towers are latency-bound chains of 5-20 us kernels that fit beside the P3 towers instead of queueing behind them.
+    The fork / join is stream events only, so a captured step replays it as parallel graph branches and autograd runs every
+    tower's backward on its forward stream.  Same outputs as the reference: ([cat(box_i, cls_i, 1)], angle)."""
+    import math
+    if (not self.training or self.end2end or not x[0].is_cuda or os.environ.get("QUAN_HEAD_STREAMS", "1") == "0"):
+        return self._reference_forward(x)
+    bs = x[0].shape[0]
+    main = torch.cuda.current_stream(x[0].device)
+    towers = [(i, j, t[i]) for i in range(self.nl) for j, t in enumerate((self.cv2, self.cv3, self.cv4))]
+    streams = _head_streams(x[0].device, len(towers))
+    outs = {}
+    for (i, j, tower), s in zip(towers, streams):
+        s.wait_stream(main)
+        with torch.cuda.stream(s):
+            outs[i, j] = tower(x[i])
+        x[i].record_stream(s)
+    for (i, j, _), s in zip(towers, streams):
+        main.wait_stream(s)
+        outs[i, j].record_stream(main)
+    angle = torch.cat([outs[i, 2].view(bs, self.ne, -1) for i in range(self.nl)], 2)
+    angle = (angle.sigmoid() - 0.25) * math.pi
+    for i in range(self.nl):
+        x[i] = torch.cat((outs[i, 0], outs[i, 1]), 1)
+    return x, angle
+
+
+def _make_obb(ref_cls):
+    """Subclass of the REFERENCE's OBB head: constructor, parameters and every non-training path are the reference's."""
+    if getattr(ref_cls, "_quan_streams", False):
+        return ref_cls
+    if ref_cls in _derived:
+        return _derived[ref_cls]
+    _derived[ref_cls] = type("OBB", (ref_cls,), {"forward": _obb_forward, "_reference_forward": ref_cls.forward, "_quan_streams": True,
+                                    "__module__": __name__, "__doc__": _obb_forward.__doc__})
+    return _derived[ref_cls]
 
 
 def install(ultralytics: bool = True, classification: bool = True) -> dict:
@@ -118,6 +176,10 @@ def install(ultralytics: bool = True, classification: bool = True) -> dict:
                 ref_cls = importlib.import_module("ultralytics.nn.modules.block").QAttention
                 _swap(mod, "QAttention", _make_qattention(ref_cls))
                 names.append("QAttention")
+            if hasattr(mod, "OBB") and isinstance(getattr(mod, "OBB"), type):   # head.py:322-350: branch-parallel training forward
+                ref_cls = importlib.import_module("ultralytics.nn.modules.head").OBB
+                _swap(mod, "OBB", _make_obb(ref_cls))
+                names.append("OBB")
             done[modname] = names
     if classification:
         for modname in ("quaternion.qconv", "quaternion", "models.quaternion_blocks", "models.quaternion_models",
