@@ -237,9 +237,50 @@ int quan_conv_block_eval_fwd(const void* x, const float* const w[4], const float
                              const quan_conv_dims* d, int dtype, int layout, const float* mix, int algo, float eps, int act,
                              void* conv_ws, size_t conv_ws_bytes, void* stream);
 
+/* ---- pack plan: all packed weights of a training step in one launch ------------------------------------------------------------
+ * The tensor-core engine reads weights in a packed operand layout (per component or, for narrow layers, the dense Hamilton matrix with
+ * the mixing matrix folded in), rebuilt from the fp32 masters by a small kernel in front of every forward and every dgrad.  Weights
+ * change once per optimizer step, so a step driver can hoist all of them into one launch:
+ *   quan_pack_plan_record(1)  start noting every pack the convolutions perform (shape, form, dtype, mix, weight pointers)
+ *   ... run one training step ...
+ *   quan_pack_plan_record(0)  stop; returns the number of distinct packs
+ *   quan_pack_plan_bytes      arena bytes for all of them (*table_bytes: bytes of the device job table)
+ *   quan_pack_plan_commit     bind caller-owned device memory (arena 1024-byte aligned) and ACTIVATE: from now on a convolution whose
+ *                             pack is in the plan reads its slot of the arena and launches no pack kernel — the caller must run
+ *   quan_pack_plan_run        (one launch: every slot rebuilt from the current masters) after each weight update and before the
+ *                             first convolution of the step, on a stream ordered before them (inside a captured graph: first node)
+ *   quan_pack_plan_release    deactivate (kernels already captured keep their arena pointers; the arena must outlive them).
+ * One plan per process; the reference has no counterpart (its extension re-reads the masters in every kernel). */
+int quan_pack_plan_record(int on);
+size_t quan_pack_plan_bytes(size_t* table_bytes);
+int quan_pack_plan_commit(void* arena, size_t arena_bytes, void* table, size_t table_bytes, void* stream);
+int quan_pack_plan_run(void* stream);
+int quan_pack_plan_release(void);
+
 /* Channel-slice gather: the dense copy of a channel `chunk` / `split` of a BHWQC tensor (what `.contiguous()` at conv.py:441 does for the
  * strided halves C2f / C3k2 / QC2PSA pass on, block.py:350-352): dst row r (row_bytes bytes) = src + r * src_ld_bytes. */
 int quan_rows_gather(const void* src, void* dst, int64_t nrows, int32_t row_bytes, int64_t src_ld_bytes, void* stream);
+
+/* ---- QER: quaternion -> real extraction of the detection heads ------------------------------------------
+ * Replaces `QER.forward` ultralytics/nn/modules/head.py:40-47 — `x.permute(0, 1, 4, 2, 3).contiguous().view(B, 4C, H, W)` followed by
+ * the real 1x1 `nn.Conv2d(4C, N)` (`output_proj`, head.py:36; input channel index c*4 + q) — and its autograd, reading the
+ * activation in QUAN_LAYOUT_BHWQC (a pixel is a row of 4C contiguous values, index q*C + c) without the permute copy.
+ *   x      [npix][4][C]  activation rows (npix = B*H*W), dense
+ *   weight [N][4C]       fp32, the reference's `output_proj.weight` as stored (index c*4 + q);  bias [N] fp32 or NULL
+ *   out    npix rows of N values, `out_ld` elements apart (>= N; any alignment): `out_ld` = the channel count of the concatenated
+ *          head tensor lets the box / class extractions write straight into `torch.cat((cv2, cv3), 1)` of head.py:143
+ *   dy     npix rows of N values, `dy_ld` apart (the gradient arrives as a channel slice of the concatenated tensor's gradient)
+ *   dx     like x (NULL: skip);  dweight [N][4C] / dbias [N] fp32 (dweight NULL: skip both; dbias NULL: skip it)
+ *   out_writable / dy_readable: columns of every out / dy row (counted from the row pointer; N <= value <= pitch, smaller values mean
+ *          N) that belong to this call — row padding.  A ragged width (15 classes in a 16-column slot) then moves as whole 16-byte
+ *          vectors: the forward writes zeros into the padding, the backward reads it and ignores what it holds.
+ * 4C <= 256 and N <= 64; bf16 needs C % 4 == 0.  bf16 contracts with fp32 accumulation (operands as stored, weight rounded to bf16);
+ * fp32 is exact fp32 FMA.  workspace: quan_qer_workspace_bytes (per-CTA partial weight gradients, folded deterministically). */
+size_t quan_qer_workspace_bytes(int64_t npix, int32_t C, int32_t N, int dtype);
+int quan_qer_fwd(const void* x, const float* weight, const float* bias, void* out, int64_t npix, int32_t C, int32_t N, int64_t out_ld,
+                 int32_t out_writable, int dtype, void* stream);
+int quan_qer_bwd(const void* dy, int64_t dy_ld, int32_t dy_readable, const void* x, const float* weight, void* dx, float* dweight, float* dbias,
+                 int64_t npix, int32_t C, int32_t N, int dtype, void* workspace, size_t ws_bytes, void* stream);
 
 /* ---- QAttention core ---------------------------------------------------------------------------------
  * Replaces the attention arithmetic of `QAttention.forward` ultralytics/nn/modules/block.py:1520-1540 (split of the qkv QConv2D output,
@@ -278,13 +319,15 @@ int quan_rotated_tal_assign(const float* pd_scores, const float* pd_bboxes, cons
  *                            AND d(total)/d(feats[l]), d(total)/d(pred_angle) in the layouts / dtype of the inputs, from the assigner's
  *                            target_bboxes [B][A][5] (pixels), target_scores [B][A][nc], fg_mask [B][A] (bytes).  Terms: BCE with logits
  *                            (:998), (1 - ProbIoU) * weight (:366-368, metrics.py:198-233), DFL (:306-329), quaternion geodesic angle
- *                            (:870-903); all divided by max(sum target_scores, 1).  scratch: 5 doubles. */
+ *                            (:870-903); all divided by max(sum target_scores, 1).  scratch: 5 doubles.
+ * feat_ld: [3] row pitches (elements) of feats[l] AND d_feats[l], or NULL for dense rows of `no`: the fused head (quan_qer_fwd with
+ * out_ld) pads the concatenated rows to a multiple of 8 elements so that every row starts on a 16-byte boundary. */
 int quan_obb_decode(const void* const feats[3], const void* pred_angle, const int32_t* hw, const float* strides, int32_t B, int32_t nc,
-                    int32_t reg_max, float* pd_scores, float* pd_bboxes, int dtype, void* stream);
+                    int32_t reg_max, const int32_t* feat_ld, float* pd_scores, float* pd_bboxes, int dtype, void* stream);
 int quan_obb_loss_fwd_bwd(const void* const feats[3], const void* pred_angle, const int32_t* hw, const float* strides, int32_t B, int32_t nc,
                           int32_t reg_max, const float* target_bboxes, const float* target_scores, const uint8_t* fg_mask, float box_gain,
-                          float cls_gain, float dfl_gain, float angle_gain, void* const d_feats[3], void* d_angle, double* scratch,
-                          float* items, float* total, int dtype, void* stream);
+                          float cls_gain, float dfl_gain, float angle_gain, const int32_t* feat_ld, void* const d_feats[3], void* d_angle,
+                          double* scratch, float* items, float* total, int dtype, void* stream);
 
 /* ---- optimizer step -------------------------------------------------------------------------------
  * Replaces `BaseTrainer.optimizer_step` ultralytics/engine/trainer.py:586-594 — torch.nn.utils.clip_grad_norm_(max_norm) followed by

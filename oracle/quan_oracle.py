@@ -301,3 +301,22 @@ def qattention_bwd(d_o, qkv, heads, key_dim, head_dim, scale=None):
     dq = np.einsum("bhqnm,bhkmq->bhknq", ds, k)
     dk = np.einsum("bhqnm,bhknq->bhkmq", ds, q)
     return np.concatenate([dq.reshape(B, heads * K, H, W, Q), dk.reshape(B, heads * K, H, W, Q), dv.reshape(B, heads * V, H, W, Q)], axis=1)
+
+
+# ---- QER: quaternion -> real extraction of the heads ------------------------------------------------------
+def qer_fwd(x, weight, bias=None):
+    """ultralytics/nn/modules/head.py:40-47: x [B,C,H,W,4] -> permute(0,1,4,2,3).view(B, 4C, H, W) (channel index c*4 + q) -> the real
+    1x1 convolution `output_proj` (head.py:36): out[b,n,h,w] = bias[n] + sum_{c,q} weight[n, c*4+q] x[b,c,h,w,q]."""
+    B, C_, H, W, Q = x.shape
+    w = np.asarray(weight).reshape(weight.shape[0], C_, Q)
+    out = np.einsum("bchwq,ncq->bnhw", x, w)
+    return out if bias is None else out + np.asarray(bias)[None, :, None, None]
+
+
+def qer_bwd(dy, x, weight):
+    """VJP of qer_fwd: (dx [B,C,H,W,4], dweight like weight, dbias [N])."""
+    B, C_, H, W, Q = x.shape
+    w = np.asarray(weight).reshape(weight.shape[0], C_, Q)
+    dx = np.einsum("bnhw,ncq->bchwq", dy, w)
+    dw = np.einsum("bnhw,bchwq->ncq", dy, x).reshape(weight.shape)
+    return dx, dw, dy.sum(axis=(0, 2, 3))

@@ -71,14 +71,22 @@ PROTOTYPES = {
                                         _vp, _sz, _vp]),
     "quan_qconv2d_bwd_premixed": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _pdims, _int, _int, _vp, _int, _vp, _sz, _vp]),
     "quan_qconv2d_bwd_wants_mixed": (_int, [_pdims, _int, _int, _int, _int, _int]),
+    "quan_pack_plan_record": (_int, [_int]),
+    "quan_pack_plan_bytes": (_sz, [C.POINTER(C.c_size_t)]),
+    "quan_pack_plan_commit": (_int, [_vp, _sz, _vp, _sz, _vp]),
+    "quan_pack_plan_run": (_int, [_vp]),
+    "quan_pack_plan_release": (_int, []),
     "quan_rows_gather": (_int, [_vp, _vp, C.c_int64, _i32, C.c_int64, _vp]),
+    "quan_qer_workspace_bytes": (_sz, [C.c_int64, _i32, _i32, _int]),
+    "quan_qer_fwd": (_int, [_vp, _vp, _vp, _vp, C.c_int64, _i32, _i32, C.c_int64, _i32, _int, _vp]),
+    "quan_qer_bwd": (_int, [_vp, C.c_int64, _i32, _vp, _vp, _vp, _vp, _vp, C.c_int64, _i32, _i32, _int, _vp, _sz, _vp]),
     "quan_qattention_fwd": (_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f, _int, _int, _vp]),
     "quan_qattention_bwd": (_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _f, _int, _int, _vp]),
     "quan_rotated_tal_workspace_bytes": (_sz, [_i32, _i32, _i32]),
     "quan_rotated_tal_assign": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _f, _f, _f, _vp, _vp, _vp, _vp,
                                        _vp, _sz, _vp]),
-    "quan_obb_decode": (_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _int, _vp]),
-    "quan_obb_loss_fwd_bwd": (_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _f, _f, _f, _f, _vp, _vp, _vp, _vp, _vp, _int, _vp]),
+    "quan_obb_decode": (_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _int, _vp]),
+    "quan_obb_loss_fwd_bwd": (_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _f, _f, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _int, _vp]),
     "quan_sgd_clip_step": (_int, [_vp, _int, _vp, _vp, _int, _vp, _vp, _int, _vp]),
     "quan_ema_update": (_int, [_vp, _int, _vp, _vp, _vp]),
 }

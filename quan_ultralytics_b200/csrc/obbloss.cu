@@ -71,6 +71,7 @@ struct ObbLossArgs {
   int H[3], W[3];
   float stride[3];
   int B, A, nc, reg_max, no;
+  int ld[3];                       // row pitch (elements) of feat / dfeat per level: >= no (padded rows of the fused head tensor)
   const float* t_boxes;            // [B][A][5] pixels
   const float* t_scores;           // [B][A][nc]
   const unsigned char* fg;         // [B][A]
@@ -92,8 +93,8 @@ __global__ void __launch_bounds__(OL_THREADS) obb_loss_kernel(ObbLossArgs p) {
     const int Wl = p.W[l], Al = p.H[l] * Wl;
     const float st = p.stride[l];
     const float ax = (float)(al % Wl) + 0.5f, ay = (float)(al / Wl) + 0.5f;
-    const T* row = reinterpret_cast<const T*>(p.feat[l]) + ((int64_t)b * Al + al) * p.no;
-    T* drow = reinterpret_cast<T*>(p.dfeat[l]) + ((int64_t)b * Al + al) * p.no;
+    const T* row = reinterpret_cast<const T*>(p.feat[l]) + ((int64_t)b * Al + al) * p.ld[l];
+    T* drow = reinterpret_cast<T*>(p.dfeat[l]) + ((int64_t)b * Al + al) * p.ld[l];
     const float tss = fmaxf((float)*p.tss, 1.f);
     const float scale = (float)p.B / tss;                       // d(total)/d(raw sum term) before the gain
     const int R = p.reg_max;
@@ -201,7 +202,7 @@ __global__ void __launch_bounds__(OL_THREADS) obb_decode_kernel(ObbLossArgs p, f
   const int Wl = p.W[l], Al = p.H[l] * Wl, R = p.reg_max;
   const float st = p.stride[l];
   const float ax = (float)(al % Wl) + 0.5f, ay = (float)(al / Wl) + 0.5f;
-  const T* row = reinterpret_cast<const T*>(p.feat[l]) + ((int64_t)b * Al + al) * p.no;
+  const T* row = reinterpret_cast<const T*>(p.feat[l]) + ((int64_t)b * Al + al) * p.ld[l];
   float dist[4];
   for (int k = 0; k < 4; ++k) {
     float mx = -INFINITY, sum = 0.f, ex = 0.f;
@@ -254,7 +255,7 @@ __global__ void obb_tss_kernel(const float* __restrict__ ts, int64_t n, double* 
 extern "C" {
 
 int quan_obb_decode(const void* const feats[3], const void* pred_angle, const int32_t* hw, const float* strides, int32_t B, int32_t nc,
-                    int32_t reg_max, float* pd_scores, float* pd_bboxes, int dtype, void* stream) {
+                    int32_t reg_max, const int32_t* feat_ld, float* pd_scores, float* pd_bboxes, int dtype, void* stream) {
   using namespace quan;
   QUAN_REQUIRE(feats && pred_angle && hw && strides && pd_scores && pd_bboxes, QUAN_E_ARG, "obb_decode: null pointer");
   QUAN_REQUIRE(B > 0 && nc > 0 && reg_max >= 2 && reg_max <= OL_MAXREG, QUAN_E_ARG, "obb_decode: B=%d nc=%d reg_max=%d", B, nc, reg_max);
@@ -263,6 +264,8 @@ int quan_obb_decode(const void* const feats[3], const void* pred_angle, const in
   for (int l = 0; l < 3; ++l) {
     QUAN_REQUIRE(feats[l] && hw[2 * l] > 0 && hw[2 * l + 1] > 0, QUAN_E_ARG, "obb_decode: level %d", l);
     p.feat[l] = feats[l]; p.H[l] = hw[2 * l]; p.W[l] = hw[2 * l + 1]; p.stride[l] = strides[l];
+    p.ld[l] = feat_ld != nullptr ? feat_ld[l] : 4 * reg_max + nc;
+    QUAN_REQUIRE(p.ld[l] >= 4 * reg_max + nc, QUAN_E_ARG, "obb_decode: feat_ld[%d] = %d below the row width", l, p.ld[l]);
     A += (int64_t)hw[2 * l] * hw[2 * l + 1];
   }
   QUAN_REQUIRE(A * B < (1ll << 31), QUAN_E_UNSUPPORTED, "obb_decode: too many anchors");
@@ -278,8 +281,8 @@ int quan_obb_decode(const void* const feats[3], const void* pred_angle, const in
 
 int quan_obb_loss_fwd_bwd(const void* const feats[3], const void* pred_angle, const int32_t* hw, const float* strides, int32_t B, int32_t nc,
                           int32_t reg_max, const float* target_bboxes, const float* target_scores, const uint8_t* fg_mask, float box_gain,
-                          float cls_gain, float dfl_gain, float angle_gain, void* const d_feats[3], void* d_angle, double* scratch,
-                          float* items, float* total, int dtype, void* stream) {
+                          float cls_gain, float dfl_gain, float angle_gain, const int32_t* feat_ld, void* const d_feats[3], void* d_angle,
+                          double* scratch, float* items, float* total, int dtype, void* stream) {
   using namespace quan;
   QUAN_REQUIRE(feats && d_feats && pred_angle && d_angle && hw && strides && target_bboxes && target_scores && fg_mask && scratch && items && total,
                QUAN_E_ARG, "obb_loss: null pointer");
@@ -290,6 +293,8 @@ int quan_obb_loss_fwd_bwd(const void* const feats[3], const void* pred_angle, co
   for (int l = 0; l < 3; ++l) {
     QUAN_REQUIRE(feats[l] && d_feats[l] && hw[2 * l] > 0 && hw[2 * l + 1] > 0, QUAN_E_ARG, "obb_loss: level %d", l);
     p.feat[l] = feats[l]; p.dfeat[l] = d_feats[l]; p.H[l] = hw[2 * l]; p.W[l] = hw[2 * l + 1]; p.stride[l] = strides[l];
+    p.ld[l] = feat_ld != nullptr ? feat_ld[l] : 4 * reg_max + nc;
+    QUAN_REQUIRE(p.ld[l] >= 4 * reg_max + nc, QUAN_E_ARG, "obb_loss: feat_ld[%d] = %d below the row width", l, p.ld[l]);
     A += (int64_t)hw[2 * l] * hw[2 * l + 1];
   }
   QUAN_REQUIRE(A * B < (1ll << 31), QUAN_E_UNSUPPORTED, "obb_loss: too many anchors");

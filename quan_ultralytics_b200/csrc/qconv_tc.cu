@@ -17,11 +17,13 @@
 #include "qconv_internal.cuh"
 #include "tc_ptx.cuh"
 #include <mutex>
+#include <vector>
 #include <stdlib.h>
 #include <string.h>
 #include <unordered_map>
 
 namespace quan {
+static size_t packed_weight_bytes_of(const quan_conv_dims& d, int dtype, int dense);
 
 // ---------------------------------------------------------------------------------------------------------------
 // driver entry point for TMA descriptor encoding (libcuda is not linked: fetched through the runtime)
@@ -1308,6 +1310,105 @@ static int pack_weights_dense(const float* const w[4], const float* bias_r, void
   return QUAN_OK;
 }
 
+// ---- pack plan: every layer's packed weights in ONE launch per optimizer step ------------------------------------------------
+// Weights change once per step but a narrow layer's chain used to start with its own 2.5 us pack kernel, in forward AND in dgrad
+// (127 launches of the QUAN-YOLO11n step).  A train-step driver (graphs.GraphedTrainStep) records the packs of a warm-up step,
+// commits them to one caller-owned arena and runs quan_pack_plan_run at the top of the step: while the plan is active every
+// tc_fwd_t / tc_dgrad_t whose (weights, form, dtype, shape, mix) is in the plan reads its slot of the arena and launches nothing.
+enum PackForm { PACK_SEP_FWD = 0, PACK_SEP_DGRAD = 1, PACK_DENSE_FWD = 2, PACK_DENSE_DGRAD = 3 };
+struct PackJob {
+  const float* w[4];
+  const float* bias_r;
+  void* out;
+  float* bias_out;
+  int Co, Ci, taps, form, esz;
+  int block0, nblocks;
+  int64_t total;
+  Mix16 mix;
+};
+struct PackPlan {
+  std::mutex mu;
+  bool recording = false, active = false;
+  std::vector<PackJob> jobs;
+  std::vector<size_t> offset, bytes;
+  const PackJob* table_dev = nullptr;
+  int total_blocks = 0;
+};
+static PackPlan& pack_plan() {
+  static PackPlan p;
+  return p;
+}
+static bool same_job(const PackJob& a, const float* const w[4], const float* bias_r, int form, int esz, const quan_conv_dims& d, const Mix16& M) {
+  return a.w[0] == w[0] && a.w[1] == w[1] && a.w[2] == w[2] && a.w[3] == w[3] && a.bias_r == bias_r && a.form == form && a.esz == esz &&
+         a.Co == d.Co && a.Ci == d.Ci && a.taps == d.kH * d.kW && memcmp(a.mix.m, M.m, sizeof(M.m)) == 0;
+}
+// the arena slot of this pack when the plan is active (else nullptr; while recording, the pack is noted for the next commit)
+static void* planned_pack(const float* const w[4], const float* bias_r, int form, int dtype, const quan_conv_dims& d, const Mix16& M) {
+  PackPlan& pl = pack_plan();
+  if (!pl.recording && !pl.active) return nullptr;
+  std::lock_guard<std::mutex> lock(pl.mu);
+  const int esz = dtype == QUAN_BF16 ? 2 : 4;
+  for (size_t i = 0; i < pl.jobs.size(); ++i)
+    if (same_job(pl.jobs[i], w, bias_r, form, esz, d, M)) return pl.active ? pl.jobs[i].out : nullptr;
+  if (pl.recording) {
+    PackJob j = {};
+    for (int q = 0; q < 4; ++q) j.w[q] = w[q];
+    j.bias_r = bias_r; j.Co = d.Co; j.Ci = d.Ci; j.taps = d.kH * d.kW; j.form = form; j.esz = esz; j.mix = M;
+    const bool dense = form >= PACK_DENSE_FWD;
+    j.total = (int64_t)(dense ? 16 : 4) * j.taps * d.Co * d.Ci;
+    pl.jobs.push_back(j);
+    pl.bytes.push_back(packed_weight_bytes_of(d, dtype, dense));
+  }
+  return nullptr;
+}
+
+// one element of job j (index i in the packed order of its form; same arithmetic as the per-layer kernels above)
+template <typename T>
+__device__ __forceinline__ void pack_one(const PackJob& j, int64_t i) {
+  const int Co = j.Co, Ci = j.Ci, taps = j.taps;
+  float v;
+  if (j.form == PACK_SEP_FWD) {                    // [q][tap][co][ci]
+    const int ci = (int)(i % Ci);
+    int64_t r = i / Ci;
+    const int co = (int)(r % Co); r /= Co;
+    const int tap = (int)(r % taps), q = (int)(r / taps);
+    v = round_operand(__ldg(j.w[q] + ((int64_t)co * Ci + ci) * taps + tap), sizeof(T));
+  } else if (j.form == PACK_SEP_DGRAD) {           // [q][t][ci][co], flipped taps
+    const int co = (int)(i % Co);
+    int64_t r = i / Co;
+    const int ci = (int)(r % Ci); r /= Ci;
+    const int t = (int)(r % taps), q = (int)(r / taps);
+    v = round_operand(__ldg(j.w[q] + ((int64_t)co * Ci + ci) * taps + (taps - 1 - t)), sizeof(T));
+  } else {
+    const bool dg = j.form == PACK_DENSE_DGRAD;
+    const int N = dg ? 4 * Ci : 4 * Co, K = dg ? 4 * Co : 4 * Ci;
+    const int k = (int)(i % K);
+    int64_t r = i / K;
+    const int n = (int)(r % N), t = (int)(r / N);
+    int pc, q, co, ci, tap;
+    if (dg) { q = n / Ci; ci = n % Ci; pc = k / Co; co = k % Co; tap = taps - 1 - t; }
+    else { pc = n / Co; co = n % Co; q = k / Ci; ci = k % Ci; tap = t; }
+    v = round_operand(j.mix.m[pc * 4 + q] * __ldg(j.w[q] + ((int64_t)co * Ci + ci) * taps + tap), sizeof(T));
+    if (!dg && j.bias_out != nullptr && i < 4 * Co) j.bias_out[i] = j.bias_r ? j.mix.m[(i / Co) * 4] * __ldg(j.bias_r + i % Co) : 0.f;
+  }
+  reinterpret_cast<T*>(j.out)[i] = from_f32<T>(v);
+}
+
+__global__ void __launch_bounds__(256) pack_plan_kernel(const PackJob* __restrict__ jobs, int njobs) {
+  pdl_prologue();
+  int lo = 0, hi = njobs - 1;                      // the job whose block range holds blockIdx.x
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (jobs[mid].block0 <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const PackJob& j = jobs[lo];
+  const int64_t step = (int64_t)j.nblocks * 256;
+  for (int64_t i = (int64_t)((int)blockIdx.x - j.block0) * 256 + threadIdx.x; i < j.total; i += step) {
+    if (j.esz == 2) pack_one<__nv_bfloat16>(j, i);
+    else pack_one<float>(j, i);
+  }
+}
+
 // ---- shapes -------------------------------------------------------------------------------------------------------
 // dense = 1: the conv over all 4*C_q real channels (nq = 1); dense = 0: one conv per component (nq = 4)
 static IgemmShape fwd_shape(const quan_conv_dims& d, int dense) {
@@ -1341,6 +1442,8 @@ static IgemmShape dgrad_shape(const quan_conv_dims& d, int dense) {
   return s;
 }
 
+static size_t packed_weight_bytes(const quan_conv_dims& d, int dtype, int dense);
+static size_t packed_weight_bytes_of(const quan_conv_dims& d, int dtype, int dense) { return packed_weight_bytes(d, dtype, dense); }
 static size_t packed_weight_bytes(const quan_conv_dims& d, int dtype, int dense) {
   const size_t w = ((size_t)(dense ? 16 : 4) * d.kH * d.kW * d.Co * d.Ci * (dtype == QUAN_BF16 ? 2 : 4) + 1023) / 1024 * 1024;
   return w + (dense ? (size_t)4 * d.Co * sizeof(float) + 1024 : 0);   // dense: + the mixed bias vector
@@ -1647,13 +1750,21 @@ template <typename T>
 static int tc_fwd_t(const void* x, const float* const w[4], const float* bias_r, void* y, const quan_conv_dims& d, int dtype,
                     int dense, const Mix16& M, void* ws, cudaStream_t st, double* stat_part, int* stat_nparts, const PostOp* post) {
   if (dense) {
+    void* pre = planned_pack(w, bias_r, PACK_DENSE_FWD, dtype, d, M);
+    if (pre != nullptr) ws = pre;
     float* bias_out = reinterpret_cast<float*>((char*)ws + packed_weight_bytes(d, dtype, 1) - (size_t)4 * d.Co * sizeof(float) - 1024);
-    int rc = pack_weights_dense<T, false>(w, bias_r, ws, bias_out, d, M, st);
-    if (rc) return rc;
+    if (pre == nullptr) {
+      int rc = pack_weights_dense<T, false>(w, bias_r, ws, bias_out, d, M, st);
+      if (rc) return rc;
+    }
     return launch_igemm<T, false, 1>(x, ws, bias_r ? bias_out : nullptr, y, fwd_shape(d, 1), dtype, M, st, stat_part, stat_nparts, post);
   }
-  int rc = pack_weights<T, false>(w, ws, d, st);
-  if (rc) return rc;
+  void* pre = planned_pack(w, nullptr, PACK_SEP_FWD, dtype, d, M);
+  if (pre != nullptr) ws = pre;
+  else {
+    int rc = pack_weights<T, false>(w, ws, d, st);
+    if (rc) return rc;
+  }
   return launch_igemm<T, true, 4>(x, ws, bias_r, y, fwd_shape(d, 0), dtype, M, st, stat_part, stat_nparts, post);
 }
 
@@ -1674,12 +1785,20 @@ template <typename T>
 static int tc_dgrad_t(const void* g, const float* const w[4], void* dx, const quan_conv_dims& d, int dtype, int dense,
                       const Mix16& M, void* ws, cudaStream_t st) {
   if (dense) {
-    int rc = pack_weights_dense<T, true>(w, nullptr, ws, nullptr, d, M, st);
-    if (rc) return rc;
+    void* pre = planned_pack(w, nullptr, PACK_DENSE_DGRAD, dtype, d, M);
+    if (pre != nullptr) ws = pre;
+    else {
+      int rc = pack_weights_dense<T, true>(w, nullptr, ws, nullptr, d, M, st);
+      if (rc) return rc;
+    }
     return launch_igemm<T, false, 1>(g, ws, nullptr, dx, dgrad_shape(d, 1), dtype, M, st);
   }
-  int rc = pack_weights<T, true>(w, ws, d, st);
-  if (rc) return rc;
+  void* pre = planned_pack(w, nullptr, PACK_SEP_DGRAD, dtype, d, M);
+  if (pre != nullptr) ws = pre;
+  else {
+    int rc = pack_weights<T, true>(w, ws, d, st);
+    if (rc) return rc;
+  }
   return launch_igemm<T, false, 4>(g, ws, nullptr, dx, dgrad_shape(d, 0), dtype, M, st);
 }
 
@@ -1702,3 +1821,81 @@ int qconv_tc_wgrad(const void* g, const void* x, float* const dw[4], const quan_
 }
 
 }  // namespace quan
+
+using namespace quan;
+
+extern "C" {
+
+int quan_pack_plan_record(int on) {
+  PackPlan& pl = pack_plan();
+  std::lock_guard<std::mutex> lock(pl.mu);
+  if (on) {
+    pl.jobs.clear(); pl.bytes.clear(); pl.offset.clear();
+    pl.active = false; pl.table_dev = nullptr; pl.total_blocks = 0;
+  }
+  pl.recording = on != 0;
+  return (int)pl.jobs.size();
+}
+
+size_t quan_pack_plan_bytes(size_t* table_bytes) {
+  PackPlan& pl = pack_plan();
+  std::lock_guard<std::mutex> lock(pl.mu);
+  size_t total = 0;
+  for (size_t b : pl.bytes) total += (b + 1023) / 1024 * 1024;
+  if (table_bytes != nullptr) *table_bytes = pl.jobs.size() * sizeof(PackJob);
+  return total;
+}
+
+int quan_pack_plan_commit(void* arena, size_t arena_bytes, void* table, size_t table_bytes, void* stream) {
+  PackPlan& pl = pack_plan();
+  std::lock_guard<std::mutex> lock(pl.mu);
+  QUAN_REQUIRE(!pl.jobs.empty(), QUAN_E_ARG, "pack_plan_commit: nothing recorded (run a step between quan_pack_plan_record(1) and (0))");
+  QUAN_REQUIRE(arena != nullptr && table != nullptr && table_bytes >= pl.jobs.size() * sizeof(PackJob), QUAN_E_ARG, "pack_plan_commit: null or small table");
+  QUAN_REQUIRE((reinterpret_cast<uintptr_t>(arena) & 1023) == 0, QUAN_E_ARG, "pack_plan_commit: arena must be 1024-byte aligned");
+  size_t off = 0;
+  int block0 = 0;
+  pl.offset.assign(pl.jobs.size(), 0);
+  for (size_t i = 0; i < pl.jobs.size(); ++i) {
+    PackJob& j = pl.jobs[i];
+    pl.offset[i] = off;
+    j.out = (char*)arena + off;
+    j.bias_out = j.form == PACK_DENSE_FWD ? reinterpret_cast<float*>((char*)j.out + pl.bytes[i] - (size_t)4 * j.Co * sizeof(float) - 1024) : nullptr;
+    off += (pl.bytes[i] + 1023) / 1024 * 1024;
+    int nb = (int)((j.total + 256 * 8 - 1) / (256 * 8));       // ~8 elements per thread
+    j.block0 = block0; j.nblocks = nb < 1 ? 1 : nb;
+    block0 += j.nblocks;
+  }
+  QUAN_REQUIRE(off <= arena_bytes, QUAN_E_WORKSPACE, "pack_plan_commit: arena needs %zu bytes, got %zu", off, arena_bytes);
+  pl.total_blocks = block0;
+  QUAN_CUDA(cudaMemcpyAsync(table, pl.jobs.data(), pl.jobs.size() * sizeof(PackJob), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  QUAN_CUDA(cudaStreamSynchronize((cudaStream_t)stream));      // the host vector may be re-used by the next record
+  pl.table_dev = reinterpret_cast<const PackJob*>(table);
+  pl.recording = false;
+  pl.active = true;
+  return QUAN_OK;
+}
+
+int quan_pack_plan_run(void* stream) {
+  PackPlan& pl = pack_plan();
+  int njobs, blocks;
+  const PackJob* table;
+  {
+    std::lock_guard<std::mutex> lock(pl.mu);
+    QUAN_REQUIRE(pl.active && pl.table_dev != nullptr, QUAN_E_ARG, "pack_plan_run: no committed plan");
+    njobs = (int)pl.jobs.size(); blocks = pl.total_blocks; table = pl.table_dev;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  QUAN_TIMED(st);
+  QUAN_LAUNCH(pack_plan_kernel, (unsigned)blocks, 256, 0, st, table, njobs);
+  QUAN_CHECK_LAUNCH("pack_plan_kernel");
+  return QUAN_OK;
+}
+
+int quan_pack_plan_release(void) {
+  PackPlan& pl = pack_plan();
+  std::lock_guard<std::mutex> lock(pl.mu);
+  pl.active = false; pl.recording = false; pl.table_dev = nullptr;
+  return QUAN_OK;
+}
+
+}  // extern "C"

@@ -254,6 +254,70 @@ def qattention(qkv: torch.Tensor, heads: int, key_dim: int, head_dim: int, scale
     return _QAttention.apply(qkv, int(heads), int(key_dim), int(head_dim), float(scale))
 
 
+class _QER(torch.autograd.Function):
+    """QER.forward (head.py:40-47) on the tensor-core layout: quan_qer_fwd / quan_qer_bwd."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x, _ = ops.as_layout(x, ops.LAYOUT_BHWQC)
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return ops.qer_fwd(x, weight, bias)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        if dy.dtype != x.dtype:
+            dy = dy.to(x.dtype)
+        dx, dw, db = ops.qer_bwd(dy, x, weight, ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2])
+        if dw is not None and dw.dtype != weight.dtype:
+            dw = dw.to(weight.dtype)
+        return dx, None if dw is None else dw.view_as(weight), db
+
+
+def qer(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
+    """Quaternion -> real 1x1 projection of a [B,C,H,W,4] activation: logical [B,N,H,W], channels-last memory."""
+    return _QER.apply(x, weight, bias)
+
+
+class _QERCat(torch.autograd.Function):
+    """`torch.cat((qer_a(xa), qer_b(xb)), 1)` (head.py:143: box and class extractions of one pyramid level) with both extractions
+    writing their columns of the concatenated tensor directly, and reading their slices of its gradient in place."""
+
+    @staticmethod
+    def forward(ctx, xa, wa, ba, xb, wb, bb):
+        xa, _ = ops.as_layout(xa, ops.LAYOUT_BHWQC)
+        xb, _ = ops.as_layout(xb, ops.LAYOUT_BHWQC)
+        B, _, H, W, _ = xa.shape
+        na, nb = wa.size(0), wb.size(0)
+        ld = (na + nb + 7) // 8 * 8                    # rows padded to 16 bytes (bf16): vector stores here, vector loads in backward
+        buf = torch.empty((B, H, W, ld), dtype=xa.dtype, device=xa.device)
+        ops.qer_fwd(xa, wa, ba, buf, 0, na)
+        ops.qer_fwd(xb, wb, bb, buf, na, ld - na)      # the padding columns belong to the second extraction (zero-filled)
+        ctx.save_for_backward(xa, wa, xb, wb)
+        ctx.has_bias = (ba is not None, bb is not None)
+        return buf[..., :na + nb].permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, dy):
+        xa, wa, xb, wb = ctx.saved_tensors
+        na = wa.size(0)
+        if dy.dtype != xa.dtype:
+            dy = dy.to(xa.dtype)
+        dy = ops.pixel_rows(dy)                        # once for both halves; the halves are channel slices of the same rows
+        need = ctx.needs_input_grad
+        ld = dy.stride(3)                               # rows of the fused head tensor's gradient: na + nb values (+ finite padding)
+        pad_ok = ld - na >= (wb.size(0) + 7) // 8 * 8        # the row padding behind the second slice may be read (the kernel clears it)
+        dxa, dwa, dba = ops.qer_bwd(dy[:, :na], xa, wa, need[0], need[1], ctx.has_bias[0] and need[2])
+        dxb, dwb, dbb = ops.qer_bwd(dy[:, na:], xb, wb, need[3], need[4], ctx.has_bias[1] and need[5], (ld - na) if pad_ok else 0)
+        fix = lambda g, w: None if g is None else (g.to(w.dtype) if g.dtype != w.dtype else g).view_as(w)
+        return dxa, fix(dwa, wa), dba, dxb, fix(dwb, wb), dbb
+
+
+def qer_cat(xa, wa, ba, xb, wb, bb) -> torch.Tensor:
+    return _QERCat.apply(xa, wa, ba, xb, wb, bb)
+
+
 class _QMaxPool(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, kernel, stride, padding):

@@ -111,12 +111,15 @@ class BucketedGradSync:
 class GraphedTrainStep:
     """forward graph -> loss -> backward (+ all-reduce) + optimizer graph.  `forward_fn(*static_inputs)` returns any pytree of
     tensors; `loss_fn(outputs, *static_inputs, *loss_args)` returns (loss, aux) with `loss` a scalar tensor that depends on the
-    outputs.  capture_loss=True puts the loss into the forward graph (it must then be free of host synchronisation, e.g.
+    outputs.  pack_plan=True hoists the weight packing of every tensor-core convolution into one launch at the top of the forward
+    graph (ops.PackPlan; the weights only change in the optimizer at the end of the backward graph).  capture_loss=True puts the loss
+    into the forward graph (it must then be free of host synchronisation, e.g.
     loss.OBBLossStatic, and read its targets from the static inputs)."""
 
     def __init__(self, forward_fn: Callable, loss_fn: Callable, optimizer, example_inputs: Sequence[torch.Tensor],
                  params: Sequence[torch.nn.Parameter], autocast: Optional[torch.dtype] = None, warmup: int = 3,
-                 loss_args: Sequence = (), grad_sync: Optional[BucketedGradSync] = None, capture_loss: bool = False):
+                 loss_args: Sequence = (), grad_sync: Optional[BucketedGradSync] = None, capture_loss: bool = False,
+                 pack_plan: bool = True):
         self.forward_fn, self.loss_fn, self.opt = forward_fn, loss_fn, optimizer
         self.params = [p for p in params if p.requires_grad]
         self.autocast = autocast
@@ -132,11 +135,17 @@ class GraphedTrainStep:
         # warm-up on a side stream (workspaces, library handles, allocator state)
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
+        from . import ops
+        self.pack_plan = ops.PackPlan() if pack_plan else None
         with torch.cuda.stream(side):
-            for _ in range(max(1, warmup)):
+            for i in range(max(1, warmup)):
+                if self.pack_plan is not None and i == max(1, warmup) - 1:
+                    self.pack_plan.record()                    # note every weight pack the last warm-up step performs
                 self._eager(loss_args)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
+        if self.pack_plan is not None and self.pack_plan.commit(dev) == 0:
+            self.pack_plan = None                              # nothing on the tensor-core engine: nothing to hoist
         if grad_sync is not None:
             grad_sync.prepare([p for p in self.params if p.grad is not None])     # the parameters this model's backward reaches
         for p in self.params:
@@ -147,6 +156,8 @@ class GraphedTrainStep:
         self.g_fwd = torch.cuda.CUDAGraph()
         self.loss = self.aux = None
         with torch.cuda.graph(self.g_fwd):
+            if self.pack_plan is not None:
+                self.pack_plan.run()                           # first node: every layer's packed weights from the current masters
             with ac():
                 out = self.forward_fn(*self.static_inputs)
                 if capture_loss:
@@ -168,6 +179,8 @@ class GraphedTrainStep:
             self.opt.step()
         if grad_sync is not None:
             grad_sync.detach()
+        if self.pack_plan is not None:
+            self.pack_plan.release()                           # eager calls pack for themselves again; the graphs keep the arena
         self.captured_launches = int(_lib.load().quan_launch_count() - n0)      # library kernels one step replays
 
     def _eager(self, loss_args):

@@ -127,15 +127,26 @@ def _obb_forward(self, x):
     import math
     if (not self.training or self.end2end or not x[0].is_cuda or os.environ.get("QUAN_HEAD_STREAMS", "1") == "0"):
         return self._reference_forward(x)
+    from . import functional as QF
     bs = x[0].shape[0]
     main = torch.cuda.current_stream(x[0].device)
     towers = [(i, j, t[i]) for i in range(self.nl) for j, t in enumerate((self.cv2, self.cv3, self.cv4))]
     streams = _head_streams(x[0].device, len(towers))
+    # box / class towers stop before their QER when the pair can write the concatenated tensor directly (functional.qer_cat)
+    pair = [isinstance(self.cv2[i][-1], M.QER) and isinstance(self.cv3[i][-1], M.QER) and
+            os.environ.get("QUAN_QER_CAT", "1") != "0" for i in range(self.nl)]
     outs = {}
     for (i, j, tower), s in zip(towers, streams):
         s.wait_stream(main)
         with torch.cuda.stream(s):
-            outs[i, j] = tower(x[i])
+            y = x[i]
+            mods = list(tower)
+            for m in (mods[:-1] if (j < 2 and pair[i]) else mods):
+                y = m(y)
+            if j < 2 and pair[i] and not mods[-1].fused_ok(y):
+                y = mods[-1](y)                     # a shape the kernel does not serve: the module's own fallback
+                pair[i] = None
+            outs[i, j] = y
         x[i].record_stream(s)
     for (i, j, _), s in zip(towers, streams):
         main.wait_stream(s)
@@ -143,7 +154,15 @@ def _obb_forward(self, x):
     angle = torch.cat([outs[i, 2].view(bs, self.ne, -1) for i in range(self.nl)], 2)
     angle = (angle.sigmoid() - 0.25) * math.pi
     for i in range(self.nl):
-        x[i] = torch.cat((outs[i, 0], outs[i, 1]), 1)
+        if pair[i]:
+            qa, qb = self.cv2[i][-1].output_proj, self.cv3[i][-1].output_proj
+            x[i] = QF.qer_cat(outs[i, 0], qa.weight, qa.bias, outs[i, 1], qb.weight, qb.bias)
+        else:
+            a, b = outs[i, 0], outs[i, 1]
+            if pair[i] is None:                     # one of the two already went through its QER: finish the other
+                a = a if a.dim() == 4 else self.cv2[i][-1](a)
+                b = b if b.dim() == 4 else self.cv3[i][-1](b)
+            x[i] = torch.cat((a, b), 1)
     return x, angle
 
 

@@ -191,10 +191,11 @@ class _ObbLossFusedFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, f0, f1, f2, angle, crit, targets, target_mask):
-        feats = [f.contiguous(memory_format=torch.channels_last) for f in (f0, f1, f2)]
+        feats = [_pixel_rows(f) for f in (f0, f1, f2)]
         angle = angle.contiguous()
-        total, items, grads = crit._run(feats, angle, targets, target_mask)
+        total, items, grads = crit._run(feats, angle, targets, target_mask)     # grads: dense [B,H,W,ld] x 3 + the angle gradient
         ctx.save_for_backward(*grads)
+        ctx.widths = [f.shape[1] for f in feats]
         ctx.mark_non_differentiable(items)
         return total, items
 
@@ -202,7 +203,18 @@ class _ObbLossFusedFn(torch.autograd.Function):
     def backward(ctx, g_total, g_items):
         grads = ctx.saved_tensors
         out = torch._foreach_mul(list(grads), g_total.to(grads[0].dtype))
-        return out[0], out[1], out[2], out[3], None, None, None
+        views = [o[..., :n].permute(0, 3, 1, 2) for o, n in zip(out[:3], ctx.widths)]
+        return views[0], views[1], views[2], out[3], None, None, None
+
+
+def _pixel_rows(f: torch.Tensor) -> torch.Tensor:
+    """A logical [B,N,H,W] head tensor whose memory is pixel rows of N contiguous values, `stride(3)` elements apart (channels-last,
+    or the padded rows functional.qer_cat writes); anything else is made channels-last."""
+    B, N, H, W = f.shape
+    sb, sn, sh, sw = f.stride()
+    if sn == 1 and sw >= N and sh == W * sw and sb == H * sh:
+        return f
+    return f.contiguous(memory_format=torch.channels_last)
 
 
 class OBBLossFused(OBBLossStatic):
@@ -224,6 +236,8 @@ class OBBLossFused(OBBLossStatic):
         hw = (C.c_int32 * 6)(*[v for s in shapes for v in s])
         st = (C.c_float * 3)(*self.stride)
         fp = (C.c_void_p * 3)(*[f.data_ptr() for f in feats])
+        lds = [f.stride(3) for f in feats]                       # row pitch per level (>= no: qer_cat pads rows to 16 bytes)
+        ldp = (C.c_int32 * 3)(*lds)
         stream = torch.cuda.current_stream(dev).cuda_stream
         # targets (loss.py:959-968)
         tg, tmask = targets.float(), target_mask.float()
@@ -234,17 +248,17 @@ class OBBLossFused(OBBLossStatic):
         gt_bboxes = (gt_bboxes * mask_gt.unsqueeze(-1)).contiguous()
         pd_scores = torch.empty(B, A, self.nc, dtype=torch.float32, device=dev)
         pd_bboxes = torch.empty(B, A, 5, dtype=torch.float32, device=dev)
-        check(lib.quan_obb_decode(fp, angle.data_ptr(), hw, st, B, self.nc, self.reg_max, pd_scores.data_ptr(), pd_bboxes.data_ptr(), dt,
+        check(lib.quan_obb_decode(fp, angle.data_ptr(), hw, st, B, self.nc, self.reg_max, ldp, pd_scores.data_ptr(), pd_bboxes.data_ptr(), dt,
                                   stream), "quan_obb_decode")
         t_boxes, t_scores, fg, _ = self._assign(pd_scores, pd_bboxes, anc_px, gt_labels, gt_bboxes, mask_gt)
-        grads = [torch.empty_like(f, memory_format=torch.preserve_format) for f in feats] + [torch.empty_like(angle)]
+        grads = [torch.empty((B, f.shape[2], f.shape[3], ld), dtype=f.dtype, device=dev) for f, ld in zip(feats, lds)] + [torch.empty_like(angle)]
         gp = (C.c_void_p * 3)(*[g.data_ptr() for g in grads[:3]])
         scratch = torch.empty(5, dtype=torch.float64, device=dev)
         items = torch.empty(4, dtype=torch.float32, device=dev)
         total = torch.empty((), dtype=torch.float32, device=dev)
         check(lib.quan_obb_loss_fwd_bwd(fp, angle.data_ptr(), hw, st, B, self.nc, self.reg_max, t_boxes.data_ptr(), t_scores.data_ptr(),
                                         fg.data_ptr(), float(self.hyp.box), float(self.hyp.cls), float(self.hyp.dfl), float(self.lambda_angular),
-                                        gp, grads[3].data_ptr(), scratch.data_ptr(), items.data_ptr(), total.data_ptr(), dt, stream),
+                                        ldp, gp, grads[3].data_ptr(), scratch.data_ptr(), items.data_ptr(), total.data_ptr(), dt, stream),
               "quan_obb_loss_fwd_bwd")
         return total, items, grads
 

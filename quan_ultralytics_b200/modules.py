@@ -168,13 +168,15 @@ class IQBN(nn.Module):
         self.register_buffer("num_batches_tracked", torch.tensor(0, dtype=torch.long))
         self.process_group = None   # set by distributed.convert_sync_iqbn
         self.sync = False
+        self._nbt_pooled = False    # set by pool_batch_counters: the model's forward pre-hook counts for every IQBN at once
 
     def forward(self, x: torch.Tensor, act: int = ACT_NONE) -> torch.Tensor:
         assert x.dim() == 5 and x.size(4) == 4, "Input must be [B, C, H, W, 4]"
         assert x.size(1) == self.num_features, f"expected {self.num_features} quaternion channels, got {x.size(1)}"
         if self.training:
-            with torch.no_grad():
-                self.num_batches_tracked += 1
+            if not self._nbt_pooled:
+                with torch.no_grad():
+                    self.num_batches_tracked += 1
             group = None
             if self.sync and torch.distributed.is_available() and torch.distributed.is_initialized():
                 group = self.process_group or torch.distributed.group.WORLD
@@ -185,6 +187,33 @@ class IQBN(nn.Module):
 
     def extra_repr(self) -> str:
         return f"{self.num_features * 4}, eps={self.eps}, momentum={self.momentum}, sync={self.sync}"
+
+
+def pool_batch_counters(model: nn.Module) -> Optional[torch.Tensor]:
+    """`num_batches_tracked += 1` (conv.py:563) is one tiny kernel per IQBN per training forward — 84 launches of the QUAN-YOLO11n
+    step.  This re-homes every IQBN's counter as a view into ONE int64 tensor (same buffer names, shapes and state-dict entries) and
+    counts with a single add in a forward pre-hook of `model` (training mode only).  Call it after the model sits on its device;
+    a later `.to(other_device)` gives every buffer its own storage again — call it again then.  Counts every pooled IQBN on every
+    training forward of `model` (the reference counts the ones that ran — all of them, in the QUAN graphs)."""
+    bns = [m for m in model.modules() if isinstance(m, IQBN)]
+    if not bns:
+        return None
+    dev = bns[0].num_batches_tracked.device
+    pool = torch.stack([m.num_batches_tracked.detach().to(dev, torch.long).reshape(()) for m in bns])
+    for i, m in enumerate(bns):
+        m._buffers["num_batches_tracked"] = pool[i]
+        m._nbt_pooled = True
+    old = getattr(model, "_quan_nbt_hook", None)
+    if old is not None:
+        old.remove()
+    model._quan_nbt_pool = pool
+
+    def count(mod, args):
+        if mod.training:
+            mod._quan_nbt_pool.add_(1)
+
+    model._quan_nbt_hook = model.register_forward_pre_hook(count)
+    return pool
 
 
 class QUpsample(nn.Module):
@@ -224,19 +253,28 @@ class QER(nn.Module):
     """Quaternion -> real extraction of the detection heads (ultralytics/nn/modules/head.py:26-47): a real `nn.Conv2d` over
     the 4C flattened quaternion channels (channel index c*4 + q).  The reference first materialises
     `x.permute(0, 1, 4, 2, 3).contiguous()`; in the tensor-core layout (BHWQC) the activation already IS a channels-last
-    real tensor with channel index q*C + c, so the copy disappears: the (tiny) weight is re-ordered instead and the GEMM is
-    the library's (cuDNN / cuBLAS 1x1 convolution — plain library GEMM, no kernel of ours).  Same constructor, parameters
-    and state-dict keys (`output_proj.weight`, `output_proj.bias`, `bias`) as the reference; output is the same logical
-    [B, out, H, W] tensor (channels-last memory when the input was BHWQC).  SURVEY §8(f) rank 2, host side only."""
+    real tensor with channel index q*C + c, so the copy disappears and the projection is quan_qer_fwd / quan_qer_bwd
+    (csrc/qer.cu: pixel-row GEMM with the weight re-ordered while it is staged, bias and bias gradient fused).  Same
+    constructor, parameters and state-dict keys (`output_proj.weight`, `output_proj.bias`, `bias`) as the reference; output is
+    the same logical [B, out, H, W] tensor in channels-last memory.  Shapes outside the kernel's range (4C > 256, N > 64, a
+    kernel size other than 1) and CPU tensors take the view + re-ordered weight + library conv path.  SURVEY §8(f) rank 2."""
 
     def __init__(self, in_channels, out_channels=None, kernel_size=None):
         super().__init__()
         self.output_proj = nn.Conv2d(in_channels, out_channels, kernel_size=kernel_size)
         self.bias = self.output_proj.bias
 
+    def fused_ok(self, x: torch.Tensor) -> bool:
+        """True when quan_qer_* serves this call: a CUDA [B,C,H,W,4] activation, the plain 1x1 projection, supported widths."""
+        conv = self.output_proj
+        return (x.dim() == 5 and ops.on_device(x) and conv.kernel_size == (1, 1) and conv.stride == (1, 1) and conv.padding == (0, 0)
+                and conv.groups == 1 and conv.padding_mode == "zeros" and ops.qer_supported(x.size(1), conv.out_channels, x.dtype))
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         B, C, H, W, Q = x.shape
         conv = self.output_proj
+        if self.fused_ok(x):
+            return QF.qer(x, conv.weight, conv.bias)             # the library's kernel: reads BHWQC rows, fp32 master weight
         if C > 1 and x.is_contiguous(memory_format=torch.channels_last_3d):
             xr = x.permute(0, 4, 1, 2, 3).reshape(B, Q * C, H, W)            # a view: memory is [B][H][W][q*C + c]
             w = conv.weight
@@ -264,8 +302,9 @@ class Conv(nn.Module):
         if (self.fuse_block and fused_act is not None and bn.training and not bn.sync and c.bias_r is None
                 and not c.is_first_layer and x.dim() == 5 and ops.on_device(x)):
             # conv -> IQBN -> act as one autograd node: the IQBN backward hands G = M^T dY straight to the conv backward
-            with torch.no_grad():
-                bn.num_batches_tracked += 1
+            if not bn._nbt_pooled:
+                with torch.no_grad():
+                    bn.num_batches_tracked += 1
             return QF.conv_iqbn_act(x, c.weight_r, c.weight_i, c.weight_j, c.weight_k, bn.gamma, bn.beta, bn.running_mean,
                                     bn.running_var, c.stride, c.padding, c.dilation, c.groups, ops.MIX[c.mix], c.algo,
                                     bn.eps, bn.momentum, fused_act)

@@ -272,6 +272,67 @@ def qmaxpool_bwd(dy: torch.Tensor, idx: torch.Tensor, in_hw, kernel, stride, pad
     return out
 
 
+# ---- QER (quaternion -> real extraction of the heads) -------------------------------------------------------------------------------
+QER_MAX_K, QER_MAX_N = 256, 64
+
+
+def qer_supported(C_: int, N: int, dtype: torch.dtype) -> bool:
+    """Shapes quan_qer_* serve (include/quan_sm100.h): 4C <= 256 input and N <= 64 output channels; bf16 rows of whole 16-element
+    MMA steps (C % 4 == 0) and, above 128 input channels, whole 128-column chunks."""
+    K = 4 * C_
+    if K > QER_MAX_K or N > QER_MAX_N or dtype not in (torch.float32, torch.bfloat16):
+        return False
+    return dtype == torch.float32 or (C_ % 4 == 0 and (K <= 128 or K % 128 == 0))
+
+
+def qer_fwd(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], out: Optional[torch.Tensor] = None,
+            col0: int = 0, writable: int = 0) -> torch.Tensor:
+    """head.py:40-47 on a dense BHWQC activation [B,C,H,W,4].  Returns the logical [B,N,H,W] result in channels-last memory; with
+    `out` (a [B,H,W,Ctot] contiguous buffer) the N columns starting at `col0` of every pixel row are written in place; `writable`
+    (>= N) columns from col0 on belong to this call (row padding, zero-filled: lets a ragged width go out as whole vectors)."""
+    _require_cuda(x, weight, bias)
+    B, C_, H, W, _ = x.shape
+    N = weight.size(0)
+    w, b = _f32c(weight), _f32c(bias)
+    buf = torch.empty((B, H, W, N), dtype=x.dtype, device=x.device) if out is None else out
+    ld = buf.size(3)
+    check(_lib.load().quan_qer_fwd(x.data_ptr(), w.data_ptr(), _ptr(b), buf.data_ptr() + col0 * buf.element_size(), B * H * W, C_, N, ld,
+                                   int(writable), _dtype_code(x), _stream(x)), "quan_qer_fwd")
+    return buf.permute(0, 3, 1, 2) if out is None else out
+
+
+def pixel_rows(dy: torch.Tensor) -> torch.Tensor:
+    """A logical [B,N,H,W] tensor whose memory is one row of N contiguous values per pixel, rows `stride(3)` elements apart:
+    channels-last tensors, their channel slices (what CatBackward hands out) and padded-row tensors pass through; anything else is
+    copied to channels-last."""
+    B, N, H, W = dy.shape
+    sb, sn, sh, sw = dy.stride()
+    if (sn == 1 or N == 1) and sw >= N and sh == W * sw and sb == H * sh:
+        return dy
+    return dy.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+
+
+def qer_bwd(dy: torch.Tensor, x: torch.Tensor, weight: torch.Tensor, need_dx: bool, need_dw: bool, need_db: bool, readable: int = 0):
+    """Returns (dx like x or None, dweight like weight (fp32) or None, dbias [N] or None); dy: logical [B,N,H,W] in x's dtype, pixel rows
+    (see pixel_rows); `readable` (>= N) columns of every dy row may be read (finite row padding)."""
+    _require_cuda(dy, x, weight)
+    B, C_, H, W, _ = x.shape
+    N = weight.size(0)
+    dy = pixel_rows(dy)
+    w = _f32c(weight)
+    lib = _lib.load()
+    dx = torch.empty_like(x, memory_format=torch.preserve_format) if need_dx else None
+    dw = torch.empty_like(w) if (need_dw or need_db) else None
+    db = torch.empty(N, dtype=torch.float32, device=x.device) if need_db else None
+    npix = B * H * W
+    wsb = _workspace(lib.quan_qer_workspace_bytes(npix, C_, N, _dtype_code(x)), x.device) if dw is not None else None
+    if dy.stride(3) < max(readable, N):
+        readable = 0
+    check(lib.quan_qer_bwd(dy.data_ptr(), dy.stride(3), int(readable), x.data_ptr(), w.data_ptr(), _ptr(dx), _ptr(dw), _ptr(db), npix, C_, N,
+                           _dtype_code(x), _ptr(wsb), 0 if wsb is None else wsb.numel(), _stream(x)), "quan_qer_bwd")
+    return dx, (dw if need_dw else None), db
+
+
 # ---- QAttention core ------------------------------------------------------------------------------------------------
 def qattention_fwd(qkv: torch.Tensor, heads: int, key_dim: int, head_dim: int, scale: float):
     """block.py:1520-1540 fused: qkv [B, heads*(2K+V), H, W, 4] (BHWQC) -> (o [B, heads*V, H, W, 4], lse [B*4*heads*H*W])."""
@@ -605,6 +666,41 @@ def conv_block_eval_fwd(x: torch.Tensor, weights: Sequence[torch.Tensor], gamma,
     return out
 
 
+# ---- pack plan (include/quan_sm100.h): every packed weight of a step rebuilt by ONE launch ------------------------------------------------
+class PackPlan:
+    """with-less protocol used by graphs.GraphedTrainStep:  p = PackPlan(); p.record(); <one eager step>; p.commit(device);
+    then `p.run()` as the first thing of every step (captured: first node of the forward graph); p.release() when the convolutions
+    should pack for themselves again.  Holds the arena and the job table (they must outlive every graph captured under the plan)."""
+
+    def __init__(self):
+        self.arena = self.table = None
+        self.jobs = 0
+
+    def record(self) -> None:
+        check(min(0, _lib.load().quan_pack_plan_record(1)), "quan_pack_plan_record")
+
+    def commit(self, device: torch.device) -> int:
+        lib = _lib.load()
+        self.jobs = lib.quan_pack_plan_record(0)
+        if self.jobs <= 0:
+            return 0
+        tb = C.c_size_t(0)
+        nbytes = lib.quan_pack_plan_bytes(C.byref(tb))
+        self.arena = torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
+        self.table = torch.empty(tb.value, dtype=torch.uint8, device=device)
+        base = (self.arena.data_ptr() + 1023) // 1024 * 1024
+        check(lib.quan_pack_plan_commit(base, nbytes, self.table.data_ptr(), tb.value, torch.cuda.current_stream(device).cuda_stream),
+              "quan_pack_plan_commit")
+        return self.jobs
+
+    def run(self) -> None:
+        if self.jobs > 0:
+            check(_lib.load().quan_pack_plan_run(torch.cuda.current_stream(self.arena.device).cuda_stream), "quan_pack_plan_run")
+
+    def release(self) -> None:
+        _lib.load().quan_pack_plan_release()
+
+
 # ---- device activation -------------------------------------------------------------------------------------------------------------
 # The library launches on the calling thread's CURRENT device (raw pointers + a stream handle carry no device); a tensor on cuda:1
 # handed over while cuda:0 is current would meet the wrong stream table.  Every entry point that launches therefore runs under the
@@ -627,7 +723,7 @@ def _device_guarded(fn):
 
 
 for _name in ("poincare_fwd", "poincare_bwd", "convert_layout", "mix", "qupsample_fwd", "qupsample_bwd", "qmaxpool_fwd", "qmaxpool_bwd",
-              "qattention_fwd", "qattention_bwd", "iqbn_train_stats", "iqbn_partial_sums", "iqbn_finalize_stats", "iqbn_eval_stats",
+              "qattention_fwd", "qattention_bwd", "qer_fwd", "qer_bwd", "iqbn_train_stats", "iqbn_partial_sums", "iqbn_finalize_stats", "iqbn_eval_stats",
               "iqbn_apply_fwd", "iqbn_eval_fwd", "iqbn_bwd_reduce", "iqbn_bwd_coef", "iqbn_bwd_apply", "iqbn_eval_bwd", "qconv2d_fwd",
               "iqbn_finalize_partials", "qconv2d_bwd", "conv_block_fwd", "conv_block_bwd", "conv_block_eval_fwd", "as_layout"):
     globals()[_name] = _device_guarded(globals()[_name])

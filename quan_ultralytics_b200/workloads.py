@@ -43,7 +43,11 @@ def build_yolo_obb(scale: str = "n", nc: int = 15, device="cuda", swapped: bool 
     model.args = get_cfg(DEFAULT_CFG)
     if not swapped:
         reference_batch_stat_iqbn(model)
-    return model.to(device)
+    model = model.to(device)
+    if swapped:
+        from . import modules
+        modules.pool_batch_counters(model)
+    return model
 
 
 def reference_batch_stat_iqbn(model) -> None:
@@ -97,7 +101,11 @@ def build_classifier(name: str = "qwrn16_2", num_classes: Optional[int] = None, 
             model = qm.create_qrn34_imagenet(num_classes or 1000)
         else:
             raise ValueError(name)
-    return model.to(device)
+    model = model.to(device)
+    if swapped:
+        from . import modules
+        modules.pool_batch_counters(model)
+    return model
 
 
 def synthetic_classification_batch(B: int, size: int, num_classes: int, device="cpu", seed: int = 0):

@@ -314,3 +314,30 @@ def qattention_bwd(qkv, o, d_o, lse, heads, key_dim, head_dim, scale):
 
 
 _NAMES += ["qattention_fwd", "qattention_bwd"]
+
+
+# ---- QER (head.py:40-47) -------------------------------------------------------------------------------------------------------
+def _qer_ref(x, weight, bias):
+    B, C_, H, W, Q = x.shape
+    return F.conv2d(x.permute(0, 1, 4, 2, 3).reshape(B, C_ * Q, H, W), weight, bias)
+
+
+def qer_fwd(x, weight, bias, out=None, col0=0):
+    y = _qer_ref(x.float(), weight.float(), None if bias is None else bias.float()).to(x.dtype)
+    if out is None:
+        return y.contiguous(memory_format=torch.channels_last)
+    out[..., col0:col0 + y.shape[1]] = y.permute(0, 2, 3, 1)
+    return out
+
+
+def qer_bwd(dy, x, weight, need_dx, need_dw, need_db):
+    with torch.enable_grad():
+        xx = x.detach().float().requires_grad_(True)
+        ww = weight.detach().float().requires_grad_(True)
+        bb = torch.zeros(weight.size(0), requires_grad=True)
+        _qer_ref(xx, ww, bb).backward(dy.float())
+    dx = _fmt(xx.grad.to(x.dtype), L_BHWQC) if need_dx else None
+    return dx, (ww.grad if need_dw else None), (bb.grad if need_db else None)
+
+
+_NAMES += ["qer_fwd", "qer_bwd"]

@@ -89,3 +89,32 @@ def test_classification_graphs_match_reference(emu, name, B, size, nc):
     assert set(g_our) == set(g_ref)
     worst = _worst(g_our, g_ref)
     assert worst[0] <= 1e-3, worst
+
+
+def test_pooled_batch_counters_count_like_the_reference(emu):
+    """modules.pool_batch_counters (workloads.build_* call it): every IQBN keeps its `num_batches_tracked` buffer and state-dict
+    entry (conv.py:516, :563) but all of them live in one tensor that a forward pre-hook of the model bumps once per training
+    forward; eval forwards do not count; load_state_dict writes through the views."""
+    import quan_ultralytics_b200 as Q
+    torch.manual_seed(0)
+    ref = workloads.build_classifier("qwrn16_2", 10, "cpu", swapped=False)
+    ours = workloads.build_classifier("qwrn16_2", 10, "cpu", swapped=True)
+    assert sorted(ours.state_dict()) == sorted(ref.state_dict())
+    bns = [m for m in ours.modules() if isinstance(m, Q.IQBN)]
+    assert len(bns) == 13 and all(m._nbt_pooled for m in bns)
+    x, _ = workloads.synthetic_classification_batch(4, 32, 10)
+    ours.train()
+    ours(x)
+    ours(x)
+    ref.train()
+    ref(x)
+    ref(x)
+    ours.eval()
+    with torch.no_grad():
+        ours(x)
+    want = {k: int(v) for k, v in ref.state_dict().items() if k.endswith("num_batches_tracked")}
+    got = {k: int(v) for k, v in ours.state_dict().items() if k.endswith("num_batches_tracked")}
+    assert got == want and set(got.values()) == {2}
+    sd = {k: (torch.tensor(7) if k.endswith("num_batches_tracked") else v) for k, v in ours.state_dict().items()}
+    ours.load_state_dict(sd)
+    assert int(ours._quan_nbt_pool.min()) == 7 and int(bns[3].num_batches_tracked) == 7
