@@ -237,6 +237,18 @@ int quan_conv_block_eval_fwd(const void* x, const float* const w[4], const float
                              const quan_conv_dims* d, int dtype, int layout, const float* mix, int algo, float eps, int act,
                              void* conv_ws, size_t conv_ws_bytes, void* stream);
 
+/* Channel concatenation in BHWQC — `torch.cat(xs, 1)` of the reference's blocks (C2f / C3k2 block.py:350-352, C3 / C3k, QSPPF, QC2PSA,
+ * `Concat` conv.py) on tensors whose memory is one row per (pixel, component): source i contributes row_bytes of every destination row,
+ * read from rows ld_bytes apart (dense tensors: ld_bytes == row_bytes; channel chunks of a wider tensor: its row pitch).  Sources fill
+ * the destination rows left to right; one launch, 16-byte vectors when every pointer / pitch / width allows.  srcs is a HOST array. */
+#define QUAN_CAT_MAX 8
+typedef struct quan_cat_src {
+  const void* ptr;
+  int64_t ld_bytes;
+  int64_t row_bytes;
+} quan_cat_src;
+int quan_rows_cat(const quan_cat_src* srcs, int32_t nsrc, void* dst, int64_t dst_ld_bytes, int64_t nrows, void* stream);
+
 /* ---- pack plan: all packed weights of a training step in one launch ------------------------------------------------------------
  * The tensor-core engine reads weights in a packed operand layout (per component or, for narrow layers, the dense Hamilton matrix with
  * the mixing matrix folded in), rebuilt from the fp32 masters by a small kernel in front of every forward and every dgrad.  Weights

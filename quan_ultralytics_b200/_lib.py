@@ -76,6 +76,7 @@ PROTOTYPES = {
     "quan_pack_plan_commit": (_int, [_vp, _sz, _vp, _sz, _vp]),
     "quan_pack_plan_run": (_int, [_vp]),
     "quan_pack_plan_release": (_int, []),
+    "quan_rows_cat": (_int, [_vp, _i32, _vp, C.c_int64, C.c_int64, _vp]),
     "quan_rows_gather": (_int, [_vp, _vp, C.c_int64, _i32, C.c_int64, _vp]),
     "quan_qer_workspace_bytes": (_sz, [C.c_int64, _i32, _i32, _int]),
     "quan_qer_fwd": (_int, [_vp, _vp, _vp, _vp, C.c_int64, _i32, _i32, C.c_int64, _i32, _int, _vp]),
@@ -90,6 +91,12 @@ PROTOTYPES = {
     "quan_sgd_clip_step": (_int, [_vp, _int, _vp, _vp, _int, _vp, _vp, _int, _vp]),
     "quan_ema_update": (_int, [_vp, _int, _vp, _vp, _vp]),
 }
+
+class CatSrc(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("ld_bytes", C.c_int64), ("row_bytes", C.c_int64)]
+
+
+CAT_MAX = 8
 
 _lib = None
 

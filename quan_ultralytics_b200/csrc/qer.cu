@@ -162,20 +162,38 @@ __device__ __forceinline__ void zero_cols(__nv_bfloat16* s, int lds, int c0, int
   for (int e = threadIdx.x; e < QER_TM * n; e += blockDim.x) s[(size_t)(e / n) * lds + c0 + e % n] = __float2bfloat16_rn(0.f);
 }
 
-// the weight as the B operand of the forward GEMM: Ws[n][k] = W[n][ref_k(k)], rows n >= N zero.  Read in the reference's order
-// (coalesced: kr = c*4 + q runs fastest), scattered into shared memory at k = q*C + c.
-__device__ __forceinline__ void stage_weight_nk(const float* __restrict__ w, int N, int Npad, int K, int C, __nv_bfloat16* s, int lds) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  for (int n = warp; n < Npad; n += nwarps)
-    for (int kr = lane; kr < K; kr += 32)
-      s[(size_t)n * lds + (kr & 3) * C + (kr >> 2)] = __float2bfloat16_rn(n < N ? __ldg(w + (size_t)n * K + kr) : 0.f);
-}
-// ... and of the dgrad GEMM: Wt[k][n] = W[n][ref_k(k)], columns n >= N zero
-__device__ __forceinline__ void stage_weight_kn(const float* __restrict__ w, int N, int Npad, int K, int C, __nv_bfloat16* s, int lds) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  for (int n = warp; n < Npad; n += nwarps)
-    for (int kr = lane; kr < K; kr += 32)
-      s[(size_t)((kr & 3) * C + (kr >> 2)) * lds + n] = __float2bfloat16_rn(n < N ? __ldg(w + (size_t)n * K + kr) : 0.f);
+// The weight staged for the tensor-core contraction.  Read as float4 = the four components of one (n, c) in the reference's order
+// (index c*4 + q), eight vectors per thread in flight (a first version loaded one value at a time: 32 dependent L2 / DRAM round trips
+// per thread, ~12 us of every launch), scattered to k = q*C + c.  KN = false: Ws[n][k] (B operand of the forward GEMM, rows n >= N
+// zero); KN = true: Wt[k][n] (B operand of the dgrad GEMM, columns n >= N zero).
+template <bool KN>
+__device__ __forceinline__ void stage_weight(const float* __restrict__ w, int N, int Npad, int K, int C, __nv_bfloat16* s, int lds) {
+  const int total = Npad * C;                                  // float4 vectors, (n, c) with c fastest
+  const int shc = pow2_shift(C);
+  for (int base = threadIdx.x; base < total; base += 8 * blockDim.x) {
+    float4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int e = base + u * blockDim.x;
+      int n, c;
+      divmod(e, C, shc, n, c);
+      v[u] = (e < total && n < N) ? __ldg(reinterpret_cast<const float4*>(w + (size_t)n * K) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int e = base + u * blockDim.x;
+      if (e < total) {
+        int n, c;
+        divmod(e, C, shc, n, c);
+        const float q4[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (KN) s[(size_t)(q * C + c) * lds + n] = __float2bfloat16_rn(q4[q]);
+          else s[(size_t)n * lds + q * C + c] = __float2bfloat16_rn(q4[q]);
+        }
+      }
+    }
+  }
 }
 
 // write a [rows][cols] tile from shared memory (pitch lds) to global rows `ld` apart; `writable` >= cols columns of every row may
@@ -215,7 +233,7 @@ __global__ void __launch_bounds__(128) qer_fwd_bf16_kernel(const __nv_bfloat16* 
   int64_t t = blockIdx.x;
   if (t < tiles) stage_rows(x + t * QER_TM * K, K, (int)min((int64_t)QER_TM, npix - t * QER_TM), K, K, K, Xs, lda);
   cp_async_commit();
-  stage_weight_nk(w, N, Npad, K, C, Ws, lda);
+  stage_weight<false>(w, N, Npad, K, C, Ws, lda);
   for (int n = threadIdx.x; n < Npad; n += blockDim.x) bs[n] = (bias != nullptr && n < N) ? __ldg(bias + n) : 0.f;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row0 = warp * 32;
@@ -281,7 +299,7 @@ __global__ void __launch_bounds__(128) qer_dgrad_bf16_kernel(const __nv_bfloat16
   bool ragged = false;
   if (t < tiles) ragged = stage_rows(dy + t * QER_TM * dy_ld, dy_ld, (int)min((int64_t)QER_TM, npix - t * QER_TM), N, Np, dy_readable, DYs, ldn) && (N & 7);
   cp_async_commit();
-  stage_weight_kn(w, N, Np, K, C, Wt, ldn);
+  stage_weight<true>(w, N, Np, K, C, Wt, ldn);
   for (int it = 0; t < tiles; t += gridDim.x, ++it) {
     const int64_t pix0 = t * QER_TM, tn = t + gridDim.x;
     const int rows = (int)min((int64_t)QER_TM, npix - pix0);

@@ -318,6 +318,37 @@ def qer_cat(xa, wa, ba, xb, wb, bb) -> torch.Tensor:
     return _QERCat.apply(xa, wa, ba, xb, wb, bb)
 
 
+class _QCat(torch.autograd.Function):
+    """`torch.cat(xs, 1)` of BHWQC tensors / channel chunks (ops.qcat); backward hands every input its channel slice of the gradient as a
+    view, exactly what torch's CatBackward does."""
+
+    @staticmethod
+    def forward(ctx, *xs):
+        ctx.widths = [x.size(1) for x in xs]
+        return ops.qcat(xs)
+
+    @staticmethod
+    def backward(ctx, dy):
+        outs, off = [], 0
+        for i, c in enumerate(ctx.widths):
+            outs.append(dy.narrow(1, off, c) if ctx.needs_input_grad[i] else None)
+            off += c
+        return tuple(outs)
+
+
+def qcat(xs) -> torch.Tensor:
+    return _QCat.apply(*xs)
+
+
+def cat(tensors, dim=0, *, out=None):
+    """Drop-in for `torch.cat` inside the reference's block modules (install.py binds it there): channel concatenations of quaternion
+    activations in the tensor-core layout take the library's one-launch copy, everything else is torch.cat itself."""
+    if out is None and dim == 1 and isinstance(tensors, (list, tuple)) and len(tensors) >= 2 and all(isinstance(t, torch.Tensor) for t in tensors) \
+            and tensors[0].dim() == 5 and tensors[0].is_cuda and ops.qcat_supported(tensors):
+        return _QCat.apply(*tensors)
+    return torch.cat(tensors, dim) if out is None else torch.cat(tensors, dim, out=out)
+
+
 class _QMaxPool(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, kernel, stride, padding):

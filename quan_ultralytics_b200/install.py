@@ -107,6 +107,26 @@ def _make_qattention(ref_cls):
     return _derived[ref_cls]
 
 
+class _TorchProxy(types.ModuleType):
+    """Stands in for the name `torch` in the globals of the reference's block modules: every attribute is torch's own except `cat`,
+    which is functional.cat (the library's channel concatenation when the operands are quaternion activations in the tensor-core
+    layout, torch.cat otherwise).  The reference calls `torch.cat(y, 1)` from C2f / C3k2 / C3 / QSPPF / QC2PSA / Concat
+    (block.py:350-352 ..., conv.py Concat) — rebinding the module global is the only hook that leaves its source untouched."""
+
+    def __init__(self):
+        super().__init__("torch")
+        self.__dict__["_real"] = torch
+
+    def __getattr__(self, name):
+        return getattr(self.__dict__["_real"], name)
+
+    @staticmethod
+    def cat(tensors, dim=0, *, out=None):
+        from . import functional as QF
+        return QF.cat(tensors, dim, out=out)
+
+
+_torch_proxy = _TorchProxy()
 _branch_streams = {}
 
 
@@ -200,6 +220,11 @@ def install(ultralytics: bool = True, classification: bool = True) -> dict:
                 _swap(mod, "OBB", _make_obb(ref_cls))
                 names.append("OBB")
             done[modname] = names
+            if modname in ("ultralytics.nn.modules.conv", "ultralytics.nn.modules.block") and getattr(mod, "torch", None) is torch \
+                    and os.environ.get("QUAN_FAST_CAT", "1") != "0":
+                _originals.append((mod, "torch", torch))
+                mod.torch = _torch_proxy
+                names.append("torch.cat")
     if classification:
         for modname in ("quaternion.qconv", "quaternion", "models.quaternion_blocks", "models.quaternion_models",
                         "models.blocks.quaternion_blocks"):

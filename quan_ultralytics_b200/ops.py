@@ -120,6 +120,60 @@ def _gather_channel_slice(x: torch.Tensor) -> Optional[torch.Tensor]:
     return out
 
 
+def _row_source(x: torch.Tensor):
+    """(pointer, row pitch in bytes, row bytes) when `x` ([B,C,H,W,4]) is stored as one row of C contiguous values per (pixel, component)
+    with uniform pitch — a dense BHWQC tensor or a channel chunk of one — else None."""
+    B, C_, H, W, _ = x.shape
+    sb, sc, sh, sw, sq = x.stride()
+    if not ((sc == 1 or C_ == 1) and sq >= C_ and sw == 4 * sq and sh == W * sw and sb == H * sh):
+        return None
+    esz = x.element_size()
+    return x.data_ptr(), sq * esz, C_ * esz
+
+
+def qcat_supported(tensors) -> bool:
+    """True when ops.qcat serves `torch.cat(tensors, 1)`: CUDA [B,C_i,H,W,4] tensors of one float32 / bfloat16 dtype and one spatial shape,
+    every one stored in pixel-component rows (dense BHWQC or a channel chunk of it), 4-byte multiples throughout."""
+    t0 = tensors[0]
+    if len(tensors) < 2 or t0.dtype not in (torch.float32, torch.bfloat16):
+        return False
+    for t in tensors:
+        if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dim() == 5 and t.size(4) == 4 and t.dtype == t0.dtype and t.device == t0.device
+                and t.shape[0] == t0.shape[0] and t.shape[2:] == t0.shape[2:] and t.size(1) > 0):
+            return False
+        src = _row_source(t)
+        if src is None or src[0] % 4 or src[1] % 4 or src[2] % 4:
+            return False
+    return (sum(t.size(1) for t in tensors) * t0.element_size()) % 4 == 0
+
+
+def qcat(tensors) -> torch.Tensor:
+    """`torch.cat(tensors, 1)` into a dense BHWQC tensor in one launch (quan_rows_cat).  Neighbouring chunks of one tensor (the two
+    halves C2f keeps of its first convolution) are moved as one wider source."""
+    _require_cuda(*tensors)
+    t0 = tensors[0]
+    B, _, H, W, _ = t0.shape
+    Ct = sum(t.size(1) for t in tensors)
+    out = empty_q((B, Ct, H, W, 4), t0.dtype, t0.device, LAYOUT_BHWQC)
+    esz = t0.element_size()
+    srcs = []
+    for t in tensors:
+        ptr, ld, rb = _row_source(t)
+        if srcs and srcs[-1][1] == ld and srcs[-1][0] + srcs[-1][2] == ptr and ld > srcs[-1][2]:
+            srcs[-1] = (srcs[-1][0], ld, srcs[-1][2] + rb)
+        else:
+            srcs.append((ptr, ld, rb))
+    lib = _lib.load()
+    nrows = B * H * W * 4
+    off = 0
+    for i in range(0, len(srcs), _lib.CAT_MAX):                      # more than CAT_MAX sources: several launches
+        part = srcs[i:i + _lib.CAT_MAX]
+        arr = (_lib.CatSrc * len(part))(*[_lib.CatSrc(p, ld, rb) for p, ld, rb in part])
+        check(lib.quan_rows_cat(C.cast(arr, C.c_void_p), len(part), out.data_ptr() + off, Ct * esz, nrows, _stream(t0)), "quan_rows_cat")
+        off += sum(rb for _, _, rb in part)
+    return out
+
+
 # ---- workspaces ------------------------------------------------------------------------------------------------
 _ws_cache = {}
 _iqbn_ws_cache = {}

@@ -508,3 +508,37 @@ def test_channel_chunks_of_bhwqc_tensors_are_gathered_exactly(dtype):
         y, layout = ops.as_layout(sl, ops.LAYOUT_BHWQC)
         assert layout == ops.LAYOUT_BHWQC and y.is_contiguous(memory_format=torch.channels_last_3d)
         torch.testing.assert_close(y, sl.contiguous(memory_format=torch.channels_last_3d), rtol=0, atol=0)
+
+
+# ---- channel concatenation (block.py:350-352 `torch.cat(y, 1)`, conv.py Concat) --------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_qcat_is_torch_cat_bit_for_bit(dtype):
+    """functional.cat (what install.py binds as `torch.cat` inside the reference's block modules) on BHWQC activations: dense tensors,
+    the two chunk halves of one tensor (moved as one source) and a lone chunk, against torch.cat — a pure copy, so bit-exact —
+    and its backward against torch's CatBackward."""
+    from quan_ultralytics_b200 import functional as QF
+    torch.manual_seed(3)
+    B, H, W = 2, 9, 7
+    mk = lambda c: torch.randn(B, c, H, W, 4, device=DEV).to(dtype).contiguous(memory_format=torch.channels_last_3d)
+    a, b, c = mk(16), mk(8), mk(24)
+    h0, h1 = a.chunk(2, 1)
+    cases = [[h0, h1, b], [h1, b, c], [c, h0], [b, c, a, h1, b, c, a, b, c, b]]      # the last one: more sources than one launch takes
+    for xs in cases:
+        xs = [x.detach().clone(memory_format=torch.preserve_format) if x.is_contiguous(memory_format=torch.channels_last_3d) else x for x in xs]
+        got = QF.cat(xs, 1)
+        want = torch.cat(xs, 1)
+        assert got.shape == want.shape and got.is_contiguous(memory_format=torch.channels_last_3d)
+        assert torch.equal(got, want)
+    xs = [h0.detach().requires_grad_(True), b.detach().requires_grad_(True), c.detach().requires_grad_(True)]
+    dy = torch.randn(B, 40, H, W, 4, device=DEV).to(dtype)
+    QF.cat(xs, 1).backward(dy)
+    g = [x.grad.clone() for x in xs]
+    for x in xs:
+        x.grad = None
+    torch.cat(xs, 1).backward(dy)
+    assert all(torch.equal(p, x.grad) for p, x in zip(g, xs))
+    # operands the kernel does not serve go to torch.cat unchanged: another dim, 4-D tensors, CPU tensors
+    assert torch.equal(QF.cat([a, a], 0), torch.cat([a, a], 0))
+    r = torch.randn(2, 3, 4, 5, device=DEV)
+    assert torch.equal(QF.cat([r, r], 1), torch.cat([r, r], 1))
+    assert torch.equal(QF.cat([r.cpu(), r.cpu()], 1), torch.cat([r.cpu(), r.cpu()], 1))
