@@ -23,6 +23,7 @@
 #include <unordered_map>
 
 namespace quan {
+static bool depthwise_as_dense(const quan_conv_dims& d);
 static size_t packed_weight_bytes_of(const quan_conv_dims& d, int dtype, int dense);
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -951,6 +952,28 @@ __global__ void __launch_bounds__(256) wgrad_reduce_flat_kernel(const float* __r
   (q == 0 ? dw0 : q == 1 ? dw1 : q == 2 ? dw2 : dw3)[r] = s;
 }
 
+// depthwise layer run as the dense form: only the block diagonal of the dense weight gradient is a parameter gradient,
+// dW_q[c][tap] = sum_p M[p][q] * partial[tap][p*C + c][q*C + c]; one thread per (q, c, tap)
+__global__ void __launch_bounds__(256) wgrad_reduce_dw_kernel(const float* __restrict__ partial, float* __restrict__ dw0, float* __restrict__ dw1,
+                                                              float* __restrict__ dw2, float* __restrict__ dw3, int splits, int taps, int C,
+                                                              const Mix16 mix) {
+  pdl_prologue();
+  const int per_q = C * taps;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= 4 * per_q) return;
+  const int q = e / per_q, r = e - q * per_q;
+  const int tap = r % taps, c = r / taps;
+  const int64_t split_stride = (int64_t)16 * taps * C * C;
+  const float* src = partial + (((int64_t)tap * 4 * C + c) * 4 * C + q * C + c);
+  const int64_t pc_stride = (int64_t)C * 4 * C;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int sp = 0; sp < splits; ++sp) {
+#pragma unroll
+    for (int pc = 0; pc < 4; ++pc) acc[pc] += __ldg(src + sp * split_stride + pc * pc_stride);
+  }
+  (q == 0 ? dw0 : q == 1 ? dw1 : q == 2 ? dw2 : dw3)[r] = mix.m[q] * acc[0] + mix.m[4 + q] * acc[1] + mix.m[8 + q] * acc[2] + mix.m[12 + q] * acc[3];
+}
+
 // dense Hamilton weights for narrow layers: one real conv over all 4*C_q channels with the mixing matrix folded in,
 //   FWD  : Wp[tap][n = p*Co + co][k = q*Ci + ci] = M[p][q] W_q[co][ci][tap];  bias'[p*Co + co] = M[p][0] b_r[co]
 //   DGRAD: Wp[tap][n = q*Ci + ci][k = p*Co + co] = M[p][q] W_q[co][ci][taps-1-tap]      (input is dY itself)
@@ -959,7 +982,7 @@ __global__ void __launch_bounds__(256) pack_weights_dense_kernel(const float* __
                                                                  const float* __restrict__ w2, const float* __restrict__ w3,
                                                                  const float* __restrict__ bias_r, T* __restrict__ out,
                                                                  float* __restrict__ bias_out, int Co, int Ci, int taps,
-                                                                 const Mix16 mix) {
+                                                                 const Mix16 mix, int depthwise) {
   pdl_prologue();
   const int N = DGRAD ? 4 * Ci : 4 * Co, K = DGRAD ? 4 * Co : 4 * Ci;
   const int64_t total = (int64_t)taps * N * K;
@@ -972,7 +995,9 @@ __global__ void __launch_bounds__(256) pack_weights_dense_kernel(const float* __
     if constexpr (DGRAD) { q = n / Ci; ci = n % Ci; pc = k / Co; co = k % Co; tap = taps - 1 - t; }
     else { pc = n / Co; co = n % Co; q = k / Ci; ci = k % Ci; tap = t; }
     const float* w = q == 0 ? w0 : q == 1 ? w1 : q == 2 ? w2 : w3;
-    float v = mix.m[pc * 4 + q] * __ldg(w + ((int64_t)co * Ci + ci) * taps + tap);
+    // depthwise: the master weight is [Co][1][taps]; the dense matrix is its block diagonal
+    float v = depthwise ? (ci == co ? mix.m[pc * 4 + q] * __ldg(w + (int64_t)co * taps + tap) : 0.f)
+                        : mix.m[pc * 4 + q] * __ldg(w + ((int64_t)co * Ci + ci) * taps + tap);
     if constexpr (sizeof(T) == 4) {
       uint32_t r32;
       asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r32) : "f"(v));
@@ -1305,7 +1330,7 @@ static int pack_weights_dense(const float* const w[4], const float* bias_r, void
   int grid = grid_for(total, 256, 4);
   QUAN_TIMED(st);
   QUAN_LAUNCH((pack_weights_dense_kernel<T, DGRAD>), grid, 256, 0, st, w[0], w[1], w[2], w[3], bias_r, reinterpret_cast<T*>(out), bias_out,
-                                                            d.Co, d.Ci, taps, mix);
+                                                            d.Co, d.Ci, taps, mix, depthwise_as_dense(d) ? 1 : 0);
   QUAN_CHECK_LAUNCH("pack_weights_dense_kernel");
   return QUAN_OK;
 }
@@ -1321,7 +1346,7 @@ struct PackJob {
   const float* bias_r;
   void* out;
   float* bias_out;
-  int Co, Ci, taps, form, esz;
+  int Co, Ci, taps, form, esz, depthwise;
   int block0, nblocks;
   int64_t total;
   Mix16 mix;
@@ -1340,7 +1365,8 @@ static PackPlan& pack_plan() {
 }
 static bool same_job(const PackJob& a, const float* const w[4], const float* bias_r, int form, int esz, const quan_conv_dims& d, const Mix16& M) {
   return a.w[0] == w[0] && a.w[1] == w[1] && a.w[2] == w[2] && a.w[3] == w[3] && a.bias_r == bias_r && a.form == form && a.esz == esz &&
-         a.Co == d.Co && a.Ci == d.Ci && a.taps == d.kH * d.kW && memcmp(a.mix.m, M.m, sizeof(M.m)) == 0;
+         a.Co == d.Co && a.Ci == d.Ci && a.taps == d.kH * d.kW && a.depthwise == (depthwise_as_dense(d) ? 1 : 0) &&
+         memcmp(a.mix.m, M.m, sizeof(M.m)) == 0;
 }
 // the arena slot of this pack when the plan is active (else nullptr; while recording, the pack is noted for the next commit)
 static void* planned_pack(const float* const w[4], const float* bias_r, int form, int dtype, const quan_conv_dims& d, const Mix16& M) {
@@ -1354,6 +1380,7 @@ static void* planned_pack(const float* const w[4], const float* bias_r, int form
     PackJob j = {};
     for (int q = 0; q < 4; ++q) j.w[q] = w[q];
     j.bias_r = bias_r; j.Co = d.Co; j.Ci = d.Ci; j.taps = d.kH * d.kW; j.form = form; j.esz = esz; j.mix = M;
+    j.depthwise = depthwise_as_dense(d) ? 1 : 0;
     const bool dense = form >= PACK_DENSE_FWD;
     j.total = (int64_t)(dense ? 16 : 4) * j.taps * d.Co * d.Ci;
     pl.jobs.push_back(j);
@@ -1388,7 +1415,9 @@ __device__ __forceinline__ void pack_one(const PackJob& j, int64_t i) {
     int pc, q, co, ci, tap;
     if (dg) { q = n / Ci; ci = n % Ci; pc = k / Co; co = k % Co; tap = taps - 1 - t; }
     else { pc = n / Co; co = n % Co; q = k / Ci; ci = k % Ci; tap = t; }
-    v = round_operand(j.mix.m[pc * 4 + q] * __ldg(j.w[q] + ((int64_t)co * Ci + ci) * taps + tap), sizeof(T));
+    v = j.depthwise ? (ci == co ? j.mix.m[pc * 4 + q] * __ldg(j.w[q] + (int64_t)co * taps + tap) : 0.f)
+                    : j.mix.m[pc * 4 + q] * __ldg(j.w[q] + ((int64_t)co * Ci + ci) * taps + tap);
+    v = round_operand(v, sizeof(T));
     if (!dg && j.bias_out != nullptr && i < 4 * Co) j.bias_out[i] = j.bias_r ? j.mix.m[(i / Co) * 4] * __ldg(j.bias_r + i % Co) : 0.f;
   }
   reinterpret_cast<T*>(j.out)[i] = from_f32<T>(v);
@@ -1640,7 +1669,10 @@ static int launch_wgrad(const void* gq, const void* x, float* const dw[4], const
     QUAN_TIMED(st);
     static const int env_flat = [] { const char* e = getenv("QUAN_TC_WG_FLATFOLD"); return e ? atoi(e) : 1; }();
     const int64_t dw_elems = (int64_t)4 * d.Co * d.Ci * p.taps;
-    if (env_flat && fold_splits <= 4 && dw_elems <= (1 << 18)) {
+    if (dense && depthwise_as_dense(d)) {
+      QUAN_LAUNCH((wgrad_reduce_dw_kernel), (unsigned)((4 * d.Co * p.taps + 255) / 256), 256, 0, st, p.partial, dw[0], dw[1], dw[2], dw[3], fold_splits,
+                  p.taps, d.Co, mix);
+    } else if (env_flat && fold_splits <= 4 && dw_elems <= (1 << 18)) {
       const unsigned fgrid = (unsigned)((dw_elems + 255) / 256);
       if (dense)
         QUAN_LAUNCH((wgrad_reduce_flat_kernel<true>), fgrid, 256, 0, st, p.partial, dw[0], dw[1], dw[2], dw[3], fold_splits, p.taps, d.Co, d.Ci, mix);
@@ -1660,6 +1692,17 @@ static int launch_wgrad(const void* gq, const void* x, float* const dw[4], const
 // the tensor core (K rows of C_i*2 bytes < one swizzle row, N = C_o).  For them the Hamilton-structured weight is
 // treated as the dense contraction it is: one GEMM over all 4*C_q channels, M folded into the packed weights — 4x the
 // separable FLOPs on a pipe with far more than 4x headroom, no mix epilogue and no G = M^T dY pre-pass.
+// Depthwise QConv2D (DWConv, conv.py:918-923: groups = C_i = C_o) on the tensor cores: the QUAN heads use it at 16-64 quaternion
+// channels, where the layer moves 2-4 bytes per MAC — far below the ridge whatever the engine — and the CUDA-core depthwise kernels
+// are bound by their own load / fold instructions (0.3 of the HBM floor forward, 0.15 backward).  The dense Hamilton form with a
+// block-diagonal weight (W[co][ci] = 0 for ci != co) spends C times the MACs on a pipe with more than C times the headroom and
+// re-uses every piece of the narrow-layer path: halo tiles, epilogue statistics, split-K wgrad (whose fold keeps the diagonal).
+// QUAN_TC_DEPTHWISE=0 keeps depthwise layers on the CUDA-core engine.
+static bool depthwise_as_dense(const quan_conv_dims& d) {
+  static const int on = [] { const char* e = getenv("QUAN_TC_DEPTHWISE"); return e ? atoi(e) : 1; }();
+  return on && d.groups > 1 && d.groups == d.Ci && d.Ci == d.Co && 4 * d.Ci <= 256;
+}
+
 static int env_dense() {   // QUAN_TC_DENSE = 0: never, 1: whenever the shape allows (tests), unset: by channel count
   static int v = -2;
   if (v == -2) { const char* e = getenv("QUAN_TC_DENSE"); v = e ? atoi(e) : -1; }
@@ -1688,9 +1731,11 @@ static ShapeKey shape_key(const quan_conv_dims& d, int dtype, int layout, int pa
 }
 
 static int qconv_tc_mode_uncached(const quan_conv_dims& d, int dtype, int layout, int pass) {
-  if (layout != QUAN_LAYOUT_BHWQC || d.groups != 1) return TC_NONE;
+  // depthwise layers of up to 64 quaternion channels run as the DENSE form with a block-diagonal packed weight (depthwise_as_dense)
+  const bool dwd = depthwise_as_dense(d);
+  if (layout != QUAN_LAYOUT_BHWQC || (d.groups != 1 && !dwd)) return TC_NONE;
   if (get_encode_fn() == nullptr) return TC_NONE;
-  const int e = env_dense();
+  const int e = dwd ? 1 : env_dense();
   bool sep = false, dense = false;
   int kch = d.Ci;
   if (pass == PASS_FWD) {
@@ -1707,6 +1752,7 @@ static int qconv_tc_mode_uncached(const quan_conv_dims& d, int dtype, int layout
     kch = d.Ci < d.Co ? d.Ci : d.Co;
   }
   if (e == 0) dense = false;
+  if (dwd) return dense ? TC_DENSE : TC_NONE;
   if (dense && (e == 1 || !sep || prefer_dense(kch, dtype))) return TC_DENSE;
   return sep ? TC_SEPARABLE : TC_NONE;
 }

@@ -84,7 +84,11 @@ def test_tc_is_what_auto_picks_for_the_sweep_shapes():
     # reference layout / grouped / 1-2 channel convs stay on the direct engine
     assert ops.qconv2d_pick_algo((16, 64, 32, 32, 4), (64, 64, 3, 3), (1, 1), (1, 1), (1, 1), 1, torch.bfloat16,
                                  ops.LAYOUT_BCHWQ, 0) == ops.ALGO_DIRECT
+    # depthwise layers of up to 64 quaternion channels: dense form with a block-diagonal weight on the tensor cores; wider ones on the
+    # streaming CUDA-core engine
     assert ops.qconv2d_pick_algo((16, 64, 32, 32, 4), (64, 1, 3, 3), (1, 1), (1, 1), (1, 1), 64, torch.bfloat16, L, 0) \
+        == ops.ALGO_TCGEN05
+    assert ops.qconv2d_pick_algo((16, 128, 32, 32, 4), (128, 1, 3, 3), (1, 1), (1, 1), (1, 1), 128, torch.bfloat16, L, 0) \
         == ops.ALGO_DEPTHWISE
     assert ops.qconv2d_pick_algo((16, 64, 32, 32, 4), (64, 2, 3, 3), (1, 1), (1, 1), (1, 1), 32, torch.bfloat16, L, 0) \
         == ops.ALGO_DIRECT
@@ -161,21 +165,57 @@ def test_depthwise_engine_matches_direct_engine(case):
     w = [torch.randn(Cq, 1, k, k, device=DEV) / k for _ in range(4)]
     b = torch.randn(Cq, device=DEV) if bias else None
     args = ((s, s), (p, p), (d, d), Cq, ops.MIX[mix])
-    picks = [ops.qconv2d_pick_algo(x.shape, w[0].shape, *args[:4], dtype, L, ps) for ps in range(3)]
-    assert picks[0] == ops.ALGO_DEPTHWISE and picks[1] == ops.ALGO_DEPTHWISE
-    assert picks[2] == (ops.ALGO_DEPTHWISE if k * k <= 9 else ops.ALGO_DIRECT)
     y_ref = ops.qconv2d_fwd(x, w, b, *args, ops.ALGO_DIRECT, L)
-    y = ops.qconv2d_fwd(x, w, b, *args, ops.ALGO_AUTO, L)
+    y = ops.qconv2d_fwd(x, w, b, *args, ops.ALGO_DEPTHWISE, L)
     assert rel(y, y_ref) <= tol
     dy = torch.randn_like(y_ref)
     dx_ref, dw_ref, db_ref = ops.qconv2d_bwd(dy, x, w, *args, True, True, bias, ops.ALGO_DIRECT)
-    dx, dw, db = ops.qconv2d_bwd(dy, x, w, *args, True, True, bias, ops.ALGO_AUTO)
+    if k * k <= 9:
+        dx, dw, db = ops.qconv2d_bwd(dy, x, w, *args, True, True, bias, ops.ALGO_DEPTHWISE)
+    else:                                                # 5x5: the depthwise engine serves forward and dgrad, the generic engine wgrad
+        dx, _, _ = ops.qconv2d_bwd(dy, x, w, *args, True, False, False, ops.ALGO_DEPTHWISE)
+        _, dw, db = ops.qconv2d_bwd(dy, x, w, *args, False, True, bias, ops.ALGO_DIRECT)
     # the generic engine rounds G = M^T dY to bf16 before using it; the depthwise kernels keep it in fp32
     assert rel(dx, dx_ref) <= 2 * tol
     for a, r in zip(dw, dw_ref):
         assert rel(a, r) <= 2 * tol
     if bias:
         assert rel(db, db_ref) <= 1e-4
+
+
+# name: (dtype, B, C, H, W, s, bias, mix) — depthwise 3x3 layers of the QUAN-YOLO11n head (16 / 32 / 64 channels) and ragged maps
+DWTC_CASES = [("bf16_c16_128", "bf16", 2, 16, 128, 128, 1, False, "A"), ("bf16_c32_64", "bf16", 4, 32, 64, 64, 1, False, "A"),
+              ("bf16_c64_32_bias", "bf16", 4, 64, 32, 32, 1, True, "B"), ("bf16_c16_ragged", "bf16", 3, 16, 21, 19, 1, False, "A"),
+              ("f32_c16", "f32", 2, 16, 32, 32, 1, True, "A"), ("bf16_c32_s2", "bf16", 2, 32, 32, 32, 2, False, "A")]
+
+
+@pytest.mark.parametrize("case", DWTC_CASES, ids=[c[0] for c in DWTC_CASES])
+def test_depthwise_on_the_tensor_cores_matches_direct_engine(case):
+    """DWConv (conv.py:918-923) of up to 64 quaternion channels as the dense tensor-core form with a block-diagonal packed weight
+    (qconv_tc.cu depthwise_as_dense) against the golden-validated generic engine: forward, dgrad, and the wgrad whose fold keeps the
+    block diagonal.  Tolerances are the engine's: 1e-2 bf16, 1e-3 tf32."""
+    name, dt, B, Cq, H, W, s, bias, mix = case
+    dtype = torch.bfloat16 if dt == "bf16" else torch.float32
+    tol = 1e-2 if dtype == torch.bfloat16 else 1e-3
+    torch.manual_seed(6)
+    x = torch.randn(B, Cq, H, W, 4, device=DEV).to(dtype).contiguous(memory_format=torch.channels_last_3d)
+    w = [torch.randn(Cq, 1, 3, 3, device=DEV) / 3 for _ in range(4)]
+    b = torch.randn(Cq, device=DEV) if bias else None
+    args = ((s, s), (1, 1), (1, 1), Cq, ops.MIX[mix])
+    picks = [ops.qconv2d_pick_algo(x.shape, w[0].shape, *args[:4], dtype, L, ps) for ps in range(3)]
+    assert picks[0] == ops.ALGO_TCGEN05 and (s != 1 or picks == [ops.ALGO_TCGEN05] * 3), picks
+    y_ref = ops.qconv2d_fwd(x, w, b, *args, ops.ALGO_DIRECT, L)
+    y = ops.qconv2d_fwd(x, w, b, *args, ops.ALGO_AUTO, L)
+    assert rel(y, y_ref) <= tol
+    dy = torch.randn_like(y_ref)
+    dx_ref, dw_ref, db_ref = ops.qconv2d_bwd(dy, x, w, *args, True, True, bias, ops.ALGO_DIRECT)
+    dx, dw, db = ops.qconv2d_bwd(dy, x, w, *args, True, True, bias, ops.ALGO_AUTO)
+    assert dx.shape == x.shape and all(a.shape == (Cq, 1, 3, 3) for a in dw)
+    assert rel(dx, dx_ref) <= 2 * tol
+    for a, r in zip(dw, dw_ref):
+        assert rel(a, r) <= 2 * tol
+    if bias:
+        assert rel(db, db_ref) <= 1e-3
 
 
 @pytest.mark.parametrize("cfg", [("sep_bf16", torch.bfloat16, 64, 64, 1), ("sep_f32", torch.float32, 64, 128, 1),
