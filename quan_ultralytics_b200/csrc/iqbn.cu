@@ -378,7 +378,6 @@ __global__ void __launch_bounds__(IQBN_TMA_THREADS, 2) iqbn_reduce_tma(const T* 
   uint8_t* ring = tsm;                                                        // [stages][NSTREAM][tile_bytes]
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + (size_t)g.stages * NSTREAM * tile_bytes);
   uint64_t* empty_bar = full_bar + g.stages;
-  double (*red)[2] = reinterpret_cast<double (*)[2]>(empty_bar + g.stages);  // [256][2]
   const int warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
     for (int i = 0; i < g.stages; ++i) {
@@ -524,9 +523,14 @@ __global__ void __launch_bounds__(IQBN_TMA_THREADS, 2) iqbn_reduce_tma(const T* 
     k[2 * i + 1] = -b;
   }
 
-  // fold over the row lanes (consumer threads only: named barrier 1) and write this block's slot of the partials
+  // fold over the row lanes (consumer threads only: named barrier 1) and write this block's slot of the partials.  All V column
+  // elements of a thread go through the tree together, in the ring's memory (free once every consumer has left the tile loop): the
+  // first version folded one element at a time through a [256][2] array — 7 barrier rounds x V = 56 per block, ~3 us of every launch,
+  // a third of the kernel on the 2-8 MB tensors of the narrow layers.
   int half = 1;
   while (half * 2 < g.rpb) half *= 2;
+  double (*redv)[2 * V] = reinterpret_cast<double (*)[2 * V]>(ring);          // [256][2V] doubles <= 32 KB <= one ring stage pair
+  asm volatile("bar.sync 1, %0;" ::"n"(IQBN_TMA_CONSUMERS) : "memory");      // every consumer is done with the ring
 #pragma unroll
   for (int i = 0; i < V; ++i) {
     double a0, a1;
@@ -538,22 +542,24 @@ __global__ void __launch_bounds__(IQBN_TMA_THREADS, 2) iqbn_reduce_tma(const T* 
       a0 = (double)s0[i];
       a1 = (double)s1[i];
     }
-    asm volatile("bar.sync 1, %0;" ::"n"(IQBN_TMA_CONSUMERS) : "memory");
-    red[threadIdx.x][0] = lane_on ? a0 : 0.0;
-    red[threadIdx.x][1] = lane_on ? a1 : 0.0;
-    asm volatile("bar.sync 1, %0;" ::"n"(IQBN_TMA_CONSUMERS) : "memory");
-    for (int st = half; st >= 1; st >>= 1) {
-      if (rl < st && rl + st < g.rpb) {
-        red[threadIdx.x][0] += red[threadIdx.x + st * g.cvpg][0];
-        red[threadIdx.x][1] += red[threadIdx.x + st * g.cvpg][1];
-      }
-      asm volatile("bar.sync 1, %0;" ::"n"(IQBN_TMA_CONSUMERS) : "memory");
+    redv[threadIdx.x][2 * i] = lane_on ? a0 : 0.0;
+    redv[threadIdx.x][2 * i + 1] = lane_on ? a1 : 0.0;
+  }
+  asm volatile("bar.sync 1, %0;" ::"n"(IQBN_TMA_CONSUMERS) : "memory");
+  for (int st = half; st >= 1; st >>= 1) {
+    if (rl < st && rl + st < g.rpb) {
+#pragma unroll
+      for (int e = 0; e < 2 * V; ++e) redv[threadIdx.x][e] += redv[threadIdx.x + st * g.cvpg][e];
     }
-    if ((int)threadIdx.x < g.cvpg) {
+    asm volatile("bar.sync 1, %0;" ::"n"(IQBN_TMA_CONSUMERS) : "memory");
+  }
+  if ((int)threadIdx.x < g.cvpg) {
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
       const int col = threadIdx.x * V + i;
       const int q = col / g.C, c = col - q * g.C;
-      ws.part[((size_t)blockIdx.x * 2 + 0) * 4 * g.C + c * 4 + q] = red[threadIdx.x][0];
-      ws.part[((size_t)blockIdx.x * 2 + 1) * 4 * g.C + c * 4 + q] = red[threadIdx.x][1];
+      ws.part[((size_t)blockIdx.x * 2 + 0) * 4 * g.C + c * 4 + q] = redv[threadIdx.x][2 * i];
+      ws.part[((size_t)blockIdx.x * 2 + 1) * 4 * g.C + c * 4 + q] = redv[threadIdx.x][2 * i + 1];
     }
   }
 }
@@ -1148,7 +1154,9 @@ static int launch_reduce(const void* x, const void* dy, int B, int C, int H, int
         if (stages > 8) stages = 8;
         if (stages >= 2) {
           g.stages = stages;
-          const size_t smem = stages * tile_bytes + 2 * stages * sizeof(uint64_t) + IQBN_TMA_CONSUMERS * 2 * sizeof(double) + 128;
+          // the block fold re-uses the ring: [256 consumers][2 x 8 column elements] doubles = 32 KB at most
+          const size_t fold_bytes = (size_t)IQBN_TMA_CONSUMERS * 16 * sizeof(double);
+          const size_t smem = (stages * tile_bytes > fold_bytes ? stages * tile_bytes : fold_bytes) + 2 * stages * sizeof(uint64_t) + 128;
           int grid = g.ntiles < bps * QUAN_NUM_SMS ? g.ntiles : bps * QUAN_NUM_SMS;
           nparts = grid;
           QUAN_TIMED(st);

@@ -236,9 +236,31 @@ __device__ __forceinline__ void stat_add(float* sacc, int cq, int col0, const fl
   atomicAdd(sacc + (lane >> 4) * 4 * cq + col0 + (lane & 15), v[0]);
 }
 
+// same butterfly on per-thread running sums (s: sums of 16 columns over the rows this thread has seen, q: sums of squares)
+__device__ __forceinline__ void stat_add_sums(float* sacc, int cq, int col0, const float (&s)[16], const float (&q)[16], int lane) {
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) { v[j] = s[j]; v[16 + j] = q[j]; }
+#pragma unroll
+  for (int n = 16, off = 16; n >= 1; n >>= 1, off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+      const float send = up ? v[i] : v[i + n];
+      const float keep = up ? v[i + n] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  atomicAdd(sacc + (lane >> 4) * 4 * cq + col0 + (lane & 15), v[0]);
+}
+
 constexpr int TC_THREADS = 192;    // wgrad kernel: warp 0 TMA producer, warp 1 TMEM alloc + MMA issuer, warps 2-5 epilogue
 constexpr int EPI_WARPS = 8;       // igemm kernel: two epilogue warps per TMEM lane quarter (they split the columns)
-constexpr int IG_THREADS = 64 + 32 * EPI_WARPS;
+// Epilogue groups: the kernel can run one group of EPI_WARPS epilogue warps per TMEM accumulator of the dense form (units alternating
+// between them).  Measured on B200 with two groups: 8 -> 8 1x1 at 256^2 88 vs 86 us, 16 -> 16 3x3 at 128^2 68 vs 61 us, whole step
+// 12.67 vs 12.35 ms — the epilogue's cost was its instruction count (the statistics butterfly), not its latency; one group it stays.
+constexpr int epi_groups(int nq) { return nq == 1 ? 1 : 1; }   // measured: a second group (one per accumulator) gains nothing — see stat_add
+constexpr int ig_threads(int nq) { return 64 + 32 * EPI_WARPS * epi_groups(nq); }
 
 // Persistent implicit-GEMM kernel.  One CTA (CG = 1) or CTA pair (CG = 2, tcgen05.mma.cta_group::2, M = 256, the
 // BN x BK weight tile split across the pair's shared memory) per SM loops over work units; the three roles run as
@@ -257,8 +279,8 @@ constexpr int IG_THREADS = 64 + 32 * EPI_WARPS;
 // `elect.sync` around the single-thread instructions, (2) a pipeline stage bundles `sub` (tap, k-block) steps, and
 // (3) this persistent form removes the per-CTA prologue and all but the S_0 copy of the epilogue from the MMA
 // thread's critical path.
-template <typename T, bool MIX, int CG, int KSTEPS, int NQ>
-__global__ void __launch_bounds__(IG_THREADS, 1)
+template <typename T, bool MIX, int CG, int KSTEPS, int NQ, bool RSTAT = false>
+__global__ void __launch_bounds__(ig_threads(NQ), 1)
 qconv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, T* __restrict__ y,
                    const TcConvParams p) {
   pdl_prologue();
@@ -306,7 +328,7 @@ qconv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     else ptx::tmem_alloc(tmem_ptr, p.tmem_cols);
   }
   if (p.stat_part != nullptr && warp >= 2)
-    for (int e = threadIdx.x - 64; e < 8 * p.stat_cq; e += 32 * EPI_WARPS) sacc[e] = 0.f;
+    for (int e = threadIdx.x - 64; e < 8 * p.stat_cq; e += 32 * EPI_WARPS * epi_groups(NQ)) sacc[e] = 0.f;
   ptx::tc_fence_before();
   if constexpr (CG == 2) ptx::cluster_sync_all();   // peer's barriers must be initialised before anything signals them
   else __syncthreads();
@@ -522,13 +544,25 @@ qconv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   } else {
     // ===== epilogue: warps 2..9; TMEM lane quarter = warp % 4, the two warps of a quarter take alternate 16-column chunks =====
     const int quarter = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int half = ((warp - 2) >> 2) & 1;
+    const uint32_t grp = (uint32_t)(warp - 2) >> 3;    // with two epilogue groups: the TMEM accumulator this one drains
+    (void)grp;
     const int m = quarter * 32 + lane;                 // accumulator row = pixel within the tile
     const int wt = m % p.Wt, ht = (m / p.Wt) % p.Ht, bt = m / (p.Wt * p.Ht);
     const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const int nchunks = p.BN >> 4;
     constexpr int VW = 16 / sizeof(T);                 // elements per 16-byte store
     uint32_t t_local = 0;
+    // Fused IQBN statistics of the dense form.  A thread always holds the same 16 (or 2 x 16) columns of ITS pixel row when the
+    // layer is one N tile wide, so the column sums can run in registers across every unit of the CTA and meet the other rows once at
+    // the end.  The per-unit butterfly (31 shuffles + a shared-memory atomic per 16 outputs) was 45 % of the forward kernel's stall
+    // samples on the narrow layers (ncu source page, 16 -> 16 3x3 at 128^2: profiles/r02_ncu_igemm_narrow_source.txt).
+    // RSTAT is its own instantiation: the 64 accumulator registers (155 per thread instead of 86) keep the plain kernels from sharing an
+    // SM with the concurrent wgrad of the narrow layers' backward (measured: dgrad 2.06 -> 2.25 ms per step with one fat kernel).
+    constexpr bool reg_stats = RSTAT;
+    float rs0[RSTAT ? 16 : 1], rq0[RSTAT ? 16 : 1], rs1[RSTAT ? 16 : 1], rq1[RSTAT ? 16 : 1];
+#pragma unroll
+    for (int j = 0; j < (RSTAT ? 16 : 1); ++j) rs0[j] = rq0[j] = rs1[j] = rq1[j] = 0.f;
     auto release = [&](uint64_t* bar) {                // one arrival per epilogue warp (TMEM reads of this warp are done)
       ptx::tc_fence_before();
       __syncwarp();
@@ -539,6 +573,9 @@ qconv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       __syncwarp();
     };
     for (int unit = cluster; unit < p.units; unit += nclusters, ++t_local) {
+      if constexpr (epi_groups(NQ) == 2) {
+        if ((t_local & 1u) != grp) continue;           // the other group's unit (warp-uniform)
+      }
       int cls, ucls, nt, tile, tw, th, tb;
       p.fd_upc.divmod((uint32_t)unit, cls, ucls);
       p.fd_ntn.divmod((uint32_t)ucls, tile, nt);
@@ -639,7 +676,8 @@ qconv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         const uint32_t a = t_local & 1u;
         ptx::mbar_wait(tile_full + a, (t_local >> 1) & 1u);
         ptx::tc_fence_after();
-        for (int c = half; c < nchunks; c += 2) {
+        // one 16-column chunk of this thread's row: TMEM -> (+bias, eval-mode IQBN + act) -> global, and the IQBN statistics
+        auto chunk = [&](const int c, float (&rsum)[RSTAT ? 16 : 1], float (&rsq)[RSTAT ? 16 : 1], const bool in_regs) {
           const int c0 = c * 16;
           float acc[16];
           ptx::tmem_ld16(lane_base + a * (uint32_t)p.BN + (uint32_t)c0, acc);
@@ -665,22 +703,39 @@ qconv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             }
           }
           if (p.stat_part != nullptr) {      // dense form: column n = p*C_o + co is already the (component, channel) pair
-            if (!valid) {
+            if constexpr (RSTAT) {           // this thread's running column sums: folded across rows ONCE, after the last unit
+              if (in_regs && valid) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+                for (int j = 0; j < 16; ++j) { rsum[j] += acc[j]; rsq[j] = fmaf(acc[j], acc[j], rsq[j]); }
+              }
+            } else {
+              if (!valid) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+              }
+              stat_add(sacc, p.stat_cq, n0 + c0, acc, lane);
             }
-            stat_add(sacc, p.stat_cq, n0 + c0, acc, lane);
           }
+        };
+        if (nchunks <= 4) {                  // <= 2 chunks per warp (BN <= 64): compile-time register sets
+          if (half < nchunks) chunk(half, rs0, rq0, reg_stats);
+          if (half + 2 < nchunks) chunk(half + 2, rs1, rq1, reg_stats);
+        } else {
+          for (int c = half; c < nchunks; c += 2) chunk(c, rs0, rq0, false);
         }
         release(acc_empty + a);
       }
     }
+    if constexpr (RSTAT) {                             // rows of the warp meet here, once per kernel
+      if (half < nchunks) stat_add_sums(sacc, p.stat_cq, half * 16, rs0, rq0, lane);
+      if (half + 2 < nchunks) stat_add_sums(sacc, p.stat_cq, (half + 2) * 16, rs1, rq1, lane);
+    }
     if (p.stat_part != nullptr) {
       // this CTA's slot of the IQBN partials buffer (what iqbn_reduce_b writes): [2][C_o*4], index c*4 + q
-      asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");   // the 8 epilogue warps only
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS * epi_groups(NQ)) : "memory");   // the epilogue warps only
       const int n4 = 4 * p.stat_cq;
       double* slot = p.stat_part + (size_t)blockIdx.x * 2 * n4;
-      for (int e = threadIdx.x - 64; e < 2 * n4; e += 32 * EPI_WARPS) {
+      for (int e = threadIdx.x - 64; e < 2 * n4; e += 32 * EPI_WARPS * epi_groups(NQ)) {
         const int which = e / n4, r = e - which * n4;
         const int pc = r / p.stat_cq, co = r - pc * p.stat_cq;
         slot[which * n4 + co * 4 + pc] = (double)sacc[e];
@@ -1145,14 +1200,14 @@ static bool igemm_supported(const IgemmShape& s, int dtype) {
 }
 
 
-template <typename T, bool MIX, int CG, int KSTEPS, int NQ>
+template <typename T, bool MIX, int CG, int KSTEPS, int NQ, bool RSTAT = false>
 static int launch_igemm_inst(const CUtensorMap& map_a, const CUtensorMap& map_b, void* out, const TcConvParams& p, size_t smem,
                              const char* name, cudaStream_t st, int* ctas) {
-  auto kern = qconv_igemm_kernel<T, MIX, CG, KSTEPS, NQ>;
+  auto kern = qconv_igemm_kernel<T, MIX, CG, KSTEPS, NQ, RSTAT>;
   // persistent grid: one CTA (pair) per SM, as many as can be co-resident (queried once per instantiation)
   static thread_local int max_groups = 0;
   cudaLaunchConfig_t cfg = {};
-  cfg.blockDim = dim3(IG_THREADS);
+  cfg.blockDim = dim3(ig_threads(NQ));
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
@@ -1323,7 +1378,16 @@ static int launch_igemm(const void* in, const void* wpacked, const float* bias, 
   }
   if (p.tt.zero_fill) QUAN_CUDA(cudaMemsetAsync(out, 0, (size_t)s.B * s.Ho * s.Wo * NQ * s.N * esz, st));
   int ctas = 0, rc = QUAN_OK;
-#define QUAN_IGEMM_CASE(CGV, KS) rc = launch_igemm_inst<T, MIX, CGV, KS, NQ>(map_a, map_b, out, p, smem, s.name, st, &ctas)
+  // the dense form's statistics run in registers (RSTAT instantiation) when a thread keeps its columns for the whole kernel
+  static const int env_rstat = [] { const char* e = getenv("QUAN_TC_RSTAT"); return e ? atoi(e) : 1; }();
+  const bool rstat = env_rstat && NQ == 1 && p.stat_part != nullptr && p.ntiles_n == 1 && p.BN <= 64;
+#define QUAN_IGEMM_CASE(CGV, KS)                                                                                           \
+  do {                                                                                                                     \
+    if constexpr (NQ == 1) {                                                                                               \
+      if (rstat) { rc = launch_igemm_inst<T, MIX, CGV, KS, NQ, true>(map_a, map_b, out, p, smem, s.name, st, &ctas); break; } \
+    }                                                                                                                      \
+    rc = launch_igemm_inst<T, MIX, CGV, KS, NQ, false>(map_a, map_b, out, p, smem, s.name, st, &ctas);                       \
+  } while (0)
   if (cg == 2) {
     if (ksteps == 4) { QUAN_IGEMM_CASE(2, 4); }
     else if (ksteps == 2) { QUAN_IGEMM_CASE(2, 2); }
