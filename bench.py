@@ -912,10 +912,51 @@ def run_sweep(a):
                                      "achieved": ach, "unit": "TFLOP/s" if kind == "tensor" else "GB/s", "peak": pk, "frac": ach / pk})
                     del x, y, dy, w
                     torch.cuda.empty_cache()
+    # ---- the HBM-bound ops around the convolutions at the QUAN-YOLO11n shapes (16 x 1024^2): algorithmic bytes of SURVEY 8(d)
+    def hbm_row(name, shape, fn, nbytes):
+        ms = time_op(fn, 6, flush)
+        ach = nbytes / ms / 1e6
+        rows.append({"op": name, "shape": shape, "dtype": "bf16", "ms": ms, "bound": "hbm", "achieved": ach, "unit": "GB/s", "peak": peaks["hbm_gbs"],
+                     "frac": ach / peaks["hbm_gbs"], "algorithmic_mb": nbytes / 1e6})
+
+    bf = torch.bfloat16
+    cl = torch.channels_last_3d
+    img = torch.rand(16, 3, 1024, 1024, device=dev)
+    qimg = ops.poincare_fwd(img, bf)
+    gq = torch.randn_like(qimg)
+    npx = 16 * 1024 * 1024
+    hbm_row("poincare_fwd", "16x3x1024^2", lambda: ops.poincare_fwd(img, bf), npx * (12 + 8))
+    hbm_row("poincare_bwd", "16x3x1024^2", lambda: ops.poincare_bwd(img, gq), npx * (12 + 8 + 12))
+    del img, qimg, gq
+    for (C, H) in ((64, 32), (32, 64)):                      # yolo11-obb-quan.yaml:35,39
+        xu = torch.randn(16, C, H, H, 4, device=dev).to(bf).contiguous(memory_format=cl)
+        yu = ops.qupsample_fwd(xu, 2)
+        S = xu.numel() * 2
+        hbm_row("qupsample_fwd", f"16x{C}x{H}^2 -> {2 * H}^2", lambda: ops.qupsample_fwd(xu, 2), 5 * S)
+        hbm_row("qupsample_bwd", f"16x{C}x{H}^2 <- {2 * H}^2", lambda: ops.qupsample_bwd(yu, 2), 5 * S)
+    xp = torch.randn(16, 32, 32, 32, 4, device=dev).to(bf).contiguous(memory_format=cl)     # QSPPF: 5x5 stride 1 pad 2
+    yp, ip = ops.qmaxpool_fwd(xp, 5, 1, 2, with_idx=True)
+    Sp = xp.numel() * 2
+    hbm_row("qmaxpool_fwd (5,1,2)", "16x32x32^2", lambda: ops.qmaxpool_fwd(xp, 5, 1, 2, with_idx=True), 2.5 * Sp)
+    hbm_row("qmaxpool_bwd (5,1,2)", "16x32x32^2", lambda: ops.qmaxpool_bwd(yp, ip, (32, 32), 5, 1, 2), 2.5 * Sp)
+    for (C, H, N) in ((16, 128, 64), (16, 128, 15), (16, 64, 64)):          # head extractions: box / class at P3, box at P4
+        xq = torch.randn(16, C, H, H, 4, device=dev).to(bf).contiguous(memory_format=cl)
+        wq, bq = torch.randn(N, 4 * C, 1, 1, device=dev), torch.randn(N, device=dev)
+        buf = torch.empty(16, H, H, 80, device=dev, dtype=bf)
+        dq = torch.randn(16, H, H, 80, device=dev).to(bf)[..., :N].permute(0, 3, 1, 2)
+        by = 16 * H * H * (4 * C + N) * 2
+        hbm_row("qer_fwd", f"16x{C}x{H}^2 -> {N}", lambda: ops.qer_fwd(xq, wq, bq, buf, 0, 80 if N % 8 else N), by)
+        hbm_row("qer_dgrad", f"16x{C}x{H}^2 <- {N}", lambda: ops.qer_bwd(dq, xq, wq, True, False, False, 80 if N % 8 else 0), by)
+        hbm_row("qer_wgrad", f"16x{C}x{H}^2 x {N}", lambda: ops.qer_bwd(dq, xq, wq, False, True, True, 80 if N % 8 else 0), by)
+    a0 = torch.randn(16, 32, 64, 64, 4, device=dev).to(bf).contiguous(memory_format=cl)
+    b0 = torch.randn(16, 16, 64, 64, 4, device=dev).to(bf).contiguous(memory_format=cl)
+    h0, h1 = a0.chunk(2, 1)
+    hbm_row("rows_cat (C2f: 2 halves + 1)", "16x(16+16+16)x64^2", lambda: ops.qcat([h0, h1, b0]), 2 * (a0.numel() + b0.numel()) * 2)
     print(json.dumps({"workload": "QConv2D/IQBN layer sweep (BASELINE configs[1])", "peaks": peaks,
                       "note": "ops timed alone, L2 swept between launches; conv ms include the weight-packing / mix pre-pass / split-K fold "
                               "kernels of the call; tensor fractions against the measured bf16 burst peak (MEASURED_PEAKS.json) and, for tf32, "
-                              "against cuBLAS TF32 8192^3 measured in this run", "rows": rows}))
+                              "against cuBLAS TF32 8192^3 measured in this run; rows with a `shape` key: the HBM-bound ops around the convolutions at the "
+                              "QUAN-YOLO11n shapes (host launch latency of the Python wrapper is inside the small ones' times)", "rows": rows}))
 
 
 # ---------------------------------------------------------------------------------------------------------------

@@ -90,8 +90,11 @@ int quan_poincare_bwd(const float* rgb, const void* grad_out, float* grad_rgb,
  * quan_iqbn_bwd_reduce: sums[0..4C) = sum dz, sums[4C..8C) = sum dz*xhat, dz = dy*act'(z).
  * quan_iqbn_bwd_apply: dx = gamma*rstd*(dz - sums_dz/n - xhat*sums_dzxhat/n); if mix_t != NULL the result
  *   is additionally multiplied per quaternion by mix_t (used to emit G = M^T dY for the preceding QConv2D).
- * Workspace: quan_iqbn_workspace_bytes(C) bytes of scratch (per-row-split fp64 partial sums; no initialisation
- *   needed, results are deterministic).  Every reduction is two launches: stream + fold. */
+ * Workspace: quan_iqbn_workspace_bytes(C) bytes, ZERO-FILLED ONCE by the caller before its first use and private to one stream:
+ *   per-row-split fp64 partial sums (plain stores, folded by a second launch: deterministic), followed by [8C] fp64 accumulators
+ *   and a ticket that the single-launch reduction of small tensors (<= 40 MB streamed) adds to with L2 atomics; its last block
+ *   finishes the statistics and leaves accumulators and ticket zero again (summation order across blocks is then not fixed:
+ *   fp64, ~1e-16 relative).  QUAN_IQBN_SMALL_MB=0 keeps every reduction on the two-launch deterministic path. */
 size_t quan_iqbn_workspace_bytes(int32_t C);
 /* stats: [20*C] floats = mean | var(+1e-8) | rstd (index c*4+q) | scaleT | shiftT (index q*C+c, the BHWQC column order:
  * scale = gamma*rstd, shift = beta - mean*scale) — the table lets the streaming kernels fetch coefficients with 16-byte loads. */

@@ -25,12 +25,15 @@ namespace quan {
 // 2048 accumulators — cost 69 us on top of a 24 us stream; measured in profiles/r01_iqbn_tune2.log.)
 constexpr int IQBN_MAX_PARTS = 4 * QUAN_NUM_SMS;
 struct IqbnWs {
-  double* part;
+  double* part;          // [IQBN_MAX_PARTS][2][4C] per-block partial sums (plain stores, folded by iqbn_fold_kernel)
+  double* acc;           // [2][4C] accumulators of the single-launch reduction for small tensors: ZERO between launches
+  unsigned* counter;     // its block ticket: ZERO between launches
 };
 static inline IqbnWs carve_ws(void* ws, int C) {
-  (void)C;
   IqbnWs w;
   w.part = reinterpret_cast<double*>(ws);
+  w.acc = w.part + (size_t)IQBN_MAX_PARTS * 8 * C;
+  w.counter = reinterpret_cast<unsigned*>(w.acc + 8 * (size_t)C);
   return w;
 }
 
@@ -561,6 +564,124 @@ __global__ void __launch_bounds__(IQBN_TMA_THREADS, 2) iqbn_reduce_tma(const T* 
       ws.part[((size_t)blockIdx.x * 2 + 0) * 4 * g.C + c * 4 + q] = redv[threadIdx.x][2 * i];
       ws.part[((size_t)blockIdx.x * 2 + 1) * 4 * g.C + c * 4 + q] = redv[threadIdx.x][2 * i + 1];
     }
+  }
+}
+
+// Small tensors (the 32^2 / 64^2 maps of the narrow layers: 2-16 MB): ONE launch.  The TMA-ring kernel above plus the fold kernel cost
+// 9-14 us + 4.6 us + a launch gap for ~2 us of traffic, 150 times per QUAN-YOLO11n step.  Here a block streams its rows with plain
+// 16-byte loads (U rows in flight), folds its row lanes through shared memory once, adds its 8C sums to fp64 accumulators in L2 with
+// atomics (<= 64 K of them per launch: ~3 us at the L2's fp64-atomic rate, overlapped with the other blocks' streams) and the LAST
+// block (ticket) finishes: mean / var / rstd / running statistics / coefficient tables, then re-zeroes accumulators and ticket for
+// the next launch on this stream.  Summation order across blocks is not fixed; the sums are fp64 (differences ~1e-16 relative).
+template <typename T, int V, int MODE, int ACT>
+__global__ void __launch_bounds__(256) iqbn_reduce_small(const T* __restrict__ x, const T* __restrict__ dy, int64_t R, int C, int cvpg,
+                                                          int rpb, IqbnWs ws, TailArgs tail) {
+  pdl_prologue();
+  extern __shared__ __align__(16) uint8_t sm_raw[];
+  double (*sred)[2 * V] = reinterpret_cast<double (*)[2 * V]>(sm_raw);        // [256][2V]
+  __shared__ int is_last;
+  using VecT = Vec<T, V>;
+  const int L = 4 * C;
+  const int cvl = threadIdx.x % cvpg, rl = threadIdx.x / cvpg;
+  const bool on = rl < rpb;
+  const int64_t coloff = (int64_t)cvl * V;
+  float sc[V], sh[V];
+  if constexpr (MODE == 1 && ACT != QUAN_ACT_NONE) {
+    load_coef<float, V>(tail.stats + 12 * C + coloff, sc);
+    load_coef<float, V>(tail.stats + 16 * C + coloff, sh);
+  }
+  float s0[V], s1[V], k[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) s0[i] = s1[i] = k[i] = 0.f;
+  int cnt = 0;
+  bool have_k = false;
+  constexpr int U = 4;
+  const int64_t step = (int64_t)gridDim.x * rpb;
+  if (on) {
+    for (int64_t r = (int64_t)blockIdx.x * rpb + rl; r < R; r += U * step) {
+      VecT xs[U], gs[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t ru = r + u * step;
+        if (ru < R) {
+          xs[u] = *reinterpret_cast<const VecT*>(x + ru * L + coloff);
+          if constexpr (MODE == 1) gs[u] = *reinterpret_cast<const VecT*>(dy + ru * L + coloff);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (r + u * step >= R) break;
+        if constexpr (MODE == 0) {
+          if (!have_k) {                               // local shift: keeps the fp32 partials well conditioned
+#pragma unroll
+            for (int i = 0; i < V; ++i) k[i] = to_f32(xs[u].v[i]);
+            have_k = true;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          const float xv = to_f32(xs[u].v[i]);
+          if constexpr (MODE == 0) {
+            const float d = xv - k[i];
+            s0[i] += d;
+            s1[i] = fmaf(d, d, s1[i]);
+          } else {
+            float dz = to_f32(gs[u].v[i]);
+            if constexpr (ACT != QUAN_ACT_NONE) dz *= act_grad<ACT, sizeof(T) == 2>(fmaf(xv, sc[i], sh[i]));
+            s0[i] += dz;
+            s1[i] = fmaf(dz, xv, s1[i]);
+          }
+        }
+        ++cnt;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    double a0, a1;
+    if constexpr (MODE == 0) {
+      const double kd = (double)k[i], nd = (double)cnt;
+      a0 = (double)s0[i] + nd * kd;
+      a1 = (double)s1[i] + 2.0 * kd * (double)s0[i] + nd * kd * kd;
+    } else {
+      a0 = (double)s0[i];
+      a1 = (double)s1[i];
+    }
+    sred[threadIdx.x][2 * i] = on ? a0 : 0.0;
+    sred[threadIdx.x][2 * i + 1] = on ? a1 : 0.0;
+  }
+  __syncthreads();
+  int half = 1;
+  while (half * 2 < rpb) half *= 2;
+  for (int st = half; st >= 1; st >>= 1) {
+    if (on && rl < st && rl + st < rpb) {
+#pragma unroll
+      for (int e = 0; e < 2 * V; ++e) sred[threadIdx.x][e] += sred[threadIdx.x + st * cvpg][e];
+    }
+    __syncthreads();
+  }
+  if ((int)threadIdx.x < cvpg) {
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const int col = threadIdx.x * V + i;
+      const int q = col / C, c = col - q * C;
+      atomicAdd(ws.acc + c * 4 + q, sred[threadIdx.x][2 * i]);
+      atomicAdd(ws.acc + 4 * C + c * 4 + q, sred[threadIdx.x][2 * i + 1]);
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = atomicAdd(ws.counter, 1u) == gridDim.x - 1 ? 1 : 0;
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    for (int i = threadIdx.x; i < 4 * C; i += blockDim.x) {
+      const double t0 = __ldcg(ws.acc + i), t1 = __ldcg(ws.acc + 4 * C + i);
+      finish_accumulator(tail, i, t0, t1);
+      ws.acc[i] = 0.0;
+      ws.acc[4 * C + i] = 0.0;
+    }
+    if (threadIdx.x == 0) *ws.counter = 0u;
   }
 }
 
@@ -1133,6 +1254,29 @@ static int launch_reduce(const void* x, const void* dy, int B, int C, int H, int
   if (layout == QUAN_LAYOUT_BHWQC && C > 1) {
     LaunchB p;
     {
+      // small tensors: one launch (iqbn_reduce_small), no fold kernel.  QUAN_IQBN_SMALL_MB = 0 disables.
+      const int Vs = largest_pow2_divisor(C, VecTraits<T>::kMaxVec);
+      const int colvecs = 4 * C / Vs;
+      const int64_t R = (int64_t)B * H * W;
+      const double mb = (double)R * 4 * C * sizeof(T) * (MODE == 1 ? 2 : 1) / 1e6;
+      static const int small_mb = env_int("QUAN_IQBN_SMALL_MB", 40);
+      if (mb <= small_mb && colvecs <= 256 && Vs * sizeof(T) >= 8) {
+        const int rpb = 256 / colvecs;
+        int64_t blocks = ceil_div64(R, (int64_t)rpb * 4);
+        if (blocks > QUAN_NUM_SMS) blocks = QUAN_NUM_SMS;
+        if (blocks * 8 * C <= 65536) {
+          const size_t smem = (size_t)256 * 2 * Vs * sizeof(double);
+          QUAN_TIMED(st);
+#define QUAN_REDUCE_S(VV) QUAN_LAUNCH((iqbn_reduce_small<T, VV, MODE, ACT>), (unsigned)blocks, 256, smem, st, xp, dyp, R, C, colvecs, rpb, ws, tail)
+          if (Vs * sizeof(T) == 16) { if constexpr (sizeof(T) == 2) QUAN_REDUCE_S(8); else QUAN_REDUCE_S(4); }
+          else { if constexpr (sizeof(T) == 2) QUAN_REDUCE_S(4); else QUAN_REDUCE_S(2); }
+#undef QUAN_REDUCE_S
+          QUAN_CHECK_LAUNCH(MODE == 0 ? "iqbn_reduce_fwd_small" : "iqbn_reduce_bwd_small");
+          return QUAN_OK;
+        }
+      }
+    }
+    {
       // TMA-fed variant: whole rows per block (<= 256 column vectors), 16-byte multiples
       const int Vt = largest_pow2_divisor(C, VecTraits<T>::kMaxVec);
       const int colvecs = 4 * C / Vt;
@@ -1335,7 +1479,7 @@ using namespace quan;
 
 extern "C" {
 
-size_t quan_iqbn_workspace_bytes(int32_t C) { return (size_t)IQBN_MAX_PARTS * 8 * C * sizeof(double); }
+size_t quan_iqbn_workspace_bytes(int32_t C) { return ((size_t)IQBN_MAX_PARTS * 8 * C + 8 * (size_t)C + 2) * sizeof(double); }
 
 static int reduce_entry(int mode, const void* x, const void* dy, int B, int C, int H, int W, int dtype, int layout,
                         const float* gamma, const float* beta, int act, TailArgs tail, void* workspace,

@@ -50,7 +50,7 @@ def test_argument_errors_use_the_c_convention():
     assert lib.quan_qupsample_nearest_fwd(1, 1, 1, 1, 1, 1, 0, 0, 0, None) == -1
     with pytest.raises(RuntimeError, match="argument/shape error"):
         _lib.check(-2, "quan_qconv2d_fwd")
-    assert lib.quan_iqbn_workspace_bytes(16) == 592 * 8 * 16 * 8      # 4 x 148 row-split partials of [8C] fp64
+    assert lib.quan_iqbn_workspace_bytes(16) == (592 * 8 * 16 + 8 * 16 + 2) * 8      # 4 x 148 row-split partials of [8C] fp64 + the single-launch accumulators and ticket
     assert lib.quan_qconv2d_pick_algo(ctypes.byref(_lib.ConvDims(1, 4, 4, 8, 8, 3, 3, 1, 1, 1, 1, 1, 1, 1)), 1, 0, 0) == 1
 
 
