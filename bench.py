@@ -307,9 +307,13 @@ def kernels_in_step(lib, step_fn, steps, a, dtype, peaks):
 
 def ncu_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the bench-shape kernels, from the committed
-    `ncu --set full` captures (profiles/r01_ncu_traffic.json); None when a kernel has no capture."""
-    p = ROOT / "profiles" / "r01_ncu_traffic.json"
-    return json.loads(p.read_text()) if p.exists() else {}
+    ncu captures (profiles/r01_ncu_traffic.json, r02_ncu_traffic.json); None when a kernel has no capture."""
+    out = {}
+    for name in ("r01_ncu_traffic.json", "r02_ncu_traffic.json"):
+        p = ROOT / "profiles" / name
+        if p.exists():
+            out.update(json.loads(p.read_text()))
+    return out
 
 
 def kernel_table(a, dev, dtype, peaks):

@@ -252,6 +252,19 @@ typedef struct quan_cat_src {
 } quan_cat_src;
 int quan_rows_cat(const quan_cat_src* srcs, int32_t nsrc, void* dst, int64_t dst_ld_bytes, int64_t nrows, void* stream);
 
+/* Weight-gradient chains off the critical path.  The backward of a narrow layer already runs its wgrad next to its dgrad (fork / join
+ * on a library-owned stream inside quan_qconv2d_bwd / quan_conv_block_bwd).  With a LENT stream the join is deferred: after
+ *   quan_bwd_side_stream_set(side, ws, ws_bytes)   side: caller-owned stream; ws: workspace used by nothing else (>= the largest
+ *                                                  quan_qconv2d_workspace_bytes of the layers; smaller -> that layer joins as before)
+ * every tensor-core wgrad of a narrow layer (and its fold) is forked onto `side` and the call returns without waiting for it — dW is
+ * then only valid after
+ *   quan_bwd_side_stream_join(stream)              `stream` waits for everything forked so far (call it before the optimizer / the
+ *                                                  gradient all-reduce reads dW; once per step is enough).
+ * The caller keeps dY (or G), x and dW alive until the join (torch: record_stream on `side`).  quan_bwd_side_stream_set(NULL, NULL, 0)
+ * switches back.  Per device (process-wide); works under stream capture (the fork and the join become graph edges). */
+int quan_bwd_side_stream_set(void* side_stream, void* wgrad_workspace, size_t ws_bytes);
+int quan_bwd_side_stream_join(void* stream);
+
 /* ---- pack plan: all packed weights of a training step in one launch ------------------------------------------------------------
  * The tensor-core engine reads weights in a packed operand layout (per component or, for narrow layers, the dense Hamilton matrix with
  * the mixing matrix folded in), rebuilt from the fp32 masters by a small kernel in front of every forward and every dgrad.  Weights

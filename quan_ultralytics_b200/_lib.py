@@ -71,6 +71,8 @@ PROTOTYPES = {
                                         _vp, _sz, _vp]),
     "quan_qconv2d_bwd_premixed": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _pdims, _int, _int, _vp, _int, _vp, _sz, _vp]),
     "quan_qconv2d_bwd_wants_mixed": (_int, [_pdims, _int, _int, _int, _int, _int]),
+    "quan_bwd_side_stream_set": (_int, [_vp, _vp, _sz]),
+    "quan_bwd_side_stream_join": (_int, [_vp]),
     "quan_pack_plan_record": (_int, [_int]),
     "quan_pack_plan_bytes": (_sz, [C.POINTER(C.c_size_t)]),
     "quan_pack_plan_commit": (_int, [_vp, _sz, _vp, _sz, _vp]),

@@ -3,6 +3,7 @@
 // (ultralytics/nn/cuda/quaternion_ops.cu:735-799, :532-679); unlike those, every launch goes to the caller's
 // stream, outputs/workspace are caller-allocated, and launch errors are reported.
 #include "qconv_internal.cuh"
+#include <mutex>
 
 namespace quan {
 
@@ -80,6 +81,27 @@ struct ForkJoin {
   cudaStream_t side = nullptr;
   cudaEvent_t fork = nullptr, join = nullptr;
 };
+// Deferred join (quan_bwd_side_stream_set): the caller lends a side stream and a workspace of its own for the wgrad chains; the
+// wgrad of a narrow layer is then forked onto that stream and NOT joined by the call — the weight gradient is only needed by the
+// optimizer, so the ~80 wgrad launches of a step leave the dX critical path of the backward pass.  quan_bwd_side_stream_join makes a
+// stream wait for everything forked so far.  Per device, process-wide.
+struct DeferredSide {
+  cudaStream_t side = nullptr;
+  void* ws = nullptr;
+  size_t ws_bytes = 0;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  bool pending = false;
+};
+// process-wide, one per device: the setter runs on the host thread that drives the step, the backward kernels are launched from the
+// autograd engine's device thread
+static std::mutex g_deferred_mu;
+static DeferredSide& deferred_side() {
+  static DeferredSide d[16];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return d[dev & 15];
+}
+
 static int get_fork_join(ForkJoin** out) {
   static thread_local ForkJoin fj[16];
   int dev = 0;
@@ -168,7 +190,7 @@ static int qconv2d_bwd_impl(const void* dy, const void* x, const float* const w[
   void* tc_ws = (char*)workspace + gb;
   const size_t tc_ws_bytes = ws_bytes - gb;
   void* wg_ws = ws_bytes >= gb + pack_bytes ? (char*)workspace + gb + pack_bytes : nullptr;
-  const size_t wg_ws_bytes = ws_bytes >= gb + pack_bytes ? ws_bytes - gb - pack_bytes : 0;
+  size_t wg_ws_bytes = ws_bytes >= gb + pack_bytes ? ws_bytes - gb - pack_bytes : 0;
 
   // engine per pass; the dense tensor-core form consumes dY directly (M is folded into its weights / reduce step)
   int a_dx = 0, a_dw = 0, m_dx = TC_NONE, m_dw = TC_NONE;
@@ -204,13 +226,27 @@ static int qconv2d_bwd_impl(const void* dy, const void* x, const float* const w[
   const bool narrow = (m_dx == TC_DENSE || raw_dy(a_dx)) && (m_dw == TC_DENSE || raw_dy(a_dw));
   ForkJoin* fj = nullptr;
   cudaStream_t st_w = st;
-  if (env_conc && dx != nullptr && dw != nullptr && narrow) {
+  std::unique_lock<std::mutex> ds_lock(g_deferred_mu);
+  DeferredSide& ds = deferred_side();
+  const bool dw_narrow = m_dw == TC_DENSE || raw_dy(a_dw);          // the wgrad reads dY itself (no G pre-pass on the main stream)
+  if (env_conc && dw != nullptr && dw_narrow && !premixed && ds.side != nullptr && dbias_r == nullptr &&
+      (a_dw != QUAN_ALGO_TCGEN05 || ds.ws_bytes >= qconv_tc_workspace_bytes(*d, dtype, layout, PASS_WGRAD))) {
+    // deferred: fork only (the caller joins once, before anything reads the weight gradients); partials live in the lender's workspace
+    QUAN_CUDA(cudaEventRecord(ds.fork, st));
+    QUAN_CUDA(cudaStreamWaitEvent(ds.side, ds.fork, 0));
+    st_w = ds.side;
+    wg_ws = ds.ws;
+    wg_ws_bytes = ds.ws_bytes;
+    ds.pending = true;
+    ds_lock.unlock();
+  } else if (env_conc && dx != nullptr && dw != nullptr && narrow) {
     rc = get_fork_join(&fj);
     if (rc) return rc;
     QUAN_CUDA(cudaEventRecord(fj->fork, st));
     QUAN_CUDA(cudaStreamWaitEvent(fj->side, fj->fork, 0));
     st_w = fj->side;
   }
+  if (ds_lock.owns_lock()) ds_lock.unlock();
 
   if (dx != nullptr) {
     announce_conv_work(*d, dtype, PASS_DGRAD);
@@ -271,6 +307,39 @@ int quan_qconv2d_bwd_premixed(const void* g, const void* x, const float* const w
                               float* dbias_r, const quan_conv_dims* d, int dtype, int layout, const float* mix, int algo,
                               void* workspace, size_t ws_bytes, void* stream) {
   return qconv2d_bwd_impl(g, x, w, dx, dw, dbias_r, d, dtype, layout, mix, algo, workspace, ws_bytes, stream, true);
+}
+
+int quan_bwd_side_stream_set(void* side_stream, void* wgrad_workspace, size_t ws_bytes) {
+  std::lock_guard<std::mutex> lock(g_deferred_mu);
+  DeferredSide& ds = deferred_side();
+  if (side_stream == nullptr) {                // off: back to fork + join inside every call
+    QUAN_REQUIRE(!ds.pending, QUAN_E_ARG, "bwd_side_stream_set: join the forked work first (quan_bwd_side_stream_join)");
+    ds.side = nullptr; ds.ws = nullptr; ds.ws_bytes = 0;
+    return QUAN_OK;
+  }
+  QUAN_REQUIRE(wgrad_workspace != nullptr && ws_bytes > 0, QUAN_E_ARG, "bwd_side_stream_set: a side stream needs its own workspace");
+  if (ds.fork == nullptr) {
+    QUAN_CUDA(cudaEventCreateWithFlags(&ds.fork, cudaEventDisableTiming));
+    QUAN_CUDA(cudaEventCreateWithFlags(&ds.join, cudaEventDisableTiming));
+  }
+  ds.side = (cudaStream_t)side_stream; ds.ws = wgrad_workspace; ds.ws_bytes = ws_bytes;
+  return QUAN_OK;
+}
+
+int quan_bwd_side_stream_join(void* stream) {
+  std::lock_guard<std::mutex> lock(g_deferred_mu);
+  DeferredSide& ds = deferred_side();
+  if (ds.side == nullptr) return QUAN_OK;
+  // under stream capture the side stream only belongs to the capture once something was forked onto it; joining an uncaptured
+  // stream into a capturing one is an error (and there is nothing to wait for)
+  cudaStreamCaptureStatus cs_main = cudaStreamCaptureStatusNone, cs_side = cudaStreamCaptureStatusNone;
+  QUAN_CUDA(cudaStreamIsCapturing((cudaStream_t)stream, &cs_main));
+  QUAN_CUDA(cudaStreamIsCapturing(ds.side, &cs_side));
+  if (cs_main != cudaStreamCaptureStatusNone && cs_side == cudaStreamCaptureStatusNone) { ds.pending = false; return QUAN_OK; }
+  QUAN_CUDA(cudaEventRecord(ds.join, ds.side));
+  QUAN_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, ds.join, 0));
+  ds.pending = false;
+  return QUAN_OK;
 }
 
 int quan_qconv2d_bwd_wants_mixed(const quan_conv_dims* d, int dtype, int layout, int algo, int need_dx, int need_dw) {

@@ -86,6 +86,8 @@ class BucketedGradSync:
         if not pairs:
             return
         grads, views = [g for g, _ in pairs], [v for _, v in pairs]
+        from . import ops
+        ops.deferred_wgrad_join(grads[0].device)       # weight gradients forked onto the side stream (ops.deferred_wgrad) land first
         ev = torch.cuda.Event()
         ev.record()                                    # every gradient of the bucket is complete on the backward stream here
         self.comm_stream.wait_event(ev)
@@ -169,13 +171,15 @@ class GraphedTrainStep:
         if grad_sync is not None:
             grad_sync.attach()
         with torch.cuda.graph(self.g_bwd, pool=self.g_fwd.pool()):
-            if capture_loss:
-                self.loss.backward()
-            else:
-                live = [(t, d) for t, d in zip(self.out_flat, self.d_out) if t.requires_grad]
-                torch.autograd.backward([t for t, _ in live], [d for _, d in live])
-            if grad_sync is not None:
-                grad_sync.finish()
+            with ops.deferred_wgrad(dev):                      # wgrad chains off the dX critical path; joined before the optimizer
+                if capture_loss:
+                    self.loss.backward()
+                else:
+                    live = [(t, d) for t, d in zip(self.out_flat, self.d_out) if t.requires_grad]
+                    torch.autograd.backward([t for t, _ in live], [d for _, d in live])
+                if grad_sync is not None:
+                    ops.deferred_wgrad_join(dev)
+                    grad_sync.finish()
             self.opt.step()
         if grad_sync is not None:
             grad_sync.detach()

@@ -382,8 +382,21 @@ def qer_bwd(dy: torch.Tensor, x: torch.Tensor, weight: torch.Tensor, need_dx: bo
     wsb = _workspace(lib.quan_qer_workspace_bytes(npix, C_, N, _dtype_code(x)), x.device) if dw is not None else None
     if dy.stride(3) < max(readable, N):
         readable = 0
-    check(lib.quan_qer_bwd(dy.data_ptr(), dy.stride(3), int(readable), x.data_ptr(), w.data_ptr(), _ptr(dx), _ptr(dw), _ptr(db), npix, C_, N,
-                           _dtype_code(x), _ptr(wsb), 0 if wsb is None else wsb.numel(), _stream(x)), "quan_qer_bwd")
+    side = _deferred["side"].get(x.device.index) if (_deferred["on"] and dw is not None) else None
+    if side is None:
+        check(lib.quan_qer_bwd(dy.data_ptr(), dy.stride(3), int(readable), x.data_ptr(), w.data_ptr(), _ptr(dx), _ptr(dw), _ptr(db), npix, C_, N,
+                               _dtype_code(x), _ptr(wsb), 0 if wsb is None else wsb.numel(), _stream(x)), "quan_qer_bwd")
+        return dx, (dw if need_dw else None), db
+    # deferred_wgrad: dX on this stream, the weight / bias gradient (and its fold) on the lent side stream, joined with the others
+    if dx is not None:
+        check(lib.quan_qer_bwd(dy.data_ptr(), dy.stride(3), int(readable), x.data_ptr(), w.data_ptr(), dx.data_ptr(), None, None, npix, C_, N,
+                               _dtype_code(x), None, 0, _stream(x)), "quan_qer_bwd")
+    side.wait_stream(torch.cuda.current_stream(x.device))
+    with torch.cuda.stream(side):
+        wss = _workspace(lib.quan_qer_workspace_bytes(npix, C_, N, _dtype_code(x)), x.device)      # keyed by the (side) stream
+        check(lib.quan_qer_bwd(dy.data_ptr(), dy.stride(3), int(readable), x.data_ptr(), w.data_ptr(), None, dw.data_ptr(), _ptr(db), npix, C_, N,
+                               _dtype_code(x), wss.data_ptr(), wss.numel(), side.cuda_stream), "quan_qer_bwd")
+    _keep_for_side(x.device, dy, x, dw, db)
     return dx, (dw if need_dw else None), db
 
 
@@ -623,6 +636,8 @@ def qconv2d_bwd(dy: torch.Tensor, x: torch.Tensor, weights: Sequence[torch.Tenso
              None if dwa is None else C.cast(dwa, C.c_void_p), _ptr(db), C.byref(d), _dtype_code(x),
              layout, C.cast(_mix_arg(mix_matrix), C.c_void_p), algo, wsb.data_ptr(), wsb.numel(),
              _stream(x)), "quan_qconv2d_bwd")
+    if dws is not None:
+        _keep_for_side(x.device, dy, x, *dws)
     return dx, dws, db
 
 
@@ -693,6 +708,8 @@ def conv_block_bwd(dout: torch.Tensor, x: torch.Tensor, y: torch.Tensor, weights
                                   None if dwa is None else C.cast(dwa, C.c_void_p), dgamma.data_ptr(), dbeta.data_ptr(),
                                   sums.data_ptr(), C.byref(d), code, layout, C.cast(_mix_arg(mix_matrix), C.c_void_p), algo, act,
                                   wsb.data_ptr(), wsb.numel(), iws.data_ptr(), iws.numel(), _stream(x)), "quan_conv_block_bwd")
+    if dws is not None:
+        _keep_for_side(x.device, g, x, *dws)
     return dx, dws, dgamma, dbeta
 
 
@@ -718,6 +735,66 @@ def conv_block_eval_fwd(x: torch.Tensor, weights: Sequence[torch.Tensor], gamma,
                                        _ptr(y), C.byref(d), code, layout, C.cast(_mix_arg(mix_matrix), C.c_void_p), algo, eps,
                                        act, wsb.data_ptr(), wsb.numel(), _stream(x)), "quan_conv_block_eval_fwd")
     return out
+
+
+# ---- deferred weight-gradient join (include/quan_sm100.h: quan_bwd_side_stream_set / _join) --------------------------------------------------
+_deferred = {"on": False, "side": {}, "ws": {}}
+DEFERRED_WGRAD_WS_BYTES = 256 << 20
+
+
+class deferred_wgrad:
+    """Context manager around a backward pass: the tensor-core wgrad chains of the narrow layers are forked onto one lent side stream and
+    joined ONCE, at exit (or at `ops.deferred_wgrad_join()`): they only feed the optimizer, so they leave the dX critical path.  Tensors a
+    forked wgrad touches are handed to the allocator with record_stream.  QUAN_BWD_DEFER=0 turns it into a no-op."""
+
+    def __init__(self, device: torch.device):
+        import os
+        self.device = torch.device(device)
+        self.enabled = os.environ.get("QUAN_BWD_DEFER", "1") != "0" and self.device.type == "cuda"
+
+    def __enter__(self):
+        if not self.enabled:
+            return self
+        key = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        if key not in _deferred["side"]:
+            _deferred["side"][key] = torch.cuda.Stream(device=self.device)
+            _deferred["ws"][key] = torch.empty(DEFERRED_WGRAD_WS_BYTES, dtype=torch.uint8, device=self.device)
+        side, ws = _deferred["side"][key], _deferred["ws"][key]
+        with torch.cuda.device(self.device):
+            check(_lib.load().quan_bwd_side_stream_set(side.cuda_stream, ws.data_ptr(), ws.numel()), "quan_bwd_side_stream_set")
+        _deferred["on"] = True
+        return self
+
+    def __exit__(self, *exc):
+        if not self.enabled:
+            return False
+        deferred_wgrad_join(self.device)
+        _deferred["on"] = False
+        with torch.cuda.device(self.device):
+            _lib.load().quan_bwd_side_stream_set(None, None, 0)
+        return False
+
+
+def deferred_wgrad_join(device=None) -> None:
+    """The current stream waits for every wgrad forked so far (no-op outside `deferred_wgrad`)."""
+    if not _deferred["on"]:
+        return
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    with torch.cuda.device(dev):
+        check(_lib.load().quan_bwd_side_stream_join(torch.cuda.current_stream(dev).cuda_stream), "quan_bwd_side_stream_join")
+
+
+def _keep_for_side(device: torch.device, *tensors) -> None:
+    """A forked wgrad may still read / write these when the caller drops them: the allocator must not hand their memory out before the
+    side stream has passed this point."""
+    if not _deferred["on"]:
+        return
+    side = _deferred["side"].get(device.index if device.index is not None else torch.cuda.current_device())
+    if side is None:
+        return
+    for t in tensors:
+        if t is not None:
+            t.record_stream(side)
 
 
 # ---- pack plan (include/quan_sm100.h): every packed weight of a step rebuilt by ONE launch ------------------------------------------------
