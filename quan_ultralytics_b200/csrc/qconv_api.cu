@@ -229,7 +229,8 @@ static int qconv2d_bwd_impl(const void* dy, const void* x, const float* const w[
   std::unique_lock<std::mutex> ds_lock(g_deferred_mu);
   DeferredSide& ds = deferred_side();
   const bool dw_narrow = m_dw == TC_DENSE || raw_dy(a_dw);          // the wgrad reads dY itself (no G pre-pass on the main stream)
-  if (env_conc && dw != nullptr && dw_narrow && !premixed && ds.side != nullptr &&
+  // ... or G handed in by the caller (premixed: a tensor of its own, not this call's workspace)
+  if (env_conc && dw != nullptr && (premixed ? a_dw == QUAN_ALGO_TCGEN05 : dw_narrow) && ds.side != nullptr &&
       (a_dw != QUAN_ALGO_TCGEN05 || ds.ws_bytes >= qconv_tc_workspace_bytes(*d, dtype, layout, PASS_WGRAD))) {
     // deferred: fork only (the caller joins once, before anything reads the weight gradients); partials live in the lender's workspace
     QUAN_CUDA(cudaEventRecord(ds.fork, st));
