@@ -251,6 +251,10 @@ typedef struct quan_cat_src {
   int64_t row_bytes;
 } quan_cat_src;
 int quan_rows_cat(const quan_cat_src* srcs, int32_t nsrc, void* dst, int64_t dst_ld_bytes, int64_t nrows, void* stream);
+/* The same geometry backwards (the gradient of the concatenation, `CatBackward` at those call sites): part i RECEIVES its row_bytes
+ * columns of every row of the wide tensor `src` (rows src_ld_bytes apart) — dense gradient slices in one launch instead of strided
+ * views that every consumer gathers (and adds through the generic strided kernel) for itself.  parts[i].ptr is written. */
+int quan_rows_split(const quan_cat_src* parts, int32_t nparts, const void* src, int64_t src_ld_bytes, int64_t nrows, void* stream);
 
 /* Weight-gradient chains off the critical path.  The backward of a narrow layer already runs its wgrad next to its dgrad (fork / join
  * on a library-owned stream inside quan_qconv2d_bwd / quan_conv_block_bwd).  With a LENT stream the join is deferred: after

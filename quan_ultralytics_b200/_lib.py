@@ -79,6 +79,7 @@ PROTOTYPES = {
     "quan_pack_plan_run": (_int, [_vp]),
     "quan_pack_plan_release": (_int, []),
     "quan_rows_cat": (_int, [_vp, _i32, _vp, C.c_int64, C.c_int64, _vp]),
+    "quan_rows_split": (_int, [_vp, _i32, _vp, C.c_int64, C.c_int64, _vp]),
     "quan_rows_gather": (_int, [_vp, _vp, C.c_int64, _i32, C.c_int64, _vp]),
     "quan_qer_workspace_bytes": (_sz, [C.c_int64, _i32, _i32, _int]),
     "quan_qer_fwd": (_int, [_vp, _vp, _vp, _vp, C.c_int64, _i32, _i32, C.c_int64, _i32, _int, _vp]),

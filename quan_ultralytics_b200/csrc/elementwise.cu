@@ -381,7 +381,9 @@ struct CatArgs {
   int vend[QUAN_CAT_MAX];      // running vector count per destination row: source s owns vectors [vend[s-1], vend[s])
   int nsrc;
 };
-template <int VB>
+// SPLIT = false: sources -> destination rows (concatenation); SPLIT = true: the same geometry backwards — every part receives its
+// columns of the wide tensor's rows (the dense gradient slices of a concatenation's backward, one launch)
+template <int VB, bool SPLIT = false>
 __global__ void __launch_bounds__(256) rows_cat_kernel(const CatArgs a, uint8_t* __restrict__ dst, int64_t dst_ld, int64_t nrows) {
   pdl_prologue();
   const int vpr = a.vend[a.nsrc - 1];
@@ -393,8 +395,10 @@ __global__ void __launch_bounds__(256) rows_cat_kernel(const CatArgs a, uint8_t*
 #pragma unroll
     for (int k = 0; k < QUAN_CAT_MAX - 1; ++k) s += (k < a.nsrc - 1 && v >= a.vend[k]) ? 1 : 0;
     const int v0 = s == 0 ? 0 : a.vend[s - 1];
-    const uint8_t* sp = a.src[s] + r * a.ld[s] + (int64_t)(v - v0) * VB;
-    uint8_t* dp = dst + r * dst_ld + (int64_t)v * VB;
+    const uint8_t* part = a.src[s] + r * a.ld[s] + (int64_t)(v - v0) * VB;
+    uint8_t* wide = dst + r * dst_ld + (int64_t)v * VB;
+    const uint8_t* sp = SPLIT ? wide : part;
+    uint8_t* dp = SPLIT ? const_cast<uint8_t*>(part) : wide;
     if constexpr (VB == 16) *reinterpret_cast<uint4*>(dp) = *reinterpret_cast<const uint4*>(sp);
     else if constexpr (VB == 8) *reinterpret_cast<uint2*>(dp) = *reinterpret_cast<const uint2*>(sp);
     else *reinterpret_cast<uint32_t*>(dp) = *reinterpret_cast<const uint32_t*>(sp);
@@ -402,7 +406,16 @@ __global__ void __launch_bounds__(256) rows_cat_kernel(const CatArgs a, uint8_t*
 }
 }  // namespace quan
 
+static int rows_cat_impl(const quan_cat_src* srcs, int32_t nsrc, void* dst, int64_t dst_ld_bytes, int64_t nrows, void* stream, bool split);
+
 extern "C" int quan_rows_cat(const quan_cat_src* srcs, int32_t nsrc, void* dst, int64_t dst_ld_bytes, int64_t nrows, void* stream) {
+  return rows_cat_impl(srcs, nsrc, dst, dst_ld_bytes, nrows, stream, false);
+}
+extern "C" int quan_rows_split(const quan_cat_src* parts, int32_t nparts, const void* src, int64_t src_ld_bytes, int64_t nrows, void* stream) {
+  return rows_cat_impl(parts, nparts, const_cast<void*>(src), src_ld_bytes, nrows, stream, true);
+}
+
+static int rows_cat_impl(const quan_cat_src* srcs, int32_t nsrc, void* dst, int64_t dst_ld_bytes, int64_t nrows, void* stream, bool split) {
   using namespace quan;
   QUAN_REQUIRE(srcs != nullptr && dst != nullptr && nsrc >= 1 && nsrc <= QUAN_CAT_MAX && nrows > 0, QUAN_E_ARG, "rows_cat: bad argument (1..%d sources)",
                QUAN_CAT_MAX);
@@ -428,9 +441,15 @@ extern "C" int quan_rows_cat(const quan_cat_src* srcs, int32_t nsrc, void* dst, 
   timing_work("rows_cat", "", 2.0 * nrows * total, 0.0);
   const int grid = grid_for(nrows * vend, 256, 8);
   QUAN_TIMED(st);
-  if (vb == 16) QUAN_LAUNCH((rows_cat_kernel<16>), grid, 256, 0, st, a, (uint8_t*)dst, dst_ld_bytes, nrows);
-  else if (vb == 8) QUAN_LAUNCH((rows_cat_kernel<8>), grid, 256, 0, st, a, (uint8_t*)dst, dst_ld_bytes, nrows);
-  else QUAN_LAUNCH((rows_cat_kernel<4>), grid, 256, 0, st, a, (uint8_t*)dst, dst_ld_bytes, nrows);
-  QUAN_CHECK_LAUNCH("rows_cat");
+  if (split) {
+    if (vb == 16) QUAN_LAUNCH((rows_cat_kernel<16, true>), grid, 256, 0, st, a, (uint8_t*)dst, dst_ld_bytes, nrows);
+    else if (vb == 8) QUAN_LAUNCH((rows_cat_kernel<8, true>), grid, 256, 0, st, a, (uint8_t*)dst, dst_ld_bytes, nrows);
+    else QUAN_LAUNCH((rows_cat_kernel<4, true>), grid, 256, 0, st, a, (uint8_t*)dst, dst_ld_bytes, nrows);
+  } else {
+    if (vb == 16) QUAN_LAUNCH((rows_cat_kernel<16>), grid, 256, 0, st, a, (uint8_t*)dst, dst_ld_bytes, nrows);
+    else if (vb == 8) QUAN_LAUNCH((rows_cat_kernel<8>), grid, 256, 0, st, a, (uint8_t*)dst, dst_ld_bytes, nrows);
+    else QUAN_LAUNCH((rows_cat_kernel<4>), grid, 256, 0, st, a, (uint8_t*)dst, dst_ld_bytes, nrows);
+  }
+  QUAN_CHECK_LAUNCH(split ? "rows_split" : "rows_cat");
   return QUAN_OK;
 }

@@ -319,8 +319,9 @@ def qer_cat(xa, wa, ba, xb, wb, bb) -> torch.Tensor:
 
 
 class _QCat(torch.autograd.Function):
-    """`torch.cat(xs, 1)` of BHWQC tensors / channel chunks (ops.qcat); backward hands every input its channel slice of the gradient as a
-    view, exactly what torch's CatBackward does."""
+    """`torch.cat(xs, 1)` of BHWQC tensors / channel chunks (ops.qcat); backward hands every input its channel slice of the gradient — as dense
+    tensors written by one launch of quan_rows_split (torch's CatBackward hands out strided views, which every consumer then gathers or
+    adds through the generic strided kernel); views when the gradient is stored some other way."""
 
     @staticmethod
     def forward(ctx, *xs):
@@ -329,6 +330,11 @@ class _QCat(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy):
+        import os
+        if os.environ.get("QUAN_CAT_SPLIT", "1") != "0":
+            parts = ops.qsplit(dy, ctx.widths)         # dense slices, one launch: no gather / strided add downstream
+            if parts is not None:
+                return tuple(p if ctx.needs_input_grad[i] else None for i, p in enumerate(parts))
         outs, off = [], 0
         for i, c in enumerate(ctx.widths):
             outs.append(dy.narrow(1, off, c) if ctx.needs_input_grad[i] else None)

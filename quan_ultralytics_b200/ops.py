@@ -174,6 +174,20 @@ def qcat(tensors) -> torch.Tensor:
     return out
 
 
+def qsplit(dy: torch.Tensor, widths) -> list:
+    """The gradient of ops.qcat as DENSE BHWQC slices in one launch (quan_rows_split): dy [B, sum(widths), H, W, 4] in pixel-component
+    rows (dense, or itself a channel chunk) -> one dense tensor per width.  None when dy is stored some other way."""
+    src = _row_source(dy) if (dy.is_cuda and dy.dim() == 5 and dy.dtype in (torch.float32, torch.bfloat16)) else None
+    esz = dy.element_size()
+    if src is None or src[0] % 4 or src[1] % 4 or any((c * esz) % 4 for c in widths) or len(widths) > _lib.CAT_MAX:
+        return None
+    B, _, H, W, _ = dy.shape
+    outs = [empty_q((B, c, H, W, 4), dy.dtype, dy.device, LAYOUT_BHWQC) for c in widths]
+    arr = (_lib.CatSrc * len(outs))(*[_lib.CatSrc(o.data_ptr(), c * esz, c * esz) for o, c in zip(outs, widths)])
+    check(_lib.load().quan_rows_split(C.cast(arr, C.c_void_p), len(outs), src[0], src[1], B * H * W * 4, _stream(dy)), "quan_rows_split")
+    return outs
+
+
 # ---- workspaces ------------------------------------------------------------------------------------------------
 _ws_cache = {}
 _iqbn_ws_cache = {}
