@@ -186,6 +186,15 @@ def _obb_forward(self, x):
     return x, angle
 
 
+def _c2f_forward(self, x):
+    """C2f.forward (block.py:348-352; C3k2 inherits it) with the chunk's backward and the concatenation on the library's row-copy
+    kernels: same tensors, same order of modules."""
+    from . import functional as QF
+    y = list(QF.chunk2(self.cv1(x)))
+    y.extend(m(y[-1]) for m in self.m)
+    return self.cv2(QF.cat(y, 1))
+
+
 def _make_obb(ref_cls):
     """Subclass of the REFERENCE's OBB head: constructor, parameters and every non-training path are the reference's."""
     if getattr(ref_cls, "_quan_streams", False):
@@ -220,6 +229,9 @@ def install(ultralytics: bool = True, classification: bool = True) -> dict:
                 _swap(mod, "OBB", _make_obb(ref_cls))
                 names.append("OBB")
             done[modname] = names
+            if modname == "ultralytics.nn.modules.block" and hasattr(mod, "C2f") and os.environ.get("QUAN_FAST_CAT", "1") != "0":
+                _swap(mod.C2f, "forward", _c2f_forward)         # a method of the reference's class, restored by uninstall()
+                names.append("C2f.forward")
             if modname in ("ultralytics.nn.modules.conv", "ultralytics.nn.modules.block") and getattr(mod, "torch", None) is torch \
                     and os.environ.get("QUAN_FAST_CAT", "1") != "0":
                 _originals.append((mod, "torch", torch))

@@ -162,14 +162,19 @@ def test_classification_train_step_matches_reference_fp32(fp32_exact, name, B, s
     assert worst[0] <= tol, worst
 
 
-def test_obb_head_branch_streams_match_serial_head(fp32_exact, monkeypatch):
-    """install.OBB: the nine head towers on nine streams give the loss and every gradient of the reference's serial OBB.forward
-    (head.py:137-147, :338-350) — same kernels, only their stream placement differs.  The yardstick is the serial head's own
-    run-to-run spread (the conv epilogue's statistics are fp32 shared-memory atomics: the last bits depend on arrival order)."""
-    from quan_ultralytics_b200 import workloads
+@pytest.mark.parametrize("engine", ["direct", "auto"])
+def test_obb_head_branch_streams_match_serial_head(fp32_exact, monkeypatch, engine):
+    """install.OBB: the nine head towers on nine streams (box + class extractions written into the concatenated tensor) give the loss
+    and the gradients of the reference's serial OBB.forward (head.py:137-147, :338-350) — same kernels, only their stream placement
+    differs.  `direct`: exact-fp32 CUDA-core engine, every parameter gradient to 1e-4.  `auto`: the tf32 tensor-core engine, whose
+    fp32 statistics atomics make max-pool arg-maxes flip from run to run even serially — there the whole-gradient relative L2 error is
+    held against the serial head's own run-to-run spread."""
+    from quan_ultralytics_b200 import ops, workloads
     torch.manual_seed(0)
     model = workloads.build_yolo_obb("n", 15, "cuda", swapped=True)
     assert getattr(type(model.model[-1]), "_quan_streams", False), "install() did not swap the OBB head"
+    if engine == "direct":
+        _set_algo(model, ops.ALGO_DIRECT)
     batch = workloads.synthetic_obb_batch(2, 256, "cuda", boxes_per_image=12, seed=5)
     monkeypatch.setenv("QUAN_HEAD_STREAMS", "0")
     l0, i0, g0 = _yolo_step(model, batch)
@@ -177,9 +182,12 @@ def test_obb_head_branch_streams_match_serial_head(fp32_exact, monkeypatch):
     monkeypatch.setenv("QUAN_HEAD_STREAMS", "1")
     l1, i1, g1 = _yolo_step(model, batch)
     noise_l = abs(l0 - l0b) / abs(l0)
-    noise_g, _ = _worst(g0b, g0)
+    (noise_g, _), (dev_g, _) = _global(g0b, g0), _global(g1, g0)
     worst, name = _worst(g1, g0)
-    print(f"[OBB head streams] loss {l1:.6f} vs serial {l0:.6f} (serial run-to-run {noise_l:.1e}); worst gradient deviation {worst:.2e} "
-          f"({name}; serial run-to-run {noise_g:.1e})")
-    assert abs(l0 - l1) / abs(l0) <= max(1e-4, 4 * noise_l)      # tf32 engine + order-dependent fp32 statistics atomics: ~1e-5 observed
-    assert worst <= max(1e-3, 4 * noise_g), (worst, name)
+    print(f"[OBB head streams / {engine}] loss {l1:.6f} vs serial {l0:.6f} (serial run-to-run {noise_l:.1e}); whole-gradient rel L2 {dev_g:.2e} "
+          f"(serial run-to-run {noise_g:.1e}); worst tensor {worst:.2e} ({name})")
+    assert abs(l0 - l1) / abs(l0) <= max(1e-4, 4 * noise_l)
+    if engine == "direct":
+        assert worst <= 1e-4, (worst, name)
+    else:
+        assert dev_g <= max(2e-2, 4 * noise_g), (dev_g, noise_g)
