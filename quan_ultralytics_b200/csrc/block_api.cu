@@ -15,13 +15,16 @@ int quan_conv_block_fwd(const void* x, const float* const w[4], const float* gam
   QUAN_REQUIRE(d != nullptr && y != nullptr && out != nullptr && stats != nullptr, QUAN_E_ARG, "conv_block_fwd: null pointer");
   QUAN_REQUIRE(iqbn_ws != nullptr && iqbn_ws_bytes >= quan_iqbn_workspace_bytes(d->Co), QUAN_E_WORKSPACE,
                "conv_block_fwd: IQBN workspace needs %zu bytes", quan_iqbn_workspace_bytes(d->Co));
-  int nparts = 0;
+  int nparts = -1;       // opt in: the narrow-layer epilogue may ADD its statistics to the workspace's accumulators (answers nparts < 0)
   int rc = epilogue_stats
                ? quan_qconv2d_fwd_stats(x, w, nullptr, y, d, dtype, layout, mix, algo, conv_ws, conv_ws_bytes, iqbn_ws,
                                         iqbn_ws_bytes, &nparts, stream)
                : quan_qconv2d_fwd(x, w, nullptr, y, d, dtype, layout, mix, algo, conv_ws, conv_ws_bytes, stream);
   if (rc) return rc;
   const int Ho = conv_out(d->H, d->kH, d->sH, d->pH, d->dH), Wo = conv_out(d->W, d->kW, d->sW, d->pW, d->dW);
+  if (nparts < 0)        // raw sums are in L2: statistics + table + running buffers + normalisation + act in one launch
+    return iqbn_apply_fwd_from_acc(y, out, d->B, d->Co, Ho, Wo, dtype, layout, iqbn_ws, (double)d->B * Ho * Wo, gamma, beta, eps, momentum,
+                                   running_mean, running_var, stats, act, stream);
   if (nparts > 0)
     rc = quan_iqbn_finalize_partials(iqbn_ws, nparts, (double)d->B * Ho * Wo, d->Co, gamma, beta, eps, momentum, running_mean,
                                      running_var, stats, stream);

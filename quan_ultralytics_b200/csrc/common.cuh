@@ -9,6 +9,7 @@
 #include "../../include/quan_sm100.h"
 
 #define QUAN_NUM_SMS 148  // B200: 2 dies x 74 SMs; grids are sized in multiples of this.
+#define QUAN_IQBN_MAX_PARTS (4 * QUAN_NUM_SMS)   // slots of the IQBN partials buffer; the [8C] fp64 accumulators follow them
 #define QUAN_STR_(x) #x
 #define QUAN_STR(x) QUAN_STR_(x)
 

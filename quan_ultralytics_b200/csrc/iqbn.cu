@@ -23,7 +23,7 @@ namespace quan {
 // kernels and folded by a second, parallel finalize kernel.  Deterministic, nothing to zero.  (The first versions used
 // fp64 atomics + a last-block tail: the L2 retires only ~18 G fp64 atomics/s chip-wide, so 1.2 M atomics — 592 blocks x
 // 2048 accumulators — cost 69 us on top of a 24 us stream; measured in profiles/r01_iqbn_tune2.log.)
-constexpr int IQBN_MAX_PARTS = 4 * QUAN_NUM_SMS;
+constexpr int IQBN_MAX_PARTS = QUAN_IQBN_MAX_PARTS;
 struct IqbnWs {
   double* part;          // [IQBN_MAX_PARTS][2][4C] per-block partial sums (plain stores, folded by iqbn_fold_kernel)
   double* acc;           // [2][4C] accumulators of the single-launch reduction for small tensors: ZERO between launches
@@ -701,6 +701,16 @@ struct ApplyArgs {
   float* dbeta;
   int C;
   const float* coefT;         // bwd train, BHWQC: k1T | k2T | k3T (index q*C+c), made by the bwd-reduce tail / bwd_coef
+  // forward, training, statistics still RAW: [8C] fp64 sums in L2 left by the conv epilogue (fsums != NULL).  Every thread finishes
+  // the statistics of its own columns, block (0,0) writes the stats table / running statistics, the last block to have read (ticket)
+  // re-zeroes the accumulators.  No fold launch between the conv and this kernel.
+  double* fsums;
+  unsigned* ticket;
+  double fcount;
+  float momentum;
+  float* stats_w;
+  float* running_mean_w;
+  float* running_var_w;
 };
 
 __device__ __forceinline__ void coeff_fwd(const ApplyArgs& a, int idx, float& scale, float& shift) {
@@ -758,7 +768,45 @@ __global__ void __launch_bounds__(256, BWD ? 3 : 4) iqbn_apply_b(const T* __rest
   const int cv = blockIdx.y * g.cvpg + cvl;
   const int64_t coloff = (int64_t)cv * V;
   float scale[V], shift[V], k1[V], k2[V], k3[V];
-  if (a.stats != nullptr && (!BWD || a.coefT != nullptr)) {
+  if (!BWD && a.fsums != nullptr) {
+    // one thread per column finishes that column's statistics (fp64 division + square root: ~100 instructions — done once per block,
+    // not once per thread and column: the first version, V columns in every thread, was slower than the fold launch it replaced),
+    // the block's threads then pick their V columns up from shared memory.  4C <= 512 (narrow layers only).
+    __shared__ float s_scale[512], s_shift[512];
+    for (int col = threadIdx.x; col < 4 * g.C; col += blockDim.x) {
+      const int q = col / g.C, c = col - q * g.C, idx = c * 4 + q;
+      const double s0 = __ldcg(a.fsums + idx), s1 = __ldcg(a.fsums + 4 * g.C + idx);
+      const double mean = s0 / a.fcount;
+      double var = s1 / a.fcount - mean * mean;
+      if (var < 0.0) var = 0.0;
+      var += 1e-8;                                       // conv.py:557
+      const float rstd = (float)(1.0 / sqrt(var + (double)a.eps));
+      const float sc = a.gamma[idx] * rstd;
+      s_scale[col] = sc;
+      s_shift[col] = a.beta[idx] - (float)mean * sc;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      scale[i] = s_scale[coloff + i];
+      shift[i] = s_shift[coloff + i];
+    }
+    if (blockIdx.x == 0 && blockIdx.y == 0) {            // the table the backward reads + the running statistics (conv.py:561-562)
+      TailArgs t = {};
+      t.mode = TAIL_FWD_STATS; t.C = g.C; t.count = a.fcount; t.eps = a.eps; t.momentum = a.momentum;
+      t.running_mean = a.running_mean_w; t.running_var = a.running_var_w; t.stats = a.stats_w; t.gamma = a.gamma; t.beta = a.beta;
+      for (int i = threadIdx.x; i < 4 * g.C; i += blockDim.x) write_fwd_stats(t, i, __ldcg(a.fsums + i), __ldcg(a.fsums + 4 * g.C + i));
+    }
+    __syncthreads();                                     // every read of the accumulators by this block is done
+    if (threadIdx.x == 0) {
+      const unsigned nblocks = gridDim.x * gridDim.y;
+      if (atomicAdd(a.ticket, 1u) == nblocks - 1) {      // all blocks have read: leave accumulators and ticket zero for the next layer
+        __threadfence();
+        for (int i = 0; i < 8 * g.C; ++i) a.fsums[i] = 0.0;
+        *a.ticket = 0u;
+      }
+    }
+  } else if (a.stats != nullptr && (!BWD || a.coefT != nullptr)) {
     // training path: coefficient tables in column order (stats[12C..20C), coefT) — a few 16-byte loads per thread
     load_coef<float, V>(a.stats + 12 * g.C + coloff, scale);
     load_coef<float, V>(a.stats + 16 * g.C + coloff, shift);
@@ -1658,6 +1706,28 @@ int quan_iqbn_apply_fwd(const void* x, void* y, int32_t B, int32_t C, int32_t H,
   announce_iqbn_work(B, C, H, W, dtype, 2);
   return apply_entry(false, x, nullptr, y, B, C, H, W, dtype, layout, a, act, nullptr, stream);
 }
+
+}  // extern "C"
+
+namespace quan {
+// y = act(IQBN(x)) with the batch statistics still as raw sums in the workspace's accumulators (left there by the conv epilogue,
+// qconv_tc.cu stat_acc): statistics, table, running buffers and the normalisation in ONE launch (block_api.cu)
+int iqbn_apply_fwd_from_acc(const void* x, void* y, int B, int C, int H, int W, int dtype, int layout, void* iqbn_ws, double count,
+                            const float* gamma, const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                            float* stats, int act, void* stream) {
+  QUAN_REQUIRE(iqbn_ws != nullptr && stats != nullptr && layout == QUAN_LAYOUT_BHWQC && C > 1 && 4 * C <= 512, QUAN_E_ARG,
+               "iqbn_apply_fwd_from_acc: bad argument");
+  const IqbnWs ws = carve_ws(iqbn_ws, C);
+  ApplyArgs a = {};
+  a.gamma = gamma; a.beta = beta; a.C = C; a.eps = eps;
+  a.fsums = ws.acc; a.ticket = ws.counter + 1; a.fcount = count; a.momentum = momentum;
+  a.stats_w = stats; a.running_mean_w = running_mean; a.running_var_w = running_var;
+  announce_iqbn_work(B, C, H, W, dtype, 2);
+  return apply_entry(false, x, nullptr, y, B, C, H, W, dtype, layout, a, act, nullptr, stream);
+}
+}  // namespace quan
+
+extern "C" {
 
 int quan_iqbn_eval_fwd(const void* x, void* y, int32_t B, int32_t C, int32_t H, int32_t W, int dtype, int layout,
                        const float* gamma, const float* beta, const float* running_mean, const float* running_var,

@@ -132,7 +132,7 @@ static void announce_conv_work(const quan_conv_dims& d, int dtype, int pass) {
 static int qconv2d_fwd_impl(const void* x, const float* const w[4], const float* bias_r, void* y, const quan_conv_dims* d,
                             int dtype, int layout, const float* mix, int algo, void* workspace, size_t ws_bytes,
                             void* stream, double* stat_part, int* stat_nparts) {
-  if (stat_nparts != nullptr) *stat_nparts = 0;
+  if (stat_nparts != nullptr) *stat_nparts = *stat_nparts < 0 ? -1 : 0;      // < 0 on entry: the caller accepts accumulated statistics
   int rc = validate(d, dtype, layout, mix);
   if (rc) return rc;
   QUAN_REQUIRE(x != nullptr && y != nullptr && w != nullptr && w[0] && w[1] && w[2] && w[3], QUAN_E_ARG,
@@ -141,6 +141,7 @@ static int qconv2d_fwd_impl(const void* x, const float* const w[4], const float*
   announce_conv_work(*d, dtype, PASS_FWD);
   const int a = resolve_algo(*d, dtype, layout, PASS_FWD, algo);
   QUAN_REQUIRE(a > 0, QUAN_E_UNSUPPORTED, "qconv2d_fwd: requested engine does not serve this shape/layout");
+  if (stat_nparts != nullptr && a != QUAN_ALGO_TCGEN05) *stat_nparts = 0;     // only the tensor-core epilogue emits statistics
   if (a == QUAN_ALGO_DEPTHWISE) return qconv_dw_fwd(x, w, bias_r, y, *d, dtype, mix, st);
   if (a == QUAN_ALGO_SMALLC) return qconv_small_fwd(x, w, bias_r, y, *d, dtype, mix, st);
   if (a == QUAN_ALGO_TCGEN05) {

@@ -54,4 +54,9 @@ int qconv_tc_dgrad(const void* g, const float* const w[4], void* dx, const quan_
 int qconv_tc_wgrad(const void* g, const void* x, float* const dw[4], const quan_conv_dims& d, int dtype, int mode,
                    const float* mix, void* ws, size_t ws_bytes, cudaStream_t st);
 
+// iqbn.cu: IQBN apply from the raw sums the conv epilogue accumulated (see ApplyArgs.fsums)
+int iqbn_apply_fwd_from_acc(const void* x, void* y, int B, int C, int H, int W, int dtype, int layout, void* iqbn_ws, double count,
+                            const float* gamma, const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                            float* stats, int act, void* stream);
+
 }  // namespace quan

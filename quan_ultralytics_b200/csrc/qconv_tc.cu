@@ -207,6 +207,7 @@ struct TcConvParams {
   uint32_t sbo_bytes, layout_type, idesc, tmem_cols;
   const float* bias;                   // NQ = 4: [Cout], joins S_r before the mix; NQ = 1: [Cout] added to the output
   double* stat_part;                   // or NULL: per-CTA partial IQBN sums of the OUTPUT, [grid][2][C_q*4] (index c*4+q)
+  double* stat_acc;                    // or NULL: instead of a slot, every CTA ADDS its sums to these [2][C_q*4] fp64 accumulators
   const float* post_scale;             // or NULL: eval-mode IQBN folded into the epilogue, y = act(y * scale + shift); tables
   const float* post_shift;             //   [4][C_o] in (component, channel) order (stats[12C..20C) of quan_iqbn_eval_stats)
   int post_act;
@@ -738,7 +739,8 @@ qconv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       for (int e = threadIdx.x - 64; e < 2 * n4; e += 32 * EPI_WARPS * epi_groups(NQ)) {
         const int which = e / n4, r = e - which * n4;
         const int pc = r / p.stat_cq, co = r - pc * p.stat_cq;
-        slot[which * n4 + co * 4 + pc] = (double)sacc[e];
+        if (p.stat_acc != nullptr) atomicAdd(p.stat_acc + which * n4 + co * 4 + pc, (double)sacc[e]);   // <= 148 x 8C adds per launch
+        else slot[which * n4 + co * 4 + pc] = (double)sacc[e];
       }
     }
     ptx::tc_fence_before();
@@ -1381,6 +1383,14 @@ static int launch_igemm(const void* in, const void* wpacked, const float* bias, 
   // the dense form's statistics run in registers (RSTAT instantiation) when a thread keeps its columns for the whole kernel
   static const int env_rstat = [] { const char* e = getenv("QUAN_TC_RSTAT"); return e ? atoi(e) : 1; }();
   const bool rstat = env_rstat && NQ == 1 && p.stat_part != nullptr && p.ntiles_n == 1 && p.BN <= 64;
+  // the caller opted in (*stat_nparts < 0 on entry) and the layer is narrow: accumulate in L2 instead of writing slots — the IQBN apply
+  // kernel then finishes the statistics itself (iqbn_apply_fwd_from_acc) and the fold launch disappears.  Measured on B200 (QUAN-YOLO11n
+  // step, same box, alternating): 54 fewer launches, 11.215 vs 11.227 ms/step — the fold's time moves into the igemm tail (atomics) and
+  // the apply prologue (fp64 finish per block); neutral, and the summation order is no longer fixed, so it is OFF unless
+  // QUAN_TC_STAT_ACC=1.
+  static const int env_acc = [] { const char* e = getenv("QUAN_TC_STAT_ACC"); return e ? atoi(e) : 0; }();
+  const bool accumulate = env_acc && rstat && stat_nparts != nullptr && *stat_nparts < 0;
+  p.stat_acc = accumulate ? stat_part + (size_t)QUAN_IQBN_MAX_PARTS * 8 * p.stat_cq : nullptr;
 #define QUAN_IGEMM_CASE(CGV, KS)                                                                                           \
   do {                                                                                                                     \
     if constexpr (NQ == 1) {                                                                                               \
@@ -1397,7 +1407,7 @@ static int launch_igemm(const void* in, const void* wpacked, const float* bias, 
     else if (ksteps == 2) { QUAN_IGEMM_CASE(1, 2); }
     else { QUAN_IGEMM_CASE(1, 1); }
   }
-  if (stat_nparts != nullptr) *stat_nparts = (rc == QUAN_OK && p.stat_part != nullptr) ? ctas : 0;
+  if (stat_nparts != nullptr) *stat_nparts = (rc == QUAN_OK && p.stat_part != nullptr) ? (p.stat_acc != nullptr ? -ctas : ctas) : 0;
   return rc;
 #undef QUAN_IGEMM_CASE
 }
