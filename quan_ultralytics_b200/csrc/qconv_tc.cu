@@ -212,6 +212,10 @@ struct TcConvParams {
   const float* post_shift;             //   [4][C_o] in (component, channel) order (stats[12C..20C) of quan_iqbn_eval_stats)
   int post_act;
   int stat_cq;                         // quaternion output channels C_o (NQ = 4: Cout; NQ = 1: Cout / 4)
+  // TMA-store epilogue (output stride 1): every epilogue warp stages the 16 columns x 32 pixel rows it holds in its own two
+  // shared-memory slots (swizzled like the tensor map, conflict-free 16-byte writes) and one lane sends the slot with
+  // cp.async.bulk.tensor; the box is the warp's 32 rows of the tile = ts_wb x ts_hb x ts_bb pixels, clipped at the tensor edge.
+  int tstore;                          // 0: per-lane stores; else slots per warp (2 or 4)
   Mix16 mix;
 };
 
@@ -282,8 +286,8 @@ constexpr int ig_threads(int nq) { return 64 + 32 * EPI_WARPS * epi_groups(nq); 
 // thread's critical path.
 template <typename T, bool MIX, int CG, int KSTEPS, int NQ, bool RSTAT = false>
 __global__ void __launch_bounds__(ig_threads(NQ), 1)
-qconv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, T* __restrict__ y,
-                   const TcConvParams p) {
+qconv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                   const __grid_constant__ CUtensorMap map_y, T* __restrict__ y, const TcConvParams p) {
   pdl_prologue();
   constexpr int NACC = NQ == 4 ? 4 : 2;   // TMEM accumulators of BN columns
   constexpr int NTB = NACC / NQ;          // units that can be in flight in TMEM (tile_full barriers)
@@ -291,8 +295,11 @@ qconv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   // 1024-byte alignment is required by the 128B swizzle atoms
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t a_stage_bytes = p.a_sub_bytes * p.sub, b_stage_bytes = p.b_sub_bytes * p.sub;
-  uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + (p.halo ? (size_t)p.a_stages * p.a_halo_bytes : (size_t)p.stages * a_stage_bytes);
+  constexpr uint32_t TS_RB = 16 * sizeof(T);           // bytes of one staged row (16 columns)
+  constexpr uint32_t TS_SLOT = 32 * TS_RB;             // one warp's box: 32 pixel rows
+  uint8_t* ts_base = smem;                             // [EPI_WARPS][2] slots when p.tstore
+  uint8_t* smem_a = smem + (size_t)EPI_WARPS * epi_groups(NQ) * p.tstore * TS_SLOT;
+  uint8_t* smem_b = smem_a + (p.halo ? (size_t)p.a_stages * p.a_halo_bytes : (size_t)p.stages * a_stage_bytes);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + (size_t)p.stages * b_stage_bytes);
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* a_full = empty_bar + p.stages;        // [4]  halo mode: the A ring has its own barriers (B ring uses full/empty_bar)
@@ -312,6 +319,7 @@ qconv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&map_a);
     ptx::prefetch_tensormap(&map_b);
+    if (p.tstore) ptx::prefetch_tensormap(&map_y);
     for (int s = 0; s < p.stages; ++s) {
       ptx::mbar_init(full_bar + s, 1);
       ptx::mbar_init(empty_bar + s, 1);
@@ -564,6 +572,41 @@ qconv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     float rs0[RSTAT ? 16 : 1], rq0[RSTAT ? 16 : 1], rs1[RSTAT ? 16 : 1], rq1[RSTAT ? 16 : 1];
 #pragma unroll
     for (int j = 0; j < (RSTAT ? 16 : 1); ++j) rs0[j] = rq0[j] = rs1[j] = rq1[j] = 0.f;
+    // TMA-store epilogue (p.tstore): this warp's 32 accumulator rows are a box of the output tensor
+    uint8_t* ts_slots = ts_base + (size_t)(warp - 2) * p.tstore * TS_SLOT;
+    uint32_t ts_n = 0;                                 // stores issued by this warp; slot = ts_n % p.tstore
+    constexpr uint32_t TS_NV = TS_RB / 16;             // 16-byte pieces of a staged row
+    const uint32_t ts_row = (uint32_t)lane * TS_RB;
+    const uint32_t ts_xor = (ts_row >> 7) & (TS_NV - 1);   // the tensor map's 32B / 64B swizzle: piece ^= address bits 7..
+    const int ts_m0 = quarter * 32;
+    const int ts_wt0 = ts_m0 % p.Wt, ts_ht0 = (ts_m0 / p.Wt) % p.Ht, ts_bt0 = ts_m0 / (p.Wt * p.Ht);
+    auto tma_out = [&](const float (&o)[16], const int col, const int pc, const int w0, const int h0, const int b0) {
+      if (w0 >= p.Wo || h0 >= p.Ho || b0 >= p.B) return;   // the whole box lies outside (warp-uniform)
+      uint8_t* slot = ts_slots + (ts_n & (uint32_t)(p.tstore - 1)) * TS_SLOT;
+      if (lane == 0) {                                 // the store that used this slot `tstore` stores ago has left shared memory
+        if (p.tstore == 4) ptx::bulk_wait_read<3>();
+        else ptx::bulk_wait_read<1>();
+      }
+      __syncwarp();
+      const uint32_t row_addr = ptx::smem_u32(slot) + ts_row;
+#pragma unroll
+      for (int v = 0; v < (int)TS_NV; ++v) {
+        Vec<T, VW> t;
+#pragma unroll
+        for (int j = 0; j < VW; ++j) t.v[j] = from_f32<T>(o[v * VW + j]);
+        const uint4 u = *reinterpret_cast<const uint4*>(&t);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_addr + (((uint32_t)v ^ ts_xor) << 4)), "r"(u.x), "r"(u.y),
+                     "r"(u.z), "r"(u.w)
+                     : "memory");
+      }
+      ptx::fence_proxy_async();                        // generic-proxy writes -> visible to the async proxy (TMA)
+      __syncwarp();
+      if (lane == 0) {
+        ptx::tma_store_5d(&map_y, slot, col, pc, w0, h0, b0);
+        ptx::bulk_commit();
+      }
+      ++ts_n;
+    };
     auto release = [&](uint64_t* bar) {                // one arrival per epilogue warp (TMEM reads of this warp are done)
       ptx::tc_fence_before();
       __syncwarp();
@@ -587,6 +630,7 @@ qconv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       const int b = tb * p.Bt + bt;
       const int n0 = nt * p.BN;
       const bool valid = (wo < p.Wo) && (ho < p.Ho) && (b < p.B);
+      const int bw0 = tw * p.Wt + ts_wt0, bh0 = th * p.Ht + ts_ht0, bb0 = tb * p.Bt + ts_bt0;   // origin of this warp's box (tstore)
       T* yrow = y + ((((int64_t)b * p.Ho + ho) * p.Wo + wo) * NQ) * p.Cout + n0;
       if constexpr (NQ == 4) {
         // dbuf (BN <= 64): the unit's accumulator set alternates, the whole epilogue overlaps the next unit's mainloop
@@ -614,7 +658,7 @@ qconv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 #pragma unroll
               for (int j = 0; j < 16; ++j) st[ci][j] += __ldg(p.bias + n0 + c0 + j);
             }
-            if (valid) {
+            if (valid || p.tstore) {
 #pragma unroll
               for (int pc = 0; pc < 4; ++pc) {
                 float o[16];
@@ -637,13 +681,17 @@ qconv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                     }
                   }
                 }
-                T* dst = yrow + (int64_t)pc * p.Cout + c0;
+                if (p.tstore) {
+                  tma_out(o, n0 + c0, pc, bw0, bh0, bb0);
+                } else {
+                  T* dst = yrow + (int64_t)pc * p.Cout + c0;
 #pragma unroll
-                for (int v = 0; v < 16 / VW; ++v) {
-                  float part[VW];
+                  for (int v = 0; v < 16 / VW; ++v) {
+                    float part[VW];
 #pragma unroll
-                  for (int j = 0; j < VW; ++j) part[j] = o[v * VW + j];
-                  store_vec<T, VW>(dst + v * VW, part);
+                    for (int j = 0; j < VW; ++j) part[j] = o[v * VW + j];
+                    store_vec<T, VW>(dst + v * VW, part);
+                  }
                 }
               }
             }
@@ -694,7 +742,9 @@ qconv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
               acc[j] = p.post_act == QUAN_ACT_SILU ? act_fwd<QUAN_ACT_SILU, sizeof(T) == 2>(z) : z;
             }
           }
-          if (valid) {
+          if (p.tstore) {
+            tma_out(acc, n0 + c0, 0, bw0, bh0, bb0);
+          } else if (valid) {
 #pragma unroll
             for (int v = 0; v < 16 / VW; ++v) {
               float part[VW];
@@ -743,6 +793,7 @@ qconv_igemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         else slot[which * n4 + co * 4 + pc] = (double)sacc[e];
       }
     }
+    if (p.tstore && lane == 0) ptx::bulk_wait_read<0>();   // staged rows must outlive the stores that read them
     ptx::tc_fence_before();
   }
   if constexpr (CG == 2) ptx::cluster_sync_all();   // neither CTA may release TMEM / exit while the pair is still using it
@@ -1203,7 +1254,8 @@ static bool igemm_supported(const IgemmShape& s, int dtype) {
 
 
 template <typename T, bool MIX, int CG, int KSTEPS, int NQ, bool RSTAT = false>
-static int launch_igemm_inst(const CUtensorMap& map_a, const CUtensorMap& map_b, void* out, const TcConvParams& p, size_t smem,
+static int launch_igemm_inst(const CUtensorMap& map_a, const CUtensorMap& map_b, const CUtensorMap& map_y, void* out,
+                             const TcConvParams& p, size_t smem,
                              const char* name, cudaStream_t st, int* ctas) {
   auto kern = qconv_igemm_kernel<T, MIX, CG, KSTEPS, NQ, RSTAT>;
   // persistent grid: one CTA (pair) per SM, as many as can be co-resident (queried once per instantiation)
@@ -1242,7 +1294,7 @@ static int launch_igemm_inst(const CUtensorMap& map_a, const CUtensorMap& map_b,
   *ctas = groups * CG;
   QUAN_TIMED(st);
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  QUAN_CUDA(cudaLaunchKernelEx(&cfg, kern, map_a, map_b, reinterpret_cast<T*>(out), p));
+  QUAN_CUDA(cudaLaunchKernelEx(&cfg, kern, map_a, map_b, map_y, reinterpret_cast<T*>(out), p));
   QUAN_CHECK_LAUNCH(name);
   return QUAN_OK;
 }
@@ -1347,14 +1399,25 @@ static int launch_igemm(const void* in, const void* wpacked, const float* bias, 
   if (p.halo) p.sub = p.tg;                          // halo mode: a B ring slot holds one filter row of taps; A has its own ring
   const size_t a_ring = p.halo ? (size_t)p.a_stages * p.a_halo_bytes : 0;
   const size_t stage_bytes = p.halo ? (size_t)p.b_sub_bytes * p.sub : (size_t)(p.a_sub_bytes + p.b_sub_bytes) * p.sub;
-  const size_t budget = 200 * 1024 - a_ring;
+  // TMA-store epilogue: whenever the output is written with stride 1 (forward of any stride, dgrad of stride-1 layers); the strided
+  // scatter of the parity-class dgrad keeps per-lane stores (its pixel dims would need a rank-7 map).  QUAN_TC_TSTORE=0 disables.
+  static const int env_tstore = [] { const char* e = getenv("QUAN_TC_TSTORE"); return e ? atoi(e) : 1; }();
+  p.tstore = (env_tstore && s.scatH == 1 && s.scatW == 1 && !p.tt.zero_fill && (s.N * esz) % 16 == 0 &&
+              (reinterpret_cast<uintptr_t>(out) & 15) == 0)
+                 ? (env_tstore == 4 || env_tstore == 2 ? env_tstore : 2)
+                 : 0;
+  const size_t ts_bytes = (size_t)EPI_WARPS * epi_groups(NQ) * p.tstore * 32 * 16 * esz;   // 2 slots: 16 KB (bf16) / 32 KB (fp32)
+  const size_t stat_bytes = p.stat_part != nullptr ? (size_t)8 * p.stat_cq * sizeof(float) : 0;
+  size_t budget = 226 * 1024 - 1024 - 512 - stat_bytes - ts_bytes;
+  if (budget > 200 * 1024) budget = 200 * 1024;
+  QUAN_REQUIRE(budget > a_ring, QUAN_E_UNSUPPORTED, "tcgen05 conv: no shared memory left for the pipeline");
+  budget -= a_ring;
   int stages = (int)(budget / stage_bytes);
   if (stages > 8) stages = 8;
   if (const char* e = getenv("QUAN_TC_STAGES")) { int v = atoi(e); if (v >= 1 && v < stages) stages = v; }
   QUAN_REQUIRE(stages >= 2, QUAN_E_UNSUPPORTED, "tcgen05 conv: stage too large");
   p.stages = stages;
-  const size_t smem = 1024 + a_ring + stages * stage_bytes + (2 * stages + 18) * sizeof(uint64_t) + 16 +
-                      (p.stat_part != nullptr ? (size_t)8 * p.stat_cq * sizeof(float) : 0);
+  const size_t smem = 1024 + ts_bytes + a_ring + stages * stage_bytes + (2 * stages + 18) * sizeof(uint64_t) + 16 + stat_bytes;
 
   // A: input activations [B][Hi][Wi][nq][K] -> 5-D map {K, nq, Wi, Hi, B}
   CUtensorMap map_a, map_b;
@@ -1378,6 +1441,20 @@ static int launch_igemm(const void* in, const void* wpacked, const float* bias, 
     int rc = encode_map(&map_b, dtype, 4, wpacked, dims, str, box, est, row_bytes);
     if (rc) return rc;
   }
+  // Y: output [B][Ho][Wo][nq][N] -> 5-D map {N, nq, Wo, Ho, B}; box = 16 columns of one component x a warp's 32 pixel rows
+  CUtensorMap map_y = map_a;
+  if (p.tstore) {
+    const int wb = t.Wt < 32 ? t.Wt : 32;
+    const int hb = t.Ht < 32 / wb ? t.Ht : 32 / wb;
+    const int bb = 32 / (wb * hb);
+    const uint64_t dims[5] = {(uint64_t)s.N, (uint64_t)NQ, (uint64_t)s.Wo, (uint64_t)s.Ho, (uint64_t)s.B};
+    const uint64_t str[4] = {(uint64_t)s.N * esz, (uint64_t)NQ * s.N * esz, (uint64_t)s.Wo * NQ * s.N * esz,
+                             (uint64_t)s.Ho * s.Wo * NQ * s.N * esz};
+    const uint32_t box[5] = {16, 1, (uint32_t)wb, (uint32_t)hb, (uint32_t)bb};
+    const uint32_t est[5] = {1, 1, 1, 1, 1};
+    int rc = encode_map(&map_y, dtype, 5, out, dims, str, box, est, 16 * esz);
+    if (rc) return rc;
+  }
   if (p.tt.zero_fill) QUAN_CUDA(cudaMemsetAsync(out, 0, (size_t)s.B * s.Ho * s.Wo * NQ * s.N * esz, st));
   int ctas = 0, rc = QUAN_OK;
   // the dense form's statistics run in registers (RSTAT instantiation) when a thread keeps its columns for the whole kernel
@@ -1394,9 +1471,9 @@ static int launch_igemm(const void* in, const void* wpacked, const float* bias, 
 #define QUAN_IGEMM_CASE(CGV, KS)                                                                                           \
   do {                                                                                                                     \
     if constexpr (NQ == 1) {                                                                                               \
-      if (rstat) { rc = launch_igemm_inst<T, MIX, CGV, KS, NQ, true>(map_a, map_b, out, p, smem, s.name, st, &ctas); break; } \
+      if (rstat) { rc = launch_igemm_inst<T, MIX, CGV, KS, NQ, true>(map_a, map_b, map_y, out, p, smem, s.name, st, &ctas); break; } \
     }                                                                                                                      \
-    rc = launch_igemm_inst<T, MIX, CGV, KS, NQ, false>(map_a, map_b, out, p, smem, s.name, st, &ctas);                       \
+    rc = launch_igemm_inst<T, MIX, CGV, KS, NQ, false>(map_a, map_b, map_y, out, p, smem, s.name, st, &ctas);                       \
   } while (0)
   if (cg == 2) {
     if (ksteps == 4) { QUAN_IGEMM_CASE(2, 4); }

@@ -363,6 +363,117 @@ __global__ void __launch_bounds__(256) qmaxpool_bwd_rows_kernel(const T* __restr
   }
 }
 
+// Tiled backward: a block owns TH x TW input pixels x cv channel vectors.  The index and gradient vectors of every window that touches
+// the tile are staged in shared memory first — all global loads of the block are independent and in flight together — and the gather
+// then runs out of shared memory.  The kernels above walk the windows with a dependent (index -> test -> gradient) load pair per
+// window: 25 serial L2 round trips for the 5x5 QSPPF pool (36 us for a 10 MB map) and a 9x re-read of index / gradient vectors through
+// L2 -> L1 on the stem pool (profiles/r01_pool_probe.txt).  Same arithmetic and summation order (window-major, row by row), so the
+// result is bit-identical to the flat kernel.
+struct PoolTile {
+  int TH, TW, cv, cv_shift;     // input pixels of a tile, channel vectors per block (power of two)
+  int oth, otw;                 // staged output rows / columns (upper bound of what a tile can touch)
+  int nth, ntw, nchunks;        // tiles per image plane, channel chunks
+};
+
+__device__ __forceinline__ void pool_out_range(int i, int n, int k, int s, int p, int no, int& lo, int& hi) {
+  // outputs whose window holds input coordinate range [i, i + n): first and last
+  lo = i + p - k + 1;
+  lo = lo <= 0 ? 0 : (lo + s - 1) / s;
+  hi = (i + n - 1 + p) / s;
+  if (hi > no - 1) hi = no - 1;
+}
+
+template <typename T, int V>
+__global__ void __launch_bounds__(256) qmaxpool_bwd_tile_kernel(const T* __restrict__ dy, const uint8_t* __restrict__ idx,
+                                                                T* __restrict__ dx, PoolGeom g, PoolTile t) {
+  pdl_prologue();
+  extern __shared__ __align__(16) uint8_t pool_smem[];
+  Vec<T, V>* s_dy = reinterpret_cast<Vec<T, V>*>(pool_smem);
+  Vec<uint8_t, V>* s_ix = reinterpret_cast<Vec<uint8_t, V>*>(pool_smem + (size_t)t.oth * t.otw * t.cv * sizeof(Vec<T, V>));
+  uint32_t b = blockIdx.x;
+  const int chunk = (int)(b % (uint32_t)t.nchunks); b /= (uint32_t)t.nchunks;
+  const int tw = (int)(b % (uint32_t)t.ntw); b /= (uint32_t)t.ntw;
+  const int th = (int)(b % (uint32_t)t.nth);
+  const int64_t o = b / (uint32_t)t.nth;
+  const int h0 = th * t.TH, w0 = tw * t.TW, c0 = chunk * t.cv;
+  const int nh = min(t.TH, g.H - h0), nw = min(t.TW, g.W - w0), ncv = min(t.cv, g.inner_vecs - c0);
+  int ho0, ho1, wo0, wo1;
+  pool_out_range(h0, nh, g.kH, g.sH, g.pH, g.Ho, ho0, ho1);
+  pool_out_range(w0, nw, g.kW, g.sW, g.pW, g.Wo, wo0, wo1);
+  const int nho = ho1 - ho0 + 1, nwo = wo1 - wo0 + 1;
+  const int64_t obase = (int64_t)o * g.Ho * g.Wo * g.inner_vecs + c0;
+  if (nho > 0 && nwo > 0) {
+    const int n = nho * nwo * t.cv;
+    for (int e = threadIdx.x; e < n; e += 256) {
+      const int c = e & (t.cv - 1);
+      const int r = e >> t.cv_shift;
+      const int wo = r % nwo, ho = r / nwo;
+      if (c < ncv) {
+        const int64_t ge = (obase + ((int64_t)(ho0 + ho) * g.Wo + (wo0 + wo)) * g.inner_vecs + c) * V;
+        s_dy[(ho * t.otw + wo) * t.cv + c] = *reinterpret_cast<const Vec<T, V>*>(dy + ge);
+        s_ix[(ho * t.otw + wo) * t.cv + c] = *reinterpret_cast<const Vec<uint8_t, V>*>(idx + ge);
+      }
+    }
+  }
+  __syncthreads();
+  const int nin = nh * nw * t.cv;
+  const int64_t ibase = (int64_t)o * g.H * g.W * g.inner_vecs + c0;
+  for (int e = threadIdx.x; e < nin; e += 256) {
+    const int c = e & (t.cv - 1);
+    if (c >= ncv) continue;
+    const int r = e >> t.cv_shift;
+    const int wl = r % nw, hl = r / nw;
+    const int hi = h0 + hl, wi = w0 + wl;
+    int a0, a1, b0, b1;
+    pool_out_range(hi, 1, g.kH, g.sH, g.pH, g.Ho, a0, a1);
+    pool_out_range(wi, 1, g.kW, g.sW, g.pW, g.Wo, b0, b1);
+    float acc[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) acc[v] = 0.f;
+    for (int ho = a0; ho <= a1; ++ho) {
+      const int kh = hi - (ho * g.sH - g.pH);
+      for (int wo = b0; wo <= b1; ++wo) {
+        const int tap = kh * g.kW + (wi - (wo * g.sW - g.pW));
+        const int se = ((ho - ho0) * t.otw + (wo - wo0)) * t.cv + c;
+        const Vec<uint8_t, V> a = s_ix[se];
+        bool any = false;
+#pragma unroll
+        for (int v = 0; v < V; ++v) any |= (a.v[v] == tap);
+        if (!any) continue;
+        const Vec<T, V> gq = s_dy[se];
+#pragma unroll
+        for (int v = 0; v < V; ++v)
+          if (a.v[v] == tap) acc[v] += to_f32(gq.v[v]);
+      }
+    }
+    store_vec<T, V>(dx + (ibase + ((int64_t)hi * g.W + wi) * g.inner_vecs + c) * V, acc);
+  }
+}
+
+static bool plan_pool_tile(const PoolGeom& g, int V, size_t esz, PoolTile& t, size_t& smem) {
+  auto p2floor = [](int v) { int r = 1; while (r * 2 <= v) r *= 2; return r; };
+  t.TH = g.H < 16 ? g.H : 16;
+  t.TW = g.W < 16 ? g.W : 16;
+  t.cv = p2floor(g.inner_vecs < 8 ? g.inner_vecs : 8);
+  for (;;) {
+    t.oth = (t.TH + g.kH - 2) / g.sH + 2;
+    t.otw = (t.TW + g.kW - 2) / g.sW + 2;
+    smem = (size_t)t.oth * t.otw * t.cv * (V * esz + V);
+    if (smem <= 40 * 1024) break;
+    if (t.cv > 1) t.cv >>= 1;
+    else if (t.TH > 4) t.TH >>= 1;
+    else if (t.TW > 4) t.TW >>= 1;
+    else return false;
+  }
+  t.cv_shift = 0;
+  while ((1 << t.cv_shift) < t.cv) ++t.cv_shift;
+  t.nth = (g.H + t.TH - 1) / t.TH;
+  t.ntw = (g.W + t.TW - 1) / t.TW;
+  t.nchunks = (g.inner_vecs + t.cv - 1) / t.cv;
+  const int64_t blocks = g.outer * t.nth * t.ntw * t.nchunks;
+  return blocks < (1ll << 31);
+}
+
 static int pool_geom(const char* who, int B, int C, int H, int W, int kH, int kW, int sH, int sW, int pH, int pW, int dtype,
                      int layout, PoolGeom& g, int& V) {
   QUAN_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, QUAN_E_ARG, "%s: non-positive dims", who);
@@ -453,6 +564,20 @@ static int launch_pool_bwd(const void* dy, const uint8_t* idx, void* dx, const P
   QUAN_TIMED(st);
   const bool small = g.outer * g.H * g.W * g.inner_vecs < (1ll << 31) - (1 << 20);   // i + grid stride stays below 2^31
   static const int env_rows = [] { const char* e = getenv("QUAN_POOL_ROWS"); return e ? atoi(e) : 1; }();
+  static const int env_tile = [] { const char* e = getenv("QUAN_POOL_TILE"); return e ? atoi(e) : 1; }();
+  {
+    PoolTile t;
+    size_t smem = 0;
+    if (env_tile && plan_pool_tile(g, V, sizeof(T), t, smem)) {
+      const unsigned blocks = (unsigned)(g.outer * t.nth * t.ntw * t.nchunks);
+      if (V == 8) { if constexpr (sizeof(T) == 2) QUAN_LAUNCH((qmaxpool_bwd_tile_kernel<T, 8>), blocks, 256, smem, st, gp, idx, dp, g, t); }
+      else if (V == 4) QUAN_LAUNCH((qmaxpool_bwd_tile_kernel<T, 4>), blocks, 256, smem, st, gp, idx, dp, g, t);
+      if (V == 8 || V == 4) {
+        QUAN_CHECK_LAUNCH("qmaxpool_bwd");
+        return QUAN_OK;
+      }
+    }
+  }
   if (env_rows && g.W * g.inner_vecs >= 128 && g.outer * g.H >= 2048 && g.outer * g.H < (1ll << 31)) {
     // measured on the Q-ResNet stem pool: 8 rows per block 348 us, flat kernel 550 us, 1 row per block 1348 us; small maps
     // (512 rows: 64 blocks of 8 rows, 132 vs 37 us) stay on the flat kernel

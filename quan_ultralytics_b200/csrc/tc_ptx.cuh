@@ -99,6 +99,19 @@ __device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// TMA store (shared::cta -> global, bulk-group completion): the box leaves shared memory as whole rows, rows outside the
+// tensor are clipped by the hardware.  The issuing thread owns the bulk group: the same thread commits and waits.
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// returns once all but the N most recent bulk groups of this thread have finished READING shared memory
+template <int N> __device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+
 // 2-CTA (cta_group::2) variants: both CTAs of the pair issue their own loads; completion bytes are credited to the
 // mbarrier of the pair's leader CTA (same smem offset, CTA-rank bit 24 of the shared::cluster address cleared).
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
