@@ -378,10 +378,30 @@ struct PoolTile {
 __device__ __forceinline__ void pool_out_range(int i, int n, int k, int s, int p, int no, int& lo, int& hi) {
   // outputs whose window holds input coordinate range [i, i + n): first and last
   lo = i + p - k + 1;
-  lo = lo <= 0 ? 0 : (lo + s - 1) / s;
-  hi = (i + n - 1 + p) / s;
+  lo = lo <= 0 ? 0 : div_stride(lo + s - 1, s);
+  hi = div_stride(i + n - 1 + p, s);
   if (hi > no - 1) hi = no - 1;
 }
+
+// byte-wise equality of the V tap indices of a vector with `tap`: one SIMD compare per four elements instead of V extract-and-compare
+// pairs (the scalar form was ~30 instructions per window and vector: the k5 QSPPF pool spent its time there, not on loads)
+template <int V> struct TapMask;
+template <> struct TapMask<8> {
+  uint32_t m0, m1;
+  __device__ __forceinline__ TapMask(const void* p, uint32_t tap4) {
+    const uint2 a = *reinterpret_cast<const uint2*>(p);
+    m0 = __vcmpeq4(a.x, tap4);
+    m1 = __vcmpeq4(a.y, tap4);
+  }
+  __device__ __forceinline__ bool any() const { return (m0 | m1) != 0u; }
+  __device__ __forceinline__ bool hit(int v) const { return ((v < 4 ? m0 : m1) >> (8 * (v & 3))) & 1u; }
+};
+template <> struct TapMask<4> {
+  uint32_t m0;
+  __device__ __forceinline__ TapMask(const void* p, uint32_t tap4) { m0 = __vcmpeq4(*reinterpret_cast<const uint32_t*>(p), tap4); }
+  __device__ __forceinline__ bool any() const { return m0 != 0u; }
+  __device__ __forceinline__ bool hit(int v) const { return (m0 >> (8 * v)) & 1u; }
+};
 
 template <typename T, int V>
 __global__ void __launch_bounds__(256) qmaxpool_bwd_tile_kernel(const T* __restrict__ dy, const uint8_t* __restrict__ idx,
@@ -407,7 +427,7 @@ __global__ void __launch_bounds__(256) qmaxpool_bwd_tile_kernel(const T* __restr
     for (int e = threadIdx.x; e < n; e += 256) {
       const int c = e & (t.cv - 1);
       const int r = e >> t.cv_shift;
-      const int wo = r % nwo, ho = r / nwo;
+      const int ho = r / nwo, wo = r - ho * nwo;
       if (c < ncv) {
         const int64_t ge = (obase + ((int64_t)(ho0 + ho) * g.Wo + (wo0 + wo)) * g.inner_vecs + c) * V;
         s_dy[(ho * t.otw + wo) * t.cv + c] = *reinterpret_cast<const Vec<T, V>*>(dy + ge);
@@ -416,44 +436,45 @@ __global__ void __launch_bounds__(256) qmaxpool_bwd_tile_kernel(const T* __restr
     }
   }
   __syncthreads();
-  const int nin = nh * nw * t.cv;
-  const int64_t ibase = (int64_t)o * g.H * g.W * g.inner_vecs + c0;
-  for (int e = threadIdx.x; e < nin; e += 256) {
-    const int c = e & (t.cv - 1);
-    if (c >= ncv) continue;
-    const int r = e >> t.cv_shift;
-    const int wl = r % nw, hl = r / nw;
-    const int hi = h0 + hl, wi = w0 + wl;
-    int a0, a1, b0, b1;
+  // a thread keeps its (pixel column, channel vector) and walks down the tile's rows: the column's window range is computed once
+  const int col = threadIdx.x & ((t.TW << t.cv_shift) - 1);       // TW is a power of two
+  const int row0 = threadIdx.x / (t.TW << t.cv_shift), rstep = 256 / (t.TW << t.cv_shift);
+  const int c = col & (t.cv - 1), wl = col >> t.cv_shift;
+  if (wl >= nw || c >= ncv) return;
+  const int wi = w0 + wl;
+  int b0, b1;
+  pool_out_range(wi, 1, g.kW, g.sW, g.pW, g.Wo, b0, b1);
+  const int kw_first = wi - (b0 * g.sW - g.pW);                    // tap column in window b0; sW less in every next one
+  const int s_col = (b0 - wo0) * t.cv + c;
+  const int64_t ibase = (int64_t)o * g.H * g.W * g.inner_vecs + c0 + c;
+  for (int hl = row0; hl < nh; hl += rstep) {
+    const int hi = h0 + hl;
+    int a0, a1;
     pool_out_range(hi, 1, g.kH, g.sH, g.pH, g.Ho, a0, a1);
-    pool_out_range(wi, 1, g.kW, g.sW, g.pW, g.Wo, b0, b1);
     float acc[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) acc[v] = 0.f;
-    for (int ho = a0; ho <= a1; ++ho) {
-      const int kh = hi - (ho * g.sH - g.pH);
-      for (int wo = b0; wo <= b1; ++wo) {
-        const int tap = kh * g.kW + (wi - (wo * g.sW - g.pW));
-        const int se = ((ho - ho0) * t.otw + (wo - wo0)) * t.cv + c;
-        const Vec<uint8_t, V> a = s_ix[se];
-        bool any = false;
-#pragma unroll
-        for (int v = 0; v < V; ++v) any |= (a.v[v] == tap);
-        if (!any) continue;
+    int kh = hi - (a0 * g.sH - g.pH);
+    for (int ho = a0; ho <= a1; ++ho, kh -= g.sH) {
+      int se = (ho - ho0) * t.otw * t.cv + s_col;
+      uint32_t tap4 = (uint32_t)(kh * g.kW + kw_first) * 0x01010101u;
+      for (int wo = b0; wo <= b1; ++wo, se += t.cv, tap4 -= (uint32_t)g.sW * 0x01010101u) {
+        const TapMask<V> m(s_ix + se, tap4);
+        if (!m.any()) continue;
         const Vec<T, V> gq = s_dy[se];
 #pragma unroll
         for (int v = 0; v < V; ++v)
-          if (a.v[v] == tap) acc[v] += to_f32(gq.v[v]);
+          if (m.hit(v)) acc[v] += to_f32(gq.v[v]);
       }
     }
-    store_vec<T, V>(dx + (ibase + ((int64_t)hi * g.W + wi) * g.inner_vecs + c) * V, acc);
+    store_vec<T, V>(dx + (ibase + ((int64_t)hi * g.W + wi) * g.inner_vecs) * V, acc);
   }
 }
 
 static bool plan_pool_tile(const PoolGeom& g, int V, size_t esz, PoolTile& t, size_t& smem) {
   auto p2floor = [](int v) { int r = 1; while (r * 2 <= v) r *= 2; return r; };
-  t.TH = g.H < 16 ? g.H : 16;
-  t.TW = g.W < 16 ? g.W : 16;
+  t.TH = 16;
+  t.TW = 16;                                     // powers of two: a thread's column is threadIdx & mask (ragged edges are masked)
   t.cv = p2floor(g.inner_vecs < 8 ? g.inner_vecs : 8);
   for (;;) {
     t.oth = (t.TH + g.kH - 2) / g.sH + 2;
