@@ -1341,7 +1341,11 @@ static int launch_reduce(const void* x, const void* dy, int B, int C, int H, int
         // ncu (profiles/r01_iqbn_tune5.log): fed by TMA the reduction is issue-bound (62-68 % issue-active, 9.4 thread
         // instructions per element); 3 or 4 smaller blocks per SM measured no better (42.6 / 50.1 vs 40.3 us with fold)
         const int bps = env_int("QUAN_IQBN_TMA_BPS", 2);
-        const size_t ring = (size_t)env_int("QUAN_IQBN_TMA_KB", bps >= 3 ? 64 : 96) * 1024;
+        // ring: 96 KB per block for the tensors of the wide layers; 56 KB below 300 MB, where the kernel runs inside the narrow models'
+        // step beside a deferred wgrad (100 KB ring) — two blocks + that CTA fit an SM.  Measured on the QUAN-YOLO11n
+        // step (two alternating runs each): 96 KB 10.87 / 10.94 ms, 56 KB 10.73 / 10.74 ms.
+        const double stream_mb = (double)g.R * row_bytes * (MODE == 1 ? 2 : 1) / 1e6;
+        const size_t ring = (size_t)env_int("QUAN_IQBN_TMA_KB", bps >= 3 ? 64 : stream_mb <= 300.0 ? 56 : 96) * 1024;
         int stages = (int)(ring / tile_bytes);
         if (stages > 8) stages = 8;
         if (stages >= 2) {
@@ -1433,7 +1437,7 @@ static int launch_apply(const void* x, const void* dy, void* out, int B, int C, 
         g.tile_rows = tr;
         g.ntiles = (int)ceil_div64(g.R, tr);
         const size_t tile_bytes = (size_t)tr * row_bytes_t * 2;
-        int stages = (int)((96 * 1024) / tile_bytes);
+        int stages = (int)(((size_t)env_int("QUAN_IQBN_APPLY_TMA_KB", 96) * 1024) / tile_bytes);
         if (stages > 8) stages = 8;
         if (stages >= 2) {
           g.stages = stages;

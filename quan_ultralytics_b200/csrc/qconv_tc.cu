@@ -1410,6 +1410,16 @@ static int launch_igemm(const void* in, const void* wpacked, const float* bias, 
   const size_t stat_bytes = p.stat_part != nullptr ? (size_t)8 * p.stat_cq * sizeof(float) : 0;
   size_t budget = 226 * 1024 - 1024 - 512 - stat_bytes - ts_bytes;
   if (budget > 200 * 1024) budget = 200 * 1024;
+  // dense (narrow-layer) form: the pipeline's shared memory is capped so that two kernels of the step (the main chain's igemm / IQBN
+  // kernels and a deferred wgrad on the side stream) can be co-resident on an SM instead of taking turns — with 200 KB
+  // rings every persistent kernel owned its SM and the side stream only ran in the gaps.  Measured on B200 (QUAN-YOLO11n step, three
+  // alternating runs each): no caps 11.20 ms, wgrad ring <= 100 KB 10.98, both <= 100 KB 10.81-10.95, 72 / 72 10.86-11.03, wgrad <= 64 KB
+  // 11.0-11.2 (its own prefetch depth starts to matter).  QUAN_TC_DENSE_SMEM_KB / QUAN_TC_WG_SMEM_KB = 0 lift the caps.
+  if (NQ == 1) {
+    static const int cap_kb = [] { const char* e = getenv("QUAN_TC_DENSE_SMEM_KB"); return e ? atoi(e) : 96; }();
+    const size_t cap = (size_t)cap_kb * 1024;
+    if (cap_kb > 0 && budget > cap && cap >= a_ring + 2 * stage_bytes) budget = cap;    // never below a two-stage ring
+  }
   QUAN_REQUIRE(budget > a_ring, QUAN_E_UNSUPPORTED, "tcgen05 conv: no shared memory left for the pipeline");
   budget -= a_ring;
   int stages = (int)(budget / stage_bytes);
@@ -1766,6 +1776,11 @@ static bool plan_wgrad(const quan_conv_dims& d, int dtype, int dense, WgradPlan&
   const size_t stage = (size_t)w.MA * atom + b_stage(w.NB);
   int stages = (int)((200 * 1024) / stage);
   if (stages > 8) stages = 8;
+  if (dense) {                                       // see QUAN_TC_DENSE_SMEM_KB in launch_igemm
+    static const int cap_kb = [] { const char* e = getenv("QUAN_TC_WG_SMEM_KB"); return e ? atoi(e) : 100; }();
+    if (cap_kb > 0 && (size_t)stages * stage > (size_t)cap_kb * 1024) stages = (int)((size_t)cap_kb * 1024 / stage);
+    if (stages < 2) stages = 2;                      // never below a two-stage ring
+  }
   if (stages < 2) return false;
   w.stages = stages;
   w.smem = 1024 + stages * stage + (2 * stages + 1) * sizeof(uint64_t) + 16;
