@@ -636,6 +636,7 @@ __global__ void __launch_bounds__(256) iqbn_reduce_small(const T* __restrict__ x
       }
     }
   }
+  double v[2 * V];                                     // this thread's sums, exact in fp64 from here on
 #pragma unroll
   for (int i = 0; i < V; ++i) {
     double a0, a1;
@@ -647,9 +648,39 @@ __global__ void __launch_bounds__(256) iqbn_reduce_small(const T* __restrict__ x
       a0 = (double)s0[i];
       a1 = (double)s1[i];
     }
-    sred[threadIdx.x][2 * i] = on ? a0 : 0.0;
-    sred[threadIdx.x][2 * i + 1] = on ? a1 : 0.0;
+    v[2 * i] = on ? a0 : 0.0;
+    v[2 * i + 1] = on ? a1 : 0.0;
   }
+  if ((cvpg & (cvpg - 1)) == 0) {
+    // power-of-two column groups (every model shape): the row lanes of a warp meet by shuffle, the warps (or, for rows wider than a
+    // warp, the row lanes) in ONE shared-memory round, and each of the 8C sums is finished and sent to L2 by its own thread.  The
+    // five-level fp64 tree through shared memory it replaces (barrier + 16 dependent DADDs per level) was 57 % of this kernel's stall
+    // samples on the 2 MB tensors (ncu source page, profiles/r02_ncu_iqbn_reduce_small.txt): 13.4-14.9 us for a 4 us stream.
+    const int lane = threadIdx.x & 31;
+    for (int off = cvpg; off < 32; off <<= 1) {
+#pragma unroll
+      for (int e = 0; e < 2 * V; ++e) v[e] += __shfl_xor_sync(0xffffffffu, v[e], off);
+    }
+    double* flat = &sred[0][0];                        // [groups][cvpg][2V]
+    const int groups = cvpg < 32 ? 256 / 32 : rpb;     // partial sets left: one per warp, or one per row lane
+    const int grp = cvpg < 32 ? (int)(threadIdx.x >> 5) : rl;
+    if (cvpg >= 32 || lane < cvpg) {
+#pragma unroll
+      for (int e = 0; e < 2 * V; ++e) flat[((size_t)grp * cvpg + cvl) * 2 * V + e] = v[e];
+    }
+    __syncthreads();
+    const int nsum = cvpg * 2 * V;                     // = 8C
+    for (int t = threadIdx.x; t < nsum; t += 256) {
+      double sum = 0.0;
+      for (int gi = 0; gi < groups; ++gi) sum += flat[(size_t)gi * nsum + t];
+      const int e = t % (2 * V), cv = t / (2 * V);
+      const int col = cv * V + (e >> 1);
+      const int q = col / C, c = col - q * C;
+      atomicAdd(ws.acc + (e & 1) * 4 * C + c * 4 + q, sum);
+    }
+  } else {
+#pragma unroll
+  for (int e = 0; e < 2 * V; ++e) sred[threadIdx.x][e] = v[e];
   __syncthreads();
   int half = 1;
   while (half * 2 < rpb) half *= 2;
@@ -668,6 +699,7 @@ __global__ void __launch_bounds__(256) iqbn_reduce_small(const T* __restrict__ x
       atomicAdd(ws.acc + c * 4 + q, sred[threadIdx.x][2 * i]);
       atomicAdd(ws.acc + 4 * C + c * 4 + q, sred[threadIdx.x][2 * i + 1]);
     }
+  }
   }
   __threadfence();
   __syncthreads();

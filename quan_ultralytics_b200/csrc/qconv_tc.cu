@@ -1406,23 +1406,27 @@ static int launch_igemm(const void* in, const void* wpacked, const float* bias, 
               (reinterpret_cast<uintptr_t>(out) & 15) == 0)
                  ? (env_tstore == 4 || env_tstore == 2 ? env_tstore : 2)
                  : 0;
-  const size_t ts_bytes = (size_t)EPI_WARPS * epi_groups(NQ) * p.tstore * 32 * 16 * esz;   // 2 slots: 16 KB (bf16) / 32 KB (fp32)
   const size_t stat_bytes = p.stat_part != nullptr ? (size_t)8 * p.stat_cq * sizeof(float) : 0;
-  size_t budget = 226 * 1024 - 1024 - 512 - stat_bytes - ts_bytes;
-  if (budget > 200 * 1024) budget = 200 * 1024;
-  // dense (narrow-layer) form: the pipeline's shared memory is capped so that two kernels of the step (the main chain's igemm / IQBN
-  // kernels and a deferred wgrad on the side stream) can be co-resident on an SM instead of taking turns — with 200 KB
-  // rings every persistent kernel owned its SM and the side stream only ran in the gaps.  Measured on B200 (QUAN-YOLO11n step, three
-  // alternating runs each): no caps 11.20 ms, wgrad ring <= 100 KB 10.98, both <= 100 KB 10.81-10.95, 72 / 72 10.86-11.03, wgrad <= 64 KB
-  // 11.0-11.2 (its own prefetch depth starts to matter).  QUAN_TC_DENSE_SMEM_KB / QUAN_TC_WG_SMEM_KB = 0 lift the caps.
-  if (NQ == 1) {
-    static const int cap_kb = [] { const char* e = getenv("QUAN_TC_DENSE_SMEM_KB"); return e ? atoi(e) : 96; }();
-    const size_t cap = (size_t)cap_kb * 1024;
-    if (cap_kb > 0 && budget > cap && cap >= a_ring + 2 * stage_bytes) budget = cap;    // never below a two-stage ring
+  size_t ts_bytes = 0;
+  int stages = 0;
+  for (;;) {
+    ts_bytes = (size_t)EPI_WARPS * epi_groups(NQ) * p.tstore * 32 * 16 * esz;   // 2 slots per warp: 16 KB (bf16) / 32 KB (fp32)
+    size_t budget = 226 * 1024 - 1024 - 512 - stat_bytes - ts_bytes;
+    if (budget > 200 * 1024) budget = 200 * 1024;
+    // dense (narrow-layer) form: the pipeline's shared memory is capped so that two kernels of the step (the main chain's igemm / IQBN
+    // kernels and a deferred wgrad on the side stream) can be co-resident on an SM instead of taking turns — with 200 KB
+    // rings every persistent kernel owned its SM and the side stream only ran in the gaps.  Measured on B200 (QUAN-YOLO11n step, three
+    // alternating runs each): no caps 11.20 ms, wgrad ring <= 100 KB 10.98, both <= 100 KB 10.81-10.95, 72 / 72 10.86-11.03, wgrad <= 64 KB
+    // 11.0-11.2 (its own prefetch depth starts to matter).  QUAN_TC_DENSE_SMEM_KB / QUAN_TC_WG_SMEM_KB = 0 lift the caps.
+    if (NQ == 1) {
+      static const int cap_kb = [] { const char* e = getenv("QUAN_TC_DENSE_SMEM_KB"); return e ? atoi(e) : 96; }();
+      const size_t cap = (size_t)cap_kb * 1024;
+      if (cap_kb > 0 && budget > cap && cap >= a_ring + 2 * stage_bytes) budget = cap;    // never below a two-stage ring
+    }
+    stages = budget > a_ring ? (int)((budget - a_ring) / stage_bytes) : 0;
+    if (stages >= 2 || p.tstore == 0) break;
+    p.tstore = 0;                                      // a two-stage ring of big tiles needs the staging slots' room: per-lane stores
   }
-  QUAN_REQUIRE(budget > a_ring, QUAN_E_UNSUPPORTED, "tcgen05 conv: no shared memory left for the pipeline");
-  budget -= a_ring;
-  int stages = (int)(budget / stage_bytes);
   if (stages > 8) stages = 8;
   if (const char* e = getenv("QUAN_TC_STAGES")) { int v = atoi(e); if (v >= 1 && v < stages) stages = v; }
   QUAN_REQUIRE(stages >= 2, QUAN_E_UNSUPPORTED, "tcgen05 conv: stage too large");

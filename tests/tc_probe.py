@@ -51,6 +51,11 @@ CASES = [
     ("bf16_s2_odd", "bf16", 3, 32, 64, 15, 13, 3, 2, 1, 1, False, "A"),
     ("bf16_c64_s2_odd", "bf16", 5, 64, 128, 17, 19, 3, 2, 1, 1, True, "B"),
     ("bf16_c16_s2_k5", "bf16", 6, 16, 16, 32, 32, 5, 2, 2, 1, False, "A"),
+    # one 128-pixel tile in total (the P5 map of a 256^2 image, batch 2): no CTA pair, so the whole 256-column weight tile sits in one CTA's
+    # stage — with fp32 operands the TMA-store staging slots no longer fit beside a two-stage ring and the epilogue falls back to per-lane stores
+    ("tf32_c64_one_tile", "f32", 2, 64, 64, 8, 8, 3, 1, 1, 1, False, "A"),
+    ("tf32_c64_k1_one_tile", "f32", 2, 64, 64, 8, 8, 1, 1, 0, 1, True, "B"),
+    ("bf16_c64_one_tile", "bf16", 2, 64, 64, 8, 8, 3, 1, 1, 1, False, "A"),
 ]
 
 
