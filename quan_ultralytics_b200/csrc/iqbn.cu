@@ -1343,7 +1343,10 @@ static int launch_reduce(const void* x, const void* dy, int B, int C, int H, int
       if (mb <= small_mb && colvecs <= 256 && Vs * sizeof(T) >= 8) {
         const int rpb = 256 / colvecs;
         int64_t blocks = ceil_div64(R, (int64_t)rpb * 4);
-        if (blocks > QUAN_NUM_SMS) blocks = QUAN_NUM_SMS;
+        static const int small_bps = env_int("QUAN_IQBN_SMALL_BPS", 1);
+        int64_t cap = (int64_t)QUAN_NUM_SMS * small_bps;
+        while (cap > QUAN_NUM_SMS && cap * 8 * C > 65536) cap -= QUAN_NUM_SMS;
+        if (blocks > cap) blocks = cap;
         if (blocks * 8 * C <= 65536) {
           const size_t smem = (size_t)256 * 2 * Vs * sizeof(double);
           QUAN_TIMED(st);
