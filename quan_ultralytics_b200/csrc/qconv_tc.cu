@@ -1688,6 +1688,7 @@ struct WgradPlan {
   int row_bytes;               // swizzle atom row: 128 / 64 / 32 bytes of channels
   int nchunks, TG, NA, NB, MA, co_blocks, ci_blocks, tap_groups, splits, chunks_per_split, stages;
   int halo;                    // B operand as one halo box per ci atom (stride 1 along W)
+  bool atomic;                 // the splits add into one partial set (dense form, > 4 splits)
   size_t b_atom_bytes;         // halo: slot pitch of a ci atom
   size_t smem, partial_bytes;
 };
@@ -1765,10 +1766,18 @@ static bool plan_wgrad(const quan_conv_dims& d, int dtype, int dense, WgradPlan&
   const double flops = 2.0 * nq * (double)d.B * Ho * Wo * (w.co_blocks * 128.0) * w.Ci * taps;   // what the tensor pipe executes
   const double in_bytes = (double)d.B * Ho * Wo * 4.0 * (d.Co + d.Ci * d.sH * d.sW) * esz;       // one pass over dY and x
   const double part_bytes = (double)nq * taps * w.Co * w.Ci * 4.0;                               // one split's fp32 partials
-  for (int64_t sp = 1; sp <= 64 && sp <= w.nchunks; ++sp) {
+  // dense form: the splits add into ONE partial set with atomics (launch_wgrad), so nothing grows with the split count and a 1x1 layer
+  // (one tap group: combos = 1) could use every SM instead of 64 of them.  Measured on the QUAN-YOLO11n step (three alternating runs):
+  // 64 splits 10.61-10.73 ms, 148 10.62-10.72, 296 with two CTAs per SM 10.78 — the wgrads run beside the main chain
+  // and more CTAs only take more of its SMs; 64 stays.  QUAN_TC_WG_MAXSPLIT / QUAN_TC_WG_RESID (CTAs per SM the wave model assumes).
+  static const int max_split_dense = [] { const char* e = getenv("QUAN_TC_WG_MAXSPLIT"); return e ? atoi(e) : 64; }();
+  static const int resid = [] { const char* e = getenv("QUAN_TC_WG_RESID"); return e ? atoi(e) : 1; }();
+  const int64_t max_sp = dense ? max_split_dense : 64;
+  const int64_t slots = (int64_t)QUAN_NUM_SMS * (dense ? resid : 1);
+  for (int64_t sp = 1; sp <= max_sp && sp <= w.nchunks; ++sp) {
     const int64_t ctas = combos * sp;
-    const int64_t waves = (ctas + QUAN_NUM_SMS - 1) / QUAN_NUM_SMS;
-    const double eff = (double)ctas / (double)(waves * QUAN_NUM_SMS);
+    const int64_t waves = (ctas + slots - 1) / slots;
+    const double eff = (double)ctas / (double)(waves * slots);
     // modelled time: tensor work at ~1 PFLOP/s or the operand stream at ~4 TB/s, scaled by wave fill, + partial
     // write/read at ~4 TB/s + per-CTA prologue
     const double work = flops / 1.0e15 > in_bytes / 4.0e12 ? flops / 1.0e15 : in_bytes / 4.0e12;
@@ -1788,7 +1797,8 @@ static bool plan_wgrad(const quan_conv_dims& d, int dtype, int dense, WgradPlan&
   if (stages < 2) return false;
   w.stages = stages;
   w.smem = 1024 + stages * stage + (2 * stages + 1) * sizeof(uint64_t) + 16;
-  w.partial_bytes = (size_t)w.splits * nq * taps * w.Co * w.Ci * sizeof(float);
+  w.atomic = dense && w.splits > 4;                  // many splits of a tiny dW: one partial set, vector atomics (launch_wgrad)
+  w.partial_bytes = (size_t)(w.atomic ? 1 : w.splits) * nq * taps * w.Co * w.Ci * sizeof(float);
   return true;
 }
 
@@ -1832,8 +1842,8 @@ static int launch_wgrad(const void* gq, const void* x, float* const dw[4], const
   p.tmem_cols = (uint32_t)pow2_ceil(w.TG * w.NA * w.NB < 32 ? 32 : w.TG * w.NA * w.NB);
   p.partial = reinterpret_cast<float*>(ws);
   // dense form with many splits: accumulate with atomics (summation order is then not deterministic, as in the direct engine)
-  p.atomic = (dense && w.splits > 4) ? 1 : 0;
-  if (p.atomic) QUAN_CUDA(cudaMemsetAsync(ws, 0, w.partial_bytes / w.splits, st));
+  p.atomic = w.atomic ? 1 : 0;
+  if (p.atomic) QUAN_CUDA(cudaMemsetAsync(ws, 0, w.partial_bytes, st));
   const int fold_splits = p.atomic ? 1 : w.splits;
 
   CUtensorMap map_g, map_x;
