@@ -33,6 +33,24 @@ sys.path.insert(0, str(ROOT))
 
 import torch  # noqa: E402
 
+_JSON_OUT = None
+
+
+def json_only_stdout():
+    """stdout carries the JSON line(s) only: whatever libraries print there (the reference's import messages, settings banners) is
+    sent to stderr at the file-descriptor level, so a driver that parses stdout sees exactly one JSON object per line."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(obj) + "\n")
+    out.flush()
+
 
 def parse_args():
     ap = argparse.ArgumentParser()
@@ -139,7 +157,7 @@ def reference_arm(a):
         "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -534,7 +552,7 @@ def run_model_trace(a, name):
         "hotpath_tflops": (fwd_flops if a.infer else flops_img) * B / t_step / 1e12,
         "roofline_floor_ms_per_step": 1e3 * B * max(flops_img / (peaks["bf16_tflops"] * 1e12), bytes_img / (peaks["hbm_gbs"] * 1e9)),
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 
@@ -586,7 +604,7 @@ def yolo_reference_arm(a):
     scale = "n" if a.workload == "yolo11n_obb" else "s"
     n = 1
     ips, sec, cores = yolo_cpu_reference(a, scale, n, a.steps, a.warmup)
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "train_images_per_sec", "value": ips, "unit": "images/s", "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": yolo_config(a, scale, a.n, a.gpus),
@@ -594,7 +612,7 @@ def yolo_reference_arm(a):
                           "v8OBBLoss, clip_grad_norm_ + torch SGD) on the host cores, fp32",
         "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "reference",
                          "sample": f"{n} image/step of the same training step ({a.steps} timed steps, {a.warmup} warm-up), per-image normalised"},
-        "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+        "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0})
 
 
 def parse_timing_report(lib):
@@ -825,7 +843,7 @@ def run_yolo_obb(a):
             line["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": cores, "kind": "reference",
                                     "sample": f"1 image/step of the same training step through the unmodified reference (baseline/_ref), "
                                               f"{a.cpu_steps} timed steps after 1 warm-up, fp32, per-image normalised"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         # the captured graphs hold NCCL work on the communicator: tearing the process group down underneath them can wait forever
         # (watchdog dump after minutes); every rank has finished its timed work at this point, so leave without the teardown
@@ -956,11 +974,11 @@ def run_sweep(a):
     b0 = torch.randn(16, 16, 64, 64, 4, device=dev).to(bf).contiguous(memory_format=cl)
     h0, h1 = a0.chunk(2, 1)
     hbm_row("rows_cat (C2f: 2 halves + 1)", "16x(16+16+16)x64^2", lambda: ops.qcat([h0, h1, b0]), 2 * (a0.numel() + b0.numel()) * 2)
-    print(json.dumps({"workload": "QConv2D/IQBN layer sweep (BASELINE configs[1])", "peaks": peaks,
+    emit({"workload": "QConv2D/IQBN layer sweep (BASELINE configs[1])", "peaks": peaks,
                       "note": "ops timed alone, L2 swept between launches; conv ms include the weight-packing / mix pre-pass / split-K fold "
                               "kernels of the call; tensor fractions against the measured bf16 burst peak (MEASURED_PEAKS.json) and, for tf32, "
                               "against cuBLAS TF32 8192^3 measured in this run; rows with a `shape` key: the HBM-bound ops around the convolutions at the "
-                              "QUAN-YOLO11n shapes (host launch latency of the Python wrapper is inside the small ones' times)", "rows": rows}))
+                              "QUAN-YOLO11n shapes (host launch latency of the Python wrapper is inside the small ones' times)", "rows": rows})
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -1005,13 +1023,13 @@ def classifier_reference_arm(a):
         return
     n = 8 if a.workload == "qresnet34" else 128
     ips, sec, cores = classifier_cpu_reference(a, n, a.steps, a.warmup)
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "train_images_per_sec", "value": ips, "unit": "images/s", "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": classifier_config(a, a.gpus),
         "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "reference",
                          "sample": f"{n} images/step of the same training step through the unmodified reference, per-image normalised"},
-        "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+        "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0})
 
 
 def run_classifier(a):
@@ -1133,7 +1151,7 @@ def run_classifier(a):
             ips, sec, cores = classifier_cpu_reference(a, n, min(a.cpu_steps, 2), 1)
             line["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": cores, "kind": "reference",
                                     "sample": f"{n} images/step through the unmodified reference model (baseline/_ref), fp32"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         torch.cuda.synchronize()
         dist.barrier()
@@ -1144,6 +1162,7 @@ def run_classifier(a):
 
 def main():
     a = parse_args()
+    json_only_stdout()
     if a.workload.endswith("_trace") and a.impl == "ours":
         name = a.workload[:-len("_trace")]
         if a.n_default:                                         # per-GPU batch of the BASELINE config that names the model
@@ -1327,7 +1346,7 @@ def main():
             ips, sec, cores = run_cpu_port(a, a.cpu_n, a.cpu_steps, 1)
             line["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
                                     "sample": f"{a.cpu_n} images/step of the same block stack, {a.cpu_steps} timed steps, fp32"}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
