@@ -133,3 +133,46 @@ def test_fused_loss_vs_live_reference_at_model_size():
     # fp32 on both sides; the ProbIoU gradient divides by sqrt(1 - exp(-bd)) ~ 0 for near-perfect boxes, where the two evaluation
     # orders (autograd's reverse mode vs the kernel's forward-mode duals) differ in the last bits of a large quotient
     assert max(errs) <= 3e-3, errs
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_fused_loss_staged_rows_match_direct_rows(dtype):
+    """The loss / decode kernels have two forms: rows staged through shared memory (pitch of whole 32-bit words: the padded rows of the
+    fused head tensor, 16-byte copies when the pitch allows) and direct per-thread row access (any pitch).  Same arithmetic per anchor:
+    padded bf16 rows (pitch 80: staged, vector copies), unpadded bf16 rows (pitch 79: direct) and fp32 rows (staged, word copies) must agree."""
+    import types
+    from quan_ultralytics_b200 import workloads
+    from quan_ultralytics_b200.loss import OBBLossFused, pad_targets
+    nc, reg_max, Bz, S = 15, 16, 3, 256
+    no = 4 * reg_max + nc
+    crit = OBBLossFused(stride=[8.0, 16.0, 32.0], nc=nc, reg_max=reg_max, hyp=types.SimpleNamespace(box=7.5, cls=0.5, dfl=1.5), device="cuda")
+    batch = workloads.synthetic_obb_batch(Bz, S, "cuda", seed=7)
+    tg, tm = pad_targets(batch, Bz)
+    tgt = {"targets": tg.cuda(), "target_mask": tm.cuda()}
+    g = torch.Generator(device="cuda").manual_seed(5)
+    base = [(torch.randn(Bz, no, S // s, S // s, device="cuda", generator=g) * 0.5).to(dtype) for s in (8, 16, 32)]
+    angle = ((torch.rand(Bz, 1, sum((S // s) ** 2 for s in (8, 16, 32)), device="cuda", generator=g) - 0.25) * 3.14159).to(dtype)
+
+    def run(pad):
+        feats = []
+        for f in base:
+            if pad:
+                big = torch.zeros(Bz, no + pad, f.shape[2], f.shape[3], device="cuda", dtype=dtype).contiguous(memory_format=torch.channels_last)
+                big[:, :no] = f
+                v = big[:, :no]
+                assert v.stride(3) == no + pad
+            else:
+                v = f.contiguous(memory_format=torch.channels_last)
+            feats.append(v.detach().requires_grad_(True))
+        a = angle.clone().requires_grad_(True)
+        total, items = crit((feats, a), tgt)
+        grads = torch.autograd.grad(total, feats + [a])
+        torch.cuda.synchronize()
+        return total, items, grads
+
+    t0, i0, g0 = run(0)
+    t1, i1, g1 = run(1)
+    torch.testing.assert_close(i1, i0, rtol=1e-6, atol=1e-7)
+    torch.testing.assert_close(t1, t0, rtol=1e-6, atol=1e-7)
+    for a, b in zip(g1, g0):
+        assert torch.equal(a.float(), b.float())
