@@ -77,7 +77,7 @@ struct TalArgs {
   float alpha, beta, eps;
   float* overlaps; float* align; int* cnt; int* cand; unsigned* pos_align; unsigned* pos_over;
   float* t_boxes; float* t_scores; unsigned char* fg; long long* tgi;
-  int use_smem;
+  int full_scan;                   // QUAN_TAL_FULLSCAN=1: always the full-row scans (tests)
 };
 
 __global__ void tal_clear_kernel(TalArgs t) {
@@ -87,23 +87,57 @@ __global__ void tal_clear_kernel(TalArgs t) {
   if (i < (int64_t)t.B * t.n) { t.pos_align[i] = 0u; t.pos_over[i] = 0u; }
 }
 
-// grid (n, B), one block per ground-truth box
+// grid (n, B), one block per ground-truth box.  Top-k with the reference's tie rule (torch.topk on the metric row; equal values ->
+// lowest anchor index, which is what matters for the zeros): the anchors with a POSITIVE metric — a few hundred of the 21 504 of a
+// 1024^2 image, those inside the box — are compacted into shared memory while the row is computed, the k arg-max passes run over that
+// list, and if fewer than k are positive the remaining picks are the lowest-index anchors whose metric is exactly zero (they only count
+// if they lie inside the box, tested below as before).  The first version kept the whole row in shared memory (84 KB per block) and
+// scanned all of it k times: 120 us per step.  A box with more positive anchors than the list holds falls back to the full scans.
+constexpr int TAL_CAP = 4096;
+
+__device__ __forceinline__ void tal_argmax_block(float& bv, int& bi, int& bp, float* red_v, int* red_i, int* red_p) {
+  // block-wide arg-max of (value desc, anchor index asc); every thread passes its candidate, thread 0 returns the winner
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov2 = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    const int op = __shfl_xor_sync(0xffffffffu, bp, o);
+    if (ov2 > bv || (ov2 == bv && oi < bi)) { bv = ov2; bi = oi; bp = op; }
+  }
+  if ((threadIdx.x & 31) == 0) { red_v[threadIdx.x >> 5] = bv; red_i[threadIdx.x >> 5] = bi; red_p[threadIdx.x >> 5] = bp; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    bv = threadIdx.x < TAL_THREADS / 32 ? red_v[threadIdx.x] : -2.f;
+    bi = threadIdx.x < TAL_THREADS / 32 ? red_i[threadIdx.x] : 0x7fffffff;
+    bp = threadIdx.x < TAL_THREADS / 32 ? red_p[threadIdx.x] : 0;
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov2 = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      const int op = __shfl_xor_sync(0xffffffffu, bp, o);
+      if (ov2 > bv || (ov2 == bv && oi < bi)) { bv = ov2; bi = oi; bp = op; }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(TAL_THREADS) tal_metrics_topk_kernel(TalArgs t) {
   pdl_prologue();
-  extern __shared__ float row_s[];
+  __shared__ float cval[TAL_CAP];
+  __shared__ int cidx[TAL_CAP];
   __shared__ float red_v[TAL_THREADS / 32];
-  __shared__ int red_i[TAL_THREADS / 32];
+  __shared__ int red_i[TAL_THREADS / 32], red_p[TAL_THREADS / 32];
   __shared__ int sel[64];
+  __shared__ int s_cnt;
   const int j = blockIdx.x, b = blockIdx.y;
   const int64_t rowoff = ((int64_t)b * t.n + j) * t.A;
   float* ov = t.overlaps + rowoff;
   float* al = t.align + rowoff;
-  float* buf = t.use_smem ? row_s : al;
   const bool valid = t.mask[b * t.n + j] != 0.f;
   if (!valid) {                                    // tal.py:121 (mask_in_gts * mask_gt): the row is all zero and selects nothing
     for (int a = threadIdx.x; a < t.A; a += TAL_THREADS) { ov[a] = 0.f; al[a] = 0.f; }
     return;
   }
+  if (threadIdx.x == 0) s_cnt = 0;
+  if (threadIdx.x < 64) sel[threadIdx.x] = 0x7fffffff;
+  __syncthreads();
   const RBox g = ld_box(t.gts + ((int64_t)b * t.n + j) * 5);
   const int label = (int)t.labels[b * t.n + j];
   float a1, b1, c1;
@@ -116,46 +150,58 @@ __global__ void __launch_bounds__(TAL_THREADS) tal_metrics_topk_kernel(TalArgs t
       o = fmaxf(probiou_dev(g, a1, b1, c1, p), 0.f);
       const float s = t.scores[((int64_t)b * t.A + a) * t.nc + label];
       m = powf(s, t.alpha) * powf(o, t.beta);
+      if (m > 0.f) {
+        const int k = atomicAdd(&s_cnt, 1);
+        if (k < TAL_CAP) { cval[k] = m; cidx[k] = a; }
+      }
     }
     ov[a] = o;
     al[a] = m;
-    if (t.use_smem) row_s[a] = m;
   }
   __syncthreads();
-  // top-k by k arg-max passes (ties -> lowest index); selected entries are hidden with -1 and restored afterwards
-  for (int k = 0; k < t.topk; ++k) {
-    float bv = -2.f;
-    int bi = 0x7fffffff;
-    for (int a = threadIdx.x; a < t.A; a += TAL_THREADS) {
-      const float v = buf[a];
-      if (v > bv) { bv = v; bi = a; }              // strided ascending scan: first maximum of this thread
-    }
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ov2 = __shfl_xor_sync(0xffffffffu, bv, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (ov2 > bv || (ov2 == bv && oi < bi)) { bv = ov2; bi = oi; }
-    }
-    if ((threadIdx.x & 31) == 0) { red_v[threadIdx.x >> 5] = bv; red_i[threadIdx.x >> 5] = bi; }
-    __syncthreads();
-    if (threadIdx.x < 32) {
-      bv = threadIdx.x < TAL_THREADS / 32 ? red_v[threadIdx.x] : -2.f;
-      bi = threadIdx.x < TAL_THREADS / 32 ? red_i[threadIdx.x] : 0x7fffffff;
-      for (int o = 16; o > 0; o >>= 1) {
-        const float ov2 = __shfl_xor_sync(0xffffffffu, bv, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (ov2 > bv || (ov2 == bv && oi < bi)) { bv = ov2; bi = oi; }
+  const int npos = s_cnt;
+  const bool compact = npos <= TAL_CAP && !t.full_scan;
+  if (compact) {
+    const int nsel = npos < t.topk ? npos : t.topk;
+    for (int k = 0; k < nsel; ++k) {
+      float bv = -2.f;
+      int bi = 0x7fffffff, bp = 0;
+      for (int e = threadIdx.x; e < npos; e += TAL_THREADS) {
+        const float v = cval[e];
+        const int a = cidx[e];
+        if (v > bv || (v == bv && a < bi)) { bv = v; bi = a; bp = e; }
       }
+      tal_argmax_block(bv, bi, bp, red_v, red_i, red_p);
+      if (threadIdx.x == 0) { sel[k] = bi; cval[bp] = -1.f; }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) {                        // fewer positives than k: the lowest-index zeros (al[] of this block is visible after the barrier)
+      int k = nsel;
+      for (int a = 0; a < t.A && k < t.topk; ++a)
+        if (al[a] == 0.f) sel[k++] = a;
+    }
+    __syncthreads();
+  } else {
+    // full scans of the row in global memory (ties -> lowest index); selected entries are hidden with -1 and restored afterwards
+    for (int k = 0; k < t.topk; ++k) {
+      float bv = -2.f;
+      int bi = 0x7fffffff, bp = 0;
+      for (int a = threadIdx.x; a < t.A; a += TAL_THREADS) {
+        const float v = al[a];
+        if (v > bv) { bv = v; bi = a; }            // strided ascending scan: first maximum of this thread
+      }
+      tal_argmax_block(bv, bi, bp, red_v, red_i, red_p);
       if (threadIdx.x == 0) {
         sel[k] = bi;
-        if (bi < t.A) buf[bi] = -1.f;
+        if (bi < t.A) al[bi] = -1.f;
       }
+      __syncthreads();
     }
-    __syncthreads();
   }
   if (threadIdx.x < t.topk) {
     const int a = sel[threadIdx.x];
     if (a < t.A) {
-      if (!t.use_smem) al[a] = powf(t.scores[((int64_t)b * t.A + a) * t.nc + label], t.alpha) * powf(ov[a], t.beta);   // restore
+      if (!compact) al[a] = powf(t.scores[((int64_t)b * t.A + a) * t.nc + label], t.alpha) * powf(ov[a], t.beta);   // restore
       if (inside(ib, t.anc[2 * a], t.anc[2 * a + 1])) {            // mask_topk * mask_in_gts (tal.py:127)
         atomicAdd(t.cnt + (int64_t)b * t.A + a, 1);
         t.cand[(int64_t)b * t.A + a] = j;
@@ -245,20 +291,16 @@ int quan_rotated_tal_assign(const float* pd_scores, const float* pd_bboxes, cons
   t.pos_align = reinterpret_cast<unsigned*>(w); w += (size_t)B * n;
   t.pos_over = reinterpret_cast<unsigned*>(w);
   t.t_boxes = target_bboxes; t.t_scores = target_scores; t.fg = fg_mask; t.tgi = reinterpret_cast<long long*>(target_gt_idx);
-  const size_t smem = (size_t)A * sizeof(float);
-  t.use_smem = smem <= 200 * 1024;
+  static const int env_full = [] { const char* e = getenv("QUAN_TAL_FULLSCAN"); return e ? atoi(e) : 0; }();
+  t.full_scan = env_full;
   auto kern = tal_metrics_topk_kernel;
-  if (t.use_smem && smem > 48 * 1024) {
-    static thread_local DeviceOnce once;
-    if (once.first()) QUAN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  }
   const int64_t na = (int64_t)B * A;
   const int blocks = (int)((na + 255) / 256);
   QUAN_TIMED(st);
   QUAN_LAUNCH((tal_clear_kernel), blocks, 256, 0, st, t);
   QUAN_CHECK_LAUNCH("tal_clear");
   QUAN_TIMED(st);
-  QUAN_LAUNCH((kern), dim3(n, B), TAL_THREADS, t.use_smem ? smem : 0, st, t);
+  QUAN_LAUNCH((kern), dim3(n, B), TAL_THREADS, 0, st, t);
   QUAN_CHECK_LAUNCH("tal_metrics_topk");
   QUAN_TIMED(st);
   QUAN_LAUNCH((tal_resolve_kernel), blocks, 256, 0, st, t);

@@ -176,3 +176,40 @@ def test_fused_loss_staged_rows_match_direct_rows(dtype):
     torch.testing.assert_close(t1, t0, rtol=1e-6, atol=1e-7)
     for a, b in zip(g1, g0):
         assert torch.equal(a.float(), b.float())
+
+
+def test_assigner_vs_live_reference_giant_and_tiny_boxes():
+    """Top-k edge cases against the reference's own RotatedTaskAlignedAssigner (tal.py:298-330) on the device: a box that covers more
+    anchors than the kernel's compact candidate list holds (full-row scans), a box so small that fewer than k anchors have a positive
+    metric (the remaining picks are the lowest-index zeros), a masked-out box, and ordinary boxes."""
+    from quan_ultralytics_b200 import refenv
+    if refenv.find_reference() is None:
+        pytest.skip("no reference tree (baseline/_ref)")
+    refenv.activate()
+    from ultralytics.utils.tal import RotatedTaskAlignedAssigner
+    from ultralytics.utils.tal import make_anchors
+    torch.manual_seed(3)
+    Bz, S, nc = 2, 1024, 15
+    feats = [torch.zeros(Bz, 1, S // s, S // s, device="cuda") for s in (8, 16, 32)]
+    anc, strides = make_anchors(feats, [8, 16, 32], 0.5)
+    anc_px = (anc * strides).contiguous()
+    A = anc_px.shape[0]
+    pd_scores = torch.rand(Bz, A, nc, device="cuda")
+    # predicted boxes near their anchors, random sizes / angles
+    pd_bboxes = torch.cat([anc_px.unsqueeze(0).expand(Bz, -1, -1) + torch.randn(Bz, A, 2, device="cuda") * 4,
+                           torch.rand(Bz, A, 2, device="cuda") * 200 + 8, (torch.rand(Bz, A, 1, device="cuda") - 0.25) * 3.14159], -1).contiguous()
+    gt = torch.tensor([[[512., 512., 900., 880., 0.3], [100., 120., 5., 4., 0.1], [700., 300., 120., 60., 1.0], [0., 0., 0., 0., 0.]],
+                       [[300., 640., 640., 700., -0.4], [900., 900., 30., 90., 0.7], [40., 40., 3., 3., 0.0], [512., 512., 64., 64., 0.2]]],
+                      device="cuda")
+    labels = torch.tensor([[[1.], [3.], [7.], [0.]], [[2.], [2.], [14.], [5.]]], device="cuda")
+    mask = torch.tensor([[[1.], [1.], [1.], [0.]], [[1.], [1.], [1.], [1.]]], device="cuda")
+    ref = RotatedTaskAlignedAssigner(topk=10, num_classes=nc, alpha=0.5, beta=6.0)
+    _, tb_r, ts_r, fg_r, tgi_r = ref(pd_scores, pd_bboxes, anc_px, labels, gt, mask)
+    crit = _crit(nc, 16, (7.5, 0.5, 1.5))
+    tb, ts, fg, tgi = crit._assign(pd_scores, pd_bboxes, anc_px, labels.squeeze(-1).contiguous(), gt.contiguous(), mask.squeeze(-1).contiguous())
+    torch.cuda.synchronize()
+    assert torch.equal(fg, fg_r.bool())
+    assert torch.equal(tgi[fg], tgi_r[fg_r.bool()])
+    torch.testing.assert_close(ts, ts_r.float(), rtol=2e-4, atol=1e-7)
+    torch.testing.assert_close(tb[fg], tb_r[fg_r.bool()], rtol=0, atol=0)
+    assert int(fg.sum()) > 20
