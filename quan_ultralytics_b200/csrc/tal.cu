@@ -236,26 +236,42 @@ __global__ void tal_resolve_kernel(TalArgs t) {
   }
 }
 
-// one thread per (b, a): tal.py:188-236 get_targets and the normalisation :108-113
-__global__ void tal_targets_kernel(TalArgs t) {
+// one thread per (b, a): tal.py:188-236 get_targets and the normalisation :108-113.  The [B][A][nc] score rows and [B][A][5] boxes of a
+// block's 256 consecutive anchors are contiguous: every thread computes its anchor's (label, normalised metric, box) into shared
+// memory and the block writes the rows with consecutive lanes on consecutive floats (the per-thread row writes — 20 floats 60 / 20
+// bytes apart across lanes — made this 36 us for 27 MB).
+__global__ void __launch_bounds__(256) tal_targets_kernel(TalArgs t) {
   pdl_prologue();
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (int64_t)t.B * t.A) return;
-  const int b = (int)(i / t.A), a = (int)(i % t.A);
-  const int j = (int)t.tgi[i];
-  const bool fg = t.fg[i] != 0;
-  const float* g = t.gts + ((int64_t)b * t.n + j) * 5;
+  __shared__ float s_norm[256];
+  __shared__ int s_label[256];
+  __shared__ float s_box[256 * 5];
+  const int64_t i0 = (int64_t)blockIdx.x * 256;
+  const int64_t i = i0 + threadIdx.x;
+  const int64_t total = (int64_t)t.B * t.A;
+  if (i < total) {
+    const int b = (int)(i / t.A), a = (int)(i % t.A);
+    const int j = (int)t.tgi[i];
+    const bool fg = t.fg[i] != 0;
+    const float* g = t.gts + ((int64_t)b * t.n + j) * 5;
 #pragma unroll
-  for (int k = 0; k < 5; ++k) t.t_boxes[i * 5 + k] = g[k];
-  int label = (int)t.labels[b * t.n + j];
-  label = label < 0 ? 0 : label;
-  float norm = 0.f;
-  if (fg) {
-    const int64_t e = ((int64_t)b * t.n + j) * t.A + a;
-    norm = t.align[e] * __uint_as_float(t.pos_over[b * t.n + j]) / (__uint_as_float(t.pos_align[b * t.n + j]) + t.eps);
+    for (int k = 0; k < 5; ++k) s_box[threadIdx.x * 5 + k] = g[k];
+    int label = (int)t.labels[b * t.n + j];
+    label = label < 0 ? 0 : label;
+    float norm = 0.f;
+    if (fg) {
+      const int64_t e = ((int64_t)b * t.n + j) * t.A + a;
+      norm = t.align[e] * __uint_as_float(t.pos_over[b * t.n + j]) / (__uint_as_float(t.pos_align[b * t.n + j]) + t.eps);
+    }
+    s_norm[threadIdx.x] = norm;
+    s_label[threadIdx.x] = fg ? label : -1;
   }
-  float* ts = t.t_scores + i * t.nc;
-  for (int c = 0; c < t.nc; ++c) ts[c] = (fg && c == label) ? norm : 0.f;
+  __syncthreads();
+  const int n = (int)(total - i0 < 256 ? total - i0 : 256);
+  for (int e = threadIdx.x; e < n * t.nc; e += 256) {
+    const int r = e / t.nc, c = e - r * t.nc;
+    t.t_scores[i0 * t.nc + e] = c == s_label[r] ? s_norm[r] : 0.f;
+  }
+  for (int e = threadIdx.x; e < n * 5; e += 256) t.t_boxes[i0 * 5 + e] = s_box[e];
 }
 
 }  // namespace quan
