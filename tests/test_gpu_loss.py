@@ -213,3 +213,19 @@ def test_assigner_vs_live_reference_giant_and_tiny_boxes():
     torch.testing.assert_close(ts, ts_r.float(), rtol=2e-4, atol=1e-7)
     torch.testing.assert_close(tb[fg], tb_r[fg_r.bool()], rtol=0, atol=0)
     assert int(fg.sum()) > 20
+
+
+def test_assigner_full_scan_path_in_subprocess():
+    """The assigner's top-k has two forms (compact candidate list / full-row scans; the second only when a box has more positive anchors
+    than the list holds).  QUAN_TAL_FULLSCAN=1 forces the full scans — the switch is read once per process, so the assigner tests run
+    again in a child process with it set."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("QUAN_TAL_FULLSCAN") == "1":
+        pytest.skip("already the child process")
+    env = dict(os.environ, QUAN_TAL_FULLSCAN="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", __file__, "-q", "-x", "-m", "gpu", "-k",
+                        "assigner_matches_reference_golden or giant_and_tiny or fused_loss_matches_reference_golden"],
+                       env=env, capture_output=True, text=True, timeout=600, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
