@@ -18,7 +18,7 @@
 
 namespace quan {
 
-constexpr int TAL_THREADS = 512;
+constexpr int TAL_THREADS = 256;
 
 struct RBox {
   float x, y, w, h, r;
